@@ -1,0 +1,191 @@
+"""TEST INFRASTRUCTURE ONLY.  Mints tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+
+    python oracle/make_golden.py
+
+Every fixture is computed by the reference's own functions in float64 on CPU
+(quaternion_conv / dual_quaternion_conv / quaternion_linear / QuaternionLinearFunction /
+dual_quaternion_linear / spectrum_fast / SELD_Model) with gradients from torch autograd.
+Inputs are stored as float32-representable values so that the CUDA path (fp32 storage) sees
+bit-identical inputs.  Seeds are recorded in each file's ``meta`` JSON.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_import  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def f32(a):
+    return np.asarray(a, np.float32).astype(np.float64)
+
+
+def _save(name, meta, d):
+    """Large arrays are stored as float32 (6e-8 relative: far below every parity tolerance);
+    small ones keep the reference's float64 so the oracle can be pinned to 1e-12."""
+    d = {k: (np.asarray(v, np.float32) if np.asarray(v).size > 20000 else np.asarray(v)) for k, v in d.items()}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), **d)
+
+
+def conv_case(ns, name, algebra, ndim, N, I, O, spatial, k, stride, padding, dilation, bias, seed):
+    rng = np.random.default_rng(seed)
+    nc = {"Q": 4, "DQ": 8}[algebra]
+    kshape = (k,) * ndim
+    ws = [f32(rng.standard_normal((O, I) + kshape) * 0.2) for _ in range(nc)]
+    x = f32(rng.standard_normal((N, nc * I) + tuple(spatial)))
+    b = f32(rng.standard_normal(nc * O)) if bias else None
+    tx = torch.tensor(x, requires_grad=True)
+    tw = [torch.tensor(w, requires_grad=True) for w in ws]
+    tb = torch.tensor(b, requires_grad=True) if bias else None
+    fn = ns.q_ops.quaternion_conv if algebra == "Q" else ns.dq_ops.dual_quaternion_conv
+    y = fn(tx, *tw, tb, stride, padding, 1, dilation)
+    gy = f32(rng.standard_normal(tuple(y.shape)))
+    y.backward(torch.tensor(gy))
+    d = dict(x=x, gy=gy, y=y.detach().numpy(), gx=tx.grad.numpy())
+    for i, (w, t) in enumerate(zip(ws, tw)):
+        d["w%d" % i] = w
+        d["gw%d" % i] = t.grad.numpy()
+    if bias:
+        d["b"] = b
+        d["gb"] = tb.grad.numpy()
+    meta = dict(kind="conv", algebra=algebra, ndim=ndim, stride=stride, padding=padding,
+                dilation=dilation, bias=bool(bias), seed=seed,
+                source="quaternion_ops.py:125-147" if algebra == "Q" else "dual_quaternion_ops.py:111-153")
+    _save(name, meta, d)
+    print(name, tuple(x.shape), "->", tuple(y.shape))
+
+
+def linear_case(ns, name, algebra, rows, I, O, bias, seed, use_function=False):
+    rng = np.random.default_rng(seed)
+    nc = {"Q": 4, "DQ": 8}[algebra]
+    ws = [f32(rng.standard_normal((I, O)) * 0.2) for _ in range(nc)]
+    x = f32(rng.standard_normal((rows, nc * I)))
+    b = f32(rng.standard_normal(nc * O)) if bias else None
+    tx = torch.tensor(x, requires_grad=True)
+    tw = [torch.tensor(w, requires_grad=True) for w in ws]
+    tb = torch.tensor(b, requires_grad=True) if bias else None
+    if algebra == "Q":
+        y = (ns.q_ops.QuaternionLinearFunction.apply(tx, *tw, tb) if use_function
+             else ns.q_ops.quaternion_linear(tx, *tw, tb))
+        src = "quaternion_ops.py:392-464" if use_function else "quaternion_ops.py:299-327"
+    else:
+        y = ns.dq_ops.dual_quaternion_linear(tx, *tw, tb)
+        src = "dual_quaternion_ops.py:156-203"
+    gy = f32(rng.standard_normal(tuple(y.shape)))
+    y.backward(torch.tensor(gy))
+    d = dict(x=x, gy=gy, y=y.detach().numpy(), gx=tx.grad.numpy())
+    for i, (w, t) in enumerate(zip(ws, tw)):
+        d["w%d" % i] = w
+        d["gw%d" % i] = t.grad.numpy()
+    if bias:
+        d["b"] = b
+        d["gb"] = tb.grad.numpy()
+    meta = dict(kind="linear", algebra=algebra, bias=bool(bias), seed=seed, source=src)
+    _save(name, meta, d)
+    print(name, tuple(x.shape), "->", tuple(y.shape))
+
+
+def stft_case(ns, name, C, n, nperseg, noverlap, phase, seed):
+    rng = np.random.default_rng(seed)
+    x = f32(0.1 * rng.standard_normal((C, n)))
+    out = ns.uf.spectrum_fast(x, nperseg=nperseg, noverlap=noverlap, output_phase=phase)
+    meta = dict(kind="stft", nperseg=nperseg, noverlap=noverlap, output_phase=phase, seed=seed,
+                source="utility_functions.py:129-155")
+    _save(name, meta, dict(x=x.astype(np.float32), out=out))
+    print(name, x.shape, "->", out.shape)
+
+
+def seld_loss(sed, doa, target, n_sed):
+    """train.py:186-204 with sed_loss_weight=1, doa_loss_weight=5 (train.py:785-786)."""
+    t_sed = torch.flatten(target[:, :, :n_sed], start_dim=1)
+    t_doa = torch.flatten(target[:, :, n_sed:], start_dim=1)
+    sed = torch.flatten(sed, start_dim=1)
+    doa = torch.flatten(doa, start_dim=1)
+    return torch.nn.BCELoss()(sed, t_sed) * 1.0 + torch.nn.MSELoss()(doa, t_doa) * 5.0
+
+
+def model_case(name, cfg, time_dim, B, seed):
+    """Whole-model forward + backward of model.SELD_Model (model.py:324-480), dropout off."""
+    m = ref_import.build_reference_model(cfg, time_dim=time_dim, spatial_dropout_rate=0,
+                                         dropout_perc=0, seed=seed)
+    m.train()
+    sd32 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.double()
+    rng = np.random.default_rng(seed + 100)
+    x = f32(rng.standard_normal((B, cfg["input_channels"], cfg["freq_dim"], time_dim)))
+    n_out = time_dim // 8
+    n_sed = 14 * 3
+    sed_t = (rng.random((B, n_out, n_sed)) < 0.05).astype(np.float64)
+    doa_t = (2 * rng.random((B, n_out, n_sed * 3)) - 1) * np.repeat(sed_t, 3, axis=-1)
+    target = f32(np.concatenate([sed_t, doa_t], axis=-1))
+    sed, doa = m(torch.tensor(x))
+    loss = seld_loss(sed, doa, torch.tensor(target), n_sed)
+    loss.backward()
+    d = dict(x=x.astype(np.float32), target=target.astype(np.float32),
+             sed=sed.detach().numpy(), doa=doa.detach().numpy(), loss=np.float64(loss.item()))
+    for k, v in sd32.items():
+        d["param/" + k] = v.numpy()
+    ngrad = 0
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            d["grad/" + k] = p.grad.numpy().astype(np.float32)
+            ngrad += 1
+    meta = dict(kind="model", cfg=cfg, time_dim=time_dim, B=B, seed=seed, model_name=m.model_name,
+                n_params=int(sum(p.numel() for p in m.parameters())), n_grads=ngrad,
+                source="model.py:324-480 + train.py:186-204")
+    _save(name, meta, d)
+    print(name, m.model_name, meta["n_params"], "params;", "loss", loss.item())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_import.load()
+    # per-op fixtures (SURVEY.md 8c suggested shapes, plus stride / bias / odd sizes)
+    conv_case(ns, "conv1d_q_k3_d5", "Q", 1, 2, 16, 16, (97,), 3, 1, 5, 5, True, 11)
+    conv_case(ns, "conv1d_dq_k3_d5", "DQ", 1, 2, 8, 8, (97,), 3, 1, 5, 5, True, 12)
+    conv_case(ns, "conv1d_dq_k1", "DQ", 1, 3, 6, 5, (50,), 1, 1, 0, 1, False, 13)
+    conv_case(ns, "conv1d_q_k3_s2", "Q", 1, 2, 3, 5, (41,), 3, 2, 1, 2, True, 14)
+    conv_case(ns, "conv2d_q_3x3", "Q", 2, 1, 4, 8, (9, 23), 3, 1, 1, 1, False, 15)
+    conv_case(ns, "conv2d_dq_3x3", "DQ", 2, 2, 2, 4, (9, 23), 3, 1, 1, 1, True, 16)
+    conv_case(ns, "conv2d_dq_first", "DQ", 2, 1, 1, 3, (16, 40), 3, 1, 1, 1, False, 17)
+    # tensor-core friendly shapes (channels per component a multiple of 8/16)
+    conv_case(ns, "conv1d_dq_c48_d3", "DQ", 1, 1, 48, 48, (168,), 3, 1, 3, 3, False, 18)
+    conv_case(ns, "conv1d_q_c32_d2", "Q", 1, 2, 32, 32, (150,), 3, 1, 2, 2, True, 19)
+    conv_case(ns, "conv2d_dq_c24", "DQ", 2, 1, 24, 24, (6, 140), 3, 1, 1, 1, False, 20)
+    conv_case(ns, "conv2d_q_c16", "Q", 2, 1, 16, 16, (5, 130), 3, 1, 1, 1, False, 21)
+    linear_case(ns, "linear_q", "Q", 7, 6, 5, True, 31)
+    linear_case(ns, "linear_q_fn", "Q", 9, 4, 8, True, 32, use_function=True)
+    linear_case(ns, "linear_dq", "DQ", 7, 6, 5, True, 33)
+    linear_case(ns, "linear_dq_c48", "DQ", 40, 48, 48, True, 34)
+    stft_case(ns, "stft_mag", 8, 6400, 512, 112, False, 41)
+    stft_case(ns, "stft_magphase", 8, 6400, 512, 112, True, 42)
+    stft_case(ns, "stft_magphase_default", 3, 5000, 512, 128, True, 43)
+    # whole-model fixtures
+    tiny = dict(ref_import.COMMON)
+    tiny.update(input_channels=8, freq_dim=128, domain="DQ", domain_classifier="DQ",
+                cnn_filters=[16, 16, 16], G=16, U=16, V=[16, 16], fc_layers=[16],
+                parallel_ConvTC_block="False", parallel_magphase=False, extra_name="_tiny")
+    model_case("model_dq_tiny", tiny, 64, 2, 1)
+    tq = dict(tiny)
+    tq.update(domain="Q", domain_classifier="Q", extra_name="_tinyq")
+    model_case("model_q_tiny", tq, 64, 2, 2)
+    mid = dict(tiny)
+    mid.update(freq_dim=256, cnn_filters=[64, 64, 64], G=128, U=128, V=[128, 128], fc_layers=[128],
+               extra_name="_mid")
+    model_case("model_dq_mid", mid, 160, 2, 3)
+    two = dict(tiny)
+    two.update(input_channels=16, domain_classifier="R", parallel_ConvTC_block="2Parallel",
+               parallel_magphase=True, extra_name="_two")
+    model_case("model_dq_2branch_tiny", two, 64, 2, 4)
+
+
+if __name__ == "__main__":
+    main()
