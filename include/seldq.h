@@ -1,0 +1,160 @@
+/*
+ * seldq.h -- C ABI of libseldq.so: the B200 (sm_100a) implementation of the quaternion /
+ * dual-quaternion convolution + linear stack and the STFT magnitude/phase front end of
+ * AuroraEchos/Sound-Event-Localization-and-Detection.
+ *
+ * Each entry point replaces one call site of the reference (file:line relative to the
+ * reference tree):
+ *   seldq_conv_fwd / _dgrad / _wgrad   quaternion/quaternion_ops.py:125-147 (quaternion_conv)
+ *                                      dual_quaternion/dual_quaternion_ops.py:111-153 (dual_quaternion_conv)
+ *                                      and the autograd of F.conv1d/F.conv2d + torch.cat behind them
+ *   seldq_linear_fwd / _dgrad / _wgrad quaternion_ops.py:299-327 (quaternion_linear),
+ *                                      :392-464 (QuaternionLinearFunction),
+ *                                      dual_quaternion_ops.py:156-203 (dual_quaternion_linear)
+ *   seldq_stft_magphase                utility_functions.py:129-155 (spectrum_fast)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *     the caller (PyTorch) owns all buffers including workspaces and outputs; the library
+ *     never allocates or frees device memory and keeps no reference after returning.
+ *   - tensors are contiguous, channels-first (NCW / NCHW), float32, exactly as the reference
+ *     hands them to F.conv*; compact weights are the reference's Parameters:
+ *     conv (Cout/nc, Cin/nc, k...) and linear (in/nc, out/nc), nc = 1 | 4 | 8.
+ *   - weight pointer arrays are HOST arrays of nc device pointers in the reference's order
+ *     r, i, j, k [, r_2, i_2, j_2, k_2].
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, nothing in the
+ *     library synchronises the device.
+ *   - return 0 on success, a negative seldq_status_t otherwise; seldq_last_error() returns a
+ *     thread-local message.  The library is re-entrant (no mutable globals besides that string
+ *     and a host-side cache of immutable driver entry points).
+ *   - there is no CPU fallback: with no CUDA device every compute call returns SELDQ_ERR_CUDA.
+ */
+#ifndef SELDQ_H_
+#define SELDQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SELDQ_ABI_VERSION 1
+
+typedef enum {
+  SELDQ_OK = 0,
+  SELDQ_ERR_INVALID = -1,     /* bad descriptor / null pointer / shape mismatch           */
+  SELDQ_ERR_UNSUPPORTED = -2, /* valid request the chosen precision path cannot serve    */
+  SELDQ_ERR_WORKSPACE = -3,   /* workspace smaller than seldq_*_workspace_bytes()        */
+  SELDQ_ERR_CUDA = -4         /* CUDA runtime / driver error (message has the details)   */
+} seldq_status_t;
+
+/* which block structure expands the compact weights (Hamilton tables) */
+typedef enum {
+  SELDQ_ALG_REAL = 0,      /* nc = 1, plain convolution / linear                              */
+  SELDQ_ALG_Q = 1,         /* nc = 4, Wq[a*O+o, b*I+i] = sign[a][b] * W_{a^b}[o,i]            */
+  SELDQ_ALG_DQ = 2         /* nc = 8, [[Q(w),0],[Q(w2),Q(w)]]; linear uses the transposed form */
+} seldq_algebra_t;
+
+/* arithmetic the contraction runs in */
+typedef enum {
+  SELDQ_PREC_FP32 = 0,     /* FFMA, fp32 operands and accumulation (parity gate: rel 1e-4)    */
+  SELDQ_PREC_BF16 = 1      /* tcgen05 kind::f16 MMA, bf16 operands, fp32 accumulation in TMEM */
+} seldq_precision_t;
+
+typedef enum { SELDQ_PASS_FWD = 0, SELDQ_PASS_DGRAD = 1, SELDQ_PASS_WGRAD = 2 } seldq_pass_t;
+
+typedef struct {
+  int32_t algebra;     /* seldq_algebra_t                                            */
+  int32_t precision;   /* seldq_precision_t                                          */
+  int32_t ndim;        /* 1 (NCW, in_h = k_h = 1) or 2 (NCHW)                        */
+  int32_t batch;
+  int32_t cin, cout;   /* expanded channel counts, multiples of nc                   */
+  int32_t in_h, in_w;
+  int32_t k_h, k_w;
+  int32_t stride_h, stride_w;
+  int32_t pad_h, pad_w;
+  int32_t dil_h, dil_w;
+} seldq_conv_desc_t;
+
+typedef struct {
+  int32_t algebra;     /* SELDQ_ALG_Q -> quaternion_linear table, SELDQ_ALG_DQ -> dual_quaternion_linear */
+  int32_t precision;
+  int32_t rows;        /* flattened leading dims (T*N)                               */
+  int32_t in_features, out_features;   /* expanded                                    */
+} seldq_linear_desc_t;
+
+int seldq_abi_version(void);
+const char* seldq_last_error(void);
+/* number of visible CUDA devices (0 on a CPU-only host); never fails */
+int seldq_device_count(void);
+
+/* ---- convolution (A1, A2 in SURVEY.md 8a) ------------------------------------------------ */
+int seldq_conv_out_shape(const seldq_conv_desc_t* d, int32_t* out_h, int32_t* out_w);
+size_t seldq_conv_workspace_bytes(const seldq_conv_desc_t* d, int32_t pass);
+
+/* y = conv(x, expand(w)) + bias.  x_bf16 / y_bf16 are optional (may be NULL):
+ *   x_bf16  a bf16 copy of x made earlier by seldq_cast_bf16 (BF16 path only; if NULL the
+ *           library casts x into the workspace first)
+ *   y_bf16  if non-NULL the epilogue also stores a bf16 copy of y for the next layer      */
+int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_bf16,
+                   const float* const* host_w, const float* bias, float* y, void* y_bf16,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* gx = conv_transpose(gy, expand(w)) : gradient w.r.t. the input */
+int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy_bf16,
+                     const float* const* host_w, float* gx,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* compact weight gradients (nc tensors, OVERWRITTEN) and, if gbias != NULL, gbias = sum gy */
+int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_bf16,
+                     const float* gy, const void* gy_bf16, float* const* host_gw, float* gbias,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- linear (A3, A4) ------------------------------------------------------------------- */
+size_t seldq_linear_workspace_bytes(const seldq_linear_desc_t* d, int32_t pass);
+int seldq_linear_fwd(const seldq_linear_desc_t* d, const float* x, const float* const* host_w,
+                     const float* bias, float* y, void* workspace, size_t workspace_bytes, void* stream);
+int seldq_linear_dgrad(const seldq_linear_desc_t* d, const float* gy, const float* const* host_w,
+                       float* gx, void* workspace, size_t workspace_bytes, void* stream);
+int seldq_linear_wgrad(const seldq_linear_desc_t* d, const float* x, const float* gy,
+                       float* const* host_gw, float* gbias,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- helpers ------------------------------------------------------------------------------ */
+/* dst_bf16[i] = bf16(src[i]) (round to nearest even) */
+int seldq_cast_bf16(const float* src, void* dst_bf16, size_t n, void* stream);
+/* "bf16 mirror" of an NCHW/NCW fp32 tensor, the layout every *_bf16 argument uses: same order of
+ * dimensions, row pitch seldq_bf16_pitch(w) = w rounded up to 8 elements (TMA needs 16-byte row
+ * strides), pad columns zero.  rows = n*c*h. */
+int seldq_bf16_pitch(int32_t w);
+int seldq_cast_bf16_mirror(const float* src, void* dst_bf16, int64_t rows, int32_t w, void* stream);
+
+/* ---- STFT front end (F1) ----------------------------------------------------------------- */
+/* x: (n_signals, n_samples) float32.  out: (n_batch, (1+output_phase)*n_ch, n_bins, n_frames)
+ * with n_signals = n_batch*n_ch, magnitude of channel c at plane c and phase at plane n_ch+c
+ * (the reference's np.concatenate on axis -3).  Periodic Hamming window, zero boundary
+ * extension of nperseg/2, zero tail padding to a whole hop, scaling 1/sum(w); bin 0 dropped if
+ * cut_dc, last frame dropped if cut_last.  nperseg must be 512. */
+int seldq_stft_shape(int64_t n_samples, int32_t nperseg, int32_t noverlap, int32_t cut_dc,
+                     int32_t cut_last, int32_t* n_bins, int32_t* n_frames);
+int seldq_stft_magphase(const float* x, int32_t n_batch, int32_t n_ch, int64_t n_samples,
+                        int32_t nperseg, int32_t noverlap, int32_t cut_dc, int32_t output_phase,
+                        int32_t cut_last, float* out, void* stream);
+
+/* ---- debug / bring-up probes (tools/umma_probe.py); not part of the reference surface ---- */
+int seldq_probe_tensor_map(void* host_map_128B, const void* gaddr, int32_t elem_bytes, int32_t rank,
+                           const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                           int32_t swizzle);
+int seldq_probe_tma_load(const void* host_map_128B, int32_t rank, const int32_t* coords,
+                         uint32_t box_bytes, uint32_t smem_offset, void* out_smem_dump,
+                         uint32_t dump_bytes, void* stream);
+int seldq_probe_umma(const void* a_image, uint32_t a_bytes, const void* b_image, uint32_t b_bytes,
+                     uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int32_t n_mma,
+                     uint32_t a_desc_step, uint32_t b_desc_step, int32_t n_cols,
+                     float* out_128xN, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELDQ_H_ */

@@ -1,0 +1,118 @@
+"""ctypes binding of libseldq.so (C ABI: include/seldq.h).  No torch types cross this boundary:
+only raw device pointers, sizes and a cudaStream_t.
+
+The library is built in-tree by csrc/build.sh (nvcc, sm_100a).  There is no CPU fallback: if
+the shared object is missing this module raises, and compute calls on a host without a CUDA
+device return SELDQ_ERR_CUDA which `check` turns into RuntimeError.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libseldq.so")
+BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
+
+ALG_REAL, ALG_Q, ALG_DQ = 0, 1, 2
+PREC_FP32, PREC_BF16 = 0, 1
+PASS_FWD, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
+ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = -1, -2, -3, -4
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "algebra", "precision", "ndim", "batch", "cin", "cout", "in_h", "in_w", "k_h", "k_w",
+        "stride_h", "stride_w", "pad_h", "pad_w", "dil_h", "dil_w")]
+
+
+class LinearDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("algebra", "precision", "rows", "in_features", "out_features")]
+
+
+def build(force=False):
+    """Compile libseldq.so in-tree (cross-compiles without a GPU)."""
+    srcs = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))
+            if f.endswith((".cu", ".cuh", ".h", ".sh"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "seldq.h"))
+    if not force and os.path.exists(LIB_PATH) and all(
+            os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs):
+        return LIB_PATH
+    subprocess.check_call(["bash", BUILD_SCRIPT, LIB_PATH])
+    return LIB_PATH
+
+
+_P = ctypes.c_void_p
+_PROTOS = {
+    "seldq_abi_version": (ctypes.c_int, []),
+    "seldq_last_error": (ctypes.c_char_p, []),
+    "seldq_device_count": (ctypes.c_int, []),
+    "seldq_conv_out_shape": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_int32),
+                                            ctypes.POINTER(ctypes.c_int32)]),
+    "seldq_conv_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc), ctypes.c_int32]),
+    "seldq_conv_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P, _P,
+                                      ctypes.c_size_t, _P]),
+    "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P,
+                                        ctypes.c_size_t, _P]),
+    "seldq_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.POINTER(_P), _P, _P,
+                                        ctypes.c_size_t, _P]),
+    "seldq_linear_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(LinearDesc), ctypes.c_int32]),
+    "seldq_linear_fwd": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, ctypes.POINTER(_P), _P, _P, _P,
+                                        ctypes.c_size_t, _P]),
+    "seldq_linear_dgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, ctypes.POINTER(_P), _P, _P,
+                                          ctypes.c_size_t, _P]),
+    "seldq_linear_wgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, _P, ctypes.POINTER(_P), _P, _P,
+                                          ctypes.c_size_t, _P]),
+    "seldq_cast_bf16": (ctypes.c_int, [_P, _P, ctypes.c_size_t, _P]),
+    "seldq_bf16_pitch": (ctypes.c_int, [ctypes.c_int32]),
+    "seldq_cast_bf16_mirror": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P]),
+    "seldq_stft_shape": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                        ctypes.POINTER(ctypes.c_int32)]),
+    "seldq_stft_magphase": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P]),
+    "seldq_probe_tensor_map": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
+                                              ctypes.POINTER(ctypes.c_uint32), ctypes.c_int32]),
+    "seldq_probe_tma_load": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_uint32,
+                                            ctypes.c_uint32, _P, ctypes.c_uint32, _P]),
+    "seldq_probe_umma": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_uint32, ctypes.c_uint64,
+                                        ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32, ctypes.c_uint32,
+                                        ctypes.c_uint32, ctypes.c_int32, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libseldq.so is missing (%s). Build it with __graft_entry__.build() or csrc/build.sh; "
+                "this package has no CPU or PyTorch fallback." % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_PROTOS)
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = lib().seldq_last_error().decode("utf-8", "replace")
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError("seldq: " + msg)
+    if rc == ERR_INVALID:
+        raise RuntimeError("seldq: " + msg)
+    raise RuntimeError("seldq (status %d): %s" % (rc, msg))
+
+
+def ptr_array(ptrs):
+    return (_P * len(ptrs))(*ptrs)

@@ -1,0 +1,71 @@
+// Parameter blocks and host entry points of the tcgen05 kernels (conv_umma.cu, wgrad_umma.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace seldq {
+namespace umma {
+
+constexpr int kTileM = 128;     // positions per accumulator tile (TMEM lanes)
+constexpr int kThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kMaxTaps = 9;
+constexpr int kMaxStages = 8;
+constexpr int kMaxAtoms = 96;   // 8-channel K atoms in one component's K sequence
+
+struct FpropParams {
+  ConvGeom g;                   // pass orientation (transposed = 1 for dgrad)
+  const float* w[8];            // compact fp32 weights (device)
+  const float* bias;
+  float* out;
+  __nv_bfloat16* out_bf16;      // optional bf16 mirror of out (row pitch o16_sH)
+  long long out_sN, out_sC, out_sH;
+  long long o16_sN, o16_sC, o16_sH;
+  int N, OH, OW, P;
+  int tiles_w, total_tiles;
+  int dense;                    // 1: signed expanded tile in smem, one MMA spans all out channels
+  int ncomp_in, ncomp_out;
+  int Rc;                       // in channels per component  = TMA box rows
+  int Pc;                       // out channels per component
+  int NBp;                      // Pc rounded up to 16        = MMA N and TMEM column stride
+  int n_img;                    // resident weight images (compact tensors)
+  int ntaps, G, stages_per_comp, atoms_per_tap, stage_atoms, kpairs;
+  int nstages, acc_stages, tmem_cols;
+  int off_h[kMaxTaps], off_w[kMaxTaps];
+  int nops[8];
+  int8_t op_img[8][8], op_neg[8][8], op_out[8][8];
+  int8_t atom_tap[kMaxAtoms], atom_chan[kMaxAtoms];
+};
+
+// wgrad: D[(a,o), (tap,b,i)] = sum_t G[(a,o), t] * X[(b,i), t + off(tap)]   (both operands K-major)
+constexpr int kWgradStages = 4;
+struct WgradParams {
+  ConvGeom g;                   // forward orientation
+  float* gw[8];                 // compact fp32 gradients (device), accumulated with atomicAdd
+  int dense;                    // rows / cols are plain expanded channels (first layer)
+  int ncomp;                    // component groups on each side (dense: 1)
+  int OS, IS;                   // rows / cols per component group  (M = ncomp*OS <= 128, NW = ncomp*IS)
+  int NW;                       // columns per tap
+  int o_tiles, i_tiles, tap_groups, taps_per_group;
+  int ntaps;
+  int off_h[kMaxTaps], off_w[kMaxTaps];
+  int OH, OW, N;
+  int chunks_w;                 // ceil(OW / 64)
+  long long ksteps;             // N * OH * chunks_w
+  int splits;
+  int nstages;
+  int tmem_cols;
+  int m_rows;                   // 64 or 128
+};
+
+int num_sms();
+
+}  // namespace umma
+
+int launch_umma_fprop(const ConvGeom& g, const void* in_bf16, int in_pitch_w, const float* const* host_w,
+                      const float* bias, float* out, void* out_bf16, int out16_pitch_w, cudaStream_t st);
+int launch_umma_wgrad(const ConvGeom& g, const void* x_bf16, int x_pitch_w, const void* gy_bf16, int gy_pitch_w,
+                      float* const* host_gw, cudaStream_t st);
+
+}  // namespace seldq

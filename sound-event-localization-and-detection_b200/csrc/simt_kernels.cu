@@ -1,0 +1,161 @@
+// __global__ wrappers of the FP32 SIMT kernels (phase functions in conv_simt.cuh) plus the small
+// bandwidth-bound helpers (bias gradient, fp32 -> bf16 cast).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "conv_simt.cuh"
+#include "launch.h"
+
+namespace seldq {
+namespace simt {
+
+__global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ ConvParams p) {
+  __shared__ ConvShared s;
+  ConvThread t;
+  conv_init(t);
+  const int ntap = p.g.KH * p.g.KW;
+  for (int tap = 0; tap < ntap; ++tap)
+    for (int r0 = 0; r0 < p.g.R; r0 += BK) {
+      if (conv_chunk_is_zero(p.g, blockIdx.y * BM, r0)) continue;  // block-uniform
+      conv_load(p, s, threadIdx.x, blockIdx.x, blockIdx.y, blockIdx.z, tap, r0);
+      __syncthreads();
+      conv_mac(s, t, threadIdx.x);
+      __syncthreads();
+    }
+  conv_store(p, t, threadIdx.x, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+__global__ void __launch_bounds__(NT) wgrad_simt_kernel(const __grid_constant__ WgradParams p) {
+  __shared__ WgradShared s;
+  WgradThread t;
+  wgrad_init(t);
+  const int ntap = p.g.KH * p.g.KW;
+  const long long units = wgrad_units(p.g, blockIdx.y / ntap);
+  const long long per = (units + p.splits - 1) / p.splits;
+  const long long u0 = blockIdx.z * per;
+  const long long u1 = u0 + per < units ? u0 + per : units;
+  for (long long u = u0; u < u1; ++u) {
+    wgrad_load(p, s, threadIdx.x, blockIdx.x, blockIdx.y, u);
+    __syncthreads();
+    wgrad_mac(s, t, threadIdx.x);
+    __syncthreads();
+  }
+  if (u0 < u1) wgrad_store(p, t, threadIdx.x, blockIdx.x, blockIdx.y, [](float* a, float v) { atomicAdd(a, v); });
+}
+
+// gb[c] = sum over (n, h, w) of gy[n, c, h, w]; one block per channel, warp-shuffle reduction
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ gy, float* __restrict__ gb, int N,
+                                                        int H, int W, long long sN, long long sC, long long sH,
+                                                        long long sW) {
+  const int c = blockIdx.x;
+  const long long total = (long long)N * H * W;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int w = (int)(i % W);
+    const long long r = i / W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    acc += gy[n * sN + c * sC + h * sH + w * sW];
+  }
+  __shared__ float part[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) gb[c] = v;
+  }
+}
+
+// fp32 -> bf16 (round to nearest even), 8 elements per thread per step
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                        size_t n) {
+  const size_t nvec = n / 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    __nv_bfloat162 o[4];
+    o[0] = __floats2bfloat162_rn(a.x, a.y);
+    o[1] = __floats2bfloat162_rn(a.z, a.w);
+    o[2] = __floats2bfloat162_rn(b.x, b.y);
+    o[3] = __floats2bfloat162_rn(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(o);
+  }
+  for (size_t i = nvec * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// fp32 (rows, w) -> bf16 (rows, pitch) with zeroed pad columns (rows whose length is not a multiple of 8)
+__global__ void __launch_bounds__(256) cast_bf16_rows_kernel(const float* __restrict__ src,
+                                                             __nv_bfloat16* __restrict__ dst, long long rows, int w,
+                                                             int pitch) {
+  const long long total = rows * pitch;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / pitch;
+    const int c = (int)(i - r * pitch);
+    dst[i] = __float2bfloat16_rn(c < w ? src[r * w + c] : 0.f);
+  }
+}
+
+}  // namespace simt
+
+// ---- host launchers ------------------------------------------------------------------------------
+int launch_conv_simt(const simt::ConvParams& p, cudaStream_t st) {
+  const ConvGeom& g = p.g;
+  dim3 grid((g.OW + simt::BN - 1) / simt::BN, (g.P + simt::BM - 1) / simt::BM, (unsigned)(g.N * g.OH));
+  if (grid.y > 65535 || grid.z > 65535) return fail(SELDQ_ERR_UNSUPPORTED, "problem too large for the fp32 grid");
+  simt::conv_simt_kernel<<<grid, simt::NT, 0, st>>>(p);
+  return check_launch("conv_simt_kernel");
+}
+
+int launch_wgrad_simt(simt::WgradParams& p, cudaStream_t st) {
+  const ConvGeom& g = p.g;
+  const int ntile = ((g.Oc + simt::WT - 1) / simt::WT) * ((g.Ic + simt::WT - 1) / simt::WT);
+  const int ny = g.tab.nw * g.KH * g.KW;
+  // enough splits to cover the chip about four times, never more than the shortest reduction
+  long long min_units = simt::wgrad_units(g, 0);
+  for (int e = 1; e < g.tab.nw; ++e) {
+    const long long u = simt::wgrad_units(g, e);
+    if (u < min_units) min_units = u;
+  }
+  long long splits = (4LL * 148 + (long long)ntile * ny - 1) / ((long long)ntile * ny);
+  if (splits > min_units) splits = min_units;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  p.splits = (int)splits;
+  dim3 grid(ntile, ny, (unsigned)splits);
+  simt::wgrad_simt_kernel<<<grid, simt::NT, 0, st>>>(p);
+  return check_launch("wgrad_simt_kernel");
+}
+
+int launch_bias_grad(const float* gy, float* gb, int C, int N, int H, int W, long long sN, long long sC, long long sH,
+                     long long sW, cudaStream_t st) {
+  simt::bias_grad_kernel<<<C, 256, 0, st>>>(gy, gb, N, H, W, sN, sC, sH, sW);
+  return check_launch("bias_grad_kernel");
+}
+
+int launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return SELDQ_OK;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+    return fail(SELDQ_ERR_INVALID, "seldq_cast_bf16 needs 16-byte aligned buffers");
+  size_t blocks = (n / 8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  simt::cast_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  return check_launch("cast_bf16_kernel");
+}
+
+int launch_cast_bf16_rows(const float* src, void* dst, long long rows, int w, int pitch, cudaStream_t st) {
+  long long blocks = (rows * pitch + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  simt::cast_bf16_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), rows, w,
+                                                               pitch);
+  return check_launch("cast_bf16_rows_kernel");
+}
+
+}  // namespace seldq

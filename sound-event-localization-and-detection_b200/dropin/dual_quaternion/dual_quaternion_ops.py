@@ -1,0 +1,101 @@
+"""Drop-in for the reference's dual_quaternion/dual_quaternion_ops.py: same public names and
+positional signatures, computed by libseldq.so (sm_100a)."""
+import os as _os
+import sys as _sys
+
+_sys.path.append(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from _seldq_pkg import pkg as _pkg  # noqa: E402
+
+_F = _pkg.functional
+_I = _pkg.init
+_ALG_DQ = _pkg._lib.ALG_DQ
+
+
+def check_input(input):
+    # dual_quaternion_ops.py:14-31
+    if input.dim() not in {2, 3, 4, 5}:
+        raise RuntimeError("Quaternion linear accepts only input of dimension 2 or 3. Quaternion conv accepts "
+                           "up to 5 dim  input.dim = " + str(input.dim()))
+    nb_hidden = input.size()[-1] if input.dim() < 4 else input.size()[1]
+    if nb_hidden % 4 != 0:
+        raise RuntimeError("Quaternion Tensors must be divisible by 4."
+                           " input.size()[1] = " + str(nb_hidden))
+
+
+def _component(input, idx):
+    check_input(input)
+    axis = input.dim() - 1 if input.dim() < 4 else 1
+    n = input.size()[axis] // 4
+    return input.narrow(axis, idx * n, n)
+
+
+def get_r(input):
+    return _component(input, 0)
+
+
+def get_i(input):
+    return _component(input, 1)
+
+
+def get_j(input):
+    return _component(input, 2)
+
+
+def get_k(input):
+    return _component(input, 3)
+
+
+def dual_quaternion_conv(input, r_weight, i_weight, j_weight, k_weight,
+                         r_weight_2, i_weight_2, j_weight_2, k_weight_2, bias, stride,
+                         padding, groups, dilatation):
+    """dual_quaternion_ops.py:111-153 -- | q 0 ; q_e q | block structure fused into the kernels;
+    the zero block is never multiplied."""
+    if groups != 1:
+        raise NotImplementedError("seldq: groups != 1 is not implemented")
+    ws = (r_weight, i_weight, j_weight, k_weight, r_weight_2, i_weight_2, j_weight_2, k_weight_2)
+    return _F.block_conv(input, ws, bias, stride, padding, dilatation, _ALG_DQ)
+
+
+def dual_quaternion_linear(input, r_weight, i_weight, j_weight, k_weight,
+                           r_weight_2, i_weight_2, j_weight_2, k_weight_2, bias=True):
+    """dual_quaternion_ops.py:156-203 (transposed block table)."""
+    if bias is True:
+        bias = None
+    ws = (r_weight, i_weight, j_weight, k_weight, r_weight_2, i_weight_2, j_weight_2, k_weight_2)
+    return _F.block_linear(input, ws, bias, _ALG_DQ)
+
+
+def _out_of_scope(name):
+    def fn(*args, **kwargs):
+        raise NotImplementedError("seldq: %s is unused by the SELD models and is not implemented "
+                                  "(SURVEY.md section 2, row 3)" % name)
+    fn.__name__ = name
+    return fn
+
+
+q_normalize = _out_of_scope("q_normalize")
+quaternion_exp = _out_of_scope("quaternion_exp")
+hamilton_product = _out_of_scope("hamilton_product")
+quaternion_init = _I.dual_quaternion_init
+get_kernel_and_weight_shape = _I.get_kernel_and_weight_shape
+
+
+def unitary_init(in_features, out_features, rng, kernel_size=None, criterion='he'):
+    return _I.unitary_init(in_features, out_features, rng, kernel_size, criterion, dual=True)
+
+
+def random_init(in_features, out_features, rng, kernel_size=None, criterion='glorot'):
+    return _I.random_init(in_features, out_features, rng, kernel_size, criterion, dual=True)
+
+
+def affect_init(r_weight, i_weight, j_weight, k_weight, r_weight_2, i_weight_2, j_weight_2, k_weight_2,
+                init_func, rng, init_criterion):
+    _I.affect_init((r_weight, i_weight, j_weight, k_weight), init_func, rng, init_criterion,
+                   ws2=(r_weight_2, i_weight_2, j_weight_2, k_weight_2))
+
+
+def affect_init_conv(r_weight, i_weight, j_weight, k_weight, kernel_size, init_func, rng, init_criterion,
+                     r_weight_2=None, i_weight_2=None, j_weight_2=None, k_weight_2=None):
+    ws2 = None if r_weight_2 is None else (r_weight_2, i_weight_2, j_weight_2, k_weight_2)
+    _I.affect_init_conv((r_weight, i_weight, j_weight, k_weight), kernel_size, init_func, rng, init_criterion,
+                        ws2=ws2)

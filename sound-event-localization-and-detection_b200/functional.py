@@ -1,0 +1,271 @@
+"""Differentiable ops over the C ABI (libseldq.so): quaternion / dual-quaternion convolution and
+linear, and the STFT magnitude/phase front end.  This is the host-side mirror of the reference's
+functional layer (quaternion/quaternion_ops.py, dual_quaternion/dual_quaternion_ops.py): the
+public names with the reference's exact signatures live in the drop-in modules next to this file;
+they all funnel into the autograd Functions below.
+
+PyTorch supplies device memory, the current stream and autograd plumbing; every FLOP of the ops
+themselves runs in the hand-written sm_100a kernels.  There is no CPU path: CPU tensors raise.
+"""
+import contextlib
+import os
+
+import torch
+
+from . import _lib
+from ._lib import ALG_DQ, ALG_Q, ALG_REAL, PASS_DGRAD, PASS_FWD, PASS_WGRAD, PREC_BF16, PREC_FP32
+
+_PRECISION = {"fp32": PREC_FP32, "bf16": PREC_BF16}[os.environ.get("SELDQ_PRECISION", "bf16").lower()]
+_NCOMP = {ALG_REAL: 1, ALG_Q: 4, ALG_DQ: 8}
+
+
+def set_precision(name):
+    """'fp32': FFMA kernels, parity gate rel 1e-4.  'bf16': tcgen05 tensor-core kernels (bf16
+    operands, fp32 accumulation), parity gate rel 2e-2.  Returns the previous setting."""
+    global _PRECISION
+    prev = get_precision()
+    _PRECISION = {"fp32": PREC_FP32, "bf16": PREC_BF16}[name]
+    return prev
+
+
+def get_precision():
+    return "fp32" if _PRECISION == PREC_FP32 else "bf16"
+
+
+@contextlib.contextmanager
+def precision(name):
+    prev = set_precision(name)
+    try:
+        yield
+    finally:
+        set_precision(prev)
+
+
+def _require_cuda_f32(t, what):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a tensor" % what)
+    if not t.is_cuda:
+        raise RuntimeError("seldq: %s is on %s; the sm_100a kernels have no CPU fallback" % (what, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("seldq: %s must be float32 (got %s)" % (what, t.dtype))
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _pair(v):
+    if isinstance(v, (tuple, list)):
+        if len(v) == 1:
+            return int(v[0]), int(v[0])
+        return int(v[0]), int(v[1])
+    return int(v), int(v)
+
+
+def bf16_mirror(x):
+    """bf16 copy of an NCW / NCHW fp32 tensor in the layout the tensor-core kernels read through
+    TMA: same dimension order, row pitch rounded up to 8 elements (see include/seldq.h)."""
+    _require_cuda_f32(x, "input")
+    x = x.contiguous()
+    w = x.shape[-1]
+    pitch = _lib.lib().seldq_bf16_pitch(w)
+    out = torch.empty(x.shape[:-1] + (pitch,), dtype=torch.bfloat16, device=x.device)
+    rows = x.numel() // w
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().seldq_cast_bf16_mirror(x.data_ptr(), out.data_ptr(), rows, w, _stream()))
+    return out
+
+
+def _conv_desc(algebra, prec, x_shape, cout, ksize, stride, padding, dilation):
+    if len(x_shape) == 3:
+        n, c, w = x_shape
+        return _lib.ConvDesc(algebra, prec, 1, n, c, cout, 1, w, 1, ksize[-1], 1, stride[-1], 0, padding[-1], 1,
+                             dilation[-1])
+    n, c, h, w = x_shape
+    return _lib.ConvDesc(algebra, prec, 2, n, c, cout, h, w, ksize[0], ksize[1], stride[0], stride[1],
+                         padding[0], padding[1], dilation[0], dilation[1])
+
+
+class _BlockConv(torch.autograd.Function):
+    """y = conv(x, expand(weights)) + bias  with the expansion fused into the kernels
+    (reference: quaternion_ops.py:125-147, dual_quaternion_ops.py:111-153)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, stride, padding, dilation, algebra, prec, *weights):
+        L = _lib.lib()
+        nc = _NCOMP[algebra]
+        _require_cuda_f32(x, "input")
+        for w in weights:
+            _require_cuda_f32(w, "weight")
+        if bias is not None:
+            _require_cuda_f32(bias, "bias")
+        x = x.contiguous()
+        weights = tuple(w.contiguous() for w in weights)
+        w0 = weights[0]
+        if x.dim() == 3:
+            stride, padding, dilation = (1, _pair(stride)[1]), (0, _pair(padding)[1]), (1, _pair(dilation)[1])
+        else:
+            stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)
+        ksize = tuple(w0.shape[2:])
+        cout = w0.shape[0] * nc
+        if w0.shape[1] * nc != x.shape[1]:
+            raise RuntimeError("Given groups=1, weight of size %s (x%d components), expected input%s to have %d "
+                               "channels, but got %d channels instead"
+                               % (list(w0.shape), nc, list(x.shape), w0.shape[1] * nc, x.shape[1]))
+        desc = _conv_desc(algebra, prec, tuple(x.shape), cout, ksize, stride, padding, dilation)
+        import ctypes
+        oh, ow = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(L.seldq_conv_out_shape(ctypes.byref(desc), ctypes.byref(oh), ctypes.byref(ow)))
+        out_shape = (x.shape[0], cout, ow.value) if x.dim() == 3 else (x.shape[0], cout, oh.value, ow.value)
+        y = torch.empty(out_shape, dtype=torch.float32, device=x.device)
+        wp = _lib.ptr_array([w.data_ptr() for w in weights])
+        with torch.cuda.device(x.device):
+            x16 = bf16_mirror(x) if prec == PREC_BF16 else None
+            _lib.check(L.seldq_conv_fwd(ctypes.byref(desc), x.data_ptr(), _ptr(x16), wp, _ptr(bias), y.data_ptr(),
+                                        None, None, 0, _stream()))
+        ctx.desc = desc
+        ctx.has_bias = bias is not None
+        # the tensor-core wgrad reads the bf16 mirror only: keep that instead of the fp32 input
+        ctx.save_for_backward(x16 if prec == PREC_BF16 else x, *weights)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        import ctypes
+        L = _lib.lib()
+        desc = ctx.desc
+        xs, *weights = ctx.saved_tensors
+        bf16 = desc.precision == PREC_BF16
+        gy = gy.contiguous()
+        if gy.dtype != torch.float32:
+            raise TypeError("seldq: grad_output must be float32")
+        dev = gy.device
+        need_x = ctx.needs_input_grad[0]
+        need_w = any(ctx.needs_input_grad[7:])
+        need_b = ctx.has_bias and ctx.needs_input_grad[1]
+        gx = gb = None
+        gws = [None] * len(weights)
+        wp = _lib.ptr_array([w.data_ptr() for w in weights])
+        with torch.cuda.device(dev):
+            gy16 = bf16_mirror(gy) if bf16 and (need_x or need_w) else None
+            if need_x:
+                if desc.ndim == 1:
+                    gx = torch.empty((desc.batch, desc.cin, desc.in_w), dtype=torch.float32, device=dev)
+                else:
+                    gx = torch.empty((desc.batch, desc.cin, desc.in_h, desc.in_w), dtype=torch.float32, device=dev)
+                _lib.check(L.seldq_conv_dgrad(ctypes.byref(desc), gy.data_ptr(), _ptr(gy16), wp, gx.data_ptr(),
+                                              None, 0, _stream()))
+            if need_w or need_b:
+                gws = [torch.empty_like(w) for w in weights]
+                gb = torch.empty(desc.cout, dtype=torch.float32, device=dev) if need_b else None
+                gp = _lib.ptr_array([g.data_ptr() for g in gws])
+                _lib.check(L.seldq_conv_wgrad(ctypes.byref(desc), None if bf16 else xs.data_ptr(),
+                                              xs.data_ptr() if bf16 else None, gy.data_ptr(), _ptr(gy16), gp,
+                                              _ptr(gb), None, 0, _stream()))
+        return (gx, gb, None, None, None, None, None) + tuple(gws)
+
+
+class _BlockLinear(torch.autograd.Function):
+    """y = x @ expand(weights) + bias  (quaternion_ops.py:299-327 / :392-464,
+    dual_quaternion_ops.py:156-203).  x is (rows, in)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, algebra, prec, *weights):
+        import ctypes
+        L = _lib.lib()
+        nc = _NCOMP[algebra]
+        _require_cuda_f32(x, "input")
+        for w in weights:
+            _require_cuda_f32(w, "weight")
+        if bias is not None:
+            _require_cuda_f32(bias, "bias")
+        if x.dim() != 2:
+            raise RuntimeError("seldq linear expects a 2-d (rows, features) input")
+        x = x.contiguous()
+        weights = tuple(w.contiguous() for w in weights)
+        fin, fout = weights[0].shape[0] * nc, weights[0].shape[1] * nc
+        if x.shape[1] != fin:
+            raise RuntimeError("mat1 and mat2 shapes cannot be multiplied (%dx%d and %dx%d)"
+                               % (x.shape[0], x.shape[1], fin, fout))
+        desc = _lib.LinearDesc(algebra, prec, x.shape[0], fin, fout)
+        y = torch.empty((x.shape[0], fout), dtype=torch.float32, device=x.device)
+        wp = _lib.ptr_array([w.data_ptr() for w in weights])
+        with torch.cuda.device(x.device):
+            _lib.check(L.seldq_linear_fwd(ctypes.byref(desc), x.data_ptr(), wp, _ptr(bias), y.data_ptr(), None, 0,
+                                          _stream()))
+        ctx.desc = desc
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, *weights)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        import ctypes
+        L = _lib.lib()
+        desc = ctx.desc
+        x, *weights = ctx.saved_tensors
+        gy = gy.contiguous()
+        dev = gy.device
+        need_x = ctx.needs_input_grad[0]
+        need_w = any(ctx.needs_input_grad[4:])
+        need_b = ctx.has_bias and ctx.needs_input_grad[1]
+        gx = gb = None
+        gws = [None] * len(weights)
+        wp = _lib.ptr_array([w.data_ptr() for w in weights])
+        with torch.cuda.device(dev):
+            if need_x:
+                gx = torch.empty_like(x)
+                _lib.check(L.seldq_linear_dgrad(ctypes.byref(desc), gy.data_ptr(), wp, gx.data_ptr(), None, 0,
+                                                _stream()))
+            if need_w or need_b:
+                gws = [torch.empty_like(w) for w in weights]
+                gb = torch.empty(desc.out_features, dtype=torch.float32, device=dev) if need_b else None
+                gp = _lib.ptr_array([g.data_ptr() for g in gws])
+                _lib.check(L.seldq_linear_wgrad(ctypes.byref(desc), x.data_ptr(), gy.data_ptr(), gp, _ptr(gb),
+                                                None, 0, _stream()))
+        return (gx, gb, None, None) + tuple(gws)
+
+
+def block_conv(x, weights, bias, stride, padding, dilation, algebra, prec=None):
+    if x.dim() not in (3, 4):
+        if x.dim() == 5:
+            raise NotImplementedError("seldq: 3-d convolution (5-d input) is not on the SELD hot path")
+        # same complaint as quaternion_ops.py:143-145
+        raise Exception("The convolutional input is either 3, 4 or 5 dimensions. input.dim = " + str(x.dim()))
+    prec = _PRECISION if prec is None else prec
+    return _BlockConv.apply(x, bias, stride, padding, dilation, algebra, prec, *weights)
+
+
+def block_linear(x, weights, bias, algebra, prec=None):
+    prec = _PRECISION if prec is None else prec
+    if x.dim() == 2:
+        return _BlockLinear.apply(x, bias, algebra, prec, *weights)
+    lead = x.shape[:-1]
+    y = _BlockLinear.apply(x.reshape(-1, x.shape[-1]), bias, algebra, prec, *weights)
+    return y.reshape(lead + (y.shape[-1],))
+
+
+def stft_magphase(x, nperseg=512, noverlap=128, cut_dc=True, output_phase=True, cut_last_timeframe=True):
+    """x: (C, n) or (B, C, n) float32 CUDA tensor -> ((1+phase)*C, F, T) or (B, (1+phase)*C, F, T)
+    (utility_functions.py:129-155)."""
+    import ctypes
+    L = _lib.lib()
+    _require_cuda_f32(x, "signal")
+    if x.dim() not in (2, 3):
+        raise ValueError("stft_magphase expects (channels, samples) or (batch, channels, samples)")
+    batched = x.dim() == 3
+    xb = (x if batched else x[None]).contiguous()
+    B, C, n = xb.shape
+    nb, nf = ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(L.seldq_stft_shape(n, nperseg, noverlap, int(cut_dc), int(cut_last_timeframe), ctypes.byref(nb),
+                                  ctypes.byref(nf)))
+    planes = 2 if output_phase else 1
+    out = torch.empty((B, planes * C, nb.value, nf.value), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.seldq_stft_magphase(xb.data_ptr(), B, C, n, nperseg, noverlap, int(cut_dc), int(output_phase),
+                                         int(cut_last_timeframe), out.data_ptr(), _stream()))
+    return out if batched else out[0]

@@ -1,0 +1,346 @@
+"""DQSELD-TCN assembly: CNN (3 conv2d blocks) -> TCN (gated dilated residual blocks) ->
+multi-head self-attention -> SED / DOA heads.
+
+Host-side mirror of the reference's model.py (MultiHeadAttention :12-51, ResBlock :53-132,
+TC_Block :134-232, ConvTC_Block :234-322, SELD_Model :324-480): same constructor arguments,
+same sub-module names and construction order, hence the same state_dict keys and -- given the
+same numpy / torch seeds -- bit-identical initial weights, so reference checkpoints load here and
+vice versa.  The reference model.py itself also runs unchanged on top of the drop-in layer
+modules; this mirror exists because the GPU box has no reference tree, and
+because it is where the fused epilogue kernels are wired in.
+
+`layer_lib` lets a caller substitute the Q / DQ layer classes (the CPU oracle does that to time
+the reference's arithmetic on host cores); the default is the sm_100a implementation.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as tF
+
+from . import layers as _default_layers
+
+_BN_TCN = {'BN', 'BN_on_TCN', 'BNonTCN'}
+_BN_CNN = {'BN', 'BN_on_CNN', 'BNonCNN'}
+_TWO_BRANCH = {'2Parallel', '2BParallel', '2ParallelBranches', '2PB'}
+
+
+def _make_conv(layer_lib, domain, ndim, cin, cout, k, padding, dilation, bias):
+    op = 'convolution1d' if ndim == 1 else 'convolution2d'
+    if domain == 'Q':
+        return layer_lib.QuaternionConv(cin, cout, kernel_size=k, stride=1, padding=padding,
+                                        dilatation=dilation, bias=bias, operation=op)
+    if domain == 'DQ':
+        return layer_lib.DualQuaternionConv(cin, cout, kernel_size=k, stride=1, padding=padding,
+                                            dilatation=dilation, bias=bias, operation=op)
+    cls = nn.Conv1d if ndim == 1 else nn.Conv2d
+    return cls(cin, cout, kernel_size=k, stride=1, padding=padding, dilation=dilation, bias=bias)
+
+
+class MultiHeadAttention(nn.Module):
+    """model.py:12-51.  Real-valued; 1x1 conv projections without bias, softmax(QK^T / sqrt(d)) V,
+    output Linear.  The S x S energy tensor of the reference is not materialised: the same
+    expression goes through scaled_dot_product_attention."""
+
+    def __init__(self, embed_size, num_heads):
+        super().__init__()
+        assert embed_size % num_heads == 0, "Embedding size must be divisible by number of heads"
+        self.num_heads = num_heads
+        self.head_dim = embed_size // num_heads
+        self.values = nn.Conv1d(embed_size, embed_size, kernel_size=1, bias=False)
+        self.keys = nn.Conv1d(embed_size, embed_size, kernel_size=1, bias=False)
+        self.queries = nn.Conv1d(embed_size, embed_size, kernel_size=1, bias=False)
+        self.fc_out = nn.Linear(embed_size, embed_size)
+
+    def _split(self, t):                       # (N, E, L) -> (N, heads, L, head_dim); e = h*head_dim + d
+        n, _, length = t.shape
+        return t.view(n, self.num_heads, self.head_dim, length).transpose(2, 3)
+
+    def forward(self, v, k, q, mask=None):
+        # inputs are (N, L, E) as in the reference; the projections want (N, E, L)
+        n, length = q.shape[0], q.shape[1]
+        vp = self._split(self.values(v.permute(0, 2, 1)))
+        kp = self._split(self.keys(k.permute(0, 2, 1)))
+        qp = self._split(self.queries(q.permute(0, 2, 1)))
+        attn_mask = None if mask is None else (mask != 0)
+        out = tF.scaled_dot_product_attention(qp, kp, vp, attn_mask=attn_mask)    # scale = 1/sqrt(head_dim)
+        out = out.transpose(1, 2).reshape(n, length, self.num_heads * self.head_dim)
+        return self.fc_out(out)
+
+
+class ResBlock(nn.Module):
+    """Pre-activation gated residual block (model.py:53-132)."""
+
+    def __init__(self, in_channels, domain='DQ', G=128, U=128, kernel_size_dilated_conv=3, dilation=1, stride=1,
+                 spatial_dropout_rate=0.5, use_bias_conv=True, batch_norm='BN', verbose=False, layer_lib=None):
+        super().__init__()
+        lib = layer_lib or _default_layers
+        self.verbose = verbose
+        self.batch_norm = batch_norm
+        self.spatial_dropout_rate = spatial_dropout_rate
+        self.domain = domain
+        padding = int(((kernel_size_dilated_conv - 1) * dilation) / 2)
+        L = in_channels
+        self.conv1_filter = _make_conv(lib, domain, 1, L, G, kernel_size_dilated_conv, padding, dilation, use_bias_conv)
+        self.conv1_gate = _make_conv(lib, domain, 1, L, G, kernel_size_dilated_conv, padding, dilation, use_bias_conv)
+        if batch_norm in _BN_TCN:
+            self.batch_filter1 = nn.BatchNorm1d(L)
+            self.batch_gate1 = nn.BatchNorm1d(L)      # allocated but unused, as in the reference
+            self.batch_filter2 = nn.BatchNorm1d(G)
+            self.batch_gate2 = nn.BatchNorm1d(G)
+        self.tanh = nn.Tanh()
+        self.sigmoid = nn.Sigmoid()
+        if not spatial_dropout_rate == 0:
+            self.dropout = nn.Dropout1d(p=spatial_dropout_rate)
+        self.conv2_skip = _make_conv(lib, domain, 1, G, U, 1, 0, 1, use_bias_conv)
+        self.conv2_residual = _make_conv(lib, domain, 1, G, L, 1, 0, 1, use_bias_conv)
+
+    def forward(self, x):
+        bn = self.batch_norm in _BN_TCN
+        if bn:
+            x = self.tanh(self.batch_filter1(x))
+        y_f = self.conv1_filter(x)
+        y_g = self.conv1_gate(x)
+        if bn:
+            y_f = self.batch_filter2(y_f)
+            y_g = self.batch_gate2(y_g)
+        y = self.tanh(y_f) * self.sigmoid(y_g)
+        if not self.spatial_dropout_rate == 0:
+            y = self.dropout(y)
+        return x + self.conv2_residual(y), self.conv2_skip(y)
+
+
+def _dilations(D, dilation_mode):
+    """Per-stack dilation lists (model.py:150-176): fibonacci 1,1,2,3,5,... or powers of two."""
+    out = []
+    for n_resblock in D:
+        if type(n_resblock) == list:
+            out.extend(n_resblock)
+            continue
+        prev1, prev2 = 1, 0
+        for d in range(n_resblock):
+            if dilation_mode == 'fibonacci':
+                if d == 0:
+                    dil = 1
+                else:
+                    dil = prev1 + prev2
+                    prev2, prev1 = prev1, dil
+            else:
+                dil = 2 ** d
+            out.append(dil)
+    return out
+
+
+class TC_Block(nn.Module):
+    """model.py:134-232."""
+
+    def __init__(self, in_channels, domain='DQ', G=128, U=128, V=[128, 128], V_kernel_size=3,
+                 pool_size=[[8, 2], [8, 2], [2, 2]], D=[10], spatial_dropout_rate=0.5, use_bias_conv=True,
+                 dilation_mode='fibonacci', pool_time='TCN', batch_norm='BN', kernel_size_dilated_conv=3,
+                 verbose=False, attention_type=None, key_size=None, value_size=None, layer_lib=None):
+        super().__init__()
+        lib = layer_lib or _default_layers
+        self.verbose = verbose
+        self.ResBlocks = nn.ModuleList()
+        self.D = D
+        self.pool_time = pool_time
+        self.domain = domain
+        for dil in _dilations(D, dilation_mode):
+            self.ResBlocks.append(ResBlock(in_channels=in_channels, domain=domain, G=G, U=U,
+                                           kernel_size_dilated_conv=kernel_size_dilated_conv, dilation=dil,
+                                           spatial_dropout_rate=spatial_dropout_rate, use_bias_conv=use_bias_conv,
+                                           batch_norm=batch_norm, verbose=verbose, layer_lib=lib))
+        self.relu1 = nn.ReLU()
+        if self.pool_time == 'TCN':
+            self.maxpool1 = nn.MaxPool1d(pool_size[0][1])
+        self.conv1 = _make_conv(lib, domain, 1, in_channels, V[0], V_kernel_size, 1, 1, use_bias_conv)
+        self.attention = MultiHeadAttention(embed_size=V[0], num_heads=8)
+        self.relu2 = nn.ReLU()
+        if self.pool_time == 'TCN':
+            self.maxpool2 = nn.MaxPool1d(pool_size[1][1])
+        self.conv2 = _make_conv(lib, domain, 1, V[0], V[1], V_kernel_size, 1, 1, use_bias_conv)
+        self.tanh = nn.Tanh()
+        if self.pool_time == 'TCN':
+            self.maxpool3 = nn.MaxPool1d(pool_size[2][1])
+
+    def forward(self, residual):
+        sum_skip = None
+        for block in self.ResBlocks:
+            residual, skip = block(residual)
+            sum_skip = skip if sum_skip is None else sum_skip + skip
+        out = self.relu1(sum_skip)
+        if self.pool_time == 'TCN':
+            out = self.maxpool1(out)
+        out = self.conv1(out)
+        out = out.permute(0, 2, 1)
+        out = self.attention(out, out, out, mask=None)
+        out = out.permute(0, 2, 1)
+        out = self.relu2(out)
+        if self.pool_time == 'TCN':
+            out = self.maxpool2(out)
+        out = self.conv2(out)
+        out = self.tanh(out)
+        if self.pool_time == 'TCN':
+            out = self.maxpool3(out)
+        return out
+
+
+class ConvTC_Block(nn.Module):
+    """model.py:234-322."""
+
+    def __init__(self, time_dim, freq_dim=256, input_channels=4, domain='DQ', cnn_filters=[64, 64, 64],
+                 kernel_size_cnn_blocks=3, pool_size=[[8, 2], [8, 2], [2, 2]], pool_time='TCN', D=[10],
+                 dilation_mode='fibonacci', G=128, U=128, kernel_size_dilated_conv=3, spatial_dropout_rate=0.5,
+                 V=[128, 128], V_kernel_size=3, dropout_perc=0.3, use_bias_conv=True, batch_norm='noBN',
+                 attention_type=None, key_size=None, value_size=None, verbose=False, layer_lib=None):
+        super().__init__()
+        lib = layer_lib or _default_layers
+        self.time_dim = time_dim
+        self.freq_dim = freq_dim
+        self.domain = domain
+        self.verbose = verbose
+        self.D = D
+        self.kernel_size_dilated_conv = kernel_size_dilated_conv
+        self.dilation_mode = dilation_mode
+        if pool_time == 'CNN':
+            self.time_pooled_size = int(time_dim / np.prod(np.array(pool_size), axis=0)[-1])
+        else:
+            self.time_pooled_size = time_dim
+        blocks = []
+        in_chans = input_channels
+        for p, c in zip(pool_size, np.array(cnn_filters)):
+            pool = [p[0], p[1]] if pool_time == 'CNN' else [p[0], 1]
+            mods = [_make_conv(lib, domain, 2, in_chans, c, kernel_size_cnn_blocks, 1, 1, use_bias_conv)]
+            if batch_norm in _BN_CNN:
+                mods.append(nn.BatchNorm2d(c))
+            mods += [nn.ReLU(), nn.MaxPool2d(pool), nn.Dropout(dropout_perc)]
+            blocks.append(nn.Sequential(*mods))
+            in_chans = c
+        self.cnn = nn.Sequential(*blocks)
+        L = int(freq_dim / np.prod(np.array(pool_size), axis=0)[0] * cnn_filters[-1])
+        self.tcn = TC_Block(in_channels=L, domain=domain, G=G, U=U, V=V, V_kernel_size=V_kernel_size,
+                            pool_size=pool_size, D=D, spatial_dropout_rate=spatial_dropout_rate,
+                            use_bias_conv=use_bias_conv, dilation_mode=dilation_mode, pool_time=pool_time,
+                            batch_norm=batch_norm, kernel_size_dilated_conv=kernel_size_dilated_conv,
+                            verbose=verbose, attention_type=attention_type, key_size=key_size,
+                            value_size=value_size, layer_lib=lib)
+
+    def forward(self, x):
+        x = self.cnn(x)                                   # (B, C, F', T)
+        x = x.permute(0, 3, 1, 2)                         # (B, T, C, F')
+        x = x.reshape(x.shape[0], self.time_pooled_size, -1)
+        x = x.permute(0, 2, 1)                            # (B, C*F', T): channel order c*F' + f
+        x = self.tcn(x)
+        return x.permute(0, 2, 1)                         # (B, T/8, V)
+
+
+class SELD_Model(nn.Module):
+    """model.py:324-480."""
+
+    def __init__(self, time_dim, freq_dim=256, input_channels=4, output_classes=14, domain='DQ',
+                 domain_classifier='same', cnn_filters=[64, 64, 64], kernel_size_cnn_blocks=3,
+                 pool_size=[[8, 2], [8, 2], [2, 2]], pool_time='TCN', D=[10], dilation_mode='fibonacci',
+                 G=128, U=128, kernel_size_dilated_conv=3, spatial_dropout_rate=0.5, V=[128, 128],
+                 V_kernel_size=3, fc_layers=[128], fc_activations='Linear', fc_dropout='all', dropout_perc=0.3,
+                 class_overlaps=3., use_bias_conv=False, use_bias_linear=True, batch_norm='BN',
+                 parallel_ConvTC_block='False', parallel_magphase=False, extra_name='', attention_type=None,
+                 key_size=None, value_size=None, verbose=False, layer_lib=None):
+        super().__init__()
+        lib = layer_lib or _default_layers
+        self.input_channels = input_channels
+        self.time_dim = time_dim
+        self.freq_dim = freq_dim
+        self.domain = domain
+        self.verbose = verbose
+        self.D = D
+        self.kernel_size_dilated_conv = kernel_size_dilated_conv
+        self.dilation_mode = dilation_mode
+        self.parallel_magphase = parallel_magphase
+        self.domain_classifier = domain if domain_classifier == 'same' else domain_classifier
+        self.receptive_field, self.total_n_resblocks = self.calculate_receptive_field()
+        self.parallel_ConvTC_block = parallel_ConvTC_block
+        self.model_name = self._name(domain, dilation_mode, D, parallel_ConvTC_block, batch_norm, pool_time,
+                                     extra_name)
+        sed_output_size = int(output_classes * class_overlaps)
+        doa_output_size = sed_output_size * 3
+        block_kw = dict(time_dim=time_dim, freq_dim=freq_dim, domain=domain, cnn_filters=cnn_filters,
+                        kernel_size_cnn_blocks=kernel_size_cnn_blocks, pool_size=pool_size, pool_time=pool_time,
+                        D=D, dilation_mode=dilation_mode, G=G, U=U,
+                        kernel_size_dilated_conv=kernel_size_dilated_conv,
+                        spatial_dropout_rate=spatial_dropout_rate, V=V, V_kernel_size=V_kernel_size,
+                        dropout_perc=dropout_perc, use_bias_conv=use_bias_conv, batch_norm=batch_norm,
+                        verbose=False, layer_lib=lib)
+        if parallel_ConvTC_block in _TWO_BRANCH:
+            self.branch_A = ConvTC_Block(input_channels=input_channels // 2, **block_kw)
+            self.branch_B = ConvTC_Block(input_channels=input_channels // 2, **block_kw)
+            fc_input_size = V[-1] * 2
+        else:
+            self.seld_block = ConvTC_Block(input_channels=input_channels, attention_type=attention_type,
+                                           key_size=key_size, value_size=value_size, **block_kw)
+            fc_input_size = V[-1]
+
+        def fc(n_in, n_out):
+            if self.domain_classifier == 'Q':
+                return lib.QuaternionLinear(n_in, n_out, bias=use_bias_linear)
+            if self.domain_classifier == 'DQ':
+                return lib.DualQuaternionLinear(n_in, n_out, bias=use_bias_linear)
+            return nn.Linear(n_in, n_out, bias=use_bias_linear)
+
+        sed_list, doa_list = [], []
+        for width in fc_layers:
+            sed_list.append(fc(fc_input_size, width))       # sed before doa: keeps the RNG stream of the reference
+            doa_list.append(fc(fc_input_size, width))
+            if fc_activations in {'relu', 'ReLU', 'RELU'}:
+                sed_list.append(nn.ReLU())
+                doa_list.append(nn.ReLU())
+            if fc_dropout in {'all', 'ALL', 'True'}:
+                sed_list.append(nn.Dropout(dropout_perc))
+                doa_list.append(nn.Dropout(dropout_perc))
+            fc_input_size = width
+        if fc_dropout in {'last', 'Last', 'LAST'}:
+            sed_list.append(nn.Dropout(dropout_perc))
+            doa_list.append(nn.Dropout(dropout_perc))
+        self.sed = nn.Sequential(*sed_list, nn.Linear(fc_layers[-1], sed_output_size, bias=use_bias_linear),
+                                 nn.Sigmoid())
+        self.doa = nn.Sequential(*doa_list, nn.Linear(fc_layers[-1], doa_output_size, bias=use_bias_linear),
+                                 nn.Tanh())
+
+    def _name(self, domain, dilation_mode, D, parallel, batch_norm, pool_time, extra_name):
+        # model.py:347-372 -- the name doubles as the output directory of train.py:461-468
+        if domain in {'q', 'Q', 'quaternion', 'Quaternion'}:
+            name = 'Q'
+        elif domain in {'dq', 'dQ', 'DQ', 'dual_quaternion', 'Dual_Quaternion'}:
+            name = 'DualQ'
+        else:
+            name = ''
+        name += 'SELD-TCN'
+        if dilation_mode == 'fibonacci':
+            name += '-PHI'
+        name += '-'
+        if len(D) > 1 and D[0] < D[1]:
+            name += 'I'
+        name += 'S' + str(len(D))
+        if parallel not in {'False', 'false', 'None', 'none'}:
+            name += '_' + parallel
+        name += '_' + batch_norm
+        if pool_time == 'CNN':
+            name += '_pooltCNN'
+        name += '_RF{}_{}RB'.format(self.receptive_field, self.total_n_resblocks)
+        return name + extra_name
+
+    def forward(self, x):
+        if self.parallel_ConvTC_block in _TWO_BRANCH:
+            if self.parallel_magphase:
+                x_a = torch.cat((x[:, :4], x[:, 8:12]), 1)      # mic A magnitude + phase
+                x_b = torch.cat((x[:, 4:8], x[:, 12:]), 1)      # mic B magnitude + phase
+            else:
+                half = self.input_channels // 2
+                x_a, x_b = x[:, :half], x[:, half:]
+            x = torch.cat((self.branch_A(x_a), self.branch_B(x_b)), 2)
+        else:
+            x = self.seld_block(x)
+        return self.sed(x), self.doa(x)
+
+    def calculate_receptive_field(self, verbose=0):
+        dils = _dilations(self.D, self.dilation_mode)
+        rf = 1 + sum((self.kernel_size_dilated_conv - 1) * d for d in dils)
+        return rf, len(dils)

@@ -1,0 +1,121 @@
+"""CPU-side checks of the drop-in boundary: C-ABI symbols, state_dict compatibility, init parity,
+error behaviour without a GPU.  No compute call succeeds here (there is no CPU fallback)."""
+import ctypes
+import importlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, ROOT, load_golden
+from oracle import ref_import
+
+
+def _cfg_kwargs(meta):
+    cfg = dict(meta["cfg"])
+    return dict(time_dim=meta["time_dim"], spatial_dropout_rate=0, dropout_perc=0, **cfg)
+
+
+def test_library_exports_every_declared_symbol(seldq):
+    seldq.build()
+    header = open(os.path.join(ROOT, "include", "seldq.h")).read()
+    declared = set(re.findall(r"\b(seldq_[a-z0-9_]+)\s*\(", header))
+    declared -= {"seldq_status_t"}
+    out = subprocess.check_output(["nm", "-D", "--defined-only", seldq._lib.LIB_PATH]).decode()
+    exported = set(re.findall(r" T (seldq_[a-z0-9_]+)", out))
+    assert declared, "no declarations parsed"
+    assert declared <= exported, sorted(declared - exported)
+    lib = seldq._lib.lib()
+    assert lib.seldq_abi_version() == 1
+    assert set(seldq._lib.exported_symbols()) <= exported
+
+
+def test_descriptor_validation_runs_without_gpu(seldq):
+    L = seldq._lib
+    lib = L.lib()
+    d = L.ConvDesc(L.ALG_DQ, L.PREC_FP32, 1, 2, 384, 384, 1, 4800, 1, 3, 1, 1, 0, 5, 1, 5)
+    oh, ow = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.seldq_conv_out_shape(ctypes.byref(d), ctypes.byref(oh), ctypes.byref(ow)) == 0
+    assert (oh.value, ow.value) == (1, 4800)
+    bad = L.ConvDesc(L.ALG_DQ, L.PREC_FP32, 1, 2, 12, 384, 1, 4800, 1, 3, 1, 1, 0, 5, 1, 5)
+    assert lib.seldq_conv_out_shape(ctypes.byref(bad), None, None) == L.ERR_INVALID
+    assert b"divisible by 8" in lib.seldq_last_error()
+    nb, nf = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.seldq_stft_shape(1920000, 512, 112, 1, 1, ctypes.byref(nb), ctypes.byref(nf)) == 0
+    assert (nb.value, nf.value) == (256, 4800)
+    d16 = L.ConvDesc(L.ALG_DQ, L.PREC_BF16, 1, 1, 384, 384, 1, 4800, 1, 3, 1, 1, 0, 1, 1, 1)
+    assert lib.seldq_conv_workspace_bytes(ctypes.byref(d16), L.PASS_WGRAD) == 2 * 384 * 4800 * 2
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(seldq):
+    conv = seldq.DualQuaternionConv(16, 16, kernel_size=3, stride=1, padding=1, operation='convolution1d')
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        conv(torch.randn(1, 16, 32))
+    lin = seldq.QuaternionLinear(8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lin(torch.randn(3, 8))
+    with pytest.raises(RuntimeError):
+        seldq.spectrum_fast(np.zeros((2, 4000), np.float32))
+
+
+@pytest.mark.parametrize("name", ["model_dq_tiny", "model_q_tiny", "model_dq_2branch_tiny", "model_dq_mid"])
+def test_state_dict_matches_reference_checkpoint_layout(seldq, name):
+    meta, d = load_golden(name)
+    m = seldq.SELD_Model(**_cfg_kwargs(meta))
+    sd = m.state_dict()
+    ref_keys = [k[len("param/"):] for k in d if k.startswith("param/")]
+    assert list(sd.keys()) == ref_keys or set(sd.keys()) == set(ref_keys)
+    for k in ref_keys:
+        assert tuple(sd[k].shape) == tuple(d["param/" + k].shape), k
+    m.load_state_dict({k: torch.from_numpy(np.asarray(d["param/" + k])) for k in ref_keys}, strict=True)
+    assert m.model_name == meta["model_name"]
+
+
+@pytest.mark.parametrize("name", ["model_dq_tiny", "model_q_tiny", "model_dq_2branch_tiny"])
+def test_init_is_bit_identical_to_reference_fixture(seldq, name):
+    """Same numpy / torch seeds -> same initial weights as the reference (its init is a pure
+    function of the global RNG streams)."""
+    meta, d = load_golden(name)
+    np.random.seed(meta["seed"])
+    torch.manual_seed(meta["seed"])
+    m = seldq.SELD_Model(**_cfg_kwargs(meta))
+    for k, v in m.state_dict().items():
+        ref = np.asarray(d["param/" + k])
+        assert np.array_equal(v.numpy(), ref), k
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree only exists in the build container")
+def test_reference_model_py_builds_on_dropin_layers():
+    """model.py, unmodified, star-imports the drop-in modules and assembles the DQ model with the
+    same parameter names / shapes / values as with its own layers."""
+    code = r'''
+import sys, types, importlib, importlib.machinery
+import numpy as np, torch
+sys.path.insert(0, %r)
+pkg = importlib.import_module(%r)
+def stub(name, **a):
+    m = types.ModuleType(name); m.__spec__ = importlib.machinery.ModuleSpec(name, None); m.__dict__.update(a); sys.modules[name] = m
+stub("torchinfo", summary=lambda *a, **k: None); stub("librosa")
+sys.path.insert(0, "/root/reference")
+pkg.install_dropin()
+import model
+assert "dropin" in sys.modules["quaternion.quaternion_layers"].__file__
+assert model.DualQuaternionConv is pkg.DualQuaternionConv and model.QuaternionLinear is pkg.QuaternionLinear
+np.random.seed(1); torch.manual_seed(1)
+m = model.SELD_Model(time_dim=64, freq_dim=128, input_channels=8, output_classes=14, domain="DQ",
+    domain_classifier="DQ", cnn_filters=[16,16,16], G=16, U=16, V=[16,16], fc_layers=[16], fc_dropout="Last",
+    fc_activations="linear", pool_time="TCN", batch_norm="BN", use_bias_conv=0, use_bias_linear=1, class_overlaps=3,
+    spatial_dropout_rate=0, dropout_perc=0, extra_name="_tiny")
+z = np.load(%r)
+for k, v in m.state_dict().items():
+    assert np.array_equal(v.numpy(), z["param/" + k]), k
+print("OK", m.model_name)
+''' % (ROOT, PKG, os.path.join(ROOT, "tests", "golden", "model_dq_tiny.npz"))
+    out = subprocess.check_output([sys.executable, "-c", code], cwd="/tmp").decode()
+    assert "OK DualQSELD-TCN-PHI-S1_BN_RF287_10RB_tiny" in out
