@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- DQSELD-TCN training samples/s on N B200s of one node (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU arithmetic (oracle port)
+
+A "step" is one full training step (train.py:546-561: zero_grad, forward, BCE+5*MSE loss, backward,
+gradient all-reduce, Adam) on one synthetic L3DAS21-shaped batch per GPU.  One process per GPU
+(torchrun for N > 1), batch-sharded data parallel, weak scaling.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "sound-event-localization-and-detection_b200"
+
+# hyper-parameters train.py passes for each config/SERVER_*.txt
+COMMON = dict(freq_dim=256, output_classes=14, kernel_size_cnn_blocks=3, pool_size=[[8, 2], [8, 2], [2, 2]],
+              pool_time="TCN", D=[10], dilation_mode="fibonacci", kernel_size_dilated_conv=3, V_kernel_size=3,
+              fc_activations="linear", fc_dropout="Last", class_overlaps=3, use_bias_conv=0, use_bias_linear=1,
+              batch_norm="BN", spatial_dropout_rate=0.5, dropout_perc=0.3)
+CONFIGS = {
+    "DQSELD-TCN-S1-PHI_8ch": dict(input_channels=8, domain="DQ", domain_classifier="DQ",
+                                  cnn_filters=[192, 192, 192], G=384, U=384, V=[384, 384], fc_layers=[384],
+                                  parallel_ConvTC_block="False", parallel_magphase=False, extra_name="_8ch",
+                                  batch_size=1, conv_train_gflop=570.9),
+    "DQSELD-TCN-S1-PHI_16chMagPhase": dict(input_channels=16, domain="DQ", domain_classifier="DQ",
+                                           cnn_filters=[192, 192, 192], G=384, U=384, V=[384, 384],
+                                           fc_layers=[384], parallel_ConvTC_block="False",
+                                           parallel_magphase=False, extra_name="_16chMagPhase", batch_size=4,
+                                           conv_train_gflop=621.9),
+    "QSELD-TCN-S1-PHI_parallel_8ch": dict(input_channels=8, domain="Q", domain_classifier="R",
+                                          cnn_filters=[64, 64, 64], G=128, U=128, V=[128, 128], fc_layers=[128],
+                                          parallel_ConvTC_block="1", parallel_magphase=False,
+                                          extra_name="_parallel_8ch", batch_size=4, conv_train_gflop=99.7),
+}
+TIME_DIM, N_FRAMES_OUT, N_SED = 4800, 600, 42
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+def synth_batch(pkg, cfg, batch, seed, device):
+    """Synthetic L3DAS21-shaped batch: 0.1*randn waveforms (B, 8, 60 s @ 32 kHz) ->
+    STFT magnitude(/phase) features via this repo's front-end kernel -> train.py-style mean/std
+    normalisation; targets: SED Bernoulli(0.05), DOA U(-1,1) masked by SED."""
+    g = torch.Generator().manual_seed(seed)
+    phase = cfg["input_channels"] == 16
+    wav = (0.1 * torch.randn(batch, 8, 1_920_000, generator=g)).to(device)
+    feat = pkg.stft_magphase(wav, 512, 112, True, phase, True)            # (B, 8|16, 256, 4800)
+    feat[:, :8] = (feat[:, :8] - feat[:, :8].mean()) / feat[:, :8].std()   # train.py:379-382
+    if phase:
+        feat[:, 8:] = (feat[:, 8:] - feat[:, 8:].mean()) / feat[:, 8:].std()   # train.py:397-400
+    sed = (torch.rand(batch, N_FRAMES_OUT, N_SED, generator=g) < 0.05).float()
+    doa = (2 * torch.rand(batch, N_FRAMES_OUT, 3 * N_SED, generator=g) - 1) * sed.repeat_interleave(3, -1)
+    return feat.contiguous(), torch.cat([sed, doa], -1).to(device)
+
+
+def model_kwargs(cfg):
+    kw = dict(COMMON)
+    kw.update({k: v for k, v in cfg.items() if k not in ("batch_size", "conv_train_gflop")})
+    return kw
+
+
+def run_reference(args, cfg, rank, world):
+    """The reference's CPU arithmetic (oracle/cpu_model.py: torch.cat expansion + F.conv / mm, stock
+    BatchNorm etc.) for the same config, on the host cores of this box.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import cpu_model
+    torch.set_num_threads(os.cpu_count())
+    np.random.seed(1)
+    torch.manual_seed(1)
+    batch = args.batch or cfg["batch_size"]
+    model = cpu_model.build_model(time_dim=TIME_DIM, **model_kwargs(cfg)).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    g = torch.Generator().manual_seed(1234)
+    # features of the same distribution as the GPU arm's (standardised STFT magnitudes): N(0,1) surrogate
+    x = torch.randn(batch, cfg["input_channels"], 256, TIME_DIM, generator=g)
+    sed = (torch.rand(batch, N_FRAMES_OUT, N_SED, generator=g) < 0.05).float()
+    doa = (2 * torch.rand(batch, N_FRAMES_OUT, 3 * N_SED, generator=g) - 1) * sed.repeat_interleave(3, -1)
+    target = torch.cat([sed, doa], -1)
+    steps, warm = max(1, min(args.steps, args.ref_max_steps)), max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        cpu_model.train_step(model, opt, x, target)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_model.train_step(model, opt, x, target)
+    dt = time.perf_counter() - t0
+    value = steps * batch / dt
+    line = dict(metric="train_samples_per_sec", value=value, unit="samples/s", n_gpus=args.gpus, steps=steps,
+                warmup=warm, ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=args.config, per_gpu_batch=batch, global_batch=batch,
+                            note="CPU port of the reference arithmetic, one replica on the host cores"),
+                cpu_baseline=dict(value=value, unit="samples/s", cores=os.cpu_count(), kind="port",
+                                  sample="%d warm-up + %d timed full training steps, batch %d" % (warm, steps, batch)),
+                e2e=dict(value=value, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="DQSELD-TCN-S1-PHI_8ch", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config file's batch_size)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches rotated through")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-max-steps", type=int, default=3)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    pkg = importlib.import_module(PKG)
+    pkg.set_precision(args.precision)
+    F = pkg.functional
+    trainer_mod = importlib.import_module(PKG + ".trainer")
+    batch = args.batch or cfg["batch_size"]
+    warm = max(3, args.warmup)
+
+    np.random.seed(1)
+    torch.manual_seed(1)                                   # train.py:214-221
+    model = pkg.SELD_Model(time_dim=TIME_DIM, **model_kwargs(cfg)).to(device).train()
+    trainer = trainer_mod.Trainer(model, lr=1e-4, n_sed=N_SED)
+    trainer.broadcast_parameters()
+    torch.manual_seed(100 + rank)                          # dropout masks differ per replica
+
+    pool_dev = [synth_batch(pkg, cfg, batch, 1234 + rank * 100 + i, device) for i in range(args.pool)]
+    pool_host = [(x.cpu().pin_memory(), t.cpu().pin_memory()) for x, t in pool_dev]
+    h2d = pool_host[0][0].numel() * 4 + pool_host[0][1].numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), (sampler.stop() if sampler else None)
+
+    def step_resident(i):
+        x, t = pool_dev[i % args.pool]
+        trainer.step(x, t)
+
+    def step_e2e(i):
+        hx, ht = pool_host[i % args.pool]
+        x = hx.to(device, non_blocking=True)
+        t = ht.to(device, non_blocking=True)
+        loss = trainer.step(x, t)
+        return float(loss.item())                          # device -> host read of the step's result
+
+    for i in range(warm):
+        step_resident(i)
+    F.profile_reset(enable=True)
+    ms, clocks = timed(step_resident, args.steps)
+    prof = F.profile_collect()
+    F.profile_reset(enable=False)
+    value = world * batch * args.steps / (ms / 1e3)
+
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    e2e_value = world * batch * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = load_peaks()
+        k = prof["kernels"].get("qconv_umma_fprop_kernel" if args.precision == "bf16" else "conv_simt_kernel", None)
+        roof = None
+        if k and k["ms"] > 0:
+            ach = k["flop"] / (k["ms"] / 1e3) / 1e12
+            roof = dict(bound="tensor", kernel=k["name"], achieved=ach, peak=peaks["tflops"], unit="TFLOP/s",
+                        frac=ach / peaks["tflops"], traffic=None, peak_source=peaks["source"],
+                        launches=k["launches"], avg_launch_us=1e3 * k["ms"] / max(1, k["launches"]),
+                        share_of_step=k["ms"] / ms)
+        line = dict(metric="train_samples_per_sec", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
+                    warmup=warm, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype=args.precision, data="synthetic",
+                    config=dict(workload=args.config, per_gpu_batch=batch, global_batch=batch * world,
+                                time_frames=TIME_DIM, parallelism="dp%d" % world,
+                                l2="activations per step (>1 GB) exceed the 126 MB L2; %d distinct input batches "
+                                   "are rotated" % args.pool),
+                    clocks=clocks,
+                    e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                             ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=prof["launches"], roofline=roof,
+                    conv_tflops_per_gpu=cfg["conv_train_gflop"] * value / world / 1e3,
+                    conv_frac_of_peak=cfg["conv_train_gflop"] * value / world / 1e3 / peaks["tflops"])
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out = subprocess.check_output([sys.executable, os.path.abspath(__file__), "--impl", "reference",
+                                               "--config", args.config, "--steps", "2", "--warmup", "1",
+                                               "--batch", str(batch)], timeout=900).decode().strip().splitlines()[-1]
+                line["cpu_baseline"] = json.loads(out)["cpu_baseline"]
+            except Exception as e:      # the baseline is reported, never required
+                line["cpu_baseline"] = dict(error=repr(e))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

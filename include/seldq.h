@@ -93,12 +93,12 @@ int seldq_device_count(void);
 int seldq_conv_out_shape(const seldq_conv_desc_t* d, int32_t* out_h, int32_t* out_w);
 size_t seldq_conv_workspace_bytes(const seldq_conv_desc_t* d, int32_t pass);
 
-/* y = conv(x, expand(w)) + bias.  x_bf16 / y_bf16 are optional (may be NULL):
- *   x_bf16  a bf16 copy of x made earlier by seldq_cast_bf16 (BF16 path only; if NULL the
- *           library casts x into the workspace first)
- *   y_bf16  if non-NULL the epilogue also stores a bf16 copy of y for the next layer      */
+/* y = conv(x, expand(w)) + bias.
+ *   x_bf16  optional (BF16 path only): the bf16 mirror set of x built earlier with
+ *           seldq_cast_bf16_mirror and the shift list seldq_conv_mirror_shifts(d, 0, ...); if NULL
+ *           the library builds it in the workspace first.  x may be NULL when x_bf16 is given. */
 int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_bf16,
-                   const float* const* host_w, const float* bias, float* y, void* y_bf16,
+                   const float* const* host_w, const float* bias, float* y,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* gx = conv_transpose(gy, expand(w)) : gradient w.r.t. the input */
@@ -124,11 +124,20 @@ int seldq_linear_wgrad(const seldq_linear_desc_t* d, const float* x, const float
 /* ---- helpers ------------------------------------------------------------------------------ */
 /* dst_bf16[i] = bf16(src[i]) (round to nearest even) */
 int seldq_cast_bf16(const float* src, void* dst_bf16, size_t n, void* stream);
-/* "bf16 mirror" of an NCHW/NCW fp32 tensor, the layout every *_bf16 argument uses: same order of
- * dimensions, row pitch seldq_bf16_pitch(w) = w rounded up to 8 elements (TMA needs 16-byte row
- * strides), pad columns zero.  rows = n*c*h. */
+/* "bf16 mirror set" of an NCHW / NCW fp32 tensor -- what every *_bf16 argument points to.
+ * TMA (cp.async.bulk.tensor) needs the innermost start coordinate of a box 16-byte aligned, while a
+ * convolution tap reads the time axis at an arbitrary offset (dilation 1, 2, 3, 5, ...).  The set
+ * therefore holds nshifts copies [shift][rows][pitch] (rows = n*c*h, pitch = seldq_bf16_pitch(w)),
+ * copy k being the tensor shifted RIGHT by shifts[k] in [0, 8) elements with zeros shifted in; a tap
+ * with offset off reads copy (-off) mod 8 at an aligned coordinate.  shifts[0] is always 0.
+ *   seldq_conv_mirror_shifts: the shift list a convolution needs; which = 0 for x (forward and
+ *   wgrad read it at the forward taps), which = 1 for gy (dgrad reads it at the transposed taps;
+ *   wgrad only uses its copy 0). */
 int seldq_bf16_pitch(int32_t w);
-int seldq_cast_bf16_mirror(const float* src, void* dst_bf16, int64_t rows, int32_t w, void* stream);
+int seldq_conv_mirror_shifts(const seldq_conv_desc_t* d, int32_t which, int32_t* shifts8, int32_t* nshifts);
+size_t seldq_bf16_mirror_bytes(int64_t rows, int32_t w, int32_t nshifts);
+int seldq_cast_bf16_mirror(const float* src, void* dst_bf16, int64_t rows, int32_t w,
+                           const int32_t* shifts, int32_t nshifts, void* stream);
 
 /* ---- STFT front end (F1) ----------------------------------------------------------------- */
 /* x: (n_signals, n_samples) float32.  out: (n_batch, (1+output_phase)*n_ch, n_bins, n_frames)
@@ -146,9 +155,9 @@ int seldq_stft_magphase(const float* x, int32_t n_batch, int32_t n_ch, int64_t n
 int seldq_probe_tensor_map(void* host_map_128B, const void* gaddr, int32_t elem_bytes, int32_t rank,
                            const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                            int32_t swizzle);
-int seldq_probe_tma_load(const void* host_map_128B, int32_t rank, const int32_t* coords,
-                         uint32_t box_bytes, uint32_t smem_offset, void* out_smem_dump,
-                         uint32_t dump_bytes, void* stream);
+int seldq_probe_tma_load(const void* host_map_128B, const void* dev_map_128B, int32_t rank,
+                         const int32_t* coords, uint32_t box_bytes, uint32_t smem_offset,
+                         void* out_smem_dump, uint32_t dump_bytes, void* stream);
 int seldq_probe_umma(const void* a_image, uint32_t a_bytes, const void* b_image, uint32_t b_bytes,
                      uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int32_t n_mma,
                      uint32_t a_desc_step, uint32_t b_desc_step, int32_t n_cols,

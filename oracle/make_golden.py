@@ -138,6 +138,28 @@ def model_case(name, cfg, time_dim, B, seed):
         if p.grad is not None:
             d["grad/" + k] = p.grad.numpy().astype(np.float32)
             ngrad += 1
+    # yardstick 1: the reference's own float32 run against its float64 run, per gradient tensor
+    m32 = ref_import.build_reference_model(cfg, time_dim=time_dim, spatial_dropout_rate=0, dropout_perc=0, seed=seed)
+    m32.load_state_dict(sd32)
+    m32.train()
+    s32, d32 = m32(torch.tensor(x, dtype=torch.float32))
+    seld_loss(s32, d32, torch.tensor(target, dtype=torch.float32), n_sed).backward()
+    from oracle import algebra as A
+    for k, p in m32.named_parameters():
+        if p.grad is not None:
+            d["ref32err/" + k] = np.float64(A.rel_err(p.grad.numpy(), d["grad/" + k]))
+    # yardstick 2: an ideal bf16-operand implementation (oracle/bf16_emulation.py) of the same model
+    from oracle import bf16_emulation, cpu_model
+    me = cpu_model.build_model(time_dim=time_dim, spatial_dropout_rate=0, dropout_perc=0, **cfg)
+    me.load_state_dict(sd32)
+    me = me.double().train()
+    with bf16_emulation.bf16_operand_convs():
+        se, de = me(torch.tensor(x))
+        cpu_model.seld_loss(se, de, torch.tensor(target)).backward()
+    d["bf16emu/sed"], d["bf16emu/doa"] = se.detach().numpy(), de.detach().numpy()
+    for k, p in me.named_parameters():
+        if p.grad is not None:
+            d["bf16emu_grad/" + k] = p.grad.numpy().astype(np.float32)
     meta = dict(kind="model", cfg=cfg, time_dim=time_dim, B=B, seed=seed, model_name=m.model_name,
                 n_params=int(sum(p.numel() for p in m.parameters())), n_grads=ngrad,
                 source="model.py:324-480 + train.py:186-204")
@@ -148,6 +170,13 @@ def model_case(name, cfg, time_dim, B, seed):
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
+    only_models = "--models-only" in sys.argv
+    if not only_models:
+        per_op_cases(ns)
+    model_cases()
+
+
+def per_op_cases(ns):
     # per-op fixtures (SURVEY.md 8c suggested shapes, plus stride / bias / odd sizes)
     conv_case(ns, "conv1d_q_k3_d5", "Q", 1, 2, 16, 16, (97,), 3, 1, 5, 5, True, 11)
     conv_case(ns, "conv1d_dq_k3_d5", "DQ", 1, 2, 8, 8, (97,), 3, 1, 5, 5, True, 12)
@@ -168,6 +197,9 @@ def main():
     stft_case(ns, "stft_mag", 8, 6400, 512, 112, False, 41)
     stft_case(ns, "stft_magphase", 8, 6400, 512, 112, True, 42)
     stft_case(ns, "stft_magphase_default", 3, 5000, 512, 128, True, 43)
+
+
+def model_cases():
     # whole-model fixtures
     tiny = dict(ref_import.COMMON)
     tiny.update(input_channels=8, freq_dim=128, domain="DQ", domain_classifier="DQ",

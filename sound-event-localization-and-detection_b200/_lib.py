@@ -49,7 +49,7 @@ _PROTOS = {
     "seldq_conv_out_shape": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_int32),
                                             ctypes.POINTER(ctypes.c_int32)]),
     "seldq_conv_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc), ctypes.c_int32]),
-    "seldq_conv_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P, _P,
+    "seldq_conv_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P,
                                       ctypes.c_size_t, _P]),
     "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P,
                                         ctypes.c_size_t, _P]),
@@ -64,7 +64,11 @@ _PROTOS = {
                                           ctypes.c_size_t, _P]),
     "seldq_cast_bf16": (ctypes.c_int, [_P, _P, ctypes.c_size_t, _P]),
     "seldq_bf16_pitch": (ctypes.c_int, [ctypes.c_int32]),
-    "seldq_cast_bf16_mirror": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P]),
+    "seldq_conv_mirror_shifts": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32,
+                                                ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "seldq_bf16_mirror_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
+    "seldq_cast_bf16_mirror": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                              ctypes.c_int32, _P]),
     "seldq_stft_shape": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                         ctypes.POINTER(ctypes.c_int32)]),
@@ -73,7 +77,7 @@ _PROTOS = {
     "seldq_probe_tensor_map": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32,
                                               ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
                                               ctypes.POINTER(ctypes.c_uint32), ctypes.c_int32]),
-    "seldq_probe_tma_load": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_uint32,
+    "seldq_probe_tma_load": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_uint32,
                                             ctypes.c_uint32, _P, ctypes.c_uint32, _P]),
     "seldq_probe_umma": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_uint32, ctypes.c_uint64,
                                         ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32, ctypes.c_uint32,

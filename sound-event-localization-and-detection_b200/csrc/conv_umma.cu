@@ -21,6 +21,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2..5 = epilogue (TMEM -> registers -> coalesced global stores, + bias, + optional bf16 copy).
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -48,9 +50,11 @@ qconv_umma_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
   const uint32_t stage_bytes = 2u * p.stage_atoms * 1024u;
   const uint32_t half_bytes = p.stage_atoms * 1024u;
   const uint32_t op_bytes = (uint32_t)p.NBp * 32u;            // one [NBp x 16] bf16 B operand
+  // layout: [activation ring][barriers, 1 KB][weight images][slack]; the tensor core may fetch past the
+  // logical end of an operand tile (seen on the bring-up probe), so the images are not the last bytes
   uint8_t* a_ring = smem;
-  uint8_t* b_img = smem + (size_t)p.nstages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_img + (size_t)p.n_img * p.kpairs * op_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstages * stage_bytes);
+  uint8_t* b_img = smem + (size_t)p.nstages * stage_bytes + 1024;
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
@@ -114,12 +118,18 @@ qconv_umma_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
             const int t0 = s * p.G;
             const int nt = min(p.G, p.ntaps - t0);
             ptx::mbar_wait(&empty_bar[slot], parity ^ 1);
-            ptx::mbar_arrive_expect_tx(&full_bar[slot], 2u * nt * p.Rc * 128u);
-            uint8_t* st = a_ring + (size_t)slot * stage_bytes;
-            for (int mh = 0; mh < 2; ++mh)
-              for (int ti = 0; ti < nt; ++ti)
-                ptx::tma_load_4d(st + mh * half_bytes + (size_t)ti * p.Rc * 128, &tm_in, &full_bar[slot],
-                                 w0 + mh * 64 + p.off_w[t0 + ti], h + p.off_h[t0 + ti], b * p.Rc, n);
+            if (p.debug & 2) {
+              ptx::mbar_arrive(&full_bar[slot]);
+            } else {
+              ptx::mbar_arrive_expect_tx(&full_bar[slot], 2u * nt * p.Rc * 128u);
+              uint8_t* st = a_ring + (size_t)slot * stage_bytes;
+              // off_w already contains the tap's mirror shift, so the inner coordinate is a multiple of 8
+              for (int mh = 0; mh < 2; ++mh)
+                for (int ti = 0; ti < nt; ++ti)
+                  ptx::tma_load_5d(st + mh * half_bytes + (size_t)ti * p.Rc * 128, &tm_in, &full_bar[slot],
+                                   w0 + mh * 64 + p.off_w[t0 + ti], h + p.off_h[t0 + ti], b * p.Rc, n,
+                                   p.tap_sidx[t0 + ti]);
+            }
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }
       }
@@ -153,15 +163,18 @@ qconv_umma_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
                 const int oc = p.op_out[b][o];
                 const uint64_t b_desc =
                     ptx::smem_desc(b_hi, b_base + (uint32_t)(p.op_img[b][o] * p.kpairs + kp) * op_bytes);
-                ptx::umma_f16(d_base + (uint32_t)(oc * p.NBp), a_desc, b_desc,
-                              idesc | ((uint32_t)p.op_neg[b][o] << 14), (written >> oc) & 1u);
+                if (!(p.debug & 1))
+                  ptx::umma_f16(d_base + (uint32_t)(oc * p.NBp), a_desc, b_desc,
+                                idesc | ((uint32_t)p.op_neg[b][o] << 14), (written >> oc) & 1u);
                 written |= 1u << oc;
               }
             }
-            ptx::umma_commit(&empty_bar[slot]);    // frees the ring slot once these MMAs retire
+            if (p.debug & 1) ptx::mbar_arrive(&empty_bar[slot]);
+            else ptx::umma_commit(&empty_bar[slot]);    // frees the ring slot once these MMAs retire
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }
-        ptx::umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
+        if (p.debug & 1) ptx::mbar_arrive(&tfull_bar[as]);
+        else ptx::umma_commit(&tfull_bar[as]);     // accumulator complete -> epilogue
       }
     }
   } else {
@@ -187,8 +200,13 @@ qconv_umma_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_
       for (int a = 0; a < p.ncomp_out; ++a)
         for (int c0 = 0; c0 < p.Pc; c0 += 16) {
           uint32_t v[16];
-          ptx::tmem_ld16(t_row + (uint32_t)(a * p.NBp + c0), v);
-          ptx::tmem_ld_wait();
+          if (p.debug & 4) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0;
+          } else {
+            ptx::tmem_ld16(t_row + (uint32_t)(a * p.NBp + c0), v);
+            ptx::tmem_ld_wait();
+          }
           if (w_ok) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -295,37 +313,73 @@ int plan_umma_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
   if (tiles > 0x7fffffffLL) return fail(SELDQ_ERR_UNSUPPORTED, "too many tiles");
   p->total_tiles = (int)tiles;
   const size_t img_bytes = (size_t)p->n_img * p->kpairs * p->NBp * 32;
-  const size_t tail = 256;   // barriers + tmem slot
+  const size_t fixed = 1024 /* barriers */ + img_bytes + 8192 /* slack behind the images */;
   const size_t stage_bytes = 2u * p->stage_atoms * 1024u;
   const size_t budget = 225 * 1024;
-  if (img_bytes + tail + 2 * stage_bytes > budget)
+  if (fixed + 2 * stage_bytes > budget)
     return fail(SELDQ_ERR_UNSUPPORTED, "compact weights (%zu B as bf16) do not fit in shared memory", img_bytes);
-  size_t ns = (budget - img_bytes - tail) / stage_bytes;
+  size_t ns = (budget - fixed) / stage_bytes;
   if (ns > (size_t)umma::kMaxStages) ns = umma::kMaxStages;
   p->nstages = (int)ns;
-  *smem_bytes = ns * stage_bytes + img_bytes + tail;
+  *smem_bytes = ns * stage_bytes + fixed;
   return SELDQ_OK;
 }
 
-int launch_umma_fprop(const ConvGeom& g, const void* in_bf16, int in_pitch_w, const float* const* host_w,
-                      const float* bias, float* out, void* out_bf16, int out16_pitch_w, cudaStream_t st) {
+// shifts[0] = 0; then one entry per distinct (-off_w) mod 8 over the taps of the pass
+void mirror_shifts(const ConvGeom& fwd_geom, int which, int* shifts, int* nshifts) {
+  int n = 0;
+  shifts[n++] = 0;
+  for (int kw = 0; kw < fwd_geom.KW; ++kw) {
+    const int off = which == 0 ? kw * fwd_geom.dw - fwd_geom.pw : fwd_geom.pw - kw * fwd_geom.dw;
+    const int s = ((-off) % 8 + 8) % 8;
+    bool seen = false;
+    for (int i = 0; i < n; ++i) seen |= shifts[i] == s;
+    if (!seen && n < 8) shifts[n++] = s;
+  }
+  *nshifts = n;
+}
+
+// fills tap_sidx / folds the shift into off_w; false if the mirror set lacks a needed shift
+static bool bind_mirror(const MirrorSet& m, int ntaps, const int* off_w_in, int* off_w_out, int* tap_sidx) {
+  for (int t = 0; t < ntaps; ++t) {
+    const int s = ((-off_w_in[t]) % 8 + 8) % 8;
+    int idx = -1;
+    for (int i = 0; i < m.nshifts; ++i)
+      if (m.shifts[i] == s) idx = i;
+    if (idx < 0) return false;
+    tap_sidx[t] = idx;
+    off_w_out[t] = off_w_in[t] + s;
+  }
+  return true;
+}
+
+// (W, H, C, N, shift) view of a mirror set with box {64, 1, rows, 1, 1}, 128-byte swizzle
+int encode_mirror_map(CUtensorMap* tm, const MirrorSet& m, int w, int h, int c, int n, int box_rows) {
+  const uint64_t pitch = (uint64_t)mirror_pitch(w);
+  const uint64_t dims[5] = {pitch, (uint64_t)h, (uint64_t)c, (uint64_t)n, (uint64_t)m.nshifts};
+  const uint64_t strides[4] = {pitch * 2, pitch * h * 2, pitch * h * c * 2, pitch * h * c * n * 2};
+  const uint32_t box[5] = {64, 1, (uint32_t)box_rows, 1, 1};
+  return encode_tensor_map(tm, m.data, 2, 5, dims, strides, box, /*128B*/ 3);
+}
+
+int launch_umma_fprop(const ConvGeom& g, const MirrorSet& in, const float* const* host_w, const float* bias,
+                      float* out, cudaStream_t st) {
   FpropParams p;
   size_t smem = 0;
   int rc = plan_umma_fprop(g, &p, &smem);
   if (rc) return rc;
   for (int i = 0; i < g.tab.nw; ++i) p.w[i] = host_w[i];
+  if (const char* dbg = getenv("SELDQ_DEBUG")) p.debug = atoi(dbg);
   p.bias = bias;
   p.out = out;
   p.out_sN = g.out_sN; p.out_sC = g.out_sC; p.out_sH = g.out_sH;
-  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  p.o16_sH = out16_pitch_w; p.o16_sC = (long long)g.OH * out16_pitch_w; p.o16_sN = (long long)g.P * p.o16_sC;
-  // activation tensor of this pass as (W, H, C, N), bf16, row pitch in_pitch_w (multiple of 8 elements)
+  p.out_bf16 = nullptr;
+  int off_w[umma::kMaxTaps];
+  for (int t = 0; t < p.ntaps; ++t) off_w[t] = p.off_w[t];
+  if (!bind_mirror(in, p.ntaps, off_w, p.off_w, p.tap_sidx))
+    return fail(SELDQ_ERR_INVALID, "bf16 mirror set lacks a shift this convolution's taps need");
   alignas(64) CUtensorMap tm;
-  const uint64_t dims[4] = {(uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.R, (uint64_t)g.N};
-  const uint64_t strides[3] = {(uint64_t)in_pitch_w * 2, (uint64_t)in_pitch_w * g.IH * 2,
-                               (uint64_t)in_pitch_w * g.IH * g.R * 2};
-  const uint32_t box[4] = {64, 1, (uint32_t)p.Rc, 1};
-  rc = encode_tensor_map(&tm, in_bf16, 2, 4, dims, strides, box, /*128B*/ 3);
+  rc = encode_mirror_map(&tm, in, g.IW, g.IH, g.R, g.N, p.Rc);
   if (rc) return rc;
   cudaError_t e = cudaFuncSetAttribute(umma::qconv_umma_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);

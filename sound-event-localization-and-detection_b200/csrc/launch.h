@@ -26,7 +26,8 @@ int launch_wgrad_simt(simt::WgradParams& p, cudaStream_t st);
 int launch_bias_grad(const float* gy, float* gb, int C, int N, int H, int W, long long sN, long long sC, long long sH,
                      long long sW, cudaStream_t st);
 int launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
-int launch_cast_bf16_rows(const float* src, void* dst, long long rows, int w, int pitch, cudaStream_t st);
+int launch_cast_bf16_mirror(const float* src, void* dst, long long rows, int w, int pitch, const int* shifts,
+                            int nshifts, cudaStream_t st);
 int launch_stft(const stft::Params& p, int n_signals, cudaStream_t st);
 
 }  // namespace seldq

@@ -11,11 +11,11 @@ using namespace seldq;
 
 namespace {
 
-inline int pitch8(int w) { return (w + 7) & ~7; }
-
-size_t bf16_mirror_bytes(int n, int c, int h, int w) { return (size_t)n * c * h * pitch8(w) * 2; }
-
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t mirror_bytes(long long rows, int w, int nshifts) {
+  return align256((size_t)nshifts * (size_t)rows * mirror_pitch(w) * 2);
+}
 
 int cuda_ready() {
   int n = 0;
@@ -26,10 +26,33 @@ int cuda_ready() {
   return SELDQ_OK;
 }
 
-// fp32 (rows, w) -> bf16 (rows, pitch8(w)); the pad columns are zeroed
-int cast_mirror(const float* src, void* dst, long long rows, int w, cudaStream_t st) {
-  if (w % 8 == 0) return launch_cast_bf16(src, dst, (size_t)rows * w, st);
-  return launch_cast_bf16_rows(src, dst, rows, w, pitch8(w), st);
+// forward-orientation geometry (tap offsets are defined on it) + the shift list of one operand
+int shifts_for(const seldq_conv_desc_t* d, int which, MirrorSet* m) {
+  ConvGeom g;
+  const int rc = make_conv_geom(d, SELDQ_PASS_FWD, &g);
+  if (rc) return rc;
+  mirror_shifts(g, which, m->shifts, &m->nshifts);
+  return SELDQ_OK;
+}
+
+// uses the caller's mirror set if given, otherwise builds it in the workspace at *offset
+int obtain_mirror(const seldq_conv_desc_t* d, int which, const float* src, const void* given, long long rows, int w,
+                  void* workspace, size_t workspace_bytes, size_t* offset, cudaStream_t st, MirrorSet* m) {
+  int rc = shifts_for(d, which, m);
+  if (rc) return rc;
+  if (given) {
+    m->data = given;
+    return SELDQ_OK;
+  }
+  const size_t need = mirror_bytes(rows, w, m->nshifts);
+  if (!workspace || *offset + need > workspace_bytes)
+    return fail(SELDQ_ERR_WORKSPACE, "workspace too small for the bf16 mirror set (%zu + %zu > %zu)", *offset, need,
+                workspace_bytes);
+  void* dst = (char*)workspace + *offset;
+  if ((rc = launch_cast_bf16_mirror(src, dst, rows, w, mirror_pitch(w), m->shifts, m->nshifts, st))) return rc;
+  m->data = dst;
+  *offset += need;
+  return SELDQ_OK;
 }
 
 }  // namespace
@@ -45,8 +68,6 @@ extern "C" int seldq_device_count(void) {
   return n;
 }
 
-extern "C" int seldq_bf16_pitch(int32_t w) { return pitch8(w); }
-
 extern "C" int seldq_conv_out_shape(const seldq_conv_desc_t* d, int32_t* out_h, int32_t* out_w) {
   BlockTable t;
   int oh, ow;
@@ -57,19 +78,35 @@ extern "C" int seldq_conv_out_shape(const seldq_conv_desc_t* d, int32_t* out_h, 
   return SELDQ_OK;
 }
 
-extern "C" size_t seldq_conv_workspace_bytes(const seldq_conv_desc_t* d, int32_t pass) {
-  BlockTable t;
-  int oh, ow;
-  if (validate_conv(d, &t, &oh, &ow)) return 0;
-  if (d->precision != SELDQ_PREC_BF16) return 0;
-  const size_t xb = align256(bf16_mirror_bytes(d->batch, d->cin, d->in_h, d->in_w));
-  const size_t yb = align256(bf16_mirror_bytes(d->batch, d->cout, oh, ow));
-  switch (pass) {
-    case SELDQ_PASS_FWD: return xb;
-    case SELDQ_PASS_DGRAD: return yb;
-    case SELDQ_PASS_WGRAD: return xb + yb;
-    default: return 0;
-  }
+// ---- bf16 mirror sets ---------------------------------------------------------------------------------
+extern "C" int seldq_bf16_pitch(int32_t w) { return mirror_pitch(w); }
+
+extern "C" int seldq_conv_mirror_shifts(const seldq_conv_desc_t* d, int32_t which, int32_t* shifts8, int32_t* nshifts) {
+  if (!shifts8 || !nshifts || (which != 0 && which != 1)) return fail(SELDQ_ERR_INVALID, "bad mirror-shift query");
+  MirrorSet m;
+  const int rc = shifts_for(d, which, &m);
+  if (rc) return rc;
+  for (int i = 0; i < m.nshifts; ++i) shifts8[i] = m.shifts[i];
+  *nshifts = m.nshifts;
+  return SELDQ_OK;
+}
+
+extern "C" size_t seldq_bf16_mirror_bytes(int64_t rows, int32_t w, int32_t nshifts) {
+  if (rows <= 0 || w <= 0 || nshifts <= 0) return 0;
+  return mirror_bytes(rows, w, nshifts);
+}
+
+extern "C" int seldq_cast_bf16_mirror(const float* src, void* dst_bf16, int64_t rows, int32_t w, const int32_t* shifts,
+                                      int32_t nshifts, void* stream) {
+  if (!src || !dst_bf16 || rows <= 0 || w <= 0 || !shifts || nshifts < 1 || nshifts > 8 || shifts[0] != 0)
+    return fail(SELDQ_ERR_INVALID, "seldq_cast_bf16_mirror: bad arguments (shifts[0] must be 0, at most 8 shifts)");
+  for (int i = 0; i < nshifts; ++i)
+    if (shifts[i] < 0 || shifts[i] > 7) return fail(SELDQ_ERR_INVALID, "mirror shifts must be in [0, 8)");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  int s[8];
+  for (int i = 0; i < nshifts; ++i) s[i] = shifts[i];
+  return launch_cast_bf16_mirror(src, dst_bf16, rows, w, mirror_pitch(w), s, nshifts, (cudaStream_t)stream);
 }
 
 extern "C" int seldq_cast_bf16(const float* src, void* dst_bf16, size_t n, void* stream) {
@@ -79,15 +116,26 @@ extern "C" int seldq_cast_bf16(const float* src, void* dst_bf16, size_t n, void*
   return launch_cast_bf16(src, dst_bf16, n, (cudaStream_t)stream);
 }
 
-extern "C" int seldq_cast_bf16_mirror(const float* src, void* dst_bf16, int64_t rows, int32_t w, void* stream) {
-  if (!src || !dst_bf16 || rows <= 0 || w <= 0) return fail(SELDQ_ERR_INVALID, "seldq_cast_bf16_mirror: bad arguments");
-  int rc = cuda_ready();
-  if (rc) return rc;
-  return cast_mirror(src, dst_bf16, rows, w, (cudaStream_t)stream);
+extern "C" size_t seldq_conv_workspace_bytes(const seldq_conv_desc_t* d, int32_t pass) {
+  BlockTable t;
+  int oh, ow;
+  if (validate_conv(d, &t, &oh, &ow)) return 0;
+  if (d->precision != SELDQ_PREC_BF16) return 0;
+  MirrorSet mx, mg;
+  if (shifts_for(d, 0, &mx) || shifts_for(d, 1, &mg)) return 0;
+  const size_t xb = mirror_bytes((long long)d->batch * d->cin * d->in_h, d->in_w, mx.nshifts);
+  const size_t gb = mirror_bytes((long long)d->batch * d->cout * oh, ow, mg.nshifts);
+  switch (pass) {
+    case SELDQ_PASS_FWD: return xb;
+    case SELDQ_PASS_DGRAD: return gb;
+    case SELDQ_PASS_WGRAD: return xb + gb;
+    default: return 0;
+  }
 }
 
+// ---- convolution ------------------------------------------------------------------------------------
 extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_bf16,
-                              const float* const* host_w, const float* bias, float* y, void* y_bf16, void* workspace,
+                              const float* const* host_w, const float* bias, float* y, void* workspace,
                               size_t workspace_bytes, void* stream) {
   ConvGeom g;
   int rc = make_conv_geom(d, SELDQ_PASS_FWD, &g);
@@ -98,21 +146,18 @@ extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const 
     if (!host_w[i]) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: weight %d is null", i);
   if ((rc = cuda_ready())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->precision == SELDQ_PREC_FP32) {
+  if (!bf16) {
     simt::ConvParams p{};
     p.g = g; p.in = x; p.out = y; p.bias = bias;
     for (int i = 0; i < g.tab.nw; ++i) p.w[i] = host_w[i];
     return launch_conv_simt(p, st);
   }
-  const void* xb = x_bf16;
-  if (!xb) {
-    if (workspace_bytes < seldq_conv_workspace_bytes(d, SELDQ_PASS_FWD) || !workspace)
-      return fail(SELDQ_ERR_WORKSPACE, "seldq_conv_fwd: workspace too small (%zu < %zu)", workspace_bytes,
-                  seldq_conv_workspace_bytes(d, SELDQ_PASS_FWD));
-    if ((rc = cast_mirror(x, workspace, (long long)d->batch * d->cin * d->in_h, d->in_w, st))) return rc;
-    xb = workspace;
-  }
-  return launch_umma_fprop(g, xb, pitch8(d->in_w), host_w, bias, y, y_bf16, pitch8(g.OW), st);
+  MirrorSet mx;
+  size_t off = 0;
+  if ((rc = obtain_mirror(d, 0, x, x_bf16, (long long)d->batch * d->cin * d->in_h, d->in_w, workspace, workspace_bytes,
+                          &off, st, &mx)))
+    return rc;
+  return launch_umma_fprop(g, mx, host_w, bias, y, st);
 }
 
 extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy_bf16,
@@ -125,20 +170,18 @@ extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, con
   if (!host_w || !gx || (!gy && !(bf16 && gy_bf16))) return fail(SELDQ_ERR_INVALID, "seldq_conv_dgrad: null pointer");
   if ((rc = cuda_ready())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->precision == SELDQ_PREC_FP32) {
+  if (!bf16) {
     simt::ConvParams p{};
     p.g = g; p.in = gy; p.out = gx; p.bias = nullptr;
     for (int i = 0; i < g.tab.nw; ++i) p.w[i] = host_w[i];
     return launch_conv_simt(p, st);
   }
-  const void* gb = gy_bf16;
-  if (!gb) {
-    if (workspace_bytes < seldq_conv_workspace_bytes(d, SELDQ_PASS_DGRAD) || !workspace)
-      return fail(SELDQ_ERR_WORKSPACE, "seldq_conv_dgrad: workspace too small");
-    if ((rc = cast_mirror(gy, workspace, (long long)d->batch * d->cout * g.IH, g.IW, st))) return rc;
-    gb = workspace;
-  }
-  return launch_umma_fprop(g, gb, pitch8(g.IW), host_w, nullptr, gx, nullptr, 0, st);
+  MirrorSet mg;
+  size_t off = 0;
+  if ((rc = obtain_mirror(d, 1, gy, gy_bf16, (long long)d->batch * d->cout * g.IH, g.IW, workspace, workspace_bytes,
+                          &off, st, &mg)))
+    return rc;
+  return launch_umma_fprop(g, mg, host_w, nullptr, gx, st);
 }
 
 extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_bf16, const float* gy,
@@ -160,29 +203,21 @@ extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, cons
   }
   if (gbias && (rc = launch_bias_grad(gy, gbias, g.P, g.N, g.OH, g.OW, g.out_sN, g.out_sC, g.out_sH, g.out_sW, st)))
     return rc;
-  if (d->precision == SELDQ_PREC_FP32) {
+  if (!bf16) {
     simt::WgradParams p{};
     p.g = g; p.x = x; p.gy = gy;
     for (int i = 0; i < g.tab.nw; ++i) p.gw[i] = host_gw[i];
     return launch_wgrad_simt(p, st);
   }
-  const size_t xbytes = align256(bf16_mirror_bytes(d->batch, d->cin, d->in_h, d->in_w));
-  const void* xb = x_bf16;
-  const void* gb = gy_bf16;
-  if (!xb || !gb) {
-    if (workspace_bytes < seldq_conv_workspace_bytes(d, SELDQ_PASS_WGRAD) || !workspace)
-      return fail(SELDQ_ERR_WORKSPACE, "seldq_conv_wgrad: workspace too small");
-    if (!xb) {
-      if ((rc = cast_mirror(x, workspace, (long long)d->batch * d->cin * d->in_h, d->in_w, st))) return rc;
-      xb = workspace;
-    }
-    if (!gb) {
-      void* dst = (char*)workspace + xbytes;
-      if ((rc = cast_mirror(gy, dst, (long long)d->batch * d->cout * g.OH, g.OW, st))) return rc;
-      gb = dst;
-    }
-  }
-  return launch_umma_wgrad(g, xb, pitch8(d->in_w), gb, pitch8(g.OW), host_gw, st);
+  MirrorSet mx, mg;
+  size_t off = 0;
+  if ((rc = obtain_mirror(d, 0, x, x_bf16, (long long)d->batch * d->cin * d->in_h, d->in_w, workspace, workspace_bytes,
+                          &off, st, &mx)))
+    return rc;
+  if ((rc = obtain_mirror(d, 1, gy, gy_bf16, (long long)d->batch * d->cout * g.OH, g.OW, workspace, workspace_bytes,
+                          &off, st, &mg)))
+    return rc;
+  return launch_umma_wgrad(g, mx, mg, host_gw, st);
 }
 
 // ---- linear: 0.18 GFLOP per call in the reference configs -> always the fp32 FFMA kernels -----------

@@ -89,16 +89,30 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     dst[i] = __float2bfloat16_rn(src[i]);
 }
 
-// fp32 (rows, w) -> bf16 (rows, pitch) with zeroed pad columns (rows whose length is not a multiple of 8)
-__global__ void __launch_bounds__(256) cast_bf16_rows_kernel(const float* __restrict__ src,
-                                                             __nv_bfloat16* __restrict__ dst, long long rows, int w,
-                                                             int pitch) {
-  const long long total = rows * pitch;
+// fp32 (rows, w) -> bf16 mirror set [nshifts][rows][pitch]: copy k holds the row shifted right by
+// shifts[k] elements with zeros shifted in and zero padding up to the pitch (conv_umma.h: MirrorSet).
+// One thread produces one 16-byte chunk (8 elements) of one copy.
+struct MirrorShifts { int v[8]; };
+__global__ void __launch_bounds__(256) cast_bf16_mirror_kernel(const float* __restrict__ src,
+                                                               __nv_bfloat16* __restrict__ dst, long long rows, int w,
+                                                               int pitch, MirrorShifts shifts, int nshifts) {
+  const int cpr = pitch >> 3;                                   // chunks per row
+  const long long per_copy = rows * cpr;
+  const long long total = per_copy * nshifts;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long r = i / pitch;
-    const int c = (int)(i - r * pitch);
-    dst[i] = __float2bfloat16_rn(c < w ? src[r * w + c] : 0.f);
+    const int k = (int)(i / per_copy);
+    const long long r = (i - k * per_copy) / cpr;
+    const int chunk = (int)(i - k * per_copy - r * cpr);
+    const int c0 = chunk * 8 - shifts.v[k];
+    const float* s = src + r * w;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      v[j] = __float2bfloat16_rn((c >= 0 && c < w) ? __ldg(s + c) : 0.f);
+    }
+    reinterpret_cast<uint4*>(dst)[i] = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -150,12 +164,17 @@ int launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st) {
   return check_launch("cast_bf16_kernel");
 }
 
-int launch_cast_bf16_rows(const float* src, void* dst, long long rows, int w, int pitch, cudaStream_t st) {
-  long long blocks = (rows * pitch + 255) / 256;
+int launch_cast_bf16_mirror(const float* src, void* dst, long long rows, int w, int pitch, const int* shifts,
+                            int nshifts, cudaStream_t st) {
+  if (reinterpret_cast<uintptr_t>(dst) & 15) return fail(SELDQ_ERR_INVALID, "bf16 mirror buffer must be 16-byte aligned");
+  simt::MirrorShifts s{};
+  for (int i = 0; i < nshifts; ++i) s.v[i] = shifts[i];
+  long long blocks = (rows * (pitch / 8) * nshifts + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  simt::cast_bf16_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), rows, w,
-                                                               pitch);
-  return check_launch("cast_bf16_rows_kernel");
+  if (blocks < 1) blocks = 1;
+  simt::cast_bf16_mirror_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), rows, w,
+                                                                 pitch, s, nshifts);
+  return check_launch("cast_bf16_mirror_kernel");
 }
 
 }  // namespace seldq

@@ -4,6 +4,8 @@
 //                            TMEM -> dump (checks descriptor semantics: major-ness, LBO/SBO, swizzle,
 //                            negate bits) without recompiling
 // They expose hardware behaviour only; nothing in the product path calls them.
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -16,9 +18,11 @@ namespace probe {
 
 constexpr uint32_t kSmemBytes = 96 * 1024;
 
-__global__ void __launch_bounds__(32) tma_load_kernel(const __grid_constant__ CUtensorMap map, int rank, int c0, int c1,
+__global__ void __launch_bounds__(32) tma_load_kernel(const __grid_constant__ CUtensorMap map_param,
+                                                     const CUtensorMap* map_global, int rank, int c0, int c1,
                                                      int c2, int c3, uint32_t box_bytes, uint32_t smem_offset,
                                                      uint32_t* out, uint32_t dump_words) {
+  const CUtensorMap* mapp = map_global ? map_global : &map_param;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   uint32_t* w = reinterpret_cast<uint32_t*>(smem);
@@ -31,8 +35,8 @@ __global__ void __launch_bounds__(32) tma_load_kernel(const __grid_constant__ CU
   __syncwarp();
   if (threadIdx.x == 0) {
     ptx::mbar_arrive_expect_tx(&bar, box_bytes);
-    if (rank == 2) ptx::tma_load_2d(smem + smem_offset, &map, &bar, c0, c1);
-    else ptx::tma_load_4d(smem + smem_offset, &map, &bar, c0, c1, c2, c3);
+    if (rank == 2) ptx::tma_load_2d(smem + smem_offset, mapp, &bar, c0, c1);
+    else ptx::tma_load_4d(smem + smem_offset, mapp, &bar, c0, c1, c2, c3);
   }
   ptx::mbar_wait(&bar, 0);
   __syncwarp();
@@ -42,7 +46,7 @@ __global__ void __launch_bounds__(32) tma_load_kernel(const __grid_constant__ CU
 __global__ void __launch_bounds__(128) umma_kernel(const uint4* a_image, uint32_t a_bytes, const uint4* b_image,
                                                   uint32_t b_bytes, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                   int n_mma, uint32_t a_step, uint32_t b_step, int n_cols,
-                                                  uint32_t tmem_cols, float* out) {
+                                                  uint32_t tmem_cols, float* out, int flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -51,7 +55,7 @@ __global__ void __launch_bounds__(128) umma_kernel(const uint4* a_image, uint32_
   for (uint32_t i = threadIdx.x; i < a_bytes / 16; i += 128) reinterpret_cast<uint4*>(a_smem)[i] = a_image[i];
   for (uint32_t i = threadIdx.x; i < b_bytes / 16; i += 128) reinterpret_cast<uint4*>(b_smem)[i] = b_image[i];
   ptx::fence_proxy_async();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 32) {
     ptx::mbar_init(&bar, 1);
     ptx::fence_barrier_init();
   }
@@ -63,17 +67,21 @@ __global__ void __launch_bounds__(128) umma_kernel(const uint4* a_image, uint32_
   if (threadIdx.x == 0) {
     const uint64_t ad = a_desc + (uint64_t)(ptx::smem_u32(a_smem) >> 4);
     const uint64_t bd = b_desc + (uint64_t)(ptx::smem_u32(b_smem) >> 4);
-    for (int i = 0; i < n_mma; ++i)
-      ptx::umma_f16(tbase, ad + (uint64_t)i * a_step, bd + (uint64_t)i * b_step, idesc, i > 0 ? 1u : 0u);
-    ptx::umma_commit(&bar);
+    if (!(flags & 1))
+      for (int i = 0; i < n_mma; ++i)
+        ptx::umma_f16(tbase, ad + (uint64_t)i * a_step, bd + (uint64_t)i * b_step, idesc, i > 0 ? 1u : 0u);
+    if (flags & 2) ptx::mbar_arrive(&bar);
+    else ptx::umma_commit(&bar);
   }
   ptx::mbar_wait(&bar, 0);
   ptx::tc_fence_after();
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = 0; c < n_cols; c += 8) {
-    uint32_t r[8];
-    ptx::tmem_ld8(tbase + ((warp * 32u) << 16) + (uint32_t)c, r);
-    ptx::tmem_ld_wait();
+    uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!(flags & 4)) {
+      ptx::tmem_ld8(tbase + ((warp * 32u) << 16) + (uint32_t)c, r);
+      ptx::tmem_ld_wait();
+    }
     for (int j = 0; j < 8; ++j)
       if (c + j < n_cols) out[(warp * 32 + lane) * n_cols + c + j] = __uint_as_float(r[j]);
   }
@@ -98,8 +106,9 @@ extern "C" int seldq_probe_tensor_map(void* host_map_128B, const void* gaddr, in
   return SELDQ_OK;
 }
 
-extern "C" int seldq_probe_tma_load(const void* host_map_128B, int32_t rank, const int32_t* coords, uint32_t box_bytes,
-                                    uint32_t smem_offset, void* out_smem_dump, uint32_t dump_bytes, void* stream) {
+extern "C" int seldq_probe_tma_load(const void* host_map_128B, const void* dev_map_128B, int32_t rank,
+                                    const int32_t* coords, uint32_t box_bytes, uint32_t smem_offset,
+                                    void* out_smem_dump, uint32_t dump_bytes, void* stream) {
   if (rank != 2 && rank != 4) return fail(SELDQ_ERR_INVALID, "tma probe supports rank 2 and 4");
   if (smem_offset + box_bytes > probe::kSmemBytes || dump_bytes > probe::kSmemBytes)
     return fail(SELDQ_ERR_INVALID, "tma probe exceeds its %u byte window", probe::kSmemBytes);
@@ -109,7 +118,8 @@ extern "C" int seldq_probe_tma_load(const void* host_map_128B, int32_t rank, con
                                        (int)probe::kSmemBytes);
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "probe smem opt-in: %s", cudaGetErrorString(e));
   probe::tma_load_kernel<<<1, 32, probe::kSmemBytes, (cudaStream_t)stream>>>(
-      m, rank, coords[0], coords[1], rank > 2 ? coords[2] : 0, rank > 3 ? coords[3] : 0, box_bytes, smem_offset,
+      m, (const CUtensorMap*)dev_map_128B, rank, coords[0], coords[1], rank > 2 ? coords[2] : 0,
+      rank > 3 ? coords[3] : 0, box_bytes, smem_offset,
       (uint32_t*)out_smem_dump, dump_bytes / 4);
   return check_launch("probe::tma_load_kernel");
 }
@@ -119,14 +129,16 @@ extern "C" int seldq_probe_umma(const void* a_image, uint32_t a_bytes, const voi
                                 uint32_t b_desc_step, int32_t n_cols, float* out_128xN, void* stream) {
   if ((a_bytes & 15) || (b_bytes & 15) || n_cols < 8 || n_cols > 512)
     return fail(SELDQ_ERR_INVALID, "bad umma probe arguments");
-  const uint32_t smem = ((a_bytes + 1023) & ~1023u) + b_bytes + 1024;
-  if (smem > 200 * 1024) return fail(SELDQ_ERR_INVALID, "umma probe images too large");
+  // generous window: a wrong descriptor hypothesis should read garbage, not fault
+  const uint32_t smem = 160 * 1024;
+  if (((a_bytes + 1023) & ~1023u) + b_bytes > smem) return fail(SELDQ_ERR_INVALID, "umma probe images too large");
   uint32_t cols = 32;
   while (cols < (uint32_t)n_cols) cols <<= 1;
   cudaError_t e = cudaFuncSetAttribute(probe::umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "probe smem opt-in: %s", cudaGetErrorString(e));
   probe::umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const uint4*)a_image, a_bytes, (const uint4*)b_image,
                                                             b_bytes, a_desc, b_desc, idesc, n_mma, a_desc_step,
-                                                            b_desc_step, n_cols, cols, out_128xN);
+                                                            b_desc_step, n_cols, cols, out_128xN,
+                                                            getenv("SELDQ_DEBUG") ? atoi(getenv("SELDQ_DEBUG")) : 0);
   return check_launch("probe::umma_kernel");
 }

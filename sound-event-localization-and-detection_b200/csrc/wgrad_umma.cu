@@ -81,12 +81,14 @@ qconv_umma_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_c
           ptx::mbar_arrive_expect_tx(&full_bar[slot], a_bytes + (uint32_t)ntap * b_bytes);
           uint8_t* st = smem + (size_t)slot * stage_bytes;
           for (int a = 0; a < p.ncomp; ++a)
-            ptx::tma_load_4d(st + (size_t)a * p.OS * 128, &tm_g, &full_bar[slot], w0, h,
-                             p.dense ? o0 : a * p.g.Oc + o0, n);
+            ptx::tma_load_5d(st + (size_t)a * p.OS * 128, &tm_g, &full_bar[slot], w0, h,
+                             p.dense ? o0 : a * p.g.Oc + o0, n, 0);
+          // off_w already contains the tap's mirror shift: the inner coordinate is a multiple of 8
           for (int t = 0; t < ntap; ++t)
             for (int b = 0; b < p.ncomp; ++b)
-              ptx::tma_load_4d(st + a_bytes + (size_t)t * b_bytes + (size_t)b * p.IS * 128, &tm_x, &full_bar[slot],
-                               w0 + p.off_w[tap0 + t], h + p.off_h[tap0 + t], p.dense ? i0 : b * p.g.Ic + i0, n);
+              ptx::tma_load_5d(st + a_bytes + (size_t)t * b_bytes + (size_t)b * p.IS * 128, &tm_x, &full_bar[slot],
+                               w0 + p.off_w[tap0 + t], h + p.off_h[tap0 + t], p.dense ? i0 : b * p.g.Ic + i0, n,
+                               p.tap_sidx[tap0 + t]);
           if (++slot == (uint32_t)nstages) { slot = 0; parity ^= 1; }
         }
       }
@@ -199,8 +201,8 @@ int num_sms() {
 
 }  // namespace umma
 
-int launch_umma_wgrad(const ConvGeom& g, const void* x_bf16, int x_pitch_w, const void* gy_bf16, int gy_pitch_w,
-                      float* const* host_gw, cudaStream_t st) {
+int launch_umma_wgrad(const ConvGeom& g, const MirrorSet& x, const MirrorSet& gy, float* const* host_gw,
+                      cudaStream_t st) {
   using namespace umma;
   if (g.sh != 1 || g.sw != 1) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 tensor-core path implements stride 1 only");
   const int ntaps = g.KH * g.KW;
@@ -269,24 +271,24 @@ int launch_umma_wgrad(const ConvGeom& g, const void* x_bf16, int x_pitch_w, cons
   size_t smem = ns * stage_bytes;
   const size_t stg = (size_t)128 * (p.NW + 1) * 4;
   if (smem < stg) smem = stg;
+  smem += 8192;   // slack: the tensor core may fetch past the logical end of the last operand tile
 
+  // x is read at the taps' offsets through its shifted mirrors, gy unshifted (mirror 0)
+  for (int t = 0; t < ntaps; ++t) {
+    const int s = ((-p.off_w[t]) % 8 + 8) % 8;
+    int idx = -1;
+    for (int i = 0; i < x.nshifts; ++i)
+      if (x.shifts[i] == s) idx = i;
+    if (idx < 0) return fail(SELDQ_ERR_INVALID, "bf16 mirror set of x lacks shift %d needed by tap %d", s, t);
+    p.tap_sidx[t] = idx;
+    p.off_w[t] += s;
+  }
+  if (gy.nshifts < 1 || gy.shifts[0] != 0) return fail(SELDQ_ERR_INVALID, "bf16 mirror set of gy must start with shift 0");
   alignas(64) CUtensorMap tm_g, tm_x;
-  {
-    const uint64_t dims[4] = {(uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.P, (uint64_t)g.N};
-    const uint64_t str[3] = {(uint64_t)gy_pitch_w * 2, (uint64_t)gy_pitch_w * g.OH * 2,
-                             (uint64_t)gy_pitch_w * g.OH * g.P * 2};
-    const uint32_t box[4] = {64, 1, (uint32_t)p.OS, 1};
-    const int rc = encode_tensor_map(&tm_g, gy_bf16, 2, 4, dims, str, box, 3);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t dims[4] = {(uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.R, (uint64_t)g.N};
-    const uint64_t str[3] = {(uint64_t)x_pitch_w * 2, (uint64_t)x_pitch_w * g.IH * 2,
-                             (uint64_t)x_pitch_w * g.IH * g.R * 2};
-    const uint32_t box[4] = {64, 1, (uint32_t)p.IS, 1};
-    const int rc = encode_tensor_map(&tm_x, x_bf16, 2, 4, dims, str, box, 3);
-    if (rc) return rc;
-  }
+  int rc = encode_mirror_map(&tm_g, gy, g.OW, g.OH, g.P, g.N, p.OS);
+  if (rc) return rc;
+  rc = encode_mirror_map(&tm_x, x, g.IW, g.IH, g.R, g.N, p.IS);
+  if (rc) return rc;
   cudaError_t e = cudaFuncSetAttribute(qconv_umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "wgrad smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
   dim3 grid(tiles, p.splits);

@@ -41,6 +41,48 @@ def precision(name):
         set_precision(prev)
 
 
+# ---- optional per-kernel timing (bench.py): CUDA events around each C-ABI call on the launching stream
+_PROF = None
+
+
+def profile_reset(enable=True):
+    global _PROF
+    _PROF = {"calls": [], "launches": 0} if enable else None
+
+
+def _timed(kernel, flop, launches, fn):
+    """Runs fn() (one C-ABI call); when profiling, brackets it with events and books `launches`
+    kernel launches and `flop` algorithmic FLOPs under `kernel`."""
+    if _PROF is None:
+        return fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = fn()
+    b.record()
+    _PROF["calls"].append((kernel, flop, a, b))
+    _PROF["launches"] += launches
+    return out
+
+
+def profile_collect():
+    """{'launches': total kernel launches, 'kernels': {name: {ms, flop, launches}}} since profile_reset."""
+    torch.cuda.synchronize()
+    out = {"launches": 0 if _PROF is None else _PROF["launches"], "kernels": {}}
+    for kernel, flop, a, b in ([] if _PROF is None else _PROF["calls"]):
+        k = out["kernels"].setdefault(kernel, {"name": kernel, "ms": 0.0, "flop": 0.0, "launches": 0})
+        k["ms"] += a.elapsed_time(b)
+        k["flop"] += flop
+        k["launches"] += 1
+    return out
+
+
+def _conv_flop(desc, oh, ow):
+    """Algorithmic FLOPs of one pass: only the non-zero blocks of the expanded weight count
+    (DQ: 0.75 of dense)."""
+    nz = 0.75 if desc.algebra == ALG_DQ else 1.0
+    return 2.0 * nz * desc.cout * desc.cin * desc.k_h * desc.k_w * desc.batch * oh * ow
+
+
 def _require_cuda_f32(t, what):
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a tensor" % what)
@@ -66,18 +108,32 @@ def _pair(v):
     return int(v), int(v)
 
 
-def bf16_mirror(x):
-    """bf16 copy of an NCW / NCHW fp32 tensor in the layout the tensor-core kernels read through
-    TMA: same dimension order, row pitch rounded up to 8 elements (see include/seldq.h)."""
+def bf16_mirror(x, shifts=(0,)):
+    """bf16 mirror set of an NCW / NCHW fp32 tensor in the layout the tensor-core kernels read
+    through TMA: one copy per entry of `shifts` (row shifted right by that many elements), row
+    pitch seldq_bf16_pitch(w) (see include/seldq.h).  Returns a (len(shifts), *x.shape[:-1], pitch)
+    bf16 tensor."""
+    import ctypes
     _require_cuda_f32(x, "input")
     x = x.contiguous()
     w = x.shape[-1]
-    pitch = _lib.lib().seldq_bf16_pitch(w)
-    out = torch.empty(x.shape[:-1] + (pitch,), dtype=torch.bfloat16, device=x.device)
+    L = _lib.lib()
+    pitch = L.seldq_bf16_pitch(w)
+    out = torch.empty((len(shifts),) + tuple(x.shape[:-1]) + (pitch,), dtype=torch.bfloat16, device=x.device)
     rows = x.numel() // w
+    arr = (ctypes.c_int32 * len(shifts))(*shifts)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().seldq_cast_bf16_mirror(x.data_ptr(), out.data_ptr(), rows, w, _stream()))
+        _timed("cast_bf16_mirror_kernel", 0.0, 1, lambda: _lib.check(
+            L.seldq_cast_bf16_mirror(x.data_ptr(), out.data_ptr(), rows, w, arr, len(shifts), _stream())))
     return out
+
+
+def _mirror_shifts(desc, which):
+    import ctypes
+    arr = (ctypes.c_int32 * 8)()
+    n = ctypes.c_int32()
+    _lib.check(_lib.lib().seldq_conv_mirror_shifts(ctypes.byref(desc), which, arr, ctypes.byref(n)))
+    return tuple(arr[i] for i in range(n.value))
 
 
 def _conv_desc(algebra, prec, x_shape, cout, ksize, stride, padding, dilation):
@@ -124,10 +180,13 @@ class _BlockConv(torch.autograd.Function):
         y = torch.empty(out_shape, dtype=torch.float32, device=x.device)
         wp = _lib.ptr_array([w.data_ptr() for w in weights])
         with torch.cuda.device(x.device):
-            x16 = bf16_mirror(x) if prec == PREC_BF16 else None
-            _lib.check(L.seldq_conv_fwd(ctypes.byref(desc), x.data_ptr(), _ptr(x16), wp, _ptr(bias), y.data_ptr(),
-                                        None, None, 0, _stream()))
+            x16 = bf16_mirror(x, _mirror_shifts(desc, 0)) if prec == PREC_BF16 else None
+            kern = "qconv_umma_fprop_kernel" if prec == PREC_BF16 else "conv_simt_kernel"
+            _timed(kern, _conv_flop(desc, oh.value, ow.value), 1, lambda: _lib.check(
+                L.seldq_conv_fwd(ctypes.byref(desc), x.data_ptr(), _ptr(x16), wp, _ptr(bias), y.data_ptr(),
+                                 None, 0, _stream())))
         ctx.desc = desc
+        ctx.out_hw = (oh.value, ow.value)
         ctx.has_bias = bias is not None
         # the tensor-core wgrad reads the bf16 mirror only: keep that instead of the fp32 input
         ctx.save_for_backward(x16 if prec == PREC_BF16 else x, *weights)
@@ -151,21 +210,25 @@ class _BlockConv(torch.autograd.Function):
         gws = [None] * len(weights)
         wp = _lib.ptr_array([w.data_ptr() for w in weights])
         with torch.cuda.device(dev):
-            gy16 = bf16_mirror(gy) if bf16 and (need_x or need_w) else None
+            gy16 = bf16_mirror(gy, _mirror_shifts(desc, 1)) if bf16 and (need_x or need_w) else None
             if need_x:
                 if desc.ndim == 1:
                     gx = torch.empty((desc.batch, desc.cin, desc.in_w), dtype=torch.float32, device=dev)
                 else:
                     gx = torch.empty((desc.batch, desc.cin, desc.in_h, desc.in_w), dtype=torch.float32, device=dev)
-                _lib.check(L.seldq_conv_dgrad(ctypes.byref(desc), gy.data_ptr(), _ptr(gy16), wp, gx.data_ptr(),
-                                              None, 0, _stream()))
+                kern = "qconv_umma_fprop_kernel" if bf16 else "conv_simt_kernel"
+                _timed(kern, _conv_flop(desc, *ctx.out_hw), 1, lambda: _lib.check(
+                    L.seldq_conv_dgrad(ctypes.byref(desc), gy.data_ptr(), _ptr(gy16), wp, gx.data_ptr(),
+                                       None, 0, _stream())))
             if need_w or need_b:
                 gws = [torch.empty_like(w) for w in weights]
                 gb = torch.empty(desc.cout, dtype=torch.float32, device=dev) if need_b else None
                 gp = _lib.ptr_array([g.data_ptr() for g in gws])
-                _lib.check(L.seldq_conv_wgrad(ctypes.byref(desc), None if bf16 else xs.data_ptr(),
-                                              xs.data_ptr() if bf16 else None, gy.data_ptr(), _ptr(gy16), gp,
-                                              _ptr(gb), None, 0, _stream()))
+                kern = "qconv_umma_wgrad_kernel" if bf16 else "wgrad_simt_kernel"
+                _timed(kern, _conv_flop(desc, *ctx.out_hw), 1 + (1 if need_b else 0), lambda: _lib.check(
+                    L.seldq_conv_wgrad(ctypes.byref(desc), None if bf16 else xs.data_ptr(),
+                                       xs.data_ptr() if bf16 else None, gy.data_ptr(), _ptr(gy16), gp,
+                                       _ptr(gb), None, 0, _stream())))
         return (gx, gb, None, None, None, None, None) + tuple(gws)
 
 
@@ -195,8 +258,9 @@ class _BlockLinear(torch.autograd.Function):
         y = torch.empty((x.shape[0], fout), dtype=torch.float32, device=x.device)
         wp = _lib.ptr_array([w.data_ptr() for w in weights])
         with torch.cuda.device(x.device):
-            _lib.check(L.seldq_linear_fwd(ctypes.byref(desc), x.data_ptr(), wp, _ptr(bias), y.data_ptr(), None, 0,
-                                          _stream()))
+            _timed("linear_simt", 0.0, 1, lambda: _lib.check(
+                L.seldq_linear_fwd(ctypes.byref(desc), x.data_ptr(), wp, _ptr(bias), y.data_ptr(), None, 0,
+                                   _stream())))
         ctx.desc = desc
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, *weights)
@@ -219,14 +283,16 @@ class _BlockLinear(torch.autograd.Function):
         with torch.cuda.device(dev):
             if need_x:
                 gx = torch.empty_like(x)
-                _lib.check(L.seldq_linear_dgrad(ctypes.byref(desc), gy.data_ptr(), wp, gx.data_ptr(), None, 0,
-                                                _stream()))
+                _timed("linear_simt", 0.0, 1, lambda: _lib.check(
+                    L.seldq_linear_dgrad(ctypes.byref(desc), gy.data_ptr(), wp, gx.data_ptr(), None, 0,
+                                         _stream())))
             if need_w or need_b:
                 gws = [torch.empty_like(w) for w in weights]
                 gb = torch.empty(desc.out_features, dtype=torch.float32, device=dev) if need_b else None
                 gp = _lib.ptr_array([g.data_ptr() for g in gws])
-                _lib.check(L.seldq_linear_wgrad(ctypes.byref(desc), x.data_ptr(), gy.data_ptr(), gp, _ptr(gb),
-                                                None, 0, _stream()))
+                _timed("linear_simt", 0.0, 1 + (1 if need_b else 0), lambda: _lib.check(
+                    L.seldq_linear_wgrad(ctypes.byref(desc), x.data_ptr(), gy.data_ptr(), gp, _ptr(gb),
+                                         None, 0, _stream())))
         return (gx, gb, None, None) + tuple(gws)
 
 
@@ -266,6 +332,7 @@ def stft_magphase(x, nperseg=512, noverlap=128, cut_dc=True, output_phase=True, 
     planes = 2 if output_phase else 1
     out = torch.empty((B, planes * C, nb.value, nf.value), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(L.seldq_stft_magphase(xb.data_ptr(), B, C, n, nperseg, noverlap, int(cut_dc), int(output_phase),
-                                         int(cut_last_timeframe), out.data_ptr(), _stream()))
+        _timed("stft_magphase_kernel", 0.0, 1, lambda: _lib.check(
+            L.seldq_stft_magphase(xb.data_ptr(), B, C, n, nperseg, noverlap, int(cut_dc), int(output_phase),
+                                  int(cut_last_timeframe), out.data_ptr(), _stream())))
     return out if batched else out[0]

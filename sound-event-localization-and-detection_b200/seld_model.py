@@ -19,6 +19,12 @@ import torch.nn.functional as tF
 
 from . import layers as _default_layers
 
+# The reference runs its real-valued nn.Conv* / nn.Linear layers (MultiHeadAttention projections,
+# the 'R' domain) in true fp32: it disables cuDNN altogether (model.py:10), so ATen's native kernels
+# are used and no TF32 is involved.  cuDNN stays enabled here (it is far faster), but its TF32 mode --
+# on by default in PyTorch -- is switched off so that those layers keep the reference's arithmetic.
+torch.backends.cudnn.allow_tf32 = False
+
 _BN_TCN = {'BN', 'BN_on_TCN', 'BNonTCN'}
 _BN_CNN = {'BN', 'BN_on_CNN', 'BNonCNN'}
 _TWO_BRANCH = {'2Parallel', '2BParallel', '2ParallelBranches', '2PB'}

@@ -1,0 +1,74 @@
+"""Batch-sharded data-parallel training step: one process per GPU, weights replicated, each rank
+takes its own samples, one exchange per step.
+
+Reproduces the step body of the reference's train.py:546-561
+    zero_grad -> seld_loss (train.py:186-204: BCE(sed) + 5 * MSE(doa)) -> backward -> Adam.step
+and adds what the reference does not have: all gradients live in ONE flat fp32
+bucket (every p.grad is a view into it, so the wgrad kernels' results are accumulated straight
+into the bucket by autograd), and the bucket is summed across ranks with a single NCCL all-reduce
+over NVLink and divided by the world size.  BatchNorm stays per replica, as N independent
+batches would in the reference.  Parameters that never receive a gradient (the unused
+batch_gate1 of every ResBlock and the last block's conv2_residual) simply keep
+zeros in their slice.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as tF
+
+
+def seld_loss(sed, doa, target, n_sed, sed_weight=1.0, doa_weight=5.0):
+    """train.py:186-204; target is (B, frames, n_sed + 3*n_sed) with SED first (train.py:191-192)."""
+    t_sed = torch.flatten(target[:, :, :n_sed], start_dim=1)
+    t_doa = torch.flatten(target[:, :, n_sed:], start_dim=1)
+    loss_sed = tF.binary_cross_entropy(torch.flatten(sed, start_dim=1), t_sed) * sed_weight
+    loss_doa = tF.mse_loss(torch.flatten(doa, start_dim=1), t_doa) * doa_weight
+    return loss_sed + loss_doa
+
+
+class FlatGradBucket(object):
+    """One contiguous fp32 buffer holding every parameter's gradient."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))
+
+
+class Trainer(object):
+    def __init__(self, model, lr=1e-4, n_sed=42, group=None):
+        self.model = model
+        self.n_sed = n_sed
+        self.group = group
+        self.bucket = FlatGradBucket(model.parameters())
+        on_cuda = self.bucket.flat.is_cuda
+        # Adam with the reference's hyper-parameters (train.py:502-504); fused = one kernel per step
+        self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, fused=on_cuda)
+
+    def broadcast_parameters(self, src=0):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=src, group=self.group)
+
+    def step(self, x, target):
+        """One optimisation step on this rank's shard; returns the (local) loss tensor."""
+        self.bucket.zero()
+        sed, doa = self.model(x)
+        loss = seld_loss(sed, doa, target, self.n_sed)
+        loss.backward()
+        self.bucket.all_reduce_mean(self.group)
+        self.optimizer.step()
+        return loss

@@ -48,7 +48,14 @@ def test_descriptor_validation_runs_without_gpu(seldq):
     assert lib.seldq_stft_shape(1920000, 512, 112, 1, 1, ctypes.byref(nb), ctypes.byref(nf)) == 0
     assert (nb.value, nf.value) == (256, 4800)
     d16 = L.ConvDesc(L.ALG_DQ, L.PREC_BF16, 1, 1, 384, 384, 1, 4800, 1, 3, 1, 1, 0, 1, 1, 1)
-    assert lib.seldq_conv_workspace_bytes(ctypes.byref(d16), L.PASS_WGRAD) == 2 * 384 * 4800 * 2
+    # bf16 path: x and gy each need the mirror copies for tap offsets -1, 0, +1 -> shifts {0, 1, 7}
+    shifts, n = (ctypes.c_int32 * 8)(), ctypes.c_int32()
+    assert lib.seldq_conv_mirror_shifts(ctypes.byref(d16), 0, shifts, ctypes.byref(n)) == 0
+    assert sorted(shifts[:n.value]) == [0, 1, 7] and shifts[0] == 0
+    assert lib.seldq_bf16_pitch(4800) == 4808
+    one = lib.seldq_bf16_mirror_bytes(384, 4800, 3)
+    assert one >= 3 * 384 * 4808 * 2
+    assert lib.seldq_conv_workspace_bytes(ctypes.byref(d16), L.PASS_WGRAD) == 2 * one
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

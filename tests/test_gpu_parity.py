@@ -1,0 +1,188 @@
+"""GPU parity tests proper: the CUDA path (through the layer / op API, i.e. through the C ABI)
+against the committed golden fixtures minted from the reference, and against the oracle on
+seeded inputs.  Tolerances (BASELINE.json north_star): rel 1e-4 in fp32 mode, rel 2e-2 in bf16
+mode, where rel = max|a-b| / max|b|."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from oracle import algebra as A
+
+pytestmark = pytest.mark.gpu
+
+NW = {"Q": 4, "DQ": 8}
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+# fixtures whose channel counts suit the tensor-core path (multiple of 8 per component, or a small dense layer)
+BF16_CONV = ["conv1d_q_k3_d5", "conv1d_dq_k3_d5", "conv1d_dq_c48_d3", "conv1d_q_c32_d2", "conv2d_dq_c24",
+             "conv2d_q_c16", "conv2d_dq_first", "conv2d_q_3x3", "conv2d_dq_3x3"]
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+
+
+def _conv_case(seldq, name, prec):
+    meta, d = load_golden(name)
+    alg = meta["algebra"]
+    nw = NW[alg]
+    x = cuda(d["x"]).requires_grad_(True)
+    ws = [cuda(d["w%d" % i]).requires_grad_(True) for i in range(nw)]
+    b = cuda(d["b"]).requires_grad_(True) if meta["bias"] else None
+    algebra = seldq._lib.ALG_Q if alg == "Q" else seldq._lib.ALG_DQ
+    with seldq.precision(prec):
+        y = seldq.block_conv(x, ws, b, meta["stride"], meta["padding"], meta["dilation"], algebra)
+        y.backward(cuda(d["gy"]))
+    torch.cuda.synchronize()
+    tol = TOL[prec]
+    errs = {"y": A.rel_err(y.detach().cpu().numpy(), d["y"]), "gx": A.rel_err(x.grad.cpu().numpy(), d["gx"])}
+    for i in range(nw):
+        errs["gw%d" % i] = A.rel_err(ws[i].grad.cpu().numpy(), d["gw%d" % i])
+    if meta["bias"]:
+        errs["gb"] = A.rel_err(b.grad.cpu().numpy(), d["gb"])
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, (name, prec, errs)
+
+
+@pytest.mark.parametrize("name", golden_names("conv"))
+def test_conv_fp32_matches_reference_fixture(seldq, name):
+    _conv_case(seldq, name, "fp32")
+
+
+@pytest.mark.parametrize("name", BF16_CONV)
+def test_conv_bf16_tensor_core_matches_reference_fixture(seldq, name):
+    _conv_case(seldq, name, "bf16")
+
+
+def test_bf16_path_rejects_shapes_it_cannot_serve(seldq):
+    # the tensor-core path is stride-1 only; it must say so instead of silently taking another route
+    meta, d = load_golden("conv1d_q_k3_s2")
+    ws = [cuda(d["w%d" % i]) for i in range(4)]
+    with seldq.precision("bf16"), pytest.raises(NotImplementedError, match="stride 1"):
+        seldq.block_conv(cuda(d["x"]), ws, None, 2, 1, 2, seldq._lib.ALG_Q)
+    # ... and channel counts that fit neither the compact nor the dense mode (12 per component, 96 in total)
+    x = torch.randn(1, 96, 64, device="cuda")
+    ws = [torch.randn(12, 12, 3, device="cuda") for _ in range(8)]
+    with seldq.precision("bf16"), pytest.raises(NotImplementedError, match="multiple of 8"):
+        seldq.block_conv(x, ws, None, 1, 1, 1, seldq._lib.ALG_DQ)
+
+
+@pytest.mark.parametrize("name", golden_names("linear"))
+def test_linear_matches_reference_fixture(seldq, name):
+    meta, d = load_golden(name)
+    alg = meta["algebra"]
+    nw = NW[alg]
+    x = cuda(d["x"]).requires_grad_(True)
+    ws = [cuda(d["w%d" % i]).requires_grad_(True) for i in range(nw)]
+    b = cuda(d["b"]).requires_grad_(True)
+    y = seldq.block_linear(x, ws, b, seldq._lib.ALG_Q if alg == "Q" else seldq._lib.ALG_DQ)
+    y.backward(cuda(d["gy"]))
+    assert A.rel_err(y.detach().cpu().numpy(), d["y"]) < 1e-4
+    assert A.rel_err(x.grad.cpu().numpy(), d["gx"]) < 1e-4
+    for i in range(nw):
+        assert A.rel_err(ws[i].grad.cpu().numpy(), d["gw%d" % i]) < 1e-4
+    assert A.rel_err(b.grad.cpu().numpy(), d["gb"]) < 1e-4
+
+
+def _check_stft(out, ref, C, phase):
+    assert out.shape == ref.shape
+    assert A.rel_err(out[:C], ref[:C]) < 1e-4
+    if phase:
+        mag = ref[:C]
+        dphi = np.abs(np.angle(np.exp(1j * (out[C:].astype(np.float64) - ref[C:]))))
+        # a bin's phase is defined to eps * max|Z| / |Z|: weight the error by the relative magnitude
+        assert (dphi * mag / mag.max()).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", golden_names("stft"))
+def test_stft_matches_reference_fixture(seldq, name):
+    meta, d = load_golden(name)
+    out = seldq.spectrum_fast(d["x"], nperseg=meta["nperseg"], noverlap=meta["noverlap"],
+                              output_phase=meta["output_phase"])
+    _check_stft(out, d["out"], d["x"].shape[0], meta["output_phase"])
+
+
+def test_stft_batched_full_length_against_oracle(seldq):
+    """One 60 s, 8-channel, 32 kHz clip (the L3DAS21 shape) against the numpy oracle; plus the
+    size-independent check that a batch equals its items."""
+    g = torch.Generator().manual_seed(1234)
+    x = 0.1 * torch.randn(2, 8, 1_920_000, generator=g)
+    out = seldq.stft_magphase(x.cuda(), 512, 112, True, True, True)
+    assert tuple(out.shape) == (2, 16, 256, 4800)
+    ref = A.spectrum_fast(x[1].numpy().astype(np.float64), nperseg=512, noverlap=112, output_phase=True)
+    _check_stft(out[1].cpu().numpy(), ref, 8, True)
+    single = seldq.stft_magphase(x[0].cuda(), 512, 112, True, True, True)
+    assert torch.equal(single, out[0])
+
+
+def test_stft_edge_cases(seldq):
+    # ragged lengths (tail zero padding), a signal shorter than one window, DC kept, last frame kept
+    rng = np.random.default_rng(3)
+    for n, nov, cut_dc, cut_last in [(513, 112, True, True), (100, 128, False, False), (40000, 0, True, False),
+                                     (12345, 511 - 128, True, True)]:
+        x = rng.standard_normal((3, n)).astype(np.float32)
+        ref = A.spectrum_fast(x.astype(np.float64), 512, nov, "hamming", cut_dc, True, cut_last)
+        out = seldq.spectrum_fast(x, 512, nov, "hamming", cut_dc, True, cut_last)
+        _check_stft(out, ref, 3, True)
+
+
+def _run_model(seldq, name, prec):
+    meta, d = load_golden(name)
+    cfg = dict(meta["cfg"])
+    m = seldq.SELD_Model(time_dim=meta["time_dim"], spatial_dropout_rate=0, dropout_perc=0, **cfg)
+    m.load_state_dict({k[6:]: torch.from_numpy(np.asarray(v)) for k, v in d.items() if k.startswith("param/")})
+    m = m.cuda().train()
+    x, target = cuda(d["x"]), cuda(d["target"])
+    n_sed = 42
+    with seldq.precision(prec):
+        sed, doa = m(x)
+        loss = (torch.nn.BCELoss()(torch.flatten(sed, 1), torch.flatten(target[:, :, :n_sed], 1))
+                + 5.0 * torch.nn.MSELoss()(torch.flatten(doa, 1), torch.flatten(target[:, :, n_sed:], 1)))
+        loss.backward()
+    torch.cuda.synchronize()
+    grads = {}
+    for k, p in m.named_parameters():
+        if ("grad/" + k) not in d:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k   # 28 params never get a gradient
+        else:
+            grads[k] = p.grad.cpu().numpy()
+    assert len(grads) == meta["n_grads"]
+    return meta, d, sed.detach().cpu().numpy(), doa.detach().cpu().numpy(), loss.item(), grads
+
+
+@pytest.mark.parametrize("name", ["model_dq_tiny", "model_q_tiny", "model_dq_2branch_tiny", "model_dq_mid"])
+def test_model_fp32_matches_reference_fixture(seldq, name):
+    """Whole model through the fp32 kernels.  Forward: rel 1e-4 against the float64 reference.
+    Gradients: this network's gradients are ill-conditioned -- the reference's OWN float32 run
+    differs from its float64 run by up to 1.4e-2 on some tensors (fixture key ref32err/*, SURVEY.md
+    8c) -- so each tensor is gated at max(5e-4, 4 x the reference's float32 error on that tensor)."""
+    meta, d, sed, doa, loss, grads = _run_model(seldq, name, "fp32")
+    assert A.rel_err(sed, d["sed"]) < 1e-4
+    assert A.rel_err(doa, d["doa"]) < 1e-4
+    assert abs(loss - float(d["loss"])) < 1e-4 * max(1.0, abs(float(d["loss"])))
+    bad = {}
+    for k, g in grads.items():
+        e, tol = A.rel_err(g, d["grad/" + k]), max(5e-4, 4.0 * float(d["ref32err/" + k]))
+        if not e < tol:
+            bad[k] = (e, tol)
+    assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
+
+
+@pytest.mark.parametrize("name", ["model_dq_tiny", "model_dq_mid"])
+def test_model_bf16_matches_reference_fixture(seldq, name):
+    """Whole model through the tcgen05 bf16 kernels.  Forward: rel 2e-2 against the float64
+    reference (north_star tolerance).  Gradients: bf16 operand rounding (2.7e-3 per convolution)
+    is amplified to tens of percent on some tensors by this network's conditioning, for ANY bf16
+    implementation; the fixture therefore carries the result of an ideal bf16-operand
+    implementation (oracle/bf16_emulation.py, keys bf16emu*) and the GPU must match THAT: 5e-3 on
+    the outputs and 5e-2 on every gradient tensor (the emulation runs everything between the
+    convolutions in float64, the GPU in float32, so a few activations round to the other bf16
+    neighbour and the same conditioning amplifies those few flips; observed 3e-3 / 2.8e-2)."""
+    meta, d, sed, doa, loss, grads = _run_model(seldq, name, "bf16")
+    assert A.rel_err(sed, d["sed"]) < 2e-2
+    assert A.rel_err(doa, d["doa"]) < 2e-2
+    assert A.rel_err(sed, d["bf16emu/sed"]) < 5e-3
+    assert A.rel_err(doa, d["bf16emu/doa"]) < 5e-3
+    bad = {k: A.rel_err(g, d["bf16emu_grad/" + k]) for k, g in grads.items()}
+    bad = {k: e for k, e in bad.items() if not e < 5e-2}
+    assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1])[:8])
