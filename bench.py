@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches rotated through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="drive every step from Python instead of one CUDA graph")
     ap.add_argument("--ref-max-steps", type=int, default=3)
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -213,29 +214,44 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), (sampler.stop() if sampler else None)
 
+    use_graph = not args.no_graph
+    if use_graph:
+        trainer.capture(*pool_dev[0], warmup=warm)
+        do_step = trainer.step_graph
+    else:
+        do_step = trainer.step
+
     def step_resident(i):
         x, t = pool_dev[i % args.pool]
-        trainer.step(x, t)
+        do_step(x, t)
 
     def step_e2e(i):
         hx, ht = pool_host[i % args.pool]
-        x = hx.to(device, non_blocking=True)
-        t = ht.to(device, non_blocking=True)
-        loss = trainer.step(x, t)
+        if use_graph:
+            loss = do_step(hx, ht)                         # pinned host -> the graph's static input buffers
+        else:
+            loss = do_step(hx.to(device, non_blocking=True), ht.to(device, non_blocking=True))
         return float(loss.item())                          # device -> host read of the step's result
 
     for i in range(warm):
         step_resident(i)
-    F.profile_reset(enable=True)
     ms, clocks = timed(step_resident, args.steps)
-    prof = F.profile_collect()
-    F.profile_reset(enable=False)
     value = world * batch * args.steps / (ms / 1e3)
 
     for i in range(2):
         step_e2e(i)
     ms_e2e, _ = timed(step_e2e, args.steps)
     e2e_value = world * batch * args.steps / (ms_e2e / 1e3)
+
+    # per-kernel durations: one eager step whose launches are queued behind a GPU-side sleep, so the
+    # CUDA events around each of our kernels are not stretched by host launch latency
+    torch.cuda.synchronize()
+    F.profile_reset(enable=True)
+    torch.cuda._sleep(int(1.5e9))
+    trainer.step(*pool_dev[0])
+    prof = F.profile_collect()
+    F.profile_reset(enable=False)
+    prof["launches"] *= args.steps                         # the same kernels run in each timed step
 
     if rank == 0:
         peaks = load_peaks()
@@ -245,13 +261,14 @@ def main():
             ach = k["flop"] / (k["ms"] / 1e3) / 1e12
             roof = dict(bound="tensor", kernel=k["name"], achieved=ach, peak=peaks["tflops"], unit="TFLOP/s",
                         frac=ach / peaks["tflops"], traffic=None, peak_source=peaks["source"],
-                        launches=k["launches"], avg_launch_us=1e3 * k["ms"] / max(1, k["launches"]),
-                        share_of_step=k["ms"] / ms)
+                        launches_per_step=k["launches"], avg_launch_us=1e3 * k["ms"] / max(1, k["launches"]),
+                        share_of_step=k["ms"] / (ms / args.steps),
+                        other_kernels_ms_per_step={n: round(v["ms"], 3) for n, v in prof["kernels"].items()})
         line = dict(metric="train_samples_per_sec", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
                     warmup=warm, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype=args.precision, data="synthetic",
                     config=dict(workload=args.config, per_gpu_batch=batch, global_batch=batch * world,
-                                time_frames=TIME_DIM, parallelism="dp%d" % world,
+                                time_frames=TIME_DIM, parallelism="dp%d" % world, cuda_graph=use_graph,
                                 l2="activations per step (>1 GB) exceed the 126 MB L2; %d distinct input batches "
                                    "are rotated" % args.pool),
                     clocks=clocks,

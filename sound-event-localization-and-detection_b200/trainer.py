@@ -55,13 +55,40 @@ class Trainer(object):
         self.group = group
         self.bucket = FlatGradBucket(model.parameters())
         on_cuda = self.bucket.flat.is_cuda
-        # Adam with the reference's hyper-parameters (train.py:502-504); fused = one kernel per step
-        self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, fused=on_cuda)
+        # Adam with the reference's hyper-parameters (train.py:502-504); fused = one kernel per step,
+        # capturable so that the whole step can live in a CUDA graph
+        self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, fused=on_cuda, capturable=on_cuda)
+        self._graph = None
 
     def broadcast_parameters(self, src=0):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 dist.broadcast(t.data, src=src, group=self.group)
+
+    def capture(self, x, target, warmup=3):
+        """Captures zero_grad -> forward -> loss -> backward -> all-reduce -> Adam into ONE CUDA graph
+        (static shapes: the step at per-GPU batch 1 is ~2000 launches of a few microseconds each, i.e.
+        launch-bound when driven from Python).  `warmup` eager steps run first on a side stream, as
+        graph capture requires; they are real optimisation steps."""
+        self._sx, self._st = x.clone(), target.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self._sx, self._st)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._sloss = self.step(self._sx, self._st)
+        self._graph = graph
+
+    def step_graph(self, x, target):
+        """Replays the captured step on new data (copied into the graph's static input buffers)."""
+        self._sx.copy_(x, non_blocking=True)
+        self._st.copy_(target, non_blocking=True)
+        self._graph.replay()
+        return self._sloss
 
     def step(self, x, target):
         """One optimisation step on this rank's shard; returns the (local) loss tensor."""

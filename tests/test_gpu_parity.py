@@ -174,15 +174,20 @@ def test_model_bf16_matches_reference_fixture(seldq, name):
     reference (north_star tolerance).  Gradients: bf16 operand rounding (2.7e-3 per convolution)
     is amplified to tens of percent on some tensors by this network's conditioning, for ANY bf16
     implementation; the fixture therefore carries the result of an ideal bf16-operand
-    implementation (oracle/bf16_emulation.py, keys bf16emu*) and the GPU must match THAT: 5e-3 on
-    the outputs and 5e-2 on every gradient tensor (the emulation runs everything between the
-    convolutions in float64, the GPU in float32, so a few activations round to the other bf16
-    neighbour and the same conditioning amplifies those few flips; observed 3e-3 / 2.8e-2)."""
+    implementation (oracle/bf16_emulation.py, keys bf16emu*): its own distance to the float64
+    reference is the inherent bf16 noise of each tensor, and the GPU may be at most twice as far
+    (floor 2e-2).  The outputs must match the emulation itself to 5e-3 (the emulation runs
+    everything between the convolutions in float64, the GPU in float32, so a few activations round
+    to the other bf16 neighbour; observed 3e-3)."""
     meta, d, sed, doa, loss, grads = _run_model(seldq, name, "bf16")
     assert A.rel_err(sed, d["sed"]) < 2e-2
     assert A.rel_err(doa, d["doa"]) < 2e-2
     assert A.rel_err(sed, d["bf16emu/sed"]) < 5e-3
     assert A.rel_err(doa, d["bf16emu/doa"]) < 5e-3
-    bad = {k: A.rel_err(g, d["bf16emu_grad/" + k]) for k, g in grads.items()}
-    bad = {k: e for k, e in bad.items() if not e < 5e-2}
-    assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1])[:8])
+    bad = {}
+    for k, g in grads.items():
+        noise = A.rel_err(d["bf16emu_grad/" + k], d["grad/" + k])
+        e, tol = A.rel_err(g, d["grad/" + k]), max(2e-2, 2.0 * noise)
+        if not e < tol:
+            bad[k] = (e, tol)
+    assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])

@@ -1,3 +1,4 @@
 cd /root/repo
-GROUPS_TO_RUN="model_fp32 model_bf16" KBENCH=0 bash tools/gpu_trip.sh
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_first.log 2>&1; echo "bench rc=$?"; tail -5 gpurun_out/bench_first.log | cut -c1-1500
+python tools/ncu_target.py > gpurun_out/ncu_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"qconv_umma|cast_bf16" -c 16 -o gpurun_out/prof_conv_r1 -f python tools/ncu_target.py > gpurun_out/ncu_run.log 2>&1
+echo "ncu rc=$?"; tail -5 gpurun_out/ncu_run.log; ls -la gpurun_out/*.ncu-rep
