@@ -1,0 +1,48 @@
+"""Per-kernel breakdown of ONE eager training step (torch.profiler, CUDA activities): which kernels
+the step spends its device time in, ours and PyTorch's.  Writes a table to stdout."""
+import argparse
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="DQSELD-TCN-S1-PHI_8ch")
+ap.add_argument("--batch", type=int, default=0)
+ap.add_argument("--top", type=int, default=45)
+args = ap.parse_args()
+cfg = bench.CONFIGS[args.config]
+pkg = importlib.import_module(bench.PKG)
+trainer_mod = importlib.import_module(bench.PKG + ".trainer")
+dev = torch.device("cuda", 0)
+np.random.seed(1)
+torch.manual_seed(1)
+batch = args.batch or cfg["batch_size"]
+model = pkg.SELD_Model(time_dim=bench.TIME_DIM, **bench.model_kwargs(cfg)).to(dev).train()
+trainer = trainer_mod.Trainer(model, lr=1e-4, n_sed=bench.N_SED)
+x, t = bench.synth_batch(pkg, cfg, batch, 1234, dev)
+for _ in range(3):
+    trainer.step(x, t)
+torch.cuda.synchronize()
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    trainer.step(x, t)
+    torch.cuda.synchronize()
+rows = {}
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        name = ev.name[:90]
+        r = rows.setdefault(name, [0.0, 0])
+        r[0] += ev.device_time
+        r[1] += 1
+total = sum(r[0] for r in rows.values())
+print("total device time %.3f ms over %d launches" % (total / 1e3, sum(r[1] for r in rows.values())))
+for name, (us, n) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:args.top]:
+    print("%9.1f us %5d x %7.1f us  %5.1f%%  %s" % (us, n, us / n, 100 * us / total, name))
