@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SELDQ_ABI_VERSION 1
+#define SELDQ_ABI_VERSION 2
 
 typedef enum {
   SELDQ_OK = 0,
@@ -93,22 +93,43 @@ int seldq_device_count(void);
 int seldq_conv_out_shape(const seldq_conv_desc_t* d, int32_t* out_h, int32_t* out_w);
 size_t seldq_conv_workspace_bytes(const seldq_conv_desc_t* d, int32_t pass);
 
-/* y = conv(x, expand(w)) + bias.
- *   x_bf16  optional (BF16 path only): the bf16 mirror set of x built earlier with
- *           seldq_cast_bf16_mirror and the shift list seldq_conv_mirror_shifts(d, 0, ...); if NULL
- *           the library builds it in the workspace first.  x may be NULL when x_bf16 is given. */
-int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_bf16,
-                   const float* const* host_w, const float* bias, float* y,
+/* bf16 operands of the tensor-core path (SELDQ_PREC_BF16).  The tcgen05 kernels read bf16 copies of the
+ * activations / gradients, laid out for TMA:
+ *   "CL operand"  [n][h][w][Cp]  channels innermost, every quaternion component padded to a multiple of 16
+ *                 channels (pad channels zero); x in this form feeds forward and wgrad, gy feeds dgrad;
+ *   "T16 operand" [n][c][h][pitch]  the tensor's own NCHW order in bf16, pitch = w rounded up to 8 (pad
+ *                 columns zero); gy in this form feeds wgrad.
+ * Every *_cl / *_t16 argument below is optional: when NULL the library stages the operand from the float32
+ * tensor into the workspace first.  A caller that stages once (seldq_stage_operand) and reuses the copy
+ * for forward and wgrad saves the second pass.  which = 0 selects x, 1 selects gy.
+ *   dense != 0: the layer's K side has fewer than 8 channels per component (first CNN layer) or the algebra
+ *   is real; its x operand is a single 16-channel-padded component, and its weight gradient reads the
+ *   float32 x (argument x of seldq_conv_wgrad must not be NULL). */
+int seldq_conv_operand_info(const seldq_conv_desc_t* d, int32_t which, int32_t* padded_channels, int32_t* dense,
+                            size_t* cl_bytes, size_t* t16_bytes);
+int seldq_stage_operand(const seldq_conv_desc_t* d, int32_t which, const float* src, void* dst_cl, void* dst_t16,
+                        void* stream);
+
+/* compact fp32 weights -> bf16 UMMA tiles of the COMPACT tensors (4 | 8 images, never the expanded
+ * weight), one set per pass (SELDQ_PASS_FWD, SELDQ_PASS_DGRAD).  Valid until the weights change, i.e.
+ * once per optimiser step.  seldq_conv_packed_bytes is 0 for dense layers (nothing to pack). */
+size_t seldq_conv_packed_bytes(const seldq_conv_desc_t* d, int32_t pass);
+int seldq_conv_pack_weights(const seldq_conv_desc_t* d, int32_t pass, const float* const* host_w, void* packed,
+                            void* stream);
+
+/* y = conv(x, expand(w)) + bias.   x may be NULL when x_cl is given (BF16 path). */
+int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
+                   const float* const* host_w, const void* packed_w, const float* bias, float* y,
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* gx = conv_transpose(gy, expand(w)) : gradient w.r.t. the input */
-int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy_bf16,
-                     const float* const* host_w, float* gx,
+int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy_cl,
+                     const float* const* host_w, const void* packed_w, float* gx,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* compact weight gradients (nc tensors, OVERWRITTEN) and, if gbias != NULL, gbias = sum gy */
-int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_bf16,
-                     const float* gy, const void* gy_bf16, float* const* host_gw, float* gbias,
+int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
+                     const float* gy, const void* gy_t16, float* const* host_gw, float* gbias,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- linear (A3, A4) ------------------------------------------------------------------- */
@@ -124,20 +145,6 @@ int seldq_linear_wgrad(const seldq_linear_desc_t* d, const float* x, const float
 /* ---- helpers ------------------------------------------------------------------------------ */
 /* dst_bf16[i] = bf16(src[i]) (round to nearest even) */
 int seldq_cast_bf16(const float* src, void* dst_bf16, size_t n, void* stream);
-/* "bf16 mirror set" of an NCHW / NCW fp32 tensor -- what every *_bf16 argument points to.
- * TMA (cp.async.bulk.tensor) needs the innermost start coordinate of a box 16-byte aligned, while a
- * convolution tap reads the time axis at an arbitrary offset (dilation 1, 2, 3, 5, ...).  The set
- * therefore holds nshifts copies [shift][rows][pitch] (rows = n*c*h, pitch = seldq_bf16_pitch(w)),
- * copy k being the tensor shifted RIGHT by shifts[k] in [0, 8) elements with zeros shifted in; a tap
- * with offset off reads copy (-off) mod 8 at an aligned coordinate.  shifts[0] is always 0.
- *   seldq_conv_mirror_shifts: the shift list a convolution needs; which = 0 for x (forward and
- *   wgrad read it at the forward taps), which = 1 for gy (dgrad reads it at the transposed taps;
- *   wgrad only uses its copy 0). */
-int seldq_bf16_pitch(int32_t w);
-int seldq_conv_mirror_shifts(const seldq_conv_desc_t* d, int32_t which, int32_t* shifts8, int32_t* nshifts);
-size_t seldq_bf16_mirror_bytes(int64_t rows, int32_t w, int32_t nshifts);
-int seldq_cast_bf16_mirror(const float* src, void* dst_bf16, int64_t rows, int32_t w,
-                           const int32_t* shifts, int32_t nshifts, void* stream);
 
 /* ---- STFT front end (F1) ----------------------------------------------------------------- */
 /* x: (n_signals, n_samples) float32.  out: (n_batch, (1+output_phase)*n_ch, n_bins, n_frames)

@@ -10,7 +10,7 @@ or put `<this dir>/dropin` on sys.path and import the reference's module names
 import os as _os
 
 from . import _lib
-from .functional import (bf16_mirror, block_conv, block_linear, get_precision, precision, set_precision,
+from .functional import (block_conv, block_linear, get_precision, precision, set_precision,
                          stft_magphase)
 from .features import spectrum_fast
 from .layers import (DualQuaternionConv, DualQuaternionLinear, QuaternionConv, QuaternionLinear,

@@ -49,9 +49,15 @@ _PROTOS = {
     "seldq_conv_out_shape": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_int32),
                                             ctypes.POINTER(ctypes.c_int32)]),
     "seldq_conv_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc), ctypes.c_int32]),
-    "seldq_conv_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P,
+    "seldq_conv_operand_info": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32,
+                                               ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                               ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
+    "seldq_stage_operand": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32, _P, _P, _P, _P]),
+    "seldq_conv_packed_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc), ctypes.c_int32]),
+    "seldq_conv_pack_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32, ctypes.POINTER(_P), _P, _P]),
+    "seldq_conv_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P, _P,
                                       ctypes.c_size_t, _P]),
-    "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P,
+    "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P,
                                         ctypes.c_size_t, _P]),
     "seldq_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.POINTER(_P), _P, _P,
                                         ctypes.c_size_t, _P]),
@@ -63,12 +69,6 @@ _PROTOS = {
     "seldq_linear_wgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, _P, ctypes.POINTER(_P), _P, _P,
                                           ctypes.c_size_t, _P]),
     "seldq_cast_bf16": (ctypes.c_int, [_P, _P, ctypes.c_size_t, _P]),
-    "seldq_bf16_pitch": (ctypes.c_int, [ctypes.c_int32]),
-    "seldq_conv_mirror_shifts": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32,
-                                                ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
-    "seldq_bf16_mirror_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
-    "seldq_cast_bf16_mirror": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
-                                              ctypes.c_int32, _P]),
     "seldq_stft_shape": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                         ctypes.POINTER(ctypes.c_int32)]),

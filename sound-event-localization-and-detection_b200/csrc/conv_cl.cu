@@ -1,0 +1,460 @@
+// tcgen05 implicit-GEMM convolution for the quaternion / dual-quaternion layers, forward and dgrad,
+// reading channels-last bf16 operands (conv_cl.h).
+//
+//   D[t, (a,o)] = sum_tap sum_b sum_i  sign[a][b] * X[t + off(tap), (b,i)] * W_{widx[a][b]}[o, i, tap]
+//
+//   * M = 128 consecutive w positions of one (n, h) row              -> TMEM lanes
+//   * N = out channels of ONE out component a (padded to 16)         -> TMEM columns al*NBp ...
+//   * K = (tap, 64-channel chunk) boxes streamed by TMA through an mbarrier ring; a box [128 w x 64 ch]
+//     lands in the canonical K-major 128B-swizzled layout, each of its four 16-channel slabs belongs to
+//     one in component b
+//
+// The Hamilton / dual-quaternion expansion (quaternion_ops.py:131-135, dual_quaternion_ops.py:122-140)
+// is never materialised: the COMPACT weights, pre-packed once per optimiser step as bf16 UMMA tiles
+// (pack_weights_kernel), are bulk-copied into shared memory and stay resident; every (a, b, slab) is one
+// tcgen05.mma whose instruction descriptor carries sign[a][b] in the negate-B bit; the structural zero
+// block of the dual quaternion is never issued, and channel chunks that only feed zero blocks of a CTA's
+// out components are never loaded.
+//
+// Work unit = (position tile, group of out components).  Splitting the out components over CTAs fills the
+// 148 SMs when there are few position tiles (batch 1: 38 tiles per TCN layer); heavier groups (the dual
+// half of a DQ layer has twice the blocks) are scheduled first.
+//
+// Layers whose K side has < 8 channels per component (first CNN layer, Cin = 8 | 16) run "dense": the
+// activation is one 16-channel-padded component and the signed expanded tile is built in shared memory
+// only, one MMA spanning all out channels.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> coalesced global stores, + bias).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "conv_cl.h"
+#include "launch.h"
+#include "tensor_map.h"
+#include "umma_ptx.cuh"
+
+namespace seldq {
+namespace cl {
+
+__global__ void __launch_bounds__(kThreads, 1)
+qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ FpropParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // layout: [activation ring][barriers, 1 KB][weight tiles][slack]
+  uint8_t* a_ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstages * p.stage_bytes);
+  uint8_t* b_img = smem + (size_t)p.nstages * p.stage_bytes + 1024;
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
+  uint64_t* w_bar = bars + 2 * kMaxStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (p.dense) {
+    // signed expanded weight -> bf16 B tiles.  Tile (tap, j) holds B[n][k], n = out channel, k = in channels
+    // 16 j ... 16 j + 15; UMMA K-major / no swizzle: core matrix = 8 rows x 16 B, LBO (K step) = NBp*16,
+    // SBO (8 rows) = 128
+    const int items = p.ntaps * p.J * 2 * p.NBp;          // one item = 8 consecutive k of one row
+    for (int it = threadIdx.x; it < items; it += kThreads) {
+      int r = it;
+      const int n = r % p.NBp; r /= p.NBp;
+      const int kc = r & 1; r >>= 1;
+      const int j = r % p.J;
+      const int tap = r / p.J;
+      __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int ch = j * 16 + kc * 8 + jj;
+        v[jj] = __float2bfloat16_rn((n < p.g.P && ch < p.g.R) ? expanded_weight(p.g, p.w, n, ch, tap) : 0.f);
+      }
+      uint8_t* dst = b_img + (size_t)(tap * p.J + j) * p.slab_bytes + (size_t)kc * (p.NBp * 16) + (n >> 3) * 128 +
+                     (n & 7) * 16;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    }
+    ptx::fence_proxy_async();
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 4); }
+    ptx::mbar_init(w_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tm_in);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc_cols = (uint32_t)(p.gc * p.NBp);
+
+  if (warp == 0) {
+    // ===== TMA producer ============================================================================
+    if (ptx::elect_one()) {
+      if (!p.dense) {
+        // resident weight tiles: one bulk copy per <= 32 KB
+        ptx::mbar_arrive_expect_tx(w_bar, p.w_bytes);
+        for (uint32_t off = 0; off < p.w_bytes; off += 32768u) {
+          const uint32_t n = p.w_bytes - off < 32768u ? p.w_bytes - off : 32768u;
+          ptx::bulk_load(b_img + off, p.packed + off, n, w_bar);
+        }
+      }
+      uint32_t slot = 0, parity = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        const int group = p.group_order[u / p.total_tiles];
+        int r = u % p.total_tiles;
+        const int wt = r % p.tiles_w; r /= p.tiles_w;
+        const int h = r % p.OH;
+        const int n = r / p.OH;
+        const int w0 = wt * kTileM;
+        const uint32_t mask = p.chunk_mask[group];
+        for (int tap = 0; tap < p.ntaps; ++tap)
+          for (int c = 0; c < p.chunks; ++c) {
+            if (!((mask >> c) & 1u)) continue;
+            ptx::mbar_wait(&empty_bar[slot], parity ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[slot], p.stage_bytes);
+            ptx::tma_load_4d(a_ring + (size_t)slot * p.stage_bytes, &tm_in, &full_bar[slot], c * p.BK,
+                             w0 + p.off_w[tap], h + p.off_h[tap], n);
+            if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ==============================================================================
+    if (ptx::elect_one()) {
+      const uint64_t a_hi = ptx::make_smem_desc_hi(16, p.a_sbo, p.a_swz);                 // K-major, swizzled
+      const uint64_t b_hi = ptx::make_smem_desc_hi((uint32_t)p.NBp * 16u, 128, ptx::kSwizzleNone);
+      const uint32_t idesc = ptx::make_idesc_bf16(kTileM, (uint32_t)p.NBp, 0, 0, 0, 0);
+      const uint32_t a_base = ptx::smem_u32(a_ring), b_base = ptx::smem_u32(b_img);
+      if (!p.dense) ptx::mbar_wait(w_bar, 0);
+      uint32_t slot = 0, parity = 0, it = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+        const int group = p.group_order[u / p.total_tiles];
+        const uint32_t mask = p.chunk_mask[group];
+        const uint32_t as = p.acc_stages == 2 ? (it & 1) : 0;
+        const uint32_t use = p.acc_stages == 2 ? (it >> 1) : it;
+        ptx::mbar_wait(&tempty_bar[as], (use & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_base = tmem_base + as * acc_cols;
+        uint32_t written = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap)
+          for (int c = 0; c < p.chunks; ++c) {
+            if (!((mask >> c) & 1u)) continue;
+            ptx::mbar_wait(&full_bar[slot], parity);
+            ptx::tc_fence_after();
+            const uint32_t a_stage = a_base + slot * p.stage_bytes;
+            for (int s = 0; s < p.slabs_per_chunk; ++s) {
+              const int ch0 = c * p.BK + s * 16;
+              const int b = ch0 / p.cpad_in;
+              const int j = (ch0 - b * p.cpad_in) >> 4;
+              const uint64_t a_desc = ptx::smem_desc(a_hi, a_stage + (uint32_t)s * 32u);
+              const uint32_t w_off = (uint32_t)(tap * p.J + j) * p.slab_bytes;
+              for (int al = 0; al < p.gc; ++al) {
+                const int a = group * p.gc + al;
+                const int img = p.op_img[b][a];
+                if (img < 0) continue;
+                const uint64_t b_desc = ptx::smem_desc(b_hi, b_base + (uint32_t)img * p.img_bytes + w_off);
+                ptx::umma_f16(d_base + (uint32_t)(al * p.NBp), a_desc, b_desc,
+                              idesc | ((uint32_t)p.op_neg[b][a] << 14), (written >> al) & 1u);
+                written |= 1u << al;
+              }
+            }
+            ptx::umma_commit(&empty_bar[slot]);    // frees the ring slot once these MMAs retire
+            if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
+          }
+        ptx::umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global ===================================================
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+      const int group = p.group_order[u / p.total_tiles];
+      const uint32_t as = p.acc_stages == 2 ? (it & 1) : 0;
+      const uint32_t use = p.acc_stages == 2 ? (it >> 1) : it;
+      int r = u % p.total_tiles;
+      const int wt = r % p.tiles_w; r /= p.tiles_w;
+      const int h = r % p.OH;
+      const int n = r / p.OH;
+      const int w = wt * kTileM + row;
+      const bool w_ok = w < p.OW;
+      ptx::mbar_wait(&tfull_bar[as], use & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
+      float* out_row = p.out + (long long)n * p.out_sN + (long long)h * p.out_sH + w;
+      for (int al = 0; al < p.gc; ++al) {
+        const int ch_base = (group * p.gc + al) * p.Pc;
+        for (int c0 = 0; c0 < p.Pc; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
+          ptx::tmem_ld_wait();
+          if (w_ok) {
+            float* dst = out_row + (long long)(ch_base + c0) * p.out_sC;
+            const int lim = p.Pc - c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < lim) {
+                float y = __uint_as_float(v[j]);
+                if (p.bias) y += __ldg(p.bias + ch_base + c0 + j);
+                *dst = y;
+              }
+              dst += p.out_sC;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// compact fp32 weights -> bf16 UMMA B tiles [img][tap][j][NBp x 16] (K-major, no swizzle; see the dense
+// prologue above for the byte layout).  Row n / column k of tile (img, tap, j):
+//   forward : W_img[o = n][i = 16 j + k][tap]        dgrad : W_img[o = 16 j + k][i = n][tap]
+struct PackParams {
+  const float* w[8];
+  uint8_t* dst;
+  int n_img, ntaps, J, NBp;
+  int rows_real, k_real;        // real extent of the row (N side) and K side
+  int transposed;
+  int wsO, wsI, wsT;
+};
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackParams p) {
+  const int items = p.n_img * p.ntaps * p.J * 2 * p.NBp;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    int r = it;
+    const int n = r % p.NBp; r /= p.NBp;
+    const int kc = r & 1; r >>= 1;
+    const int j = r % p.J; r /= p.J;
+    const int tap = r % p.ntaps;
+    const int img = r / p.ntaps;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int k = j * 16 + kc * 8 + jj;
+      float x = 0.f;
+      if (n < p.rows_real && k < p.k_real) {
+        const int o = p.transposed ? k : n, i = p.transposed ? n : k;
+        x = __ldg(p.w[img] + (long long)o * p.wsO + (long long)i * p.wsI + (long long)tap * p.wsT);
+      }
+      v[jj] = __float2bfloat16_rn(x);
+    }
+    uint8_t* dst = p.dst + ((size_t)(img * p.ntaps + tap) * p.J + j) * ((size_t)p.NBp * 32) +
+                   (size_t)kc * (p.NBp * 16) + (n >> 3) * 128 + (n & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      return 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace cl
+
+// ---- host side: layouts, plan, launch -------------------------------------------------------------
+using cl::FpropParams;
+
+cl::OperandLayout x_operand_layout(const ConvGeom& fwd) {
+  return cl::operand_layout(fwd.tab.nc, fwd.tab.nc * fwd.Ic, fwd.tab.nc == 1 || fwd.Ic < 8);
+}
+cl::OperandLayout gy_operand_layout(const ConvGeom& fwd) {
+  return cl::operand_layout(fwd.tab.nc, fwd.tab.nc * fwd.Oc, fwd.tab.nc == 1 || fwd.Oc < 8);
+}
+
+// geometry of the resident weight tiles of one pass
+struct WeightPlan {
+  int dense, n_img, ntaps, J, NBp, rows_real, k_real;
+  size_t slab_bytes, img_bytes, total;
+};
+static WeightPlan weight_plan(const ConvGeom& g) {
+  WeightPlan w;
+  w.dense = cl::is_dense(g) ? 1 : 0;
+  w.ntaps = g.KH * g.KW;
+  if (w.dense) {
+    const cl::OperandLayout l = cl::operand_layout(1, g.R, true);
+    w.n_img = 1; w.J = l.Cp / 16; w.NBp = cl::round_up(g.P, 16); w.rows_real = g.P; w.k_real = g.R;
+  } else {
+    const int kc = g.transposed ? g.Oc : g.Ic, pc = g.transposed ? g.Ic : g.Oc;
+    w.n_img = g.tab.nw; w.J = cl::round_up(kc, 16) / 16; w.NBp = cl::round_up(pc, 16); w.rows_real = pc; w.k_real = kc;
+  }
+  w.slab_bytes = (size_t)w.NBp * 32;
+  w.img_bytes = (size_t)w.ntaps * w.J * w.slab_bytes;
+  w.total = (size_t)w.n_img * w.img_bytes;
+  return w;
+}
+
+size_t packed_weight_bytes(const ConvGeom& g) {
+  const WeightPlan w = weight_plan(g);
+  return w.dense ? 0 : w.total;
+}
+
+int launch_pack_weights(const ConvGeom& g, const float* const* host_w, void* packed, cudaStream_t st) {
+  const WeightPlan w = weight_plan(g);
+  if (w.dense) return SELDQ_OK;      // dense layers build their tile from the fp32 weights inside the kernel
+  if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(SELDQ_ERR_INVALID, "packed weight buffer must be 16-byte aligned");
+  cl::PackParams p{};
+  for (int i = 0; i < w.n_img; ++i) p.w[i] = host_w[i];
+  p.dst = reinterpret_cast<uint8_t*>(packed);
+  p.n_img = w.n_img; p.ntaps = w.ntaps; p.J = w.J; p.NBp = w.NBp;
+  p.rows_real = w.rows_real; p.k_real = w.k_real; p.transposed = g.transposed;
+  p.wsO = g.wsO; p.wsI = g.wsI; p.wsT = g.wsT;
+  const int items = w.n_img * w.ntaps * w.J * 2 * w.NBp;
+  int blocks = (items + 255) / 256;
+  if (blocks > 4 * cl::num_sms()) blocks = 4 * cl::num_sms();
+  cl::pack_weights_kernel<<<blocks, 256, 0, st>>>(p);
+  return check_launch("pack_weights_kernel");
+}
+
+int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
+  memset(p, 0, sizeof(*p));
+  if (g.sh != 1 || g.sw != 1)
+    return fail(SELDQ_ERR_UNSUPPORTED, "bf16 tensor-core path implements stride 1 only (got %dx%d)", g.sh, g.sw);
+  const int ntaps = g.KH * g.KW;
+  if (ntaps > cl::kMaxTaps) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path supports at most %d taps", cl::kMaxTaps);
+  const WeightPlan w = weight_plan(g);
+  const int nc = g.tab.nc;
+  p->g = g;
+  p->ntaps = ntaps;
+  p->N = g.N; p->OH = g.OH; p->OW = g.OW;
+  for (int t = 0; t < ntaps; ++t) {
+    const int kh = t / g.KW, kw = t % g.KW;
+    // forward: in = out - pad + k*dil ; dgrad: gy position = gx position + pad - k*dil   (stride 1)
+    p->off_h[t] = g.transposed ? g.ph - kh * g.dh : kh * g.dh - g.ph;
+    p->off_w[t] = g.transposed ? g.pw - kw * g.dw : kw * g.dw - g.pw;
+  }
+  p->dense = w.dense;
+  cl::OperandLayout l;
+  for (int b = 0; b < 8; ++b)
+    for (int a = 0; a < 8; ++a) p->op_img[b][a] = -1;
+  if (w.dense) {
+    if (g.P > 256)
+      return fail(SELDQ_ERR_UNSUPPORTED, "bf16 dense mode (K side < 8 channels per component) needs <= 256 out channels, got %d",
+                  g.P);
+    l = cl::operand_layout(1, g.R, true);
+    p->ncomp_out = 1; p->Pc = g.P;
+    p->op_img[0][0] = 0; p->op_neg[0][0] = 0;
+  } else {
+    l = cl::operand_layout(nc, g.R, false);
+    p->ncomp_out = nc; p->Pc = g.transposed ? g.Ic : g.Oc;
+    for (int b = 0; b < nc; ++b)
+      for (int a = 0; a < nc; ++a) {
+        const int fa = g.transposed ? b : a, fb = g.transposed ? a : b;   // forward-sense (out, in) components
+        const int e = g.tab.widx[fa][fb];
+        if (e < 0) continue;
+        p->op_img[b][a] = (int8_t)e;
+        p->op_neg[b][a] = (int8_t)(g.tab.sign[fa][fb] < 0);
+      }
+  }
+  p->NBp = w.NBp; p->J = w.J; p->n_img = w.n_img;
+  p->slab_bytes = (uint32_t)w.slab_bytes; p->img_bytes = (uint32_t)w.img_bytes; p->w_bytes = (uint32_t)w.total;
+  p->BK = l.BK; p->chunks = l.Cp / l.BK; p->slabs_per_chunk = l.BK / 16; p->cpad_in = l.cpad;
+  if (p->chunks > 32) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path supports at most 2048 padded input channels");
+  p->stage_bytes = (uint32_t)cl::kTileM * l.BK * 2;
+  p->a_sbo = 8u * l.BK * 2;
+  p->a_swz = l.BK == 64 ? ptx::kSwizzle128B : (l.BK == 32 ? ptx::kSwizzle64B : ptx::kSwizzle32B);
+
+  p->tiles_w = (g.OW + cl::kTileM - 1) / cl::kTileM;
+  const long long tiles = (long long)g.N * g.OH * p->tiles_w;
+  if (tiles > 0x0fffffffLL) return fail(SELDQ_ERR_UNSUPPORTED, "too many tiles");
+  p->total_tiles = (int)tiles;
+  // out-component groups: as few as TMEM allows, more while that helps to fill the SMs
+  int ngroups = 1;
+  while (p->ncomp_out / ngroups * p->NBp > 512 && ngroups < p->ncomp_out) ngroups *= 2;
+  if (p->ncomp_out / ngroups * p->NBp > 512)
+    return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path supports at most 512 out channels per component");
+  while (ngroups < p->ncomp_out && tiles * ngroups * 2 <= cl::num_sms() + cl::num_sms() / 16) ngroups *= 2;
+  p->ngroups = ngroups;
+  p->gc = p->ncomp_out / ngroups;
+  p->total_units = (int)(tiles * ngroups);
+  // cost (number of non-zero blocks) and needed chunks per group
+  int cost[8];
+  for (int gi = 0; gi < ngroups; ++gi) {
+    cost[gi] = 0;
+    uint32_t mask = 0;
+    for (int c = 0; c < p->chunks; ++c)
+      for (int s = 0; s < p->slabs_per_chunk; ++s) {
+        const int b = (c * l.BK + s * 16) / l.cpad;
+        for (int al = 0; al < p->gc; ++al)
+          if (p->op_img[b][gi * p->gc + al] >= 0) { mask |= 1u << c; ++cost[gi]; }
+      }
+    p->chunk_mask[gi] = mask;
+    p->group_order[gi] = gi;
+  }
+  for (int i = 1; i < ngroups; ++i)                  // insertion sort, heaviest first
+    for (int j = i; j > 0 && cost[p->group_order[j]] > cost[p->group_order[j - 1]]; --j) {
+      const int t = p->group_order[j]; p->group_order[j] = p->group_order[j - 1]; p->group_order[j - 1] = t;
+    }
+
+  const int acc_cols = p->gc * p->NBp;
+  p->acc_stages = acc_cols * 2 <= 512 ? 2 : 1;
+  int cols = 32;
+  while (cols < acc_cols * p->acc_stages) cols <<= 1;
+  p->tmem_cols = cols;
+  const size_t fixed = 1024 /* barriers */ + w.total + 4096 /* slack behind the tiles */;
+  const size_t budget = 226 * 1024;
+  if (fixed + 2 * (size_t)p->stage_bytes > budget)
+    return fail(SELDQ_ERR_UNSUPPORTED, "compact weights (%zu B as bf16 tiles) do not fit in shared memory", w.total);
+  size_t ns = (budget - fixed) / p->stage_bytes;
+  if (ns > (size_t)cl::kMaxStages) ns = cl::kMaxStages;
+  p->nstages = (int)ns;
+  *smem_bytes = ns * p->stage_bytes + fixed;
+  return SELDQ_OK;
+}
+
+// (C, W, H, N) view of a CL operand, box {BK, 128, 1, 1}
+static int encode_cl_map(CUtensorMap* tm, const void* data, const cl::OperandLayout& l, int w, int h, int n,
+                         int box_rows) {
+  const uint64_t dims[4] = {(uint64_t)l.Cp, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+  const uint64_t strides[3] = {(uint64_t)l.Cp * 2, (uint64_t)l.Cp * 2 * w, (uint64_t)l.Cp * 2 * w * h};
+  const uint32_t box[4] = {(uint32_t)l.BK, (uint32_t)box_rows, 1, 1};
+  return encode_tensor_map(tm, data, 2, 4, dims, strides, box, l.BK == 64 ? 3 : (l.BK == 32 ? 2 : 1));
+}
+
+int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
+                    const float* bias, float* out, cudaStream_t st) {
+  FpropParams p;
+  size_t smem = 0;
+  int rc = plan_cl_fprop(g, &p, &smem);
+  if (rc) return rc;
+  if (p.dense) {
+    for (int i = 0; i < g.tab.nw; ++i) p.w[i] = host_w[i];
+  } else {
+    if (!packed) return fail(SELDQ_ERR_INVALID, "bf16 path needs the packed weight tiles");
+    if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(SELDQ_ERR_INVALID, "packed weights must be 16-byte aligned");
+    p.packed = reinterpret_cast<const uint8_t*>(packed);
+  }
+  p.bias = bias;
+  p.out = out;
+  p.out_sN = g.out_sN; p.out_sC = g.out_sC; p.out_sH = g.out_sH;
+  const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, p.dense != 0);
+  alignas(64) CUtensorMap tm;
+  rc = encode_cl_map(&tm, in_cl, l, g.IW, g.IH, g.N, cl::kTileM);
+  if (rc) return rc;
+  cudaError_t e = cudaFuncSetAttribute(cl::qconv_cl_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "fprop smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+  const int grid = p.total_units < cl::num_sms() ? p.total_units : cl::num_sms();
+  cl::qconv_cl_fprop_kernel<<<grid, cl::kThreads, smem, st>>>(tm, p);
+  return check_launch("qconv_cl_fprop_kernel");
+}
+
+}  // namespace seldq

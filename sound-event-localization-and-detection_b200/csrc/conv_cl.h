@@ -1,0 +1,127 @@
+// Channels-last tensor-core path (conv_cl.cu, wgrad_cl.cu): operand layouts, parameter blocks and
+// host entry points.
+//
+// "CL operand" = bf16 copy of an activation (or gradient) tensor laid out [n][h][w][Cp]: channels
+// innermost, each of the nc quaternion components padded to a multiple of 16 channels
+// (Cp = nc * cpad, pad channels are zero).  A TMA box [128 w x 64 ch] of it is a K-major UMMA A
+// operand in the canonical 128B-swizzled layout; a convolution tap is an offset on the w / h
+// coordinates (any value, out-of-range rows are zero-filled = padding), so no shifted copies are
+// needed; every 16-channel K slab lies inside one component, so one tcgen05.mma serves one
+// (out component, in component) block and carries the block's Hamilton sign in its negate bit.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace seldq {
+namespace cl {
+
+constexpr int kTileM = 128;     // positions per accumulator tile (TMEM lanes)
+constexpr int kThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kMaxTaps = 9;
+constexpr int kMaxStages = 8;
+
+SELDQ_HD int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct OperandLayout {
+  int nc;      // components that are padded separately (1 in dense mode)
+  int cc;      // real channels per component
+  int cpad;    // padded channels per component (multiple of 16)
+  int Cp;      // nc * cpad
+  int BK;      // channels per TMA box: 64 (128B swizzle), 32 (64B) or 16 (32B)
+};
+
+// dense = the layer's K side has fewer than 8 channels per component (first CNN layer) or the algebra
+// is real: the tensor is laid out as ONE component and the signed expanded weight tile is built in
+// shared memory only.
+inline OperandLayout operand_layout(int nc, int channels, bool dense) {
+  OperandLayout l;
+  if (dense) {
+    l.nc = 1; l.cc = channels;
+    const int p16 = round_up(channels, 16);
+    l.cpad = (p16 == 16 || p16 == 32 || p16 == 64) ? p16 : round_up(channels, 64);
+  } else {
+    l.nc = nc; l.cc = channels / nc;
+    l.cpad = round_up(l.cc, 16);                               // nc = 4 | 8  =>  Cp is a multiple of 64
+  }
+  l.Cp = l.nc * l.cpad;
+  l.BK = l.Cp < 64 ? l.Cp : 64;
+  return l;
+}
+
+// is the K side of this pass a "dense" operand?  (kc = per-component channels on the K side)
+inline bool is_dense(const ConvGeom& g) {
+  const int kc = g.transposed ? g.Oc : g.Ic;
+  return g.tab.nc == 1 || kc < 8;
+}
+
+struct FpropParams {
+  ConvGeom g;                   // pass orientation (transposed = 1 for dgrad); dense prologue reads it
+  const float* w[8];            // compact fp32 weights (dense prologue only)
+  const uint8_t* packed;        // pre-packed bf16 weight images (non-dense)
+  const float* bias;
+  float* out;                   // fp32 NCHW
+  long long out_sN, out_sC, out_sH;
+  int N, OH, OW;
+  int tiles_w, total_tiles, ngroups, total_units;
+  int group_order[8];           // heaviest groups first
+  int ntaps;
+  int off_h[kMaxTaps], off_w[kMaxTaps];
+  // K side
+  int BK, chunks, slabs_per_chunk, cpad_in, J;
+  uint32_t stage_bytes, a_sbo, a_swz;
+  uint32_t chunk_mask[8];       // per group: which channel chunks carry at least one non-zero block
+  // N side
+  int dense, ncomp_out, Pc, NBp, gc;
+  int n_img;
+  uint32_t slab_bytes;          // NBp * 32: one [NBp x 16] bf16 B tile
+  uint32_t img_bytes;           // ntaps * J * slab_bytes
+  uint32_t w_bytes;             // n_img * img_bytes
+  int8_t op_img[8][8];          // [in comp b][out comp a] -> image index or -1
+  int8_t op_neg[8][8];
+  int nstages, acc_stages, tmem_cols;
+};
+
+// wgrad: D[(a,o), (b,i)] per tap = sum_t GY[(a,o), t] * X[t + off(tap), (b,i)]
+//   A = gy from its pitched NCHW bf16 copy (K-major, time contiguous), rows gathered per component
+//   B = x from its CL operand (MN-major, channels contiguous), the tap is a row offset
+constexpr int kWgradStages = 4;
+struct WgradParams {
+  ConvGeom g;                   // forward orientation
+  float* gw[8];                 // compact fp32 gradients, accumulated with atomicAdd
+  int ncomp, OS;                // M rows = ncomp * OS (= 128)
+  int o_tiles;
+  int cpad_in, Cp, nchunks;     // x operand: Cp = ncomp*cpad_in channels = nchunks boxes of 64
+  int taps_per_group, tap_groups, ntaps;
+  int off_h[kMaxTaps], off_w[kMaxTaps];
+  int OH, OW, N;
+  int chunks_w;
+  long long ksteps;
+  int splits, nstages, tmem_cols;
+  uint32_t stage_bytes, b_tap_bytes;
+  int8_t pair_n[8];             // which (a,b) blocks feed compact tensor e
+  int8_t pair_a[8][8], pair_b[8][8], pair_neg[8][8];
+};
+
+int num_sms();
+
+}  // namespace cl
+
+// x / gy operand layouts of a convolution (forward-orientation geometry)
+cl::OperandLayout x_operand_layout(const ConvGeom& fwd);
+cl::OperandLayout gy_operand_layout(const ConvGeom& fwd);
+
+size_t packed_weight_bytes(const ConvGeom& pass_geom);
+int launch_pack_weights(const ConvGeom& pass_geom, const float* const* host_w, void* packed, cudaStream_t st);
+int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
+                    const float* bias, float* out, cudaStream_t st);
+int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, float* const* host_gw,
+                    cudaStream_t st);
+// fp32 NCHW -> CL operand (and, optionally, the pitched NCHW bf16 copy wgrad reads gy from)
+int launch_stage_operand(const float* src, void* dst_cl, void* dst_nchw16, const cl::OperandLayout& l, int n, int c,
+                         int h, int w, cudaStream_t st);
+inline int nchw16_pitch(int w) { return (w + 7) & ~7; }
+
+}  // namespace seldq

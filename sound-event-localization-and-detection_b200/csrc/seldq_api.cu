@@ -1,6 +1,7 @@
 // extern "C" surface of libseldq.so (see include/seldq.h for the contract of every entry point).
 #include <cuda_runtime.h>
 
+#include "conv_cl.h"
 #include "conv_simt.cuh"
 #include "conv_umma.h"
 #include "geom.h"
@@ -26,33 +27,39 @@ int cuda_ready() {
   return SELDQ_OK;
 }
 
-// forward-orientation geometry (tap offsets are defined on it) + the shift list of one operand
-int shifts_for(const seldq_conv_desc_t* d, int which, MirrorSet* m) {
-  ConvGeom g;
-  const int rc = make_conv_geom(d, SELDQ_PASS_FWD, &g);
-  if (rc) return rc;
-  mirror_shifts(g, which, m->shifts, &m->nshifts);
-  return SELDQ_OK;
+// bf16 operands of a convolution (forward-orientation geometry): which = 0 -> x, 1 -> gy
+struct OperandInfo {
+  cl::OperandLayout lay;
+  int n, c, h, w;
+  size_t cl_bytes, t16_bytes;
+};
+OperandInfo operand_info(const ConvGeom& fwd, int which) {
+  OperandInfo o;
+  o.lay = which == 0 ? x_operand_layout(fwd) : gy_operand_layout(fwd);
+  o.n = fwd.N;
+  o.c = which == 0 ? fwd.R : fwd.P;
+  o.h = which == 0 ? fwd.IH : fwd.OH;
+  o.w = which == 0 ? fwd.IW : fwd.OW;
+  o.cl_bytes = align256((size_t)o.n * o.h * o.w * o.lay.Cp * 2);
+  o.t16_bytes = align256((size_t)o.n * o.c * o.h * nchw16_pitch(o.w) * 2);
+  return o;
 }
 
-// uses the caller's mirror set if given, otherwise builds it in the workspace at *offset
-int obtain_mirror(const seldq_conv_desc_t* d, int which, const float* src, const void* given, long long rows, int w,
-                  void* workspace, size_t workspace_bytes, size_t* offset, cudaStream_t st, MirrorSet* m) {
-  int rc = shifts_for(d, which, m);
-  if (rc) return rc;
-  if (given) {
-    m->data = given;
-    return SELDQ_OK;
+// bump allocator over the caller's workspace
+struct Workspace {
+  char* base;
+  size_t size, used;
+  void* take(size_t bytes) {
+    bytes = align256(bytes);
+    if (!base || used + bytes > size) return nullptr;
+    void* p = base + used;
+    used += bytes;
+    return p;
   }
-  const size_t need = mirror_bytes(rows, w, m->nshifts);
-  if (!workspace || *offset + need > workspace_bytes)
-    return fail(SELDQ_ERR_WORKSPACE, "workspace too small for the bf16 mirror set (%zu + %zu > %zu)", *offset, need,
-                workspace_bytes);
-  void* dst = (char*)workspace + *offset;
-  if ((rc = launch_cast_bf16_mirror(src, dst, rows, w, mirror_pitch(w), m->shifts, m->nshifts, st))) return rc;
-  m->data = dst;
-  *offset += need;
-  return SELDQ_OK;
+};
+int workspace_short(size_t need, const Workspace& ws) {
+  return fail(SELDQ_ERR_WORKSPACE, "workspace too small: %zu more bytes needed after %zu of %zu (see seldq_conv_workspace_bytes)",
+              need, ws.used, ws.size);
 }
 
 }  // namespace
@@ -78,35 +85,53 @@ extern "C" int seldq_conv_out_shape(const seldq_conv_desc_t* d, int32_t* out_h, 
   return SELDQ_OK;
 }
 
-// ---- bf16 mirror sets ---------------------------------------------------------------------------------
-extern "C" int seldq_bf16_pitch(int32_t w) { return mirror_pitch(w); }
-
-extern "C" int seldq_conv_mirror_shifts(const seldq_conv_desc_t* d, int32_t which, int32_t* shifts8, int32_t* nshifts) {
-  if (!shifts8 || !nshifts || (which != 0 && which != 1)) return fail(SELDQ_ERR_INVALID, "bad mirror-shift query");
-  MirrorSet m;
-  const int rc = shifts_for(d, which, &m);
+// ---- bf16 operand staging ---------------------------------------------------------------------------
+extern "C" int seldq_conv_operand_info(const seldq_conv_desc_t* d, int32_t which, int32_t* padded_channels,
+                                       int32_t* dense, size_t* cl_bytes, size_t* t16_bytes) {
+  if (which != 0 && which != 1) return fail(SELDQ_ERR_INVALID, "operand selector must be 0 (x) or 1 (gy)");
+  ConvGeom g;
+  const int rc = make_conv_geom(d, SELDQ_PASS_FWD, &g);
   if (rc) return rc;
-  for (int i = 0; i < m.nshifts; ++i) shifts8[i] = m.shifts[i];
-  *nshifts = m.nshifts;
+  const OperandInfo o = operand_info(g, which);
+  if (padded_channels) *padded_channels = o.lay.Cp;
+  if (dense) *dense = (o.lay.nc != g.tab.nc || g.tab.nc == 1) ? 1 : 0;
+  if (cl_bytes) *cl_bytes = o.cl_bytes;
+  if (t16_bytes) *t16_bytes = o.t16_bytes;
   return SELDQ_OK;
 }
 
-extern "C" size_t seldq_bf16_mirror_bytes(int64_t rows, int32_t w, int32_t nshifts) {
-  if (rows <= 0 || w <= 0 || nshifts <= 0) return 0;
-  return mirror_bytes(rows, w, nshifts);
+extern "C" int seldq_stage_operand(const seldq_conv_desc_t* d, int32_t which, const float* src, void* dst_cl,
+                                   void* dst_t16, void* stream) {
+  if (which != 0 && which != 1) return fail(SELDQ_ERR_INVALID, "operand selector must be 0 (x) or 1 (gy)");
+  if (!src || (!dst_cl && !dst_t16)) return fail(SELDQ_ERR_INVALID, "seldq_stage_operand: null pointer");
+  ConvGeom g;
+  int rc = make_conv_geom(d, SELDQ_PASS_FWD, &g);
+  if (rc) return rc;
+  if ((rc = cuda_ready())) return rc;
+  const OperandInfo o = operand_info(g, which);
+  return launch_stage_operand(src, dst_cl, dst_t16, o.lay, o.n, o.c, o.h, o.w, (cudaStream_t)stream);
 }
 
-extern "C" int seldq_cast_bf16_mirror(const float* src, void* dst_bf16, int64_t rows, int32_t w, const int32_t* shifts,
-                                      int32_t nshifts, void* stream) {
-  if (!src || !dst_bf16 || rows <= 0 || w <= 0 || !shifts || nshifts < 1 || nshifts > 8 || shifts[0] != 0)
-    return fail(SELDQ_ERR_INVALID, "seldq_cast_bf16_mirror: bad arguments (shifts[0] must be 0, at most 8 shifts)");
-  for (int i = 0; i < nshifts; ++i)
-    if (shifts[i] < 0 || shifts[i] > 7) return fail(SELDQ_ERR_INVALID, "mirror shifts must be in [0, 8)");
-  int rc = cuda_ready();
+extern "C" size_t seldq_conv_packed_bytes(const seldq_conv_desc_t* d, int32_t pass) {
+  ConvGeom g;
+  if ((pass != SELDQ_PASS_FWD && pass != SELDQ_PASS_DGRAD) || make_conv_geom(d, pass, &g)) return 0;
+  return align256(packed_weight_bytes(g));
+}
+
+extern "C" int seldq_conv_pack_weights(const seldq_conv_desc_t* d, int32_t pass, const float* const* host_w,
+                                       void* packed, void* stream) {
+  if (pass != SELDQ_PASS_FWD && pass != SELDQ_PASS_DGRAD)
+    return fail(SELDQ_ERR_INVALID, "weights are packed for the forward or the dgrad pass");
+  ConvGeom g;
+  int rc = make_conv_geom(d, pass, &g);
   if (rc) return rc;
-  int s[8];
-  for (int i = 0; i < nshifts; ++i) s[i] = shifts[i];
-  return launch_cast_bf16_mirror(src, dst_bf16, rows, w, mirror_pitch(w), s, nshifts, (cudaStream_t)stream);
+  if (!host_w) return fail(SELDQ_ERR_INVALID, "seldq_conv_pack_weights: null pointer");
+  for (int i = 0; i < g.tab.nw; ++i)
+    if (!host_w[i]) return fail(SELDQ_ERR_INVALID, "seldq_conv_pack_weights: weight %d is null", i);
+  if (packed_weight_bytes(g) == 0) return SELDQ_OK;
+  if (!packed) return fail(SELDQ_ERR_INVALID, "seldq_conv_pack_weights: null destination");
+  if ((rc = cuda_ready())) return rc;
+  return launch_pack_weights(g, host_w, packed, (cudaStream_t)stream);
 }
 
 extern "C" int seldq_cast_bf16(const float* src, void* dst_bf16, size_t n, void* stream) {
@@ -117,31 +142,35 @@ extern "C" int seldq_cast_bf16(const float* src, void* dst_bf16, size_t n, void*
 }
 
 extern "C" size_t seldq_conv_workspace_bytes(const seldq_conv_desc_t* d, int32_t pass) {
-  BlockTable t;
-  int oh, ow;
-  if (validate_conv(d, &t, &oh, &ow)) return 0;
+  ConvGeom g;
+  if (make_conv_geom(d, SELDQ_PASS_FWD, &g)) return 0;
   if (d->precision != SELDQ_PREC_BF16) return 0;
-  MirrorSet mx, mg;
-  if (shifts_for(d, 0, &mx) || shifts_for(d, 1, &mg)) return 0;
-  const size_t xb = mirror_bytes((long long)d->batch * d->cin * d->in_h, d->in_w, mx.nshifts);
-  const size_t gb = mirror_bytes((long long)d->batch * d->cout * oh, ow, mg.nshifts);
+  const OperandInfo ox = operand_info(g, 0), og = operand_info(g, 1);
   switch (pass) {
-    case SELDQ_PASS_FWD: return xb;
-    case SELDQ_PASS_DGRAD: return gb;
-    case SELDQ_PASS_WGRAD: return xb + gb;
+    case SELDQ_PASS_FWD: return ox.cl_bytes + seldq_conv_packed_bytes(d, SELDQ_PASS_FWD);
+    case SELDQ_PASS_DGRAD: return og.cl_bytes + seldq_conv_packed_bytes(d, SELDQ_PASS_DGRAD);
+    case SELDQ_PASS_WGRAD: {
+      size_t xb = ox.cl_bytes;
+      if (ox.lay.nc != g.tab.nc || g.tab.nc == 1) {   // narrow first layer: shifted mirror set of x instead
+        MirrorSet m;
+        mirror_shifts(g, 0, m.shifts, &m.nshifts);
+        xb = mirror_bytes((long long)g.N * g.R * g.IH, g.IW, m.nshifts);
+      }
+      return xb + og.t16_bytes;
+    }
     default: return 0;
   }
 }
 
 // ---- convolution ------------------------------------------------------------------------------------
-extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_bf16,
-                              const float* const* host_w, const float* bias, float* y, void* workspace,
-                              size_t workspace_bytes, void* stream) {
+extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
+                              const float* const* host_w, const void* packed_w, const float* bias, float* y,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   ConvGeom g;
   int rc = make_conv_geom(d, SELDQ_PASS_FWD, &g);
   if (rc) return rc;
   const bool bf16 = d->precision == SELDQ_PREC_BF16;
-  if (!host_w || !y || (!x && !(bf16 && x_bf16))) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: null pointer");
+  if (!host_w || !y || (!x && !(bf16 && x_cl))) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: null pointer");
   for (int i = 0; i < g.tab.nw; ++i)
     if (!host_w[i]) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: weight %d is null", i);
   if ((rc = cuda_ready())) return rc;
@@ -152,22 +181,34 @@ extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const 
     for (int i = 0; i < g.tab.nw; ++i) p.w[i] = host_w[i];
     return launch_conv_simt(p, st);
   }
-  MirrorSet mx;
-  size_t off = 0;
-  if ((rc = obtain_mirror(d, 0, x, x_bf16, (long long)d->batch * d->cin * d->in_h, d->in_w, workspace, workspace_bytes,
-                          &off, st, &mx)))
-    return rc;
-  return launch_umma_fprop(g, mx, host_w, bias, y, st);
+  Workspace ws{(char*)workspace, workspace_bytes, 0};
+  if (!x_cl) {
+    const OperandInfo o = operand_info(g, 0);
+    void* buf = ws.take(o.cl_bytes);
+    if (!buf) return workspace_short(o.cl_bytes, ws);
+    if ((rc = launch_stage_operand(x, buf, nullptr, o.lay, o.n, o.c, o.h, o.w, st))) return rc;
+    x_cl = buf;
+  }
+  const size_t pb = packed_weight_bytes(g);
+  if (!packed_w && pb) {
+    void* buf = ws.take(pb);
+    if (!buf) return workspace_short(pb, ws);
+    if ((rc = launch_pack_weights(g, host_w, buf, st))) return rc;
+    packed_w = buf;
+  }
+  return launch_cl_fprop(g, x_cl, host_w, packed_w, bias, y, st);
 }
 
-extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy_bf16,
-                                const float* const* host_w, float* gx, void* workspace, size_t workspace_bytes,
-                                void* stream) {
-  ConvGeom g;
+extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy_cl,
+                                const float* const* host_w, const void* packed_w, float* gx, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  ConvGeom g, fwd;
   int rc = make_conv_geom(d, SELDQ_PASS_DGRAD, &g);
   if (rc) return rc;
   const bool bf16 = d->precision == SELDQ_PREC_BF16;
-  if (!host_w || !gx || (!gy && !(bf16 && gy_bf16))) return fail(SELDQ_ERR_INVALID, "seldq_conv_dgrad: null pointer");
+  if (!host_w || !gx || (!gy && !(bf16 && gy_cl))) return fail(SELDQ_ERR_INVALID, "seldq_conv_dgrad: null pointer");
+  for (int i = 0; i < g.tab.nw; ++i)
+    if (!host_w[i]) return fail(SELDQ_ERR_INVALID, "seldq_conv_dgrad: weight %d is null", i);
   if ((rc = cuda_ready())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (!bf16) {
@@ -176,23 +217,37 @@ extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, con
     for (int i = 0; i < g.tab.nw; ++i) p.w[i] = host_w[i];
     return launch_conv_simt(p, st);
   }
-  MirrorSet mg;
-  size_t off = 0;
-  if ((rc = obtain_mirror(d, 1, gy, gy_bf16, (long long)d->batch * d->cout * g.IH, g.IW, workspace, workspace_bytes,
-                          &off, st, &mg)))
-    return rc;
-  return launch_umma_fprop(g, mg, host_w, nullptr, gx, st);
+  if ((rc = make_conv_geom(d, SELDQ_PASS_FWD, &fwd))) return rc;
+  Workspace ws{(char*)workspace, workspace_bytes, 0};
+  if (!gy_cl) {
+    const OperandInfo o = operand_info(fwd, 1);
+    void* buf = ws.take(o.cl_bytes);
+    if (!buf) return workspace_short(o.cl_bytes, ws);
+    if ((rc = launch_stage_operand(gy, buf, nullptr, o.lay, o.n, o.c, o.h, o.w, st))) return rc;
+    gy_cl = buf;
+  }
+  const size_t pb = packed_weight_bytes(g);
+  if (!packed_w && pb) {
+    void* buf = ws.take(pb);
+    if (!buf) return workspace_short(pb, ws);
+    if ((rc = launch_pack_weights(g, host_w, buf, st))) return rc;
+    packed_w = buf;
+  }
+  return launch_cl_fprop(g, gy_cl, host_w, packed_w, nullptr, gx, st);
 }
 
-extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_bf16, const float* gy,
-                                const void* gy_bf16, float* const* host_gw, float* gbias, void* workspace,
+extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_cl, const float* gy,
+                                const void* gy_t16, float* const* host_gw, float* gbias, void* workspace,
                                 size_t workspace_bytes, void* stream) {
   ConvGeom g;
   int rc = make_conv_geom(d, SELDQ_PASS_WGRAD, &g);
   if (rc) return rc;
   const bool bf16 = d->precision == SELDQ_PREC_BF16;
-  if (!host_gw || (!x && !(bf16 && x_bf16)) || (!gy && (gbias || !(bf16 && gy_bf16))))
-    return fail(SELDQ_ERR_INVALID, "seldq_conv_wgrad: null pointer");
+  const OperandInfo ox = operand_info(g, 0), og = operand_info(g, 1);
+  const bool narrow = bf16 && (ox.lay.nc != g.tab.nc || g.tab.nc == 1);   // first layer: mirror-set kernel, needs fp32 x
+  if (!host_gw || (!x && (!bf16 || narrow || !x_cl)) || (!gy && (gbias || !(bf16 && gy_t16))))
+    return fail(SELDQ_ERR_INVALID, "seldq_conv_wgrad: null pointer%s",
+                narrow && !x ? " (this layer's weight gradient reads the float32 input)" : "");
   if ((rc = cuda_ready())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t wbytes = (size_t)g.Oc * g.Ic * g.KH * g.KW * sizeof(float);
@@ -209,15 +264,34 @@ extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, cons
     for (int i = 0; i < g.tab.nw; ++i) p.gw[i] = host_gw[i];
     return launch_wgrad_simt(p, st);
   }
-  MirrorSet mx, mg;
-  size_t off = 0;
-  if ((rc = obtain_mirror(d, 0, x, x_bf16, (long long)d->batch * d->cin * d->in_h, d->in_w, workspace, workspace_bytes,
-                          &off, st, &mx)))
-    return rc;
-  if ((rc = obtain_mirror(d, 1, gy, gy_bf16, (long long)d->batch * d->cout * g.OH, g.OW, workspace, workspace_bytes,
-                          &off, st, &mg)))
-    return rc;
-  return launch_umma_wgrad(g, mx, mg, host_gw, st);
+  Workspace ws{(char*)workspace, workspace_bytes, 0};
+  if (!gy_t16) {
+    void* buf = ws.take(og.t16_bytes);
+    if (!buf) return workspace_short(og.t16_bytes, ws);
+    if ((rc = launch_stage_operand(gy, nullptr, buf, og.lay, og.n, og.c, og.h, og.w, st))) return rc;
+    gy_t16 = buf;
+  }
+  if (narrow) {
+    MirrorSet mx, mg;
+    mirror_shifts(g, 0, mx.shifts, &mx.nshifts);
+    mx.pitch = 0;
+    const size_t need = mirror_bytes((long long)g.N * g.R * g.IH, g.IW, mx.nshifts);
+    void* buf = ws.take(need);
+    if (!buf) return workspace_short(need, ws);
+    if ((rc = launch_cast_bf16_mirror(x, buf, (long long)g.N * g.R * g.IH, g.IW, mirror_pitch(g.IW), mx.shifts,
+                                      mx.nshifts, st)))
+      return rc;
+    mx.data = buf;
+    mg.data = gy_t16; mg.nshifts = 1; mg.shifts[0] = 0; mg.pitch = nchw16_pitch(g.OW);
+    return launch_umma_wgrad(g, mx, mg, host_gw, st);
+  }
+  if (!x_cl) {
+    void* buf = ws.take(ox.cl_bytes);
+    if (!buf) return workspace_short(ox.cl_bytes, ws);
+    if ((rc = launch_stage_operand(x, buf, nullptr, ox.lay, ox.n, ox.c, ox.h, ox.w, st))) return rc;
+    x_cl = buf;
+  }
+  return launch_cl_wgrad(g, x_cl, gy_t16, host_gw, st);
 }
 
 // ---- linear: 0.18 GFLOP per call in the reference configs -> always the fp32 FFMA kernels -----------

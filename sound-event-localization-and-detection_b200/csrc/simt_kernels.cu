@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "conv_cl.h"
 #include "conv_simt.cuh"
 #include "launch.h"
 
@@ -116,6 +117,56 @@ __global__ void __launch_bounds__(256) cast_bf16_mirror_kernel(const float* __re
   }
 }
 
+
+// fp32 NCHW -> channels-last bf16 operand [n][h][w][Cp] (conv_cl.h: each of the nc components padded to cpad
+// channels, pad channels zero) and, optionally, the pitched NCHW bf16 copy [n][c][h][pitch] that the
+// weight-gradient kernel reads gy from (pad columns zero).  One block transposes a tile of 64 padded
+// channels x 32 positions through shared memory: reads are coalesced along w, writes along the channels.
+__global__ void __launch_bounds__(256) stage_operand_kernel(const float* __restrict__ src,
+                                                            __nv_bfloat16* __restrict__ dst_cl,
+                                                            __nv_bfloat16* __restrict__ dst_t, int C, int H, int W,
+                                                            int nc, int cc, int cpad, int Cp, int pitch, int tiles_w,
+                                                            int tiles_c, long long total_blocks) {
+  __shared__ float tile[64][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
+    long long r = blk;
+    const int wt = (int)(r % tiles_w); r /= tiles_w;
+    const int ct = (int)(r % tiles_c); r /= tiles_c;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    const int w = wt * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int cl = warp + 8 * k;                 // padded channel within the tile
+      const int cp = ct * 64 + cl;
+      const int comp = cp / cpad, ci = cp - comp * cpad;
+      float v = 0.f;
+      if (cp < Cp && ci < cc) {
+        const int c = comp * cc + ci;
+        const long long row = ((long long)n * C + c) * H + h;
+        if (w < W) v = __ldg(src + row * W + w);
+        if (dst_t && w < pitch) dst_t[row * pitch + w] = __float2bfloat16_rn(v);
+      }
+      tile[cl][lane] = v;
+    }
+    __syncthreads();
+    if (dst_cl) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int wl = warp + 8 * k;
+        const int ww = wt * 32 + wl;
+        const int cp = ct * 64 + 2 * lane;
+        if (ww < W && cp < Cp) {
+          const __nv_bfloat162 o = __floats2bfloat162_rn(tile[2 * lane][wl], tile[2 * lane + 1][wl]);
+          *reinterpret_cast<__nv_bfloat162*>(dst_cl + (((long long)n * H + h) * W + ww) * Cp + cp) = o;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace simt
 
 // ---- host launchers ------------------------------------------------------------------------------
@@ -175,6 +226,22 @@ int launch_cast_bf16_mirror(const float* src, void* dst, long long rows, int w, 
   simt::cast_bf16_mirror_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), rows, w,
                                                                  pitch, s, nshifts);
   return check_launch("cast_bf16_mirror_kernel");
+}
+
+
+int launch_stage_operand(const float* src, void* dst_cl, void* dst_nchw16, const cl::OperandLayout& l, int n, int c,
+                         int h, int w, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(dst_cl) & 15) || (reinterpret_cast<uintptr_t>(dst_nchw16) & 15))
+    return fail(SELDQ_ERR_INVALID, "bf16 operand buffers must be 16-byte aligned");
+  const int pitch = nchw16_pitch(w);
+  const int tiles_w = (pitch + 31) / 32, tiles_c = (l.Cp + 63) / 64;
+  const long long total = (long long)tiles_w * tiles_c * h * n;
+  long long blocks = total < 148LL * 32 ? total : 148LL * 32;
+  if (blocks < 1) blocks = 1;
+  simt::stage_operand_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_cl),
+                                                              reinterpret_cast<__nv_bfloat16*>(dst_nchw16), c, h, w,
+                                                              l.nc, l.cc, l.cpad, l.Cp, pitch, tiles_w, tiles_c, total);
+  return check_launch("stage_operand_kernel");
 }
 
 }  // namespace seldq

@@ -1,0 +1,243 @@
+// tcgen05 weight-gradient kernel for the quaternion / dual-quaternion convolutions (channels-last x).
+//
+//   dWq[(a,o), (b,i), tap] = sum_{n,h,w} gy[n, a*Oc+o, h, w] * x[n, b*Ic+i, h + off_h(tap), w + off_w(tap)]
+//   gW_e[o, i, tap]        = sum_{(a,b): widx[a][b] = e} sign[a][b] * dWq[(a,o), (b,i), tap]     
+//
+// The contraction runs over positions.  A = gy from its pitched NCHW bf16 copy: time is contiguous, so a TMA
+// box [OS channels x 64 t] is a K-major operand and the rows of the M = 128 tile are gathered per component
+// (all components a x OS out channels).  B = x from its channels-last operand: a box [64 t x 64 ch] is an
+// MN-major operand, all Cp padded input channels form the N extent (one or two MMAs of <= 256 columns), and
+// the convolution tap is just an offset on the box's w / h coordinates.  One CTA owns (OS out channels of
+// every component) x (all in channels) x (a group of taps) and reduces a contiguous slice of the position
+// axis (split-K).  The dense 128 x Cp accumulator lives in TMEM; the epilogue folds it onto the COMPACT
+// gradients inside the CTA (sign-weighted sum over the (a,b) pairs of each compact tensor, through shared
+// memory) and adds the result with one atomicAdd per compact element -- the expanded gradient never
+// reaches HBM.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "conv_cl.h"
+#include "launch.h"
+#include "tensor_map.h"
+#include "umma_ptx.cuh"
+
+namespace seldq {
+namespace cl {
+
+__global__ void __launch_bounds__(kThreads, 1)
+qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
+                      const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[kWgradStages], empty_bar[kWgradStages], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile decode: blockIdx.x = tap_group * o_tiles + o_tile, blockIdx.y = split
+  const int o_tile = blockIdx.x % p.o_tiles;
+  const int tg = blockIdx.x / p.o_tiles;
+  const int tap0 = tg * p.taps_per_group;
+  const int ntap = min(p.taps_per_group, p.ntaps - tap0);
+  const int o0 = o_tile * p.OS;
+  const long long per = (p.ksteps + p.splits - 1) / p.splits;
+  const long long k_begin = (long long)blockIdx.y * per;
+  const long long k_end = min(p.ksteps, k_begin + per);
+  const int nk = (int)max(0LL, k_end - k_begin);
+
+  const uint32_t a_bytes = 128u * 128u;                    // [128 rows x 64 t] bf16
+  const int nstages = p.nstages;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    ptx::mbar_init(&done_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tm_g);
+    ptx::prefetch_tensormap(&tm_x);
+  }
+  if (warp == 1) ptx::tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (nk > 0) {
+    if (warp == 0) {
+      if (ptx::elect_one()) {
+        uint32_t slot = 0, parity = 0;
+        for (int ks = 0; ks < nk; ++ks) {
+          long long u = k_begin + ks;
+          const int wc = (int)(u % p.chunks_w); u /= p.chunks_w;
+          const int h = (int)(u % p.OH);
+          const int n = (int)(u / p.OH);
+          const int w0 = wc * 64;
+          ptx::mbar_wait(&empty_bar[slot], parity ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[slot], a_bytes + (uint32_t)ntap * p.b_tap_bytes);
+          uint8_t* st = smem + (size_t)slot * p.stage_bytes;
+          for (int a = 0; a < p.ncomp; ++a)
+            ptx::tma_load_4d(st + (size_t)a * p.OS * 128, &tm_g, &full_bar[slot], w0, h, a * p.g.Oc + o0, n);
+          for (int t = 0; t < ntap; ++t)
+            for (int c = 0; c < p.nchunks; ++c)
+              ptx::tma_load_4d(st + a_bytes + (size_t)t * p.b_tap_bytes + (size_t)c * 8192, &tm_x, &full_bar[slot],
+                               c * 64, w0 + p.off_w[tap0 + t], h + p.off_h[tap0 + t], n);
+          if (++slot == (uint32_t)nstages) { slot = 0; parity ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (ptx::elect_one()) {
+        // A: K-major, 128B swizzle: 8-row groups 1024 B apart (SBO), K advances inside the swizzled row
+        // B: MN-major, 128B swizzle: 64-channel chunks 8192 B apart (LBO), 8 t-rows 1024 B apart (SBO),
+        //    a K = 16 slab is 16 rows = 2048 B
+        const uint64_t a_hi = ptx::make_smem_desc_hi(16, 1024, ptx::kSwizzle128B);
+        const uint64_t b_hi = ptx::make_smem_desc_hi(8192, 1024, ptx::kSwizzle128B);
+        const uint32_t base = ptx::smem_u32(smem);
+        uint32_t slot = 0, parity = 0;
+        for (int ks = 0; ks < nk; ++ks) {
+          ptx::mbar_wait(&full_bar[slot], parity);
+          ptx::tc_fence_after();
+          const uint32_t st = base + slot * p.stage_bytes;
+          for (int t = 0; t < ntap; ++t)
+            for (int n0 = 0; n0 < p.Cp; n0 += 256) {
+              const uint32_t nn = (uint32_t)min(256, p.Cp - n0);
+              const uint32_t idesc = ptx::make_idesc_bf16(128, nn, 0, 1, 0, 0);
+              const uint32_t b0 = st + a_bytes + (uint32_t)t * p.b_tap_bytes + (uint32_t)(n0 / 64) * 8192u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_f16(tmem_base + (uint32_t)(t * p.Cp + n0), ptx::smem_desc(a_hi, st + k * 32u),
+                              ptx::smem_desc(b_hi, b0 + k * 2048u), idesc, (ks > 0 || k > 0) ? 1u : 0u);
+            }
+          ptx::umma_commit(&empty_bar[slot]);
+          if (++slot == (uint32_t)nstages) { slot = 0; parity ^= 1; }
+        }
+        ptx::umma_commit(&done_bar);
+      }
+    } else {
+      // ===== epilogue ==============================================================================
+      const int q = warp & 3;
+      const int row = q * 32 + lane;                 // accumulator row = TMEM lane = (a, ol)
+      const int et = threadIdx.x - 64;               // 0..127 among the epilogue threads
+      ptx::mbar_wait(&done_bar, 0);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+      const ConvGeom& g = p.g;
+      // all MMAs have retired: the operand ring is free and is reused as a [128][ncomp*16 + 1] fp32 staging tile
+      float* stg = reinterpret_cast<float*>(smem);
+      const int pitch = p.ncomp * 16 + 1;
+      const int targets = g.tab.nw * p.OS * 16;
+      for (int t = 0; t < ntap; ++t)
+        for (int ic = 0; ic < p.cpad_in; ic += 16) {
+          for (int b = 0; b < p.ncomp; ++b) {
+            uint32_t v[16];
+            ptx::tmem_ld16(t_row + (uint32_t)(t * p.Cp + b * p.cpad_in + ic), v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) stg[row * pitch + b * 16 + j] = __uint_as_float(v[j]);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int tg_i = et; tg_i < targets; tg_i += 128) {
+            const int il = tg_i & 15;
+            int rr = tg_i >> 4;
+            const int ol = rr % p.OS;
+            const int e = rr / p.OS;
+            if (o0 + ol < g.Oc && ic + il < g.Ic) {
+              float acc = 0.f;
+              for (int k = 0; k < p.pair_n[e]; ++k) {
+                const float val = stg[(p.pair_a[e][k] * p.OS + ol) * pitch + p.pair_b[e][k] * 16 + il];
+                acc += p.pair_neg[e][k] ? -val : val;
+              }
+              atomicAdd(p.gw[e] + (long long)(o0 + ol) * g.wsO + (long long)(ic + il) * g.wsI +
+                            (long long)(tap0 + t) * g.wsT, acc);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace cl
+
+int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, float* const* host_gw,
+                    cudaStream_t st) {
+  using namespace cl;
+  if (g.sh != 1 || g.sw != 1) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 tensor-core path implements stride 1 only");
+  const int ntaps = g.KH * g.KW;
+  if (ntaps > kMaxTaps) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path supports at most %d taps", kMaxTaps);
+  const int nc = g.tab.nc;
+  const OperandLayout lx = x_operand_layout(g);
+  if (lx.nc != nc || lx.Cp % 64) return fail(SELDQ_ERR_INVALID, "channels-last wgrad needs a component-padded x operand");
+  if (lx.Cp > 512) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 wgrad supports at most 512 padded input channels, got %d", lx.Cp);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  for (int i = 0; i < g.tab.nw; ++i) p.gw[i] = host_gw[i];
+  p.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) {
+    p.off_h[t] = (t / g.KW) * g.dh - g.ph;
+    p.off_w[t] = (t % g.KW) * g.dw - g.pw;
+  }
+  p.OH = g.OH; p.OW = g.OW; p.N = g.N;
+  p.ncomp = nc;
+  p.OS = 128 / nc;
+  p.o_tiles = (g.Oc + p.OS - 1) / p.OS;
+  p.cpad_in = lx.cpad; p.Cp = lx.Cp; p.nchunks = lx.Cp / 64;
+  for (int a = 0; a < nc; ++a)
+    for (int b = 0; b < nc; ++b) {
+      const int e = g.tab.widx[a][b];
+      if (e < 0) continue;
+      const int k = p.pair_n[e]++;
+      p.pair_a[e][k] = (int8_t)a; p.pair_b[e][k] = (int8_t)b; p.pair_neg[e][k] = (int8_t)(g.tab.sign[a][b] < 0);
+    }
+  p.taps_per_group = 256 / lx.Cp;
+  if (p.taps_per_group < 1) p.taps_per_group = 1;
+  if (p.taps_per_group > ntaps) p.taps_per_group = ntaps;
+  p.tap_groups = (ntaps + p.taps_per_group - 1) / p.taps_per_group;
+  int cols = 32;
+  while (cols < p.taps_per_group * lx.Cp) cols <<= 1;
+  p.tmem_cols = cols;
+  p.chunks_w = (g.OW + 63) / 64;
+  p.ksteps = (long long)g.N * g.OH * p.chunks_w;
+  const int tiles = p.tap_groups * p.o_tiles;
+  long long splits = (2LL * num_sms() + tiles - 1) / tiles;
+  if (splits > p.ksteps) splits = p.ksteps;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  p.splits = (int)splits;
+  p.b_tap_bytes = (uint32_t)lx.Cp * 128u;
+  p.stage_bytes = 128u * 128u + (uint32_t)p.taps_per_group * p.b_tap_bytes;
+  size_t ns = (208 * 1024) / p.stage_bytes;
+  if (ns > (size_t)kWgradStages) ns = kWgradStages;
+  if (ns < 2) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 wgrad: operand stage of %u B does not fit twice", p.stage_bytes);
+  p.nstages = (int)ns;
+  size_t smem = ns * p.stage_bytes;
+  const size_t stg = (size_t)128 * (nc * 16 + 1) * 4;
+  if (smem < stg) smem = stg;
+  smem += 4096;   // slack: the tensor core may fetch past the logical end of the last operand tile
+
+  // gy: (pitch, H, C, N) view of the pitched NCHW bf16 copy, box {64 t, 1, OS channels, 1}
+  alignas(64) CUtensorMap tm_g, tm_x;
+  {
+    const uint64_t pitch = (uint64_t)nchw16_pitch(g.OW);
+    const uint64_t dims[4] = {pitch, (uint64_t)g.OH, (uint64_t)g.P, (uint64_t)g.N};
+    const uint64_t strides[3] = {pitch * 2, pitch * g.OH * 2, pitch * g.OH * g.P * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)p.OS, 1};
+    const int rc = encode_tensor_map(&tm_g, gy_nchw16, 2, 4, dims, strides, box, 3);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)lx.Cp, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+    const uint64_t strides[3] = {(uint64_t)lx.Cp * 2, (uint64_t)lx.Cp * 2 * g.IW, (uint64_t)lx.Cp * 2 * g.IW * g.IH};
+    const uint32_t box[4] = {64, 64, 1, 1};
+    const int rc = encode_tensor_map(&tm_x, x_cl, 2, 4, dims, strides, box, 3);
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaFuncSetAttribute(qconv_cl_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "wgrad smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+  dim3 grid(tiles, p.splits);
+  qconv_cl_wgrad_kernel<<<grid, kThreads, smem, st>>>(tm_g, tm_x, p);
+  return check_launch("qconv_cl_wgrad_kernel");
+}
+
+}  // namespace seldq

@@ -108,32 +108,54 @@ def _pair(v):
     return int(v), int(v)
 
 
-def bf16_mirror(x, shifts=(0,)):
-    """bf16 mirror set of an NCW / NCHW fp32 tensor in the layout the tensor-core kernels read
-    through TMA: one copy per entry of `shifts` (row shifted right by that many elements), row
-    pitch seldq_bf16_pitch(w) (see include/seldq.h).  Returns a (len(shifts), *x.shape[:-1], pitch)
-    bf16 tensor."""
+def _operand_info(desc, which):
+    """(padded channels, dense?, CL operand bytes, T16 operand bytes) of x (which=0) or gy (which=1)."""
     import ctypes
-    _require_cuda_f32(x, "input")
-    x = x.contiguous()
-    w = x.shape[-1]
+    cp, dense = ctypes.c_int32(), ctypes.c_int32()
+    clb, t16b = ctypes.c_size_t(), ctypes.c_size_t()
+    _lib.check(_lib.lib().seldq_conv_operand_info(ctypes.byref(desc), which, ctypes.byref(cp), ctypes.byref(dense),
+                                                  ctypes.byref(clb), ctypes.byref(t16b)))
+    return cp.value, bool(dense.value), clb.value, t16b.value
+
+
+def stage_operand(t, desc, which, want_cl=True, want_t16=False):
+    """bf16 operand copies of an NCW / NCHW fp32 tensor for the tensor-core kernels (include/seldq.h):
+    the channels-last operand (forward / dgrad / wgrad's x) and / or the pitched NCHW copy (wgrad's gy).
+    Returns (cl, t16) uint8 buffers (None where not requested)."""
+    import ctypes
+    _, _, clb, t16b = _operand_info(desc, which)
+    cl = torch.empty(clb, dtype=torch.uint8, device=t.device) if want_cl else None
+    t16 = torch.empty(t16b, dtype=torch.uint8, device=t.device) if want_t16 else None
+    _timed("stage_operand_kernel", 0.0, 1, lambda: _lib.check(
+        _lib.lib().seldq_stage_operand(ctypes.byref(desc), which, t.data_ptr(), _ptr(cl), _ptr(t16), _stream())))
+    return cl, t16
+
+
+# packed bf16 weight tiles, one set per (layer, pass); re-packed when a weight's version counter moves
+# (optimizer.step updates in place) and always while a CUDA graph is being captured, so that a replayed
+# step packs the weights it is about to use
+_PACKED = {}
+
+
+def packed_weights(weights, desc, pass_):
+    import ctypes
     L = _lib.lib()
-    pitch = L.seldq_bf16_pitch(w)
-    out = torch.empty((len(shifts),) + tuple(x.shape[:-1]) + (pitch,), dtype=torch.bfloat16, device=x.device)
-    rows = x.numel() // w
-    arr = (ctypes.c_int32 * len(shifts))(*shifts)
-    with torch.cuda.device(x.device):
-        _timed("cast_bf16_mirror_kernel", 0.0, 1, lambda: _lib.check(
-            L.seldq_cast_bf16_mirror(x.data_ptr(), out.data_ptr(), rows, w, arr, len(shifts), _stream())))
-    return out
-
-
-def _mirror_shifts(desc, which):
-    import ctypes
-    arr = (ctypes.c_int32 * 8)()
-    n = ctypes.c_int32()
-    _lib.check(_lib.lib().seldq_conv_mirror_shifts(ctypes.byref(desc), which, arr, ctypes.byref(n)))
-    return tuple(arr[i] for i in range(n.value))
+    nbytes = L.seldq_conv_packed_bytes(ctypes.byref(desc), pass_)
+    if nbytes == 0:
+        return None
+    key = (tuple(w.data_ptr() for w in weights), pass_, desc.algebra, desc.cin, desc.cout, desc.k_h, desc.k_w)
+    versions = tuple(w._version for w in weights)
+    ent = _PACKED.get(key)
+    capturing = torch.cuda.is_current_stream_capturing()
+    if ent is not None and ent[0] == versions and not capturing and ent[1].numel() == nbytes:
+        return ent[1]
+    buf = ent[1] if ent is not None and ent[1].numel() == nbytes else torch.empty(
+        nbytes, dtype=torch.uint8, device=weights[0].device)
+    wp = _lib.ptr_array([w.data_ptr() for w in weights])
+    _timed("pack_weights_kernel", 0.0, 1, lambda: _lib.check(
+        L.seldq_conv_pack_weights(ctypes.byref(desc), pass_, wp, buf.data_ptr(), _stream())))
+    _PACKED[key] = (versions, buf)
+    return buf
 
 
 def _conv_desc(algebra, prec, x_shape, cout, ksize, stride, padding, dilation):
@@ -179,17 +201,23 @@ class _BlockConv(torch.autograd.Function):
         out_shape = (x.shape[0], cout, ow.value) if x.dim() == 3 else (x.shape[0], cout, oh.value, ow.value)
         y = torch.empty(out_shape, dtype=torch.float32, device=x.device)
         wp = _lib.ptr_array([w.data_ptr() for w in weights])
+        bf16 = prec == PREC_BF16
         with torch.cuda.device(x.device):
-            x16 = bf16_mirror(x, _mirror_shifts(desc, 0)) if prec == PREC_BF16 else None
-            kern = "qconv_umma_fprop_kernel" if prec == PREC_BF16 else "conv_simt_kernel"
+            x_cl = pk = None
+            if bf16:
+                x_cl, _ = stage_operand(x, desc, 0)
+                pk = packed_weights(weights, desc, PASS_FWD)
+            kern = "qconv_cl_fprop_kernel" if bf16 else "conv_simt_kernel"
             _timed(kern, _conv_flop(desc, oh.value, ow.value), 1, lambda: _lib.check(
-                L.seldq_conv_fwd(ctypes.byref(desc), x.data_ptr(), _ptr(x16), wp, _ptr(bias), y.data_ptr(),
-                                 None, 0, _stream())))
+                L.seldq_conv_fwd(ctypes.byref(desc), x.data_ptr(), _ptr(x_cl), wp, _ptr(pk), _ptr(bias),
+                                 y.data_ptr(), None, 0, _stream())))
         ctx.desc = desc
         ctx.out_hw = (oh.value, ow.value)
         ctx.has_bias = bias is not None
-        # the tensor-core wgrad reads the bf16 mirror only: keep that instead of the fp32 input
-        ctx.save_for_backward(x16 if prec == PREC_BF16 else x, *weights)
+        # the tensor-core wgrad reads the channels-last bf16 operand only: keep that instead of the fp32
+        # input (except for the narrow first layer, whose wgrad stages its own copy of the fp32 input)
+        ctx.x_is_cl = bf16 and not _operand_info(desc, 0)[1]
+        ctx.save_for_backward(x_cl if ctx.x_is_cl else x, *weights)
         return y
 
     @staticmethod
@@ -210,25 +238,34 @@ class _BlockConv(torch.autograd.Function):
         gws = [None] * len(weights)
         wp = _lib.ptr_array([w.data_ptr() for w in weights])
         with torch.cuda.device(dev):
-            gy16 = bf16_mirror(gy, _mirror_shifts(desc, 1)) if bf16 and (need_x or need_w) else None
+            need_w_any = need_w or need_b
+            gy_cl = gy_t16 = None
+            if bf16 and (need_x or need_w_any):
+                gy_cl, gy_t16 = stage_operand(gy, desc, 1, want_cl=need_x, want_t16=need_w_any)
             if need_x:
                 if desc.ndim == 1:
                     gx = torch.empty((desc.batch, desc.cin, desc.in_w), dtype=torch.float32, device=dev)
                 else:
                     gx = torch.empty((desc.batch, desc.cin, desc.in_h, desc.in_w), dtype=torch.float32, device=dev)
-                kern = "qconv_umma_fprop_kernel" if bf16 else "conv_simt_kernel"
+                pk = packed_weights(weights, desc, PASS_DGRAD) if bf16 else None
+                kern = "qconv_cl_fprop_kernel" if bf16 else "conv_simt_kernel"
                 _timed(kern, _conv_flop(desc, *ctx.out_hw), 1, lambda: _lib.check(
-                    L.seldq_conv_dgrad(ctypes.byref(desc), gy.data_ptr(), _ptr(gy16), wp, gx.data_ptr(),
+                    L.seldq_conv_dgrad(ctypes.byref(desc), gy.data_ptr(), _ptr(gy_cl), wp, _ptr(pk), gx.data_ptr(),
                                        None, 0, _stream())))
-            if need_w or need_b:
+            if need_w_any:
                 gws = [torch.empty_like(w) for w in weights]
                 gb = torch.empty(desc.cout, dtype=torch.float32, device=dev) if need_b else None
                 gp = _lib.ptr_array([g.data_ptr() for g in gws])
-                kern = "qconv_umma_wgrad_kernel" if bf16 else "wgrad_simt_kernel"
+                x_cl = xs if ctx.x_is_cl else None
+                x32 = None if ctx.x_is_cl else xs
+                work = None
+                if bf16 and not ctx.x_is_cl:      # narrow first layer: the library stages x itself
+                    work = torch.empty(L.seldq_conv_workspace_bytes(ctypes.byref(desc), PASS_WGRAD), dtype=torch.uint8,
+                                       device=dev)
+                kern = "qconv_cl_wgrad_kernel" if bf16 else "wgrad_simt_kernel"
                 _timed(kern, _conv_flop(desc, *ctx.out_hw), 1 + (1 if need_b else 0), lambda: _lib.check(
-                    L.seldq_conv_wgrad(ctypes.byref(desc), None if bf16 else xs.data_ptr(),
-                                       xs.data_ptr() if bf16 else None, gy.data_ptr(), _ptr(gy16), gp,
-                                       _ptr(gb), None, 0, _stream())))
+                    L.seldq_conv_wgrad(ctypes.byref(desc), _ptr(x32), _ptr(x_cl), gy.data_ptr(), _ptr(gy_t16), gp,
+                                       _ptr(gb), _ptr(work), 0 if work is None else work.numel(), _stream())))
         return (gx, gb, None, None, None, None, None) + tuple(gws)
 
 

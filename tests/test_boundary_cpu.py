@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(seldq):
     assert declared, "no declarations parsed"
     assert declared <= exported, sorted(declared - exported)
     lib = seldq._lib.lib()
-    assert lib.seldq_abi_version() == 1
+    assert lib.seldq_abi_version() == 2
     assert set(seldq._lib.exported_symbols()) <= exported
 
 
@@ -48,14 +48,25 @@ def test_descriptor_validation_runs_without_gpu(seldq):
     assert lib.seldq_stft_shape(1920000, 512, 112, 1, 1, ctypes.byref(nb), ctypes.byref(nf)) == 0
     assert (nb.value, nf.value) == (256, 4800)
     d16 = L.ConvDesc(L.ALG_DQ, L.PREC_BF16, 1, 1, 384, 384, 1, 4800, 1, 3, 1, 1, 0, 1, 1, 1)
-    # bf16 path: x and gy each need the mirror copies for tap offsets -1, 0, +1 -> shifts {0, 1, 7}
-    shifts, n = (ctypes.c_int32 * 8)(), ctypes.c_int32()
-    assert lib.seldq_conv_mirror_shifts(ctypes.byref(d16), 0, shifts, ctypes.byref(n)) == 0
-    assert sorted(shifts[:n.value]) == [0, 1, 7] and shifts[0] == 0
-    assert lib.seldq_bf16_pitch(4800) == 4808
-    one = lib.seldq_bf16_mirror_bytes(384, 4800, 3)
-    assert one >= 3 * 384 * 4808 * 2
-    assert lib.seldq_conv_workspace_bytes(ctypes.byref(d16), L.PASS_WGRAD) == 2 * one
+    # bf16 path: channels-last operands, every component padded to a multiple of 16 channels
+    cp, dense = ctypes.c_int32(), ctypes.c_int32()
+    clb, t16b = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.seldq_conv_operand_info(ctypes.byref(d16), 0, ctypes.byref(cp), ctypes.byref(dense), ctypes.byref(clb),
+                                       ctypes.byref(t16b)) == 0
+    assert (cp.value, dense.value) == (384, 0)
+    assert clb.value >= 4800 * 384 * 2 and t16b.value >= 384 * 4800 * 2
+    # CNN layers: 24 channels per component -> 32, first layer (1 channel per component) -> dense, 16 channels
+    cnn1 = L.ConvDesc(L.ALG_DQ, L.PREC_BF16, 2, 1, 192, 192, 32, 4800, 3, 3, 1, 1, 1, 1, 1, 1)
+    assert lib.seldq_conv_operand_info(ctypes.byref(cnn1), 0, ctypes.byref(cp), ctypes.byref(dense), None, None) == 0
+    assert (cp.value, dense.value) == (256, 0)
+    cnn0 = L.ConvDesc(L.ALG_DQ, L.PREC_BF16, 2, 1, 8, 192, 256, 4800, 3, 3, 1, 1, 1, 1, 1, 1)
+    assert lib.seldq_conv_operand_info(ctypes.byref(cnn0), 0, ctypes.byref(cp), ctypes.byref(dense), None, None) == 0
+    assert (cp.value, dense.value) == (16, 1)
+    assert lib.seldq_conv_packed_bytes(ctypes.byref(cnn0), L.PASS_FWD) == 0
+    # packed compact weights: 8 images x 3 taps x 3 slabs x (48 x 16) bf16 -- never the expanded weight
+    assert lib.seldq_conv_packed_bytes(ctypes.byref(d16), L.PASS_FWD) == 8 * 3 * 3 * 48 * 16 * 2
+    assert lib.seldq_conv_packed_bytes(ctypes.byref(d16), L.PASS_DGRAD) == 8 * 3 * 3 * 48 * 16 * 2
+    assert lib.seldq_conv_workspace_bytes(ctypes.byref(d16), L.PASS_FWD) == clb.value * 0 + 4800 * 384 * 2 + 8 * 3 * 3 * 48 * 32
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -60,11 +60,35 @@ def test_bf16_path_rejects_shapes_it_cannot_serve(seldq):
     ws = [cuda(d["w%d" % i]) for i in range(4)]
     with seldq.precision("bf16"), pytest.raises(NotImplementedError, match="stride 1"):
         seldq.block_conv(cuda(d["x"]), ws, None, 2, 1, 2, seldq._lib.ALG_Q)
-    # ... and channel counts that fit neither the compact nor the dense mode (12 per component, 96 in total)
-    x = torch.randn(1, 96, 64, device="cuda")
-    ws = [torch.randn(12, 12, 3, device="cuda") for _ in range(8)]
-    with seldq.precision("bf16"), pytest.raises(NotImplementedError, match="multiple of 8"):
-        seldq.block_conv(x, ws, None, 1, 1, 1, seldq._lib.ALG_DQ)
+    # ... and more taps than the tap table holds
+    x = torch.randn(1, 64, 16, 64, device="cuda")
+    ws = [torch.randn(8, 8, 5, 5, device="cuda") for _ in range(8)]
+    with seldq.precision("bf16"), pytest.raises(NotImplementedError, match="at most 9 taps"):
+        seldq.block_conv(x, ws, None, 1, 2, 1, seldq._lib.ALG_DQ)
+
+
+@pytest.mark.parametrize("alg,cc,k,pad,dil,T", [("DQ", 12, 3, 2, 2, 200), ("Q", 20, 3, 1, 1, 131), ("DQ", 5, 1, 0, 1, 64),
+                                                ("Q", 3, 3, 3, 3, 77)])
+def test_conv_bf16_odd_channel_counts_vs_oracle(seldq, alg, cc, k, pad, dil, T):
+    """Channel counts per component that are not multiples of 16 (padded inside the bf16 operand) and below 8
+    (dense mode), checked against the oracle on seeded inputs (rel 2e-2, north_star bf16 tolerance)."""
+    rng = np.random.default_rng(7)
+    nc = NW[alg]
+    x = rng.standard_normal((2, nc * cc, T)).astype(np.float32)
+    ws = [(0.2 * rng.standard_normal((cc, cc, k))).astype(np.float32) for _ in range(nc)]
+    gy = rng.standard_normal((2, nc * cc, T + 2 * pad - dil * (k - 1))).astype(np.float32)
+    f64 = lambda a: a.astype(np.float64)
+    y_ref = A.qconv(f64(x), [f64(w) for w in ws], None, 1, pad, dil, alg)
+    gx_ref, gw_ref, _ = A.qconv_backward(f64(x), [f64(w) for w in ws], f64(gy), 1, pad, dil, alg)
+    xt = cuda(x).requires_grad_(True)
+    wt = [cuda(w).requires_grad_(True) for w in ws]
+    with seldq.precision("bf16"):
+        y = seldq.block_conv(xt, wt, None, 1, pad, dil, seldq._lib.ALG_Q if alg == "Q" else seldq._lib.ALG_DQ)
+        y.backward(cuda(gy))
+    assert A.rel_err(y.detach().cpu().numpy(), y_ref) < 2e-2
+    assert A.rel_err(xt.grad.cpu().numpy(), gx_ref) < 2e-2
+    for i in range(nc):
+        assert A.rel_err(wt[i].grad.cpu().numpy(), gw_ref[i]) < 2e-2
 
 
 @pytest.mark.parametrize("name", golden_names("linear"))
