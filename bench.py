@@ -255,7 +255,7 @@ def main():
 
     if rank == 0:
         peaks = load_peaks()
-        k = prof["kernels"].get("qconv_umma_fprop_kernel" if args.precision == "bf16" else "conv_simt_kernel", None)
+        k = prof["kernels"].get("qconv_cl_fprop_kernel" if args.precision == "bf16" else "conv_simt_kernel", None)
         roof = None
         if k and k["ms"] > 0:
             ach = k["flop"] / (k["ms"] / 1e3) / 1e12

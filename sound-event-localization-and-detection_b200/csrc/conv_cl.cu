@@ -38,10 +38,13 @@
 namespace seldq {
 namespace cl {
 
+template <int GC>
 __global__ void __launch_bounds__(kThreads, 1)
 qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so role branches and the MMA loop compile to the
+  // uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   // layout: [activation ring][barriers, 1 KB][weight tiles][slack]
   uint8_t* a_ring = smem;
@@ -90,7 +93,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc_cols = (uint32_t)(p.gc * p.NBp);
+  const uint32_t acc_cols = (uint32_t)(GC * p.NBp);
 
   if (warp == 0) {
     // ===== TMA producer ============================================================================
@@ -125,11 +128,14 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     }
   } else if (warp == 1) {
     // ===== MMA issuer ==============================================================================
-    if (ptx::elect_one()) {
+    // The whole warp runs this loop convergently so that descriptors, table entries (constant bank) and
+    // addresses stay in uniform registers; one elected lane issues the tcgen05 instructions.
+    {
+      const bool leader = ptx::elect_one();
       const uint64_t a_hi = ptx::make_smem_desc_hi(16, p.a_sbo, p.a_swz);                 // K-major, swizzled
       const uint64_t b_hi = ptx::make_smem_desc_hi((uint32_t)p.NBp * 16u, 128, ptx::kSwizzleNone);
       const uint32_t idesc = ptx::make_idesc_bf16(kTileM, (uint32_t)p.NBp, 0, 0, 0, 0);
-      const uint32_t a_base = ptx::smem_u32(a_ring), b_base = ptx::smem_u32(b_img);
+      const uint32_t a_base = ptx::smem_u32(a_ring), b_lo16 = ptx::smem_u32(b_img) >> 4;
       if (!p.dense) ptx::mbar_wait(w_bar, 0);
       uint32_t slot = 0, parity = 0, it = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
@@ -147,26 +153,28 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
             ptx::mbar_wait(&full_bar[slot], parity);
             ptx::tc_fence_after();
             const uint32_t a_stage = a_base + slot * p.stage_bytes;
-            for (int s = 0; s < p.slabs_per_chunk; ++s) {
-              const int ch0 = c * p.BK + s * 16;
-              const int b = ch0 / p.cpad_in;
-              const int j = (ch0 - b * p.cpad_in) >> 4;
+            const uint32_t tap16 = b_lo16 + (((uint32_t)(tap * p.J) * p.slab_bytes) >> 4);
+            int row = (c * p.slabs_per_chunk) * p.ncomp_out + group * GC;
+            for (int s = 0; s < p.slabs_per_chunk; ++s, row += p.ncomp_out) {
               const uint64_t a_desc = ptx::smem_desc(a_hi, a_stage + (uint32_t)s * 32u);
-              const uint32_t w_off = (uint32_t)(tap * p.J + j) * p.slab_bytes;
-              for (int al = 0; al < p.gc; ++al) {
-                const int a = group * p.gc + al;
-                const int img = p.op_img[b][a];
-                if (img < 0) continue;
-                const uint64_t b_desc = ptx::smem_desc(b_hi, b_base + (uint32_t)img * p.img_bytes + w_off);
-                ptx::umma_f16(d_base + (uint32_t)(al * p.NBp), a_desc, b_desc,
-                              idesc | ((uint32_t)p.op_neg[b][a] << 14), (written >> al) & 1u);
-                written |= 1u << al;
+#pragma unroll
+              for (int al = 0; al < GC; ++al) {
+                const uint32_t e = p.op_tbl[row + al];
+                if (e & 1u) {
+                  const uint64_t b_desc = b_hi | (uint64_t)((tap16 + (e >> 2)) & 0x3fffu);
+                  if (leader)
+                    ptx::umma_f16(d_base + (uint32_t)(al * p.NBp), a_desc, b_desc, idesc | ((e & 2u) << 13),
+                                  (written >> al) & 1u);
+                  written |= 1u << al;
+                }
               }
             }
-            ptx::umma_commit(&empty_bar[slot]);    // frees the ring slot once these MMAs retire
+            if (leader) ptx::umma_commit(&empty_bar[slot]);    // frees the ring slot once these MMAs retire
+            __syncwarp();
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }
-        ptx::umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
+        if (leader) ptx::umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {
@@ -188,8 +196,8 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
       float* out_row = p.out + (long long)n * p.out_sN + (long long)h * p.out_sH + w;
-      for (int al = 0; al < p.gc; ++al) {
-        const int ch_base = (group * p.gc + al) * p.Pc;
+      for (int al = 0; al < GC; ++al) {
+        const int ch_base = (group * GC + al) * p.Pc;
         for (int c0 = 0; c0 < p.Pc; c0 += 16) {
           uint32_t v[16];
           ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
@@ -197,14 +205,15 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
           if (w_ok) {
             float* dst = out_row + (long long)(ch_base + c0) * p.out_sC;
             const int lim = p.Pc - c0;
+            if (lim >= 16 && p.bias == nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (j < lim) {
-                float y = __uint_as_float(v[j]);
-                if (p.bias) y += __ldg(p.bias + ch_base + c0 + j);
-                *dst = y;
+              for (int j = 0; j < 16; ++j) { *dst = __uint_as_float(v[j]); dst += p.out_sC; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (j < lim) *dst = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch_base + c0 + j) : 0.f);
+                dst += p.out_sC;
               }
-              dst += p.out_sC;
             }
           }
         }
@@ -405,6 +414,22 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
       const int t = p->group_order[j]; p->group_order[j] = p->group_order[j - 1]; p->group_order[j - 1] = t;
     }
 
+  // MMA op table: entry [(chunk, slab), out component a] = valid | neg << 1 | (byte offset of the weight
+  // tile of (image, slab-in-component) inside the resident set) >> 4 << 2, read from the constant bank by
+  // the MMA-issuing warp
+  if (p->chunks * p->slabs_per_chunk * p->ncomp_out > cl::kOpTableEntries)
+    return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: too many (slab, component) pairs for the MMA op table");
+  for (int cs = 0; cs < p->chunks * p->slabs_per_chunk; ++cs)
+    for (int a = 0; a < p->ncomp_out; ++a) {
+      const int ch0 = cs * 16;
+      const int b = ch0 / l.cpad;
+      const int j = (ch0 - b * l.cpad) >> 4;
+      const int img = p->op_img[b][a];
+      p->op_tbl[cs * p->ncomp_out + a] =
+          img < 0 ? 0u
+                  : (1u | ((uint32_t)p->op_neg[b][a] << 1) |
+                     ((((uint32_t)img * p->img_bytes + (uint32_t)j * p->slab_bytes) >> 4) << 2));
+    }
   const int acc_cols = p->gc * p->NBp;
   p->acc_stages = acc_cols * 2 <= 512 ? 2 : 1;
   int cols = 32;
@@ -450,10 +475,18 @@ int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* ho
   alignas(64) CUtensorMap tm;
   rc = encode_cl_map(&tm, in_cl, l, g.IW, g.IH, g.N, cl::kTileM);
   if (rc) return rc;
-  cudaError_t e = cudaFuncSetAttribute(cl::qconv_cl_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "fprop smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
   const int grid = p.total_units < cl::num_sms() ? p.total_units : cl::num_sms();
-  cl::qconv_cl_fprop_kernel<<<grid, cl::kThreads, smem, st>>>(tm, p);
+  void (*kern)(const CUtensorMap, const FpropParams) = nullptr;
+  switch (p.gc) {
+    case 1: kern = cl::qconv_cl_fprop_kernel<1>; break;
+    case 2: kern = cl::qconv_cl_fprop_kernel<2>; break;
+    case 4: kern = cl::qconv_cl_fprop_kernel<4>; break;
+    case 8: kern = cl::qconv_cl_fprop_kernel<8>; break;
+    default: return fail(SELDQ_ERR_UNSUPPORTED, "unexpected out-component group size %d", p.gc);
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "fprop smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+  kern<<<grid, cl::kThreads, smem, st>>>(tm, p);
   return check_launch("qconv_cl_fprop_kernel");
 }
 

@@ -22,6 +22,7 @@ constexpr int kTileM = 128;     // positions per accumulator tile (TMEM lanes)
 constexpr int kThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kMaxTaps = 9;
 constexpr int kMaxStages = 8;
+constexpr int kOpTableEntries = 512;  // (16-channel slab, out component) pairs: 1024 padded channels x 8
 
 SELDQ_HD int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -82,6 +83,7 @@ struct FpropParams {
   int8_t op_img[8][8];          // [in comp b][out comp a] -> image index or -1
   int8_t op_neg[8][8];
   int nstages, acc_stages, tmem_cols;
+  uint32_t op_tbl[kOpTableEntries];
 };
 
 // wgrad: D[(a,o), (b,i)] per tap = sum_t GY[(a,o), t] * X[t + off(tap), (b,i)]

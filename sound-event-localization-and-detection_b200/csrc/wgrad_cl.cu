@@ -31,7 +31,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[kWgradStages], empty_bar[kWgradStages], done_bar;
   __shared__ uint32_t tmem_slot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   // tile decode: blockIdx.x = tap_group * o_tiles + o_tile, blockIdx.y = split
   const int o_tile = blockIdx.x % p.o_tiles;
