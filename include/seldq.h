@@ -127,10 +127,12 @@ int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy
                      const float* const* host_w, const void* packed_w, float* gx,
                      void* workspace, size_t workspace_bytes, void* stream);
 
-/* compact weight gradients (nc tensors, OVERWRITTEN) and, if gbias != NULL, gbias = sum gy */
+/* compact weight gradients (nc tensors) and, if gbias != NULL, the bias gradient sum(gy).
+ * accumulate == 0: the outputs are overwritten; != 0: the results are ADDED to what the buffers hold, so a
+ * caller can point them straight at its gradient bucket (no zero-fill + add pass per parameter). */
 int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
                      const float* gy, const void* gy_t16, float* const* host_gw, float* gbias,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- linear (A3, A4) ------------------------------------------------------------------- */
 size_t seldq_linear_workspace_bytes(const seldq_linear_desc_t* d, int32_t pass);
@@ -139,7 +141,7 @@ int seldq_linear_fwd(const seldq_linear_desc_t* d, const float* x, const float* 
 int seldq_linear_dgrad(const seldq_linear_desc_t* d, const float* gy, const float* const* host_w,
                        float* gx, void* workspace, size_t workspace_bytes, void* stream);
 int seldq_linear_wgrad(const seldq_linear_desc_t* d, const float* x, const float* gy,
-                       float* const* host_gw, float* gbias,
+                       float* const* host_gw, float* gbias, int32_t accumulate,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- helpers ------------------------------------------------------------------------------ */

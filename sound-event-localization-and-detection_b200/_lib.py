@@ -59,15 +59,15 @@ _PROTOS = {
                                       ctypes.c_size_t, _P]),
     "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P,
                                         ctypes.c_size_t, _P]),
-    "seldq_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.POINTER(_P), _P, _P,
-                                        ctypes.c_size_t, _P]),
+    "seldq_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.POINTER(_P), _P,
+                                        ctypes.c_int32, _P, ctypes.c_size_t, _P]),
     "seldq_linear_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(LinearDesc), ctypes.c_int32]),
     "seldq_linear_fwd": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, ctypes.POINTER(_P), _P, _P, _P,
                                         ctypes.c_size_t, _P]),
     "seldq_linear_dgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, ctypes.POINTER(_P), _P, _P,
                                           ctypes.c_size_t, _P]),
-    "seldq_linear_wgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, _P, ctypes.POINTER(_P), _P, _P,
-                                          ctypes.c_size_t, _P]),
+    "seldq_linear_wgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, _P, ctypes.POINTER(_P), _P,
+                                          ctypes.c_int32, _P, ctypes.c_size_t, _P]),
     "seldq_cast_bf16": (ctypes.c_int, [_P, _P, ctypes.c_size_t, _P]),
     "seldq_stft_shape": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),

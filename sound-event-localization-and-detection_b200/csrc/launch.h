@@ -24,7 +24,7 @@ inline int check_launch(const char* what) {
 int launch_conv_simt(const simt::ConvParams& p, cudaStream_t st);
 int launch_wgrad_simt(simt::WgradParams& p, cudaStream_t st);
 int launch_bias_grad(const float* gy, float* gb, int C, int N, int H, int W, long long sN, long long sC, long long sH,
-                     long long sW, cudaStream_t st);
+                     long long sW, int accumulate, cudaStream_t st);
 int launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
 int launch_cast_bf16_mirror(const float* src, void* dst, long long rows, int w, int pitch, const int* shifts,
                             int nshifts, cudaStream_t st);

@@ -237,8 +237,8 @@ extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, con
 }
 
 extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_cl, const float* gy,
-                                const void* gy_t16, float* const* host_gw, float* gbias, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                const void* gy_t16, float* const* host_gw, float* gbias, int32_t accumulate,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   ConvGeom g;
   int rc = make_conv_geom(d, SELDQ_PASS_WGRAD, &g);
   if (rc) return rc;
@@ -253,10 +253,12 @@ extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, cons
   const size_t wbytes = (size_t)g.Oc * g.Ic * g.KH * g.KW * sizeof(float);
   for (int i = 0; i < g.tab.nw; ++i) {
     if (!host_gw[i]) return fail(SELDQ_ERR_INVALID, "seldq_conv_wgrad: gradient %d is null", i);
+    if (accumulate) continue;
     const cudaError_t e = cudaMemsetAsync(host_gw[i], 0, wbytes, st);
     if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
   }
-  if (gbias && (rc = launch_bias_grad(gy, gbias, g.P, g.N, g.OH, g.OW, g.out_sN, g.out_sC, g.out_sH, g.out_sW, st)))
+  if (gbias && (rc = launch_bias_grad(gy, gbias, g.P, g.N, g.OH, g.OW, g.out_sN, g.out_sC, g.out_sH, g.out_sW,
+                                      accumulate, st)))
     return rc;
   if (!bf16) {
     simt::WgradParams p{};
@@ -322,7 +324,7 @@ extern "C" int seldq_linear_dgrad(const seldq_linear_desc_t* d, const float* gy,
 }
 
 extern "C" int seldq_linear_wgrad(const seldq_linear_desc_t* d, const float* x, const float* gy, float* const* host_gw,
-                                  float* gbias, void*, size_t, void* stream) {
+                                  float* gbias, int32_t accumulate, void*, size_t, void* stream) {
   simt::WgradParams p{};
   int rc = make_linear_geom(d, SELDQ_PASS_WGRAD, &p.g);
   if (rc) return rc;
@@ -332,12 +334,13 @@ extern "C" int seldq_linear_wgrad(const seldq_linear_desc_t* d, const float* x, 
   const ConvGeom& g = p.g;
   for (int i = 0; i < g.tab.nw; ++i) {
     if (!host_gw[i]) return fail(SELDQ_ERR_INVALID, "seldq_linear_wgrad: gradient %d is null", i);
+    p.gw[i] = host_gw[i];
+    if (accumulate) continue;
     const cudaError_t e = cudaMemsetAsync(host_gw[i], 0, (size_t)g.Oc * g.Ic * sizeof(float), st);
     if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
-    p.gw[i] = host_gw[i];
   }
   p.x = x; p.gy = gy;
-  if (gbias && (rc = launch_bias_grad(gy, gbias, g.P, 1, 1, g.OW, 0, g.out_sC, 0, g.out_sW, st))) return rc;
+  if (gbias && (rc = launch_bias_grad(gy, gbias, g.P, 1, 1, g.OW, 0, g.out_sC, 0, g.out_sW, accumulate, st))) return rc;
   return launch_wgrad_simt(p, st);
 }
 

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(NT) wgrad_simt_kernel(const __grid_constant__ 
 // gb[c] = sum over (n, h, w) of gy[n, c, h, w]; one block per channel, warp-shuffle reduction
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ gy, float* __restrict__ gb, int N,
                                                         int H, int W, long long sN, long long sC, long long sH,
-                                                        long long sW) {
+                                                        long long sW, int accumulate) {
   const int c = blockIdx.x;
   const long long total = (long long)N * H * W;
   float acc = 0.f;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
     float v = threadIdx.x < 8 ? part[threadIdx.x] : 0.f;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) gb[c] = v;
+    if (threadIdx.x == 0) gb[c] = accumulate ? gb[c] + v : v;
   }
 }
 
@@ -199,8 +199,8 @@ int launch_wgrad_simt(simt::WgradParams& p, cudaStream_t st) {
 }
 
 int launch_bias_grad(const float* gy, float* gb, int C, int N, int H, int W, long long sN, long long sC, long long sH,
-                     long long sW, cudaStream_t st) {
-  simt::bias_grad_kernel<<<C, 256, 0, st>>>(gy, gb, N, H, W, sN, sC, sH, sW);
+                     long long sW, int accumulate, cudaStream_t st) {
+  simt::bias_grad_kernel<<<C, 256, 0, st>>>(gy, gb, N, H, W, sN, sC, sH, sW, accumulate);
   return check_launch("bias_grad_kernel");
 }
 

@@ -41,6 +41,28 @@ def precision(name):
         set_precision(prev)
 
 
+# ---- gradient accumulation straight into preallocated .grad buffers (trainer.FlatGradBucket) ----------
+_ACCUMULATE = False
+
+
+def set_grad_accumulation(flag):
+    """True: the weight-gradient kernels ADD their result into `param.grad` when that buffer already exists
+    (the trainer's flat bucket) and autograd receives None for the parameter, which removes one zero-fill and
+    one add kernel per parameter and step.  Returns the previous setting."""
+    global _ACCUMULATE
+    prev, _ACCUMULATE = _ACCUMULATE, bool(flag)
+    return prev
+
+
+def _grad_targets(params, needs):
+    """(buffers, direct): param.grad buffers to accumulate into when every parameter that needs a gradient has
+    a contiguous fp32 one; otherwise fresh buffers that autograd accumulates as usual."""
+    if _ACCUMULATE and all((not n) or (p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32
+                                       and p.grad.device == p.device) for p, n in zip(params, needs)) and all(needs):
+        return [p.grad for p in params], True
+    return [torch.empty_like(p) for p in params], False
+
+
 # ---- optional per-kernel timing (bench.py): CUDA events around each C-ABI call on the launching stream
 _PROF = None
 
@@ -217,6 +239,7 @@ class _BlockConv(torch.autograd.Function):
         # the tensor-core wgrad reads the channels-last bf16 operand only: keep that instead of the fp32
         # input (except for the narrow first layer, whose wgrad stages its own copy of the fp32 input)
         ctx.x_is_cl = bf16 and not _operand_info(desc, 0)[1]
+        ctx.bias_ref = bias
         ctx.save_for_backward(x_cl if ctx.x_is_cl else x, *weights)
         return y
 
@@ -253,8 +276,14 @@ class _BlockConv(torch.autograd.Function):
                     L.seldq_conv_dgrad(ctypes.byref(desc), gy.data_ptr(), _ptr(gy_cl), wp, _ptr(pk), gx.data_ptr(),
                                        None, 0, _stream())))
             if need_w_any:
-                gws = [torch.empty_like(w) for w in weights]
-                gb = torch.empty(desc.cout, dtype=torch.float32, device=dev) if need_b else None
+                gws, direct = _grad_targets(weights, ctx.needs_input_grad[7:])
+                gb = None
+                if need_b:
+                    gb = ctx.bias_ref.grad if direct and ctx.bias_ref.grad is not None else torch.empty(
+                        desc.cout, dtype=torch.float32, device=dev)
+                    direct_b = direct and gb is ctx.bias_ref.grad
+                    if direct and not direct_b:       # mixed case: keep it simple, overwrite semantics for all
+                        gws, direct = [torch.empty_like(w) for w in weights], False
                 gp = _lib.ptr_array([g.data_ptr() for g in gws])
                 x_cl = xs if ctx.x_is_cl else None
                 x32 = None if ctx.x_is_cl else xs
@@ -265,7 +294,10 @@ class _BlockConv(torch.autograd.Function):
                 kern = "qconv_cl_wgrad_kernel" if bf16 else "wgrad_simt_kernel"
                 _timed(kern, _conv_flop(desc, *ctx.out_hw), 1 + (1 if need_b else 0), lambda: _lib.check(
                     L.seldq_conv_wgrad(ctypes.byref(desc), _ptr(x32), _ptr(x_cl), gy.data_ptr(), _ptr(gy_t16), gp,
-                                       _ptr(gb), _ptr(work), 0 if work is None else work.numel(), _stream())))
+                                       _ptr(gb), 1 if direct else 0, _ptr(work),
+                                       0 if work is None else work.numel(), _stream())))
+                if direct:                            # already added into param.grad
+                    gws, gb = [None] * len(weights), None
         return (gx, gb, None, None, None, None, None) + tuple(gws)
 
 
@@ -300,6 +332,7 @@ class _BlockLinear(torch.autograd.Function):
                                    _stream())))
         ctx.desc = desc
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         ctx.save_for_backward(x, *weights)
         return y
 
@@ -324,12 +357,19 @@ class _BlockLinear(torch.autograd.Function):
                     L.seldq_linear_dgrad(ctypes.byref(desc), gy.data_ptr(), wp, gx.data_ptr(), None, 0,
                                          _stream())))
             if need_w or need_b:
-                gws = [torch.empty_like(w) for w in weights]
-                gb = torch.empty(desc.out_features, dtype=torch.float32, device=dev) if need_b else None
+                gws, direct = _grad_targets(weights, ctx.needs_input_grad[4:])
+                gb = None
+                if need_b:
+                    gb = ctx.bias_ref.grad if direct and ctx.bias_ref.grad is not None else torch.empty(
+                        desc.out_features, dtype=torch.float32, device=dev)
+                    if direct and gb is not ctx.bias_ref.grad:
+                        gws, direct = [torch.empty_like(w) for w in weights], False
                 gp = _lib.ptr_array([g.data_ptr() for g in gws])
                 _timed("linear_simt", 0.0, 1 + (1 if need_b else 0), lambda: _lib.check(
                     L.seldq_linear_wgrad(ctypes.byref(desc), x.data_ptr(), gy.data_ptr(), gp, _ptr(gb),
-                                         None, 0, _stream())))
+                                         1 if direct else 0, None, 0, _stream())))
+                if direct:
+                    gws, gb = [None] * len(weights), None
         return (gx, gb, None, None) + tuple(gws)
 
 

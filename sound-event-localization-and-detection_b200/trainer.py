@@ -26,13 +26,13 @@ def seld_loss(sed, doa, target, n_sed, sed_weight=1.0, doa_weight=5.0):
 
 
 class FlatGradBucket(object):
-    """One contiguous fp32 buffer holding every parameter's gradient."""
+    """One contiguous buffer (the parameters' dtype: fp32 in training) holding every parameter's gradient."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat = torch.zeros(total, dtype=self.params[0].dtype, device=dev)
         off = 0
         for p in self.params:
             n = p.numel()
@@ -55,6 +55,10 @@ class Trainer(object):
         self.group = group
         self.bucket = FlatGradBucket(model.parameters())
         on_cuda = self.bucket.flat.is_cuda
+        if on_cuda:
+            # the weight-gradient kernels add straight into the bucket (functional.set_grad_accumulation)
+            from . import functional
+            functional.set_grad_accumulation(True)
         # Adam with the reference's hyper-parameters (train.py:502-504); fused = one kernel per step,
         # capturable so that the whole step can live in a CUDA graph
         self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, fused=on_cuda, capturable=on_cuda)

@@ -215,3 +215,27 @@ def test_model_bf16_matches_reference_fixture(seldq, name):
         if not e < tol:
             bad[k] = (e, tol)
     assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
+
+
+def test_trainer_bucket_accumulation_matches_autograd(seldq):
+    """The trainer lets the weight-gradient kernels add straight into its flat bucket
+    (functional.set_grad_accumulation); the bucket must hold what plain autograd produces."""
+    import importlib
+    trainer_mod = importlib.import_module(seldq.__name__ + ".trainer")
+    prev = seldq.functional.set_grad_accumulation(False)
+    try:
+        meta, d, _, _, _, grads = _run_model(seldq, "model_dq_tiny", "fp32")
+        cfg = dict(meta["cfg"])
+        m = seldq.SELD_Model(time_dim=meta["time_dim"], spatial_dropout_rate=0, dropout_perc=0, **cfg)
+        m.load_state_dict({k[6:]: torch.from_numpy(np.asarray(v)) for k, v in d.items() if k.startswith("param/")})
+        m = m.cuda().train()
+        tr = trainer_mod.Trainer(m, lr=0.0, n_sed=42)           # enables the accumulation mode
+        assert seldq.functional._ACCUMULATE
+        with seldq.precision("fp32"):
+            tr.step(cuda(d["x"]), cuda(d["target"]))
+        torch.cuda.synchronize()
+        for k, p in m.named_parameters():
+            if k in grads:
+                assert A.rel_err(p.grad.cpu().numpy(), grads[k]) < 1e-5, k
+    finally:
+        seldq.functional.set_grad_accumulation(prev)
