@@ -122,6 +122,11 @@ int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
                    const float* const* host_w, const void* packed_w, const float* bias, float* y,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* same, but y is written in bf16 (same NCHW order): the form the fused CNN-block glue below consumes */
+int seldq_conv_fwd_bf16(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
+                        const float* const* host_w, const void* packed_w, const float* bias, void* y_bf16,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* gx = conv_transpose(gy, expand(w)) : gradient w.r.t. the input */
 int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy_cl,
                      const float* const* host_w, const void* packed_w, float* gx,
@@ -133,6 +138,35 @@ int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy
 int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
                      const float* gy, const void* gy_t16, float* const* host_gw, float* gbias,
                      int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- glue between the convolutions (E1 in SURVEY.md 8a) -------------------------------------------------
+ * CNN block, model.py:276-283: conv -> BatchNorm2d(train) -> ReLU -> MaxPool2d([pool,1]) -> Dropout(drop_p).
+ *   seldq_bn_stats      sums[c][0] += sum v, sums[c][1] += sum v^2 over an NCHW tensor (plane = H*W elements per
+ *                       (n, c)); the caller zeroes sums
+ *   seldq_bn_finalize   coef[c] = {a, b, mean, rstd}: BN(v) = a v + b (batch statistics, biased variance, eps);
+ *                       running_mean / running_var (may be NULL) get nn.BatchNorm's momentum update
+ *   seldq_cnn_tail_fwd  z = dropout(max_{pool rows}(relu(BN(y)))) written as the channels-last bf16 operand of
+ *                       the consuming convolution (z_cl, may be NULL) and / or as fp32 NCHW (z_f32, may be NULL);
+ *                       idx gets one byte per pooled element (arg-max row | 0x80 if kept) for the backward pass.
+ *                       seed: device counter the caller advances every step (needed iff drop_p > 0)
+ *   seldq_cnn_tail_bwd  d(conv out) from gz (fp32, pooled NCHW): written as the pitched NCHW bf16 operand
+ *                       (d_t16) and / or the channels-last operand (d_cl) of the producing convolution's
+ *                       gradient kernels; dsums: 3*c doubles, zeroed by the caller; on return dsums[2c], dsums[2c+1] =
+ *                       sum dy, sum dy*xhat = (d beta, d gamma) of channel c (the last c doubles are scratch) */
+typedef struct {
+  int32_t n, c, h, w;     /* conv output (N, C, H, W) */
+  int32_t pool;           /* rows pooled along h (1..8); the pooled height is h / pool */
+  float drop_p;
+  uint32_t salt;          /* distinguishes the dropout streams of different layers */
+} seldq_cnn_tail_desc_t;
+int seldq_bn_stats(const void* src, int32_t is_bf16, int32_t n, int32_t c, int64_t plane, double* sums, void* stream);
+int seldq_bn_finalize(const double* sums, const float* gamma, const float* beta, int32_t c, double count, float eps,
+                      float momentum, float* running_mean, float* running_var, float* coef, void* stream);
+int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* consumer, const void* y_bf16,
+                       const float* coef, const int64_t* seed, void* z_cl, float* z_f32, uint8_t* idx, void* stream);
+int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* producer, const void* y_bf16,
+                       const float* coef, const uint8_t* idx, const float* gz, double* dsums, void* d_t16, void* d_cl,
+                       void* stream);
 
 /* ---- linear (A3, A4) ------------------------------------------------------------------- */
 size_t seldq_linear_workspace_bytes(const seldq_linear_desc_t* d, int32_t pass);

@@ -149,17 +149,19 @@ def model_case(name, cfg, time_dim, B, seed):
         if p.grad is not None:
             d["ref32err/" + k] = np.float64(A.rel_err(p.grad.numpy(), d["grad/" + k]))
     # yardstick 2: an ideal bf16-operand implementation (oracle/bf16_emulation.py) of the same model
+    # (key bf16emu*), and the same with the 2-d conv outputs stored in bf16 as the fused CNN path does (bf16emu16*)
     from oracle import bf16_emulation, cpu_model
-    me = cpu_model.build_model(time_dim=time_dim, spatial_dropout_rate=0, dropout_perc=0, **cfg)
-    me.load_state_dict(sd32)
-    me = me.double().train()
-    with bf16_emulation.bf16_operand_convs():
-        se, de = me(torch.tensor(x))
-        cpu_model.seld_loss(se, de, torch.tensor(target)).backward()
-    d["bf16emu/sed"], d["bf16emu/doa"] = se.detach().numpy(), de.detach().numpy()
-    for k, p in me.named_parameters():
-        if p.grad is not None:
-            d["bf16emu_grad/" + k] = p.grad.numpy().astype(np.float32)
+    for tag, store in (("bf16emu", False), ("bf16emu16", True)):
+        me = cpu_model.build_model(time_dim=time_dim, spatial_dropout_rate=0, dropout_perc=0, **cfg)
+        me.load_state_dict(sd32)
+        me = me.double().train()
+        with bf16_emulation.bf16_operand_convs(store_conv2d_bf16=store):
+            se, de = me(torch.tensor(x))
+            cpu_model.seld_loss(se, de, torch.tensor(target)).backward()
+        d[tag + "/sed"], d[tag + "/doa"] = se.detach().numpy(), de.detach().numpy()
+        for k, p in me.named_parameters():
+            if p.grad is not None:
+                d[tag + "_grad/" + k] = p.grad.numpy().astype(np.float32)
     meta = dict(kind="model", cfg=cfg, time_dim=time_dim, B=B, seed=seed, model_name=m.model_name,
                 n_params=int(sum(p.numel() for p in m.parameters())), n_grads=ngrad,
                 source="model.py:324-480 + train.py:186-204")

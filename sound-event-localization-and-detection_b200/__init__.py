@@ -10,6 +10,7 @@ or put `<this dir>/dropin` on sys.path and import the reference's module names
 import os as _os
 
 from . import _lib
+from . import fused
 from .functional import (block_conv, block_linear, get_precision, precision, set_precision,
                          stft_magphase)
 from .features import spectrum_fast

@@ -25,6 +25,11 @@ class ConvDesc(ctypes.Structure):
         "stride_h", "stride_w", "pad_h", "pad_w", "dil_h", "dil_w")]
 
 
+class CnnTailDesc(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("c", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+                ("pool", ctypes.c_int32), ("drop_p", ctypes.c_float), ("salt", ctypes.c_uint32)]
+
+
 class LinearDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("algebra", "precision", "rows", "in_features", "out_features")]
 
@@ -57,6 +62,15 @@ _PROTOS = {
     "seldq_conv_pack_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32, ctypes.POINTER(_P), _P, _P]),
     "seldq_conv_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P, _P,
                                       ctypes.c_size_t, _P]),
+    "seldq_conv_fwd_bf16": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P, _P,
+                                           ctypes.c_size_t, _P]),
+    "seldq_bn_stats": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, _P, _P]),
+    "seldq_bn_finalize": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_double, ctypes.c_float, ctypes.c_float,
+                                         _P, _P, _P, _P]),
+    "seldq_cnn_tail_fwd": (ctypes.c_int, [ctypes.POINTER(CnnTailDesc), ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P,
+                                          _P, _P]),
+    "seldq_cnn_tail_bwd": (ctypes.c_int, [ctypes.POINTER(CnnTailDesc), ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P,
+                                          _P, _P, _P]),
     "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P,
                                         ctypes.c_size_t, _P]),
     "seldq_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.POINTER(_P), _P,

@@ -195,14 +195,26 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       ptx::mbar_wait(&tfull_bar[as], use & 1);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
-      float* out_row = p.out + (long long)n * p.out_sN + (long long)h * p.out_sH + w;
+      const long long row_off = (long long)n * p.out_sN + (long long)h * p.out_sH + w;
+      float* out_row = p.out + row_off;
+      __nv_bfloat16* out16_row = p.out16 + row_off;
       for (int al = 0; al < GC; ++al) {
         const int ch_base = (group * GC + al) * p.Pc;
         for (int c0 = 0; c0 < p.Pc; c0 += 16) {
           uint32_t v[16];
           ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
           ptx::tmem_ld_wait();
-          if (w_ok) {
+          if (w_ok && p.out16) {
+            // bf16 output in the tensor's own NCHW order (fused CNN-block path, epilogue.cu)
+            __nv_bfloat16* dst = out16_row + (long long)(ch_base + c0) * p.out_sC;
+            const int lim = p.Pc - c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (j < lim)
+                *dst = __float2bfloat16_rn(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch_base + c0 + j) : 0.f));
+              dst += p.out_sC;
+            }
+          } else if (w_ok) {
             float* dst = out_row + (long long)(ch_base + c0) * p.out_sC;
             const int lim = p.Pc - c0;
             if (lim >= 16 && p.bias == nullptr) {
@@ -456,7 +468,7 @@ static int encode_cl_map(CUtensorMap* tm, const void* data, const cl::OperandLay
 }
 
 int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
-                    const float* bias, float* out, cudaStream_t st) {
+                    const float* bias, float* out, void* out_bf16, cudaStream_t st) {
   FpropParams p;
   size_t smem = 0;
   int rc = plan_cl_fprop(g, &p, &smem);
@@ -470,6 +482,7 @@ int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* ho
   }
   p.bias = bias;
   p.out = out;
+  p.out16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   p.out_sN = g.out_sN; p.out_sC = g.out_sC; p.out_sH = g.out_sH;
   const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, p.dense != 0);
   alignas(64) CUtensorMap tm;

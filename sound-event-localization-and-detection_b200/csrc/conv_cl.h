@@ -63,7 +63,8 @@ struct FpropParams {
   const float* w[8];            // compact fp32 weights (dense prologue only)
   const uint8_t* packed;        // pre-packed bf16 weight images (non-dense)
   const float* bias;
-  float* out;                   // fp32 NCHW
+  float* out;                   // fp32 NCHW ...
+  __nv_bfloat16* out16;         // ... or, when not null, bf16 NCHW instead
   long long out_sN, out_sC, out_sH;
   int N, OH, OW;
   int tiles_w, total_tiles, ngroups, total_units;
@@ -118,7 +119,7 @@ cl::OperandLayout gy_operand_layout(const ConvGeom& fwd);
 size_t packed_weight_bytes(const ConvGeom& pass_geom);
 int launch_pack_weights(const ConvGeom& pass_geom, const float* const* host_w, void* packed, cudaStream_t st);
 int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
-                    const float* bias, float* out, cudaStream_t st);
+                    const float* bias, float* out, void* out_bf16, cudaStream_t st);
 int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, float* const* host_gw,
                     cudaStream_t st);
 // fp32 NCHW -> CL operand (and, optionally, the pitched NCHW bf16 copy wgrad reads gy from)

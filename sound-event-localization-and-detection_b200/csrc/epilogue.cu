@@ -1,0 +1,342 @@
+// Bandwidth-bound kernels for the glue between the convolutions:
+//
+//   CNN block   model.py:276-283   conv -> BatchNorm2d (batch statistics) -> ReLU -> MaxPool2d([p,1]) -> Dropout
+//
+// The convolution writes its output once, in bf16, in the tensor's own NCHW order.  Then
+//   bn_stats_kernel        per-channel sum / sum of squares (warp-shuffle + block reduction, one double
+//                          atomicAdd pair per block)
+//   bn_finalize_kernel     mean / rstd / affine coefficients per channel, running-statistics update
+//   cnn_tail_fwd_kernel    BN-apply + ReLU + max over p frequency rows + dropout in one pass; emits the pooled
+//                          activation directly as the NEXT convolution's channels-last bf16 operand (transposed
+//                          through shared memory, conv_cl.h), optionally as fp32 NCHW, and one byte per pooled
+//                          element (argmax row | keep flag) for the backward pass
+//   cnn_tail_bwd_reduce    sum(dy), sum(dy * xhat) per channel (the two BatchNorm backward reductions), reading
+//                          only the pooled gradient and the arg-max elements of the conv output
+//   cnn_tail_bwd_apply     d(conv out) for every element, written straight into the two bf16 operand layouts the
+//                          gradient kernels read (pitched NCHW for wgrad, channels-last for dgrad)
+// so the full-resolution fp32 tensors of the reference (944 MB per sample after the first convolution, read
+// and written by five separate PyTorch kernels) never exist.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "conv_cl.h"
+#include "epilogue.h"
+#include "launch.h"
+
+namespace seldq {
+namespace epi {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of two values; result valid in thread 0
+__device__ __forceinline__ void block_sum2(float& a, float& b) {
+  __shared__ float sa[32], sb[32];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    a = lane < nw ? sa[lane] : 0.f;
+    b = lane < nw ? sb[lane] : 0.f;
+    a = warp_sum(a);
+    b = warp_sum(b);
+  }
+}
+
+__device__ __forceinline__ float load_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// grid (C, N, splits): block (c, n, z) reduces elements [z*chunk, (z+1)*chunk) of plane (n, c)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ src, long long plane, int C,
+                                                       long long chunk, double* __restrict__ sums) {
+  const int c = blockIdx.x, n = blockIdx.y;
+  const long long lo = (long long)blockIdx.z * chunk;
+  const long long hi = lo + chunk < plane ? lo + chunk : plane;
+  const T* base = src + ((long long)n * C + c) * plane;
+  float s1 = 0.f, s2 = 0.f;
+  if (sizeof(T) == 2 && (plane & 7) == 0 && (chunk & 7) == 0) {
+    const uint4* v = reinterpret_cast<const uint4*>(base + lo);
+    const long long nv = (hi - lo) >> 3;
+    for (long long i = threadIdx.x; i < nv; i += blockDim.x) {
+      const uint4 q = __ldg(v + i);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        s1 += f.x + f.y;
+        s2 += f.x * f.x + f.y * f.y;
+      }
+    }
+  } else {
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const float f = load_as_float(base + i);
+      s1 += f;
+      s2 += f * f;
+    }
+  }
+  block_sum2(s1, s2);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 2 * c, (double)s1);
+    atomicAdd(sums + 2 * c + 1, (double)s2);
+  }
+}
+
+// coef[c] = {a, b, mean, rstd} with BN(v) = a*v + b;  running statistics as nn.BatchNorm (momentum update,
+// unbiased variance)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int C, double count, float eps, float momentum,
+                                   float* running_mean, float* running_var, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[2 * c] / count;
+  double var = sums[2 * c + 1] / count - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  const float a = g * rstd;
+  coef[4 * c + 0] = a;
+  coef[4 * c + 1] = bt - (float)mean * a;
+  coef[4 * c + 2] = (float)mean;
+  coef[4 * c + 3] = rstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return (uint32_t)x;
+}
+// counter-based dropout mask: the same (seed, salt, element) always gives the same decision, so the backward
+// pass needs no stored mask beyond the keep bit
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, uint32_t salt, long long elem, uint32_t thresh) {
+  return hash_u32((seed * 0x9E3779B97F4A7C15ULL) ^ ((unsigned long long)salt << 44) ^ (unsigned long long)elem) >= thresh;
+}
+
+// One block: 64 padded channels x 32 w positions of one pooled row (n, h').
+__global__ void __launch_bounds__(256) cnn_tail_fwd_kernel(const __grid_constant__ TailParams p) {
+  __shared__ float tile[64][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HP = p.H / p.pool;
+  const unsigned long long seed = p.seed_ptr ? (unsigned long long)*p.seed_ptr : 0ULL;
+  const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
+  const float scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  for (long long blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
+    long long r = blk;
+    const int wt = (int)(r % p.tiles_w); r /= p.tiles_w;
+    const int ct = (int)(r % p.tiles_c); r /= p.tiles_c;
+    const int hp = (int)(r % HP);
+    const int n = (int)(r / HP);
+    const int w = wt * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int cl = warp + 8 * k;
+      const int cp = ct * 64 + cl;
+      const int comp = cp / p.cpad, ci = cp - comp * p.cpad;
+      float z = 0.f;
+      if (cp < p.Cp && ci < p.cc && w < p.W) {
+        const int c = comp * p.cc + ci;
+        const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
+        const __nv_bfloat16* src = p.y + (((long long)n * p.C + c) * p.H + (long long)hp * p.pool) * p.W + w;
+        float best = -INFINITY;
+        int arg = 0;
+        for (int j = 0; j < p.pool; ++j) {
+          const float v = cf.x * __bfloat162float(src[(long long)j * p.W]) + cf.y;
+          if (v > best || v != v) { best = v; arg = j; }
+        }
+        const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
+        bool keep = best > 0.f;
+        if (keep && thresh) keep = dropout_keep(seed, p.salt, e, thresh);
+        z = keep ? best * scale : 0.f;
+        p.idx[e] = (uint8_t)(arg | (keep ? 0x80 : 0));
+        if (p.z32) p.z32[e] = z;
+      }
+      tile[cl][lane] = z;
+    }
+    __syncthreads();
+    if (p.z_cl) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int wl = warp + 8 * k;
+        const int ww = wt * 32 + wl;
+        const int cp = ct * 64 + 2 * lane;
+        if (ww < p.W && cp < p.Cp) {
+          const __nv_bfloat162 o = __floats2bfloat162_rn(tile[2 * lane][wl], tile[2 * lane + 1][wl]);
+          *reinterpret_cast<__nv_bfloat162*>(p.z_cl + (((long long)n * HP + hp) * p.W + ww) * p.Cp + cp) = o;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// grid (C, N, splits) over the pooled plane H' x W of (n, c)
+__global__ void __launch_bounds__(256) cnn_tail_bwd_reduce_kernel(const __grid_constant__ TailParams p, long long chunk,
+                                                                 double* __restrict__ dsums) {
+  const int c = blockIdx.x, n = blockIdx.y;
+  const int HP = p.H / p.pool;
+  const long long plane = (long long)HP * p.W;
+  const long long lo = (long long)blockIdx.z * chunk;
+  const long long hi = lo + chunk < plane ? lo + chunk : plane;
+  const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
+  const float scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  const long long base = ((long long)n * p.C + c) * plane;
+  const __nv_bfloat16* y = p.y + ((long long)n * p.C + c) * (long long)p.H * p.W;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const uint8_t id = p.idx[base + i];
+    if (id & 0x80) {
+      const int hp = (int)(i / p.W), w = (int)(i - (long long)hp * p.W);
+      const float g = __ldg(p.gz + base + i) * scale;
+      const float yv = __bfloat162float(y[((long long)hp * p.pool + (id & 7)) * p.W + w]);
+      s1 += g;
+      s2 += g * (yv - cf.z) * cf.w;
+    }
+  }
+  block_sum2(s1, s2);
+  if (threadIdx.x == 0) {
+    atomicAdd(dsums + 2 * c, (double)s1);
+    atomicAdd(dsums + 2 * c + 1, (double)s2);
+  }
+}
+
+// dmean[c] = {sum(dy) / M, sum(dy * xhat) / M} in fp32 (keeps the FP64 pipe out of the per-element kernel)
+__global__ void cnn_tail_bwd_finalize_kernel(const double* __restrict__ dsums, int C, double count,
+                                             float2* __restrict__ dmean) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) dmean[c] = make_float2((float)(dsums[2 * c] / count), (float)(dsums[2 * c + 1] / count));
+}
+
+// One block: 64 padded channels x 32 w positions of one full-resolution row (n, h).
+__global__ void __launch_bounds__(256) cnn_tail_bwd_apply_kernel(const __grid_constant__ TailParams p,
+                                                                const float2* __restrict__ dmean) {
+  __shared__ float tile[64][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HP = p.H / p.pool;
+  const float scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  for (long long blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
+    long long r = blk;
+    const int wt = (int)(r % p.tiles_w); r /= p.tiles_w;
+    const int ct = (int)(r % p.tiles_c); r /= p.tiles_c;
+    const int h = (int)(r % p.H);
+    const int n = (int)(r / p.H);
+    const int hp = h / p.pool, kk = h - hp * p.pool;
+    const int w = wt * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int cl = warp + 8 * k;
+      const int cp = ct * 64 + cl;
+      const int comp = cp / p.cpad, ci = cp - comp * p.cpad;
+      float d = 0.f;
+      if (cp < p.Cp && ci < p.cc) {
+        const int c = comp * p.cc + ci;
+        const long long row = ((long long)n * p.C + c) * p.H + h;
+        if (w < p.W) {
+          const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
+          const float xhat = (__bfloat162float(p.y[row * p.W + w]) - cf.z) * cf.w;
+          float g = 0.f;
+          if (hp < HP) {
+            const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
+            const uint8_t id = p.idx[e];
+            if ((id & 0x80) && (id & 7) == kk) g = __ldg(p.gz + e) * scale;
+          }
+          const float2 dm = __ldg(dmean + c);
+          d = cf.x * (g - dm.x - xhat * dm.y);
+        }
+        if (p.d_t16 && w < p.pitch) p.d_t16[row * p.pitch + w] = __float2bfloat16_rn(d);
+      }
+      tile[cl][lane] = d;
+    }
+    __syncthreads();
+    if (p.d_cl) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int wl = warp + 8 * k;
+        const int ww = wt * 32 + wl;
+        const int cp = ct * 64 + 2 * lane;
+        if (ww < p.W && cp < p.Cp) {
+          const __nv_bfloat162 o = __floats2bfloat162_rn(tile[2 * lane][wl], tile[2 * lane + 1][wl]);
+          *reinterpret_cast<__nv_bfloat162*>(p.d_cl + (((long long)n * p.H + h) * p.W + ww) * p.Cp + cp) = o;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace epi
+
+// ---- host launchers ------------------------------------------------------------------------------------
+static int grid_cap() { return 148 * 16; }
+
+int launch_bn_stats(const void* src, int is_bf16, int n, int c, long long plane, double* sums, cudaStream_t st) {
+  if (n > 65535) return fail(SELDQ_ERR_UNSUPPORTED, "bn_stats: batch too large for the grid");
+  // about 32 K elements per block, but never more than 64 splits of a plane
+  long long splits = (plane + 32767) / 32768;
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  long long chunk = (plane + splits - 1) / splits;
+  chunk = (chunk + 7) & ~7LL;
+  splits = (plane + chunk - 1) / chunk;
+  dim3 grid((unsigned)c, (unsigned)n, (unsigned)splits);
+  if (is_bf16)
+    epi::bn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), plane, c, chunk, sums);
+  else
+    epi::bn_stats_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), plane, c, chunk, sums);
+  return check_launch("bn_stats_kernel");
+}
+
+int launch_bn_finalize(const double* sums, const float* gamma, const float* beta, int c, double count, float eps,
+                       float momentum, float* running_mean, float* running_var, float* coef, cudaStream_t st) {
+  epi::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, gamma, beta, c, count, eps, momentum, running_mean,
+                                                           running_var, coef);
+  return check_launch("bn_finalize_kernel");
+}
+
+int launch_cnn_tail_fwd(epi::TailParams& p, cudaStream_t st) {
+  p.tiles_w = (p.W + 31) / 32;
+  p.tiles_c = (p.Cp + 63) / 64;
+  p.total_blocks = (long long)p.tiles_w * p.tiles_c * (p.H / p.pool) * p.N;
+  const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
+  epi::cnn_tail_fwd_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p);
+  return check_launch("cnn_tail_fwd_kernel");
+}
+
+int launch_cnn_tail_bwd(epi::TailParams& p, double* dsums, cudaStream_t st) {
+  const int HP = p.H / p.pool;
+  const long long plane = (long long)HP * p.W;
+  long long splits = (plane + 16383) / 16384;
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  const long long chunk = (plane + splits - 1) / splits;
+  splits = (plane + chunk - 1) / chunk;
+  if (p.N > 65535) return fail(SELDQ_ERR_UNSUPPORTED, "cnn tail: batch too large for the grid");
+  dim3 grid((unsigned)p.C, (unsigned)p.N, (unsigned)splits);
+  epi::cnn_tail_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p, chunk, dsums);
+  int rc = check_launch("cnn_tail_bwd_reduce_kernel");
+  if (rc) return rc;
+  const double count = (double)p.N * p.H * p.W;
+  float2* dmean = reinterpret_cast<float2*>(dsums + 2 * (size_t)p.C);      // third C doubles of the caller's buffer
+  epi::cnn_tail_bwd_finalize_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(dsums, p.C, count, dmean);
+  if ((rc = check_launch("cnn_tail_bwd_finalize_kernel"))) return rc;
+  p.pitch = nchw16_pitch(p.W);
+  p.tiles_w = (p.pitch + 31) / 32;
+  p.tiles_c = (p.Cp + 63) / 64;
+  p.total_blocks = (long long)p.tiles_w * p.tiles_c * p.H * p.N;
+  const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
+  epi::cnn_tail_bwd_apply_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p, dmean);
+  return check_launch("cnn_tail_bwd_apply_kernel");
+}
+
+}  // namespace seldq

@@ -4,6 +4,7 @@
 #include "conv_cl.h"
 #include "conv_simt.cuh"
 #include "conv_umma.h"
+#include "epilogue.h"
 #include "geom.h"
 #include "launch.h"
 #include "stft.cuh"
@@ -163,14 +164,15 @@ extern "C" size_t seldq_conv_workspace_bytes(const seldq_conv_desc_t* d, int32_t
 }
 
 // ---- convolution ------------------------------------------------------------------------------------
-extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
-                              const float* const* host_w, const void* packed_w, const float* bias, float* y,
-                              void* workspace, size_t workspace_bytes, void* stream) {
+static int conv_fwd_impl(const seldq_conv_desc_t* d, const float* x, const void* x_cl, const float* const* host_w,
+                         const void* packed_w, const float* bias, float* y, void* y_bf16, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   ConvGeom g;
   int rc = make_conv_geom(d, SELDQ_PASS_FWD, &g);
   if (rc) return rc;
   const bool bf16 = d->precision == SELDQ_PREC_BF16;
-  if (!host_w || !y || (!x && !(bf16 && x_cl))) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: null pointer");
+  if (!host_w || (!y && !y_bf16) || (!x && !(bf16 && x_cl))) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: null pointer");
+  if (y_bf16 && !bf16) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 output exists on the SELDQ_PREC_BF16 path only");
   for (int i = 0; i < g.tab.nw; ++i)
     if (!host_w[i]) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: weight %d is null", i);
   if ((rc = cuda_ready())) return rc;
@@ -196,7 +198,20 @@ extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const 
     if ((rc = launch_pack_weights(g, host_w, buf, st))) return rc;
     packed_w = buf;
   }
-  return launch_cl_fprop(g, x_cl, host_w, packed_w, bias, y, st);
+  return launch_cl_fprop(g, x_cl, host_w, packed_w, bias, y, y_bf16, st);
+}
+
+extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
+                              const float* const* host_w, const void* packed_w, const float* bias, float* y,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  return conv_fwd_impl(d, x, x_cl, host_w, packed_w, bias, y, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int seldq_conv_fwd_bf16(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
+                                   const float* const* host_w, const void* packed_w, const float* bias, void* y_bf16,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y_bf16) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd_bf16: null output");
+  return conv_fwd_impl(d, x, x_cl, host_w, packed_w, bias, nullptr, y_bf16, workspace, workspace_bytes, stream);
 }
 
 extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy_cl,
@@ -233,7 +248,7 @@ extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, con
     if ((rc = launch_pack_weights(g, host_w, buf, st))) return rc;
     packed_w = buf;
   }
-  return launch_cl_fprop(g, gy_cl, host_w, packed_w, nullptr, gx, st);
+  return launch_cl_fprop(g, gy_cl, host_w, packed_w, nullptr, gx, nullptr, st);
 }
 
 extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_cl, const float* gy,
@@ -294,6 +309,85 @@ extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, cons
     x_cl = buf;
   }
   return launch_cl_wgrad(g, x_cl, gy_t16, host_gw, st);
+}
+
+// ---- glue between the convolutions (E1) ------------------------------------------------------------------
+extern "C" int seldq_bn_stats(const void* src, int32_t is_bf16, int32_t n, int32_t c, int64_t plane, double* sums,
+                              void* stream) {
+  if (!src || !sums || n <= 0 || c <= 0 || plane <= 0) return fail(SELDQ_ERR_INVALID, "seldq_bn_stats: bad arguments");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  return launch_bn_stats(src, is_bf16, n, c, plane, sums, (cudaStream_t)stream);
+}
+
+extern "C" int seldq_bn_finalize(const double* sums, const float* gamma, const float* beta, int32_t c, double count,
+                                 float eps, float momentum, float* running_mean, float* running_var, float* coef,
+                                 void* stream) {
+  if (!sums || !coef || c <= 0 || count <= 0) return fail(SELDQ_ERR_INVALID, "seldq_bn_finalize: bad arguments");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  return launch_bn_finalize(sums, gamma, beta, c, count, eps, momentum, running_mean, running_var, coef,
+                            (cudaStream_t)stream);
+}
+
+static int tail_params(const seldq_cnn_tail_desc_t* t, const cl::OperandLayout* lay, epi::TailParams* p) {
+  if (!t || t->n <= 0 || t->c <= 0 || t->h <= 0 || t->w <= 0 || t->pool <= 0 || t->pool > 8 || t->h / t->pool <= 0 ||
+      t->drop_p < 0.f || t->drop_p >= 1.f)
+    return fail(SELDQ_ERR_INVALID, "bad CNN tail descriptor (pool must be in [1, 8], 0 <= drop_p < 1)");
+  memset(p, 0, sizeof(*p));
+  p->N = t->n; p->C = t->c; p->H = t->h; p->W = t->w; p->pool = t->pool;
+  p->drop_p = t->drop_p; p->salt = t->salt;
+  if (lay) { p->nc = lay->nc; p->cc = lay->cc; p->cpad = lay->cpad; p->Cp = lay->Cp; }
+  else { p->nc = 1; p->cc = t->c; p->cpad = (t->c + 63) / 64 * 64; p->Cp = p->cpad; }
+  return SELDQ_OK;
+}
+
+extern "C" int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* consumer, const void* y_bf16,
+                                  const float* coef, const int64_t* seed, void* z_cl, float* z_f32, uint8_t* idx,
+                                  void* stream) {
+  epi::TailParams p;
+  cl::OperandLayout lay;
+  int rc;
+  if (z_cl) {
+    if (!consumer) return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_fwd: z_cl needs the consuming convolution's descriptor");
+    ConvGeom g;
+    if ((rc = make_conv_geom(consumer, SELDQ_PASS_FWD, &g))) return rc;
+    lay = x_operand_layout(g);
+    if (g.R != t->c || g.N != t->n || g.IH != t->h / t->pool || g.IW != t->w)
+      return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_fwd: pooled output does not match the consumer's input");
+  }
+  if ((rc = tail_params(t, z_cl ? &lay : nullptr, &p))) return rc;
+  if (!y_bf16 || !coef || !idx || (!z_cl && !z_f32)) return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_fwd: null pointer");
+  if (t->drop_p > 0.f && !seed) return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_fwd: dropout needs a seed pointer");
+  if ((rc = cuda_ready())) return rc;
+  p.y = reinterpret_cast<const __nv_bfloat16*>(y_bf16); p.coef = coef;
+  p.z_cl = reinterpret_cast<__nv_bfloat16*>(z_cl); p.z32 = z_f32; p.idx = idx;
+  p.seed_ptr = reinterpret_cast<const long long*>(seed);
+  return launch_cnn_tail_fwd(p, (cudaStream_t)stream);
+}
+
+extern "C" int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* producer, const void* y_bf16,
+                                  const float* coef, const uint8_t* idx, const float* gz, double* dsums, void* d_t16,
+                                  void* d_cl, void* stream) {
+  epi::TailParams p;
+  cl::OperandLayout lay;
+  int rc;
+  if (d_cl) {
+    if (!producer) return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_bwd: d_cl needs the producing convolution's descriptor");
+    ConvGeom g;
+    if ((rc = make_conv_geom(producer, SELDQ_PASS_FWD, &g))) return rc;
+    lay = gy_operand_layout(g);
+    if (g.P != t->c || g.N != t->n || g.OH != t->h || g.OW != t->w)
+      return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_bwd: descriptor does not match the producer's output");
+  }
+  if ((rc = tail_params(t, d_cl ? &lay : nullptr, &p))) return rc;
+  if (!y_bf16 || !coef || !idx || !gz || !dsums || (!d_t16 && !d_cl))
+    return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_bwd: null pointer");
+  if ((rc = cuda_ready())) return rc;
+  p.y = reinterpret_cast<const __nv_bfloat16*>(y_bf16); p.coef = coef;
+  p.idx = const_cast<uint8_t*>(idx); p.gz = gz;
+  p.d_t16 = reinterpret_cast<__nv_bfloat16*>(d_t16); p.d_cl = reinterpret_cast<__nv_bfloat16*>(d_cl);
+  return launch_cnn_tail_bwd(p, dsums, (cudaStream_t)stream);
 }
 
 // ---- linear: 0.18 GFLOP per call in the reference configs -> always the fp32 FFMA kernels -----------

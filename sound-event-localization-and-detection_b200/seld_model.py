@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as tF
 
+from . import fused as _fused
 from . import layers as _default_layers
 
 # The reference runs its real-valued nn.Conv* / nn.Linear layers (MultiHeadAttention projections,
@@ -222,6 +223,8 @@ class ConvTC_Block(nn.Module):
             blocks.append(nn.Sequential(*mods))
             in_chans = c
         self.cnn = nn.Sequential(*blocks)
+        # step counter that seeds the dropout masks of the fused CNN path (not part of the state_dict)
+        self.register_buffer("_drop_seed", torch.zeros(1, dtype=torch.int64), persistent=False)
         L = int(freq_dim / np.prod(np.array(pool_size), axis=0)[0] * cnn_filters[-1])
         self.tcn = TC_Block(in_channels=L, domain=domain, G=G, U=U, V=V, V_kernel_size=V_kernel_size,
                             pool_size=pool_size, D=D, spatial_dropout_rate=spatial_dropout_rate,
@@ -230,8 +233,24 @@ class ConvTC_Block(nn.Module):
                             verbose=verbose, attention_type=attention_type, key_size=key_size,
                             value_size=value_size, layer_lib=lib)
 
+    def _cnn_forward(self, x):
+        """The CNN front: fused conv -> BN -> ReLU -> pool -> dropout kernels (fused.cnn_stack) in the training
+        configuration they serve, the layer-by-layer modules otherwise."""
+        convs, bns, pools, drops = [], [], [], []
+        for blk in self.cnn:
+            mods = list(blk)
+            convs.append(mods[0])
+            bns.append(next((m for m in mods if isinstance(m, nn.BatchNorm2d)), None))
+            pools.append(next((m for m in mods if isinstance(m, nn.MaxPool2d)), None))
+            drops.append(next((m for m in mods if isinstance(m, nn.Dropout)), None))
+        if all(p is not None for p in pools) and _fused.cnn_stack_supported(convs, bns, pools, drops, x,
+                                                                           self.training):
+            self._drop_seed.add_(1)
+            return _fused.cnn_stack(x, convs, bns, pools, drops, self._drop_seed)
+        return self.cnn(x)
+
     def forward(self, x):
-        x = self.cnn(x)                                   # (B, C, F', T)
+        x = self._cnn_forward(x)                          # (B, C, F', T)
         x = x.permute(0, 3, 1, 2)                         # (B, T, C, F')
         x = x.reshape(x.shape[0], self.time_pooled_size, -1)
         x = x.permute(0, 2, 1)                            # (B, C*F', T): channel order c*F' + f

@@ -192,25 +192,36 @@ def test_model_fp32_matches_reference_fixture(seldq, name):
     assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("name", ["model_dq_tiny", "model_dq_mid"])
-def test_model_bf16_matches_reference_fixture(seldq, name):
+def test_model_bf16_matches_reference_fixture(seldq, name, fused):
     """Whole model through the tcgen05 bf16 kernels.  Forward: rel 2e-2 against the float64
     reference (north_star tolerance).  Gradients: bf16 operand rounding (2.7e-3 per convolution)
     is amplified to tens of percent on some tensors by this network's conditioning, for ANY bf16
     implementation; the fixture therefore carries the result of an ideal bf16-operand
-    implementation (oracle/bf16_emulation.py, keys bf16emu*): its own distance to the float64
-    reference is the inherent bf16 noise of each tensor, and the GPU may be at most twice as far
-    (floor 2e-2).  The outputs must match the emulation itself to 5e-3 (the emulation runs
-    everything between the convolutions in float64, the GPU in float32, so a few activations round
-    to the other bf16 neighbour; observed 3e-3)."""
-    meta, d, sed, doa, loss, grads = _run_model(seldq, name, "bf16")
+    implementation (oracle/bf16_emulation.py): its own distance to the float64 reference is the
+    inherent bf16 noise of each tensor, and the GPU may be at most twice as far (floor 2e-2).  The
+    outputs must match the emulation itself to 5e-3 (the emulation runs everything between the
+    convolutions in float64, the GPU in float32, so a few activations round to the other bf16
+    neighbour; observed 3e-3).
+    fused=False: layer-by-layer modules, emulation keys bf16emu*.  fused=True: the fused CNN-block
+    kernels (fused.py), which store the 2-d conv outputs once in bf16 -- emulation keys bf16emu16*
+    model exactly that extra rounding (model_dq_tiny's CNN is too narrow for the fused path and
+    runs layer by layer either way)."""
+    prev = seldq.fused.ENABLED
+    seldq.fused.ENABLED = fused
+    try:
+        meta, d, sed, doa, loss, grads = _run_model(seldq, name, "bf16")
+    finally:
+        seldq.fused.ENABLED = prev
+    emu = "bf16emu16" if (fused and name == "model_dq_mid") else "bf16emu"
     assert A.rel_err(sed, d["sed"]) < 2e-2
     assert A.rel_err(doa, d["doa"]) < 2e-2
-    assert A.rel_err(sed, d["bf16emu/sed"]) < 5e-3
-    assert A.rel_err(doa, d["bf16emu/doa"]) < 5e-3
+    assert A.rel_err(sed, d[emu + "/sed"]) < 5e-3
+    assert A.rel_err(doa, d[emu + "/doa"]) < 5e-3
     bad = {}
     for k, g in grads.items():
-        noise = A.rel_err(d["bf16emu_grad/" + k], d["grad/" + k])
+        noise = A.rel_err(d[emu + "_grad/" + k], d["grad/" + k])
         e, tol = A.rel_err(g, d["grad/" + k]), max(2e-2, 2.0 * noise)
         if not e < tol:
             bad[k] = (e, tol)
