@@ -42,6 +42,7 @@ template <int GC>
 __global__ void __launch_bounds__(kThreads, 1)
 qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint2 op_tbl_s[kOpTableEntries];
   // warp index through a shuffle: provably warp-uniform, so role branches and the MMA loop compile to the
   // uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -58,6 +59,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
 
   // ---- one-time setup ---------------------------------------------------------------------------
+  for (int i = threadIdx.x; i < p.chunks * p.slabs_per_chunk * p.ncomp_out; i += kThreads) op_tbl_s[i] = p.op_tbl[i];
   if (p.dense) {
     // signed expanded weight -> bf16 B tiles.  Tile (tap, j) holds B[n][k], n = out channel, k = in channels
     // 16 j ... 16 j + 15; UMMA K-major / no swizzle: core matrix = 8 rows x 16 B, LBO (K step) = NBp*16,
@@ -115,65 +117,78 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         const int n = r / p.OH;
         const int w0 = wt * kTileM;
         const uint32_t mask = p.chunk_mask[group];
-        for (int tap = 0; tap < p.ntaps; ++tap)
-          for (int c = 0; c < p.chunks; ++c) {
-            if (!((mask >> c) & 1u)) continue;
+        for (int c = 0; c < p.chunks; ++c) {
+          if (!((mask >> c) & 1u)) continue;
+          for (int tap = 0; tap < p.ntaps; ++tap) {
             ptx::mbar_wait(&empty_bar[slot], parity ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[slot], p.stage_bytes);
             ptx::tma_load_4d(a_ring + (size_t)slot * p.stage_bytes, &tm_in, &full_bar[slot], c * p.BK,
                              w0 + p.off_w[tap], h + p.off_h[tap], n);
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer ==============================================================================
-    // The whole warp runs this loop convergently so that descriptors, table entries (constant bank) and
-    // addresses stay in uniform registers; one elected lane issues the tcgen05 instructions.
+    // Lane-parallel issue: the MMAs of one stage (<= 32: slabs x out components of the group, structural zero
+    // blocks left out) are dealt to lanes 0 .. n-1 in (slab, component) order.  All lanes build their
+    // descriptors at once; the tcgen05.mma under the lane predicate then costs one short elect-and-issue round
+    // per active lane (~50 cycles per MMA instead of ~100 for descriptor arithmetic on the uniform datapath;
+    // tools/umma_rate.py).  The accumulator-initialising MMAs of a unit (tap 0, one per out component, distinct
+    // columns) go through their own issue site ahead of the accumulating ones.
     {
-      const bool leader = ptx::elect_one();
       const uint64_t a_hi = ptx::make_smem_desc_hi(16, p.a_sbo, p.a_swz);                 // K-major, swizzled
       const uint64_t b_hi = ptx::make_smem_desc_hi((uint32_t)p.NBp * 16u, 128, ptx::kSwizzleNone);
-      const uint32_t idesc = ptx::make_idesc_bf16(kTileM, (uint32_t)p.NBp, 0, 0, 0, 0);
       const uint32_t a_base = ptx::smem_u32(a_ring), b_lo16 = ptx::smem_u32(b_img) >> 4;
+      const int lanes_per_stage = p.slabs_per_chunk * GC;
       if (!p.dense) ptx::mbar_wait(w_bar, 0);
       uint32_t slot = 0, parity = 0, it = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
-        const int group = p.group_order[u / p.total_tiles];
-        const uint32_t mask = p.chunk_mask[group];
+        const int gi = u / p.total_tiles;
+        const uint32_t mask = p.chunk_mask[p.group_order[gi]];
         const uint32_t as = p.acc_stages == 2 ? (it & 1) : 0;
         const uint32_t use = p.acc_stages == 2 ? (it >> 1) : it;
         ptx::mbar_wait(&tempty_bar[as], (use & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_base = tmem_base + as * acc_cols;
-        uint32_t written = 0;
-        for (int tap = 0; tap < p.ntaps; ++tap)
-          for (int c = 0; c < p.chunks; ++c) {
-            if (!((mask >> c) & 1u)) continue;
+        const uint32_t d_unit = tmem_base + as * acc_cols;
+        const uint2* tbl_g = op_tbl_s + (size_t)p.group_order[gi] * p.chunks * lanes_per_stage;
+        bool closes = false;
+        for (int c = 0; c < p.chunks; ++c) {
+          if (!((mask >> c) & 1u)) continue;
+          // per chunk: this lane's MMA (the same for every tap up to the tap's weight-tile offset)
+          uint2 e = make_uint2(0u, 0u);
+          if (lane < lanes_per_stage) e = tbl_g[c * lanes_per_stage + lane];
+          const bool valid = (int)e.x < 0;
+          const bool first = valid && (e.x & (1u << 30)) != 0u;
+          closes = (e.x & (1u << 29)) != 0u;                   // last MMA of the stage: this lane commits
+          const uint32_t a_off16 = ((e.x >> 16) & 3u) * 2u;
+          const uint32_t d_lane = d_unit + ((e.x >> 20) & 7u) * (uint32_t)p.NBp;
+          uint32_t b16 = b_lo16 + (e.x & 0x3fffu);
+          for (int tap = 0; tap < p.ntaps; ++tap, b16 += p.tap_stride16) {
+            const uint64_t a_desc = a_hi | (uint64_t)((((a_base + slot * p.stage_bytes) >> 4) + a_off16) & 0x3fffu);
+            const uint64_t b_desc = b_hi | (uint64_t)(b16 & 0x3fffu);
             ptx::mbar_wait(&full_bar[slot], parity);
             ptx::tc_fence_after();
-            const uint32_t a_stage = a_base + slot * p.stage_bytes;
-            const uint32_t tap16 = b_lo16 + (((uint32_t)(tap * p.J) * p.slab_bytes) >> 4);
-            int row = (c * p.slabs_per_chunk) * p.ncomp_out + group * GC;
-            for (int s = 0; s < p.slabs_per_chunk; ++s, row += p.ncomp_out) {
-              const uint64_t a_desc = ptx::smem_desc(a_hi, a_stage + (uint32_t)s * 32u);
-#pragma unroll
-              for (int al = 0; al < GC; ++al) {
-                const uint32_t e = p.op_tbl[row + al];
-                if (e & 1u) {
-                  const uint64_t b_desc = b_hi | (uint64_t)((tap16 + (e >> 2)) & 0x3fffu);
-                  if (leader)
-                    ptx::umma_f16(d_base + (uint32_t)(al * p.NBp), a_desc, b_desc, idesc | ((e & 2u) << 13),
-                                  (written >> al) & 1u);
-                  written |= 1u << al;
-                }
-              }
+            // The accumulate flag of an issue site must be warp-uniform (ptxas derives the instruction's predicate
+            // with a vote over the issuing lanes), so the accumulator-initialising MMAs of a unit (tap 0, one
+            // per out component, distinct columns) have their own site ahead of the accumulating ones.
+            if (tap == 0) {
+              if (first) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 0u);
+              __syncwarp();
+              if (valid && !first) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 1u);
+            } else {
+              if (valid) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 1u);
             }
-            if (leader) ptx::umma_commit(&empty_bar[slot]);    // frees the ring slot once these MMAs retire
+            __syncwarp();
+            // tcgen05.commit tracks the MMAs of the executing thread; the tensor pipe retires in order, so the
+            // commit of the lane that issued last covers the whole stage
+            if (closes) ptx::umma_commit(&empty_bar[slot]);
             __syncwarp();
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }
-        if (leader) ptx::umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
+        }
+        if (closes) ptx::umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
         __syncwarp();
       }
     }
@@ -426,29 +441,49 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
       const int t = p->group_order[j]; p->group_order[j] = p->group_order[j - 1]; p->group_order[j - 1] = t;
     }
 
-  // MMA op table: entry [(chunk, slab), out component a] = valid | neg << 1 | (byte offset of the weight
-  // tile of (image, slab-in-component) inside the resident set) >> 4 << 2, read from the constant bank by
-  // the MMA-issuing warp
+  // MMA op table (conv_cl.h): per (group, chunk) the valid MMAs in (slab, component) order, zero-padded to
+  // slabs_per_chunk * gc entries.  `first` = the first MMA of a unit into out component a's accumulator columns
+  // (chunks outside the group's mask hold no valid entry for its components by construction).
   if (p->chunks * p->slabs_per_chunk * p->ncomp_out > cl::kOpTableEntries)
     return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: too many (slab, component) pairs for the MMA op table");
-  for (int cs = 0; cs < p->chunks * p->slabs_per_chunk; ++cs)
-    for (int a = 0; a < p->ncomp_out; ++a) {
-      const int ch0 = cs * 16;
-      const int b = ch0 / l.cpad;
-      const int j = (ch0 - b * l.cpad) >> 4;
-      const int img = p->op_img[b][a];
-      p->op_tbl[cs * p->ncomp_out + a] =
-          img < 0 ? 0u
-                  : (1u | ((uint32_t)p->op_neg[b][a] << 1) |
-                     ((((uint32_t)img * p->img_bytes + (uint32_t)j * p->slab_bytes) >> 4) << 2));
+  if (p->slabs_per_chunk * p->gc > 32)
+    return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: more than 32 MMAs per stage");
+  p->tap_stride16 = (uint32_t)(((size_t)p->J * p->slab_bytes) >> 4);
+  {
+    const uint32_t idesc = ptx::make_idesc_bf16(cl::kTileM, (uint32_t)p->NBp, 0, 0, 0, 0);
+    const int lps = p->slabs_per_chunk * p->gc;
+    for (int gi = 0; gi < ngroups; ++gi) {
+      bool seen[8] = {false, false, false, false, false, false, false, false};
+      for (int c = 0; c < p->chunks; ++c) {
+        uint2* dst = p->op_tbl + ((size_t)gi * p->chunks + c) * lps;
+        int n = 0;
+        for (int s = 0; s < p->slabs_per_chunk; ++s)
+          for (int al = 0; al < p->gc; ++al) {
+            const int ch0 = (c * p->slabs_per_chunk + s) * 16;
+            const int b = ch0 / l.cpad;
+            const int j = (ch0 - b * l.cpad) >> 4;
+            const int a = gi * p->gc + al;
+            const int img = p->op_img[b][a];
+            if (img < 0) continue;
+            uint2 e;
+            e.x = (1u << 31) | (seen[al] ? 0u : (1u << 30)) | ((uint32_t)al << 20) | ((uint32_t)s << 16) |
+                  (uint32_t)(((size_t)img * p->img_bytes + (size_t)j * p->slab_bytes) >> 4);
+            e.y = idesc | ((uint32_t)p->op_neg[b][a] << 14);
+            seen[al] = true;
+            dst[n++] = e;
+          }
+        if (n > 0) dst[n - 1].x |= 1u << 29;                 // the lane that issues last commits the stage
+        for (; n < lps; ++n) dst[n] = make_uint2(0u, 0u);
+      }
     }
+  }
   const int acc_cols = p->gc * p->NBp;
   p->acc_stages = acc_cols * 2 <= 512 ? 2 : 1;
   int cols = 32;
   while (cols < acc_cols * p->acc_stages) cols <<= 1;
   p->tmem_cols = cols;
   const size_t fixed = 1024 /* barriers */ + w.total + 4096 /* slack behind the tiles */;
-  const size_t budget = 226 * 1024;
+  const size_t budget = 222 * 1024;   // + 4 KB static (op table) + barriers stays under the 227 KB limit
   if (fixed + 2 * (size_t)p->stage_bytes > budget)
     return fail(SELDQ_ERR_UNSUPPORTED, "compact weights (%zu B as bf16 tiles) do not fit in shared memory", w.total);
   size_t ns = (budget - fixed) / p->stage_bytes;

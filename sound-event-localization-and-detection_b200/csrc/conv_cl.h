@@ -84,7 +84,14 @@ struct FpropParams {
   int8_t op_img[8][8];          // [in comp b][out comp a] -> image index or -1
   int8_t op_neg[8][8];
   int nstages, acc_stages, tmem_cols;
-  uint32_t op_tbl[kOpTableEntries];
+  // MMA op table [group][chunk][lane]: the MMAs of one stage dealt to the lanes of the MMA warp (copied to
+  // shared memory):
+  //   x = valid << 31 | first << 30 | last-of-stage << 29 | out component << 20 | slab << 16 |
+  //       (16-byte offset of the weight tile inside one tap's tile set)
+  //   y = the complete instruction descriptor (carries the block's sign in its negate-B bit)
+  // `first` marks the first MMA of a unit into that out component's accumulator columns (tap 0 only)
+  uint32_t tap_stride16;        // J * slab_bytes >> 4
+  uint2 op_tbl[kOpTableEntries];
 };
 
 // wgrad: D[(a,o), (b,i)] per tap = sum_t GY[(a,o), t] * X[t + off(tap), (b,i)]

@@ -275,6 +275,181 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_kernel(const __grid_co
   }
 }
 
+
+// ---- vectorised variants (W a multiple of 8, which covers every shipped configuration) -----------------
+// One block: 64 padded channels x 128 w.  Phase 1: a thread owns 8 consecutive w of one channel (16-byte
+// loads / stores in the tensor's own NCHW order) and drops its results, as bf16, into a [w][64 ch] shared
+// tile; phase 2 writes the tile as channels-last rows, 16 bytes per thread.
+constexpr int kVecTileW = 128;
+constexpr int kVecPitch = 128;          // bytes per w row of the shared tile: 64 ch x 2 B
+// element (w, c) of the tile lives at w * 128 + ((2 c) ^ (((w >> 3) & 15) << 3)): the 16 lanes of a phase-1
+// half-warp (same channel, w = 8 l + j) hit 16 different banks, and an aligned 16-byte group of 8 channels
+// stays an aligned 16-byte group (its 8-byte halves swap when bit 3 of the key is set)
+__device__ __forceinline__ uint32_t vec_tile_off(int wl, int byte_in_row) {
+  return (uint32_t)(wl * kVecPitch + (byte_in_row ^ (((wl >> 3) & 15) << 3)));
+}
+
+__device__ __forceinline__ void vec_tile_store_cl(const uint8_t* tile, __nv_bfloat16* dst_cl, long long row0,
+                                                  int w_base, int W, int Cp, int ct) {
+  // thread -> (w = tid / 8 + 32 k, channels 8 (tid % 8) ... + 7)
+  const int c0 = (threadIdx.x & 7) * 8;
+  if (ct * 64 + c0 >= Cp) return;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int wl = (threadIdx.x >> 3) + 32 * k;
+    const int w = w_base + wl;
+    if (w < W) {
+      const uint32_t key = (uint32_t)((wl >> 3) & 15) << 3;
+      uint4 v = *reinterpret_cast<const uint4*>(tile + wl * kVecPitch + ((c0 * 2) ^ (key & ~8u)));
+      if (key & 8u) v = make_uint4(v.z, v.w, v.x, v.y);
+      *reinterpret_cast<uint4*>(dst_cl + (row0 + w) * Cp + ct * 64 + c0) = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_constant__ TailParams p) {
+  __shared__ __align__(16) uint8_t tile[kVecTileW * kVecPitch];
+  const int HP = p.H / p.pool;
+  const unsigned long long seed = p.seed_ptr ? (unsigned long long)*p.seed_ptr : 0ULL;
+  const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
+  const float scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  for (long long blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
+    long long r = blk;
+    const int wt = (int)(r % p.tiles_w); r /= p.tiles_w;
+    const int ct = (int)(r % p.tiles_c); r /= p.tiles_c;
+    const int hp = (int)(r % HP);
+    const int n = (int)(r / HP);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int item = threadIdx.x + 256 * k;
+      const int cl = item >> 4, wl = (item & 15) * 8;
+      const int w = wt * kVecTileW + wl;
+      const int cp = ct * 64 + cl;
+      const int comp = cp / p.cpad, ci = cp - comp * p.cpad;
+      float z[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = 0.f;
+      if (cp < p.Cp && ci < p.cc && w < p.W) {
+        const int c = comp * p.cc + ci;
+        const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
+        const __nv_bfloat16* src = p.y + (((long long)n * p.C + c) * p.H + (long long)hp * p.pool) * p.W + w;
+        float best[8];
+        int arg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+        for (int q = 0; q < p.pool; ++q) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * p.W));
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h2[j]);
+            const float v0 = cf.x * f.x + cf.y, v1 = cf.x * f.y + cf.y;
+            if (v0 > best[2 * j] || v0 != v0) { best[2 * j] = v0; arg[2 * j] = q; }
+            if (v1 > best[2 * j + 1] || v1 != v1) { best[2 * j + 1] = v1; arg[2 * j + 1] = q; }
+          }
+        }
+        const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
+        uint32_t id[2] = {0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          bool keep = best[j] > 0.f;
+          if (keep && thresh) keep = dropout_keep(seed, p.salt, e + j, thresh);
+          z[j] = keep ? best[j] * scale : 0.f;
+          id[j >> 2] |= (uint32_t)(arg[j] | (keep ? 0x80 : 0)) << (8 * (j & 3));
+        }
+        *reinterpret_cast<uint2*>(p.idx + e) = make_uint2(id[0], id[1]);
+        if (p.z32) {
+          *reinterpret_cast<float4*>(p.z32 + e) = make_float4(z[0], z[1], z[2], z[3]);
+          *reinterpret_cast<float4*>(p.z32 + e + 4) = make_float4(z[4], z[5], z[6], z[7]);
+        }
+      }
+      if (p.z_cl) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<__nv_bfloat16*>(tile + vec_tile_off(wl + j, cl * 2)) = __float2bfloat16_rn(z[j]);
+      }
+    }
+    if (p.z_cl) {
+      __syncthreads();
+      vec_tile_store_cl(tile, p.z_cl, ((long long)n * HP + hp) * p.W, wt * kVecTileW, p.W, p.Cp, ct);
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cnn_tail_bwd_apply_vec_kernel(const __grid_constant__ TailParams p,
+                                                                    const float2* __restrict__ dmean) {
+  __shared__ __align__(16) uint8_t tile[kVecTileW * kVecPitch];
+  const int HP = p.H / p.pool;
+  const float scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  for (long long blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
+    long long r = blk;
+    const int wt = (int)(r % p.tiles_w); r /= p.tiles_w;
+    const int ct = (int)(r % p.tiles_c); r /= p.tiles_c;
+    const int h = (int)(r % p.H);
+    const int n = (int)(r / p.H);
+    const int hp = h / p.pool, kk = h - hp * p.pool;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int item = threadIdx.x + 256 * k;
+      const int cl = item >> 4, wl = (item & 15) * 8;
+      const int w = wt * kVecTileW + wl;
+      const int cp = ct * 64 + cl;
+      const int comp = cp / p.cpad, ci = cp - comp * p.cpad;
+      uint32_t o[4] = {0u, 0u, 0u, 0u};
+      if (cp < p.Cp && ci < p.cc && w < p.W) {
+        const int c = comp * p.cc + ci;
+        const long long row = ((long long)n * p.C + c) * p.H + h;
+        const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
+        const float2 dm = __ldg(dmean + c);
+        const uint4 yv = __ldg(reinterpret_cast<const uint4*>(p.y + row * p.W + w));
+        const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&yv);
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+        if (hp < HP) {
+          const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
+          const uint2 idv = __ldg(reinterpret_cast<const uint2*>(p.idx + e));
+          const uint32_t want = 0x80u | (uint32_t)kk;
+          // only load the pooled gradient when at least one of the 8 elements selects this row
+          uint32_t hit = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t b = ((j < 4 ? idv.x : idv.y) >> (8 * (j & 3))) & 0xffu;
+            hit |= (uint32_t)((b & 0x87u) == want) << j;
+          }
+          if (hit) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gz + e));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gz + e + 4));
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = ((hit >> j) & 1u) ? gg[j] * scale : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(y2[j]);
+          const float d0 = cf.x * (g[2 * j] - dm.x - (f.x - cf.z) * cf.w * dm.y);
+          const float d1 = cf.x * (g[2 * j + 1] - dm.x - (f.y - cf.z) * cf.w * dm.y);
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
+          o[j] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        if (p.d_t16) *reinterpret_cast<uint4*>(p.d_t16 + row * p.pitch + w) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      if (p.d_cl) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint16_t*>(tile + vec_tile_off(wl + j, cl * 2)) = (uint16_t)(o[j >> 1] >> (16 * (j & 1)));
+      }
+    }
+    if (p.d_cl) {
+      __syncthreads();
+      vec_tile_store_cl(tile, p.d_cl, ((long long)n * p.H + h) * p.W, wt * kVecTileW, p.W, p.Cp, ct);
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace epi
 
 // ---- host launchers ------------------------------------------------------------------------------------
@@ -304,7 +479,21 @@ int launch_bn_finalize(const double* sums, const float* gamma, const float* beta
   return check_launch("bn_finalize_kernel");
 }
 
+static bool tail_vec_ok(const epi::TailParams& p) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return p.W % 8 == 0 && al16(p.y) && al16(p.idx) && al16(p.z32) && al16(p.z_cl) && al16(p.gz) && al16(p.d_t16) &&
+         al16(p.d_cl) && (p.Cp % 8 == 0);
+}
+
 int launch_cnn_tail_fwd(epi::TailParams& p, cudaStream_t st) {
+  if (tail_vec_ok(p)) {
+    p.tiles_w = (p.W + epi::kVecTileW - 1) / epi::kVecTileW;
+    p.tiles_c = (p.Cp + 63) / 64;
+    p.total_blocks = (long long)p.tiles_w * p.tiles_c * (p.H / p.pool) * p.N;
+    const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
+    epi::cnn_tail_fwd_vec_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p);
+    return check_launch("cnn_tail_fwd_vec_kernel");
+  }
   p.tiles_w = (p.W + 31) / 32;
   p.tiles_c = (p.Cp + 63) / 64;
   p.total_blocks = (long long)p.tiles_w * p.tiles_c * (p.H / p.pool) * p.N;
@@ -331,6 +520,14 @@ int launch_cnn_tail_bwd(epi::TailParams& p, double* dsums, cudaStream_t st) {
   epi::cnn_tail_bwd_finalize_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(dsums, p.C, count, dmean);
   if ((rc = check_launch("cnn_tail_bwd_finalize_kernel"))) return rc;
   p.pitch = nchw16_pitch(p.W);
+  if (tail_vec_ok(p)) {      // W % 8 == 0  =>  pitch == W
+    p.tiles_w = (p.W + epi::kVecTileW - 1) / epi::kVecTileW;
+    p.tiles_c = (p.Cp + 63) / 64;
+    p.total_blocks = (long long)p.tiles_w * p.tiles_c * p.H * p.N;
+    const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
+    epi::cnn_tail_bwd_apply_vec_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p, dmean);
+    return check_launch("cnn_tail_bwd_apply_vec_kernel");
+  }
   p.tiles_w = (p.pitch + 31) / 32;
   p.tiles_c = (p.Cp + 63) / 64;
   p.total_blocks = (long long)p.tiles_w * p.tiles_c * p.H * p.N;

@@ -90,6 +90,125 @@ __global__ void __launch_bounds__(128) umma_kernel(const uint4* a_image, uint32_
   if (threadIdx.x < 32) ptx::tmem_dealloc(tbase, tmem_cols);
 }
 
+
+// tcgen05.mma issue-rate probe: one thread issues n_mma back-to-back MMAs (M = 128, K = 16, bf16) with the
+// product kernels' operand layouts (A: K-major 128B-swizzled [128 x 64] stages, one 16-channel slab per
+// MMA; B: K-major unswizzled [N x 16] tiles) cycling over `d_cycle` accumulator column ranges, and reports
+// SM cycles from the first issue to the completion of the last.  mode bit 0: A is MN-major ([64 t x 128])
+__global__ void __launch_bounds__(128) umma_rate_kernel(uint32_t n, int n_mma, int d_cycle, int mode,
+                                                       long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  for (uint32_t i = threadIdx.x; i < (128u * 1024u) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  ptx::fence_proxy_async();
+  if (threadIdx.x == 32) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < 32) ptx::tmem_alloc(&tmem_base, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tbase = tmem_base;
+  if ((mode & 8) && threadIdx.x < 32) {
+    // lane-parallel preparation: lane l owns MMA l of every stage (nl = d_cycle >> 8 lanes per stage); the
+    // descriptors are computed by all lanes at once and the issue is a per-lane tcgen05.mma
+    const int nl = d_cycle >> 8, dcyc = d_cycle & 255;
+    const int lane = threadIdx.x;
+    const uint32_t a0 = ptx::smem_u32(smem), b0 = a0 + 64 * 1024;
+    const uint64_t a_hi = ptx::make_smem_desc_hi(16, 1024, ptx::kSwizzle128B);
+    const uint64_t b_hi = ptx::make_smem_desc_hi(n * 16u, 128, ptx::kSwizzleNone);
+    const uint32_t idesc = ptx::make_idesc_bf16(128, n, 0, 0, 0, (uint32_t)(lane & 1));
+    const uint32_t a_off = (uint32_t)(lane & 3) * 32u, b_off = (uint32_t)((lane >> 2) & 7) * (n * 32u);
+    const uint32_t d = tbase + (uint32_t)((lane >> 2) % dcyc) * n;
+    const long long t0 = clock64();
+    uint32_t stage = 0;
+    for (int i = 0; i < n_mma; i += nl) {
+      const uint64_t ad = ptx::smem_desc(a_hi, a0 + stage * 16384u + a_off);
+      const uint64_t bd = ptx::smem_desc(b_hi, b0 + b_off + stage * 16u);
+      if (lane < nl) ptx::umma_f16(d, ad, bd, idesc, 1u);
+      __syncwarp();
+      stage = (stage + 1) & 3;
+    }
+    const long long t1 = clock64();
+    if (lane == 0) {
+      ptx::umma_commit(&bar);
+      ptx::mbar_wait(&bar, 0);
+      const long long t2 = clock64();
+      out[2 * blockIdx.x] = t1 - t0;
+      out[2 * blockIdx.x + 1] = t2 - t0;
+    }
+  } else if ((mode & 16) && threadIdx.x == 0) {
+    // one thread, ready-made entries {a offset, b offset, idesc, d offset} fetched from shared memory
+    __shared__ uint4 ent[32];
+    for (int l = 0; l < 32; ++l)
+      ent[l] = make_uint4((uint32_t)(l & 3) * 2u, ((uint32_t)((l >> 2) & 7) * (n * 32u)) >> 4,
+                          ptx::make_idesc_bf16(128, n, 0, 0, 0, (uint32_t)(l & 1)), (uint32_t)((l >> 2) % (d_cycle & 255)) * n);
+    const int nl = d_cycle >> 8;
+    const uint32_t a0 = ptx::smem_u32(smem), b0 = a0 + 64 * 1024;
+    const uint64_t a_hi = ptx::make_smem_desc_hi(16, 1024, ptx::kSwizzle128B);
+    const uint64_t b_hi = ptx::make_smem_desc_hi(n * 16u, 128, ptx::kSwizzleNone);
+    const long long t0 = clock64();
+    uint32_t stage = 0;
+    for (int i = 0; i < n_mma; i += nl) {
+      const uint32_t a16 = (a0 + stage * 16384u) >> 4, b16 = (b0 + stage * 16u) >> 4;
+#pragma unroll 4
+      for (int l = 0; l < nl; ++l) {
+        const uint4 e = ent[l];
+        ptx::umma_f16(tbase + e.w, a_hi | (uint64_t)(a16 + e.x), b_hi | (uint64_t)(b16 + e.y), e.z, 1u);
+      }
+      stage = (stage + 1) & 3;
+    }
+    const long long t1 = clock64();
+    ptx::umma_commit(&bar);
+    ptx::mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[2 * blockIdx.x] = t1 - t0;
+    out[2 * blockIdx.x + 1] = t2 - t0;
+  } else if (!(mode & 24) && threadIdx.x == 0) {
+    const uint32_t a0 = ptx::smem_u32(smem), b0 = a0 + 64 * 1024;
+    const uint64_t a_hi = (mode & 1) ? ptx::make_smem_desc_hi(8192, 1024, ptx::kSwizzle128B)
+                                     : ptx::make_smem_desc_hi(16, 1024, ptx::kSwizzle128B);
+    const uint64_t b_hi = ptx::make_smem_desc_hi(n * 16u, 128, ptx::kSwizzleNone);
+    const uint32_t idesc = ptx::make_idesc_bf16(128, n, (mode & 1) ? 1 : 0, 0, 0, 0);
+    const long long t0 = clock64();
+    int dc = 0;
+    if (mode & 2) {
+      // descriptors precomputed, 8 MMAs per iteration, no address arithmetic in the loop
+      uint64_t ad[4], bd[2];
+      for (int k = 0; k < 4; ++k) ad[k] = ptx::smem_desc(a_hi, a0 + (uint32_t)k * ((mode & 1) ? 2048u : 32u));
+      for (int k = 0; k < 2; ++k) bd[k] = ptx::smem_desc(b_hi, b0 + (uint32_t)k * (n * 32u));
+      const uint32_t d1 = tbase + ((d_cycle > 1) ? n : 0u);
+      for (int i = 0; i < n_mma; i += 8) {
+        ptx::umma_f16(tbase, ad[0], bd[0], idesc, 1u);
+        ptx::umma_f16(d1, ad[0], bd[1], idesc, 1u);
+        ptx::umma_f16(tbase, ad[1], bd[0], idesc, 1u);
+        ptx::umma_f16(d1, ad[1], bd[1], idesc, 1u);
+        ptx::umma_f16(tbase, ad[2], bd[0], idesc, 1u);
+        ptx::umma_f16(d1, ad[2], bd[1], idesc, 1u);
+        ptx::umma_f16(tbase, ad[3], bd[0], idesc, 1u);
+        ptx::umma_f16(d1, ad[3], bd[1], idesc, 1u);
+      }
+    } else
+    for (int i = 0; i < n_mma; ++i) {
+      const uint32_t a_addr = a0 + (uint32_t)((i >> 2) & 3) * 16384u + (uint32_t)(i & 3) * ((mode & 1) ? 2048u : 32u);
+      const uint32_t b_addr = b0 + (uint32_t)(i & 7) * (n * 32u);
+      ptx::umma_f16(tbase + (uint32_t)dc * n, ptx::smem_desc(a_hi, a_addr), ptx::smem_desc(b_hi, b_addr), idesc, 1u);
+      if (++dc == d_cycle) dc = 0;
+    }
+    const long long t1 = clock64();
+    ptx::umma_commit(&bar);
+    ptx::mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[2 * blockIdx.x] = t1 - t0;
+    out[2 * blockIdx.x + 1] = t2 - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace probe
 }  // namespace seldq
 
@@ -141,4 +260,17 @@ extern "C" int seldq_probe_umma(const void* a_image, uint32_t a_bytes, const voi
                                                             b_desc_step, n_cols, cols, out_128xN,
                                                             getenv("SELDQ_DEBUG") ? atoi(getenv("SELDQ_DEBUG")) : 0);
   return check_launch("probe::umma_kernel");
+}
+
+// out: 2 x blocks int64 (issue cycles, issue + drain cycles)
+extern "C" int seldq_probe_umma_rate(uint32_t n, int32_t n_mma, int32_t d_cycle, int32_t mode, int32_t blocks,
+                                     void* out, void* stream) {
+  if (n < 8 || n > 256 || (n & 7) || (d_cycle & 255) < 1 || (uint32_t)(d_cycle & 255) * n > 512 || blocks < 1 ||
+      ((mode & 24) && ((d_cycle >> 8) < 1 || (d_cycle >> 8) > 32 || n_mma % (d_cycle >> 8))))
+    return fail(SELDQ_ERR_INVALID, "bad umma rate probe arguments");
+  const uint32_t smem = 128 * 1024 + 4096;
+  cudaError_t e = cudaFuncSetAttribute(probe::umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "probe smem opt-in: %s", cudaGetErrorString(e));
+  probe::umma_rate_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(n, n_mma, d_cycle, mode, (long long*)out);
+  return check_launch("probe::umma_rate_kernel");
 }

@@ -200,10 +200,15 @@ int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, 
   p.chunks_w = (g.OW + 63) / 64;
   p.ksteps = (long long)g.N * g.OH * p.chunks_w;
   const int tiles = p.tap_groups * p.o_tiles;
-  long long splits = (2LL * num_sms() + tiles - 1) / tiles;
-  if (splits > p.ksteps) splits = p.ksteps;
+  // split-K over positions: one wave of CTAs (every split pays a TMEM round trip and one atomicAdd per compact
+  // element in its epilogue), at least 4 K steps each, and no empty splits
+  long long splits = num_sms() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > (p.ksteps + 3) / 4) splits = (p.ksteps + 3) / 4;
   if (splits > 65535) splits = 65535;
   if (splits < 1) splits = 1;
+  const long long per = (p.ksteps + splits - 1) / splits;
+  splits = (p.ksteps + per - 1) / per;
   p.splits = (int)splits;
   p.b_tap_bytes = (uint32_t)lx.Cp * 128u;
   p.stage_bytes = 128u * 128u + (uint32_t)p.taps_per_group * p.b_tap_bytes;
