@@ -287,7 +287,13 @@ def main():
                 line["cpu_baseline"] = dict(error=repr(e))
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down without destroy_process_group(): destroying the NCCL communicator while the captured training
+        # graph (which holds the all-reduce) is alive can block forever.  All ranks are done and synchronised here.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -168,6 +168,59 @@ int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* 
                        const float* coef, const uint8_t* idx, const float* gz, double* dsums, void* d_t16, void* d_cl,
                        void* stream);
 
+/* TCN residual block, model.py:109-132:
+ *     x = tanh(BN1(r));  y = dropout1d(tanh(BN_f(conv_f x)) * sigmoid(BN_g(conv_g x)));
+ *     r' = x + conv_res(y);  skips += conv_skip(y)
+ * The four convolutions are the entry points above; seldq_tcn_glue runs the bandwidth-bound steps between them.
+ * All tensors are fp32 (N, C, T); T must be a multiple of 8.  BatchNorm is train-mode: statistics travel as
+ * per-channel (sum, sum of squares) in double and every step derives mean / rstd from them itself.  bf16 operand
+ * outputs use the layouts of `layout_of`'s x (which = 0) or gy (which = 1) operand (seldq_conv_operand_info).
+ *   op                     in[0..4]                      writes
+ *   PREACT_FWD             r                             out32 = x, out_cl[0] = x operand; bn[0] running stats
+ *   ROW_STATS (flag = k)   k <= 2 tensors                stats_out[i] += (sum, sum sq) of in[i]  (caller zeroes)
+ *   GATE_FWD               y_f, y_g                      out_cl[0] = y operand; bn[0], bn[1] running stats
+ *   RESIDUAL_FWD           x, conv_res(y) | NULL, conv_skip(y)
+ *                                                        out32 = r', dsums[c] += (sum, sum sq) of r' (the next
+ *                                                        block's BN1 statistics; may be NULL),
+ *                                                        accum = (flag ? 0 : accum) + in[2]  (c2 channels)
+ *   GATE_BWD_REDUCE        y_f, y_g, gy1, gy2 | NULL     dsums[0..3][c] += sum dz_f, sum dz_f xhat_f, sum dz_g, sum dz_g xhat_g
+ *                                                        (= d beta_f, d gamma_f, d beta_g, d gamma_g)
+ *   GATE_BWD_APPLY         same                          d y_f -> out_cl[0], out_t16[0];  d y_g -> out_cl[1], out_t16[1]
+ *   PREACT_BWD_REDUCE      g_r' | NULL, gx1, gx2, x, r   dsums[0..1][c] += sum dz, sum dz xhat (= d beta, d gamma of BN1)
+ *   PREACT_BWD_APPLY       same                          out32 = g_r; out_cl[0], out_t16[0] (may be NULL) = its operands
+ * gy = gy1 + gy2 is the gradient w.r.t. y (two dgrad outputs), gx1 + gx2 the one w.r.t. x. */
+enum {
+  SELDQ_TCN_PREACT_FWD = 0, SELDQ_TCN_ROW_STATS = 1, SELDQ_TCN_GATE_FWD = 2, SELDQ_TCN_RESIDUAL_FWD = 3,
+  SELDQ_TCN_GATE_BWD_REDUCE = 4, SELDQ_TCN_GATE_BWD_APPLY = 5, SELDQ_TCN_PREACT_BWD_REDUCE = 6,
+  SELDQ_TCN_PREACT_BWD_APPLY = 7
+};
+typedef struct {
+  const double* sums;                 /* [C][2] batch sum, sum of squares */
+  const float* gamma;
+  const float* beta;
+  float* running_mean;                /* nn.BatchNorm momentum update by the forward steps; may be NULL */
+  float* running_var;
+} seldq_bn_ref_t;
+typedef struct {
+  int32_t n, c, t;
+  int32_t c2;                         /* channels of the skip tensors (RESIDUAL_FWD) */
+  float eps, momentum, drop_p;
+  uint32_t salt;                      /* dropout stream of this block */
+  double count;                       /* N * T */
+  seldq_bn_ref_t bn[2];
+  const float* in[5];
+  float* out32;
+  void* out_cl[2];
+  void* out_t16[2];
+  double* dsums;
+  double* stats_out[2];
+  float* accum;
+  const int64_t* seed;                /* device counter, advanced by the caller every step (iff drop_p > 0) */
+  int32_t flag;
+} seldq_tcn_glue_t;
+int seldq_tcn_glue(int32_t op, const seldq_tcn_glue_t* args, const seldq_conv_desc_t* layout_of, int32_t which,
+                   void* stream);
+
 /* ---- linear (A3, A4) ------------------------------------------------------------------- */
 size_t seldq_linear_workspace_bytes(const seldq_linear_desc_t* d, int32_t pass);
 int seldq_linear_fwd(const seldq_linear_desc_t* d, const float* x, const float* const* host_w,

@@ -30,6 +30,24 @@ class CnnTailDesc(ctypes.Structure):
                 ("pool", ctypes.c_int32), ("drop_p", ctypes.c_float), ("salt", ctypes.c_uint32)]
 
 
+class BnRef(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("sums", "gamma", "beta", "running_mean", "running_var")]
+
+
+class TcnGlue(ctypes.Structure):
+    """seldq_tcn_glue_t (include/seldq.h)."""
+    _fields_ = [("n", ctypes.c_int32), ("c", ctypes.c_int32), ("t", ctypes.c_int32), ("c2", ctypes.c_int32),
+                ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("drop_p", ctypes.c_float),
+                ("salt", ctypes.c_uint32), ("count", ctypes.c_double), ("bn", BnRef * 2),
+                ("inp", ctypes.c_void_p * 5), ("out32", ctypes.c_void_p), ("out_cl", ctypes.c_void_p * 2),
+                ("out_t16", ctypes.c_void_p * 2), ("dsums", ctypes.c_void_p), ("stats_out", ctypes.c_void_p * 2),
+                ("accum", ctypes.c_void_p), ("seed", ctypes.c_void_p), ("flag", ctypes.c_int32)]
+
+
+TCN_PREACT_FWD, TCN_ROW_STATS, TCN_GATE_FWD, TCN_RESIDUAL_FWD = 0, 1, 2, 3
+TCN_GATE_BWD_REDUCE, TCN_GATE_BWD_APPLY, TCN_PREACT_BWD_REDUCE, TCN_PREACT_BWD_APPLY = 4, 5, 6, 7
+
+
 class LinearDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("algebra", "precision", "rows", "in_features", "out_features")]
 
@@ -71,6 +89,8 @@ _PROTOS = {
                                           _P, _P]),
     "seldq_cnn_tail_bwd": (ctypes.c_int, [ctypes.POINTER(CnnTailDesc), ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P,
                                           _P, _P, _P]),
+    "seldq_tcn_glue": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(TcnGlue), ctypes.POINTER(ConvDesc), ctypes.c_int32,
+                                      _P]),
     "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P,
                                         ctypes.c_size_t, _P]),
     "seldq_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.POINTER(_P), _P,

@@ -71,10 +71,13 @@ SELDQ_HD void conv_load(const ConvParams& p, ConvShared& s, int tid, int bx, int
   }
   int ih;
   const bool hok = map_pos(g.transposed, oh, kh, g.sh, g.ph, g.dh, g.IH, &ih);
+  // consecutive threads walk along the contiguous axis of `in`: positions for NCW / NCHW tensors, channels for
+  // the (rows, features) matrices of the linear layers
+  const bool chan_fast = g.in_sC == 1 && g.in_sW != 1;
 #pragma unroll
   for (int j = 0; j < (BK * BN) / NT; ++j) {
     const int idx = tid + j * NT;
-    const int k = idx / BN, q = idx - k * BN;
+    const int k = chan_fast ? idx % BK : idx / BN, q = chan_fast ? idx / BK : idx - (idx / BN) * BN;
     float v = 0.f;
     int iw;
     if (hok && r0 + k < g.R && ow0 + q < g.OW &&
@@ -84,8 +87,12 @@ SELDQ_HD void conv_load(const ConvParams& p, ConvShared& s, int tid, int bx, int
   }
 }
 
-SELDQ_HD void conv_mac(const ConvShared& s, ConvThread& t, int tid) {
-  const int ty = tid >> 4, tx = tid & 15;
+SELDQ_HD bool conv_swap(const ConvGeom& g) { return g.out_sC == 1 && g.out_sW != 1; }
+
+// acc[i][j]: out channel ty + 16 i, position tx + 16 j.  swap: the 16 consecutive lanes index channels instead of
+// positions (output with unit channel stride, i.e. the linear layers), so that stores stay coalesced
+SELDQ_HD void conv_mac(const ConvShared& s, ConvThread& t, int tid, bool swap = false) {
+  const int ty = swap ? (tid & 15) : (tid >> 4), tx = swap ? (tid >> 4) : (tid & 15);
 #pragma unroll
   for (int k = 0; k < BK; ++k) {
     float a[4], b[4];
@@ -102,7 +109,8 @@ SELDQ_HD void conv_mac(const ConvShared& s, ConvThread& t, int tid) {
 
 SELDQ_HD void conv_store(const ConvParams& p, const ConvThread& t, int tid, int bx, int by, int bz) {
   const ConvGeom& g = p.g;
-  const int ty = tid >> 4, tx = tid & 15;
+  const bool swap = conv_swap(g);
+  const int ty = swap ? (tid & 15) : (tid >> 4), tx = swap ? (tid >> 4) : (tid & 15);
   const int n = bz / g.OH, oh = bz - n * g.OH;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -174,7 +182,9 @@ SELDQ_HD void wgrad_load(const WgradParams& p, WgradShared& s, int tid, int bx, 
 #pragma unroll
   for (int j = 0; j < (WK * WT) / NT; ++j) {
     const int idx = tid + j * NT;
-    const int c = idx / WK, q = idx - c * WK;   // consecutive threads walk along W (coalesced)
+    // consecutive threads walk along the contiguous axis: W for NCW / NCHW, channels for the linear layers
+    const bool chan_fast = g.out_sC == 1 && g.out_sW != 1;
+    const int c = chan_fast ? idx % WT : idx / WK, q = chan_fast ? idx / WT : idx - (idx / WK) * WK;
     const int ow = chunk * WK + q;
     float gv = 0.f, xv = 0.f;
     if (ow < g.OW) {

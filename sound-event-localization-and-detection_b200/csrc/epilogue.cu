@@ -22,32 +22,10 @@
 #include "conv_cl.h"
 #include "epilogue.h"
 #include "launch.h"
+#include "tile_cl.cuh"
 
 namespace seldq {
 namespace epi {
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// block-wide sum of two values; result valid in thread 0
-__device__ __forceinline__ void block_sum2(float& a, float& b) {
-  __shared__ float sa[32], sb[32];
-  a = warp_sum(a);
-  b = warp_sum(b);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) { sa[warp] = a; sb[warp] = b; }
-  __syncthreads();
-  if (warp == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    a = lane < nw ? sa[lane] : 0.f;
-    b = lane < nw ? sb[lane] : 0.f;
-    a = warp_sum(a);
-    b = warp_sum(b);
-  }
-}
 
 __device__ __forceinline__ float load_as_float(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float load_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
@@ -110,18 +88,6 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
     const double unbiased = count > 1 ? var * count / (count - 1) : var;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
   }
-}
-
-__device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33;
-  return (uint32_t)x;
-}
-// counter-based dropout mask: the same (seed, salt, element) always gives the same decision, so the backward
-// pass needs no stored mask beyond the keep bit
-__device__ __forceinline__ bool dropout_keep(unsigned long long seed, uint32_t salt, long long elem, uint32_t thresh) {
-  return hash_u32((seed * 0x9E3779B97F4A7C15ULL) ^ ((unsigned long long)salt << 44) ^ (unsigned long long)elem) >= thresh;
 }
 
 // One block: 64 padded channels x 32 w positions of one pooled row (n, h').
@@ -280,33 +246,6 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_kernel(const __grid_co
 // One block: 64 padded channels x 128 w.  Phase 1: a thread owns 8 consecutive w of one channel (16-byte
 // loads / stores in the tensor's own NCHW order) and drops its results, as bf16, into a [w][64 ch] shared
 // tile; phase 2 writes the tile as channels-last rows, 16 bytes per thread.
-constexpr int kVecTileW = 128;
-constexpr int kVecPitch = 128;          // bytes per w row of the shared tile: 64 ch x 2 B
-// element (w, c) of the tile lives at w * 128 + ((2 c) ^ (((w >> 3) & 15) << 3)): the 16 lanes of a phase-1
-// half-warp (same channel, w = 8 l + j) hit 16 different banks, and an aligned 16-byte group of 8 channels
-// stays an aligned 16-byte group (its 8-byte halves swap when bit 3 of the key is set)
-__device__ __forceinline__ uint32_t vec_tile_off(int wl, int byte_in_row) {
-  return (uint32_t)(wl * kVecPitch + (byte_in_row ^ (((wl >> 3) & 15) << 3)));
-}
-
-__device__ __forceinline__ void vec_tile_store_cl(const uint8_t* tile, __nv_bfloat16* dst_cl, long long row0,
-                                                  int w_base, int W, int Cp, int ct) {
-  // thread -> (w = tid / 8 + 32 k, channels 8 (tid % 8) ... + 7)
-  const int c0 = (threadIdx.x & 7) * 8;
-  if (ct * 64 + c0 >= Cp) return;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int wl = (threadIdx.x >> 3) + 32 * k;
-    const int w = w_base + wl;
-    if (w < W) {
-      const uint32_t key = (uint32_t)((wl >> 3) & 15) << 3;
-      uint4 v = *reinterpret_cast<const uint4*>(tile + wl * kVecPitch + ((c0 * 2) ^ (key & ~8u)));
-      if (key & 8u) v = make_uint4(v.z, v.w, v.x, v.y);
-      *reinterpret_cast<uint4*>(dst_cl + (row0 + w) * Cp + ct * 64 + c0) = v;
-    }
-  }
-}
-
 __global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_constant__ TailParams p) {
   __shared__ __align__(16) uint8_t tile[kVecTileW * kVecPitch];
   const int HP = p.H / p.pool;

@@ -28,6 +28,6 @@ int launch_bias_grad(const float* gy, float* gb, int C, int N, int H, int W, lon
 int launch_cast_bf16(const float* src, void* dst, size_t n, cudaStream_t st);
 int launch_cast_bf16_mirror(const float* src, void* dst, long long rows, int w, int pitch, const int* shifts,
                             int nshifts, cudaStream_t st);
-int launch_stft(const stft::Params& p, int n_signals, cudaStream_t st);
+int launch_stft(stft::Params& p, int n_signals, cudaStream_t st);
 
 }  // namespace seldq

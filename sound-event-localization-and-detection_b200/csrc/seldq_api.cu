@@ -8,6 +8,7 @@
 #include "geom.h"
 #include "launch.h"
 #include "stft.cuh"
+#include "tcn_glue.h"
 
 using namespace seldq;
 
@@ -388,6 +389,73 @@ extern "C" int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_co
   p.idx = const_cast<uint8_t*>(idx); p.gz = gz;
   p.d_t16 = reinterpret_cast<__nv_bfloat16*>(d_t16); p.d_cl = reinterpret_cast<__nv_bfloat16*>(d_cl);
   return launch_cnn_tail_bwd(p, dsums, (cudaStream_t)stream);
+}
+
+extern "C" int seldq_tcn_glue(int32_t op, const seldq_tcn_glue_t* a, const seldq_conv_desc_t* layout_of, int32_t which,
+                              void* stream) {
+  if (!a || a->n <= 0 || a->c <= 0 || a->t <= 0 || a->count <= 0 || a->drop_p < 0.f || a->drop_p >= 1.f)
+    return fail(SELDQ_ERR_INVALID, "seldq_tcn_glue: bad arguments");
+  tcn::GlueParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = a->n; p.C = a->c; p.T = a->t; p.C2 = a->c2;
+  p.count = a->count; p.eps = a->eps; p.momentum = a->momentum;
+  p.drop_p = a->drop_p; p.salt = a->salt; p.seed_ptr = reinterpret_cast<const long long*>(a->seed);
+  if (a->drop_p > 0.f && !a->seed) return fail(SELDQ_ERR_INVALID, "seldq_tcn_glue: dropout needs a seed pointer");
+  for (int i = 0; i < 2; ++i) {
+    p.bn[i].sums = a->bn[i].sums; p.bn[i].gamma = a->bn[i].gamma; p.bn[i].beta = a->bn[i].beta;
+    p.bn[i].running_mean = a->bn[i].running_mean; p.bn[i].running_var = a->bn[i].running_var;
+    p.out_cl[i] = reinterpret_cast<__nv_bfloat16*>(a->out_cl[i]);
+    p.out_t16[i] = reinterpret_cast<__nv_bfloat16*>(a->out_t16[i]);
+    p.stats_out[i] = a->stats_out[i];
+  }
+  for (int i = 0; i < 5; ++i) p.in[i] = a->in[i];
+  p.out32 = a->out32; p.dsums = a->dsums; p.accum = a->accum;
+  p.cc = a->c; p.cpad = (a->c + 63) / 64 * 64; p.Cp = p.cpad;
+  p.pitch = nchw16_pitch(a->t);
+  int rc;
+  if (layout_of) {
+    if (which != 0 && which != 1) return fail(SELDQ_ERR_INVALID, "operand selector must be 0 (x) or 1 (gy)");
+    ConvGeom g;
+    if ((rc = make_conv_geom(layout_of, SELDQ_PASS_FWD, &g))) return rc;
+    const OperandInfo o = operand_info(g, which);
+    if (o.c != a->c || o.n != a->n || o.h != 1 || o.w != a->t)
+      return fail(SELDQ_ERR_INVALID, "seldq_tcn_glue: tensor (%d, %d, %d) is not operand %d of the given convolution",
+                  a->n, a->c, a->t, which);
+    p.cc = o.lay.cc; p.cpad = o.lay.cpad; p.Cp = o.lay.Cp;
+    if (o.lay.nc == 1) { p.cc = a->c; p.cpad = o.lay.Cp; }
+  } else if (a->out_cl[0] || a->out_cl[1]) {
+    return fail(SELDQ_ERR_INVALID, "seldq_tcn_glue: channels-last outputs need the consuming convolution's descriptor");
+  }
+  // required pointers per step
+  auto need = [&](bool ok) { return ok ? SELDQ_OK : fail(SELDQ_ERR_INVALID, "seldq_tcn_glue: null pointer for op %d", op); };
+  switch (op) {
+    case SELDQ_TCN_PREACT_FWD: rc = need(a->in[0] && a->out32 && a->out_cl[0] && a->bn[0].sums); break;
+    case SELDQ_TCN_ROW_STATS:
+      rc = need(a->flag >= 1 && a->flag <= 2 && a->in[0] && a->stats_out[0] && (a->flag < 2 || (a->in[1] && a->stats_out[1])));
+      break;
+    case SELDQ_TCN_GATE_FWD: rc = need(a->in[0] && a->in[1] && a->out_cl[0] && a->bn[0].sums && a->bn[1].sums); break;
+    case SELDQ_TCN_RESIDUAL_FWD:
+      rc = need((a->in[1] == nullptr || (a->in[0] && a->out32)) && (a->in[2] == nullptr || (a->accum && a->c2 > 0)) &&
+                (a->in[1] || a->in[2]));
+      break;
+    case SELDQ_TCN_GATE_BWD_REDUCE:
+      rc = need(a->in[0] && a->in[1] && a->in[2] && a->dsums && a->bn[0].sums && a->bn[1].sums);
+      break;
+    case SELDQ_TCN_GATE_BWD_APPLY:
+      rc = need(a->in[0] && a->in[1] && a->in[2] && a->dsums && a->bn[0].sums && a->bn[1].sums && a->out_cl[0] &&
+                a->out_cl[1] && a->out_t16[0] && a->out_t16[1]);
+      break;
+    case SELDQ_TCN_PREACT_BWD_REDUCE:
+      rc = need(a->in[1] && a->in[2] && a->in[3] && a->in[4] && a->dsums && a->bn[0].sums);
+      break;
+    case SELDQ_TCN_PREACT_BWD_APPLY:
+      rc = need(a->in[1] && a->in[2] && a->in[3] && a->in[4] && a->dsums && a->bn[0].sums && a->out32);
+      break;
+    default: return fail(SELDQ_ERR_INVALID, "seldq_tcn_glue: unknown op %d", op);
+  }
+  if (rc) return rc;
+  if ((rc = cuda_ready())) return rc;
+  return launch_tcn_glue(op, p, a->flag, (cudaStream_t)stream);
 }
 
 // ---- linear: 0.18 GFLOP per call in the reference configs -> always the fp32 FFMA kernels -----------

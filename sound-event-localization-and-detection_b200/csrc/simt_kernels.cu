@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const __grid_constant__ C
       if (conv_chunk_is_zero(p.g, blockIdx.y * BM, r0)) continue;  // block-uniform
       conv_load(p, s, threadIdx.x, blockIdx.x, blockIdx.y, blockIdx.z, tap, r0);
       __syncthreads();
-      conv_mac(s, t, threadIdx.x);
+      conv_mac(s, t, threadIdx.x, conv_swap(p.g));
       __syncthreads();
     }
   conv_store(p, t, threadIdx.x, blockIdx.x, blockIdx.y, blockIdx.z);

@@ -13,6 +13,8 @@
 // gradients inside the CTA (sign-weighted sum over the (a,b) pairs of each compact tensor, through shared
 // memory) and adds the result with one atomicAdd per compact element -- the expanded gradient never
 // reaches HBM.
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -207,6 +209,10 @@ int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, 
   if (splits > (p.ksteps + 3) / 4) splits = (p.ksteps + 3) / 4;
   if (splits > 65535) splits = 65535;
   if (splits < 1) splits = 1;
+  if (const char* e = getenv("SELDQ_WGRAD_SPLITS")) {      // tuning knob (tools/kprof.py)
+    const long long v = atoll(e);
+    if (v >= 1 && v <= p.ksteps) splits = v;
+  }
   const long long per = (p.ksteps + splits - 1) / splits;
   splits = (p.ksteps + per - 1) / per;
   p.splits = (int)splits;

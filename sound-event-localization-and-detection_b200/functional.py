@@ -19,12 +19,23 @@ _PRECISION = {"fp32": PREC_FP32, "bf16": PREC_BF16}[os.environ.get("SELDQ_PRECIS
 _NCOMP = {ALG_REAL: 1, ALG_Q: 4, ALG_DQ: 8}
 
 
+def _apply_tf32_policy():
+    """The real-valued layers around the hot path (MultiHeadAttention projections / attention products, the final
+    nn.Linear heads) are PyTorch ops.  In 'fp32' mode they keep the reference's true-fp32 arithmetic (the reference
+    disables cuDNN, model.py:10, so no TF32 is involved); in 'bf16' mode -- the tensor-core mode, gated at rel 2e-2 --
+    they may use TF32 tensor cores (rel ~5e-4), which replaces their SIMT sgemm kernels."""
+    on = _PRECISION == PREC_BF16
+    torch.backends.cuda.matmul.allow_tf32 = on
+    torch.backends.cudnn.allow_tf32 = on
+
+
 def set_precision(name):
     """'fp32': FFMA kernels, parity gate rel 1e-4.  'bf16': tcgen05 tensor-core kernels (bf16
     operands, fp32 accumulation), parity gate rel 2e-2.  Returns the previous setting."""
     global _PRECISION
     prev = get_precision()
     _PRECISION = {"fp32": PREC_FP32, "bf16": PREC_BF16}[name]
+    _apply_tf32_policy()
     return prev
 
 

@@ -208,3 +208,285 @@ def cnn_stack(x, convs, bns, pools, drops, seed):
         tensors += list(ws) + [bn.weight, bn.bias]
         bn.num_batches_tracked.add_(1)
     return _CnnStack.apply(x, spec, seed, *tensors)
+
+
+# ---- TCN residual blocks (model.py:109-132) -------------------------------------------------------------------
+def _glue(op, layout_of, which, N, C, T, c2=0, eps=1e-5, momentum=0.1, drop_p=0.0, salt=0, bn=(), inp=(), out32=None,
+          out_cl=(), out_t16=(), dsums=None, stats_out=(), accum=None, seed=None, flag=0):
+    """One seldq_tcn_glue call (include/seldq.h).  bn: up to two (sums, gamma, beta, running_mean, running_var)."""
+    a = _lib.TcnGlue()
+    a.n, a.c, a.t, a.c2 = N, C, T, c2
+    a.eps, a.momentum, a.drop_p, a.salt = eps, momentum, drop_p, salt
+    a.count = float(N * T)
+    for i, b in enumerate(bn):
+        a.bn[i].sums, a.bn[i].gamma, a.bn[i].beta, a.bn[i].running_mean, a.bn[i].running_var = [_ptr(t) for t in b]
+    for i, t in enumerate(inp):
+        a.inp[i] = _ptr(t)
+    a.out32 = _ptr(out32)
+    for i, t in enumerate(out_cl):
+        a.out_cl[i] = _ptr(t)
+    for i, t in enumerate(out_t16):
+        a.out_t16[i] = _ptr(t)
+    a.dsums = _ptr(dsums)
+    for i, t in enumerate(stats_out):
+        a.stats_out[i] = _ptr(t)
+    a.accum = _ptr(accum)
+    a.seed = _ptr(seed) if drop_p > 0 else None
+    a.flag = flag
+    F._timed("tcn_glue_kernels", 0.0, 1, lambda: _lib.check(_lib.lib().seldq_tcn_glue(
+        op, ctypes.byref(a), None if layout_of is None else ctypes.byref(layout_of), which, _stream())))
+
+
+class _TcnStack(torch.autograd.Function):
+    """All residual blocks of TC_Block in one autograd node.
+       spec: per block dict(algebra, nw, k, dil, pad, drop_p, salt, has_res, bn1, bnf, bng) with bn* = (eps, momentum,
+             running_mean, running_var)
+       tensors: per block  conv1_filter (nw), conv1_gate (nw), conv2_skip (nw), conv2_residual (nw) compact
+             weights, then gamma / beta of batch_filter1, batch_filter2, batch_gate2."""
+
+    @staticmethod
+    def forward(ctx, r, spec, seed, *tensors):
+        L_ = _lib.lib()
+        dev = r.device
+        r = r.contiguous()
+        N, Lc, T = r.shape
+        f32 = dict(dtype=torch.float32, device=dev)
+        blocks, pos = [], 0
+        for s in spec:
+            nw = s["nw"]
+            wf, wg, wsk, wr = (tuple(t.contiguous() for t in tensors[pos + i * nw:pos + (i + 1) * nw]) for i in range(4))
+            bnp = tensors[pos + 4 * nw:pos + 4 * nw + 6]
+            pos += 4 * nw + 6
+            blocks.append((s, wf, wg, wsk, wr, bnp))
+        saved, metas = [], []
+        skip_sum = None
+        with torch.cuda.device(dev):
+            # batch statistics of every BatchNorm of the stack: one zeroed buffer, [block](sums1 (L,2), sums2 (2,G,2))
+            gs_ = [w[1][0].shape[0] * F._NCOMP[w[0]["algebra"]] for w in blocks]
+            stats = torch.zeros(sum(2 * Lc + 4 * g for g in gs_), dtype=torch.float64, device=dev)
+            offs, o = [], 0
+            for g in gs_:
+                offs.append(o)
+                o += 2 * Lc + 4 * g
+            sums1 = stats[:2 * Lc].view(Lc, 2)
+            _glue(_lib.TCN_ROW_STATS, None, 0, N, Lc, T, inp=(r,), stats_out=(sums1,), flag=1)
+            for k, (s, wf, wg, wsk, wr, bnp) in enumerate(blocks):
+                nc = F._NCOMP[s["algebra"]]
+                G, U = wf[0].shape[0] * nc, wsk[0].shape[0] * nc
+                d1 = _lib.ConvDesc(s["algebra"], PREC_BF16, 1, N, Lc, G, 1, T, 1, s["k"], 1, 1, 0, s["pad"], 1, s["dil"])
+                dsk = _lib.ConvDesc(s["algebra"], PREC_BF16, 1, N, G, U, 1, T, 1, 1, 1, 1, 0, 0, 1, 1)
+                dre = _lib.ConvDesc(s["algebra"], PREC_BF16, 1, N, G, Lc, 1, T, 1, 1, 1, 1, 0, 0, 1, 1)
+                g1, b1, gf, bf, gg, bg = bnp
+                e1, m1, rm1, rv1 = s["bn1"]
+                ef, mf, rmf, rvf = s["bnf"]
+                eg, mg, rmg, rvg = s["bng"]
+                # x = tanh(BN1(r))
+                xa = torch.empty((N, Lc, T), **f32)
+                xa_cl = torch.empty(F._operand_info(d1, 0)[2], dtype=torch.uint8, device=dev)
+                _glue(_lib.TCN_PREACT_FWD, d1, 0, N, Lc, T, eps=e1, momentum=m1, bn=((sums1, g1, b1, rm1, rv1),),
+                      inp=(r,), out32=xa, out_cl=(xa_cl,))
+                # y_f, y_g
+                ys = []
+                for w in (wf, wg):
+                    y = torch.empty((N, G, T), **f32)
+                    wp = _lib.ptr_array([t.data_ptr() for t in w])
+                    pk = F.packed_weights(w, d1, PASS_FWD)
+                    F._timed("qconv_cl_fprop_kernel", F._conv_flop(d1, 1, T), 1, lambda: _lib.check(
+                        L_.seldq_conv_fwd(ctypes.byref(d1), None, xa_cl.data_ptr(), wp, _ptr(pk), None, y.data_ptr(),
+                                          None, 0, _stream())))
+                    ys.append(y)
+                yf, yg = ys
+                sums2 = stats[offs[k] + 2 * Lc:offs[k] + 2 * Lc + 4 * G].view(2, G, 2)
+                _glue(_lib.TCN_ROW_STATS, None, 0, N, G, T, inp=(yf, yg), stats_out=(sums2[0], sums2[1]), flag=2)
+                # y = dropout1d(tanh(BN_f y_f) * sigmoid(BN_g y_g)), only as conv2's operand
+                y_cl = torch.empty(F._operand_info(dsk, 0)[2], dtype=torch.uint8, device=dev)
+                _glue(_lib.TCN_GATE_FWD, dsk, 0, N, G, T, eps=ef, momentum=mf, drop_p=s["drop_p"], salt=s["salt"],
+                      bn=((sums2[0], gf, bf, rmf, rvf), (sums2[1], gg, bg, rmg, rvg)), inp=(yf, yg), out_cl=(y_cl,),
+                      seed=seed)
+                outs = []
+                for w, d, on in ((wsk, dsk, True), (wr, dre, s["has_res"])):
+                    if not on:
+                        outs.append(None)
+                        continue
+                    o = torch.empty((N, d.cout, T), **f32)
+                    wp = _lib.ptr_array([t.data_ptr() for t in w])
+                    pk = F.packed_weights(w, d, PASS_FWD)
+                    F._timed("qconv_cl_fprop_kernel", F._conv_flop(d, 1, T), 1, lambda: _lib.check(
+                        L_.seldq_conv_fwd(ctypes.byref(d), None, y_cl.data_ptr(), wp, _ptr(pk), None, o.data_ptr(),
+                                          None, 0, _stream())))
+                    outs.append(o)
+                skip, res = outs
+                if skip_sum is None:
+                    skip_sum = torch.empty((N, U, T), **f32)
+                r_next = sums1_next = None
+                if s["has_res"]:
+                    r_next = torch.empty((N, Lc, T), **f32)
+                    sums1_next = stats[offs[k + 1]:offs[k + 1] + 2 * Lc].view(Lc, 2)
+                _glue(_lib.TCN_RESIDUAL_FWD, None, 0, N, Lc, T, c2=U, inp=(xa, res, skip), out32=r_next,
+                      dsums=sums1_next, accum=skip_sum, flag=1 if k == 0 else 0)
+                saved += [r, xa, xa_cl, yf, yg, y_cl, sums1, sums2]
+                metas.append((s, d1, dsk, dre, G, U))
+                r, sums1 = r_next, sums1_next
+        ctx.metas = metas
+        ctx.shape = (N, Lc, T)
+        ctx.block_params = [(wf, wg, wsk, wr, bnp) for _, wf, wg, wsk, wr, bnp in blocks]
+        ctx.seed = seed
+        ctx.save_for_backward(*saved)
+        return skip_sum
+
+    @staticmethod
+    def backward(ctx, gs):
+        L_ = _lib.lib()
+        saved = ctx.saved_tensors
+        dev = gs.device
+        gs = gs.contiguous()
+        N, Lc, T = ctx.shape
+        f32 = dict(dtype=torch.float32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        nblocks = len(ctx.metas)
+        grads = [None] * nblocks
+
+        def dgrad(d, w, gy_cl):
+            gx = torch.empty((N, d.cin, T), **f32)
+            wp = _lib.ptr_array([t.data_ptr() for t in w])
+            pk = F.packed_weights(w, d, PASS_DGRAD)
+            F._timed("qconv_cl_fprop_kernel", F._conv_flop(d, 1, T), 1, lambda: _lib.check(
+                L_.seldq_conv_dgrad(ctypes.byref(d), None, gy_cl.data_ptr(), wp, _ptr(pk), gx.data_ptr(), None, 0,
+                                    _stream())))
+            return gx
+
+        def wgrad(d, w, x_cl, gy_t16):
+            gws, direct = F._grad_targets(w, [True] * len(w))
+            gp = _lib.ptr_array([g.data_ptr() for g in gws])
+            F._timed("qconv_cl_wgrad_kernel", F._conv_flop(d, 1, T), 1, lambda: _lib.check(
+                L_.seldq_conv_wgrad(ctypes.byref(d), None, x_cl.data_ptr(), None, gy_t16.data_ptr(), gp, None,
+                                    1 if direct else 0, None, 0, _stream())))
+            return [None] * len(w) if direct else list(gws)
+
+        with torch.cuda.device(dev):
+            g_rn = g_rn_cl = g_rn_t16 = None
+            gs_cl = gs_t16 = None
+            # BatchNorm backward reductions of the whole stack (= d beta / d gamma): one zeroed double buffer,
+            # [block](pre-activation (2, L), gate (4, G)), converted to fp32 once at the end
+            sizes = [2 * Lc + 4 * m[4] for m in ctx.metas]
+            red = torch.zeros(sum(sizes), dtype=torch.float64, device=dev)
+            roff = [sum(sizes[:i]) for i in range(nblocks)]
+            for k in reversed(range(nblocks)):
+                s, d1, dsk, dre, G, U = ctx.metas[k]
+                r, xa, xa_cl, yf, yg, y_cl, sums1, sums2 = saved[8 * k:8 * k + 8]
+                wf, wg, wsk, wr, (g1, b1, gf, bf, gg, bg) = ctx.block_params[k]
+                e1 = s["bn1"][0]
+                ef = s["bnf"][0]
+                if gs_cl is None:
+                    gs_cl, gs_t16 = F.stage_operand(gs, dsk, 1, want_cl=True, want_t16=True)
+                # conv2: gradient w.r.t. y and the weights
+                gy1 = dgrad(dsk, wsk, gs_cl)
+                gw_sk = wgrad(dsk, wsk, y_cl, gs_t16)
+                gy2, gw_r = None, [None] * len(wr)
+                if s["has_res"]:
+                    gy2 = dgrad(dre, wr, g_rn_cl)
+                    gw_r = wgrad(dre, wr, y_cl, g_rn_t16)
+                # gate
+                bn2 = ((sums2[0], gf, bf, None, None), (sums2[1], gg, bg, None, None))
+                dsg = red[roff[k] + 2 * Lc:roff[k] + 2 * Lc + 4 * G]
+                _glue(_lib.TCN_GATE_BWD_REDUCE, None, 0, N, G, T, eps=ef, drop_p=s["drop_p"], salt=s["salt"], bn=bn2,
+                      inp=(yf, yg, gy1, gy2), dsums=dsg, seed=ctx.seed)
+                _, _, clb, t16b = F._operand_info(d1, 1)
+                df_cl, dg_cl = torch.empty(clb, **u8), torch.empty(clb, **u8)
+                df_t16, dg_t16 = torch.empty(t16b, **u8), torch.empty(t16b, **u8)
+                _glue(_lib.TCN_GATE_BWD_APPLY, d1, 1, N, G, T, eps=ef, drop_p=s["drop_p"], salt=s["salt"], bn=bn2,
+                      inp=(yf, yg, gy1, gy2), dsums=dsg, out_cl=(df_cl, dg_cl), out_t16=(df_t16, dg_t16), seed=ctx.seed)
+                # conv1
+                gx1 = dgrad(d1, wf, df_cl)
+                gx2 = dgrad(d1, wg, dg_cl)
+                gw_f = wgrad(d1, wf, xa_cl, df_t16)
+                gw_g = wgrad(d1, wg, xa_cl, dg_t16)
+                # pre-activation
+                bn1 = ((sums1, g1, b1, None, None),)
+                ds1 = red[roff[k]:roff[k] + 2 * Lc]
+                _glue(_lib.TCN_PREACT_BWD_REDUCE, None, 0, N, Lc, T, eps=e1, bn=bn1, inp=(g_rn, gx1, gx2, xa, r), dsums=ds1)
+                g_r = torch.empty((N, Lc, T), **f32)
+                if k > 0:
+                    dprev = ctx.metas[k - 1][3]
+                    _, _, clb, t16b = F._operand_info(dprev, 1)
+                    g_rn_cl, g_rn_t16 = torch.empty(clb, **u8), torch.empty(t16b, **u8)
+                    _glue(_lib.TCN_PREACT_BWD_APPLY, dprev, 1, N, Lc, T, eps=e1, bn=bn1, inp=(g_rn, gx1, gx2, xa, r),
+                          dsums=ds1, out32=g_r, out_cl=(g_rn_cl,), out_t16=(g_rn_t16,))
+                else:
+                    _glue(_lib.TCN_PREACT_BWD_APPLY, None, 0, N, Lc, T, eps=e1, bn=bn1, inp=(g_rn, gx1, gx2, xa, r),
+                          dsums=ds1, out32=g_r)
+                g_rn = g_r
+                grads[k] = list(gw_f) + list(gw_g) + list(gw_sk) + list(gw_r)
+            redf = red.float()
+        flat = []
+        for k, g in enumerate(grads):
+            G = ctx.metas[k][4]
+            p1, pg = redf[roff[k]:roff[k] + 2 * Lc].view(2, Lc), redf[roff[k] + 2 * Lc:roff[k] + 2 * Lc + 4 * G].view(4, G)
+            # (gamma, beta) of batch_filter1, batch_filter2, batch_gate2
+            flat += g + [p1[1], p1[0], pg[1], pg[0], pg[3], pg[2]]
+        return (g_rn, None, None) + tuple(flat)
+
+
+def tcn_stack_supported(blocks, x, training):
+    """Fused residual-block path: CUDA, bf16 precision, training mode, Q / DQ conv1d without bias, BatchNorm on,
+    stride 1 and 'same' padding, time extent a multiple of 8."""
+    if not ENABLED or not (training and x.is_cuda and x.dtype == torch.float32 and x.dim() == 3):
+        return False
+    if F.get_precision() != "bf16" or not torch.is_grad_enabled() or x.shape[2] % 8:
+        return False
+    for b in blocks:
+        if not hasattr(b, "batch_filter1"):
+            return False
+        convs = (b.conv1_filter, b.conv1_gate, b.conv2_skip, b.conv2_residual)
+        alg = getattr(convs[0], "_algebra", None)
+        for c in convs:
+            if getattr(c, "_algebra", None) is None or c._algebra != alg or c.bias is not None or c.rotation or c.groups != 1:
+                return False
+            if F._pair(c.stride) != (1, 1):
+                return False
+            if c.in_channels < 8:                      # narrow layers take the dense path, which reads fp32 x
+                return False
+        k = b.conv1_filter.kernel_size
+        k = int(k[-1] if isinstance(k, (tuple, list)) else k)
+        dil = F._pair(b.conv1_filter.dilatation)[1]
+        if not isinstance(b.conv1_filter.padding, int) or 2 * b.conv1_filter.padding != dil * (k - 1):
+            return False
+        if (F._pair(b.conv1_gate.dilatation)[1] != dil or b.conv1_gate.padding != b.conv1_filter.padding
+                or b.conv1_gate.kernel_size != b.conv1_filter.kernel_size):
+            return False
+        for c in (b.conv2_skip, b.conv2_residual):
+            kk = c.kernel_size
+            if int(kk[-1] if isinstance(kk, (tuple, list)) else kk) != 1 or c.padding != 0:
+                return False
+        if b.conv1_filter.out_channels != b.conv1_gate.out_channels:
+            return False
+        if b.conv2_skip.out_channels > max(b.conv2_residual.out_channels, 1) * 64:
+            return False
+        for bn in (b.batch_filter1, b.batch_filter2, b.batch_gate2):
+            if bn.momentum is None or not bn.track_running_stats or not bn.affine:
+                return False
+        if b.batch_filter2.eps != b.batch_gate2.eps or b.batch_filter2.momentum != b.batch_gate2.momentum:
+            return False
+    return True
+
+
+def tcn_stack(x, blocks, seed):
+    """x (N, L, T) fp32 -> sum of the blocks' skip outputs (N, U, T) fp32 (TC_Block.forward, model.py:210-216)."""
+    spec, tensors = [], []
+    for k, b in enumerate(blocks):
+        ws = [c._weights() for c in (b.conv1_filter, b.conv1_gate, b.conv2_skip, b.conv2_residual)]
+        kk = b.conv1_filter.kernel_size
+        bns = (b.batch_filter1, b.batch_filter2, b.batch_gate2)
+        spec.append(dict(algebra=b.conv1_filter._algebra, nw=len(ws[0]),
+                         k=int(kk[-1] if isinstance(kk, (tuple, list)) else kk),
+                         dil=F._pair(b.conv1_filter.dilatation)[1], pad=int(b.conv1_filter.padding),
+                         drop_p=float(b.spatial_dropout_rate), salt=101 + k, has_res=k < len(blocks) - 1,
+                         bn1=(float(bns[0].eps), float(bns[0].momentum), bns[0].running_mean, bns[0].running_var),
+                         bnf=(float(bns[1].eps), float(bns[1].momentum), bns[1].running_mean, bns[1].running_var),
+                         bng=(float(bns[2].eps), float(bns[2].momentum), bns[2].running_mean, bns[2].running_var)))
+        for w in ws:
+            tensors += list(w)
+        for bn in bns:
+            tensors += [bn.weight, bn.bias]
+            bn.num_batches_tracked.add_(1)
+    return _TcnStack.apply(x, spec, seed, *tensors)

@@ -17,14 +17,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as tF
 
+from . import functional as _F
 from . import fused as _fused
 from . import layers as _default_layers
 
-# The reference runs its real-valued nn.Conv* / nn.Linear layers (MultiHeadAttention projections,
-# the 'R' domain) in true fp32: it disables cuDNN altogether (model.py:10), so ATen's native kernels
-# are used and no TF32 is involved.  cuDNN stays enabled here (it is far faster), but its TF32 mode --
-# on by default in PyTorch -- is switched off so that those layers keep the reference's arithmetic.
-torch.backends.cudnn.allow_tf32 = False
+# The reference runs its real-valued nn.Conv* / nn.Linear layers (MultiHeadAttention projections, the 'R' domain)
+# in true fp32: it disables cuDNN altogether (model.py:10), so ATen's native kernels are used and no TF32 is
+# involved.  cuDNN stays enabled here (it is far faster); TF32 follows the precision mode (functional.py): off in
+# 'fp32' mode so that those layers keep the reference's arithmetic, on in the tensor-core 'bf16' mode.
+_F._apply_tf32_policy()
 
 _BN_TCN = {'BN', 'BN_on_TCN', 'BNonTCN'}
 _BN_CNN = {'BN', 'BN_on_CNN', 'BNonCNN'}
@@ -168,12 +169,18 @@ class TC_Block(nn.Module):
         self.tanh = nn.Tanh()
         if self.pool_time == 'TCN':
             self.maxpool3 = nn.MaxPool1d(pool_size[2][1])
+        # step counter that seeds the channel-dropout masks of the fused residual-block path (not in the state_dict)
+        self.register_buffer("_drop_seed", torch.zeros(1, dtype=torch.int64), persistent=False)
 
     def forward(self, residual):
-        sum_skip = None
-        for block in self.ResBlocks:
-            residual, skip = block(residual)
-            sum_skip = skip if sum_skip is None else sum_skip + skip
+        if _fused.tcn_stack_supported(self.ResBlocks, residual, self.training):
+            self._drop_seed.add_(1)
+            sum_skip = _fused.tcn_stack(residual, self.ResBlocks, self._drop_seed)
+        else:
+            sum_skip = None
+            for block in self.ResBlocks:
+                residual, skip = block(residual)
+                sum_skip = skip if sum_skip is None else sum_skip + skip
         out = self.relu1(sum_skip)
         if self.pool_time == 'TCN':
             out = self.maxpool1(out)

@@ -24,7 +24,7 @@ static void run_conv(const simt::ConvParams& p) {
           for (int r0 = 0; r0 < g.R; r0 += simt::BK) {
             if (simt::conv_chunk_is_zero(g, by * simt::BM, r0)) continue;
             for (int t = 0; t < simt::NT; ++t) simt::conv_load(p, sh, t, bx, by, bz, tap, r0);
-            for (int t = 0; t < simt::NT; ++t) simt::conv_mac(sh, th[t], t);
+            for (int t = 0; t < simt::NT; ++t) simt::conv_mac(sh, th[t], t, simt::conv_swap(g));
           }
         for (int t = 0; t < simt::NT; ++t) simt::conv_store(p, th[t], t, bx, by, bz);
       }
@@ -106,23 +106,20 @@ int emul_stft(const float* x, int n_batch, int n_ch, long long n_samples, int np
   stft::Params p{};
   p.x = x; p.out = out; p.n_samples = n_samples; p.n_ch = n_ch; p.hop = nperseg - noverlap;
   p.n_frames = n_frames; p.bin0 = cut_dc ? 1 : 0; p.n_bins = n_bins; p.output_phase = output_phase;
-  std::vector<float> samples(stft::span(p.hop));
+  p.groups = (n_frames + stft::FRB - 1) / stft::FRB;
+  p.total = (long long)n_batch * n_ch * p.groups;
   stft::Shared* sh = new stft::Shared;
-  sh->samples = samples.data();
-  const int gx = (n_frames + stft::FR - 1) / stft::FR, gy = n_batch * n_ch;
-  for (int by = 0; by < gy; ++by)
-    for (int bx = 0; bx < gx; ++bx) {
-      for (int t = 0; t < stft::NT; ++t) stft::load(p, *sh, t, bx, by);
-      for (int round = 0; round < stft::FR / stft::FPR; ++round) {
-        for (int t = 0; t < stft::NT; ++t) stft::pack(p, *sh, t, round);
-        int src = 0;
-        for (int Ns = 1; Ns < stft::NC; Ns *= 4) {
-          for (int t = 0; t < stft::NT; ++t) stft::fft_pass(*sh, t, Ns, src);
-          src ^= 1;
-        }
-        for (int t = 0; t < stft::NT; ++t) stft::emit(p, *sh, t, bx, by, round);
-      }
-    }
+  std::vector<stft::Thread> th(stft::NT);
+  for (int t = 0; t < stft::NT; ++t) stft::init_tables(*sh, t);
+  for (long long batch = 0; batch < p.total; ++batch) {
+    int signal, t0;
+    stft::batch_decode(p, batch, &signal, &t0);
+    for (int t = 0; t < stft::NT; ++t) stft::phase_a(p, *sh, th[t], t, signal, t0);
+    for (int t = 0; t < stft::NT; ++t) stft::phase_b(*sh, th[t], t);
+    for (int t = 0; t < stft::NT; ++t) stft::phase_b2(*sh, th[t], t);
+    for (int t = 0; t < stft::NT; ++t) stft::phase_c(p, *sh, th[t], t);
+    for (int t = 0; t < stft::NT; ++t) stft::phase_d(p, *sh, t, signal, t0);
+  }
   delete sh;
   return 0;
 }

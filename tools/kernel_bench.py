@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--prec", nargs="+", default=["bf16", "fp32"])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kbench.json"))
     ap.add_argument("--skip-stft", action="store_true")
+    ap.add_argument("--skip-conv", action="store_true")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     res = {}
@@ -128,7 +129,7 @@ def main():
         except Exception as e:
             res["stft_error"] = repr(e)
             traceback.print_exc()
-    for B in args.batch:
+    for B in ([] if args.skip_conv else args.batch):
         bench_conv(B, args.prec, res)
         json.dump(res, open(args.out, "w"), indent=1)
     json.dump(res, open(args.out, "w"), indent=1)
