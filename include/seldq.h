@@ -53,7 +53,10 @@ typedef enum {
 typedef enum {
   SELDQ_ALG_REAL = 0,      /* nc = 1, plain convolution / linear                              */
   SELDQ_ALG_Q = 1,         /* nc = 4, Wq[a*O+o, b*I+i] = sign[a][b] * W_{a^b}[o,i]            */
-  SELDQ_ALG_DQ = 2         /* nc = 8, [[Q(w),0],[Q(w2),Q(w)]]; linear uses the transposed form */
+  SELDQ_ALG_DQ = 2,        /* nc = 8, [[Q(w),0],[Q(w2),Q(w)]]; linear uses the transposed form */
+  SELDQ_ALG_DQ_LINEAR = 3  /* nc = 8, the block table of dual_quaternion_linear (dual_quaternion_ops.py:170-188)
+                              used as a convolution table: lets a DQ linear layer run as a 1x1 convolution over
+                              the transposed matrices on the tensor-core path (functional.block_linear)          */
 } seldq_algebra_t;
 
 /* arithmetic the contraction runs in */
@@ -117,6 +120,15 @@ size_t seldq_conv_packed_bytes(const seldq_conv_desc_t* d, int32_t pass);
 int seldq_conv_pack_weights(const seldq_conv_desc_t* d, int32_t pass, const float* const* host_w, void* packed,
                             void* stream);
 
+/* The same for many layers in ONE launch (a training step re-packs every layer after the optimiser update):
+ * seldq_conv_pack_table_fill writes one entry (seldq_conv_pack_table_entry_bytes() bytes, host memory) per
+ * (layer, pass) and reports its work items; the caller keeps a device copy of the table while the weight and
+ * packed buffers stay in place and replays it with seldq_conv_pack_table_run(dev_table, entries, max items). */
+size_t seldq_conv_pack_table_entry_bytes(void);
+int seldq_conv_pack_table_fill(const seldq_conv_desc_t* d, int32_t pass, const float* const* host_w, void* packed,
+                               void* host_entry, int32_t* items);
+int seldq_conv_pack_table_run(const void* dev_table, int32_t count, int32_t max_items, void* stream);
+
 /* y = conv(x, expand(w)) + bias.   x may be NULL when x_cl is given (BF16 path). */
 int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
                    const float* const* host_w, const void* packed_w, const float* bias, float* y,
@@ -147,7 +159,9 @@ int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_c
  *                       running_mean / running_var (may be NULL) get nn.BatchNorm's momentum update
  *   seldq_cnn_tail_fwd  z = dropout(max_{pool rows}(relu(BN(y)))) written as the channels-last bf16 operand of
  *                       the consuming convolution (z_cl, may be NULL) and / or as fp32 NCHW (z_f32, may be NULL);
- *                       idx gets one byte per pooled element (arg-max row | 0x80 if kept) for the backward pass.
+ *                       idx gets one byte per pooled element (arg-max row | 0x80 if kept) for the backward pass;
+ *                       ymax_bf16 (pooled shape, may be NULL) gets the conv output at the arg-max, which lets the
+ *                       backward reductions stream it instead of gathering from y.
  *                       seed: device counter the caller advances every step (needed iff drop_p > 0)
  *   seldq_cnn_tail_bwd  d(conv out) from gz (fp32, pooled NCHW): written as the pitched NCHW bf16 operand
  *                       (d_t16) and / or the channels-last operand (d_cl) of the producing convolution's
@@ -163,10 +177,11 @@ int seldq_bn_stats(const void* src, int32_t is_bf16, int32_t n, int32_t c, int64
 int seldq_bn_finalize(const double* sums, const float* gamma, const float* beta, int32_t c, double count, float eps,
                       float momentum, float* running_mean, float* running_var, float* coef, void* stream);
 int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* consumer, const void* y_bf16,
-                       const float* coef, const int64_t* seed, void* z_cl, float* z_f32, uint8_t* idx, void* stream);
-int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* producer, const void* y_bf16,
-                       const float* coef, const uint8_t* idx, const float* gz, double* dsums, void* d_t16, void* d_cl,
+                       const float* coef, const int64_t* seed, void* z_cl, float* z_f32, uint8_t* idx, void* ymax_bf16,
                        void* stream);
+int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* producer, const void* y_bf16,
+                       const float* coef, const uint8_t* idx, const void* ymax_bf16, const float* gz, double* dsums,
+                       void* d_t16, void* d_cl, void* stream);
 
 /* TCN residual block, model.py:109-132:
  *     x = tanh(BN1(r));  y = dropout1d(tanh(BN_f(conv_f x)) * sigmoid(BN_g(conv_g x)));

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libseldq.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
-ALG_REAL, ALG_Q, ALG_DQ = 0, 1, 2
+ALG_REAL, ALG_Q, ALG_DQ, ALG_DQ_LINEAR = 0, 1, 2, 3
 PREC_FP32, PREC_BF16 = 0, 1
 PASS_FWD, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
 ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = -1, -2, -3, -4
@@ -78,6 +78,10 @@ _PROTOS = {
     "seldq_stage_operand": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32, _P, _P, _P, _P]),
     "seldq_conv_packed_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc), ctypes.c_int32]),
     "seldq_conv_pack_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32, ctypes.POINTER(_P), _P, _P]),
+    "seldq_conv_pack_table_entry_bytes": (ctypes.c_size_t, []),
+    "seldq_conv_pack_table_fill": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32, ctypes.POINTER(_P), _P, _P,
+                                                  ctypes.POINTER(ctypes.c_int32)]),
+    "seldq_conv_pack_table_run": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P]),
     "seldq_conv_fwd": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P, _P,
                                       ctypes.c_size_t, _P]),
     "seldq_conv_fwd_bf16": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P, _P,
@@ -86,9 +90,9 @@ _PROTOS = {
     "seldq_bn_finalize": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_double, ctypes.c_float, ctypes.c_float,
                                          _P, _P, _P, _P]),
     "seldq_cnn_tail_fwd": (ctypes.c_int, [ctypes.POINTER(CnnTailDesc), ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P,
-                                          _P, _P]),
-    "seldq_cnn_tail_bwd": (ctypes.c_int, [ctypes.POINTER(CnnTailDesc), ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P,
                                           _P, _P, _P]),
+    "seldq_cnn_tail_bwd": (ctypes.c_int, [ctypes.POINTER(CnnTailDesc), ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P,
+                                          _P, _P, _P, _P]),
     "seldq_tcn_glue": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(TcnGlue), ctypes.POINTER(ConvDesc), ctypes.c_int32,
                                       _P]),
     "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P,

@@ -58,6 +58,7 @@ inline bool make_block_table(int algebra, bool dq_linear, BlockTable* t) {
       for (int b = 0; b < 4; ++b) { t->widx[a][b] = (int8_t)(a ^ b); t->sign[a][b] = S[a][b]; }
     return true;
   }
+  if (algebra == SELDQ_ALG_DQ_LINEAR) { algebra = SELDQ_ALG_DQ; dq_linear = true; }
   if (algebra == SELDQ_ALG_DQ) {
     t->nc = 8; t->nw = 8;
     for (int a = 0; a < 8; ++a)

@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint2 op_tbl_s[kOpTableEntries];
+  __shared__ __align__(16) uint8_t out_stage[4][16 * 64];   // per epilogue warp: [16 ch][32 w] bf16
   // warp index through a shuffle: provably warp-uniform, so role branches and the MMA loop compile to the
   // uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -196,6 +197,9 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     // ===== epilogue: TMEM -> registers -> global ===================================================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
+    // 16-byte bf16 stores need 8-element alignment of every row start
+    const bool vec16 = p.out16 != nullptr && (p.OW & 7) == 0 && (p.out_sC & 7) == 0 && (p.out_sH & 7) == 0 &&
+                       (p.out_sN & 7) == 0 && (reinterpret_cast<unsigned long long>(p.out16) & 15ull) == 0;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
       const int group = p.group_order[u / p.total_tiles];
@@ -219,8 +223,28 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
           uint32_t v[16];
           ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
           ptx::tmem_ld_wait();
-          if (w_ok && p.out16) {
-            // bf16 output in the tensor's own NCHW order (fused CNN-block path, epilogue.cu)
+          if (p.out16 && vec16) {
+            // bf16 output in the tensor's own NCHW order (fused CNN-block path, epilogue.cu): the warp's
+            // [32 w x 16 ch] block is transposed through shared memory and leaves as 16-byte pieces
+            const int lim = p.Pc - c0;
+            uint8_t* stg = out_stage[q];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              *reinterpret_cast<__nv_bfloat16*>(stg + j * 64 + lane * 2) =
+                  __float2bfloat16_rn(__uint_as_float(v[j]) + ((p.bias && j < lim) ? __ldg(p.bias + ch_base + c0 + j) : 0.f));
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const int ch = r * 8 + (lane >> 2), piece = lane & 3;
+              const int wp = wt * kTileM + q * 32 + piece * 8;
+              if (ch < lim && wp < p.OW) {
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + ch * 64 + piece * 16);
+                *reinterpret_cast<uint4*>(p.out16 + (long long)n * p.out_sN + (long long)h * p.out_sH +
+                                          (long long)(ch_base + c0 + ch) * p.out_sC + wp) = val;
+              }
+            }
+            __syncwarp();
+          } else if (w_ok && p.out16) {
             __nv_bfloat16* dst = out16_row + (long long)(ch_base + c0) * p.out_sC;
             const int lim = p.Pc - c0;
 #pragma unroll
@@ -267,6 +291,34 @@ struct PackParams {
   int wsO, wsI, wsT;
 };
 __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackParams p) {
+  const int items = p.n_img * p.ntaps * p.J * 2 * p.NBp;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    int r = it;
+    const int n = r % p.NBp; r /= p.NBp;
+    const int kc = r & 1; r >>= 1;
+    const int j = r % p.J; r /= p.J;
+    const int tap = r % p.ntaps;
+    const int img = r / p.ntaps;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int k = j * 16 + kc * 8 + jj;
+      float x = 0.f;
+      if (n < p.rows_real && k < p.k_real) {
+        const int o = p.transposed ? k : n, i = p.transposed ? n : k;
+        x = __ldg(p.w[img] + (long long)o * p.wsO + (long long)i * p.wsI + (long long)tap * p.wsT);
+      }
+      v[jj] = __float2bfloat16_rn(x);
+    }
+    uint8_t* dst = p.dst + ((size_t)(img * p.ntaps + tap) * p.J + j) * ((size_t)p.NBp * 32) +
+                   (size_t)kc * (p.NBp * 16) + (n >> 3) * 128 + (n & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// the same for many layers in one launch: blockIdx.y selects an entry of a device-resident parameter table
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackParams* __restrict__ table) {
+  const PackParams p = table[blockIdx.y];
   const int items = p.n_img * p.ntaps * p.J * 2 * p.NBp;
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
     int r = it;
@@ -359,6 +411,35 @@ int launch_pack_weights(const ConvGeom& g, const float* const* host_w, void* pac
   if (blocks > 4 * cl::num_sms()) blocks = 4 * cl::num_sms();
   cl::pack_weights_kernel<<<blocks, 256, 0, st>>>(p);
   return check_launch("pack_weights_kernel");
+}
+
+size_t pack_table_entry_bytes() { return sizeof(cl::PackParams); }
+
+// fills one host-side table entry; returns the number of 8-element items of that entry (0 for dense layers)
+int fill_pack_table_entry(const ConvGeom& g, const float* const* host_w, void* packed, void* entry, int* items) {
+  const WeightPlan w = weight_plan(g);
+  cl::PackParams p{};
+  *items = 0;
+  if (!w.dense) {
+    if (reinterpret_cast<uintptr_t>(packed) & 15) return fail(SELDQ_ERR_INVALID, "packed weight buffer must be 16-byte aligned");
+    for (int i = 0; i < w.n_img; ++i) p.w[i] = host_w[i];
+    p.dst = reinterpret_cast<uint8_t*>(packed);
+    p.n_img = w.n_img; p.ntaps = w.ntaps; p.J = w.J; p.NBp = w.NBp;
+    p.rows_real = w.rows_real; p.k_real = w.k_real; p.transposed = g.transposed;
+    p.wsO = g.wsO; p.wsI = g.wsI; p.wsT = g.wsT;
+    *items = w.n_img * w.ntaps * w.J * 2 * w.NBp;
+  }
+  memcpy(entry, &p, sizeof(p));
+  return SELDQ_OK;
+}
+
+int launch_pack_weights_multi(const void* dev_table, int count, int max_items, cudaStream_t st) {
+  if (count <= 0 || max_items <= 0) return SELDQ_OK;
+  int bx = (max_items + 255) / 256;
+  if (bx > 16) bx = 16;
+  dim3 grid((unsigned)bx, (unsigned)count);
+  cl::pack_weights_multi_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const cl::PackParams*>(dev_table));
+  return check_launch("pack_weights_multi_kernel");
 }
 
 int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
@@ -483,7 +564,7 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
   while (cols < acc_cols * p->acc_stages) cols <<= 1;
   p->tmem_cols = cols;
   const size_t fixed = 1024 /* barriers */ + w.total + 4096 /* slack behind the tiles */;
-  const size_t budget = 222 * 1024;   // + 4 KB static (op table) + barriers stays under the 227 KB limit
+  const size_t budget = 218 * 1024;   // + 8 KB static (op table, output staging) stays under the 227 KB limit
   if (fixed + 2 * (size_t)p->stage_bytes > budget)
     return fail(SELDQ_ERR_UNSUPPORTED, "compact weights (%zu B as bf16 tiles) do not fit in shared memory", w.total);
   size_t ns = (budget - fixed) / p->stage_bytes;

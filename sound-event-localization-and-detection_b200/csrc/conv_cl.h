@@ -125,6 +125,9 @@ cl::OperandLayout gy_operand_layout(const ConvGeom& fwd);
 
 size_t packed_weight_bytes(const ConvGeom& pass_geom);
 int launch_pack_weights(const ConvGeom& pass_geom, const float* const* host_w, void* packed, cudaStream_t st);
+size_t pack_table_entry_bytes();
+int fill_pack_table_entry(const ConvGeom& pass_geom, const float* const* host_w, void* packed, void* entry, int* items);
+int launch_pack_weights_multi(const void* dev_table, int count, int max_items, cudaStream_t st);
 int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
                     const float* bias, float* out, void* out_bf16, cudaStream_t st);
 int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, float* const* host_gw,

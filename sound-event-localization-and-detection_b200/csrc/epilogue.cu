@@ -117,11 +117,14 @@ __global__ void __launch_bounds__(256) cnn_tail_fwd_kernel(const __grid_constant
         const __nv_bfloat16* src = p.y + (((long long)n * p.C + c) * p.H + (long long)hp * p.pool) * p.W + w;
         float best = -INFINITY;
         int arg = 0;
+        __nv_bfloat16 yb = src[0];
         for (int j = 0; j < p.pool; ++j) {
-          const float v = cf.x * __bfloat162float(src[(long long)j * p.W]) + cf.y;
-          if (v > best || v != v) { best = v; arg = j; }
+          const __nv_bfloat16 yj = src[(long long)j * p.W];
+          const float v = cf.x * __bfloat162float(yj) + cf.y;
+          if (v > best || v != v) { best = v; arg = j; yb = yj; }
         }
         const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
+        if (p.ymax) p.ymax[e] = yb;
         bool keep = best > 0.f;
         if (keep && thresh) keep = dropout_keep(seed, p.salt, e, thresh);
         z = keep ? best * scale : 0.f;
@@ -165,9 +168,48 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_reduce_kernel(const __grid_c
     if (id & 0x80) {
       const int hp = (int)(i / p.W), w = (int)(i - (long long)hp * p.W);
       const float g = __ldg(p.gz + base + i) * scale;
-      const float yv = __bfloat162float(y[((long long)hp * p.pool + (id & 7)) * p.W + w]);
+      const float yv = __bfloat162float(p.ymax ? p.ymax[base + i] : y[((long long)hp * p.pool + (id & 7)) * p.W + w]);
       s1 += g;
       s2 += g * (yv - cf.z) * cf.w;
+    }
+  }
+  block_sum2(s1, s2);
+  if (threadIdx.x == 0) {
+    atomicAdd(dsums + 2 * c, (double)s1);
+    atomicAdd(dsums + 2 * c + 1, (double)s2);
+  }
+}
+
+// same reduction from the arg-max values the forward pass kept (ymax): 8 pooled elements per thread, every
+// stream (1-byte flags, fp32 gradient, bf16 values) read contiguously
+__global__ void __launch_bounds__(256) cnn_tail_bwd_reduce_vec_kernel(const __grid_constant__ TailParams p,
+                                                                     long long chunk, double* __restrict__ dsums) {
+  const int c = blockIdx.x, n = blockIdx.y;
+  const int HP = p.H / p.pool;
+  const long long plane = (long long)HP * p.W;
+  const long long lo = (long long)blockIdx.z * chunk;
+  const long long hi = lo + chunk < plane ? lo + chunk : plane;
+  const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
+  const float scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+  const long long base = ((long long)n * p.C + c) * plane;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = lo + (long long)threadIdx.x * 8; i < hi; i += 256 * 8) {
+    const uint2 idv = __ldg(reinterpret_cast<const uint2*>(p.idx + base + i));
+    if (((idv.x | idv.y) & 0x80808080u) == 0u) continue;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gz + base + i));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gz + base + i + 4));
+    const uint4 yv = __ldg(reinterpret_cast<const uint4*>(p.ymax + base + i));
+    const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&yv);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t b = ((j < 4 ? idv.x : idv.y) >> (8 * (j & 3))) & 0xffu;
+      if (b & 0x80u) {
+        const float2 f = __bfloat1622float2(y2[j >> 1]);
+        const float g = gg[j] * scale;
+        s1 += g;
+        s2 += g * (((j & 1) ? f.y : f.x) - cf.z) * cf.w;
+      }
     }
   }
   block_sum2(s1, s2);
@@ -272,10 +314,10 @@ __global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_cons
         const int c = comp * p.cc + ci;
         const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
         const __nv_bfloat16* src = p.y + (((long long)n * p.C + c) * p.H + (long long)hp * p.pool) * p.W + w;
-        float best[8];
+        float best[8], ybest[8];
         int arg[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; ybest[j] = 0.f; }
         for (int q = 0; q < p.pool; ++q) {
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * p.W));
           const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -283,11 +325,20 @@ __global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_cons
           for (int j = 0; j < 4; ++j) {
             const float2 f = __bfloat1622float2(h2[j]);
             const float v0 = cf.x * f.x + cf.y, v1 = cf.x * f.y + cf.y;
-            if (v0 > best[2 * j] || v0 != v0) { best[2 * j] = v0; arg[2 * j] = q; }
-            if (v1 > best[2 * j + 1] || v1 != v1) { best[2 * j + 1] = v1; arg[2 * j + 1] = q; }
+            if (v0 > best[2 * j] || v0 != v0) { best[2 * j] = v0; arg[2 * j] = q; ybest[2 * j] = f.x; }
+            if (v1 > best[2 * j + 1] || v1 != v1) { best[2 * j + 1] = v1; arg[2 * j + 1] = q; ybest[2 * j + 1] = f.y; }
           }
         }
         const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
+        if (p.ymax) {
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(ybest[2 * j], ybest[2 * j + 1]);   // exact: bf16 values
+            o[j] = *reinterpret_cast<const uint32_t*>(&b2);
+          }
+          *reinterpret_cast<uint4*>(p.ymax + e) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
         uint32_t id[2] = {0u, 0u};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -447,11 +498,15 @@ int launch_cnn_tail_bwd(epi::TailParams& p, double* dsums, cudaStream_t st) {
   long long splits = (plane + 16383) / 16384;
   if (splits > 64) splits = 64;
   if (splits < 1) splits = 1;
-  const long long chunk = (plane + splits - 1) / splits;
+  long long chunk = (plane + splits - 1) / splits;
+  chunk = (chunk + 7) & ~7LL;
   splits = (plane + chunk - 1) / chunk;
   if (p.N > 65535) return fail(SELDQ_ERR_UNSUPPORTED, "cnn tail: batch too large for the grid");
   dim3 grid((unsigned)p.C, (unsigned)p.N, (unsigned)splits);
-  epi::cnn_tail_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p, chunk, dsums);
+  if (p.ymax && tail_vec_ok(p) && chunk % 8 == 0 && (reinterpret_cast<uintptr_t>(p.ymax) & 15) == 0)
+    epi::cnn_tail_bwd_reduce_vec_kernel<<<grid, 256, 0, st>>>(p, chunk, dsums);
+  else
+    epi::cnn_tail_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p, chunk, dsums);
   int rc = check_launch("cnn_tail_bwd_reduce_kernel");
   if (rc) return rc;
   const double count = (double)p.N * p.H * p.W;

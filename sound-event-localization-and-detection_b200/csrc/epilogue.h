@@ -18,6 +18,7 @@ struct TailParams {
   __nv_bfloat16* z_cl;          // [N][H/pool][W][Cp] or null
   float* z32;                   // [N][C][H/pool][W] or null
   uint8_t* idx;                 // [N][C][H/pool][W]: arg-max row | 0x80 keep flag (written fwd, read bwd)
+  __nv_bfloat16* ymax;          // [N][C][H/pool][W]: conv output at the arg-max (written fwd, read bwd) or null
   // backward
   const float* gz;              // gradient w.r.t. the pooled output, fp32 [N][C][H/pool][W]
   __nv_bfloat16* d_t16;         // d(conv out), bf16 [N][C][H][pitch] or null

@@ -114,6 +114,30 @@ extern "C" int seldq_stage_operand(const seldq_conv_desc_t* d, int32_t which, co
   return launch_stage_operand(src, dst_cl, dst_t16, o.lay, o.n, o.c, o.h, o.w, (cudaStream_t)stream);
 }
 
+// many layers in one launch: the caller builds a table on the host (one entry per (layer, pass)), keeps a copy of
+// it in device memory for as long as the weight / packed buffers stay where they are, and replays it every step
+extern "C" size_t seldq_conv_pack_table_entry_bytes(void) { return pack_table_entry_bytes(); }
+
+extern "C" int seldq_conv_pack_table_fill(const seldq_conv_desc_t* d, int32_t pass, const float* const* host_w,
+                                          void* packed, void* host_entry, int32_t* items) {
+  ConvGeom g;
+  if (pass != SELDQ_PASS_FWD && pass != SELDQ_PASS_DGRAD) return fail(SELDQ_ERR_INVALID, "weights are packed for FWD and DGRAD");
+  if (!host_w || !packed || !host_entry || !items) return fail(SELDQ_ERR_INVALID, "seldq_conv_pack_table_fill: null pointer");
+  int rc = make_conv_geom(d, pass, &g);
+  if (rc) return rc;
+  int n = 0;
+  if ((rc = fill_pack_table_entry(g, host_w, packed, host_entry, &n))) return rc;
+  *items = n;
+  return SELDQ_OK;
+}
+
+extern "C" int seldq_conv_pack_table_run(const void* dev_table, int32_t count, int32_t max_items, void* stream) {
+  if (!dev_table || count < 0) return fail(SELDQ_ERR_INVALID, "seldq_conv_pack_table_run: bad arguments");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  return launch_pack_weights_multi(dev_table, count, max_items, (cudaStream_t)stream);
+}
+
 extern "C" size_t seldq_conv_packed_bytes(const seldq_conv_desc_t* d, int32_t pass) {
   ConvGeom g;
   if ((pass != SELDQ_PASS_FWD && pass != SELDQ_PASS_DGRAD) || make_conv_geom(d, pass, &g)) return 0;
@@ -345,7 +369,7 @@ static int tail_params(const seldq_cnn_tail_desc_t* t, const cl::OperandLayout* 
 
 extern "C" int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* consumer, const void* y_bf16,
                                   const float* coef, const int64_t* seed, void* z_cl, float* z_f32, uint8_t* idx,
-                                  void* stream) {
+                                  void* ymax, void* stream) {
   epi::TailParams p;
   cl::OperandLayout lay;
   int rc;
@@ -363,13 +387,14 @@ extern "C" int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_co
   if ((rc = cuda_ready())) return rc;
   p.y = reinterpret_cast<const __nv_bfloat16*>(y_bf16); p.coef = coef;
   p.z_cl = reinterpret_cast<__nv_bfloat16*>(z_cl); p.z32 = z_f32; p.idx = idx;
+  p.ymax = reinterpret_cast<__nv_bfloat16*>(ymax);
   p.seed_ptr = reinterpret_cast<const long long*>(seed);
   return launch_cnn_tail_fwd(p, (cudaStream_t)stream);
 }
 
 extern "C" int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* producer, const void* y_bf16,
-                                  const float* coef, const uint8_t* idx, const float* gz, double* dsums, void* d_t16,
-                                  void* d_cl, void* stream) {
+                                  const float* coef, const uint8_t* idx, const void* ymax, const float* gz, double* dsums,
+                                  void* d_t16, void* d_cl, void* stream) {
   epi::TailParams p;
   cl::OperandLayout lay;
   int rc;
@@ -387,6 +412,7 @@ extern "C" int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_co
   if ((rc = cuda_ready())) return rc;
   p.y = reinterpret_cast<const __nv_bfloat16*>(y_bf16); p.coef = coef;
   p.idx = const_cast<uint8_t*>(idx); p.gz = gz;
+  p.ymax = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ymax));
   p.d_t16 = reinterpret_cast<__nv_bfloat16*>(d_t16); p.d_cl = reinterpret_cast<__nv_bfloat16*>(d_cl);
   return launch_cnn_tail_bwd(p, dsums, (cudaStream_t)stream);
 }

@@ -13,10 +13,10 @@ import os
 import torch
 
 from . import _lib
-from ._lib import ALG_DQ, ALG_Q, ALG_REAL, PASS_DGRAD, PASS_FWD, PASS_WGRAD, PREC_BF16, PREC_FP32
+from ._lib import ALG_DQ, ALG_DQ_LINEAR, ALG_Q, ALG_REAL, PASS_DGRAD, PASS_FWD, PASS_WGRAD, PREC_BF16, PREC_FP32
 
 _PRECISION = {"fp32": PREC_FP32, "bf16": PREC_BF16}[os.environ.get("SELDQ_PRECISION", "bf16").lower()]
-_NCOMP = {ALG_REAL: 1, ALG_Q: 4, ALG_DQ: 8}
+_NCOMP = {ALG_REAL: 1, ALG_Q: 4, ALG_DQ: 8, ALG_DQ_LINEAR: 8}
 
 
 def _apply_tf32_policy():
@@ -112,7 +112,7 @@ def profile_collect():
 def _conv_flop(desc, oh, ow):
     """Algorithmic FLOPs of one pass: only the non-zero blocks of the expanded weight count
     (DQ: 0.75 of dense)."""
-    nz = 0.75 if desc.algebra == ALG_DQ else 1.0
+    nz = 0.75 if desc.algebra in (ALG_DQ, ALG_DQ_LINEAR) else 1.0
     return 2.0 * nz * desc.cout * desc.cin * desc.k_h * desc.k_w * desc.batch * oh * ow
 
 
@@ -168,27 +168,83 @@ def stage_operand(t, desc, which, want_cl=True, want_t16=False):
 # (optimizer.step updates in place) and always while a CUDA graph is being captured, so that a replayed
 # step packs the weights it is about to use
 _PACKED = {}
+_PACK_EPOCH = 0
 
 
-def packed_weights(weights, desc, pass_):
+def invalidate_packed_weights():
+    """Forget every packed weight set.  For callers that update weights through storage the parameters' version
+    counters do not see (trainer.FlatGradBucket steps ONE flat tensor the parameters are views of)."""
+    global _PACK_EPOCH
+    _PACK_EPOCH += 1
+
+
+def packed_weights(weights, desc, pass_, cache=True):
+    """cache=False: weights that are temporaries (their address says nothing about their content) are packed into
+    a fresh buffer on every call."""
     import ctypes
     L = _lib.lib()
     nbytes = L.seldq_conv_packed_bytes(ctypes.byref(desc), pass_)
     if nbytes == 0:
         return None
+    if not cache:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=weights[0].device)
+        wp = _lib.ptr_array([w.data_ptr() for w in weights])
+        _timed("pack_weights_kernel", 0.0, 1, lambda: _lib.check(
+            L.seldq_conv_pack_weights(ctypes.byref(desc), pass_, wp, buf.data_ptr(), _stream())))
+        return buf
     key = (tuple(w.data_ptr() for w in weights), pass_, desc.algebra, desc.cin, desc.cout, desc.k_h, desc.k_w)
     versions = tuple(w._version for w in weights)
     ent = _PACKED.get(key)
     capturing = torch.cuda.is_current_stream_capturing()
-    if ent is not None and ent[0] == versions and not capturing and ent[1].numel() == nbytes:
-        return ent[1]
+    if ent is not None and ent[1].numel() == nbytes and ent[0] == versions and ent[3] == _PACK_EPOCH:
+        # valid as long as the version counters stand still; while a graph is being captured only sets that
+        # repack_all() refreshes (epoch > 0) may be reused, because the replayed step must see current weights
+        if not capturing or ent[3] > 0:
+            return ent[1]
     buf = ent[1] if ent is not None and ent[1].numel() == nbytes else torch.empty(
         nbytes, dtype=torch.uint8, device=weights[0].device)
     wp = _lib.ptr_array([w.data_ptr() for w in weights])
     _timed("pack_weights_kernel", 0.0, 1, lambda: _lib.check(
         L.seldq_conv_pack_weights(ctypes.byref(desc), pass_, wp, buf.data_ptr(), _stream())))
-    _PACKED[key] = (versions, buf)
+    if ent is None or ent[1] is not buf:
+        global _PACK_TABLE
+        _PACK_TABLE = None                              # a new buffer: the multi-pack table must be rebuilt
+    _PACKED[key] = (versions, buf, (tuple(weights), _lib.ConvDesc.from_buffer_copy(desc), pass_), _PACK_EPOCH)
     return buf
+
+
+_PACK_TABLE = None
+
+
+def repack_all():
+    """Re-packs every weight set packed so far in ONE launch (seldq_conv_pack_table_run) and marks them fresh: the
+    call a trainer makes right after its optimiser step, so that the next step's layers find their bf16 tiles
+    ready (and a captured step holds one pack launch instead of one per layer and pass)."""
+    import ctypes
+    global _PACK_TABLE, _PACK_EPOCH
+    if not _PACKED:
+        return
+    L = _lib.lib()
+    if _PACK_TABLE is None:
+        esz = L.seldq_conv_pack_table_entry_bytes()
+        keys = list(_PACKED)
+        host = torch.zeros(len(keys) * esz, dtype=torch.uint8)
+        max_items = 0
+        for i, k in enumerate(keys):
+            _, buf, (ws, desc, pass_), _ = _PACKED[k]
+            wp = _lib.ptr_array([w.data_ptr() for w in ws])
+            items = ctypes.c_int32()
+            _lib.check(L.seldq_conv_pack_table_fill(ctypes.byref(desc), pass_, wp, buf.data_ptr(),
+                                                    host.data_ptr() + i * esz, ctypes.byref(items)))
+            max_items = max(max_items, items.value)
+        dev = next(iter(_PACKED.values()))[1].device
+        _PACK_TABLE = (host.to(dev), len(keys), max_items)
+    table, count, max_items = _PACK_TABLE
+    _timed("pack_weights_kernel", 0.0, 1, lambda: _lib.check(
+        L.seldq_conv_pack_table_run(table.data_ptr(), count, max_items, _stream())))
+    _PACK_EPOCH += 1
+    for k, (ver, buf, info, _) in list(_PACKED.items()):
+        _PACKED[k] = (tuple(w._version for w in info[0]), buf, info, _PACK_EPOCH)
 
 
 def _conv_desc(algebra, prec, x_shape, cout, ksize, stride, padding, dilation):
@@ -199,6 +255,9 @@ def _conv_desc(algebra, prec, x_shape, cout, ksize, stride, padding, dilation):
     n, c, h, w = x_shape
     return _lib.ConvDesc(algebra, prec, 2, n, c, cout, h, w, ksize[0], ksize[1], stride[0], stride[1],
                          padding[0], padding[1], dilation[0], dilation[1])
+
+
+_PACK_CACHE = True      # False while _linear_as_conv builds its node: its weights are per-call temporaries
 
 
 class _BlockConv(torch.autograd.Function):
@@ -239,12 +298,13 @@ class _BlockConv(torch.autograd.Function):
             x_cl = pk = None
             if bf16:
                 x_cl, _ = stage_operand(x, desc, 0)
-                pk = packed_weights(weights, desc, PASS_FWD)
+                pk = packed_weights(weights, desc, PASS_FWD, cache=_PACK_CACHE)
             kern = "qconv_cl_fprop_kernel" if bf16 else "conv_simt_kernel"
             _timed(kern, _conv_flop(desc, oh.value, ow.value), 1, lambda: _lib.check(
                 L.seldq_conv_fwd(ctypes.byref(desc), x.data_ptr(), _ptr(x_cl), wp, _ptr(pk), _ptr(bias),
                                  y.data_ptr(), None, 0, _stream())))
         ctx.desc = desc
+        ctx.pack_cache = _PACK_CACHE
         ctx.out_hw = (oh.value, ow.value)
         ctx.has_bias = bias is not None
         # the tensor-core wgrad reads the channels-last bf16 operand only: keep that instead of the fp32
@@ -281,7 +341,7 @@ class _BlockConv(torch.autograd.Function):
                     gx = torch.empty((desc.batch, desc.cin, desc.in_w), dtype=torch.float32, device=dev)
                 else:
                     gx = torch.empty((desc.batch, desc.cin, desc.in_h, desc.in_w), dtype=torch.float32, device=dev)
-                pk = packed_weights(weights, desc, PASS_DGRAD) if bf16 else None
+                pk = packed_weights(weights, desc, PASS_DGRAD, cache=ctx.pack_cache) if bf16 else None
                 kern = "qconv_cl_fprop_kernel" if bf16 else "conv_simt_kernel"
                 _timed(kern, _conv_flop(desc, *ctx.out_hw), 1, lambda: _lib.check(
                     L.seldq_conv_dgrad(ctypes.byref(desc), gy.data_ptr(), _ptr(gy_cl), wp, _ptr(pk), gx.data_ptr(),
@@ -394,8 +454,27 @@ def block_conv(x, weights, bias, stride, padding, dilation, algebra, prec=None):
     return _BlockConv.apply(x, bias, stride, padding, dilation, algebra, prec, *weights)
 
 
+def _linear_as_conv(x, weights, bias, algebra):
+    """(rows, in) @ expand(weights) on the tensor-core path: the matrices are transposed into (1, features, rows)
+    NCW tensors and the layer runs as a 1x1 convolution whose block table is the linear layer's
+    (SELDQ_ALG_DQ_LINEAR for dual_quaternion_linear; quaternion_linear shares the convolution's table)."""
+    conv_alg = ALG_DQ_LINEAR if algebra == ALG_DQ else algebra
+    global _PACK_CACHE
+    ws = tuple(w.t().contiguous().unsqueeze(-1) for w in weights)          # (in/nc, out/nc) -> (out/nc, in/nc, 1)
+    prev, _PACK_CACHE = _PACK_CACHE, False
+    try:
+        y = _BlockConv.apply(x.t().contiguous().unsqueeze(0), bias, 1, 0, 1, conv_alg, PREC_BF16, *ws)
+    finally:
+        _PACK_CACHE = prev
+    return y[0].t()
+
+
 def block_linear(x, weights, bias, algebra, prec=None):
     prec = _PRECISION if prec is None else prec
+    if prec == PREC_BF16 and x.is_cuda and weights[0].shape[0] >= 8 and weights[0].shape[1] >= 8:
+        lead = x.shape[:-1]
+        y = _linear_as_conv(x.reshape(-1, x.shape[-1]), weights, bias, algebra)
+        return y.reshape(lead + (y.shape[-1],))
     if x.dim() == 2:
         return _BlockLinear.apply(x, bias, algebra, prec, *weights)
     lead = x.shape[:-1]

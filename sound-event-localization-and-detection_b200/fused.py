@@ -92,6 +92,7 @@ class _CnnStack(torch.autograd.Function):
                 hp = oh // s["pool"]
                 td = _lib.CnnTailDesc(N, C, oh, ow, s["pool"], s["drop_p"], s["salt"])
                 idx = torch.empty((N, C, hp, ow), dtype=torch.uint8, device=dev)
+                ymax = torch.empty((N, C, hp, ow), dtype=torch.bfloat16, device=dev)
                 if last:
                     z32 = torch.empty((N, C, hp, ow), dtype=torch.float32, device=dev)
                     nxt_cl, consumer = None, None
@@ -101,10 +102,10 @@ class _CnnStack(torch.autograd.Function):
                 F._timed("cnn_tail_fwd_kernel", 0.0, 1, lambda: _lib.check(
                     L.seldq_cnn_tail_fwd(ctypes.byref(td), None if consumer is None else ctypes.byref(consumer),
                                          y16.data_ptr(), coef.data_ptr(), _ptr(seed) if s["drop_p"] > 0 else None,
-                                         _ptr(nxt_cl), _ptr(z32), idx.data_ptr(), _stream())))
+                                         _ptr(nxt_cl), _ptr(z32), idx.data_ptr(), ymax.data_ptr(), _stream())))
                 # block 0 of a narrow first layer keeps the fp32 input for its weight gradient (seldq.h)
                 keep_in = x if (k == 0 and x_dense) else cur_cl
-                saved += [keep_in, y16, coef, idx]
+                saved += [keep_in, y16, coef, idx, ymax]
                 metas.append((s, d, oh, ow, td))
                 cur_cl = nxt_cl
         ctx.metas = metas
@@ -125,7 +126,7 @@ class _CnnStack(torch.autograd.Function):
         with torch.cuda.device(dev):
             for k in reversed(range(ctx.nblocks)):
                 s, d, oh, ow, td = ctx.metas[k]
-                xin, y16, coef, idx = saved[4 * k:4 * k + 4]
+                xin, y16, coef, idx, ymax = saved[5 * k:5 * k + 5]
                 ws, gamma, beta = ctx.block_params[k]
                 N, C = d.batch, d.cout
                 need_gx = k > 0 or ctx.needs_input_grad[0]
@@ -135,7 +136,8 @@ class _CnnStack(torch.autograd.Function):
                 dsums = torch.zeros((C * 3,), dtype=torch.float64, device=dev)
                 F._timed("cnn_tail_bwd_kernels", 0.0, 3, lambda: _lib.check(
                     L.seldq_cnn_tail_bwd(ctypes.byref(td), ctypes.byref(d), y16.data_ptr(), coef.data_ptr(),
-                                         idx.data_ptr(), gz.data_ptr(), dsums.data_ptr(), d_t16.data_ptr(), _ptr(d_cl),
+                                         idx.data_ptr(), ymax.data_ptr(), gz.data_ptr(), dsums.data_ptr(),
+                                         d_t16.data_ptr(), _ptr(d_cl),
                                          _stream())))
                 dsf = dsums[:2 * C].view(C, 2).float()
                 g_gamma, g_beta = dsf[:, 1].contiguous(), dsf[:, 0].contiguous()

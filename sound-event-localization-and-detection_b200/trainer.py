@@ -26,18 +26,25 @@ def seld_loss(sed, doa, target, n_sed, sed_weight=1.0, doa_weight=5.0):
 
 
 class FlatGradBucket(object):
-    """One contiguous buffer (the parameters' dtype: fp32 in training) holding every parameter's gradient."""
+    """One contiguous buffer (the parameters' dtype: fp32 in training) holding every parameter's gradient, and a
+    second one holding the parameters themselves (every p.data / p.grad is a view), so that the all-reduce and the
+    optimiser each touch ONE tensor instead of a few hundred."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=self.params[0].dtype, device=dev)
+        self.flat_param = torch.nn.Parameter(torch.empty(total, dtype=self.params[0].dtype, device=dev))
         off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                self.flat_param.data[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat_param.data[off:off + n].view_as(p)
+                p.grad = self.flat[off:off + n].view_as(p)
+                off += n
+        self.flat_param.grad = self.flat
 
     def zero(self):
         self.flat.zero_()
@@ -55,13 +62,16 @@ class Trainer(object):
         self.group = group
         self.bucket = FlatGradBucket(model.parameters())
         on_cuda = self.bucket.flat.is_cuda
+        self._functional = None
         if on_cuda:
             # the weight-gradient kernels add straight into the bucket (functional.set_grad_accumulation)
             from . import functional
             functional.set_grad_accumulation(True)
+            self._functional = functional
         # Adam with the reference's hyper-parameters (train.py:502-504); fused = one kernel per step,
         # capturable so that the whole step can live in a CUDA graph
-        self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, fused=on_cuda, capturable=on_cuda)
+        # (element-wise update: one flat parameter is the same arithmetic as one tensor per parameter)
+        self.optimizer = torch.optim.Adam([self.bucket.flat_param], lr=lr, fused=on_cuda, capturable=on_cuda)
         self._graph = None
 
     def broadcast_parameters(self, src=0):
@@ -102,4 +112,8 @@ class Trainer(object):
         loss.backward()
         self.bucket.all_reduce_mean(self.group)
         self.optimizer.step()
+        if self._functional is not None:
+            # the flat update bypasses the parameters' version counters: refresh every packed bf16 weight set now,
+            # in one launch, for the next step
+            self._functional.repack_all()
         return loss
