@@ -183,6 +183,20 @@ int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* 
                        const float* coef, const uint8_t* idx, const void* ymax_bf16, const float* gz, double* dsums,
                        void* d_t16, void* d_cl, void* stream);
 
+/* First CNN block, backward.  The first convolution needs no input gradient, so d(conv out) has a single consumer,
+ * the layer's weight gradient: seldq_cnn_first_bwd runs the two BatchNorm reductions (as seldq_cnn_tail_bwd) and
+ * then ONE kernel that forms d(conv out) tile by tile in shared memory and feeds it to the tensor cores, so the
+ * largest gradient tensor of the model (472 MB per sample) is never written.  x is the float32 input of the
+ * convolution; host_gw / accumulate as in seldq_conv_wgrad; dsums as in seldq_cnn_tail_bwd.  Geometry: stride 1,
+ * input channels a multiple of 8 with taps * channels <= 128, at most 256 output channels, output width a multiple
+ * of 8 (seldq_cnn_first_bwd_supported returns 1). */
+int seldq_cnn_first_bwd_supported(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* conv);
+size_t seldq_cnn_first_bwd_workspace_bytes(const seldq_conv_desc_t* conv);
+int seldq_cnn_first_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* conv, const float* x,
+                        const void* y_bf16, const float* coef, const uint8_t* idx, const void* ymax_bf16,
+                        const float* gz, double* dsums, float* const* host_gw, int32_t accumulate, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* TCN residual block, model.py:109-132:
  *     x = tanh(BN1(r));  y = dropout1d(tanh(BN_f(conv_f x)) * sigmoid(BN_g(conv_g x)));
  *     r' = x + conv_res(y);  skips += conv_skip(y)

@@ -93,6 +93,10 @@ _PROTOS = {
                                           _P, _P, _P]),
     "seldq_cnn_tail_bwd": (ctypes.c_int, [ctypes.POINTER(CnnTailDesc), ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P,
                                           _P, _P, _P, _P]),
+    "seldq_cnn_first_bwd_supported": (ctypes.c_int, [ctypes.POINTER(CnnTailDesc), ctypes.POINTER(ConvDesc)]),
+    "seldq_cnn_first_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc)]),
+    "seldq_cnn_first_bwd": (ctypes.c_int, [ctypes.POINTER(CnnTailDesc), ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P,
+                                           _P, ctypes.POINTER(_P), ctypes.c_int32, _P, ctypes.c_size_t, _P]),
     "seldq_tcn_glue": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(TcnGlue), ctypes.POINTER(ConvDesc), ctypes.c_int32,
                                       _P]),
     "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P,

@@ -23,6 +23,7 @@
 #include "epilogue.h"
 #include "launch.h"
 #include "tile_cl.cuh"
+#include "wgrad_first.h"
 
 namespace seldq {
 namespace epi {
@@ -493,6 +494,27 @@ int launch_cnn_tail_fwd(epi::TailParams& p, cudaStream_t st) {
 }
 
 int launch_cnn_tail_bwd(epi::TailParams& p, double* dsums, cudaStream_t st) {
+  int rc = launch_cnn_tail_bwd_reduce(p, dsums, st);
+  if (rc) return rc;
+  float2* dmean = reinterpret_cast<float2*>(dsums + 2 * (size_t)p.C);      // third C doubles of the caller's buffer
+  p.pitch = nchw16_pitch(p.W);
+  if (tail_vec_ok(p)) {      // W % 8 == 0  =>  pitch == W
+    p.tiles_w = (p.W + epi::kVecTileW - 1) / epi::kVecTileW;
+    p.tiles_c = (p.Cp + 63) / 64;
+    p.total_blocks = (long long)p.tiles_w * p.tiles_c * p.H * p.N;
+    const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
+    epi::cnn_tail_bwd_apply_vec_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p, dmean);
+    return check_launch("cnn_tail_bwd_apply_vec_kernel");
+  }
+  p.tiles_w = (p.pitch + 31) / 32;
+  p.tiles_c = (p.Cp + 63) / 64;
+  p.total_blocks = (long long)p.tiles_w * p.tiles_c * p.H * p.N;
+  const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
+  epi::cnn_tail_bwd_apply_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p, dmean);
+  return check_launch("cnn_tail_bwd_apply_kernel");
+}
+
+int launch_cnn_tail_bwd_reduce(epi::TailParams& p, double* dsums, cudaStream_t st) {
   const int HP = p.H / p.pool;
   const long long plane = (long long)HP * p.W;
   long long splits = (plane + 16383) / 16384;
@@ -512,22 +534,7 @@ int launch_cnn_tail_bwd(epi::TailParams& p, double* dsums, cudaStream_t st) {
   const double count = (double)p.N * p.H * p.W;
   float2* dmean = reinterpret_cast<float2*>(dsums + 2 * (size_t)p.C);      // third C doubles of the caller's buffer
   epi::cnn_tail_bwd_finalize_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(dsums, p.C, count, dmean);
-  if ((rc = check_launch("cnn_tail_bwd_finalize_kernel"))) return rc;
-  p.pitch = nchw16_pitch(p.W);
-  if (tail_vec_ok(p)) {      // W % 8 == 0  =>  pitch == W
-    p.tiles_w = (p.W + epi::kVecTileW - 1) / epi::kVecTileW;
-    p.tiles_c = (p.Cp + 63) / 64;
-    p.total_blocks = (long long)p.tiles_w * p.tiles_c * p.H * p.N;
-    const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
-    epi::cnn_tail_bwd_apply_vec_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p, dmean);
-    return check_launch("cnn_tail_bwd_apply_vec_kernel");
-  }
-  p.tiles_w = (p.pitch + 31) / 32;
-  p.tiles_c = (p.Cp + 63) / 64;
-  p.total_blocks = (long long)p.tiles_w * p.tiles_c * p.H * p.N;
-  const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
-  epi::cnn_tail_bwd_apply_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p, dmean);
-  return check_launch("cnn_tail_bwd_apply_kernel");
+  return check_launch("cnn_tail_bwd_finalize_kernel");
 }
 
 }  // namespace seldq

@@ -9,6 +9,7 @@
 #include "launch.h"
 #include "stft.cuh"
 #include "tcn_glue.h"
+#include "wgrad_first.h"
 
 using namespace seldq;
 
@@ -415,6 +416,70 @@ extern "C" int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_co
   p.ymax = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ymax));
   p.d_t16 = reinterpret_cast<__nv_bfloat16*>(d_t16); p.d_cl = reinterpret_cast<__nv_bfloat16*>(d_cl);
   return launch_cnn_tail_bwd(p, dsums, (cudaStream_t)stream);
+}
+
+// ---- first CNN block, backward: BatchNorm-backward apply fused into the weight-gradient kernel ----------------
+static int first_bwd_geom(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* conv, ConvGeom* g) {
+  int rc = make_conv_geom(conv, SELDQ_PASS_WGRAD, g);
+  if (rc) return rc;
+  if (!t || g->P != t->c || g->N != t->n || g->OH != t->h || g->OW != t->w)
+    return fail(SELDQ_ERR_INVALID, "seldq_cnn_first_bwd: tail descriptor does not match the convolution's output");
+  return SELDQ_OK;
+}
+
+extern "C" int seldq_cnn_first_bwd_supported(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* conv) {
+  ConvGeom g;
+  if (!conv || conv->precision != SELDQ_PREC_BF16 || first_bwd_geom(t, conv, &g)) return 0;
+  return (first_layer_bwd_supported(g) && t->pool >= 1 && t->pool <= 8 && t->h / t->pool > 0 && t->h % t->pool == 0) ? 1 : 0;
+}
+
+extern "C" size_t seldq_cnn_first_bwd_workspace_bytes(const seldq_conv_desc_t* conv) {
+  ConvGeom g;
+  if (make_conv_geom(conv, SELDQ_PASS_WGRAD, &g)) return 0;
+  int shifts[8], ns = 0;
+  mirror_shifts(g, 0, shifts, &ns);
+  return mirror_bytes((long long)g.N * g.R * g.IH, g.IW, ns) + 256;
+}
+
+extern "C" int seldq_cnn_first_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* conv, const float* x,
+                                   const void* y_bf16, const float* coef, const uint8_t* idx, const void* ymax,
+                                   const float* gz, double* dsums, float* const* host_gw, int32_t accumulate,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  ConvGeom g;
+  int rc = first_bwd_geom(t, conv, &g);
+  if (rc) return rc;
+  if (!seldq_cnn_first_bwd_supported(t, conv))
+    return fail(SELDQ_ERR_UNSUPPORTED, "seldq_cnn_first_bwd: geometry outside the fused kernel (see seldq_cnn_first_bwd_supported)");
+  if (!x || !y_bf16 || !coef || !idx || !gz || !dsums || !host_gw)
+    return fail(SELDQ_ERR_INVALID, "seldq_cnn_first_bwd: null pointer");
+  if ((rc = cuda_ready())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  epi::TailParams p;
+  if ((rc = tail_params(t, nullptr, &p))) return rc;
+  p.y = reinterpret_cast<const __nv_bfloat16*>(y_bf16); p.coef = coef;
+  p.idx = const_cast<uint8_t*>(idx); p.gz = gz;
+  p.ymax = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ymax));
+  if ((rc = launch_cnn_tail_bwd_reduce(p, dsums, st))) return rc;
+  const float2* dmean = reinterpret_cast<const float2*>(dsums + 2 * (size_t)t->c);
+  const size_t wbytes = (size_t)g.Oc * g.Ic * g.KH * g.KW * sizeof(float);
+  for (int i = 0; i < g.tab.nw; ++i) {
+    if (!host_gw[i]) return fail(SELDQ_ERR_INVALID, "seldq_cnn_first_bwd: gradient %d is null", i);
+    if (accumulate) continue;
+    const cudaError_t e = cudaMemsetAsync(host_gw[i], 0, wbytes, st);
+    if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  }
+  Workspace ws{(char*)workspace, workspace_bytes, 0};
+  MirrorSet mx;
+  mirror_shifts(g, 0, mx.shifts, &mx.nshifts);
+  mx.pitch = 0;
+  const size_t need = mirror_bytes((long long)g.N * g.R * g.IH, g.IW, mx.nshifts);
+  void* buf = ws.take(need);
+  if (!buf) return workspace_short(need, ws);
+  if ((rc = launch_cast_bf16_mirror(x, buf, (long long)g.N * g.R * g.IH, g.IW, mirror_pitch(g.IW), mx.shifts, mx.nshifts,
+                                    st)))
+    return rc;
+  mx.data = buf;
+  return launch_first_layer_bwd(g, mx, p, dmean, host_gw, st);
 }
 
 extern "C" int seldq_tcn_glue(int32_t op, const seldq_tcn_glue_t* a, const seldq_conv_desc_t* layout_of, int32_t which,

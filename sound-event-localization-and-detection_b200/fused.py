@@ -25,6 +25,8 @@ from ._lib import PASS_DGRAD, PASS_FWD, PASS_WGRAD, PREC_BF16
 
 _P = ctypes.c_void_p
 ENABLED = os.environ.get("SELDQ_FUSED", "1") != "0"      # SELDQ_FUSED=0: always the layer-by-layer modules
+# SELDQ_FIRST_FUSED=0: the first CNN block's backward writes d(conv out) and runs the stand-alone wgrad kernel
+FIRST_FUSED = os.environ.get("SELDQ_FIRST_FUSED", "1") != "0"
 
 
 def _ptr(t):
@@ -130,6 +132,25 @@ class _CnnStack(torch.autograd.Function):
                 ws, gamma, beta = ctx.block_params[k]
                 N, C = d.batch, d.cout
                 need_gx = k > 0 or ctx.needs_input_grad[0]
+                if (FIRST_FUSED and k == 0 and ctx.x_dense and not need_gx
+                        and L.seldq_cnn_first_bwd_supported(ctypes.byref(td), ctypes.byref(d))):
+                    # no input gradient: d(conv out) is formed inside the weight-gradient kernel (wgrad_first.cu)
+                    dsums = torch.zeros((C * 3,), dtype=torch.float64, device=dev)
+                    gws, direct = F._grad_targets(ws, [True] * len(ws))
+                    gp = _lib.ptr_array([g.data_ptr() for g in gws])
+                    work = torch.empty(L.seldq_cnn_first_bwd_workspace_bytes(ctypes.byref(d)), dtype=torch.uint8,
+                                       device=dev)
+                    F._timed("qconv_cl_wgrad_kernel", F._conv_flop(d, oh, ow), 4, lambda: _lib.check(
+                        L.seldq_cnn_first_bwd(ctypes.byref(td), ctypes.byref(d), xin.data_ptr(), y16.data_ptr(),
+                                              coef.data_ptr(), idx.data_ptr(), ymax.data_ptr(), gz.data_ptr(),
+                                              dsums.data_ptr(), gp, 1 if direct else 0, work.data_ptr(),
+                                              work.numel(), _stream())))
+                    dsf = dsums[:2 * C].view(C, 2).float()
+                    if direct:
+                        gws = [None] * len(ws)
+                    grads = list(gws) + [dsf[:, 1].contiguous() if gamma is not None else None,
+                                         dsf[:, 0].contiguous() if beta is not None else None] + grads
+                    continue
                 _, _, clb, t16b = F._operand_info(d, 1)
                 d_t16 = torch.empty(t16b, dtype=torch.uint8, device=dev)
                 d_cl = torch.empty(clb, dtype=torch.uint8, device=dev) if need_gx else None

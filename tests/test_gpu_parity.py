@@ -342,3 +342,35 @@ def test_fused_tcn_channel_dropout_is_consistent(seldq):
     assert torch.isfinite(y1).all() and torch.isfinite(g1).all()
     assert torch.allclose(y1, y2, rtol=1e-4, atol=1e-5) and torch.allclose(g1, g2, rtol=1e-3, atol=1e-6)
     assert not torch.equal(y1, y3)
+
+
+def test_fused_first_layer_backward_matches_two_kernel_path(seldq):
+    """wgrad_first.cu (BatchNorm-backward apply formed in shared memory and fed straight to the tensor cores) against
+    the two-kernel path (cnn_tail_bwd writes d(conv out), the stand-alone wgrad kernel reads it): both round d to the
+    same bf16 values, so the weight and BatchNorm gradients agree to accumulation order."""
+    model_mod = __import__("importlib").import_module(seldq.__name__ + ".seld_model")
+    torch.manual_seed(11)
+    np.random.seed(11)
+    blk = model_mod.ConvTC_Block(time_dim=200, freq_dim=64, input_channels=8, domain="DQ", cnn_filters=[64, 64, 64],
+                                 pool_size=[[8, 2], [4, 2], [2, 2]], G=64, U=64, V=[64, 64], D=[1], dropout_perc=0.3,
+                                 spatial_dropout_rate=0, use_bias_conv=False, batch_norm="BN").cuda().train()
+    x = torch.randn(2, 8, 64, 200, device="cuda")
+    gz = None
+    res = {}
+    for fused_first in (True, False):
+        prev = seldq.fused.FIRST_FUSED
+        seldq.fused.FIRST_FUSED = fused_first
+        try:
+            blk.zero_grad(set_to_none=True)
+            blk._drop_seed.fill_(3)
+            with seldq.precision("bf16"):
+                z = blk._cnn_forward(x)
+                if gz is None:
+                    gz = torch.randn_like(z)
+                z.backward(gz)
+            torch.cuda.synchronize()
+            res[fused_first] = {k: p.grad.clone() for k, p in blk.cnn[0].named_parameters()}
+        finally:
+            seldq.fused.FIRST_FUSED = prev
+    for k in res[True]:
+        assert A.rel_err(res[True][k].cpu().numpy(), res[False][k].cpu().numpy()) < 2e-3, k
