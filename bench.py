@@ -225,11 +225,20 @@ def main():
         x, t = pool_dev[i % args.pool]
         do_step(x, t)
 
+    e2e_state = {"staged": False}
+
     def step_e2e(i):
-        hx, ht = pool_host[i % args.pool]
+        # every step copies its own batch from pinned host memory and reads its loss back; with the captured
+        # step the copy of batch i+1 is started before step i is replayed, so that it runs on the copy engine
+        # while the SMs work on step i (trainer.stage / step_graph_staged)
         if use_graph:
-            loss = do_step(hx, ht)                         # pinned host -> the graph's static input buffers
+            if not e2e_state["staged"]:
+                trainer.stage(*pool_host[i % args.pool])
+            loss = trainer.step_graph_staged()
+            trainer.stage(*pool_host[(i + 1) % args.pool])
+            e2e_state["staged"] = True
         else:
+            hx, ht = pool_host[i % args.pool]
             loss = do_step(hx.to(device, non_blocking=True), ht.to(device, non_blocking=True))
         return float(loss.item())                          # device -> host read of the step's result
 

@@ -32,16 +32,27 @@
 
 #include "conv_cl.h"
 #include "launch.h"
+#include "pdl.cuh"
 #include "tensor_map.h"
 #include "umma_ptx.cuh"
 
 namespace seldq {
 namespace cl {
 
+// Unit schedule of a CTA: units are ordered heaviest group first; round r hands unit r*G + b to CTA b in even rounds
+// and r*G + (G-1-b) in odd rounds (snake order), so the few units of a last, partial round go to the CTAs that
+// hold the lightest units of the round before instead of the heaviest.  Returns -1 when the CTA sits a round out.
+__device__ __forceinline__ int unit_of_round(int round, int total_units) {
+  const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  const int u = round * G + ((round & 1) ? G - 1 - b : b);
+  return u < total_units ? u : -1;
+}
+
 template <int GC>
 __global__ void __launch_bounds__(kThreads, 1)
 qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   __shared__ uint2 op_tbl_s[kOpTableEntries];
   __shared__ __align__(16) uint8_t out_stage[4][16 * 64];   // per epilogue warp: [16 ch][32 w] bf16
   // warp index through a shuffle: provably warp-uniform, so role branches and the MMA loop compile to the
@@ -109,8 +120,11 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
           ptx::bulk_load(b_img + off, p.packed + off, n, w_bar);
         }
       }
+      pdl_wait();            // activations of the previous kernel from here on (the weights above never race)
       uint32_t slot = 0, parity = 0;
-      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
+        const int u = unit_of_round(round, p.total_units);
+        if (u < 0) continue;
         const int group = p.group_order[u / p.total_tiles];
         int r = u % p.total_tiles;
         const int wt = r % p.tiles_w; r /= p.tiles_w;
@@ -145,7 +159,9 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       const int lanes_per_stage = p.slabs_per_chunk * GC;
       if (!p.dense) ptx::mbar_wait(w_bar, 0);
       uint32_t slot = 0, parity = 0, it = 0;
-      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+      for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
+        const int u = unit_of_round(round, p.total_units);
+        if (u < 0) continue;
         const int gi = u / p.total_tiles;
         const uint32_t mask = p.chunk_mask[p.group_order[gi]];
         const uint32_t as = p.acc_stages == 2 ? (it & 1) : 0;
@@ -191,17 +207,21 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         }
         if (closes) ptx::umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
         __syncwarp();
+        ++it;
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global ===================================================
+    pdl_wait();
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     // 16-byte bf16 stores need 8-element alignment of every row start
     const bool vec16 = p.out16 != nullptr && (p.OW & 7) == 0 && (p.out_sC & 7) == 0 && (p.out_sH & 7) == 0 &&
                        (p.out_sN & 7) == 0 && (reinterpret_cast<unsigned long long>(p.out16) & 15ull) == 0;
     uint32_t it = 0;
-    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+    for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
+      const int u = unit_of_round(round, p.total_units);
+      if (u < 0) continue;
       const int group = p.group_order[u / p.total_tiles];
       const uint32_t as = p.acc_stages == 2 ? (it & 1) : 0;
       const uint32_t use = p.acc_stages == 2 ? (it >> 1) : it;
@@ -272,6 +292,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      ++it;
     }
   }
   ptx::tc_fence_before();
@@ -615,7 +636,8 @@ int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* ho
   }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "fprop smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
-  kern<<<grid, cl::kThreads, smem, st>>>(tm, p);
+  const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(cl::kThreads), smem, st, tm, p);
+  if (le != cudaSuccess) return fail(SELDQ_ERR_CUDA, "qconv_cl_fprop_kernel: %s", cudaGetErrorString(le));
   return check_launch("qconv_cl_fprop_kernel");
 }
 

@@ -22,6 +22,7 @@
 #include "conv_cl.h"
 #include "epilogue.h"
 #include "launch.h"
+#include "pdl.cuh"
 #include "tile_cl.cuh"
 #include "wgrad_first.h"
 
@@ -35,6 +36,8 @@ __device__ __forceinline__ float load_as_float(const __nv_bfloat16* p) { return 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ src, long long plane, int C,
                                                        long long chunk, double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x, n = blockIdx.y;
   const long long lo = (long long)blockIdx.z * chunk;
   const long long hi = lo + chunk < plane ? lo + chunk : plane;
@@ -72,6 +75,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ src
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, int C, double count, float eps, float momentum,
                                    float* running_mean, float* running_var, float* __restrict__ coef) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = sums[2 * c] / count;
@@ -93,6 +98,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
 
 // One block: 64 padded channels x 32 w positions of one pooled row (n, h').
 __global__ void __launch_bounds__(256) cnn_tail_fwd_kernel(const __grid_constant__ TailParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[64][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int HP = p.H / p.pool;
@@ -154,6 +161,8 @@ __global__ void __launch_bounds__(256) cnn_tail_fwd_kernel(const __grid_constant
 // grid (C, N, splits) over the pooled plane H' x W of (n, c)
 __global__ void __launch_bounds__(256) cnn_tail_bwd_reduce_kernel(const __grid_constant__ TailParams p, long long chunk,
                                                                  double* __restrict__ dsums) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x, n = blockIdx.y;
   const int HP = p.H / p.pool;
   const long long plane = (long long)HP * p.W;
@@ -185,6 +194,8 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_reduce_kernel(const __grid_c
 // stream (1-byte flags, fp32 gradient, bf16 values) read contiguously
 __global__ void __launch_bounds__(256) cnn_tail_bwd_reduce_vec_kernel(const __grid_constant__ TailParams p,
                                                                      long long chunk, double* __restrict__ dsums) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x, n = blockIdx.y;
   const int HP = p.H / p.pool;
   const long long plane = (long long)HP * p.W;
@@ -223,6 +234,8 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_reduce_vec_kernel(const __gr
 // dmean[c] = {sum(dy) / M, sum(dy * xhat) / M} in fp32 (keeps the FP64 pipe out of the per-element kernel)
 __global__ void cnn_tail_bwd_finalize_kernel(const double* __restrict__ dsums, int C, double count,
                                              float2* __restrict__ dmean) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) dmean[c] = make_float2((float)(dsums[2 * c] / count), (float)(dsums[2 * c + 1] / count));
 }
@@ -230,6 +243,8 @@ __global__ void cnn_tail_bwd_finalize_kernel(const double* __restrict__ dsums, i
 // One block: 64 padded channels x 32 w positions of one full-resolution row (n, h).
 __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_kernel(const __grid_constant__ TailParams p,
                                                                 const float2* __restrict__ dmean) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[64][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int HP = p.H / p.pool;
@@ -290,6 +305,8 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_kernel(const __grid_co
 // loads / stores in the tensor's own NCHW order) and drops its results, as bf16, into a [w][64 ch] shared
 // tile; phase 2 writes the tile as channels-last rows, 16 bytes per thread.
 __global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_constant__ TailParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) uint8_t tile[kVecTileW * kVecPitch];
   const int HP = p.H / p.pool;
   const unsigned long long seed = p.seed_ptr ? (unsigned long long)*p.seed_ptr : 0ULL;
@@ -370,6 +387,8 @@ __global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_cons
 
 __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_vec_kernel(const __grid_constant__ TailParams p,
                                                                     const float2* __restrict__ dmean) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) uint8_t tile[kVecTileW * kVecPitch];
   const int HP = p.H / p.pool;
   const float scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
@@ -457,16 +476,16 @@ int launch_bn_stats(const void* src, int is_bf16, int n, int c, long long plane,
   splits = (plane + chunk - 1) / chunk;
   dim3 grid((unsigned)c, (unsigned)n, (unsigned)splits);
   if (is_bf16)
-    epi::bn_stats_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), plane, c, chunk, sums);
+    launch_pdl(epi::bn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(src), plane, c, chunk, sums);
   else
-    epi::bn_stats_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), plane, c, chunk, sums);
+    launch_pdl(epi::bn_stats_kernel<float>, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float*>(src), plane, c, chunk, sums);
   return check_launch("bn_stats_kernel");
 }
 
 int launch_bn_finalize(const double* sums, const float* gamma, const float* beta, int c, double count, float eps,
                        float momentum, float* running_mean, float* running_var, float* coef, cudaStream_t st) {
-  epi::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, gamma, beta, c, count, eps, momentum, running_mean,
-                                                           running_var, coef);
+  launch_pdl(epi::bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), 0, st, sums, gamma, beta, c, count, eps, momentum,
+             running_mean, running_var, coef);
   return check_launch("bn_finalize_kernel");
 }
 
@@ -482,14 +501,14 @@ int launch_cnn_tail_fwd(epi::TailParams& p, cudaStream_t st) {
     p.tiles_c = (p.Cp + 63) / 64;
     p.total_blocks = (long long)p.tiles_w * p.tiles_c * (p.H / p.pool) * p.N;
     const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
-    epi::cnn_tail_fwd_vec_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p);
+    launch_pdl(epi::cnn_tail_fwd_vec_kernel, dim3((unsigned)(blocks < 1 ? 1 : blocks)), dim3(256), 0, st, p);
     return check_launch("cnn_tail_fwd_vec_kernel");
   }
   p.tiles_w = (p.W + 31) / 32;
   p.tiles_c = (p.Cp + 63) / 64;
   p.total_blocks = (long long)p.tiles_w * p.tiles_c * (p.H / p.pool) * p.N;
   const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
-  epi::cnn_tail_fwd_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p);
+  launch_pdl(epi::cnn_tail_fwd_kernel, dim3((unsigned)(blocks < 1 ? 1 : blocks)), dim3(256), 0, st, p);
   return check_launch("cnn_tail_fwd_kernel");
 }
 
@@ -503,14 +522,14 @@ int launch_cnn_tail_bwd(epi::TailParams& p, double* dsums, cudaStream_t st) {
     p.tiles_c = (p.Cp + 63) / 64;
     p.total_blocks = (long long)p.tiles_w * p.tiles_c * p.H * p.N;
     const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
-    epi::cnn_tail_bwd_apply_vec_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p, dmean);
+    launch_pdl(epi::cnn_tail_bwd_apply_vec_kernel, dim3((unsigned)(blocks < 1 ? 1 : blocks)), dim3(256), 0, st, p, dmean);
     return check_launch("cnn_tail_bwd_apply_vec_kernel");
   }
   p.tiles_w = (p.pitch + 31) / 32;
   p.tiles_c = (p.Cp + 63) / 64;
   p.total_blocks = (long long)p.tiles_w * p.tiles_c * p.H * p.N;
   const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
-  epi::cnn_tail_bwd_apply_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(p, dmean);
+  launch_pdl(epi::cnn_tail_bwd_apply_kernel, dim3((unsigned)(blocks < 1 ? 1 : blocks)), dim3(256), 0, st, p, dmean);
   return check_launch("cnn_tail_bwd_apply_kernel");
 }
 
@@ -526,14 +545,14 @@ int launch_cnn_tail_bwd_reduce(epi::TailParams& p, double* dsums, cudaStream_t s
   if (p.N > 65535) return fail(SELDQ_ERR_UNSUPPORTED, "cnn tail: batch too large for the grid");
   dim3 grid((unsigned)p.C, (unsigned)p.N, (unsigned)splits);
   if (p.ymax && tail_vec_ok(p) && chunk % 8 == 0 && (reinterpret_cast<uintptr_t>(p.ymax) & 15) == 0)
-    epi::cnn_tail_bwd_reduce_vec_kernel<<<grid, 256, 0, st>>>(p, chunk, dsums);
+    launch_pdl(epi::cnn_tail_bwd_reduce_vec_kernel, dim3(grid), dim3(256), 0, st, p, chunk, dsums);
   else
-    epi::cnn_tail_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p, chunk, dsums);
+    launch_pdl(epi::cnn_tail_bwd_reduce_kernel, dim3(grid), dim3(256), 0, st, p, chunk, dsums);
   int rc = check_launch("cnn_tail_bwd_reduce_kernel");
   if (rc) return rc;
   const double count = (double)p.N * p.H * p.W;
   float2* dmean = reinterpret_cast<float2*>(dsums + 2 * (size_t)p.C);      // third C doubles of the caller's buffer
-  epi::cnn_tail_bwd_finalize_kernel<<<(p.C + 127) / 128, 128, 0, st>>>(dsums, p.C, count, dmean);
+  launch_pdl(epi::cnn_tail_bwd_finalize_kernel, dim3((p.C + 127) / 128), dim3(128), 0, st, dsums, p.C, count, dmean);
   return check_launch("cnn_tail_bwd_finalize_kernel");
 }
 

@@ -21,6 +21,7 @@
 
 #include "conv_cl.h"
 #include "launch.h"
+#include "pdl.cuh"
 #include "tcn_glue.h"
 #include "tile_cl.cuh"
 
@@ -122,6 +123,8 @@ __device__ __forceinline__ void tile_coefs(const GlueParams& p, const TileIdx& t
 // ---- forward -------------------------------------------------------------------------------------------------
 // x = tanh(BN1(r)):  in[0] = r -> out32 = x, out_cl[0] = x operand
 __global__ void __launch_bounds__(256) preact_fwd_kernel(const __grid_constant__ GlueParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) uint8_t tile[kVecTileW * epi::kVecPitch];
   __shared__ float4 s_coef[64];
   if (blockIdx.x == 0)
@@ -154,6 +157,8 @@ __global__ void __launch_bounds__(256) preact_fwd_kernel(const __grid_constant__
 
 // y = dropout1d(tanh(BN_f(y_f)) * sigmoid(BN_g(y_g))):  in[0] = y_f, in[1] = y_g -> out_cl[0] = y operand
 __global__ void __launch_bounds__(256) gate_fwd_kernel(const __grid_constant__ GlueParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) uint8_t tile[kVecTileW * epi::kVecPitch];
   __shared__ float4 s_coef[2][64];
   const unsigned long long seed = p.seed_ptr ? (unsigned long long)*p.seed_ptr : 0ULL;
@@ -195,6 +200,8 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const __grid_constant__ G
 // row kernel: per-channel (sum, sum of squares) of up to two tensors: in[z] -> stats_out[z] (zeroed by the
 // caller); blockIdx.z = z * splits + split
 __global__ void __launch_bounds__(256) row_stats_kernel(const __grid_constant__ GlueParams p, int splits, int chunk) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x, n = blockIdx.y;
   const int z = blockIdx.z / splits, sp = blockIdx.z - z * splits;
   const int lo = sp * chunk, hi = min(p.T, lo + chunk);
@@ -216,6 +223,8 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const __grid_constant__ 
 // skips: accum = (accum_init ? 0 : accum) + in[2].  in[1] == null (last block): only the skip accumulation.
 __global__ void __launch_bounds__(256) residual_fwd_kernel(const __grid_constant__ GlueParams p, int splits, int chunk,
                                                           int accum_init) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x, n = blockIdx.y, sp = blockIdx.z;
   const int lo = sp * chunk, hi = min(p.T, lo + chunk);
   const bool res = p.in[1] != nullptr && c < p.C;
@@ -264,6 +273,8 @@ __device__ __forceinline__ void gate_dz(float f, float g, float gy, const float4
 // row kernel: dsums[0..3][c] = sum dz_f, sum dz_f xhat_f, sum dz_g, sum dz_g xhat_g (planar);  in = {y_f, y_g, gy1, gy2 | null}
 __global__ void __launch_bounds__(256) gate_bwd_reduce_kernel(const __grid_constant__ GlueParams p, int splits,
                                                              int chunk) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x, n = blockIdx.y, sp = blockIdx.z;
   const int lo = sp * chunk, hi = min(p.T, lo + chunk);
   const long long base = ((long long)n * p.C + c) * p.T;
@@ -300,6 +311,8 @@ __global__ void __launch_bounds__(256) gate_bwd_reduce_kernel(const __grid_const
 
 // tile kernel: d y_f, d y_g -> channels-last operands out_cl[0|1] and pitched NCW operands out_t16[0|1]
 __global__ void __launch_bounds__(256) gate_bwd_apply_kernel(const __grid_constant__ GlueParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) uint8_t tile[2][kVecTileW * epi::kVecPitch];
   __shared__ float4 s_coef[2][64];
   const unsigned long long seed = p.seed_ptr ? (unsigned long long)*p.seed_ptr : 0ULL;
@@ -355,6 +368,8 @@ __global__ void __launch_bounds__(256) gate_bwd_apply_kernel(const __grid_consta
 // row kernel: dsums[0..1][c] = sum dz, sum dz xhat (planar)
 __global__ void __launch_bounds__(256) preact_bwd_reduce_kernel(const __grid_constant__ GlueParams p, int splits,
                                                                int chunk) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x, n = blockIdx.y, sp = blockIdx.z;
   const int lo = sp * chunk, hi = min(p.T, lo + chunk);
   const long long base = ((long long)n * p.C + c) * p.T;
@@ -388,6 +403,8 @@ __global__ void __launch_bounds__(256) preact_bwd_reduce_kernel(const __grid_con
 // tile kernel: g_r = a (dz - mean dz - xhat mean(dz xhat)) -> out32 (fp32) and, when requested, the operands
 // out_cl[0] / out_t16[0] of the previous block's conv2 gradient kernels
 __global__ void __launch_bounds__(256) preact_bwd_apply_kernel(const __grid_constant__ GlueParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) uint8_t tile[kVecTileW * epi::kVecPitch];
   __shared__ float4 s_coef[64];
   const float inv_count = (float)(1.0 / p.count);
@@ -464,33 +481,33 @@ int launch_tcn_glue(int op, tcn::GlueParams& p, int flag, cudaStream_t st) {
   int splits = 1, chunk = 0;
   switch (op) {
     case tcn::OP_PREACT_FWD:
-      tcn::preact_fwd_kernel<<<tile_grid(p), 256, 0, st>>>(p);
+      launch_pdl(tcn::preact_fwd_kernel, dim3(tile_grid(p)), dim3(256), 0, st, p);
       return check_launch("tcn::preact_fwd_kernel");
     case tcn::OP_GATE_FWD:
-      tcn::gate_fwd_kernel<<<tile_grid(p), 256, 0, st>>>(p);
+      launch_pdl(tcn::gate_fwd_kernel, dim3(tile_grid(p)), dim3(256), 0, st, p);
       return check_launch("tcn::gate_fwd_kernel");
     case tcn::OP_ROW_STATS:
       row_grid(p, flag, &grid, &splits, &chunk);
-      tcn::row_stats_kernel<<<grid, 256, 0, st>>>(p, splits, chunk);
+      launch_pdl(tcn::row_stats_kernel, grid, dim3(256), 0, st, p, splits, chunk);
       return check_launch("tcn::row_stats_kernel");
     case tcn::OP_RESIDUAL_FWD:
       row_grid(p, 1, &grid, &splits, &chunk);
       grid.x = (unsigned)(p.C2 > p.C ? p.C2 : p.C);
-      tcn::residual_fwd_kernel<<<grid, 256, 0, st>>>(p, splits, chunk, flag);
+      launch_pdl(tcn::residual_fwd_kernel, grid, dim3(256), 0, st, p, splits, chunk, flag);
       return check_launch("tcn::residual_fwd_kernel");
     case tcn::OP_GATE_BWD_REDUCE:
       row_grid(p, 1, &grid, &splits, &chunk);
-      tcn::gate_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p, splits, chunk);
+      launch_pdl(tcn::gate_bwd_reduce_kernel, grid, dim3(256), 0, st, p, splits, chunk);
       return check_launch("tcn::gate_bwd_reduce_kernel");
     case tcn::OP_GATE_BWD_APPLY:
-      tcn::gate_bwd_apply_kernel<<<tile_grid(p), 256, 0, st>>>(p);
+      launch_pdl(tcn::gate_bwd_apply_kernel, dim3(tile_grid(p)), dim3(256), 0, st, p);
       return check_launch("tcn::gate_bwd_apply_kernel");
     case tcn::OP_PREACT_BWD_REDUCE:
       row_grid(p, 1, &grid, &splits, &chunk);
-      tcn::preact_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p, splits, chunk);
+      launch_pdl(tcn::preact_bwd_reduce_kernel, grid, dim3(256), 0, st, p, splits, chunk);
       return check_launch("tcn::preact_bwd_reduce_kernel");
     case tcn::OP_PREACT_BWD_APPLY:
-      tcn::preact_bwd_apply_kernel<<<tile_grid(p), 256, 0, st>>>(p);
+      launch_pdl(tcn::preact_bwd_apply_kernel, dim3(tile_grid(p)), dim3(256), 0, st, p);
       return check_launch("tcn::preact_bwd_apply_kernel");
   }
   return fail(SELDQ_ERR_INVALID, "unknown TCN glue op %d", op);

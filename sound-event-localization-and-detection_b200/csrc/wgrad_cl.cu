@@ -21,6 +21,7 @@
 
 #include "conv_cl.h"
 #include "launch.h"
+#include "pdl.cuh"
 #include "tensor_map.h"
 #include "umma_ptx.cuh"
 
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
                       const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   __shared__ __align__(8) uint64_t full_bar[kWgradStages], empty_bar[kWgradStages], done_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -61,6 +63,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                   // operands and the gradient buffers belong to earlier kernels up to here
 
   if (nk > 0) {
     if (warp == 0) {
@@ -247,7 +250,8 @@ int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, 
   cudaError_t e = cudaFuncSetAttribute(qconv_cl_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "wgrad smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
   dim3 grid(tiles, p.splits);
-  qconv_cl_wgrad_kernel<<<grid, kThreads, smem, st>>>(tm_g, tm_x, p);
+  const cudaError_t le = launch_pdl(qconv_cl_wgrad_kernel, grid, dim3(kThreads), smem, st, tm_g, tm_x, p);
+  if (le != cudaSuccess) return fail(SELDQ_ERR_CUDA, "qconv_cl_wgrad_kernel: %s", cudaGetErrorString(le));
   return check_launch("qconv_cl_wgrad_kernel");
 }
 

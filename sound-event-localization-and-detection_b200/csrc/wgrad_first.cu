@@ -24,6 +24,7 @@
 #include "conv_umma.h"
 #include "epilogue.h"
 #include "launch.h"
+#include "pdl.cuh"
 #include "tensor_map.h"
 #include "umma_ptx.cuh"
 #include "wgrad_first.h"
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 first_layer_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
                        const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   __shared__ __align__(8) uint64_t full_a[kStages], full_y[kStages], full_b[kStages], empty_bar[kStages], done_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -71,6 +73,7 @@ first_layer_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();
 
   if (nk > 0) {
     if (warp == 0) {
@@ -300,7 +303,8 @@ int launch_first_layer_bwd(const ConvGeom& g, const MirrorSet& x, const epi::Tai
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "first-layer backward smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
   long long grid = umma::num_sms();
   if (grid > p.ksteps) grid = p.ksteps;
-  first_layer_bwd_kernel<<<(unsigned)grid, kThreads, smem, st>>>(tm_x, tm_y, p);
+  const cudaError_t le = launch_pdl(first_layer_bwd_kernel, dim3((unsigned)grid), dim3(kThreads), smem, st, tm_x, tm_y, p);
+  if (le != cudaSuccess) return fail(SELDQ_ERR_CUDA, "first_layer_bwd_kernel: %s", cudaGetErrorString(le));
   return check_launch("first_layer_bwd_kernel");
 }
 

@@ -104,6 +104,31 @@ class Trainer(object):
         self._graph.replay()
         return self._sloss
 
+    # ---- input pipeline of the captured step: the host -> device copy of batch i+1 overlaps step i ---------
+    def stage(self, x_host, target_host):
+        """Starts the asynchronous copy of a (pinned) host batch into the device staging buffers on a copy stream."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._gx, self._gt = torch.empty_like(self._sx), torch.empty_like(self._st)
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
+        self._copy_stream.wait_event(self._consumed)          # the previous staged batch has been taken over
+        with torch.cuda.stream(self._copy_stream):
+            self._gx.copy_(x_host, non_blocking=True)
+            self._gt.copy_(target_host, non_blocking=True)
+            self._staged.record(self._copy_stream)
+
+    def step_graph_staged(self):
+        """Replays the captured step on the batch `stage` copied last (device -> device into the graph's static
+        input buffers, ordered after the copy stream's transfer)."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        self._sx.copy_(self._gx, non_blocking=True)
+        self._st.copy_(self._gt, non_blocking=True)
+        self._consumed.record(cur)
+        self._graph.replay()
+        return self._sloss
+
     def step(self, x, target):
         """One optimisation step on this rank's shard; returns the (local) loss tensor."""
         self.bucket.zero()
