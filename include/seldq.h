@@ -151,6 +151,12 @@ int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_c
                      const float* gy, const void* gy_t16, float* const* host_gw, float* gbias,
                      int32_t accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The weight gradients of TWO convolutions of equal geometry that read the same x (the filter / gate and the
+ * skip / residual convolutions of a residual block, model.py:118-132) in one launch; bf16 path, both operands
+ * pre-staged (x as CL operand, the gy's as T16 operands). */
+int seldq_conv_wgrad_pair(const seldq_conv_desc_t* d, const void* x_cl, const void* gy_t16_a, const void* gy_t16_b,
+                          float* const* host_gw_a, float* const* host_gw_b, int32_t accumulate, void* stream);
+
 /* ---- glue between the convolutions (E1 in SURVEY.md 8a) -------------------------------------------------
  * CNN block, model.py:276-283: conv -> BatchNorm2d(train) -> ReLU -> MaxPool2d([pool,1]) -> Dropout(drop_p).
  *   seldq_bn_stats      sums[c][0] += sum v, sums[c][1] += sum v^2 over an NCHW tensor (plane = H*W elements per

@@ -103,6 +103,8 @@ _PROTOS = {
                                         ctypes.c_size_t, _P]),
     "seldq_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.POINTER(_P), _P,
                                         ctypes.c_int32, _P, ctypes.c_size_t, _P]),
+    "seldq_conv_wgrad_pair": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, ctypes.POINTER(_P),
+                                             ctypes.POINTER(_P), ctypes.c_int32, _P]),
     "seldq_linear_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(LinearDesc), ctypes.c_int32]),
     "seldq_linear_fwd": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, ctypes.POINTER(_P), _P, _P, _P,
                                         ctypes.c_size_t, _P]),

@@ -100,7 +100,9 @@ struct FpropParams {
 constexpr int kWgradStages = 4;
 struct WgradParams {
   ConvGeom g;                   // forward orientation
-  float* gw[8];                 // compact fp32 gradients, accumulated with atomicAdd
+  float* gw[2][8];              // compact fp32 gradients of up to two problems, accumulated with atomicAdd
+  int nprob;                    // 1, or 2: two convolutions of equal geometry that read the same x (e.g. the filter
+                                // and gate convolutions of a residual block) share one launch
   int ncomp, OS;                // M rows = ncomp * OS (= 128)
   int o_tiles;
   int cpad_in, Cp, nchunks;     // x operand: Cp = ncomp*cpad_in channels = nchunks boxes of 64
@@ -131,7 +133,7 @@ int launch_pack_weights_multi(const void* dev_table, int count, int max_items, c
 int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
                     const float* bias, float* out, void* out_bf16, cudaStream_t st);
 int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, float* const* host_gw,
-                    cudaStream_t st);
+                    cudaStream_t st, const void* gy2_nchw16 = nullptr, float* const* host_gw2 = nullptr);
 // fp32 NCHW -> CL operand (and, optionally, the pitched NCHW bf16 copy wgrad reads gy from)
 int launch_stage_operand(const float* src, void* dst_cl, void* dst_nchw16, const cl::OperandLayout& l, int n, int c,
                          int h, int w, cudaStream_t st);

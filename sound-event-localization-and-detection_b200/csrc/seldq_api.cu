@@ -418,6 +418,33 @@ extern "C" int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_co
   return launch_cnn_tail_bwd(p, dsums, (cudaStream_t)stream);
 }
 
+// two convolutions of equal geometry reading the same x (filter / gate, skip / residual of a residual block):
+// both weight gradients in one launch (twice the K extent per CTA for the same fixed cost)
+extern "C" int seldq_conv_wgrad_pair(const seldq_conv_desc_t* d, const void* x_cl, const void* gy_t16_a,
+                                     const void* gy_t16_b, float* const* host_gw_a, float* const* host_gw_b,
+                                     int32_t accumulate, void* stream) {
+  ConvGeom g;
+  int rc = make_conv_geom(d, SELDQ_PASS_WGRAD, &g);
+  if (rc) return rc;
+  if (d->precision != SELDQ_PREC_BF16) return fail(SELDQ_ERR_UNSUPPORTED, "seldq_conv_wgrad_pair exists on the SELDQ_PREC_BF16 path only");
+  const OperandInfo ox = operand_info(g, 0);
+  if (ox.lay.nc != g.tab.nc || g.tab.nc == 1)
+    return fail(SELDQ_ERR_UNSUPPORTED, "seldq_conv_wgrad_pair: narrow / real layers take seldq_conv_wgrad");
+  if (!x_cl || !gy_t16_a || !gy_t16_b || !host_gw_a || !host_gw_b) return fail(SELDQ_ERR_INVALID, "seldq_conv_wgrad_pair: null pointer");
+  if ((rc = cuda_ready())) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t wbytes = (size_t)g.Oc * g.Ic * g.KH * g.KW * sizeof(float);
+  for (int k = 0; k < 2; ++k)
+    for (int i = 0; i < g.tab.nw; ++i) {
+      float* gw = (k ? host_gw_b : host_gw_a)[i];
+      if (!gw) return fail(SELDQ_ERR_INVALID, "seldq_conv_wgrad_pair: gradient %d is null", i);
+      if (accumulate) continue;
+      const cudaError_t e = cudaMemsetAsync(gw, 0, wbytes, st);
+      if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    }
+  return launch_cl_wgrad(g, x_cl, gy_t16_a, host_gw_a, st, gy_t16_b, host_gw_b);
+}
+
 // ---- first CNN block, backward: BatchNorm-backward apply fused into the weight-gradient kernel ----------------
 static int first_bwd_geom(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* conv, ConvGeom* g) {
   int rc = make_conv_geom(conv, SELDQ_PASS_WGRAD, g);

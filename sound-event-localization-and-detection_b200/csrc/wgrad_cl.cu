@@ -29,17 +29,19 @@ namespace seldq {
 namespace cl {
 
 __global__ void __launch_bounds__(kThreads, 1)
-qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_x,
-                      const __grid_constant__ WgradParams p) {
+qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_constant__ CUtensorMap tm_g1,
+                      const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
   __shared__ __align__(8) uint64_t full_bar[kWgradStages], empty_bar[kWgradStages], done_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
-  // tile decode: blockIdx.x = tap_group * o_tiles + o_tile, blockIdx.y = split
+  // tile decode: blockIdx.x = (problem * tap_groups + tap_group) * o_tiles + o_tile, blockIdx.y = split
   const int o_tile = blockIdx.x % p.o_tiles;
-  const int tg = blockIdx.x / p.o_tiles;
+  const int prob = (blockIdx.x / p.o_tiles) / p.tap_groups;
+  const int tg = (blockIdx.x / p.o_tiles) % p.tap_groups;
+  const CUtensorMap* tm_g = prob ? &tm_g1 : &tm_g0;
   const int tap0 = tg * p.taps_per_group;
   const int ntap = min(p.taps_per_group, p.ntaps - tap0);
   const int o0 = o_tile * p.OS;
@@ -55,7 +57,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
     for (int i = 0; i < nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
     ptx::mbar_init(&done_bar, 1);
     ptx::fence_barrier_init();
-    ptx::prefetch_tensormap(&tm_g);
+    ptx::prefetch_tensormap(tm_g);
     ptx::prefetch_tensormap(&tm_x);
   }
   if (warp == 1) ptx::tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
@@ -79,7 +81,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
           ptx::mbar_arrive_expect_tx(&full_bar[slot], a_bytes + (uint32_t)ntap * p.b_tap_bytes);
           uint8_t* st = smem + (size_t)slot * p.stage_bytes;
           for (int a = 0; a < p.ncomp; ++a)
-            ptx::tma_load_4d(st + (size_t)a * p.OS * 128, &tm_g, &full_bar[slot], w0, h, a * p.g.Oc + o0, n);
+            ptx::tma_load_4d(st + (size_t)a * p.OS * 128, tm_g, &full_bar[slot], w0, h, a * p.g.Oc + o0, n);
           for (int t = 0; t < ntap; ++t)
             for (int c = 0; c < p.nchunks; ++c)
               ptx::tma_load_4d(st + a_bytes + (size_t)t * p.b_tap_bytes + (size_t)c * 8192, &tm_x, &full_bar[slot],
@@ -149,7 +151,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
                 const float val = stg[(p.pair_a[e][k] * p.OS + ol) * pitch + p.pair_b[e][k] * 16 + il];
                 acc += p.pair_neg[e][k] ? -val : val;
               }
-              atomicAdd(p.gw[e] + (long long)(o0 + ol) * g.wsO + (long long)(ic + il) * g.wsI +
+              atomicAdd(p.gw[prob][e] + (long long)(o0 + ol) * g.wsO + (long long)(ic + il) * g.wsI +
                             (long long)(tap0 + t) * g.wsT, acc);
             }
           }
@@ -165,7 +167,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g, const __grid_con
 }  // namespace cl
 
 int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, float* const* host_gw,
-                    cudaStream_t st) {
+                    cudaStream_t st, const void* gy2_nchw16, float* const* host_gw2) {
   using namespace cl;
   if (g.sh != 1 || g.sw != 1) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 tensor-core path implements stride 1 only");
   const int ntaps = g.KH * g.KW;
@@ -177,7 +179,11 @@ int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, 
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.g = g;
-  for (int i = 0; i < g.tab.nw; ++i) p.gw[i] = host_gw[i];
+  p.nprob = (gy2_nchw16 && host_gw2) ? 2 : 1;
+  for (int i = 0; i < g.tab.nw; ++i) {
+    p.gw[0][i] = host_gw[i];
+    p.gw[1][i] = p.nprob == 2 ? host_gw2[i] : nullptr;
+  }
   p.ntaps = ntaps;
   for (int t = 0; t < ntaps; ++t) {
     p.off_h[t] = (t / g.KW) * g.dh - g.ph;
@@ -204,7 +210,7 @@ int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, 
   p.tmem_cols = cols;
   p.chunks_w = (g.OW + 63) / 64;
   p.ksteps = (long long)g.N * g.OH * p.chunks_w;
-  const int tiles = p.tap_groups * p.o_tiles;
+  const int tiles = p.nprob * p.tap_groups * p.o_tiles;
   // split-K over positions: one wave of CTAs (every split pays a TMEM round trip and one atomicAdd per compact
   // element in its epilogue), at least 4 K steps each, and no empty splits
   long long splits = num_sms() / tiles;
@@ -231,13 +237,14 @@ int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, 
   smem += 4096;   // slack: the tensor core may fetch past the logical end of the last operand tile
 
   // gy: (pitch, H, C, N) view of the pitched NCHW bf16 copy, box {64 t, 1, OS channels, 1}
-  alignas(64) CUtensorMap tm_g, tm_x;
-  {
+  alignas(64) CUtensorMap tm_g, tm_g2, tm_x;
+  for (int k = 0; k < 2; ++k) {
     const uint64_t pitch = (uint64_t)nchw16_pitch(g.OW);
     const uint64_t dims[4] = {pitch, (uint64_t)g.OH, (uint64_t)g.P, (uint64_t)g.N};
     const uint64_t strides[3] = {pitch * 2, pitch * g.OH * 2, pitch * g.OH * g.P * 2};
     const uint32_t box[4] = {64, 1, (uint32_t)p.OS, 1};
-    const int rc = encode_tensor_map(&tm_g, gy_nchw16, 2, 4, dims, strides, box, 3);
+    const int rc = encode_tensor_map(k ? &tm_g2 : &tm_g, (k && p.nprob == 2) ? gy2_nchw16 : gy_nchw16, 2, 4, dims, strides,
+                                     box, 3);
     if (rc) return rc;
   }
   {
@@ -250,7 +257,7 @@ int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, 
   cudaError_t e = cudaFuncSetAttribute(qconv_cl_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "wgrad smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
   dim3 grid(tiles, p.splits);
-  const cudaError_t le = launch_pdl(qconv_cl_wgrad_kernel, grid, dim3(kThreads), smem, st, tm_g, tm_x, p);
+  const cudaError_t le = launch_pdl(qconv_cl_wgrad_kernel, grid, dim3(kThreads), smem, st, tm_g, tm_g2, tm_x, p);
   if (le != cudaSuccess) return fail(SELDQ_ERR_CUDA, "qconv_cl_wgrad_kernel: %s", cudaGetErrorString(le));
   return check_launch("qconv_cl_wgrad_kernel");
 }

@@ -386,6 +386,18 @@ class _TcnStack(torch.autograd.Function):
                                     1 if direct else 0, None, 0, _stream())))
             return [None] * len(w) if direct else list(gws)
 
+        def wgrad_pair(d, wa, wb, x_cl, gya_t16, gyb_t16):
+            gwa, da = F._grad_targets(wa, [True] * len(wa))
+            gwb, db = F._grad_targets(wb, [True] * len(wb))
+            if da != db:                                   # mixed targets: keep it simple
+                return wgrad(d, wa, x_cl, gya_t16), wgrad(d, wb, x_cl, gyb_t16)
+            pa = _lib.ptr_array([g.data_ptr() for g in gwa])
+            pb = _lib.ptr_array([g.data_ptr() for g in gwb])
+            F._timed("qconv_cl_wgrad_kernel", 2 * F._conv_flop(d, 1, T), 1, lambda: _lib.check(
+                L_.seldq_conv_wgrad_pair(ctypes.byref(d), x_cl.data_ptr(), gya_t16.data_ptr(), gyb_t16.data_ptr(), pa, pb,
+                                         1 if da else 0, _stream())))
+            return ([None] * len(wa) if da else list(gwa)), ([None] * len(wb) if db else list(gwb))
+
         with torch.cuda.device(dev):
             g_rn = g_rn_cl = g_rn_t16 = None
             gs_cl = gs_t16 = None
@@ -404,11 +416,16 @@ class _TcnStack(torch.autograd.Function):
                     gs_cl, gs_t16 = F.stage_operand(gs, dsk, 1, want_cl=True, want_t16=True)
                 # conv2: gradient w.r.t. y and the weights
                 gy1 = dgrad(dsk, wsk, gs_cl)
-                gw_sk = wgrad(dsk, wsk, y_cl, gs_t16)
                 gy2, gw_r = None, [None] * len(wr)
                 if s["has_res"]:
                     gy2 = dgrad(dre, wr, g_rn_cl)
-                    gw_r = wgrad(dre, wr, y_cl, g_rn_t16)
+                    if dsk.cout == dre.cout:               # same geometry: both weight gradients in one launch
+                        gw_sk, gw_r = wgrad_pair(dsk, wsk, wr, y_cl, gs_t16, g_rn_t16)
+                    else:
+                        gw_sk = wgrad(dsk, wsk, y_cl, gs_t16)
+                        gw_r = wgrad(dre, wr, y_cl, g_rn_t16)
+                else:
+                    gw_sk = wgrad(dsk, wsk, y_cl, gs_t16)
                 # gate
                 bn2 = ((sums2[0], gf, bf, None, None), (sums2[1], gg, bg, None, None))
                 dsg = red[roff[k] + 2 * Lc:roff[k] + 2 * Lc + 4 * G]
@@ -422,8 +439,7 @@ class _TcnStack(torch.autograd.Function):
                 # conv1
                 gx1 = dgrad(d1, wf, df_cl)
                 gx2 = dgrad(d1, wg, dg_cl)
-                gw_f = wgrad(d1, wf, xa_cl, df_t16)
-                gw_g = wgrad(d1, wg, xa_cl, dg_t16)
+                gw_f, gw_g = wgrad_pair(d1, wf, wg, xa_cl, df_t16, dg_t16)
                 # pre-activation
                 bn1 = ((sums1, g1, b1, None, None),)
                 ds1 = red[roff[k]:roff[k] + 2 * Lc]
