@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_kernel(const __grid_co
 // One block: 64 padded channels x 128 w.  Phase 1: a thread owns 8 consecutive w of one channel (16-byte
 // loads / stores in the tensor's own NCHW order) and drops its results, as bf16, into a [w][64 ch] shared
 // tile; phase 2 writes the tile as channels-last rows, 16 bytes per thread.
+template <int POOL>   // pooled rows as a compile-time constant: all POOL loads of an item are in flight together
 __global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_constant__ TailParams p) {
   pdl_trigger();
   pdl_wait();
@@ -336,8 +337,12 @@ __global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_cons
         int arg[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; ybest[j] = 0.f; }
-        for (int q = 0; q < p.pool; ++q) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * p.W));
+        uint4 rows[POOL];
+#pragma unroll
+        for (int q = 0; q < POOL; ++q) rows[q] = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * p.W));
+#pragma unroll
+        for (int q = 0; q < POOL; ++q) {
+          const uint4 v = rows[q];
           const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -501,7 +506,17 @@ int launch_cnn_tail_fwd(epi::TailParams& p, cudaStream_t st) {
     p.tiles_c = (p.Cp + 63) / 64;
     p.total_blocks = (long long)p.tiles_w * p.tiles_c * (p.H / p.pool) * p.N;
     const long long blocks = p.total_blocks < grid_cap() ? p.total_blocks : grid_cap();
-    launch_pdl(epi::cnn_tail_fwd_vec_kernel, dim3((unsigned)(blocks < 1 ? 1 : blocks)), dim3(256), 0, st, p);
+    const dim3 grid((unsigned)(blocks < 1 ? 1 : blocks));
+    switch (p.pool) {
+      case 1: launch_pdl(epi::cnn_tail_fwd_vec_kernel<1>, grid, dim3(256), 0, st, p); break;
+      case 2: launch_pdl(epi::cnn_tail_fwd_vec_kernel<2>, grid, dim3(256), 0, st, p); break;
+      case 3: launch_pdl(epi::cnn_tail_fwd_vec_kernel<3>, grid, dim3(256), 0, st, p); break;
+      case 4: launch_pdl(epi::cnn_tail_fwd_vec_kernel<4>, grid, dim3(256), 0, st, p); break;
+      case 5: launch_pdl(epi::cnn_tail_fwd_vec_kernel<5>, grid, dim3(256), 0, st, p); break;
+      case 6: launch_pdl(epi::cnn_tail_fwd_vec_kernel<6>, grid, dim3(256), 0, st, p); break;
+      case 7: launch_pdl(epi::cnn_tail_fwd_vec_kernel<7>, grid, dim3(256), 0, st, p); break;
+      default: launch_pdl(epi::cnn_tail_fwd_vec_kernel<8>, grid, dim3(256), 0, st, p); break;
+    }
     return check_launch("cnn_tail_fwd_vec_kernel");
   }
   p.tiles_w = (p.W + 31) / 32;

@@ -457,12 +457,23 @@ class _TcnStack(torch.autograd.Function):
                 g_rn = g_r
                 grads[k] = list(gw_f) + list(gw_g) + list(gw_sk) + list(gw_r)
             redf = red.float()
+            bn_grads = []
+            for k in range(nblocks):
+                G = ctx.metas[k][4]
+                p1 = redf[roff[k]:roff[k] + 2 * Lc].view(2, Lc)
+                pg = redf[roff[k] + 2 * Lc:roff[k] + 2 * Lc + 4 * G].view(4, G)
+                # (gamma, beta) of batch_filter1, batch_filter2, batch_gate2
+                bn_grads.append([p1[1], p1[0], pg[1], pg[0], pg[3], pg[2]])
+            # with the trainer's gradient bucket in place the 6 x nblocks BatchNorm gradients are added by one
+            # multi-tensor launch instead of one accumulation kernel per parameter
+            bn_params = [t for k in range(nblocks) for t in ctx.block_params[k][4]]
+            direct_bn = F._ACCUMULATE and all(t.grad is not None and t.grad.dtype == torch.float32 for t in bn_params)
+            if direct_bn:
+                torch._foreach_add_([t.grad for t in bn_params], [g for gs_k in bn_grads for g in gs_k])
+                bn_grads = [[None] * 6 for _ in range(nblocks)]
         flat = []
         for k, g in enumerate(grads):
-            G = ctx.metas[k][4]
-            p1, pg = redf[roff[k]:roff[k] + 2 * Lc].view(2, Lc), redf[roff[k] + 2 * Lc:roff[k] + 2 * Lc + 4 * G].view(4, G)
-            # (gamma, beta) of batch_filter1, batch_filter2, batch_gate2
-            flat += g + [p1[1], p1[0], pg[1], pg[0], pg[3], pg[2]]
+            flat += g + bn_grads[k]
         return (g_rn, None, None) + tuple(flat)
 
 
