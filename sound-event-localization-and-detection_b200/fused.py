@@ -27,6 +27,16 @@ _P = ctypes.c_void_p
 ENABLED = os.environ.get("SELDQ_FUSED", "1") != "0"      # SELDQ_FUSED=0: always the layer-by-layer modules
 # SELDQ_FIRST_FUSED=0: the first CNN block's backward writes d(conv out) and runs the stand-alone wgrad kernel
 FIRST_FUSED = os.environ.get("SELDQ_FIRST_FUSED", "1") != "0"
+# SELDQ_SIDE_WGRAD=0: the TCN weight gradients stay on the main stream
+SIDE_WGRAD = os.environ.get("SELDQ_SIDE_WGRAD", "1") != "0"
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 def _ptr(t):
@@ -378,12 +388,26 @@ class _TcnStack(torch.autograd.Function):
                                     _stream())))
             return gx
 
+        # The weight gradients are off the critical path (nothing in this backward pass reads them): they run on a
+        # side stream, forked behind the producers of their operands and joined at the end, so that they fill the
+        # SMs the latency-bound glue kernels of the dgrad chain leave idle.
+        side = _side_stream(dev) if SIDE_WGRAD else None
+        keep = []                       # operands of side-stream work stay referenced until the join
+
+        def on_side(fn, *tensors):
+            if side is None:
+                return fn()
+            keep.extend(tensors)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                return fn()
+
         def wgrad(d, w, x_cl, gy_t16):
             gws, direct = F._grad_targets(w, [True] * len(w))
             gp = _lib.ptr_array([g.data_ptr() for g in gws])
-            F._timed("qconv_cl_wgrad_kernel", F._conv_flop(d, 1, T), 1, lambda: _lib.check(
+            on_side(lambda: F._timed("qconv_cl_wgrad_kernel", F._conv_flop(d, 1, T), 1, lambda: _lib.check(
                 L_.seldq_conv_wgrad(ctypes.byref(d), None, x_cl.data_ptr(), None, gy_t16.data_ptr(), gp, None,
-                                    1 if direct else 0, None, 0, _stream())))
+                                    1 if direct else 0, None, 0, _stream()))), x_cl, gy_t16, *gws)
             return [None] * len(w) if direct else list(gws)
 
         def wgrad_pair(d, wa, wb, x_cl, gya_t16, gyb_t16):
@@ -393,9 +417,9 @@ class _TcnStack(torch.autograd.Function):
                 return wgrad(d, wa, x_cl, gya_t16), wgrad(d, wb, x_cl, gyb_t16)
             pa = _lib.ptr_array([g.data_ptr() for g in gwa])
             pb = _lib.ptr_array([g.data_ptr() for g in gwb])
-            F._timed("qconv_cl_wgrad_kernel", 2 * F._conv_flop(d, 1, T), 1, lambda: _lib.check(
+            on_side(lambda: F._timed("qconv_cl_wgrad_kernel", 2 * F._conv_flop(d, 1, T), 1, lambda: _lib.check(
                 L_.seldq_conv_wgrad_pair(ctypes.byref(d), x_cl.data_ptr(), gya_t16.data_ptr(), gyb_t16.data_ptr(), pa, pb,
-                                         1 if da else 0, _stream())))
+                                         1 if da else 0, _stream()))), x_cl, gya_t16, gyb_t16, *gwa, *gwb)
             return ([None] * len(wa) if da else list(gwa)), ([None] * len(wb) if db else list(gwb))
 
         with torch.cuda.device(dev):
@@ -456,6 +480,9 @@ class _TcnStack(torch.autograd.Function):
                           dsums=ds1, out32=g_r)
                 g_rn = g_r
                 grads[k] = list(gw_f) + list(gw_g) + list(gw_sk) + list(gw_r)
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)      # join: the weight gradients are complete
+                keep.clear()
             redf = red.float()
             bn_grads = []
             for k in range(nblocks):

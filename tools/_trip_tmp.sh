@@ -1,5 +1,8 @@
 cd /root/repo
 mkdir -p gpurun_out
 timeout 500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_all.log 2>&1; echo "pytest all rc=$? $(tail -1 gpurun_out/pytest_all.log)"; grep -E "^FAILED|^E  |Error" gpurun_out/pytest_all.log | cut -c1-300 | head -20
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1o.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_r1o.log | cut -c1-200; tail -1 gpurun_out/bench_r1o.log | grep -o '"roofline": {[^}]*'  | cut -c1-200
-SELDQ_PDL=0 timeout 300 python tools/kprof.py --layers cnn1,cnn2,tcn3,tcn1 > gpurun_out/kprof_b1.log 2>&1; grep -E "^==|fprop|wgrad" gpurun_out/kprof_b1.log | cut -c1-140
+for i in 1 2; do
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_w1.log 2>&1; echo "side wgrad on:  rc=$? $(tail -1 gpurun_out/bench_w1.log | grep -o '"ms_per_step": [0-9.]*' | head -1)"
+SELDQ_SIDE_WGRAD=0 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_w0.log 2>&1; echo "side wgrad off: rc=$? $(tail -1 gpurun_out/bench_w0.log | grep -o '"ms_per_step": [0-9.]*' | head -1)"
+done
+tail -3 gpurun_out/bench_w1.log | cut -c1-300
