@@ -516,7 +516,7 @@ extern "C" int seldq_tcn_glue(int32_t op, const seldq_tcn_glue_t* a, const seldq
   tcn::GlueParams p;
   memset(&p, 0, sizeof(p));
   p.N = a->n; p.C = a->c; p.T = a->t; p.C2 = a->c2;
-  p.count = a->count; p.eps = a->eps; p.momentum = a->momentum;
+  p.count = a->count; p.inv_count = 1.0 / a->count; p.eps = a->eps; p.momentum = a->momentum;
   p.drop_p = a->drop_p; p.salt = a->salt; p.seed_ptr = reinterpret_cast<const long long*>(a->seed);
   if (a->drop_p > 0.f && !a->seed) return fail(SELDQ_ERR_INVALID, "seldq_tcn_glue: dropout needs a seed pointer");
   for (int i = 0; i < 2; ++i) {

@@ -33,11 +33,18 @@ using epi::vec_tile_off;
 using epi::vec_tile_store_cl;
 
 // {a, b, mean, rstd}: BN(v) = a v + b
-__device__ __forceinline__ float4 bn_coef(const BnRef& bn, int c, double count, float eps) {
-  const double mean = bn.sums[2 * c] / count;
-  double var = bn.sums[2 * c + 1] / count - mean * mean;
+// (everything in double, where the mean / variance difference cancels safely, but without double division or square
+// root: those cost hundreds of cycles at the GPU's fp64 rate and every thread of the row kernels evaluates this)
+__device__ __forceinline__ float4 bn_coef(const BnRef& bn, int c, double inv_count, float eps) {
+  const double mean = bn.sums[2 * c] * inv_count;
+  double var = bn.sums[2 * c + 1] * inv_count - mean * mean;
   if (var < 0) var = 0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  // 1 / sqrt(var + eps) to double accuracy from the fp32 estimate and two Newton steps (multiplies only)
+  const double v = var + (double)eps;
+  double r = (double)rsqrtf((float)v);
+  r = r * (1.5 - 0.5 * v * r * r);
+  r = r * (1.5 - 0.5 * v * r * r);
+  const float rstd = (float)r;
   const float g = bn.gamma ? __ldg(bn.gamma + c) : 1.f, bt = bn.beta ? __ldg(bn.beta + c) : 0.f;
   const float a = g * rstd;
   return make_float4(a, bt - (float)mean * a, (float)mean, rstd);
@@ -116,7 +123,7 @@ __device__ __forceinline__ void tile_coefs(const GlueParams& p, const TileIdx& t
   if (threadIdx.x < 64) {
     const int cp = ti.ct * 64 + threadIdx.x;
     const int comp = cp / p.cpad, ci = cp - comp * p.cpad;
-    if (cp < p.Cp && ci < p.cc) s_coef[threadIdx.x] = bn_coef(p.bn[which], comp * p.cc + ci, p.count, p.eps);
+    if (cp < p.Cp && ci < p.cc) s_coef[threadIdx.x] = bn_coef(p.bn[which], comp * p.cc + ci, p.inv_count, p.eps);
   }
 }
 
@@ -282,7 +289,7 @@ __global__ void __launch_bounds__(256) gate_bwd_reduce_kernel(const __grid_const
   const float m = drop_scale(p, seed, n, c);
   float s[4] = {0.f, 0.f, 0.f, 0.f};
   if (m != 0.f) {
-    const float4 cf = bn_coef(p.bn[0], c, p.count, p.eps), cg = bn_coef(p.bn[1], c, p.count, p.eps);
+    const float4 cf = bn_coef(p.bn[0], c, p.inv_count, p.eps), cg = bn_coef(p.bn[1], c, p.inv_count, p.eps);
     for (int t = lo + threadIdx.x * 4; t < hi; t += 256 * 4) {
       const float4 f4 = __ldg(reinterpret_cast<const float4*>(p.in[0] + base + t));
       const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.in[1] + base + t));
@@ -316,7 +323,7 @@ __global__ void __launch_bounds__(256) gate_bwd_apply_kernel(const __grid_consta
   __shared__ __align__(16) uint8_t tile[2][kVecTileW * epi::kVecPitch];
   __shared__ float4 s_coef[2][64];
   const unsigned long long seed = p.seed_ptr ? (unsigned long long)*p.seed_ptr : 0ULL;
-  const float inv_count = (float)(1.0 / p.count);
+  const float inv_count = (float)p.inv_count;
   for (long long blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
     const TileIdx ti = tile_decode(p, blk);
     tile_coefs(p, ti, 0, s_coef[0]);
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(256) preact_bwd_reduce_kernel(const __grid_con
   const int c = blockIdx.x, n = blockIdx.y, sp = blockIdx.z;
   const int lo = sp * chunk, hi = min(p.T, lo + chunk);
   const long long base = ((long long)n * p.C + c) * p.T;
-  const float4 cf = bn_coef(p.bn[0], c, p.count, p.eps);
+  const float4 cf = bn_coef(p.bn[0], c, p.inv_count, p.eps);
   float s1 = 0.f, s2 = 0.f;
   for (int t = lo + threadIdx.x * 4; t < hi; t += 256 * 4) {
     float4 g = __ldg(reinterpret_cast<const float4*>(p.in[1] + base + t));
@@ -407,7 +414,7 @@ __global__ void __launch_bounds__(256) preact_bwd_apply_kernel(const __grid_cons
   pdl_wait();
   __shared__ __align__(16) uint8_t tile[kVecTileW * epi::kVecPitch];
   __shared__ float4 s_coef[64];
-  const float inv_count = (float)(1.0 / p.count);
+  const float inv_count = (float)p.inv_count;
   for (long long blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
     const TileIdx ti = tile_decode(p, blk);
     tile_coefs(p, ti, 0, s_coef);

@@ -34,6 +34,7 @@ struct GlueParams {
   int cc, cpad, Cp;      // channels-last operand layout of C channels (conv_cl.h)
   int pitch;             // pitched NCW operand: T rounded up to 8
   double count;          // elements per channel behind the statistics (N * T)
+  double inv_count;
   float eps, momentum;
   BnRef bn[2];
   const float* in[5];
