@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) cnn_tail_fwd_kernel(const __grid_constant
         const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
         if (p.ymax) p.ymax[e] = yb;
         bool keep = best > 0.f;
-        if (keep && thresh) keep = dropout_keep(seed, p.salt, e, thresh);
+        if (keep && thresh) keep = dropout_keep_fast(dropout_key(seed, p.salt), e, thresh);
         z = keep ? best * scale : 0.f;
         p.idx[e] = (uint8_t)(arg | (keep ? 0x80 : 0));
         if (p.z32) p.z32[e] = z;
@@ -305,12 +305,13 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_kernel(const __grid_co
 // loads / stores in the tensor's own NCHW order) and drops its results, as bf16, into a [w][64 ch] shared
 // tile; phase 2 writes the tile as channels-last rows, 16 bytes per thread.
 template <int POOL>   // pooled rows as a compile-time constant: all POOL loads of an item are in flight together
-__global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_constant__ TailParams p) {
+__global__ void __launch_bounds__(256, 3) cnn_tail_fwd_vec_kernel(const __grid_constant__ TailParams p) {
   pdl_trigger();
   pdl_wait();
   __shared__ __align__(16) uint8_t tile[kVecTileW * kVecPitch];
   const int HP = p.H / p.pool;
   const unsigned long long seed = p.seed_ptr ? (unsigned long long)*p.seed_ptr : 0ULL;
+  const uint32_t dkey = dropout_key(seed, p.salt);
   const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
   const float scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   for (long long blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(256) cnn_tail_fwd_vec_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           bool keep = best[j] > 0.f;
-          if (keep && thresh) keep = dropout_keep(seed, p.salt, e + j, thresh);
+          if (keep && thresh) keep = dropout_keep_fast(dkey, e + j, thresh);
           z[j] = keep ? best[j] * scale : 0.f;
           id[j >> 2] |= (uint32_t)(arg[j] | (keep ? 0x80 : 0)) << (8 * (j & 3));
         }

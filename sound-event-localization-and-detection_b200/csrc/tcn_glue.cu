@@ -28,9 +28,9 @@
 namespace seldq {
 namespace tcn {
 
-using epi::kVecTileW;
+// 64 channels x 64 t per block: at batch 1 (T = 4800) that is 450 blocks, all resident at once
+constexpr int kTileW = 64;
 using epi::vec_tile_off;
-using epi::vec_tile_store_cl;
 
 // {a, b, mean, rstd}: BN(v) = a v + b
 // (everything in double, where the mean / variance difference cancels safely, but without double division or square
@@ -111,9 +111,10 @@ __device__ __forceinline__ TileIdx tile_decode(const GlueParams& p, long long bl
 __device__ __forceinline__ void item_decode(const GlueParams& p, const TileIdx& ti, int k, int* cl, int* wl, int* c,
                                             int* t) {
   const int item = threadIdx.x + 256 * k;
-  *cl = item >> 4;
-  *wl = (item & 15) * 8;
-  *t = ti.wt * kVecTileW + *wl;
+  constexpr int kVecPerRow = kTileW / 8;
+  *cl = item / kVecPerRow;
+  *wl = (item % kVecPerRow) * 8;
+  *t = ti.wt * kTileW + *wl;
   const int cp = ti.ct * 64 + *cl;
   const int comp = cp / p.cpad, ci = cp - comp * p.cpad;
   *c = (cp < p.Cp && ci < p.cc && *t < p.T) ? comp * p.cc + ci : -1;
@@ -132,7 +133,7 @@ __device__ __forceinline__ void tile_coefs(const GlueParams& p, const TileIdx& t
 __global__ void __launch_bounds__(256) preact_fwd_kernel(const __grid_constant__ GlueParams p) {
   pdl_trigger();
   pdl_wait();
-  __shared__ __align__(16) uint8_t tile[kVecTileW * epi::kVecPitch];
+  __shared__ __align__(16) uint8_t tile[kTileW * epi::kVecPitch];
   __shared__ float4 s_coef[64];
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < p.C; c += 256) bn_update_running(p.bn[0], c, p.count, p.momentum);
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) preact_fwd_kernel(const __grid_constant__
     tile_coefs(p, ti, 0, s_coef);
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kTileW / 32; ++k) {
       int cl, wl, c, t;
       item_decode(p, ti, k, &cl, &wl, &c, &t);
       float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(256) preact_fwd_kernel(const __grid_constant__
       tile_put8(tile, wl, cl, pack8(x));
     }
     __syncthreads();
-    vec_tile_store_cl(tile, p.out_cl[0], (long long)ti.n * p.T, ti.wt * kVecTileW, p.T, p.Cp, ti.ct);
+    epi::vec_tile_store_cl<kTileW>(tile, p.out_cl[0], (long long)ti.n * p.T, ti.wt * kTileW, p.T, p.Cp, ti.ct);
     __syncthreads();
   }
 }
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) preact_fwd_kernel(const __grid_constant__
 __global__ void __launch_bounds__(256) gate_fwd_kernel(const __grid_constant__ GlueParams p) {
   pdl_trigger();
   pdl_wait();
-  __shared__ __align__(16) uint8_t tile[kVecTileW * epi::kVecPitch];
+  __shared__ __align__(16) uint8_t tile[kTileW * epi::kVecPitch];
   __shared__ float4 s_coef[2][64];
   const unsigned long long seed = p.seed_ptr ? (unsigned long long)*p.seed_ptr : 0ULL;
   if (blockIdx.x == 0)
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const __grid_constant__ G
     tile_coefs(p, ti, 1, s_coef[1]);
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kTileW / 32; ++k) {
       int cl, wl, c, t;
       item_decode(p, ti, k, &cl, &wl, &c, &t);
       float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const __grid_constant__ G
       tile_put8(tile, wl, cl, pack8(y));
     }
     __syncthreads();
-    vec_tile_store_cl(tile, p.out_cl[0], (long long)ti.n * p.T, ti.wt * kVecTileW, p.T, p.Cp, ti.ct);
+    epi::vec_tile_store_cl<kTileW>(tile, p.out_cl[0], (long long)ti.n * p.T, ti.wt * kTileW, p.T, p.Cp, ti.ct);
     __syncthreads();
   }
 }
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(256) gate_bwd_reduce_kernel(const __grid_const
 __global__ void __launch_bounds__(256) gate_bwd_apply_kernel(const __grid_constant__ GlueParams p) {
   pdl_trigger();
   pdl_wait();
-  __shared__ __align__(16) uint8_t tile[2][kVecTileW * epi::kVecPitch];
+  __shared__ __align__(16) uint8_t tile[2][kTileW * epi::kVecPitch];
   __shared__ float4 s_coef[2][64];
   const unsigned long long seed = p.seed_ptr ? (unsigned long long)*p.seed_ptr : 0ULL;
   const float inv_count = (float)p.inv_count;
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(256) gate_bwd_apply_kernel(const __grid_consta
     tile_coefs(p, ti, 1, s_coef[1]);
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kTileW / 32; ++k) {
       int cl, wl, c, t;
       item_decode(p, ti, k, &cl, &wl, &c, &t);
       float df[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -365,8 +366,8 @@ __global__ void __launch_bounds__(256) gate_bwd_apply_kernel(const __grid_consta
       tile_put8(tile[1], wl, cl, pack8(dg));
     }
     __syncthreads();
-    vec_tile_store_cl(tile[0], p.out_cl[0], (long long)ti.n * p.T, ti.wt * kVecTileW, p.T, p.Cp, ti.ct);
-    vec_tile_store_cl(tile[1], p.out_cl[1], (long long)ti.n * p.T, ti.wt * kVecTileW, p.T, p.Cp, ti.ct);
+    epi::vec_tile_store_cl<kTileW>(tile[0], p.out_cl[0], (long long)ti.n * p.T, ti.wt * kTileW, p.T, p.Cp, ti.ct);
+    epi::vec_tile_store_cl<kTileW>(tile[1], p.out_cl[1], (long long)ti.n * p.T, ti.wt * kTileW, p.T, p.Cp, ti.ct);
     __syncthreads();
   }
 }
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(256) preact_bwd_reduce_kernel(const __grid_con
 __global__ void __launch_bounds__(256) preact_bwd_apply_kernel(const __grid_constant__ GlueParams p) {
   pdl_trigger();
   pdl_wait();
-  __shared__ __align__(16) uint8_t tile[kVecTileW * epi::kVecPitch];
+  __shared__ __align__(16) uint8_t tile[kTileW * epi::kVecPitch];
   __shared__ float4 s_coef[64];
   const float inv_count = (float)p.inv_count;
   for (long long blk = blockIdx.x; blk < p.total_blocks; blk += gridDim.x) {
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(256) preact_bwd_apply_kernel(const __grid_cons
     tile_coefs(p, ti, 0, s_coef);
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kTileW / 32; ++k) {
       int cl, wl, c, t;
       item_decode(p, ti, k, &cl, &wl, &c, &t);
       float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(256) preact_bwd_apply_kernel(const __grid_cons
     }
     if (p.out_cl[0]) {
       __syncthreads();
-      vec_tile_store_cl(tile, p.out_cl[0], (long long)ti.n * p.T, ti.wt * kVecTileW, p.T, p.Cp, ti.ct);
+      epi::vec_tile_store_cl<kTileW>(tile, p.out_cl[0], (long long)ti.n * p.T, ti.wt * kTileW, p.T, p.Cp, ti.ct);
     }
     __syncthreads();
   }
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(256) preact_bwd_apply_kernel(const __grid_cons
 
 // ---- launchers -------------------------------------------------------------------------------------------------
 static int tile_grid(tcn::GlueParams& p) {
-  p.tiles_t = (p.T + epi::kVecTileW - 1) / epi::kVecTileW;
+  p.tiles_t = (p.T + tcn::kTileW - 1) / tcn::kTileW;
   p.tiles_c = (p.Cp + 63) / 64;
   p.total_blocks = (long long)p.tiles_t * p.tiles_c * p.N;
   const long long cap = 148LL * 16;

@@ -40,6 +40,18 @@ __device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {
 }
 // counter-based dropout mask: the same (seed, salt, element) always gives the same decision, so the backward
 // pass needs no stored mask beyond the keep bit
+// the per-element variant of the CNN tail: the (seed, salt) part is mixed once per thread (dropout_key), an element then
+// costs two 32-bit multiplies (lowbias32 finaliser) instead of two 64-bit ones
+__device__ __forceinline__ uint32_t dropout_key(unsigned long long seed, uint32_t salt) {
+  return hash_u32((seed * 0x9E3779B97F4A7C15ULL) ^ ((unsigned long long)salt << 44));
+}
+__device__ __forceinline__ bool dropout_keep_fast(uint32_t key, long long elem, uint32_t thresh) {
+  uint32_t x = (uint32_t)elem ^ key ^ ((uint32_t)((unsigned long long)elem >> 32) * 0x27d4eb2fu);
+  x ^= x >> 16; x *= 0x7feb352du;
+  x ^= x >> 15; x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x >= thresh;
+}
 __device__ __forceinline__ bool dropout_keep(unsigned long long seed, uint32_t salt, long long elem, uint32_t thresh) {
   return hash_u32((seed * 0x9E3779B97F4A7C15ULL) ^ ((unsigned long long)salt << 44) ^ (unsigned long long)elem) >= thresh;
 }
@@ -53,13 +65,14 @@ __device__ __forceinline__ uint32_t vec_tile_off(int wl, int byte_in_row) {
   return (uint32_t)(wl * kVecPitch + (byte_in_row ^ (((wl >> 3) & 15) << 3)));
 }
 
+template <int ROWS = kVecTileW>
 __device__ __forceinline__ void vec_tile_store_cl(const uint8_t* tile, __nv_bfloat16* dst_cl, long long row0,
                                                   int w_base, int W, int Cp, int ct) {
   // thread -> (w = tid / 8 + 32 k, channels 8 (tid % 8) ... + 7)
   const int c0 = (threadIdx.x & 7) * 8;
   if (ct * 64 + c0 >= Cp) return;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < ROWS / 32; ++k) {
     const int wl = (threadIdx.x >> 3) + 32 * k;
     const int w = w_base + wl;
     if (w < W) {
