@@ -167,6 +167,38 @@ __global__ void __launch_bounds__(256) stage_operand_kernel(const float* __restr
   }
 }
 
+// Narrow single-component operands (the model input: C <= 16 channels padded to 16): a thread owns 4 consecutive w
+// of every channel -- float4 loads, coalesced per channel row -- and writes the 4 channels-last rows (32 B each) as
+// one contiguous 128-byte run; no shared memory.  W % 4 == 0.
+template <int C>
+__global__ void __launch_bounds__(256) stage_narrow_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst_cl,
+                                                           long long planes /* N */, int H, int W) {
+  const long long quads_per_plane = (long long)H * W / 4;
+  const long long total = planes * quads_per_plane;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    const long long n = q / quads_per_plane, pos = (q - n * quads_per_plane) * 4;     // pos = h * W + w
+    const float* base = src + n * C * (long long)H * W + pos;
+    float4 v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = __ldg(reinterpret_cast<const float4*>(base + (long long)c * H * W));
+    uint4* out = reinterpret_cast<uint4*>(dst_cl + (n * (long long)H * W + pos) * 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t wv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c0 = 2 * k, c1 = 2 * k + 1;
+        const float a = c0 < C ? (j == 0 ? v[c0 < C ? c0 : 0].x : j == 1 ? v[c0 < C ? c0 : 0].y : j == 2 ? v[c0 < C ? c0 : 0].z : v[c0 < C ? c0 : 0].w) : 0.f;
+        const float b = c1 < C ? (j == 0 ? v[c1 < C ? c1 : 0].x : j == 1 ? v[c1 < C ? c1 : 0].y : j == 2 ? v[c1 < C ? c1 : 0].z : v[c1 < C ? c1 : 0].w) : 0.f;
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+        wv[k] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      out[2 * j] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      out[2 * j + 1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+    }
+  }
+}
+
 }  // namespace simt
 
 // ---- host launchers ------------------------------------------------------------------------------
@@ -233,6 +265,17 @@ int launch_stage_operand(const float* src, void* dst_cl, void* dst_nchw16, const
                          int h, int w, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(dst_cl) & 15) || (reinterpret_cast<uintptr_t>(dst_nchw16) & 15))
     return fail(SELDQ_ERR_INVALID, "bf16 operand buffers must be 16-byte aligned");
+  if (l.nc == 1 && l.Cp == 16 && !dst_nchw16 && dst_cl && (w & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+      (c == 8 || c == 16)) {
+    const long long total = (long long)n * h * w / 4;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    if (c == 8)
+      simt::stage_narrow_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_cl), n, h, w);
+    else
+      simt::stage_narrow_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_cl), n, h, w);
+    return check_launch("stage_narrow_kernel");
+  }
   const int pitch = nchw16_pitch(w);
   const int tiles_w = (pitch + 31) / 32, tiles_c = (l.Cp + 63) / 64;
   const long long total = (long long)tiles_w * tiles_c * h * n;

@@ -258,9 +258,10 @@ class ConvTC_Block(nn.Module):
 
     def forward(self, x):
         x = self._cnn_forward(x)                          # (B, C, F', T)
-        x = x.permute(0, 3, 1, 2)                         # (B, T, C, F')
-        x = x.reshape(x.shape[0], self.time_pooled_size, -1)
-        x = x.permute(0, 2, 1)                            # (B, C*F', T): channel order c*F' + f
+        # model.py:301-310 permutes to (B, T, C, F'), flattens (C, F') and permutes back: channel c*F' + f, time last,
+        # which is this view of the contiguous CNN output (no copy)
+        assert x.shape[3] == self.time_pooled_size
+        x = x.reshape(x.shape[0], x.shape[1] * x.shape[2], x.shape[3])
         x = self.tcn(x)
         return x.permute(0, 2, 1)                         # (B, T/8, V)
 
