@@ -460,7 +460,9 @@ def _linear_as_conv(x, weights, bias, algebra):
     (SELDQ_ALG_DQ_LINEAR for dual_quaternion_linear; quaternion_linear shares the convolution's table)."""
     conv_alg = ALG_DQ_LINEAR if algebra == ALG_DQ else algebra
     global _PACK_CACHE
-    ws = tuple(w.t().contiguous().unsqueeze(-1) for w in weights)          # (in/nc, out/nc) -> (out/nc, in/nc, 1)
+    # (in/nc, out/nc) -> (out/nc, in/nc, 1): one stacked transpose for all compact tensors (2 launches, not 2 per
+    # tensor; the slices of the stacked result are contiguous)
+    ws = tuple(w.unsqueeze(-1) for w in torch.stack(tuple(weights), 0).transpose(1, 2).contiguous().unbind(0))
     prev, _PACK_CACHE = _PACK_CACHE, False
     try:
         y = _BlockConv.apply(x.t().contiguous().unsqueeze(0), bias, 1, 0, 1, conv_alg, PREC_BF16, *ws)
