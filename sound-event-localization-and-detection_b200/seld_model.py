@@ -27,6 +27,9 @@ from . import layers as _default_layers
 # 'fp32' mode so that those layers keep the reference's arithmetic, on in the tensor-core 'bf16' mode.
 _F._apply_tf32_policy()
 
+import os as _os
+# SELDQ_ATTN_BF16=1: in 'bf16' mode MultiHeadAttention feeds bf16 operands to the library's fused attention kernel
+ATTN_BF16 = _os.environ.get("SELDQ_ATTN_BF16", "0") == "1"
 _BN_TCN = {'BN', 'BN_on_TCN', 'BNonTCN'}
 _BN_CNN = {'BN', 'BN_on_CNN', 'BNonCNN'}
 _TWO_BRANCH = {'2Parallel', '2BParallel', '2ParallelBranches', '2PB'}
@@ -70,7 +73,11 @@ class MultiHeadAttention(nn.Module):
         kp = self._split(self.keys(k.permute(0, 2, 1)))
         qp = self._split(self.queries(q.permute(0, 2, 1)))
         attn_mask = None if mask is None else (mask != 0)
-        out = tF.scaled_dot_product_attention(qp, kp, vp, attn_mask=attn_mask)    # scale = 1/sqrt(head_dim)
+        if ATTN_BF16 and q.is_cuda and _F.get_precision() == "bf16" and attn_mask is None:
+            # tensor-core mode: bf16 operands into the library's fused attention kernel (no S x S tensor in HBM)
+            out = tF.scaled_dot_product_attention(qp.bfloat16(), kp.bfloat16(), vp.bfloat16()).float()
+        else:
+            out = tF.scaled_dot_product_attention(qp, kp, vp, attn_mask=attn_mask)    # scale = 1/sqrt(head_dim)
         out = out.transpose(1, 2).reshape(n, length, self.num_heads * self.head_dim)
         return self.fc_out(out)
 
