@@ -24,7 +24,7 @@
 // activation is one 16-channel-padded component and the signed expanded tile is built in shared memory
 // only, one MMA spanning all out channels.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// Warp roles (224 threads): warp 0 = TMA producer, warps 1 and 6 = MMA issuers (warp 1 owns the TMEM allocation),
 // warps 2..5 = epilogue (TMEM -> registers -> coalesced global stores, + bias).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -49,7 +49,7 @@ __device__ __forceinline__ int unit_of_round(int round, int total_units) {
 }
 
 template <int GC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFpropThreads, 1)
 qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
@@ -71,13 +71,13 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
 
   // ---- one-time setup ---------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < p.chunks * p.slabs_per_chunk * p.ncomp_out; i += kThreads) op_tbl_s[i] = p.op_tbl[i];
+  for (int i = threadIdx.x; i < p.chunks * p.slabs_per_chunk * p.ncomp_out; i += kFpropThreads) op_tbl_s[i] = p.op_tbl[i];
   if (p.dense) {
     // signed expanded weight -> bf16 B tiles.  Tile (tap, j) holds B[n][k], n = out channel, k = in channels
     // 16 j ... 16 j + 15; UMMA K-major / no swizzle: core matrix = 8 rows x 16 B, LBO (K step) = NBp*16,
     // SBO (8 rows) = 128
     const int items = p.ntaps * p.J * 2 * p.NBp;          // one item = 8 consecutive k of one row
-    for (int it = threadIdx.x; it < items; it += kThreads) {
+    for (int it = threadIdx.x; it < items; it += kFpropThreads) {
       int r = it;
       const int n = r % p.NBp; r /= p.NBp;
       const int kc = r & 1; r >>= 1;
@@ -96,8 +96,9 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     ptx::fence_proxy_async();
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 4); }
+    // two MMA-issuing warps: each arrives once per stage / accumulator
+    for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 2); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 2); ptx::mbar_init(&tempty_bar[i], 4); }
     ptx::mbar_init(w_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tm_in);
@@ -144,19 +145,25 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer ==============================================================================
+  } else if (warp == 1 || warp == 6) {
+    // ===== MMA issuers =============================================================================
     // Lane-parallel issue: the MMAs of one stage (<= 32: slabs x out components of the group, structural zero
-    // blocks left out) are dealt to lanes 0 .. n-1 in (slab, component) order.  All lanes build their
-    // descriptors at once; the tcgen05.mma under the lane predicate then costs one short elect-and-issue round
-    // per active lane (~50 cycles per MMA instead of ~100 for descriptor arithmetic on the uniform datapath;
-    // tools/umma_rate.py).  The accumulator-initialising MMAs of a unit (tap 0, one per out component, distinct
-    // columns) go through their own issue site ahead of the accumulating ones.
+    // blocks left out) form a dense list in (slab, component) order.  All lanes build their descriptors at once;
+    // the tcgen05.mma under the lane predicate then costs one short elect-and-issue round per active lane (~40
+    // cycles per MMA instead of ~100 for descriptor arithmetic on the uniform datapath; tools/umma_rate.py).
+    // TWO warps share the list (even / odd entries) and issue concurrently: accumulating MMAs commute, so only
+    // the accumulator-initialising ones (tap 0, one per out component, distinct columns) need an order -- they go
+    // first, from both warps, and a 64-thread named barrier separates them from the rest of that stage.
+    // The accumulate flag of an issue site must be warp-uniform (ptxas derives the instruction's predicate with a
+    // vote over the issuing lanes), hence the separate sites.  tcgen05.commit tracks the MMAs of the executing
+    // thread; the tensor pipe retires in order, so each warp's commit comes from the lane that issued last.
     {
+      const int me = warp == 1 ? 0 : 1;
       const uint64_t a_hi = ptx::make_smem_desc_hi(16, p.a_sbo, p.a_swz);                 // K-major, swizzled
       const uint64_t b_hi = ptx::make_smem_desc_hi((uint32_t)p.NBp * 16u, 128, ptx::kSwizzleNone);
       const uint32_t a_base = ptx::smem_u32(a_ring), b_lo16 = ptx::smem_u32(b_img) >> 4;
       const int lanes_per_stage = p.slabs_per_chunk * GC;
+      const int my_entry = 2 * lane + me;
       if (!p.dense) ptx::mbar_wait(w_bar, 0);
       uint32_t slot = 0, parity = 0, it = 0;
       for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
@@ -170,15 +177,18 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         ptx::tc_fence_after();
         const uint32_t d_unit = tmem_base + as * acc_cols;
         const uint2* tbl_g = op_tbl_s + (size_t)p.group_order[gi] * p.chunks * lanes_per_stage;
-        bool closes = false;
+        int last_closer = -1;                                  // lane that issued this warp's last MMA of the unit
         for (int c = 0; c < p.chunks; ++c) {
           if (!((mask >> c) & 1u)) continue;
           // per chunk: this lane's MMA (the same for every tap up to the tap's weight-tile offset)
           uint2 e = make_uint2(0u, 0u);
-          if (lane < lanes_per_stage) e = tbl_g[c * lanes_per_stage + lane];
+          if (my_entry < lanes_per_stage) e = tbl_g[c * lanes_per_stage + my_entry];
           const bool valid = (int)e.x < 0;
           const bool first = valid && (e.x & (1u << 30)) != 0u;
-          closes = (e.x & (1u << 29)) != 0u;                   // last MMA of the stage: this lane commits
+          const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+          const bool any = vmask != 0u;
+          const int closer = any ? 31 - __clz((int)vmask) : -1;
+          if (any) last_closer = closer;
           const uint32_t a_off16 = ((e.x >> 16) & 3u) * 2u;
           const uint32_t d_lane = d_unit + ((e.x >> 20) & 7u) * (uint32_t)p.NBp;
           uint32_t b16 = b_lo16 + (e.x & 0x3fffu);
@@ -187,30 +197,35 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
             const uint64_t b_desc = b_hi | (uint64_t)(b16 & 0x3fffu);
             ptx::mbar_wait(&full_bar[slot], parity);
             ptx::tc_fence_after();
-            // The accumulate flag of an issue site must be warp-uniform (ptxas derives the instruction's predicate
-            // with a vote over the issuing lanes), so the accumulator-initialising MMAs of a unit (tap 0, one
-            // per out component, distinct columns) have their own site ahead of the accumulating ones.
             if (tap == 0) {
               if (first) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 0u);
               __syncwarp();
+              asm volatile("bar.sync 2, 64;" ::: "memory");      // both warps' initialising MMAs are issued
               if (valid && !first) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 1u);
             } else {
               if (valid) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 1u);
             }
             __syncwarp();
-            // tcgen05.commit tracks the MMAs of the executing thread; the tensor pipe retires in order, so the
-            // commit of the lane that issued last covers the whole stage
-            if (closes) ptx::umma_commit(&empty_bar[slot]);
+            if (any) {
+              if (lane == closer) ptx::umma_commit(&empty_bar[slot]);
+            } else if (lane == 0) {
+              ptx::mbar_arrive(&empty_bar[slot]);               // nothing of this warp reads the slot
+            }
             __syncwarp();
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }
         }
-        if (closes) ptx::umma_commit(&tfull_bar[as]);          // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (one arrival per MMA warp)
+        if (last_closer >= 0) {
+          if (lane == last_closer) ptx::umma_commit(&tfull_bar[as]);
+        } else if (lane == 0) {
+          ptx::mbar_arrive(&tfull_bar[as]);
+        }
         __syncwarp();
         ++it;
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 5) {
     // ===== epilogue: TMEM -> registers -> global ===================================================
     pdl_wait();
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
@@ -636,7 +651,7 @@ int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* ho
   }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "fprop smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
-  const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(cl::kThreads), smem, st, tm, p);
+  const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(cl::kFpropThreads), smem, st, tm, p);
   if (le != cudaSuccess) return fail(SELDQ_ERR_CUDA, "qconv_cl_fprop_kernel: %s", cudaGetErrorString(le));
   return check_launch("qconv_cl_fprop_kernel");
 }
