@@ -24,7 +24,7 @@
 // activation is one 16-channel-padded component and the signed expanded tile is built in shared memory
 // only, one MMA spanning all out channels.
 //
-// Warp roles (224 threads): warp 0 = TMA producer, warps 1 and 6 = MMA issuers (warp 1 owns the TMEM allocation),
+// Warp roles: warp 0 = TMA producer, warps 1 and 6.. = MMA issuers (kMmaWarps; warp 1 owns the TMEM allocation),
 // warps 2..5 = epilogue (TMEM -> registers -> coalesced global stores, + bias).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -97,8 +97,8 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   }
   if (threadIdx.x == 0) {
     // two MMA-issuing warps: each arrives once per stage / accumulator
-    for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 2); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 2); ptx::mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], kMmaWarps); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], kMmaWarps); ptx::mbar_init(&tempty_bar[i], 4); }
     ptx::mbar_init(w_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tm_in);
@@ -145,25 +145,25 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         }
       }
     }
-  } else if (warp == 1 || warp == 6) {
+  } else if (warp == 1 || warp >= 6) {
     // ===== MMA issuers =============================================================================
     // Lane-parallel issue: the MMAs of one stage (<= 32: slabs x out components of the group, structural zero
     // blocks left out) form a dense list in (slab, component) order.  All lanes build their descriptors at once;
     // the tcgen05.mma under the lane predicate then costs one short elect-and-issue round per active lane (~40
     // cycles per MMA instead of ~100 for descriptor arithmetic on the uniform datapath; tools/umma_rate.py).
-    // TWO warps share the list (even / odd entries) and issue concurrently: accumulating MMAs commute, so only
+    // kMmaWarps warps share the list (entry i goes to warp i mod kMmaWarps) and issue concurrently: accumulating MMAs commute, so only
     // the accumulator-initialising ones (tap 0, one per out component, distinct columns) need an order -- they go
-    // first, from both warps, and a 64-thread named barrier separates them from the rest of that stage.
+    // first, from all warps, and a named barrier separates them from the rest of that stage.
     // The accumulate flag of an issue site must be warp-uniform (ptxas derives the instruction's predicate with a
     // vote over the issuing lanes), hence the separate sites.  tcgen05.commit tracks the MMAs of the executing
     // thread; the tensor pipe retires in order, so each warp's commit comes from the lane that issued last.
     {
-      const int me = warp == 1 ? 0 : 1;
+      const int me = warp == 1 ? 0 : warp - 5;
       const uint64_t a_hi = ptx::make_smem_desc_hi(16, p.a_sbo, p.a_swz);                 // K-major, swizzled
       const uint64_t b_hi = ptx::make_smem_desc_hi((uint32_t)p.NBp * 16u, 128, ptx::kSwizzleNone);
       const uint32_t a_base = ptx::smem_u32(a_ring), b_lo16 = ptx::smem_u32(b_img) >> 4;
       const int lanes_per_stage = p.slabs_per_chunk * GC;
-      const int my_entry = 2 * lane + me;
+      const int my_entry = kMmaWarps * lane + me;
       if (!p.dense) ptx::mbar_wait(w_bar, 0);
       uint32_t slot = 0, parity = 0, it = 0;
       for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
@@ -200,7 +200,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
             if (tap == 0) {
               if (first) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 0u);
               __syncwarp();
-              asm volatile("bar.sync 2, 64;" ::: "memory");      // both warps' initialising MMAs are issued
+              asm volatile("bar.sync 2, %0;" ::"n"(32 * kMmaWarps) : "memory");      // every warp's initialising MMAs are issued
               if (valid && !first) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 1u);
             } else {
               if (valid) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 1u);

@@ -20,7 +20,8 @@ namespace cl {
 
 constexpr int kTileM = 128;     // positions per accumulator tile (TMEM lanes)
 constexpr int kThreads = 192;   // wgrad: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kFpropThreads = 224;   // fprop: + warp 6, the second MMA-issuing warp
+constexpr int kMmaWarps = 4;          // fprop: MMA-issuing warps (warp 1 and warps 6 ...)
+constexpr int kFpropThreads = 192 + 32 * (kMmaWarps - 1);
 constexpr int kMaxTaps = 9;
 constexpr int kMaxStages = 8;
 constexpr int kOpTableEntries = 512;  // (16-channel slab, out component) pairs: 1024 padded channels x 8
