@@ -137,3 +137,39 @@ print("OK", m.model_name)
 ''' % (ROOT, PKG, os.path.join(ROOT, "tests", "golden", "model_dq_tiny.npz"))
     out = subprocess.check_output([sys.executable, "-c", code], cwd="/tmp").decode()
     assert "OK DualQSELD-TCN-PHI-S1_BN_RF287_10RB_tiny" in out
+
+
+def test_fused_paths_decline_what_they_do_not_serve(seldq):
+    """fused.cnn_stack_supported / tcn_stack_supported gate the fused kernels: CPU tensors, eval mode and fp32
+    precision fall through to the layer-by-layer modules (which raise on CPU: there is no CPU path)."""
+    import importlib
+    import torch
+    model_mod = importlib.import_module(seldq.__name__ + ".seld_model")
+    blk = model_mod.TC_Block(in_channels=128, domain="DQ", G=128, U=128, V=[128, 128], D=[2], spatial_dropout_rate=0.5,
+                             use_bias_conv=False, batch_norm="BN")
+    x = torch.zeros(1, 128, 64)
+    assert not seldq.fused.tcn_stack_supported(blk.ResBlocks, x, True)            # CPU tensor
+    assert not seldq.fused.tcn_stack_supported(blk.ResBlocks, x, False)           # eval mode
+    nobn = model_mod.TC_Block(in_channels=128, domain="DQ", G=128, U=128, V=[128, 128], D=[1], use_bias_conv=False,
+                              batch_norm="noBN")
+    assert not seldq.fused.tcn_stack_supported(nobn.ResBlocks, x, True)
+
+
+def test_trainer_keeps_parameters_and_gradients_in_flat_buffers(seldq):
+    """trainer.FlatGradBucket: every parameter / gradient is a view into ONE tensor (single all-reduce, single-tensor
+    Adam); an optimiser step through the flat parameter moves the module's parameters."""
+    import importlib
+    import torch
+    trainer_mod = importlib.import_module(seldq.__name__ + ".trainer")
+    m = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    before = [p.detach().clone() for p in m.parameters()]
+    tr = trainer_mod.Trainer(m, lr=1e-2, n_sed=1)
+    base = tr.bucket.flat_param.data.untyped_storage().data_ptr()
+    for p, b in zip(m.parameters(), before):
+        assert torch.equal(p.detach(), b)
+        assert p.data.untyped_storage().data_ptr() == base
+        assert p.grad.untyped_storage().data_ptr() == tr.bucket.flat.untyped_storage().data_ptr()
+    tr.bucket.zero()
+    m(torch.ones(5, 4)).sum().backward()
+    tr.optimizer.step()
+    assert all(not torch.equal(p.detach(), b) for p, b in zip(m.parameters(), before))

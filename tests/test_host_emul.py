@@ -113,3 +113,29 @@ def test_emulated_stft_kernel_matches_golden(emul, name):
         dphi = np.abs(np.angle(np.exp(1j * (out[C:].astype(np.float64) - d["out"][C:]))))
         # phase of a bin is only defined to ~eps_fp32 * max|Z| / |Z|
         assert (dphi * mag / mag.max()).max() < 1e-5
+
+
+def test_dq_linear_runs_as_a_1x1_convolution_with_its_own_block_table(emul):
+    """functional._linear_as_conv: dual_quaternion_linear (dual_quaternion_ops.py:156-203) on (rows, in) equals a
+    1x1 convolution over the transposed matrices with the block table SELDQ_ALG_DQ_LINEAR (= 3) and transposed
+    compact weights; checked here through the emulated FFMA kernels, which read the same table."""
+    meta, d = load_golden("linear_dq_c48")
+    x = np.ascontiguousarray(d["x"], np.float32)                      # (rows, in)
+    gy = np.ascontiguousarray(d["gy"], np.float32)                    # (rows, out)
+    rows, fin = x.shape
+    fout = gy.shape[1]
+    ws = [np.ascontiguousarray(d["w%d" % i].T[:, :, None], np.float32) for i in range(8)]     # (out/8, in/8, 1)
+    desc = ConvDesc(3, 0, 1, 1, fin, fout, 1, rows, 1, 1, 1, 1, 0, 0, 1, 1)
+    xc = np.ascontiguousarray(x.T[None], np.float32)                  # (1, in, rows)
+    y = np.full((1, fout, rows), np.nan, np.float32)
+    b = np.ascontiguousarray(d["b"], np.float32)
+    assert emul.emul_conv(ctypes.byref(desc), 0, fptr(xc), ptr_array(ws), fptr(b), fptr(y)) == 0
+    assert A.rel_err(y[0].T, d["y"]) < 1e-5
+    gyc = np.ascontiguousarray(gy.T[None], np.float32)
+    gx = np.full(xc.shape, np.nan, np.float32)
+    assert emul.emul_conv(ctypes.byref(desc), 1, fptr(gyc), ptr_array(ws), None, fptr(gx)) == 0
+    assert A.rel_err(gx[0].T, d["gx"]) < 1e-5
+    gws = [np.zeros_like(w) for w in ws]
+    assert emul.emul_conv_wgrad(ctypes.byref(desc), fptr(xc), fptr(gyc), ptr_array(gws), 2) == 0
+    for i in range(8):
+        assert A.rel_err(gws[i][:, :, 0].T, d["gw%d" % i]) < 1e-5, i

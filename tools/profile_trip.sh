@@ -15,7 +15,11 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_be
 timeout 300 python tools/step_profile.py --top 60 2>&1 | grep -v "Warn\|_warn\|_ACCUMULATE" > $O/${TAG}_step_profile_b1.txt; echo "step profile rc=$?"
 timeout 300 python tools/kernel_bench.py --skip-conv --out $O/${TAG}_stft.json > $O/${TAG}_stft.log 2>&1; echo "stft rc=$?"; grep stft $O/${TAG}_stft.log | cut -c1-160
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_ncu_launches.csv python tools/ncu_step.py --stft > $O/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  -k regex:"qconv_cl_fprop|qconv_cl_wgrad|first_layer_bwd|cnn_tail_fwd_vec|cnn_tail_bwd_apply|stft_magphase|gate_fwd_kernel" \
-  -c 40 -o $O/${TAG}_ncu_full -f python tools/ncu_step.py --stft > $O/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+# full captures of the top kernels, a few launches each (ncu replays every kernel ~40 times)
+i=0
+for spec in "qconv_cl_fprop_kernel:14" "qconv_cl_wgrad_kernel:6" "first_layer_bwd_kernel:1" "cnn_tail_fwd_vec_kernel:2" "cnn_tail_bwd_apply_vec_kernel:1" "stft_magphase_kernel:2" "gate_fwd_kernel:1" "gate_bwd_apply_kernel:1"; do
+  k="${spec%%:*}"; c="${spec##*:}"; i=$((i+1))
+  SELDQ_PDL=0 SELDQ_SIDE_WGRAD=0 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
+    -k regex:"$k" -c $c -o $O/${TAG}_ncu_full_$i -f python tools/ncu_step.py --stft > $O/${TAG}_ncu_full_$i.log 2>&1; echo "ncu full $k rc=$?"
+done
 ls -la $O/${TAG}_* | cut -c30-
