@@ -134,9 +134,11 @@ int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
                    const float* const* host_w, const void* packed_w, const float* bias, float* y,
                    void* workspace, size_t workspace_bytes, void* stream);
 
-/* same, but y is written in bf16 (same NCHW order): the form the fused CNN-block glue below consumes */
+/* same (bf16 operands), but y is written once in 16 bits, IEEE fp16 saturating at +-65504, in the same NCHW order:
+ * the form the fused CNN-block glue below consumes.  fp16 and not bf16 because this tensor is only stored, never a
+ * tensor-core operand: the 8x finer rounding keeps the fused path inside the bf16 error budget. */
 int seldq_conv_fwd_bf16(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
-                        const float* const* host_w, const void* packed_w, const float* bias, void* y_bf16,
+                        const float* const* host_w, const void* packed_w, const float* bias, void* y_f16,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* gx = conv_transpose(gy, expand(w)) : gradient w.r.t. the input */
@@ -166,7 +168,7 @@ int seldq_conv_wgrad_pair(const seldq_conv_desc_t* d, const void* x_cl, const vo
  *   seldq_cnn_tail_fwd  z = dropout(max_{pool rows}(relu(BN(y)))) written as the channels-last bf16 operand of
  *                       the consuming convolution (z_cl, may be NULL) and / or as fp32 NCHW (z_f32, may be NULL);
  *                       idx gets one byte per pooled element (arg-max row | 0x80 if kept) for the backward pass;
- *                       ymax_bf16 (pooled shape, may be NULL) gets the conv output at the arg-max, which lets the
+ *                       ymax_f16 (pooled shape, may be NULL) gets the conv output at the arg-max, which lets the
  *                       backward reductions stream it instead of gathering from y.
  *                       seed: device counter the caller advances every step (needed iff drop_p > 0)
  *   seldq_cnn_tail_bwd  d(conv out) from gz (fp32, pooled NCHW): written as the pitched NCHW bf16 operand
@@ -179,14 +181,14 @@ typedef struct {
   float drop_p;
   uint32_t salt;          /* distinguishes the dropout streams of different layers */
 } seldq_cnn_tail_desc_t;
-int seldq_bn_stats(const void* src, int32_t is_bf16, int32_t n, int32_t c, int64_t plane, double* sums, void* stream);
+int seldq_bn_stats(const void* src, int32_t is_f16, int32_t n, int32_t c, int64_t plane, double* sums, void* stream);
 int seldq_bn_finalize(const double* sums, const float* gamma, const float* beta, int32_t c, double count, float eps,
                       float momentum, float* running_mean, float* running_var, float* coef, void* stream);
-int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* consumer, const void* y_bf16,
-                       const float* coef, const int64_t* seed, void* z_cl, float* z_f32, uint8_t* idx, void* ymax_bf16,
+int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* consumer, const void* y_f16,
+                       const float* coef, const int64_t* seed, void* z_cl, float* z_f32, uint8_t* idx, void* ymax_f16,
                        void* stream);
-int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* producer, const void* y_bf16,
-                       const float* coef, const uint8_t* idx, const void* ymax_bf16, const float* gz, double* dsums,
+int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* producer, const void* y_f16,
+                       const float* coef, const uint8_t* idx, const void* ymax_f16, const float* gz, double* dsums,
                        void* d_t16, void* d_cl, void* stream);
 
 /* First CNN block, backward.  The first convolution needs no input gradient, so d(conv out) has a single consumer,
@@ -199,7 +201,7 @@ int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* 
 int seldq_cnn_first_bwd_supported(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* conv);
 size_t seldq_cnn_first_bwd_workspace_bytes(const seldq_conv_desc_t* conv);
 int seldq_cnn_first_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* conv, const float* x,
-                        const void* y_bf16, const float* coef, const uint8_t* idx, const void* ymax_bf16,
+                        const void* y_f16, const float* coef, const uint8_t* idx, const void* ymax_f16,
                         const float* gz, double* dsums, float* const* host_gw, int32_t accumulate, void* workspace,
                         size_t workspace_bytes, void* stream);
 

@@ -18,9 +18,10 @@ import torch.nn.functional as F
 
 from oracle import cpu_model
 
-# True: 2-d convolutions also round their OUTPUT to bf16 (identity gradient), which is what the fused CNN-block
-# path does when it stores the conv output once in bf16 for BatchNorm / ReLU / max-pool (fused.py)
-STORE_CONV2D_BF16 = False
+# True: 2-d convolutions also round their OUTPUT to IEEE fp16 (identity gradient), which is what the fused
+# CNN-block path does when it stores the conv output once in 16 bits for BatchNorm / ReLU / max-pool (fused.py;
+# fp16 rather than bf16 because the tensor is only stored, never a tensor-core operand)
+STORE_CONV2D_F16 = False
 
 
 def _bf(t):
@@ -34,7 +35,7 @@ class Bf16OperandConv(torch.autograd.Function):
         ctx.args = (stride, pad, dil)
         fn = F.conv1d if x.dim() == 3 else F.conv2d
         y = fn(_bf(x), _bf(W), None, stride, pad, dil)
-        return _bf(y) if (x.dim() == 4 and STORE_CONV2D_BF16) else y
+        return y.to(torch.float16).to(y.dtype) if (x.dim() == 4 and STORE_CONV2D_F16) else y
 
     @staticmethod
     def backward(ctx, gy):
@@ -53,13 +54,13 @@ class Bf16OperandConv(torch.autograd.Function):
 class _Bf16Convs(object):
     """Context manager: the CPU port's convolutions round their operands to bf16."""
 
-    def __init__(self, store_conv2d_bf16=False):
-        self._store = store_conv2d_bf16
+    def __init__(self, store_conv2d_f16=False):
+        self._store = store_conv2d_f16
 
     def __enter__(self):
-        global STORE_CONV2D_BF16
+        global STORE_CONV2D_F16
         self._saved = cpu_model._conv
-        self._saved_flag, STORE_CONV2D_BF16 = STORE_CONV2D_BF16, self._store
+        self._saved_flag, STORE_CONV2D_F16 = STORE_CONV2D_F16, self._store
 
         def conv(x, weights, bias, stride, padding, dilation, algebra):
             y = Bf16OperandConv.apply(x, cpu_model.expand_weight_torch(weights, algebra), stride, padding, dilation)
@@ -70,10 +71,10 @@ class _Bf16Convs(object):
         return self
 
     def __exit__(self, *exc):
-        global STORE_CONV2D_BF16
+        global STORE_CONV2D_F16
         cpu_model._conv = self._saved
-        STORE_CONV2D_BF16 = self._saved_flag
+        STORE_CONV2D_F16 = self._saved_flag
 
 
-def bf16_operand_convs(store_conv2d_bf16=False):
-    return _Bf16Convs(store_conv2d_bf16)
+def bf16_operand_convs(store_conv2d_f16=False):
+    return _Bf16Convs(store_conv2d_f16)

@@ -149,13 +149,13 @@ def model_case(name, cfg, time_dim, B, seed):
         if p.grad is not None:
             d["ref32err/" + k] = np.float64(A.rel_err(p.grad.numpy(), d["grad/" + k]))
     # yardstick 2: an ideal bf16-operand implementation (oracle/bf16_emulation.py) of the same model
-    # (key bf16emu*), and the same with the 2-d conv outputs stored in bf16 as the fused CNN path does (bf16emu16*)
+    # (key bf16emu*), and the same with the 2-d conv outputs stored in fp16 as the fused CNN path does (bf16emu16*)
     from oracle import bf16_emulation, cpu_model
     for tag, store in (("bf16emu", False), ("bf16emu16", True)):
         me = cpu_model.build_model(time_dim=time_dim, spatial_dropout_rate=0, dropout_perc=0, **cfg)
         me.load_state_dict(sd32)
         me = me.double().train()
-        with bf16_emulation.bf16_operand_convs(store_conv2d_bf16=store):
+        with bf16_emulation.bf16_operand_convs(store_conv2d_f16=store):
             se, de = me(torch.tensor(x))
             cpu_model.seld_loss(se, de, torch.tensor(target)).backward()
         d[tag + "/sed"], d[tag + "/doa"] = se.detach().numpy(), de.detach().numpy()

@@ -28,6 +28,7 @@
 // warps 2..5 = epilogue (TMEM -> registers -> coalesced global stores, + bias).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "conv_cl.h"
@@ -38,6 +39,9 @@
 
 namespace seldq {
 namespace cl {
+
+// fp16 store of a convolution output, saturating (the value range of fp16 ends at 65504)
+__device__ __forceinline__ __half to_f16_sat(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
 
 // Unit schedule of a CTA: units are ordered heaviest group first; round r hands unit r*G + b to CTA b in even rounds
 // and r*G + (G-1-b) in odd rounds (snake order), so the few units of a last, partial round go to the CTAs that
@@ -251,7 +255,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
       const long long row_off = (long long)n * p.out_sN + (long long)h * p.out_sH + w;
       float* out_row = p.out + row_off;
-      __nv_bfloat16* out16_row = p.out16 + row_off;
+      __half* out16_row = p.out16 + row_off;
       for (int al = 0; al < GC; ++al) {
         const int ch_base = (group * GC + al) * p.Pc;
         for (int c0 = 0; c0 < p.Pc; c0 += 16) {
@@ -259,14 +263,14 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
           ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
           ptx::tmem_ld_wait();
           if (p.out16 && vec16) {
-            // bf16 output in the tensor's own NCHW order (fused CNN-block path, epilogue.cu): the warp's
+            // fp16 output in the tensor's own NCHW order (fused CNN-block path, epilogue.cu): the warp's
             // [32 w x 16 ch] block is transposed through shared memory and leaves as 16-byte pieces
             const int lim = p.Pc - c0;
             uint8_t* stg = out_stage[q];
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              *reinterpret_cast<__nv_bfloat16*>(stg + j * 64 + lane * 2) =
-                  __float2bfloat16_rn(__uint_as_float(v[j]) + ((p.bias && j < lim) ? __ldg(p.bias + ch_base + c0 + j) : 0.f));
+              *reinterpret_cast<__half*>(stg + j * 64 + lane * 2) =
+                  to_f16_sat(__uint_as_float(v[j]) + ((p.bias && j < lim) ? __ldg(p.bias + ch_base + c0 + j) : 0.f));
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -280,12 +284,12 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
             }
             __syncwarp();
           } else if (w_ok && p.out16) {
-            __nv_bfloat16* dst = out16_row + (long long)(ch_base + c0) * p.out_sC;
+            __half* dst = out16_row + (long long)(ch_base + c0) * p.out_sC;
             const int lim = p.Pc - c0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               if (j < lim)
-                *dst = __float2bfloat16_rn(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch_base + c0 + j) : 0.f));
+                *dst = to_f16_sat(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch_base + c0 + j) : 0.f));
               dst += p.out_sC;
             }
           } else if (w_ok) {
@@ -620,7 +624,7 @@ static int encode_cl_map(CUtensorMap* tm, const void* data, const cl::OperandLay
 }
 
 int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
-                    const float* bias, float* out, void* out_bf16, cudaStream_t st) {
+                    const float* bias, float* out, void* out_f16, cudaStream_t st) {
   FpropParams p;
   size_t smem = 0;
   int rc = plan_cl_fprop(g, &p, &smem);
@@ -634,7 +638,7 @@ int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* ho
   }
   p.bias = bias;
   p.out = out;
-  p.out16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.out16 = reinterpret_cast<__half*>(out_f16);
   p.out_sN = g.out_sN; p.out_sC = g.out_sC; p.out_sH = g.out_sH;
   const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, p.dense != 0);
   alignas(64) CUtensorMap tm;

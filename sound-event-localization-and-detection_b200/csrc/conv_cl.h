@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -66,7 +67,7 @@ struct FpropParams {
   const uint8_t* packed;        // pre-packed bf16 weight images (non-dense)
   const float* bias;
   float* out;                   // fp32 NCHW ...
-  __nv_bfloat16* out16;         // ... or, when not null, bf16 NCHW instead
+  __half* out16;                // ... or, when not null, IEEE fp16 NCHW instead (storage format of the fused CNN path)
   long long out_sN, out_sC, out_sH;
   int N, OH, OW;
   int tiles_w, total_tiles, ngroups, total_units;
@@ -133,7 +134,7 @@ size_t pack_table_entry_bytes();
 int fill_pack_table_entry(const ConvGeom& pass_geom, const float* const* host_w, void* packed, void* entry, int* items);
 int launch_pack_weights_multi(const void* dev_table, int count, int max_items, cudaStream_t st);
 int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
-                    const float* bias, float* out, void* out_bf16, cudaStream_t st);
+                    const float* bias, float* out, void* out_f16, cudaStream_t st);
 int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, float* const* host_gw,
                     cudaStream_t st, const void* gy2_nchw16 = nullptr, float* const* host_gw2 = nullptr);
 // fp32 NCHW -> CL operand (and, optionally, the pitched NCHW bf16 copy wgrad reads gy from)

@@ -2,7 +2,10 @@
 //
 //   CNN block   model.py:276-283   conv -> BatchNorm2d (batch statistics) -> ReLU -> MaxPool2d([p,1]) -> Dropout
 //
-// The convolution writes its output once, in bf16, in the tensor's own NCHW order.  Then
+// The convolution writes its output once, in 16 bits, in the tensor's own NCHW order.  The format is IEEE fp16
+// (10-bit mantissa), not bf16: this tensor is only stored, never fed to the tensor cores, its values are O(1)
+// pre-BatchNorm activations (the store saturates at +-65504), and the 8x finer rounding keeps the fused path's
+// distance to the fp32 reference at that of the layer-by-layer bf16 path instead of using up the 2e-2 budget.  Then
 //   bn_stats_kernel        per-channel sum / sum of squares (warp-shuffle + block reduction, one double
 //                          atomicAdd pair per block)
 //   bn_finalize_kernel     mean / rstd / affine coefficients per channel, running-statistics update
@@ -17,6 +20,7 @@
 // so the full-resolution fp32 tensors of the reference (944 MB per sample after the first convolution, read
 // and written by five separate PyTorch kernels) never exist.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "conv_cl.h"
@@ -30,7 +34,7 @@ namespace seldq {
 namespace epi {
 
 __device__ __forceinline__ float load_as_float(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float load_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float load_as_float(const __half* p) { return __half2float(*p); }
 
 // grid (C, N, splits): block (c, n, z) reduces elements [z*chunk, (z+1)*chunk) of plane (n, c)
 template <typename T>
@@ -48,10 +52,10 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ src
     const long long nv = (hi - lo) >> 3;
     for (long long i = threadIdx.x; i < nv; i += blockDim.x) {
       const uint4 q = __ldg(v + i);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h[j]);
+        const float2 f = __half22float2(h[j]);
         s1 += f.x + f.y;
         s2 += f.x * f.x + f.y * f.y;
       }
@@ -122,13 +126,13 @@ __global__ void __launch_bounds__(256) cnn_tail_fwd_kernel(const __grid_constant
       if (cp < p.Cp && ci < p.cc && w < p.W) {
         const int c = comp * p.cc + ci;
         const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
-        const __nv_bfloat16* src = p.y + (((long long)n * p.C + c) * p.H + (long long)hp * p.pool) * p.W + w;
+        const __half* src = p.y + (((long long)n * p.C + c) * p.H + (long long)hp * p.pool) * p.W + w;
         float best = -INFINITY;
         int arg = 0;
-        __nv_bfloat16 yb = src[0];
+        __half yb = src[0];
         for (int j = 0; j < p.pool; ++j) {
-          const __nv_bfloat16 yj = src[(long long)j * p.W];
-          const float v = cf.x * __bfloat162float(yj) + cf.y;
+          const __half yj = src[(long long)j * p.W];
+          const float v = cf.x * __half2float(yj) + cf.y;
           if (v > best || v != v) { best = v; arg = j; yb = yj; }
         }
         const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
@@ -171,14 +175,14 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_reduce_kernel(const __grid_c
   const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
   const float scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const long long base = ((long long)n * p.C + c) * plane;
-  const __nv_bfloat16* y = p.y + ((long long)n * p.C + c) * (long long)p.H * p.W;
+  const __half* y = p.y + ((long long)n * p.C + c) * (long long)p.H * p.W;
   float s1 = 0.f, s2 = 0.f;
   for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const uint8_t id = p.idx[base + i];
     if (id & 0x80) {
       const int hp = (int)(i / p.W), w = (int)(i - (long long)hp * p.W);
       const float g = __ldg(p.gz + base + i) * scale;
-      const float yv = __bfloat162float(p.ymax ? p.ymax[base + i] : y[((long long)hp * p.pool + (id & 7)) * p.W + w]);
+      const float yv = __half2float(p.ymax ? p.ymax[base + i] : y[((long long)hp * p.pool + (id & 7)) * p.W + w]);
       s1 += g;
       s2 += g * (yv - cf.z) * cf.w;
     }
@@ -211,13 +215,13 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_reduce_vec_kernel(const __gr
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gz + base + i));
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gz + base + i + 4));
     const uint4 yv = __ldg(reinterpret_cast<const uint4*>(p.ymax + base + i));
-    const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&yv);
+    const __half2* y2 = reinterpret_cast<const __half2*>(&yv);
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t b = ((j < 4 ? idv.x : idv.y) >> (8 * (j & 3))) & 0xffu;
       if (b & 0x80u) {
-        const float2 f = __bfloat1622float2(y2[j >> 1]);
+        const float2 f = __half22float2(y2[j >> 1]);
         const float g = gg[j] * scale;
         s1 += g;
         s2 += g * (((j & 1) ? f.y : f.x) - cf.z) * cf.w;
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_kernel(const __grid_co
         const long long row = ((long long)n * p.C + c) * p.H + h;
         if (w < p.W) {
           const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
-          const float xhat = (__bfloat162float(p.y[row * p.W + w]) - cf.z) * cf.w;
+          const float xhat = (__half2float(p.y[row * p.W + w]) - cf.z) * cf.w;
           float g = 0.f;
           if (hp < HP) {
             const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(256, 3) cnn_tail_fwd_vec_kernel(const __grid_c
       if (cp < p.Cp && ci < p.cc && w < p.W) {
         const int c = comp * p.cc + ci;
         const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
-        const __nv_bfloat16* src = p.y + (((long long)n * p.C + c) * p.H + (long long)hp * p.pool) * p.W + w;
+        const __half* src = p.y + (((long long)n * p.C + c) * p.H + (long long)hp * p.pool) * p.W + w;
         float best[8], ybest[8];
         int arg[8];
 #pragma unroll
@@ -344,10 +348,10 @@ __global__ void __launch_bounds__(256, 3) cnn_tail_fwd_vec_kernel(const __grid_c
 #pragma unroll
         for (int q = 0; q < POOL; ++q) {
           const uint4 v = rows[q];
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(h2[j]);
+            const float2 f = __half22float2(h2[j]);
             const float v0 = cf.x * f.x + cf.y, v1 = cf.x * f.y + cf.y;
             if (v0 > best[2 * j] || v0 != v0) { best[2 * j] = v0; arg[2 * j] = q; ybest[2 * j] = f.x; }
             if (v1 > best[2 * j + 1] || v1 != v1) { best[2 * j + 1] = v1; arg[2 * j + 1] = q; ybest[2 * j + 1] = f.y; }
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(256, 3) cnn_tail_fwd_vec_kernel(const __grid_c
           uint32_t o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 b2 = __floats2bfloat162_rn(ybest[2 * j], ybest[2 * j + 1]);   // exact: bf16 values
+            const __half2 b2 = __floats2half2_rn(ybest[2 * j], ybest[2 * j + 1]);   // exact: fp16 values
             o[j] = *reinterpret_cast<const uint32_t*>(&b2);
           }
           *reinterpret_cast<uint4*>(p.ymax + e) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_vec_kernel(const __gri
         const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
         const float2 dm = __ldg(dmean + c);
         const uint4 yv = __ldg(reinterpret_cast<const uint4*>(p.y + row * p.W + w));
-        const __nv_bfloat162* y2 = reinterpret_cast<const __nv_bfloat162*>(&yv);
+        const __half2* y2 = reinterpret_cast<const __half2*>(&yv);
         float g[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = 0.f;
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_vec_kernel(const __gri
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(y2[j]);
+          const float2 f = __half22float2(y2[j]);
           const float d0 = cf.x * (g[2 * j] - dm.x - (f.x - cf.z) * cf.w * dm.y);
           const float d1 = cf.x * (g[2 * j + 1] - dm.x - (f.y - cf.z) * cf.w * dm.y);
           const __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(256) cnn_tail_bwd_apply_vec_kernel(const __gri
 // ---- host launchers ------------------------------------------------------------------------------------
 static int grid_cap() { return 148 * 16; }
 
-int launch_bn_stats(const void* src, int is_bf16, int n, int c, long long plane, double* sums, cudaStream_t st) {
+int launch_bn_stats(const void* src, int is_f16, int n, int c, long long plane, double* sums, cudaStream_t st) {
   if (n > 65535) return fail(SELDQ_ERR_UNSUPPORTED, "bn_stats: batch too large for the grid");
   // about 32 K elements per block, but never more than 64 splits of a plane
   long long splits = (plane + 32767) / 32768;
@@ -481,8 +485,8 @@ int launch_bn_stats(const void* src, int is_bf16, int n, int c, long long plane,
   chunk = (chunk + 7) & ~7LL;
   splits = (plane + chunk - 1) / chunk;
   dim3 grid((unsigned)c, (unsigned)n, (unsigned)splits);
-  if (is_bf16)
-    launch_pdl(epi::bn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(src), plane, c, chunk, sums);
+  if (is_f16)
+    launch_pdl(epi::bn_stats_kernel<__half>, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __half*>(src), plane, c, chunk, sums);
   else
     launch_pdl(epi::bn_stats_kernel<float>, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float*>(src), plane, c, chunk, sums);
   return check_launch("bn_stats_kernel");

@@ -1,6 +1,7 @@
 // Parameter block and host entry points of the bandwidth-bound glue kernels (epilogue.cu).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -9,7 +10,7 @@ namespace seldq {
 namespace epi {
 
 struct TailParams {
-  const __nv_bfloat16* y;       // conv output, bf16 [N][C][H][W]
+  const __half* y;              // conv output, IEEE fp16 [N][C][H][W] (see epilogue.cu: why fp16 and not bf16)
   const float* coef;            // [C][4] = {a, b, mean, rstd} from bn_finalize_kernel
   int N, C, H, W, pool;
   // channels-last operand layout of the tensor being written (z forward, d(conv out) backward)
@@ -18,7 +19,7 @@ struct TailParams {
   __nv_bfloat16* z_cl;          // [N][H/pool][W][Cp] or null
   float* z32;                   // [N][C][H/pool][W] or null
   uint8_t* idx;                 // [N][C][H/pool][W]: arg-max row | 0x80 keep flag (written fwd, read bwd)
-  __nv_bfloat16* ymax;          // [N][C][H/pool][W]: conv output at the arg-max (written fwd, read bwd) or null
+  __half* ymax;                 // [N][C][H/pool][W]: conv output at the arg-max (written fwd, read bwd) or null
   // backward
   const float* gz;              // gradient w.r.t. the pooled output, fp32 [N][C][H/pool][W]
   __nv_bfloat16* d_t16;         // d(conv out), bf16 [N][C][H][pitch] or null

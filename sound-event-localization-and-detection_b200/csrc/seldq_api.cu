@@ -191,14 +191,14 @@ extern "C" size_t seldq_conv_workspace_bytes(const seldq_conv_desc_t* d, int32_t
 
 // ---- convolution ------------------------------------------------------------------------------------
 static int conv_fwd_impl(const seldq_conv_desc_t* d, const float* x, const void* x_cl, const float* const* host_w,
-                         const void* packed_w, const float* bias, float* y, void* y_bf16, void* workspace,
+                         const void* packed_w, const float* bias, float* y, void* y_f16, void* workspace,
                          size_t workspace_bytes, void* stream) {
   ConvGeom g;
   int rc = make_conv_geom(d, SELDQ_PASS_FWD, &g);
   if (rc) return rc;
   const bool bf16 = d->precision == SELDQ_PREC_BF16;
-  if (!host_w || (!y && !y_bf16) || (!x && !(bf16 && x_cl))) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: null pointer");
-  if (y_bf16 && !bf16) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 output exists on the SELDQ_PREC_BF16 path only");
+  if (!host_w || (!y && !y_f16) || (!x && !(bf16 && x_cl))) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: null pointer");
+  if (y_f16 && !bf16) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 output exists on the SELDQ_PREC_BF16 path only");
   for (int i = 0; i < g.tab.nw; ++i)
     if (!host_w[i]) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd: weight %d is null", i);
   if ((rc = cuda_ready())) return rc;
@@ -224,7 +224,7 @@ static int conv_fwd_impl(const seldq_conv_desc_t* d, const float* x, const void*
     if ((rc = launch_pack_weights(g, host_w, buf, st))) return rc;
     packed_w = buf;
   }
-  return launch_cl_fprop(g, x_cl, host_w, packed_w, bias, y, y_bf16, st);
+  return launch_cl_fprop(g, x_cl, host_w, packed_w, bias, y, y_f16, st);
 }
 
 extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
@@ -234,10 +234,10 @@ extern "C" int seldq_conv_fwd(const seldq_conv_desc_t* d, const float* x, const 
 }
 
 extern "C" int seldq_conv_fwd_bf16(const seldq_conv_desc_t* d, const float* x, const void* x_cl,
-                                   const float* const* host_w, const void* packed_w, const float* bias, void* y_bf16,
+                                   const float* const* host_w, const void* packed_w, const float* bias, void* y_f16,
                                    void* workspace, size_t workspace_bytes, void* stream) {
-  if (!y_bf16) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd_bf16: null output");
-  return conv_fwd_impl(d, x, x_cl, host_w, packed_w, bias, nullptr, y_bf16, workspace, workspace_bytes, stream);
+  if (!y_f16) return fail(SELDQ_ERR_INVALID, "seldq_conv_fwd_bf16: null output");
+  return conv_fwd_impl(d, x, x_cl, host_w, packed_w, bias, nullptr, y_f16, workspace, workspace_bytes, stream);
 }
 
 extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, const void* gy_cl,
@@ -338,12 +338,12 @@ extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, cons
 }
 
 // ---- glue between the convolutions (E1) ------------------------------------------------------------------
-extern "C" int seldq_bn_stats(const void* src, int32_t is_bf16, int32_t n, int32_t c, int64_t plane, double* sums,
+extern "C" int seldq_bn_stats(const void* src, int32_t is_f16, int32_t n, int32_t c, int64_t plane, double* sums,
                               void* stream) {
   if (!src || !sums || n <= 0 || c <= 0 || plane <= 0) return fail(SELDQ_ERR_INVALID, "seldq_bn_stats: bad arguments");
   int rc = cuda_ready();
   if (rc) return rc;
-  return launch_bn_stats(src, is_bf16, n, c, plane, sums, (cudaStream_t)stream);
+  return launch_bn_stats(src, is_f16, n, c, plane, sums, (cudaStream_t)stream);
 }
 
 extern "C" int seldq_bn_finalize(const double* sums, const float* gamma, const float* beta, int32_t c, double count,
@@ -368,7 +368,7 @@ static int tail_params(const seldq_cnn_tail_desc_t* t, const cl::OperandLayout* 
   return SELDQ_OK;
 }
 
-extern "C" int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* consumer, const void* y_bf16,
+extern "C" int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* consumer, const void* y_f16,
                                   const float* coef, const int64_t* seed, void* z_cl, float* z_f32, uint8_t* idx,
                                   void* ymax, void* stream) {
   epi::TailParams p;
@@ -383,17 +383,17 @@ extern "C" int seldq_cnn_tail_fwd(const seldq_cnn_tail_desc_t* t, const seldq_co
       return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_fwd: pooled output does not match the consumer's input");
   }
   if ((rc = tail_params(t, z_cl ? &lay : nullptr, &p))) return rc;
-  if (!y_bf16 || !coef || !idx || (!z_cl && !z_f32)) return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_fwd: null pointer");
+  if (!y_f16 || !coef || !idx || (!z_cl && !z_f32)) return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_fwd: null pointer");
   if (t->drop_p > 0.f && !seed) return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_fwd: dropout needs a seed pointer");
   if ((rc = cuda_ready())) return rc;
-  p.y = reinterpret_cast<const __nv_bfloat16*>(y_bf16); p.coef = coef;
+  p.y = reinterpret_cast<const __half*>(y_f16); p.coef = coef;
   p.z_cl = reinterpret_cast<__nv_bfloat16*>(z_cl); p.z32 = z_f32; p.idx = idx;
-  p.ymax = reinterpret_cast<__nv_bfloat16*>(ymax);
+  p.ymax = reinterpret_cast<__half*>(ymax);
   p.seed_ptr = reinterpret_cast<const long long*>(seed);
   return launch_cnn_tail_fwd(p, (cudaStream_t)stream);
 }
 
-extern "C" int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* producer, const void* y_bf16,
+extern "C" int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* producer, const void* y_f16,
                                   const float* coef, const uint8_t* idx, const void* ymax, const float* gz, double* dsums,
                                   void* d_t16, void* d_cl, void* stream) {
   epi::TailParams p;
@@ -408,12 +408,12 @@ extern "C" int seldq_cnn_tail_bwd(const seldq_cnn_tail_desc_t* t, const seldq_co
       return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_bwd: descriptor does not match the producer's output");
   }
   if ((rc = tail_params(t, d_cl ? &lay : nullptr, &p))) return rc;
-  if (!y_bf16 || !coef || !idx || !gz || !dsums || (!d_t16 && !d_cl))
+  if (!y_f16 || !coef || !idx || !gz || !dsums || (!d_t16 && !d_cl))
     return fail(SELDQ_ERR_INVALID, "seldq_cnn_tail_bwd: null pointer");
   if ((rc = cuda_ready())) return rc;
-  p.y = reinterpret_cast<const __nv_bfloat16*>(y_bf16); p.coef = coef;
+  p.y = reinterpret_cast<const __half*>(y_f16); p.coef = coef;
   p.idx = const_cast<uint8_t*>(idx); p.gz = gz;
-  p.ymax = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ymax));
+  p.ymax = reinterpret_cast<__half*>(const_cast<void*>(ymax));
   p.d_t16 = reinterpret_cast<__nv_bfloat16*>(d_t16); p.d_cl = reinterpret_cast<__nv_bfloat16*>(d_cl);
   return launch_cnn_tail_bwd(p, dsums, (cudaStream_t)stream);
 }
@@ -469,7 +469,7 @@ extern "C" size_t seldq_cnn_first_bwd_workspace_bytes(const seldq_conv_desc_t* c
 }
 
 extern "C" int seldq_cnn_first_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t* conv, const float* x,
-                                   const void* y_bf16, const float* coef, const uint8_t* idx, const void* ymax,
+                                   const void* y_f16, const float* coef, const uint8_t* idx, const void* ymax,
                                    const float* gz, double* dsums, float* const* host_gw, int32_t accumulate,
                                    void* workspace, size_t workspace_bytes, void* stream) {
   ConvGeom g;
@@ -477,15 +477,15 @@ extern "C" int seldq_cnn_first_bwd(const seldq_cnn_tail_desc_t* t, const seldq_c
   if (rc) return rc;
   if (!seldq_cnn_first_bwd_supported(t, conv))
     return fail(SELDQ_ERR_UNSUPPORTED, "seldq_cnn_first_bwd: geometry outside the fused kernel (see seldq_cnn_first_bwd_supported)");
-  if (!x || !y_bf16 || !coef || !idx || !gz || !dsums || !host_gw)
+  if (!x || !y_f16 || !coef || !idx || !gz || !dsums || !host_gw)
     return fail(SELDQ_ERR_INVALID, "seldq_cnn_first_bwd: null pointer");
   if ((rc = cuda_ready())) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   epi::TailParams p;
   if ((rc = tail_params(t, nullptr, &p))) return rc;
-  p.y = reinterpret_cast<const __nv_bfloat16*>(y_bf16); p.coef = coef;
+  p.y = reinterpret_cast<const __half*>(y_f16); p.coef = coef;
   p.idx = const_cast<uint8_t*>(idx); p.gz = gz;
-  p.ymax = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(ymax));
+  p.ymax = reinterpret_cast<__half*>(const_cast<void*>(ymax));
   if ((rc = launch_cnn_tail_bwd_reduce(p, dsums, st))) return rc;
   const float2* dmean = reinterpret_cast<const float2*>(dsums + 2 * (size_t)t->c);
   const size_t wbytes = (size_t)g.Oc * g.Ic * g.KH * g.KW * sizeof(float);

@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "launch.h"
@@ -209,6 +210,120 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(uint32_t n, int n_mma, i
   if (threadIdx.x < 32) ptx::tmem_dealloc(tbase, 512);
 }
 
+// A-from-tensor-memory probe.  The product MMAs are small (N = 32 | 48 per Hamilton block) and in the SS form every
+// one re-reads its 4 KB A slab from shared memory (~45 cycles, r1b_umma_rate.txt).  Here the slab is copied to
+// tensor memory once (tcgen05.cp.128x256b) and G MMAs read it from there.
+//   mode 0  correctness: K = 64 (4 slabs) through the SS form and through cp + TS form, bitwise comparison of the
+//           accumulators; out[0] = mismatching elements, out[1] = non-zero elements of the SS result
+//   mode 1  TS MMAs only (A resident), mode 2  one cp + G TS MMAs per slab, mode 3  cp only,
+//   mode 4  G SS MMAs per slab (same loop, the baseline);  out[2b], out[2b+1] = issue, issue + drain cycles
+template <int G, int MODE>
+__device__ __forceinline__ void ts_slab_loop(uint32_t n, int n_slabs, int nbuf, uint32_t tD, uint32_t tA, uint32_t a0,
+                                             uint32_t b0, int d_cycle) {
+  const uint64_t a_hi = ptx::make_smem_desc_hi(16, 1024, ptx::kSwizzle128B);
+  const uint64_t b_hi = ptx::make_smem_desc_hi(n * 16u, 128, ptx::kSwizzleNone);
+  uint64_t bd[G];
+  uint32_t id[G], dd[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    bd[j] = ptx::smem_desc(b_hi, b0 + (uint32_t)(j & 7) * (n * 32u));
+    id[j] = ptx::make_idesc_bf16(128, n, 0, 0, 0, (uint32_t)(j & 1));
+    dd[j] = tD + (uint32_t)(j % d_cycle) * n;
+  }
+  const uint64_t ad0 = ptx::smem_desc(a_hi, a0);
+  int buf = 0;
+  for (int s = 0; s < n_slabs; ++s) {
+    const uint64_t ad = ad0 + (uint64_t)(((s >> 2) & 3) * 1024 + (s & 3) * 2);   // stage * 16 KB + slab * 32 B, >> 4
+    const uint32_t ab = tA + (uint32_t)buf * 8u;
+    if (MODE == 2 || MODE == 3) ptx::tmem_cp_128x256b(ab, ad);
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      if (MODE == 1 || MODE == 2) ptx::umma_f16_ts(dd[j], ab, bd[j], id[j], 1u);
+      if (MODE == 4) ptx::umma_f16(dd[j], ad, bd[j], id[j], 1u);
+    }
+    if (++buf == nbuf) buf = 0;
+  }
+}
+
+__global__ void __launch_bounds__(128) umma_ts_kernel(uint32_t n, int n_slabs, int g, int mode, int nbuf,
+                                                     long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  // small integers as bf16 (exact in fp32 accumulation, any placement is a valid operand)
+  for (uint32_t i = threadIdx.x; i < (128u * 1024u) / 2; i += 128) {
+    const uint32_t h = (i * 2654435761u) >> 13;
+    const float v = mode == 0 ? (float)((int)(h % 7u) - 3) : 0.f;
+    reinterpret_cast<__nv_bfloat16*>(smem)[i] = __float2bfloat16_rn(v);
+  }
+  ptx::fence_proxy_async();
+  if (threadIdx.x == 32) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < 32) ptx::tmem_alloc(&tmem_base, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tbase = tmem_base;
+  const uint32_t a0 = ptx::smem_u32(smem), b0 = a0 + 64 * 1024;
+  const uint32_t tA = tbase + 448;
+  if (mode == 0) {
+    if (threadIdx.x == 0) {
+      const uint64_t a_hi = ptx::make_smem_desc_hi(16, 1024, ptx::kSwizzle128B);
+      const uint64_t b_hi = ptx::make_smem_desc_hi(n * 16u, 128, ptx::kSwizzleNone);
+      for (int k = 0; k < 4 * n_slabs; ++k) {
+        const uint64_t ad = ptx::smem_desc(a_hi, a0 + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u);
+        const uint64_t bd = ptx::smem_desc(b_hi, b0 + (uint32_t)(k & 7) * (n * 32u));
+        const uint32_t idesc = ptx::make_idesc_bf16(128, n, 0, 0, 0, (uint32_t)(k & 1));
+        ptx::umma_f16(tbase, ad, bd, idesc, k > 0 ? 1u : 0u);
+      }
+      for (int k = 0; k < 4 * n_slabs; ++k) {
+        const uint64_t ad = ptx::smem_desc(a_hi, a0 + (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u);
+        const uint64_t bd = ptx::smem_desc(b_hi, b0 + (uint32_t)(k & 7) * (n * 32u));
+        const uint32_t idesc = ptx::make_idesc_bf16(128, n, 0, 0, 0, (uint32_t)(k & 1));
+        const uint32_t ab = tA + (uint32_t)(k % nbuf) * 8u;
+        ptx::tmem_cp_128x256b(ab, ad);
+        // g MMAs read the slab: the first computes, the others re-add and subtract it (net zero)
+        ptx::umma_f16_ts(tbase + 256, ab, bd, idesc, k > 0 ? 1u : 0u);
+        for (int j = 1; j < g; ++j) ptx::umma_f16_ts(tbase + 256, ab, bd, idesc ^ ((uint32_t)(j & 1) << 14) ^ (1u << 14), 1u);
+      }
+      ptx::umma_commit(&bar);
+    }
+    ptx::mbar_wait(&bar, 0);
+    ptx::tc_fence_after();
+    const uint32_t warp = threadIdx.x >> 5;
+    unsigned long long bad = 0, nz = 0;
+    for (uint32_t c = 0; c < n; c += 8) {
+      uint32_t r0[8], r1[8];
+      ptx::tmem_ld8(tbase + ((warp * 32u) << 16) + c, r0);
+      ptx::tmem_ld8(tbase + ((warp * 32u) << 16) + 256 + c, r1);
+      ptx::tmem_ld_wait();
+      for (int j = 0; j < 8; ++j) { bad += r0[j] != r1[j]; nz += r0[j] != 0; }
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(out), bad);
+    atomicAdd(reinterpret_cast<unsigned long long*>(out) + 1, nz);
+  } else if (threadIdx.x == 0) {
+    if (mode == 1 || mode == 2) ptx::tmem_cp_128x256b(tA, ptx::smem_desc(ptx::make_smem_desc_hi(16, 1024, ptx::kSwizzle128B), a0));
+    const int dcyc = (int)(256u / n) < 4 ? (int)(256u / n) : 4;
+    const long long t0 = clock64();
+#define SELDQ_TS_CASE(GG, MM) if (g == GG && mode == MM) ts_slab_loop<GG, MM>(n, n_slabs, nbuf, tbase, tA, a0, b0, dcyc);
+#define SELDQ_TS_G(MM) SELDQ_TS_CASE(1, MM) SELDQ_TS_CASE(2, MM) SELDQ_TS_CASE(3, MM) SELDQ_TS_CASE(4, MM) SELDQ_TS_CASE(6, MM) SELDQ_TS_CASE(8, MM)
+    SELDQ_TS_G(1) SELDQ_TS_G(2) SELDQ_TS_G(3) SELDQ_TS_G(4)
+#undef SELDQ_TS_G
+#undef SELDQ_TS_CASE
+    const long long t1 = clock64();
+    ptx::umma_commit(&bar);
+    ptx::mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[2 * blockIdx.x] = t1 - t0;
+    out[2 * blockIdx.x + 1] = t2 - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc(tbase, 512);
+}
+
 }  // namespace probe
 }  // namespace seldq
 
@@ -273,4 +388,17 @@ extern "C" int seldq_probe_umma_rate(uint32_t n, int32_t n_mma, int32_t d_cycle,
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "probe smem opt-in: %s", cudaGetErrorString(e));
   probe::umma_rate_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(n, n_mma, d_cycle, mode, (long long*)out);
   return check_launch("probe::umma_rate_kernel");
+}
+
+// A-from-tensor-memory probe (see probe::umma_ts_kernel); out: 2 x blocks int64
+extern "C" int seldq_probe_umma_ts(uint32_t n, int32_t n_slabs, int32_t g, int32_t mode, int32_t nbuf, int32_t blocks,
+                                   void* out, void* stream) {
+  if (n < 8 || n > 256 || (n & 7) || n_slabs < 1 || mode < 0 || mode > 4 || nbuf < 1 || nbuf > 8 || blocks < 1 ||
+      !(g == 1 || g == 2 || g == 3 || g == 4 || g == 6 || g == 8) || (mode == 0 && n_slabs > 4))
+    return fail(SELDQ_ERR_INVALID, "bad umma ts probe arguments");
+  const uint32_t smem = 128 * 1024 + 4096;
+  cudaError_t e = cudaFuncSetAttribute(probe::umma_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "probe smem opt-in: %s", cudaGetErrorString(e));
+  probe::umma_ts_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(n, n_slabs, g, mode, nbuf, (long long*)out);
+  return check_launch("probe::umma_ts_kernel");
 }

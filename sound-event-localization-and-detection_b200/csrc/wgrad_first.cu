@@ -4,7 +4,7 @@
 //     d = a (g - mean(dy) - xhat mean(dy xhat)),  g = pooled gradient routed to the arg-max row (epilogue.cu)
 // has exactly one consumer: this layer's weight gradient.  Writing it to HBM and reading it back costs 2 x 472 MB
 // per sample (the largest tensor of the model) plus a kernel; here the gradient tile is produced in shared memory
-// instead: TMA drops the conv-output tile (bf16, K-major, 128B swizzle) where the B operand is expected, and
+// instead: TMA drops the conv-output tile (fp16, K-major, 128B swizzle) where the B operand is expected, and
 // "transform" warps turn it into d in place, from the arg-max flags and the pooled gradient they hold in registers.
 //
 //   D[(tap, c), (a, o)] = sum_{n, h, w} x[n, c, h + off_h(tap), w + off_w(tap)] * d[n, a*Oc + o, h, w]
@@ -19,6 +19,7 @@
 // owner + MMA issuer, warps 2..9 = transform producers of d, then epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "conv_umma.h"
@@ -184,7 +185,8 @@ first_layer_bwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             const uint32_t hit[2] = {__vcmpeq4(idv[i].x & 0x87878787u, want4), __vcmpeq4(idv[i].y & 0x87878787u, want4)};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float y0 = __uint_as_float(yw[q] << 16), y1 = __uint_as_float(yw[q] & 0xffff0000u);
+              const float2 yf = __half22float2(*reinterpret_cast<const __half2*>(&yw[q]));
+              const float y0 = yf.x, y1 = yf.y;
               const float g0 = (hit[q >> 1] & (1u << (16 * (q & 1)))) ? ga[i][2 * q] : 0.f;
               const float g1 = (hit[q >> 1] & (1u << (16 * (q & 1) + 8))) ? ga[i][2 * q + 1] : 0.f;
               const __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaf(-Bc[i], y0, Cc[i] + g0), fmaf(-Bc[i], y1, Cc[i] + g1));

@@ -1,6 +1,7 @@
 // Parameter block and host entry points of the fused first-layer backward kernel (wgrad_first.cu).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -14,7 +15,7 @@ struct Params {
   ConvGeom g;                   // forward orientation
   float* gw[8];                 // compact fp32 gradients, accumulated with atomicAdd
   // CNN-block tail (epilogue.h): conv output, BN coefficients, arg-max flags, pooled gradient, BN-backward means
-  const __nv_bfloat16* y;
+  const __half* y;              // conv output, fp16 (epilogue.cu)
   const float* coef;
   const uint8_t* idx;
   const float* gz;

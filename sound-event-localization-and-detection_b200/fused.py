@@ -3,7 +3,7 @@
 `cnn_stack` runs the whole CNN front of ConvTC_Block (model.py:261-285: per block Q/DQ conv2d ->
 BatchNorm2d -> ReLU -> MaxPool2d([p, 1]) -> Dropout) as one autograd Function over the C ABI:
 
-    forward, per block    conv (tcgen05, bf16 NCHW output)  ->  bn_stats  ->  bn_finalize  ->  cnn_tail_fwd
+    forward, per block    conv (tcgen05, fp16 NCHW output)  ->  bn_stats  ->  bn_finalize  ->  cnn_tail_fwd
                           (the pooled activation leaves cnn_tail_fwd directly as the next convolution's
                           channels-last bf16 operand; only the last block also emits fp32 NCHW)
     backward, per block   cnn_tail_bwd (both BatchNorm reductions + d(conv out) in the two bf16 operand
@@ -90,7 +90,7 @@ class _CnnStack(torch.autograd.Function):
                 C = d.cout
                 wp = _lib.ptr_array([w.data_ptr() for w in ws])
                 pk = F.packed_weights(ws, d, PASS_FWD)
-                y16 = torch.empty((N, C, oh, ow), dtype=torch.bfloat16, device=dev)
+                y16 = torch.empty((N, C, oh, ow), dtype=torch.float16, device=dev)
                 F._timed("qconv_cl_fprop_kernel", F._conv_flop(d, oh, ow), 1, lambda: _lib.check(
                     L.seldq_conv_fwd_bf16(ctypes.byref(d), None, cur_cl.data_ptr(), wp, _ptr(pk), None, y16.data_ptr(),
                                           None, 0, _stream())))
@@ -104,7 +104,7 @@ class _CnnStack(torch.autograd.Function):
                 hp = oh // s["pool"]
                 td = _lib.CnnTailDesc(N, C, oh, ow, s["pool"], s["drop_p"], s["salt"])
                 idx = torch.empty((N, C, hp, ow), dtype=torch.uint8, device=dev)
-                ymax = torch.empty((N, C, hp, ow), dtype=torch.bfloat16, device=dev)
+                ymax = torch.empty((N, C, hp, ow), dtype=torch.float16, device=dev)
                 if last:
                     z32 = torch.empty((N, C, hp, ow), dtype=torch.float32, device=dev)
                     nxt_cl, consumer = None, None

@@ -210,7 +210,7 @@ def test_model_bf16_matches_reference_fixture(seldq, name, fused):
     convolutions in float64, the GPU in float32, so a few activations round to the other bf16
     neighbour; observed 3e-3).
     fused=False: layer-by-layer modules, emulation keys bf16emu*.  fused=True: the fused CNN-block
-    kernels (fused.py), which store the 2-d conv outputs once in bf16 -- emulation keys bf16emu16*
+    kernels (fused.py), which store the 2-d conv outputs once in fp16 -- emulation keys bf16emu16*
     model exactly that extra rounding (model_dq_tiny's CNN is too narrow for the fused path and
     runs layer by layer either way)."""
     prev = seldq.fused.ENABLED
