@@ -25,7 +25,12 @@
 // only, one MMA spanning all out channels.
 //
 // Warp roles: warp 0 = TMA producer, warps 1 and 6.. = MMA issuers (kMmaWarps; warp 1 owns the TMEM allocation),
-// warps 2..5 = epilogue (TMEM -> registers -> coalesced global stores, + bias).
+// warps 2..5 and kFirstExtraEpiWarp.. = epilogue (TMEM -> registers -> coalesced global stores, + bias): kEpiSets sets
+// of four warps (one per TMEM lane quarter) that take alternate 16-channel chunks -- a single warp per quarter runs
+// its dependent ld / convert / store chain at well under one instruction per cycle, which bounded the layers with
+// little K per output (first CNN layer: 9 MMAs but 12 column chunks per tile).
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -58,7 +63,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
   __shared__ uint2 op_tbl_s[kOpTableEntries];
-  __shared__ __align__(16) uint8_t out_stage[4][16 * 64];   // per epilogue warp: [16 ch][32 w] bf16
+  __shared__ __align__(16) uint8_t out_stage[4 * kEpiSets][8 * 64];    // per epilogue warp: [8 ch][32 w] fp16
   // warp index through a shuffle: provably warp-uniform, so role branches and the MMA loop compile to the
   // uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -102,7 +107,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   if (threadIdx.x == 0) {
     // two MMA-issuing warps: each arrives once per stage / accumulator
     for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], kMmaWarps); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], kMmaWarps); ptx::mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], kMmaWarps); ptx::mbar_init(&tempty_bar[i], 4 * kEpiSets); }
     ptx::mbar_init(w_bar, 1);
     ptx::fence_barrier_init();
     ptx::prefetch_tensormap(&tm_in);
@@ -139,17 +144,18 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         const uint32_t mask = p.chunk_mask[group];
         for (int c = 0; c < p.chunks; ++c) {
           if (!((mask >> c) & 1u)) continue;
-          for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int tap = 0; tap < p.ntaps; tap += p.tps) {
             ptx::mbar_wait(&empty_bar[slot], parity ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[slot], p.stage_bytes);
-            ptx::tma_load_4d(a_ring + (size_t)slot * p.stage_bytes, &tm_in, &full_bar[slot], c * p.BK,
-                             w0 + p.off_w[tap], h + p.off_h[tap], n);
+            for (int tl = 0; tl < p.tps; ++tl)       // one stage = the boxes of p.tps taps
+              ptx::tma_load_4d(a_ring + (size_t)slot * p.stage_bytes + (size_t)tl * p.box_bytes, &tm_in, &full_bar[slot],
+                               c * p.BK, w0 + p.off_w[tap + tl], h + p.off_h[tap + tl], n);
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1 || warp >= 6) {
+  } else if (warp == 1 || (warp >= 6 && warp < kFirstExtraEpiWarp)) {
     // ===== MMA issuers =============================================================================
     // Lane-parallel issue: the MMAs of one stage (<= 32: slabs x out components of the group, structural zero
     // blocks left out) form a dense list in (slab, component) order.  All lanes build their descriptors at once;
@@ -166,8 +172,11 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       const uint64_t a_hi = ptx::make_smem_desc_hi(16, p.a_sbo, p.a_swz);                 // K-major, swizzled
       const uint64_t b_hi = ptx::make_smem_desc_hi((uint32_t)p.NBp * 16u, 128, ptx::kSwizzleNone);
       const uint32_t a_base = ptx::smem_u32(a_ring), b_lo16 = ptx::smem_u32(b_img) >> 4;
-      const int lanes_per_stage = p.slabs_per_chunk * GC;
+      const int lanes_per_chunk = p.slabs_per_chunk * GC;          // op-table entries of one (group, chunk)
+      const int lanes_per_stage = lanes_per_chunk * p.tps;         // a stage holds p.tps taps (1, or all of them)
       const int my_entry = kMmaWarps * lane + me;
+      const int my_tl = my_entry / lanes_per_chunk;                // tap of the stage this lane's MMA belongs to
+      const int my_rest = my_entry - my_tl * lanes_per_chunk;      // ... and its entry in the chunk's op list
       if (!p.dense) ptx::mbar_wait(w_bar, 0);
       uint32_t slot = 0, parity = 0, it = 0;
       for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
@@ -180,23 +189,23 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         ptx::mbar_wait(&tempty_bar[as], (use & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_unit = tmem_base + as * acc_cols;
-        const uint2* tbl_g = op_tbl_s + (size_t)p.group_order[gi] * p.chunks * lanes_per_stage;
+        const uint2* tbl_g = op_tbl_s + (size_t)p.group_order[gi] * p.chunks * lanes_per_chunk;
         int last_closer = -1;                                  // lane that issued this warp's last MMA of the unit
         for (int c = 0; c < p.chunks; ++c) {
           if (!((mask >> c) & 1u)) continue;
           // per chunk: this lane's MMA (the same for every tap up to the tap's weight-tile offset)
           uint2 e = make_uint2(0u, 0u);
-          if (my_entry < lanes_per_stage) e = tbl_g[c * lanes_per_stage + my_entry];
+          if (my_entry < lanes_per_stage) e = tbl_g[c * lanes_per_chunk + my_rest];
           const bool valid = (int)e.x < 0;
-          const bool first = valid && (e.x & (1u << 30)) != 0u;
+          const bool first = valid && (e.x & (1u << 30)) != 0u && my_tl == 0;
           const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
           const bool any = vmask != 0u;
           const int closer = any ? 31 - __clz((int)vmask) : -1;
           if (any) last_closer = closer;
-          const uint32_t a_off16 = ((e.x >> 16) & 3u) * 2u;
+          const uint32_t a_off16 = ((e.x >> 16) & 3u) * 2u + (((uint32_t)my_tl * p.box_bytes) >> 4);
           const uint32_t d_lane = d_unit + ((e.x >> 20) & 7u) * (uint32_t)p.NBp;
-          uint32_t b16 = b_lo16 + (e.x & 0x3fffu);
-          for (int tap = 0; tap < p.ntaps; ++tap, b16 += p.tap_stride16) {
+          uint32_t b16 = b_lo16 + (e.x & 0x3fffu) + (uint32_t)my_tl * p.tap_stride16;
+          for (int tap = 0; tap < p.ntaps; tap += p.tps, b16 += p.tap_stride16 * (uint32_t)p.tps) {
             const uint64_t a_desc = a_hi | (uint64_t)((((a_base + slot * p.stage_bytes) >> 4) + a_off16) & 0x3fffu);
             const uint64_t b_desc = b_hi | (uint64_t)(b16 & 0x3fffu);
             ptx::mbar_wait(&full_bar[slot], parity);
@@ -229,10 +238,11 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         ++it;
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
+  } else {
     // ===== epilogue: TMEM -> registers -> global ===================================================
     pdl_wait();
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int eset = warp >= kFirstExtraEpiWarp ? 1 + (warp - kFirstExtraEpiWarp) / 4 : 0;
     const int row = q * 32 + lane;
     // 16-byte bf16 stores need 8-element alignment of every row start
     const bool vec16 = p.out16 != nullptr && (p.OW & 7) == 0 && (p.out_sC & 7) == 0 && (p.out_sH & 7) == 0 &&
@@ -256,9 +266,11 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       const long long row_off = (long long)n * p.out_sN + (long long)h * p.out_sH + w;
       float* out_row = p.out + row_off;
       __half* out16_row = p.out16 + row_off;
+      int piece_no = 0;
       for (int al = 0; al < GC; ++al) {
         const int ch_base = (group * GC + al) * p.Pc;
-        for (int c0 = 0; c0 < p.Pc; c0 += 16) {
+        for (int c0 = 0; c0 < p.Pc; c0 += 16, ++piece_no) {
+          if (piece_no % kEpiSets != eset) continue;
           uint32_t v[16];
           ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
           ptx::tmem_ld_wait();
@@ -266,23 +278,29 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
             // fp16 output in the tensor's own NCHW order (fused CNN-block path, epilogue.cu): the warp's
             // [32 w x 16 ch] block is transposed through shared memory and leaves as 16-byte pieces
             const int lim = p.Pc - c0;
-            uint8_t* stg = out_stage[q];
+            uint8_t* stg = out_stage[eset * 4 + q];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              *reinterpret_cast<__half*>(stg + j * 64 + lane * 2) =
-                  to_f16_sat(__uint_as_float(v[j]) + ((p.bias && j < lim) ? __ldg(p.bias + ch_base + c0 + j) : 0.f));
-            __syncwarp();
+            for (int r = 0; r < 2; ++r) {                      // 8 channels per pass: [8 ch][32 w] staging
+              if (p.bias == nullptr) {        // the common case (--use_bias_conv=False): no per-element select / load / add
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const int ch = r * 8 + (lane >> 2), piece = lane & 3;
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<__half*>(stg + j * 64 + lane * 2) = to_f16_sat(__uint_as_float(v[r * 8 + j]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<__half*>(stg + j * 64 + lane * 2) = to_f16_sat(
+                      __uint_as_float(v[r * 8 + j]) + (r * 8 + j < lim ? __ldg(p.bias + ch_base + c0 + r * 8 + j) : 0.f));
+              }
+              __syncwarp();
+              const int ch = lane >> 2, piece = lane & 3;
               const int wp = wt * kTileM + q * 32 + piece * 8;
-              if (ch < lim && wp < p.OW) {
+              if (r * 8 + ch < lim && wp < p.OW) {
                 const uint4 val = *reinterpret_cast<const uint4*>(stg + ch * 64 + piece * 16);
                 *reinterpret_cast<uint4*>(p.out16 + (long long)n * p.out_sN + (long long)h * p.out_sH +
-                                          (long long)(ch_base + c0 + ch) * p.out_sC + wp) = val;
+                                          (long long)(ch_base + c0 + r * 8 + ch) * p.out_sC + wp) = val;
               }
+              __syncwarp();
             }
-            __syncwarp();
           } else if (w_ok && p.out16) {
             __half* dst = out16_row + (long long)(ch_base + c0) * p.out_sC;
             const int lim = p.Pc - c0;
@@ -526,7 +544,8 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
   p->slab_bytes = (uint32_t)w.slab_bytes; p->img_bytes = (uint32_t)w.img_bytes; p->w_bytes = (uint32_t)w.total;
   p->BK = l.BK; p->chunks = l.Cp / l.BK; p->slabs_per_chunk = l.BK / 16; p->cpad_in = l.cpad;
   if (p->chunks > 32) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path supports at most 2048 padded input channels");
-  p->stage_bytes = (uint32_t)cl::kTileM * l.BK * 2;
+  p->box_bytes = (uint32_t)cl::kTileM * l.BK * 2;
+  p->tps = 1;
   p->a_sbo = 8u * l.BK * 2;
   p->a_swz = l.BK == 64 ? ptx::kSwizzle128B : (l.BK == 32 ? ptx::kSwizzle64B : ptx::kSwizzle32B);
 
@@ -569,6 +588,10 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
     return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: too many (slab, component) pairs for the MMA op table");
   if (p->slabs_per_chunk * p->gc > 32)
     return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: more than 32 MMAs per stage");
+  // Narrow K side (first CNN layer: one 16-channel slab per tap): a stage per tap is a 4 KB box and one MMA, so the
+  // producer's and the issuers' per-stage bookkeeping (~0.3 us) would bound the layer; all taps share one stage then.
+  if (l.BK <= 16 && ntaps * p->slabs_per_chunk * p->gc <= 32 && !getenv("SELDQ_NO_TPS")) p->tps = ntaps;
+  p->stage_bytes = p->box_bytes * (uint32_t)p->tps;
   p->tap_stride16 = (uint32_t)(((size_t)p->J * p->slab_bytes) >> 4);
   {
     const uint32_t idesc = ptx::make_idesc_bf16(cl::kTileM, (uint32_t)p->NBp, 0, 0, 0, 0);

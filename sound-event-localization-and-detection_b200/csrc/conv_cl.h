@@ -22,7 +22,10 @@ namespace cl {
 constexpr int kTileM = 128;     // positions per accumulator tile (TMEM lanes)
 constexpr int kThreads = 192;   // wgrad: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kMmaWarps = 4;          // fprop: MMA-issuing warps (warp 1 and warps 6 ...)
-constexpr int kFpropThreads = 192 + 32 * (kMmaWarps - 1);
+constexpr int kEpiSets = 2;           // fprop: epilogue warp sets of 4 (one warp per TMEM lane quarter); the sets split
+                                      // the 16-channel column chunks of a tile between them
+constexpr int kFirstExtraEpiWarp = 6 + (kMmaWarps - 1);
+constexpr int kFpropThreads = 192 + 32 * (kMmaWarps - 1) + 128 * (kEpiSets - 1);
 constexpr int kMaxTaps = 9;
 constexpr int kMaxStages = 8;
 constexpr int kOpTableEntries = 512;  // (16-channel slab, out component) pairs: 1024 padded channels x 8
@@ -77,6 +80,8 @@ struct FpropParams {
   // K side
   int BK, chunks, slabs_per_chunk, cpad_in, J;
   uint32_t stage_bytes, a_sbo, a_swz;
+  uint32_t box_bytes;           // one TMA box [128 w x BK ch]; a stage holds `tps` of them (taps per stage)
+  int tps;
   uint32_t chunk_mask[8];       // per group: which channel chunks carry at least one non-zero block
   // N side
   int dense, ncomp_out, Pc, NBp, gc;

@@ -239,7 +239,8 @@ def cnn_stack(x, convs, bns, pools, drops, seed):
                          momentum=float(bn.momentum), nw=len(ws), running_mean=bn.running_mean,
                          running_var=bn.running_var, salt=k + 1))
         tensors += list(ws) + [bn.weight, bn.bias]
-        bn.num_batches_tracked.add_(1)
+    # nn.BatchNorm's step counters: one multi-tensor launch instead of one tiny kernel per layer
+    torch._foreach_add_([bn.num_batches_tracked for bn in bns], 1)
     return _CnnStack.apply(x, spec, seed, *tensors)
 
 
@@ -549,7 +550,7 @@ def tcn_stack_supported(blocks, x, training):
 
 def tcn_stack(x, blocks, seed):
     """x (N, L, T) fp32 -> sum of the blocks' skip outputs (N, U, T) fp32 (TC_Block.forward, model.py:210-216)."""
-    spec, tensors = [], []
+    spec, tensors, counters = [], [], []
     for k, b in enumerate(blocks):
         ws = [c._weights() for c in (b.conv1_filter, b.conv1_gate, b.conv2_skip, b.conv2_residual)]
         kk = b.conv1_filter.kernel_size
@@ -565,5 +566,6 @@ def tcn_stack(x, blocks, seed):
             tensors += list(w)
         for bn in bns:
             tensors += [bn.weight, bn.bias]
-            bn.num_batches_tracked.add_(1)
+            counters.append(bn.num_batches_tracked)
+    torch._foreach_add_(counters, 1)      # one multi-tensor launch for the 30 BatchNorm step counters
     return _TcnStack.apply(x, spec, seed, *tensors)

@@ -28,8 +28,13 @@ from . import layers as _default_layers
 _F._apply_tf32_policy()
 
 import os as _os
-# SELDQ_ATTN_BF16=1: in 'bf16' mode MultiHeadAttention feeds bf16 operands to the library's fused attention kernel
-ATTN_BF16 = _os.environ.get("SELDQ_ATTN_BF16", "0") == "1"
+# In 'bf16' mode MultiHeadAttention (model.py:12-51; real-valued, not a Q / DQ layer -- SURVEY 8f N1) may feed 16-bit
+# operands to the library's fused attention kernel, so the S x S energy tensor never exists in HBM.
+#   SELDQ_ATTN=fp16  IEEE half operands: 10-bit mantissa = the TF32 rounding the fp32 path applies anyway
+#   SELDQ_ATTN=bf16  bf16 operands (7-bit mantissa: costs 0.2e-2 of the 2e-2 output tolerance)
+#   SELDQ_ATTN=fp32  fp32 / TF32 scaled_dot_product_attention
+ATTN_DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": None}[
+    "bf16" if _os.environ.get("SELDQ_ATTN_BF16", "0") == "1" else _os.environ.get("SELDQ_ATTN", "fp32")]
 _BN_TCN = {'BN', 'BN_on_TCN', 'BNonTCN'}
 _BN_CNN = {'BN', 'BN_on_CNN', 'BNonCNN'}
 _TWO_BRANCH = {'2Parallel', '2BParallel', '2ParallelBranches', '2PB'}
@@ -73,9 +78,15 @@ class MultiHeadAttention(nn.Module):
         kp = self._split(self.keys(k.permute(0, 2, 1)))
         qp = self._split(self.queries(q.permute(0, 2, 1)))
         attn_mask = None if mask is None else (mask != 0)
-        if ATTN_BF16 and q.is_cuda and _F.get_precision() == "bf16" and attn_mask is None:
-            # tensor-core mode: bf16 operands into the library's fused attention kernel (no S x S tensor in HBM)
-            out = tF.scaled_dot_product_attention(qp.bfloat16(), kp.bfloat16(), vp.bfloat16()).float()
+        if ATTN_DTYPE is not None and q.is_cuda and _F.get_precision() == "bf16" and attn_mask is None:
+            # tensor-core mode: 16-bit operands into the library's fused attention kernel (no S x S tensor in HBM)
+            out = tF.scaled_dot_product_attention(qp.to(ATTN_DTYPE), kp.to(ATTN_DTYPE), vp.to(ATTN_DTYPE)).float()
+        elif attn_mask is None and q.is_cuda:
+            # the reference's three steps (model.py:40-47) as two batched GEMMs around one softmax; the scale is
+            # folded into q.  (scaled_dot_product_attention's fp32 math backend adds a masking pass, an -inf scan
+            # and a scaling pass over the S x S tensor: 0.25 ms of a 5 ms step.)
+            attn = torch.softmax(torch.matmul(qp * (1.0 / self.head_dim ** 0.5), kp.transpose(-1, -2)), dim=-1)
+            out = torch.matmul(attn, vp)
         else:
             out = tF.scaled_dot_product_attention(qp, kp, vp, attn_mask=attn_mask)    # scale = 1/sqrt(head_dim)
         out = out.transpose(1, 2).reshape(n, length, self.num_heads * self.head_dim)

@@ -206,9 +206,10 @@ def test_model_bf16_matches_reference_fixture(seldq, name, fused):
     implementation; the fixture therefore carries the result of an ideal bf16-operand
     implementation (oracle/bf16_emulation.py): its own distance to the float64 reference is the
     inherent bf16 noise of each tensor, and the GPU may be at most twice as far (floor 2e-2).  The
-    outputs must match the emulation itself to 5e-3 (the emulation runs everything between the
-    convolutions in float64, the GPU in float32, so a few activations round to the other bf16
-    neighbour; observed 3e-3).
+    outputs must match the emulation itself to 1e-2 (the emulation runs everything between the
+    convolutions in float64, the GPU in float32 with a timing-dependent accumulation order in the
+    tensor path, so a few activations round to the other bf16 neighbour; observed 3e-3 .. 5.2e-3
+    from run to run).
     fused=False: layer-by-layer modules, emulation keys bf16emu*.  fused=True: the fused CNN-block
     kernels (fused.py), which store the 2-d conv outputs once in fp16 -- emulation keys bf16emu16*
     model exactly that extra rounding (model_dq_tiny's CNN is too narrow for the fused path and
@@ -222,8 +223,8 @@ def test_model_bf16_matches_reference_fixture(seldq, name, fused):
     emu = "bf16emu16" if (fused and name == "model_dq_mid") else "bf16emu"
     assert A.rel_err(sed, d["sed"]) < 2e-2
     assert A.rel_err(doa, d["doa"]) < 2e-2
-    assert A.rel_err(sed, d[emu + "/sed"]) < 5e-3
-    assert A.rel_err(doa, d[emu + "/doa"]) < 5e-3
+    assert A.rel_err(sed, d[emu + "/sed"]) < 1e-2
+    assert A.rel_err(doa, d[emu + "/doa"]) < 1e-2
     bad = {}
     for k, g in grads.items():
         noise = A.rel_err(d[emu + "_grad/" + k], d["grad/" + k])
@@ -340,8 +341,13 @@ def test_fused_tcn_channel_dropout_is_consistent(seldq):
     y2, g2 = run(7)
     y3, _ = run(8)
     assert torch.isfinite(y1).all() and torch.isfinite(g1).all()
-    assert torch.allclose(y1, y2, rtol=1e-4, atol=1e-5) and torch.allclose(g1, g2, rtol=1e-3, atol=1e-6)
-    assert not torch.equal(y1, y3)
+    # "Repeatable" up to the tensor path's own noise: the four MMA-issuing warps of the convolution kernel accumulate
+    # in a timing-dependent order (fp32 sums differ in the last bit), and a value that sits on a bf16 rounding
+    # boundary of the next layer's operand then flips -- observed: a handful of discrete outcomes 2e-4 apart.  A
+    # different dropout mask moves the output by tens of percent.
+    n = lambda t: t.cpu().numpy()
+    assert A.rel_err(n(y1), n(y2)) < 2e-3 and A.rel_err(n(g1), n(g2)) < 1e-2
+    assert A.rel_err(n(y1), n(y3)) > 5e-2
 
 
 def test_fused_first_layer_backward_matches_two_kernel_path(seldq):

@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="DQSELD-TCN-S1-PHI_8ch")
 ap.add_argument("--batch", type=int, default=0)
 ap.add_argument("--top", type=int, default=45)
+ap.add_argument("--ops", action="store_true", help="also list the aten ops (with input shapes) by self device time")
 args = ap.parse_args()
 cfg = bench.CONFIGS[args.config]
 pkg = importlib.import_module(bench.PKG)
@@ -32,7 +33,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=args.ops) as prof:
     trainer.step(x, t)
     torch.cuda.synchronize()
 rows = {}
@@ -46,3 +47,7 @@ total = sum(r[0] for r in rows.values())
 print("total device time %.3f ms over %d launches" % (total / 1e3, sum(r[1] for r in rows.values())))
 for name, (us, n) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:args.top]:
     print("%9.1f us %5d x %7.1f us  %5.1f%%  %s" % (us, n, us / n, 100 * us / total, name))
+if args.ops:
+    print()
+    print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=60,
+                                                             max_name_column_width=48, max_shapes_column_width=70))
