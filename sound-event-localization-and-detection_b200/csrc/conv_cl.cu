@@ -80,7 +80,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
 
   // ---- one-time setup ---------------------------------------------------------------------------
-  for (int i = threadIdx.x; i < p.chunks * p.slabs_per_chunk * p.ncomp_out; i += kFpropThreads) op_tbl_s[i] = p.op_tbl[i];
+  for (int i = threadIdx.x; i < p.op_entries; i += kFpropThreads) op_tbl_s[i] = p.op_tbl[i];
   if (p.dense) {
     // signed expanded weight -> bf16 B tiles.  Tile (tap, j) holds B[n][k], n = out channel, k = in channels
     // 16 j ... 16 j + 15; UMMA K-major / no swizzle: core matrix = 8 rows x 16 B, LBO (K step) = NBp*16,
@@ -117,7 +117,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc_cols = (uint32_t)(GC * p.NBp);
+  const uint32_t acc_cols = (uint32_t)p.acc_cols;
 
   if (warp == 0) {
     // ===== TMA producer ============================================================================
@@ -170,9 +170,9 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     {
       const int me = warp == 1 ? 0 : warp - 5;
       const uint64_t a_hi = ptx::make_smem_desc_hi(16, p.a_sbo, p.a_swz);                 // K-major, swizzled
-      const uint64_t b_hi = ptx::make_smem_desc_hi((uint32_t)p.NBp * 16u, 128, ptx::kSwizzleNone);
+      const uint64_t b_hi = ptx::make_smem_desc_hi((uint32_t)p.NBmma * 16u, 128, ptx::kSwizzleNone);
       const uint32_t a_base = ptx::smem_u32(a_ring), b_lo16 = ptx::smem_u32(b_img) >> 4;
-      const int lanes_per_chunk = p.slabs_per_chunk * GC;          // op-table entries of one (group, chunk)
+      const int lanes_per_chunk = p.slabs_per_chunk * p.mma_per_slab;   // op-table entries of one (group, chunk)
       const int lanes_per_stage = lanes_per_chunk * p.tps;         // a stage holds p.tps taps (1, or all of them)
       const int my_entry = kMmaWarps * lane + me;
       const int my_tl = my_entry / lanes_per_chunk;                // tap of the stage this lane's MMA belongs to
@@ -203,7 +203,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
           const int closer = any ? 31 - __clz((int)vmask) : -1;
           if (any) last_closer = closer;
           const uint32_t a_off16 = ((e.x >> 16) & 3u) * 2u + (((uint32_t)my_tl * p.box_bytes) >> 4);
-          const uint32_t d_lane = d_unit + ((e.x >> 20) & 7u) * (uint32_t)p.NBp;
+          const uint32_t d_lane = d_unit + ((e.x >> 20) & 0x1ffu);
           uint32_t b16 = b_lo16 + (e.x & 0x3fffu) + (uint32_t)my_tl * p.tap_stride16;
           for (int tap = 0; tap < p.ntaps; tap += p.tps, b16 += p.tap_stride16 * (uint32_t)p.tps) {
             const uint64_t a_desc = a_hi | (uint64_t)((((a_base + slot * p.stage_bytes) >> 4) + a_off16) & 0x3fffu);
@@ -268,12 +268,36 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       __half* out16_row = p.out16 + row_off;
       int piece_no = 0;
       for (int al = 0; al < GC; ++al) {
-        const int ch_base = (group * GC + al) * p.Pc;
+        const int ch_base = p.comp_of[group][al] * p.Pc;
         for (int c0 = 0; c0 < p.Pc; c0 += 16, ++piece_no) {
           if (piece_no % kEpiSets != eset) continue;
           uint32_t v[16];
-          ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
-          ptx::tmem_ld_wait();
+          if (!p.fuse) {
+            ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
+            ptx::tmem_ld_wait();
+          } else {
+            // pair fusion: channels [c0, c0 + 8) and [c0 + 8, c0 + 16) of this component are 8-column groups of the
+            // pair's (up to) two column sets; sum them with the component's signs (conv_cl.h)
+            uint32_t u[2][2][8];
+#pragma unroll
+            for (int st = 0; st < 2; ++st)
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                if (p.epi_sgn[group][al][st] != 0 && c0 + hf * 8 < p.Pc)
+                  ptx::tmem_ld8(t_row + (uint32_t)p.epi_col[group][al][st] + (uint32_t)((c0 >> 3) + hf) * 16u, u[st][hf]);
+                else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) u[st][hf][j] = 0u;
+                }
+              }
+            ptx::tmem_ld_wait();
+            const float s0 = (float)p.epi_sgn[group][al][0], s1 = (float)p.epi_sgn[group][al][1];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                v[hf * 8 + j] = __float_as_uint(s0 * __uint_as_float(u[0][hf][j]) + s1 * __uint_as_float(u[1][hf][j]));
+          }
           if (p.out16 && vec16) {
             // fp16 output in the tensor's own NCHW order (fused CNN-block path, epilogue.cu): the warp's
             // [32 w x 16 ch] block is transposed through shared memory and leaves as 16-byte pieces
@@ -340,6 +364,8 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 // compact fp32 weights -> bf16 UMMA B tiles [img][tap][j][NBp x 16] (K-major, no swizzle; see the dense
 // prologue above for the byte layout).  Row n / column k of tile (img, tap, j):
 //   forward : W_img[o = n][i = 16 j + k][tap]        dgrad : W_img[o = 16 j + k][i = n][tap]
+// Pair fusion (pair_xor != 0): tile (image pair q, tap, j) is [2 NB8 x 16]; its 8-row groups alternate between
+// the pair's lower image (i & pair_xor == 0) and upper image: row (n / 8) * 16 + slot * 8 + n % 8.
 struct PackParams {
   const float* w[8];
   uint8_t* dst;
@@ -347,59 +373,51 @@ struct PackParams {
   int rows_real, k_real;        // real extent of the row (N side) and K side
   int transposed;
   int wsO, wsI, wsT;
+  int pair_xor, NB8;            // pair fusion; rows per image = NB8 then, NBp otherwise
 };
-__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackParams p) {
-  const int items = p.n_img * p.ntaps * p.J * 2 * p.NBp;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-    int r = it;
-    const int n = r % p.NBp; r /= p.NBp;
-    const int kc = r & 1; r >>= 1;
-    const int j = r % p.J; r /= p.J;
-    const int tap = r % p.ntaps;
-    const int img = r / p.ntaps;
-    __align__(16) __nv_bfloat16 v[8];
+__device__ __forceinline__ int pack_rows(const PackParams& p) { return p.pair_xor ? p.NB8 : p.NBp; }
+__device__ __forceinline__ void pack_item(const PackParams& p, int it) {
+  const int rows = pack_rows(p);
+  int r = it;
+  const int n = r % rows; r /= rows;
+  const int kc = r & 1; r >>= 1;
+  const int j = r % p.J; r /= p.J;
+  const int tap = r % p.ntaps;
+  const int img = r / p.ntaps;
+  __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const int k = j * 16 + kc * 8 + jj;
-      float x = 0.f;
-      if (n < p.rows_real && k < p.k_real) {
-        const int o = p.transposed ? k : n, i = p.transposed ? n : k;
-        x = __ldg(p.w[img] + (long long)o * p.wsO + (long long)i * p.wsI + (long long)tap * p.wsT);
-      }
-      v[jj] = __float2bfloat16_rn(x);
+  for (int jj = 0; jj < 8; ++jj) {
+    const int k = j * 16 + kc * 8 + jj;
+    float x = 0.f;
+    if (n < p.rows_real && k < p.k_real) {
+      const int o = p.transposed ? k : n, i = p.transposed ? n : k;
+      x = __ldg(p.w[img] + (long long)o * p.wsO + (long long)i * p.wsI + (long long)tap * p.wsT);
     }
-    uint8_t* dst = p.dst + ((size_t)(img * p.ntaps + tap) * p.J + j) * ((size_t)p.NBp * 32) +
-                   (size_t)kc * (p.NBp * 16) + (n >> 3) * 128 + (n & 7) * 16;
-    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    v[jj] = __float2bfloat16_rn(x);
   }
+  uint8_t* dst;
+  if (p.pair_xor) {
+    const int m = p.pair_xor, lo = img & ~m, slot = (img & m) ? 1 : 0;
+    const int q = m == 1 ? (lo >> 1) : ((lo >> 2) * 2 + (lo & 1));       // index of the pair among the lower images
+    const int nf = (n >> 3) * 16 + slot * 8 + (n & 7), NBf = 2 * p.NB8;
+    dst = p.dst + ((size_t)(q * p.ntaps + tap) * p.J + j) * ((size_t)NBf * 32) + (size_t)kc * (NBf * 16) +
+          (nf >> 3) * 128 + (nf & 7) * 16;
+  } else {
+    dst = p.dst + ((size_t)(img * p.ntaps + tap) * p.J + j) * ((size_t)p.NBp * 32) + (size_t)kc * (p.NBp * 16) +
+          (n >> 3) * 128 + (n & 7) * 16;
+  }
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+}
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackParams p) {
+  const int items = p.n_img * p.ntaps * p.J * 2 * pack_rows(p);
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) pack_item(p, it);
 }
 
 // the same for many layers in one launch: blockIdx.y selects an entry of a device-resident parameter table
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackParams* __restrict__ table) {
   const PackParams p = table[blockIdx.y];
-  const int items = p.n_img * p.ntaps * p.J * 2 * p.NBp;
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
-    int r = it;
-    const int n = r % p.NBp; r /= p.NBp;
-    const int kc = r & 1; r >>= 1;
-    const int j = r % p.J; r /= p.J;
-    const int tap = r % p.ntaps;
-    const int img = r / p.ntaps;
-    __align__(16) __nv_bfloat16 v[8];
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const int k = j * 16 + kc * 8 + jj;
-      float x = 0.f;
-      if (n < p.rows_real && k < p.k_real) {
-        const int o = p.transposed ? k : n, i = p.transposed ? n : k;
-        x = __ldg(p.w[img] + (long long)o * p.wsO + (long long)i * p.wsI + (long long)tap * p.wsT);
-      }
-      v[jj] = __float2bfloat16_rn(x);
-    }
-    uint8_t* dst = p.dst + ((size_t)(img * p.ntaps + tap) * p.J + j) * ((size_t)p.NBp * 32) +
-                   (size_t)kc * (p.NBp * 16) + (n >> 3) * 128 + (n & 7) * 16;
-    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
-  }
+  const int items = p.n_img * p.ntaps * p.J * 2 * pack_rows(p);
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) pack_item(p, it);
 }
 
 static int g_num_sms = 0;
@@ -427,13 +445,52 @@ cl::OperandLayout gy_operand_layout(const ConvGeom& fwd) {
   return cl::operand_layout(fwd.tab.nc, fwd.tab.nc * fwd.Oc, fwd.tab.nc == 1 || fwd.Oc < 8);
 }
 
+// block (pass-out component a, pass-in component b) of the expanded weight: image index (-1: structural zero) and sign
+static void pass_block(const ConvGeom& g, int a, int b, int* img, int* neg) {
+  const int fa = g.transposed ? b : a, fb = g.transposed ? a : b;   // forward-sense (out, in) components
+  *img = g.tab.widx[fa][fb];
+  *neg = g.tab.sign[fa][fb] < 0;
+}
+
+// Pair fusion (conv_cl.h): with out components paired as {a, a ^ m}, does every pair see at most two
+// (slot order, relative sign) classes over the in components?  Fills set_of[a0][b] (a0 = lower member) with the
+// class index of block column b, or -1 where the pair has a structural zero.
+static bool pairing_works(const ConvGeom& g, int m, int8_t set_of[8][8]) {
+  const int nc = g.tab.nc;
+  for (int a0 = 0; a0 < nc; ++a0) {
+    if (a0 & m) continue;
+    const int a1 = a0 | m;
+    int nclass = 0, key[2] = {0, 0};
+    for (int b = 0; b < nc; ++b) {
+      int e0, e1, s0, s1;
+      pass_block(g, a0, b, &e0, &s0);
+      pass_block(g, a1, b, &e1, &s1);
+      set_of[a0][b] = -1;
+      if (e0 < 0 && e1 < 0) continue;
+      if (e0 < 0 || e1 < 0 || (e0 ^ e1) != m) return false;
+      const int k = (((e0 & m) != 0) ? 2 : 0) | (s0 ^ s1);
+      int c = 0;
+      while (c < nclass && key[c] != k) ++c;
+      if (c == nclass) {
+        if (nclass == 2) return false;
+        key[nclass++] = k;
+      }
+      set_of[a0][b] = (int8_t)c;
+    }
+  }
+  return true;
+}
+
 // geometry of the resident weight tiles of one pass
 struct WeightPlan {
   int dense, n_img, ntaps, J, NBp, rows_real, k_real;
+  int fuse, pair_xor, NB8, NBmma;   // pair fusion: a tile holds the two images of a pair, N = NBmma = 2 * NB8
+  int n_tilesets;                   // images, or image pairs when fused
   size_t slab_bytes, img_bytes, total;
 };
 static WeightPlan weight_plan(const ConvGeom& g) {
   WeightPlan w;
+  memset(&w, 0, sizeof(w));
   w.dense = cl::is_dense(g) ? 1 : 0;
   w.ntaps = g.KH * g.KW;
   if (w.dense) {
@@ -442,10 +499,19 @@ static WeightPlan weight_plan(const ConvGeom& g) {
   } else {
     const int kc = g.transposed ? g.Oc : g.Ic, pc = g.transposed ? g.Ic : g.Oc;
     w.n_img = g.tab.nw; w.J = cl::round_up(kc, 16) / 16; w.NBp = cl::round_up(pc, 16); w.rows_real = pc; w.k_real = kc;
+    static const bool enabled = getenv("SELDQ_PAIR_FUSE") == nullptr || atoi(getenv("SELDQ_PAIR_FUSE")) != 0;
+    if (enabled && g.tab.nc >= 4 && (pc & 7) == 0 && pc <= 128 && (w.n_img & 1) == 0) {
+      int8_t scratch[8][8];
+      for (int m = 1; m <= 2 && !w.fuse; ++m)
+        if (pairing_works(g, m, scratch)) { w.fuse = 1; w.pair_xor = m; }
+    }
   }
-  w.slab_bytes = (size_t)w.NBp * 32;
+  w.NB8 = cl::round_up(w.rows_real, 8);
+  w.NBmma = w.fuse ? 2 * w.NB8 : w.NBp;
+  w.n_tilesets = w.fuse ? w.n_img / 2 : w.n_img;
+  w.slab_bytes = (size_t)w.NBmma * 32;
   w.img_bytes = (size_t)w.ntaps * w.J * w.slab_bytes;
-  w.total = (size_t)w.n_img * w.img_bytes;
+  w.total = (size_t)w.n_tilesets * w.img_bytes;
   return w;
 }
 
@@ -464,7 +530,8 @@ int launch_pack_weights(const ConvGeom& g, const float* const* host_w, void* pac
   p.n_img = w.n_img; p.ntaps = w.ntaps; p.J = w.J; p.NBp = w.NBp;
   p.rows_real = w.rows_real; p.k_real = w.k_real; p.transposed = g.transposed;
   p.wsO = g.wsO; p.wsI = g.wsI; p.wsT = g.wsT;
-  const int items = w.n_img * w.ntaps * w.J * 2 * w.NBp;
+  p.pair_xor = w.fuse ? w.pair_xor : 0; p.NB8 = w.NB8;
+  const int items = w.n_img * w.ntaps * w.J * 2 * (w.fuse ? w.NB8 : w.NBp);
   int blocks = (items + 255) / 256;
   if (blocks > 4 * cl::num_sms()) blocks = 4 * cl::num_sms();
   cl::pack_weights_kernel<<<blocks, 256, 0, st>>>(p);
@@ -485,7 +552,8 @@ int fill_pack_table_entry(const ConvGeom& g, const float* const* host_w, void* p
     p.n_img = w.n_img; p.ntaps = w.ntaps; p.J = w.J; p.NBp = w.NBp;
     p.rows_real = w.rows_real; p.k_real = w.k_real; p.transposed = g.transposed;
     p.wsO = g.wsO; p.wsI = g.wsI; p.wsT = g.wsT;
-    *items = w.n_img * w.ntaps * w.J * 2 * w.NBp;
+    p.pair_xor = w.fuse ? w.pair_xor : 0; p.NB8 = w.NB8;
+    *items = w.n_img * w.ntaps * w.J * 2 * (w.fuse ? w.NB8 : w.NBp);
   }
   memcpy(entry, &p, sizeof(p));
   return SELDQ_OK;
@@ -553,15 +621,39 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
   const long long tiles = (long long)g.N * g.OH * p->tiles_w;
   if (tiles > 0x0fffffffLL) return fail(SELDQ_ERR_UNSUPPORTED, "too many tiles");
   p->total_tiles = (int)tiles;
-  // out-component groups: as few as TMEM allows, more while that helps to fill the SMs
+  // out-component groups: as few as TMEM allows, more while that helps to fill the SMs.  A component costs NBp
+  // accumulator columns, or 2 * NB8 when pairs are fused (two column sets per pair); fused groups hold whole pairs.
+  p->fuse = w.fuse; p->pair_xor = w.pair_xor; p->NB8 = w.NB8; p->NBmma = w.NBmma;
+  const int cols_per_comp = w.fuse ? 2 * w.NB8 : w.NBp;
+  const int max_groups = w.fuse ? p->ncomp_out / 2 : p->ncomp_out;
   int ngroups = 1;
-  while (p->ncomp_out / ngroups * p->NBp > 512 && ngroups < p->ncomp_out) ngroups *= 2;
-  if (p->ncomp_out / ngroups * p->NBp > 512)
+  while (p->ncomp_out / ngroups * cols_per_comp > 512 && ngroups < max_groups) ngroups *= 2;
+  if (p->ncomp_out / ngroups * cols_per_comp > 512)
     return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path supports at most 512 out channels per component");
-  while (ngroups < p->ncomp_out && tiles * ngroups * 2 <= cl::num_sms() + cl::num_sms() / 16) ngroups *= 2;
+  while (ngroups < max_groups && tiles * ngroups * 2 <= cl::num_sms() + cl::num_sms() / 16) ngroups *= 2;
   p->ngroups = ngroups;
   p->gc = p->ncomp_out / ngroups;
+  p->mma_per_slab = w.fuse ? p->gc / 2 : p->gc;
+  p->acc_cols = p->gc * cols_per_comp;
   p->total_units = (int)(tiles * ngroups);
+  // members of the groups.  Unfused: consecutive components.  Fused: consecutive PAIRS {a0, a0 ^ pair_xor} in the
+  // order of their lower members; local component 2 q + t is member t of the group's pair q.
+  int8_t set_of[8][8];
+  if (w.fuse) {
+    if (!pairing_works(g, w.pair_xor, set_of)) return fail(SELDQ_ERR_INVALID, "pair fusion: inconsistent pairing");
+    int lower[4], nl = 0;
+    for (int a = 0; a < p->ncomp_out; ++a)
+      if (!(a & w.pair_xor)) lower[nl++] = a;
+    const int ppg = p->gc / 2;
+    for (int gi = 0; gi < ngroups; ++gi)
+      for (int q = 0; q < ppg; ++q) {
+        p->comp_of[gi][2 * q] = (int8_t)lower[gi * ppg + q];
+        p->comp_of[gi][2 * q + 1] = (int8_t)(lower[gi * ppg + q] | w.pair_xor);
+      }
+  } else {
+    for (int gi = 0; gi < ngroups; ++gi)
+      for (int al = 0; al < p->gc; ++al) p->comp_of[gi][al] = (int8_t)(gi * p->gc + al);
+  }
   // cost (number of non-zero blocks) and needed chunks per group
   int cost[8];
   for (int gi = 0; gi < ngroups; ++gi) {
@@ -571,7 +663,7 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
       for (int s = 0; s < p->slabs_per_chunk; ++s) {
         const int b = (c * l.BK + s * 16) / l.cpad;
         for (int al = 0; al < p->gc; ++al)
-          if (p->op_img[b][gi * p->gc + al] >= 0) { mask |= 1u << c; ++cost[gi]; }
+          if (p->op_img[b][p->comp_of[gi][al]] >= 0) { mask |= 1u << c; ++cost[gi]; }
       }
     p->chunk_mask[gi] = mask;
     p->group_order[gi] = gi;
@@ -581,39 +673,69 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
       const int t = p->group_order[j]; p->group_order[j] = p->group_order[j - 1]; p->group_order[j - 1] = t;
     }
 
-  // MMA op table (conv_cl.h): per (group, chunk) the valid MMAs in (slab, component) order, zero-padded to
-  // slabs_per_chunk * gc entries.  `first` = the first MMA of a unit into out component a's accumulator columns
+  // MMA op table (conv_cl.h): per (group, chunk) the valid MMAs in (slab, component | pair) order, zero-padded to
+  // slabs_per_chunk * mma_per_slab entries.  `first` = the first MMA of a unit into its accumulator columns
   // (chunks outside the group's mask hold no valid entry for its components by construction).
-  if (p->chunks * p->slabs_per_chunk * p->ncomp_out > cl::kOpTableEntries)
+  const int lps = p->slabs_per_chunk * p->mma_per_slab;
+  p->op_entries = ngroups * p->chunks * lps;
+  if (p->op_entries > cl::kOpTableEntries)
     return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: too many (slab, component) pairs for the MMA op table");
-  if (p->slabs_per_chunk * p->gc > 32)
-    return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: more than 32 MMAs per stage");
+  if (lps > 32) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: more than 32 MMAs per stage");
+  if (p->acc_cols > 512) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: accumulators do not fit in tensor memory");
   // Narrow K side (first CNN layer: one 16-channel slab per tap): a stage per tap is a 4 KB box and one MMA, so the
   // producer's and the issuers' per-stage bookkeeping (~0.3 us) would bound the layer; all taps share one stage then.
-  if (l.BK <= 16 && ntaps * p->slabs_per_chunk * p->gc <= 32 && !getenv("SELDQ_NO_TPS")) p->tps = ntaps;
+  if (l.BK <= 16 && ntaps * lps <= 32 && !getenv("SELDQ_NO_TPS")) p->tps = ntaps;
   p->stage_bytes = p->box_bytes * (uint32_t)p->tps;
   p->tap_stride16 = (uint32_t)(((size_t)p->J * p->slab_bytes) >> 4);
   {
-    const uint32_t idesc = ptx::make_idesc_bf16(cl::kTileM, (uint32_t)p->NBp, 0, 0, 0, 0);
-    const int lps = p->slabs_per_chunk * p->gc;
+    const uint32_t idesc = ptx::make_idesc_bf16(cl::kTileM, (uint32_t)p->NBmma, 0, 0, 0, 0);
     for (int gi = 0; gi < ngroups; ++gi) {
-      bool seen[8] = {false, false, false, false, false, false, false, false};
+      bool seen[8][2];
+      memset(seen, 0, sizeof(seen));
+      for (int al = 0; al < 8; ++al)
+        for (int st = 0; st < 2; ++st) { p->epi_col[gi][al][st] = 0; p->epi_sgn[gi][al][st] = 0; }
       for (int c = 0; c < p->chunks; ++c) {
         uint2* dst = p->op_tbl + ((size_t)gi * p->chunks + c) * lps;
         int n = 0;
         for (int s = 0; s < p->slabs_per_chunk; ++s)
-          for (int al = 0; al < p->gc; ++al) {
+          for (int ml = 0; ml < p->mma_per_slab; ++ml) {
             const int ch0 = (c * p->slabs_per_chunk + s) * 16;
             const int b = ch0 / l.cpad;
             const int j = (ch0 - b * l.cpad) >> 4;
-            const int a = gi * p->gc + al;
-            const int img = p->op_img[b][a];
-            if (img < 0) continue;
+            uint32_t col, tile16, neg;
+            int fi, fs;                                       // which `seen` flag this MMA initialises
+            if (!w.fuse) {
+              const int a = p->comp_of[gi][ml];
+              const int img = p->op_img[b][a];
+              if (img < 0) continue;
+              col = (uint32_t)(ml * p->NBp);
+              tile16 = (uint32_t)(((size_t)img * p->img_bytes + (size_t)j * p->slab_bytes) >> 4);
+              neg = (uint32_t)p->op_neg[b][a];
+              fi = ml; fs = 0;
+            } else {
+              const int a0 = p->comp_of[gi][2 * ml], a1 = p->comp_of[gi][2 * ml + 1], m = w.pair_xor;
+              const int e0 = p->op_img[b][a0], e1 = p->op_img[b][a1];
+              if (e0 < 0) continue;
+              const int st = set_of[a0][b];
+              const int lo = e0 & ~m, slot0 = (e0 & m) ? 1 : 0;
+              const int q = m == 1 ? (lo >> 1) : ((lo >> 2) * 2 + (lo & 1));
+              const int rel = p->op_neg[b][a0] ^ p->op_neg[b][a1];
+              (void)e1;
+              col = (uint32_t)((ml * 2 + st) * p->NBmma);
+              tile16 = (uint32_t)(((size_t)q * p->img_bytes + (size_t)j * p->slab_bytes) >> 4);
+              neg = (uint32_t)p->op_neg[b][a0];                // a0's product enters with sign +
+              fi = ml; fs = st;
+              // epilogue: member 0 reads slot0 of this set with +, member 1 the other slot with the relative sign
+              p->epi_col[gi][2 * ml][st] = (uint16_t)(col + slot0 * 8);
+              p->epi_sgn[gi][2 * ml][st] = 1;
+              p->epi_col[gi][2 * ml + 1][st] = (uint16_t)(col + (slot0 ^ 1) * 8);
+              p->epi_sgn[gi][2 * ml + 1][st] = (int8_t)(rel ? -1 : 1);
+            }
+            if (col > 0x1ffu || tile16 > 0x3fffu) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: op table field overflow");
             uint2 e;
-            e.x = (1u << 31) | (seen[al] ? 0u : (1u << 30)) | ((uint32_t)al << 20) | ((uint32_t)s << 16) |
-                  (uint32_t)(((size_t)img * p->img_bytes + (size_t)j * p->slab_bytes) >> 4);
-            e.y = idesc | ((uint32_t)p->op_neg[b][a] << 14);
-            seen[al] = true;
+            e.x = (1u << 31) | (seen[fi][fs] ? 0u : (1u << 30)) | (col << 20) | ((uint32_t)s << 16) | tile16;
+            e.y = idesc | (neg << 14);
+            seen[fi][fs] = true;
             dst[n++] = e;
           }
         if (n > 0) dst[n - 1].x |= 1u << 29;                 // the lane that issues last commits the stage
@@ -621,7 +743,7 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
       }
     }
   }
-  const int acc_cols = p->gc * p->NBp;
+  const int acc_cols = p->acc_cols;
   p->acc_stages = acc_cols * 2 <= 512 ? 2 : 1;
   int cols = 32;
   while (cols < acc_cols * p->acc_stages) cols <<= 1;

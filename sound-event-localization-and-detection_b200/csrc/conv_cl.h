@@ -92,9 +92,25 @@ struct FpropParams {
   int8_t op_img[8][8];          // [in comp b][out comp a] -> image index or -1
   int8_t op_neg[8][8];
   int nstages, acc_stages, tmem_cols;
+  // Pair fusion (fuse = 1).  A small-N tcgen05.mma costs ~45 cycles whatever its N (it is bound by loading its A
+  // slab: tools/umma_ts.py), so the per-block MMAs of N = 24..48 leave half of the tensor pipe idle.  Two out
+  // components a0, a1 = a0 ^ pair_xor always read the two images of one image pair {i, i ^ pair_xor}; with the
+  // pair's tiles interleaved by 8-row groups in shared memory ([8 rows of image i][8 rows of i ^ pair_xor] ...) ONE
+  // MMA of N = 2 * NB8 serves both.  Which slot holds whose product, and the sign of a1's product relative to a0's
+  // (a0's own sign is the negate-B bit), depend on the in component only through TWO classes, so each pair
+  // accumulates into two column sets and the epilogue adds / subtracts them (epi_col / epi_sgn).
+  int fuse, pair_xor;
+  int NB8;                      // out channels of one component rounded up to 8 (fuse) -- NBp rounds to 16
+  int NBmma;                    // N of one MMA: NBp, or 2 * NB8 when fused
+  int mma_per_slab;             // MMAs per 16-channel slab and unit: gc, or gc / 2 when fused
+  int acc_cols;                 // accumulator columns of one unit
+  int op_entries;               // valid length of op_tbl
+  int8_t comp_of[8][8];         // [group][local component] -> out component
+  uint16_t epi_col[8][8][2];    // fused: [group][local component][set] -> first accumulator column of its 8-channel
+  int8_t epi_sgn[8][8][2];      //        groups (+ og * 16), and the sign to apply (0: the set does not exist)
   // MMA op table [group][chunk][lane]: the MMAs of one stage dealt to the lanes of the MMA warp (copied to
   // shared memory):
-  //   x = valid << 31 | first << 30 | last-of-stage << 29 | out component << 20 | slab << 16 |
+  //   x = valid << 31 | first << 30 | last-of-stage << 29 | accumulator column offset << 20 (9 bits) | slab << 16 |
   //       (16-byte offset of the weight tile inside one tap's tile set)
   //   y = the complete instruction descriptor (carries the block's sign in its negate-B bit)
   // `first` marks the first MMA of a unit into that out component's accumulator columns (tap 0 only)
