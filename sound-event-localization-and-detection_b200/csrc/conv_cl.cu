@@ -146,10 +146,14 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
           if (!((mask >> c) & 1u)) continue;
           for (int tap = 0; tap < p.ntaps; tap += p.tps) {
             ptx::mbar_wait(&empty_bar[slot], parity ^ 1);
-            ptx::mbar_arrive_expect_tx(&full_bar[slot], p.stage_bytes);
-            for (int tl = 0; tl < p.tps; ++tl)       // one stage = the boxes of p.tps taps
-              ptx::tma_load_4d(a_ring + (size_t)slot * p.stage_bytes + (size_t)tl * p.box_bytes, &tm_in, &full_bar[slot],
-                               c * p.BK, w0 + p.off_w[tap + tl], h + p.off_h[tap + tl], n);
+            ptx::mbar_arrive_expect_tx(&full_bar[slot], p.stage_tx);
+            if (p.rs)                                // one box of 128 + span rows serves the taps of a kernel row
+              ptx::tma_load_4d(a_ring + (size_t)slot * p.stage_bytes, &tm_in, &full_bar[slot], c * p.BK,
+                               w0 + p.rs_min_off, h + p.off_h[tap], n);
+            else
+              for (int tl = 0; tl < p.tps; ++tl)     // one stage = the boxes of p.tps taps
+                ptx::tma_load_4d(a_ring + (size_t)slot * p.stage_bytes + (size_t)tl * p.box_bytes, &tm_in,
+                                 &full_bar[slot], c * p.BK, w0 + p.off_w[tap + tl], h + p.off_h[tap + tl], n);
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }
         }
@@ -177,6 +181,10 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       const int my_entry = kMmaWarps * lane + me;
       const int my_tl = my_entry / lanes_per_chunk;                // tap of the stage this lane's MMA belongs to
       const int my_rest = my_entry - my_tl * lanes_per_chunk;      // ... and its entry in the chunk's op list
+      // where that tap's A operand starts inside a stage: its own box, or a row offset into the shared box
+      const uint32_t my_tap_off16 = my_tl >= p.tps ? 0u
+                                    : p.rs ? (uint32_t)p.rs_row[my_tl] * ((uint32_t)p.BK * 2u >> 4)
+                                           : ((uint32_t)my_tl * p.box_bytes) >> 4;
       if (!p.dense) ptx::mbar_wait(w_bar, 0);
       uint32_t slot = 0, parity = 0, it = 0;
       for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
@@ -202,7 +210,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
           const bool any = vmask != 0u;
           const int closer = any ? 31 - __clz((int)vmask) : -1;
           if (any) last_closer = closer;
-          const uint32_t a_off16 = ((e.x >> 16) & 3u) * 2u + (((uint32_t)my_tl * p.box_bytes) >> 4);
+          const uint32_t a_off16 = ((e.x >> 16) & 3u) * 2u + my_tap_off16;
           const uint32_t d_lane = d_unit + ((e.x >> 20) & 0x1ffu);
           uint32_t b16 = b_lo16 + (e.x & 0x3fffu) + (uint32_t)my_tl * p.tap_stride16;
           for (int tap = 0; tap < p.ntaps; tap += p.tps, b16 += p.tap_stride16 * (uint32_t)p.tps) {
@@ -686,6 +694,18 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
   // producer's and the issuers' per-stage bookkeeping (~0.3 us) would bound the layer; all taps share one stage then.
   if (l.BK <= 16 && ntaps * lps <= 32 && !getenv("SELDQ_NO_TPS")) p->tps = ntaps;
   p->stage_bytes = p->box_bytes * (uint32_t)p->tps;
+  p->box_rows = cl::kTileM;
+  // Row-shared taps (conv_cl.h): the KW taps of a kernel row from one box, if their shifts span at most 8 rows
+  if (p->tps == 1 && l.BK == 64 && g.KW > 1 && (g.KW - 1) * g.dw <= 8 && g.KW * lps <= 32 * cl::kMmaWarps &&
+      !getenv("SELDQ_NO_RS")) {
+    int mn = p->off_w[0];
+    for (int t = 0; t < g.KW; ++t) mn = p->off_w[t] < mn ? p->off_w[t] : mn;
+    p->rs = 1; p->tps = g.KW; p->rs_min_off = mn;
+    for (int t = 0; t < g.KW; ++t) p->rs_row[t] = p->off_w[t] - mn;        // the same for every kernel row
+    p->box_rows = cl::kTileM + (g.KW - 1) * g.dw;
+    p->stage_bytes = (uint32_t)cl::round_up(p->box_rows * l.BK * 2, 1024);
+  }
+  p->stage_tx = p->rs ? (uint32_t)(p->box_rows * l.BK * 2) : p->stage_bytes;
   p->tap_stride16 = (uint32_t)(((size_t)p->J * p->slab_bytes) >> 4);
   {
     const uint32_t idesc = ptx::make_idesc_bf16(cl::kTileM, (uint32_t)p->NBmma, 0, 0, 0, 0);
@@ -787,7 +807,7 @@ int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* ho
   p.out_sN = g.out_sN; p.out_sC = g.out_sC; p.out_sH = g.out_sH;
   const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, p.dense != 0);
   alignas(64) CUtensorMap tm;
-  rc = encode_cl_map(&tm, in_cl, l, g.IW, g.IH, g.N, cl::kTileM);
+  rc = encode_cl_map(&tm, in_cl, l, g.IW, g.IH, g.N, p.box_rows);
   if (rc) return rc;
   const int grid = p.total_units < cl::num_sms() ? p.total_units : cl::num_sms();
   void (*kern)(const CUtensorMap, const FpropParams) = nullptr;

@@ -82,6 +82,13 @@ struct FpropParams {
   uint32_t stage_bytes, a_sbo, a_swz;
   uint32_t box_bytes;           // one TMA box [128 w x BK ch]; a stage holds `tps` of them (taps per stage)
   int tps;
+  // Row-shared taps (rs = 1): the `tps` = KW taps of one kernel row differ only by a small shift along w, so one
+  // box of 128 + span rows serves them all -- each tap's A descriptor starts rs_row[tap % KW] rows into the box (the
+  // tensor core derives the 128B-swizzle phase from the address, tools/umma_probe.py u3) -- and the activation
+  // tile crosses L2 -> shared memory once per kernel row instead of once per tap.
+  int rs, rs_min_off, box_rows;
+  uint32_t stage_tx;            // bytes one stage's TMA traffic signals on its mbarrier
+  int rs_row[kMaxTaps];
   uint32_t chunk_mask[8];       // per group: which channel chunks carry at least one non-zero block
   // N side
   int dense, ncomp_out, Pc, NBp, gc;

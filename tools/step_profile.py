@@ -40,13 +40,16 @@ rows = {}
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
         name = ev.name[:90]
-        r = rows.setdefault(name, [0.0, 0])
+        r = rows.setdefault(name, [0.0, 0, []])
         r[0] += ev.device_time
         r[1] += 1
+        r[2].append(ev.device_time)
 total = sum(r[0] for r in rows.values())
 print("total device time %.3f ms over %d launches" % (total / 1e3, sum(r[1] for r in rows.values())))
-for name, (us, n) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:args.top]:
+for name, (us, n, each) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:args.top]:
     print("%9.1f us %5d x %7.1f us  %5.1f%%  %s" % (us, n, us / n, 100 * us / total, name))
+    if 1 < n <= 10 and us > 100:
+        print("             each: " + " ".join("%.0f" % e for e in each))
 if args.ops:
     print()
     print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=60,

@@ -102,6 +102,8 @@ def main():
         probe_u1(res, rng)
     if only in ("all", "u2"):
         probe_u2(res, rng)
+    if only in ("all", "u3"):
+        probe_u3(res, rng)
     for k, v in res.items():
         print("%-24s %.3e %s" % (k, v, "PASS" if v < 1e-2 else "fail"))
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "umma_probe_%s.json" % only), "w"), indent=1)
@@ -160,6 +162,26 @@ def probe_u2(res, rng):
                        4, 2, 2, NW)
         res["U2_" + name] = err(out, ref2)
 
+
+
+def probe_u3(res, rng):
+    # ---- U3: A operand starting at a row that is not a multiple of 8 inside a K-major SW128 tile: the three
+    #      w-taps of a 3x3 convolution as row-shifted views of ONE [130 w x 64 ch] TMA box.  Does the tensor core
+    #      derive the swizzle phase from the address (base offset 0), or does the descriptor's base-offset field
+    #      (bits 49..51) have to carry row & 7?
+    N = 48
+    A = rng.standard_normal((144, 64))
+    B = rng.standard_normal((N, 64))
+    Ab, Af = bf16_bits(A)
+    Bb, Bf = bf16_bits(B)
+    a_img = image_k_major_sw128(Ab, 144)
+    b_img = image_k_major_noswizzle(Bb, N, 4)
+    for r in (0, 1, 2, 5, 8, 11):
+        ref = Af[r:r + 128] @ Bf.T
+        for name, bo in (("addr", 0), ("baseoff", r & 7)):
+            a_desc = desc_hi(16, 1024, SW_128) + r * 8 + (bo << 49)
+            out = run_umma(a_img, b_img, a_desc, desc_hi(N * 16, 128, SW_NONE), idesc(128, N, 0, 0), 4, 2, (N * 32) // 16, N)
+            res["U3_row%d_%s" % (r, name)] = err(out, ref)
 
 
 def probe_t1(res):
