@@ -268,8 +268,16 @@ def main():
         roof = None
         if k and k["ms"] > 0:
             ach = k["flop"] / (k["ms"] / 1e3) / 1e12
+            # DRAM bytes per launch of the same kernel from the committed Nsight Compute pass (profiles/, made by
+            # tools/profile_trip.sh + tools/ncu_summary.py traffic): a recorded measurement, not taken in this run
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "fprop_traffic.json")
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                if tj.get("kernel") == k["name"]:
+                    traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/fprop_traffic.json (ncu dram__bytes_read + write)"
             roof = dict(bound="tensor", kernel=k["name"], achieved=ach, peak=peaks["tflops"], unit="TFLOP/s",
-                        frac=ach / peaks["tflops"], traffic=None, peak_source=peaks["source"],
+                        frac=ach / peaks["tflops"], traffic=traffic, traffic_source=traffic_src, peak_source=peaks["source"],
                         launches_per_step=k["launches"], avg_launch_us=1e3 * k["ms"] / max(1, k["launches"]),
                         share_of_step=k["ms"] / (ms / args.steps),
                         other_kernels_ms_per_step={n: round(v["ms"], 3) for n, v in prof["kernels"].items()})

@@ -15,6 +15,9 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_be
 timeout 300 python tools/step_profile.py --top 60 2>&1 | grep -v "Warn\|_warn\|_ACCUMULATE" > $O/${TAG}_step_profile_b1.txt; echo "step profile rc=$?"
 timeout 300 python tools/kernel_bench.py --skip-conv --out $O/${TAG}_stft.json > $O/${TAG}_stft.log 2>&1; echo "stft rc=$?"; grep stft $O/${TAG}_stft.log | cut -c1-160
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_ncu_launches.csv python tools/ncu_step.py --stft > $O/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+# DRAM traffic of every convolution launch of one step (the roofline's `traffic`: tools/ncu_summary.py traffic)
+timeout 600 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+  -k regex:qconv_cl_fprop_kernel --csv --log-file $O/${TAG}_ncu_traffic.csv python tools/ncu_step.py > $O/${TAG}_ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
 # full captures of the top kernels, a few launches each (ncu replays every kernel ~40 times)
 i=0
 for spec in "qconv_cl_fprop_kernel:14" "qconv_cl_wgrad_kernel:6" "first_layer_bwd_kernel:1" "cnn_tail_fwd_vec_kernel:2" "cnn_tail_bwd_apply_vec_kernel:1" "stft_magphase_kernel:2" "gate_fwd_kernel:1" "gate_bwd_apply_kernel:1"; do
