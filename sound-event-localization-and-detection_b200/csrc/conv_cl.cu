@@ -47,6 +47,12 @@ namespace cl {
 
 // fp16 store of a convolution output, saturating (the value range of fp16 ends at 65504)
 __device__ __forceinline__ __half to_f16_sat(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+// two values at once: cvt.rn.satfinite.f16x2.f32 clamps to +-65504 and packs {hi, lo} in one instruction
+__device__ __forceinline__ uint32_t to_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 // Unit schedule of a CTA: units are ordered heaviest group first; round r hands unit r*G + b to CTA b in even rounds
 // and r*G + (G-1-b) in odd rounds (snake order), so the few units of a last, partial round go to the CTAs that
@@ -284,15 +290,19 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
             ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
             ptx::tmem_ld_wait();
           } else {
-            // pair fusion: channels [c0, c0 + 8) and [c0 + 8, c0 + 16) of this component are 8-column groups of the
-            // pair's (up to) two column sets; sum them with the component's signs (conv_cl.h)
-            uint32_t u[2][2][8];
+            // fusion: channels [c0, c0 + 8) and [c0 + 8, c0 + 16) of this component are 8-column groups of the
+            // (up to four) column sets of its pair / quad; sum them with the component's signs (conv_cl.h)
+            const uint32_t og_stride = 8u * (uint32_t)p.fuse;
+            // all loads of the piece in flight before the one wait (a wait per column set would serialise four
+            // tensor-memory round trips); sets that do not exist load column 0 and are multiplied by 0
+            uint32_t u[4][2][8];
 #pragma unroll
-            for (int st = 0; st < 2; ++st)
+            for (int st = 0; st < 4; ++st)
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {
-                if (p.epi_sgn[group][al][st] != 0 && c0 + hf * 8 < p.Pc)
-                  ptx::tmem_ld8(t_row + (uint32_t)p.epi_col[group][al][st] + (uint32_t)((c0 >> 3) + hf) * 16u, u[st][hf]);
+                const bool on = p.epi_sgn[group][al][st] != 0 && c0 + hf * 8 < p.Pc;       // warp-uniform
+                if (on)
+                  ptx::tmem_ld8(t_row + (uint32_t)p.epi_col[group][al][st] + (uint32_t)((c0 >> 3) + hf) * og_stride, u[st][hf]);
                 else {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) u[st][hf][j] = 0u;
@@ -300,11 +310,13 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
               }
             ptx::tmem_ld_wait();
             const float s0 = (float)p.epi_sgn[group][al][0], s1 = (float)p.epi_sgn[group][al][1];
+            const float s2 = (float)p.epi_sgn[group][al][2], s3 = (float)p.epi_sgn[group][al][3];
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                v[hf * 8 + j] = __float_as_uint(s0 * __uint_as_float(u[0][hf][j]) + s1 * __uint_as_float(u[1][hf][j]));
+                v[hf * 8 + j] = __float_as_uint(fmaf(s3, __uint_as_float(u[3][hf][j]), fmaf(s2, __uint_as_float(u[2][hf][j]),
+                                                fmaf(s1, __uint_as_float(u[1][hf][j]), s0 * __uint_as_float(u[0][hf][j])))));
           }
           if (p.out16 && vec16) {
             // fp16 output in the tensor's own NCHW order (fused CNN-block path, epilogue.cu): the warp's
@@ -315,8 +327,11 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
             for (int r = 0; r < 2; ++r) {                      // 8 channels per pass: [8 ch][32 w] staging
               if (p.bias == nullptr) {        // the common case (--use_bias_conv=False): no per-element select / load / add
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  *reinterpret_cast<__half*>(stg + j * 64 + lane * 2) = to_f16_sat(__uint_as_float(v[r * 8 + j]));
+                for (int j = 0; j < 8; j += 2) {
+                  const uint32_t h2 = to_f16x2_sat(__uint_as_float(v[r * 8 + j]), __uint_as_float(v[r * 8 + j + 1]));
+                  *reinterpret_cast<uint16_t*>(stg + j * 64 + lane * 2) = (uint16_t)(h2 & 0xffffu);
+                  *reinterpret_cast<uint16_t*>(stg + (j + 1) * 64 + lane * 2) = (uint16_t)(h2 >> 16);
+                }
               } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -372,8 +387,9 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 // compact fp32 weights -> bf16 UMMA B tiles [img][tap][j][NBp x 16] (K-major, no swizzle; see the dense
 // prologue above for the byte layout).  Row n / column k of tile (img, tap, j):
 //   forward : W_img[o = n][i = 16 j + k][tap]        dgrad : W_img[o = 16 j + k][i = n][tap]
-// Pair fusion (pair_xor != 0): tile (image pair q, tap, j) is [2 NB8 x 16]; its 8-row groups alternate between
-// the pair's lower image (i & pair_xor == 0) and upper image: row (n / 8) * 16 + slot * 8 + n % 8.
+// Fusion (pair_xor = m != 0; F = 2 for m = 1 | 2, F = 4 for m = 3): tile (image set q, tap, j) is [F NB8 x 16]; its
+// 8-row groups cycle through the F images {i0 | sub : sub a submask of m} of the set:
+// row (n / 8) * 8 F + slot * 8 + n % 8, slot = the bits of the image index under m.
 struct PackParams {
   const float* w[8];
   uint8_t* dst;
@@ -384,6 +400,10 @@ struct PackParams {
   int pair_xor, NB8;            // pair fusion; rows per image = NB8 then, NBp otherwise
 };
 __device__ __forceinline__ int pack_rows(const PackParams& p) { return p.pair_xor ? p.NB8 : p.NBp; }
+// position of image (or component) index i inside its fusion set, and the index of that set: the bits of i under
+// the mask m, and the remaining bits squeezed together
+__host__ __device__ __forceinline__ int fuse_slot(int i, int m) { return m == 1 ? (i & 1) : m == 2 ? ((i >> 1) & 1) : (i & 3); }
+__host__ __device__ __forceinline__ int fuse_set(int i, int m) { return m == 1 ? (i >> 1) : m == 2 ? (((i >> 2) << 1) | (i & 1)) : (i >> 2); }
 __device__ __forceinline__ void pack_item(const PackParams& p, int it) {
   const int rows = pack_rows(p);
   int r = it;
@@ -405,9 +425,9 @@ __device__ __forceinline__ void pack_item(const PackParams& p, int it) {
   }
   uint8_t* dst;
   if (p.pair_xor) {
-    const int m = p.pair_xor, lo = img & ~m, slot = (img & m) ? 1 : 0;
-    const int q = m == 1 ? (lo >> 1) : ((lo >> 2) * 2 + (lo & 1));       // index of the pair among the lower images
-    const int nf = (n >> 3) * 16 + slot * 8 + (n & 7), NBf = 2 * p.NB8;
+    const int m = p.pair_xor, F = m == 3 ? 4 : 2;
+    const int slot = fuse_slot(img, m), q = fuse_set(img, m);
+    const int nf = (n >> 3) * (8 * F) + slot * 8 + (n & 7), NBf = F * p.NB8;
     dst = p.dst + ((size_t)(q * p.ntaps + tap) * p.J + j) * ((size_t)NBf * 32) + (size_t)kc * (NBf * 16) +
           (nf >> 3) * 128 + (nf & 7) * 16;
   } else {
@@ -460,40 +480,49 @@ static void pass_block(const ConvGeom& g, int a, int b, int* img, int* neg) {
   *neg = g.tab.sign[fa][fb] < 0;
 }
 
-// Pair fusion (conv_cl.h): with out components paired as {a, a ^ m}, does every pair see at most two
-// (slot order, relative sign) classes over the in components?  Fills set_of[a0][b] (a0 = lower member) with the
-// class index of block column b, or -1 where the pair has a structural zero.
-static bool pairing_works(const ConvGeom& g, int m, int8_t set_of[8][8]) {
-  const int nc = g.tab.nc;
+// Fusion (conv_cl.h): with the out components grouped as {a0 | sub : sub a submask of m} (pairs for m = 1 | 2, quads
+// for m = 3), does every group see at most `max_sets` (slot order, relative signs) classes over the in components?
+// Fills set_of[a0][b] (a0 = lowest member) with the class index of block column b, or -1 where the group has a
+// structural zero, and returns the number of classes needed (0: this grouping does not work).
+static int fusion_sets(const ConvGeom& g, int m, int max_sets, int8_t set_of[8][8]) {
+  const int nc = g.tab.nc, F = m == 3 ? 4 : 2;
+  int need = 0;
   for (int a0 = 0; a0 < nc; ++a0) {
     if (a0 & m) continue;
-    const int a1 = a0 | m;
-    int nclass = 0, key[2] = {0, 0};
+    int nclass = 0, key[4] = {0, 0, 0, 0};
     for (int b = 0; b < nc; ++b) {
-      int e0, e1, s0, s1;
-      pass_block(g, a0, b, &e0, &s0);
-      pass_block(g, a1, b, &e1, &s1);
+      int e[4], sg[4], nz = 0, used = 0, k = 0;
+      for (int t = 0, sub = 0; t < F; ++t, sub = (sub - m) & m) {      // submasks of m in increasing order
+        pass_block(g, a0 | sub, b, &e[t], &sg[t]);
+        nz += e[t] >= 0;
+      }
       set_of[a0][b] = -1;
-      if (e0 < 0 && e1 < 0) continue;
-      if (e0 < 0 || e1 < 0 || (e0 ^ e1) != m) return false;
-      const int k = (((e0 & m) != 0) ? 2 : 0) | (s0 ^ s1);
+      if (nz == 0) continue;
+      if (nz != F) return 0;
+      for (int t = 0; t < F; ++t) {
+        if (cl::fuse_set(e[t], m) != cl::fuse_set(e[0], m)) return 0;
+        used |= 1 << cl::fuse_slot(e[t], m);
+        k = (k << 3) | (cl::fuse_slot(e[t], m) << 1) | (sg[t] ^ sg[0]);
+      }
+      if (used != (1 << F) - 1) return 0;
       int c = 0;
       while (c < nclass && key[c] != k) ++c;
       if (c == nclass) {
-        if (nclass == 2) return false;
+        if (nclass == max_sets) return 0;
         key[nclass++] = k;
       }
       set_of[a0][b] = (int8_t)c;
     }
+    need = nclass > need ? nclass : need;
   }
-  return true;
+  return need;
 }
 
 // geometry of the resident weight tiles of one pass
 struct WeightPlan {
   int dense, n_img, ntaps, J, NBp, rows_real, k_real;
-  int fuse, pair_xor, NB8, NBmma;   // pair fusion: a tile holds the two images of a pair, N = NBmma = 2 * NB8
-  int n_tilesets;                   // images, or image pairs when fused
+  int fuse, pair_xor, nsets, NB8, NBmma;   // fusion factor F (0 | 2 | 4): a tile holds the F images of a set, N = F * NB8
+  int n_tilesets;                   // images, or image sets when fused
   size_t slab_bytes, img_bytes, total;
 };
 static WeightPlan weight_plan(const ConvGeom& g) {
@@ -508,15 +537,18 @@ static WeightPlan weight_plan(const ConvGeom& g) {
     const int kc = g.transposed ? g.Oc : g.Ic, pc = g.transposed ? g.Ic : g.Oc;
     w.n_img = g.tab.nw; w.J = cl::round_up(kc, 16) / 16; w.NBp = cl::round_up(pc, 16); w.rows_real = pc; w.k_real = kc;
     static const bool enabled = getenv("SELDQ_PAIR_FUSE") == nullptr || atoi(getenv("SELDQ_PAIR_FUSE")) != 0;
-    if (enabled && g.tab.nc >= 4 && (pc & 7) == 0 && pc <= 128 && (w.n_img & 1) == 0) {
+    static const bool quads = getenv("SELDQ_QUAD_FUSE") == nullptr || atoi(getenv("SELDQ_QUAD_FUSE")) != 0;
+    if (enabled && g.tab.nc >= 4 && (pc & 7) == 0 && pc <= 128 && (w.n_img & 3) == 0) {
       int8_t scratch[8][8];
+      // quads need four column sets of 4 * pc accumulator columns each: they fit for pc <= 32 (the CNN layers)
+      if (quads && 16 * pc <= 512 && (w.nsets = fusion_sets(g, 3, 4, scratch)) > 0) { w.fuse = 4; w.pair_xor = 3; }
       for (int m = 1; m <= 2 && !w.fuse; ++m)
-        if (pairing_works(g, m, scratch)) { w.fuse = 1; w.pair_xor = m; }
+        if ((w.nsets = fusion_sets(g, m, 2, scratch)) > 0) { w.fuse = 2; w.pair_xor = m; }
     }
   }
   w.NB8 = cl::round_up(w.rows_real, 8);
-  w.NBmma = w.fuse ? 2 * w.NB8 : w.NBp;
-  w.n_tilesets = w.fuse ? w.n_img / 2 : w.n_img;
+  w.NBmma = w.fuse ? w.fuse * w.NB8 : w.NBp;
+  w.n_tilesets = w.fuse ? w.n_img / w.fuse : w.n_img;
   w.slab_bytes = (size_t)w.NBmma * 32;
   w.img_bytes = (size_t)w.ntaps * w.J * w.slab_bytes;
   w.total = (size_t)w.n_tilesets * w.img_bytes;
@@ -632,8 +664,9 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
   // out-component groups: as few as TMEM allows, more while that helps to fill the SMs.  A component costs NBp
   // accumulator columns, or 2 * NB8 when pairs are fused (two column sets per pair); fused groups hold whole pairs.
   p->fuse = w.fuse; p->pair_xor = w.pair_xor; p->NB8 = w.NB8; p->NBmma = w.NBmma;
-  const int cols_per_comp = w.fuse ? 2 * w.NB8 : w.NBp;
-  const int max_groups = w.fuse ? p->ncomp_out / 2 : p->ncomp_out;
+  const int F = w.fuse ? w.fuse : 1, S = w.fuse ? w.nsets : 1;
+  const int cols_per_comp = w.fuse ? S * w.NB8 : w.NBp;                // a fused set of F components: S * F * NB8
+  const int max_groups = p->ncomp_out / F;
   int ngroups = 1;
   while (p->ncomp_out / ngroups * cols_per_comp > 512 && ngroups < max_groups) ngroups *= 2;
   if (p->ncomp_out / ngroups * cols_per_comp > 512)
@@ -641,23 +674,22 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
   while (ngroups < max_groups && tiles * ngroups * 2 <= cl::num_sms() + cl::num_sms() / 16) ngroups *= 2;
   p->ngroups = ngroups;
   p->gc = p->ncomp_out / ngroups;
-  p->mma_per_slab = w.fuse ? p->gc / 2 : p->gc;
+  p->mma_per_slab = p->gc / F;
   p->acc_cols = p->gc * cols_per_comp;
   p->total_units = (int)(tiles * ngroups);
   // members of the groups.  Unfused: consecutive components.  Fused: consecutive PAIRS {a0, a0 ^ pair_xor} in the
   // order of their lower members; local component 2 q + t is member t of the group's pair q.
   int8_t set_of[8][8];
   if (w.fuse) {
-    if (!pairing_works(g, w.pair_xor, set_of)) return fail(SELDQ_ERR_INVALID, "pair fusion: inconsistent pairing");
+    if (fusion_sets(g, w.pair_xor, S, set_of) != S) return fail(SELDQ_ERR_INVALID, "fusion: inconsistent grouping");
     int lower[4], nl = 0;
     for (int a = 0; a < p->ncomp_out; ++a)
       if (!(a & w.pair_xor)) lower[nl++] = a;
-    const int ppg = p->gc / 2;
+    const int spg = p->gc / F;                       // fused sets per group; local component F q + t = member t of set q
     for (int gi = 0; gi < ngroups; ++gi)
-      for (int q = 0; q < ppg; ++q) {
-        p->comp_of[gi][2 * q] = (int8_t)lower[gi * ppg + q];
-        p->comp_of[gi][2 * q + 1] = (int8_t)(lower[gi * ppg + q] | w.pair_xor);
-      }
+      for (int q = 0; q < spg; ++q)
+        for (int t = 0, sub = 0; t < F; ++t, sub = (sub - w.pair_xor) & w.pair_xor)
+          p->comp_of[gi][F * q + t] = (int8_t)(lower[gi * spg + q] | sub);
   } else {
     for (int gi = 0; gi < ngroups; ++gi)
       for (int al = 0; al < p->gc; ++al) p->comp_of[gi][al] = (int8_t)(gi * p->gc + al);
@@ -710,10 +742,10 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
   {
     const uint32_t idesc = ptx::make_idesc_bf16(cl::kTileM, (uint32_t)p->NBmma, 0, 0, 0, 0);
     for (int gi = 0; gi < ngroups; ++gi) {
-      bool seen[8][2];
+      bool seen[8][4];
       memset(seen, 0, sizeof(seen));
       for (int al = 0; al < 8; ++al)
-        for (int st = 0; st < 2; ++st) { p->epi_col[gi][al][st] = 0; p->epi_sgn[gi][al][st] = 0; }
+        for (int st = 0; st < 4; ++st) { p->epi_col[gi][al][st] = 0; p->epi_sgn[gi][al][st] = 0; }
       for (int c = 0; c < p->chunks; ++c) {
         uint2* dst = p->op_tbl + ((size_t)gi * p->chunks + c) * lps;
         int n = 0;
@@ -733,23 +765,20 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
               neg = (uint32_t)p->op_neg[b][a];
               fi = ml; fs = 0;
             } else {
-              const int a0 = p->comp_of[gi][2 * ml], a1 = p->comp_of[gi][2 * ml + 1], m = w.pair_xor;
-              const int e0 = p->op_img[b][a0], e1 = p->op_img[b][a1];
+              const int a0 = p->comp_of[gi][F * ml], m = w.pair_xor;
+              const int e0 = p->op_img[b][a0];
               if (e0 < 0) continue;
               const int st = set_of[a0][b];
-              const int lo = e0 & ~m, slot0 = (e0 & m) ? 1 : 0;
-              const int q = m == 1 ? (lo >> 1) : ((lo >> 2) * 2 + (lo & 1));
-              const int rel = p->op_neg[b][a0] ^ p->op_neg[b][a1];
-              (void)e1;
-              col = (uint32_t)((ml * 2 + st) * p->NBmma);
-              tile16 = (uint32_t)(((size_t)q * p->img_bytes + (size_t)j * p->slab_bytes) >> 4);
+              col = (uint32_t)((ml * S + st) * p->NBmma);
+              tile16 = (uint32_t)(((size_t)cl::fuse_set(e0, m) * p->img_bytes + (size_t)j * p->slab_bytes) >> 4);
               neg = (uint32_t)p->op_neg[b][a0];                // a0's product enters with sign +
               fi = ml; fs = st;
-              // epilogue: member 0 reads slot0 of this set with +, member 1 the other slot with the relative sign
-              p->epi_col[gi][2 * ml][st] = (uint16_t)(col + slot0 * 8);
-              p->epi_sgn[gi][2 * ml][st] = 1;
-              p->epi_col[gi][2 * ml + 1][st] = (uint16_t)(col + (slot0 ^ 1) * 8);
-              p->epi_sgn[gi][2 * ml + 1][st] = (int8_t)(rel ? -1 : 1);
+              // epilogue: member t reads the 8-column slot of ITS image in this column set, with its sign relative to a0's
+              for (int t = 0; t < F; ++t) {
+                const int at = p->comp_of[gi][F * ml + t];
+                p->epi_col[gi][F * ml + t][st] = (uint16_t)(col + cl::fuse_slot(p->op_img[b][at], m) * 8);
+                p->epi_sgn[gi][F * ml + t][st] = (int8_t)((p->op_neg[b][a0] ^ p->op_neg[b][at]) ? -1 : 1);
+              }
             }
             if (col > 0x1ffu || tile16 > 0x3fffu) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path: op table field overflow");
             uint2 e;

@@ -106,15 +106,16 @@ struct FpropParams {
   // MMA of N = 2 * NB8 serves both.  Which slot holds whose product, and the sign of a1's product relative to a0's
   // (a0's own sign is the negate-B bit), depend on the in component only through TWO classes, so each pair
   // accumulates into two column sets and the epilogue adds / subtracts them (epi_col / epi_sgn).
-  int fuse, pair_xor;
+  int fuse, pair_xor;           // fuse = F: 0 (off), 2 (pairs, pair_xor = 1 | 2) or 4 (quads, pair_xor = 3: four column
+                                // sets, one per in component mod 4 -- fits where 16 * Pc <= 512, the CNN layers)
   int NB8;                      // out channels of one component rounded up to 8 (fuse) -- NBp rounds to 16
   int NBmma;                    // N of one MMA: NBp, or 2 * NB8 when fused
   int mma_per_slab;             // MMAs per 16-channel slab and unit: gc, or gc / 2 when fused
   int acc_cols;                 // accumulator columns of one unit
   int op_entries;               // valid length of op_tbl
   int8_t comp_of[8][8];         // [group][local component] -> out component
-  uint16_t epi_col[8][8][2];    // fused: [group][local component][set] -> first accumulator column of its 8-channel
-  int8_t epi_sgn[8][8][2];      //        groups (+ og * 16), and the sign to apply (0: the set does not exist)
+  uint16_t epi_col[8][8][4];    // fused: [group][local component][set] -> first accumulator column of its 8-channel
+  int8_t epi_sgn[8][8][4];      //        groups (+ og * 8 F), and the sign to apply (0: the set does not exist)
   // MMA op table [group][chunk][lane]: the MMAs of one stage dealt to the lanes of the MMA warp (copied to
   // shared memory):
   //   x = valid << 31 | first << 30 | last-of-stage << 29 | accumulator column offset << 20 (9 bits) | slab << 16 |
