@@ -540,8 +540,10 @@ static WeightPlan weight_plan(const ConvGeom& g) {
     static const bool quads = getenv("SELDQ_QUAD_FUSE") == nullptr || atoi(getenv("SELDQ_QUAD_FUSE")) != 0;
     if (enabled && g.tab.nc >= 4 && (pc & 7) == 0 && pc <= 128 && (w.n_img & 3) == 0) {
       int8_t scratch[8][8];
-      // quads need four column sets of 4 * pc accumulator columns each: they fit for pc <= 32 (the CNN layers)
-      if (quads && 16 * pc <= 512 && (w.nsets = fusion_sets(g, 3, 4, scratch)) > 0) { w.fuse = 4; w.pair_xor = 3; }
+      // quads need four column sets of 4 * pc accumulator columns each: 16 * pc <= 512.  SELDQ_QUAD_FUSE=2 takes them
+      // only where that fits TWICE (pc <= 16), i.e. where MMA and epilogue phases of successive units still overlap
+      static const int quad_cols = (getenv("SELDQ_QUAD_FUSE") && atoi(getenv("SELDQ_QUAD_FUSE")) == 2) ? 256 : 512;
+      if (quads && 16 * pc <= quad_cols && (w.nsets = fusion_sets(g, 3, 4, scratch)) > 0) { w.fuse = 4; w.pair_xor = 3; }
       for (int m = 1; m <= 2 && !w.fuse; ++m)
         if ((w.nsets = fusion_sets(g, m, 2, scratch)) > 0) { w.fuse = 2; w.pair_xor = m; }
     }
@@ -672,6 +674,12 @@ int plan_cl_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
   if (p->ncomp_out / ngroups * cols_per_comp > 512)
     return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path supports at most 512 out channels per component");
   while (ngroups < max_groups && tiles * ngroups * 2 <= cl::num_sms() + cl::num_sms() / 16) ngroups *= 2;
+  // SELDQ_ACC_DOUBLE=1: split once more if that lets the accumulators double-buffer (the epilogue of a unit then
+  // overlaps the MMAs of the next; costs re-loading the shared channel chunks per group)
+  if (getenv("SELDQ_ACC_DOUBLE") && atoi(getenv("SELDQ_ACC_DOUBLE")) != 0 && ngroups < max_groups &&
+      p->ncomp_out / ngroups * cols_per_comp * 2 > 512 && p->ncomp_out / (ngroups * 2) * cols_per_comp * 2 <= 512 &&
+      tiles * ngroups >= cl::num_sms())
+    ngroups *= 2;
   p->ngroups = ngroups;
   p->gc = p->ncomp_out / ngroups;
   p->mma_per_slab = p->gc / F;
