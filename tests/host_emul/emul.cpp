@@ -5,11 +5,127 @@
 #include <cmath>
 #include <vector>
 
+#include "../../sound-event-localization-and-detection_b200/csrc/conv_cl_plan.h"
 #include "../../sound-event-localization-and-detection_b200/csrc/conv_simt.cuh"
 #include "../../sound-event-localization-and-detection_b200/csrc/geom.h"
 #include "../../sound-event-localization-and-detection_b200/csrc/stft.cuh"
 
 using namespace seldq;
+
+
+// ---- channels-last tensor-core path (csrc/conv_cl.cu), data flow on the CPU -----------------------------------------
+// Runs the REAL host plan (cl::plan_fprop: fusion sets, op table, epilogue column / sign table, stage geometry, chunk
+// masks, group schedule) and the REAL pack mapping (cl::pack_dst_offset) through a plain-loop model of what the kernel
+// does with them: TMA boxes with zero fill, one "MMA" per op-table entry (A rows x B rows, K = 16, sign = negate-B
+// bit, accumulate flag honoured), accumulator column sets, epilogue combination.  No rounding to bf16: the result
+// must match the expanded-weight convolution to float accuracy, so any table or offset error shows as O(1).
+static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* const* w, float* out, int n_sms,
+                        int* info) {
+  cl::FpropParams* pp = new cl::FpropParams;
+  cl::FpropParams& p = *pp;
+  size_t smem = 0;
+  int rc = cl::plan_fprop(g, &p, &smem, n_sms);
+  if (rc) { delete pp; return rc; }
+  if (p.dense) { delete pp; return fail(SELDQ_ERR_UNSUPPORTED, "emulation covers the packed (non-dense) path"); }
+  if (info) { info[0] = p.fuse; info[1] = p.pair_xor; info[2] = p.gc; info[3] = p.ngroups; info[4] = p.rs; info[5] = p.tps;
+              info[6] = p.acc_cols; info[7] = p.acc_stages; info[8] = p.nstages; info[9] = (int)smem; }
+  const cl::WeightPlan wp = cl::weight_plan(g);
+  // packed weights as floats, 2 "bytes" per element like the bf16 image
+  std::vector<float> packed(wp.total / 2, 0.f);
+  cl::PackParams pk{};
+  cl::fill_pack_params(g, wp, &pk);
+  const int rows = cl::pack_rows(pk);
+  for (int img = 0; img < pk.n_img; ++img)
+    for (int tap = 0; tap < pk.ntaps; ++tap)
+      for (int j = 0; j < pk.J; ++j)
+        for (int kc = 0; kc < 2; ++kc)
+          for (int n = 0; n < rows; ++n) {
+            const size_t off = cl::pack_dst_offset(pk, img, tap, j, kc, n);
+            if (off + 16 > wp.total) { delete pp; return fail(SELDQ_ERR_INVALID, "pack offset %zu beyond %zu", off, wp.total); }
+            for (int jj = 0; jj < 8; ++jj) {
+              const int k = j * 16 + kc * 8 + jj;
+              float x = 0.f;
+              if (n < pk.rows_real && k < pk.k_real) {
+                const int o = pk.transposed ? k : n, i = pk.transposed ? n : k;
+                x = w[img][(long long)o * pk.wsO + (long long)i * pk.wsI + (long long)tap * pk.wsT];
+              }
+              packed[off / 2 + jj] = x;
+            }
+          }
+  // the channels-last operand: [n][h][w][Cp], every component padded to cpad channels
+  const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, false);
+  std::vector<float> xcl((size_t)g.N * g.IH * g.IW * l.Cp, 0.f);
+  for (int n = 0; n < g.N; ++n)
+    for (int c = 0; c < g.R; ++c)
+      for (int h = 0; h < g.IH; ++h)
+        for (int x = 0; x < g.IW; ++x)
+          xcl[(((size_t)n * g.IH + h) * g.IW + x) * l.Cp + (c / l.cc) * l.cpad + c % l.cc] =
+              in_nchw[n * g.in_sN + c * g.in_sC + h * g.in_sH + x * g.in_sW];
+  auto a_elem = [&](int n, int h, int x, int ch) -> double {          // TMA: out-of-range coordinates read zero
+    if (h < 0 || h >= g.IH || x < 0 || x >= g.IW) return 0.0;
+    return xcl[(((size_t)n * g.IH + h) * g.IW + x) * l.Cp + ch];
+  };
+  const int lpc = p.slabs_per_chunk * p.mma_per_slab;
+  std::vector<double> acc((size_t)cl::kTileM * 512);
+  std::vector<char> init((size_t)512);
+  for (int u = 0; u < p.total_units; ++u) {
+    const int group = p.group_order[u / p.total_tiles];
+    int r = u % p.total_tiles;
+    const int wt = r % p.tiles_w; r /= p.tiles_w;
+    const int h = r % p.OH, n = r / p.OH, w0 = wt * cl::kTileM;
+    std::fill(acc.begin(), acc.end(), 1e30);                          // an accumulator never initialised shows up
+    std::fill(init.begin(), init.end(), 0);
+    for (int c = 0; c < p.chunks; ++c) {
+      if (!((p.chunk_mask[group] >> c) & 1u)) continue;
+      for (int tap0 = 0; tap0 < p.ntaps; tap0 += p.tps)
+        for (int tl = 0; tl < p.tps; ++tl)
+          for (int e_i = 0; e_i < lpc; ++e_i) {
+            const uint2 e = p.op_tbl[((size_t)group * p.chunks + c) * lpc + e_i];
+            if (!((int)e.x < 0)) continue;
+            const int tap = tap0 + tl;
+            const bool first = (e.x & (1u << 30)) != 0u && tap == 0;
+            const int col = (e.x >> 20) & 0x1ff, slab = (e.x >> 16) & 3;
+            const size_t tile = ((size_t)(e.x & 0x3fffu) + (size_t)tap * p.tap_stride16) * 16;   // bytes
+            const int nmma = (e.y >> 17) & 0x3f, neg = (e.y >> 14) & 1;
+            if (nmma * 8 != p.NBmma) { delete pp; return fail(SELDQ_ERR_INVALID, "idesc N %d != NBmma %d", nmma * 8, p.NBmma); }
+            if (tile + (size_t)p.NBmma * 32 > wp.total) { delete pp; return fail(SELDQ_ERR_INVALID, "weight tile beyond the packed buffer"); }
+            if (col + p.NBmma > p.acc_cols) { delete pp; return fail(SELDQ_ERR_INVALID, "accumulator columns %d+%d beyond %d", col, p.NBmma, p.acc_cols); }
+            // where the tap's A rows start: its own box, or rs_row rows into the kernel row's shared box
+            const int x_base = p.rs ? w0 + p.rs_min_off + p.rs_row[tl] : w0 + p.off_w[tap];
+            const int hh = h + p.off_h[p.rs ? tap0 : tap];
+            for (int m = 0; m < cl::kTileM; ++m)
+              for (int nn = 0; nn < p.NBmma; ++nn) {
+                double sacc = 0.0;
+                for (int k = 0; k < 16; ++k) {
+                  const double a = a_elem(n, hh, x_base + m, c * p.BK + slab * 16 + k);
+                  const double b = packed[(tile + (size_t)(k >> 3) * (p.NBmma * 16) + (nn >> 3) * 128 + (nn & 7) * 16) / 2 + (k & 7)];
+                  sacc += a * b;
+                }
+                double& d = acc[(size_t)m * 512 + col + nn];
+                d = (first ? 0.0 : d) + (neg ? -sacc : sacc);
+              }
+            if (first) for (int nn = 0; nn < p.NBmma; ++nn) init[col + nn] = 1;
+          }
+    }
+    // epilogue
+    for (int al = 0; al < p.gc; ++al) {
+      const int ch_base = p.comp_of[group][al] * p.Pc;
+      for (int o = 0; o < p.Pc; ++o)
+        for (int m = 0; m < cl::kTileM; ++m) {
+          if (w0 + m >= p.OW) continue;
+          double v = 0.0;
+          if (!p.fuse) v = acc[(size_t)m * 512 + al * p.NBp + o];
+          else
+            for (int st = 0; st < 4; ++st)
+              if (p.epi_sgn[group][al][st] != 0)
+                v += p.epi_sgn[group][al][st] * acc[(size_t)m * 512 + p.epi_col[group][al][st] + (o >> 3) * 8 * p.fuse + (o & 7)];
+          out[n * g.out_sN + (ch_base + o) * g.out_sC + h * g.out_sH + (w0 + m) * g.out_sW] = (float)v;
+        }
+    }
+  }
+  delete pp;
+  return 0;
+}
 
 static void run_conv(const simt::ConvParams& p) {
   const ConvGeom& g = p.g;
@@ -53,6 +169,23 @@ static void run_wgrad(const simt::WgradParams& p) {
 }
 
 extern "C" {
+
+// forward (pass 0) or dgrad (pass 1) of a Q / DQ convolution through the emulated tensor-core data flow; info (10
+// ints, may be NULL) reports the plan: fuse, pair_xor, gc, ngroups, rs, tps, acc_cols, acc_stages, nstages, smem bytes
+int emul_cl_conv(const seldq_conv_desc_t* d, int pass, const float* in, const float* const* w, float* out, int n_sms,
+                 int* info) {
+  ConvGeom g;
+  int rc = make_conv_geom(d, pass, &g);
+  if (rc) return rc;
+  return run_cl_fprop(g, in, w, out, n_sms, info);
+}
+int emul_cl_linear(const seldq_linear_desc_t* d, int pass, const float* in, const float* const* w, float* out,
+                   int n_sms, int* info) {
+  ConvGeom g;
+  int rc = make_linear_geom(d, pass, &g);
+  if (rc) return rc;
+  return run_cl_fprop(g, in, w, out, n_sms, info);
+}
 
 const char* emul_last_error() { return error_buffer(); }
 

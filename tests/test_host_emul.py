@@ -139,3 +139,115 @@ def test_dq_linear_runs_as_a_1x1_convolution_with_its_own_block_table(emul):
     assert emul.emul_conv_wgrad(ctypes.byref(desc), fptr(xc), fptr(gyc), ptr_array(gws), 2) == 0
     for i in range(8):
         assert A.rel_err(gws[i][:, :, 0].T, d["gw%d" % i]) < 1e-5, i
+
+
+# ---- channels-last tensor-core path: the host plan (csrc/conv_cl_plan.h) through a CPU model of the kernel's data flow ---
+# tests/host_emul/emul.cpp run_cl_fprop: real plan_fprop (fusion sets, MMA op table, epilogue column / sign table, row-shared
+# taps, chunk masks, unit schedule) + real pack mapping, plain-loop "MMAs" in double.  A wrong table entry, tile offset, slot
+# or sign gives an O(1) error; the GPU tests then only have to vouch for the hardware semantics (descriptors, TMA, TMEM).
+CL_GOLDEN = ["conv1d_dq_c48_d3", "conv1d_q_c32_d2", "conv2d_dq_c24", "conv2d_q_c16"]
+POLICIES = {"default": {}, "unfused": {"SELDQ_PAIR_FUSE": "0"}, "pairs": {"SELDQ_QUAD_FUSE": "0"},
+            "pairs_double": {"SELDQ_QUAD_FUSE": "2", "SELDQ_ACC_DOUBLE": "1"}, "no_row_sharing": {"SELDQ_NO_RS": "1"}}
+
+
+class _Env(object):
+    def __init__(self, env):
+        self.env = env
+
+    def __enter__(self):
+        self.saved = {k: os.environ.get(k) for k in ("SELDQ_PAIR_FUSE", "SELDQ_QUAD_FUSE", "SELDQ_ACC_DOUBLE", "SELDQ_NO_RS")}
+        for k in self.saved:
+            os.environ.pop(k, None)
+        os.environ.update(self.env)
+
+    def __exit__(self, *exc):
+        for k, v in self.saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+
+
+def _cl_conv(emul, desc, pass_, inp, ws, out_shape, n_sms=148):
+    out = np.full(out_shape, np.nan, np.float32)
+    info = (ctypes.c_int32 * 10)()
+    rc = emul.emul_cl_conv(ctypes.byref(desc), pass_, fptr(inp), ptr_array(ws), fptr(out), n_sms, info)
+    assert rc == 0, emul.emul_last_error()
+    return out, dict(zip(("fuse", "pair_xor", "gc", "ngroups", "rs", "tps", "acc_cols", "acc_stages", "nstages", "smem"), info))
+
+
+@pytest.mark.parametrize("policy", sorted(POLICIES))
+@pytest.mark.parametrize("name", CL_GOLDEN)
+def test_tensor_core_plan_reproduces_golden_conv(emul, name, policy):
+    meta, d = load_golden(name)
+    nw = NW[meta["algebra"]]
+    desc = conv_desc(meta, d)
+    desc.precision = 1
+    x = np.ascontiguousarray(d["x"], np.float32)
+    gy = np.ascontiguousarray(d["gy"], np.float32)
+    ws = [np.ascontiguousarray(d["w%d" % i], np.float32) for i in range(nw)]
+    bias = d["b"].reshape((1, -1) + (1,) * (x.ndim - 2)) if meta["bias"] else 0.0
+    with _Env(POLICIES[policy]):
+        for n_sms in (148, 2):                      # few SMs: no splitting of the out components over CTAs
+            y, info = _cl_conv(emul, desc, 0, x, ws, d["y"].shape, n_sms)
+            assert A.rel_err(y, d["y"] - bias) < 1e-5, (info, A.rel_err(y, d["y"] - bias))
+            gx, info_d = _cl_conv(emul, desc, 1, gy, ws, x.shape, n_sms)
+            assert A.rel_err(gx, d["gx"]) < 1e-5, (info_d, A.rel_err(gx, d["gx"]))
+            if policy == "unfused":
+                assert info["fuse"] == 0 and info_d["fuse"] == 0
+            if policy == "pairs":
+                assert info["fuse"] == 2 and info_d["fuse"] == 2 and info["pair_xor"] != info_d["pair_xor"]
+
+
+@pytest.mark.parametrize("alg,cc_in,cc_out,ks,dil,shape", [
+    ("DQ", 48, 48, (3,), 5, (1, 300)),           # TCN residual block: pairs (four quad sets would need 768 columns)
+    ("DQ", 48, 48, (1,), 1, (2, 131)),           # skip / residual convolution
+    ("DQ", 24, 24, (3, 3), 1, (1, 5, 140)),      # CNN block: quads
+    ("Q", 16, 16, (3, 3), 1, (1, 4, 130)),       # quaternion model, CNN block
+    ("Q", 32, 32, (3,), 2, (2, 200)),            # quaternion model, residual block
+    ("DQ", 8, 16, (3,), 3, (1, 260)),            # unequal channel counts
+    ("Q", 40, 24, (1,), 1, (1, 129)),            # channels per component not a multiple of 16 on the K side
+])
+def test_tensor_core_plan_matches_oracle_on_random_layers(emul, alg, cc_in, cc_out, ks, dil, shape):
+    rng = np.random.default_rng(7)
+    nc = NW[alg]
+    nd = len(ks)
+    x = rng.standard_normal((shape[0], nc * cc_in) + shape[1:]).astype(np.float32)
+    ws = [(0.3 * rng.standard_normal((cc_out, cc_in) + ks)).astype(np.float32) for _ in range(nc)]
+    pad = dil * (ks[-1] - 1) // 2
+    y_ref = A.qconv(x.astype(np.float64), [w.astype(np.float64) for w in ws], None, 1, pad, dil, alg)
+    gy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    gx_ref, _, _ = A.qconv_backward(x.astype(np.float64), [w.astype(np.float64) for w in ws], gy.astype(np.float64), 1, pad,
+                                    dil, alg)
+    one_d = nd == 1
+    desc = ConvDesc(ALG[alg], 1, nd, x.shape[0], x.shape[1], nc * cc_out, 1 if one_d else x.shape[2], x.shape[-1],
+                    1 if one_d else ks[0], ks[-1], 1, 1, 0 if one_d else pad, pad, 1 if one_d else dil, dil)
+    for policy in ("default", "pairs_double", "unfused"):
+        with _Env(POLICIES[policy]):
+            y, info = _cl_conv(emul, desc, 0, x, ws, y_ref.shape)
+            assert A.rel_err(y, y_ref) < 1e-5, (policy, info, A.rel_err(y, y_ref))
+            gx, info_d = _cl_conv(emul, desc, 1, gy, ws, x.shape)
+            assert A.rel_err(gx, gx_ref) < 1e-5, (policy, info_d, A.rel_err(gx, gx_ref))
+            if policy == "default":
+                want = 4 if cc_out <= 32 and cc_out % 8 == 0 else (2 if cc_out % 8 == 0 else 0)
+                assert info["fuse"] == want, info
+                assert info["acc_cols"] * info["acc_stages"] <= 512 and info["smem"] <= 227 * 1024 - 12 * 1024, info
+                if ks[-1] == 3 and dil <= 4 and cc_in * nc >= 64:
+                    assert info["rs"] == 1 and info["tps"] == 3, info
+
+
+def test_tensor_core_plan_dq_linear_as_1x1_convolution(emul):
+    """dual_quaternion_linear's block table (the transpose of the convolution's) through the same planner."""
+    meta, d = load_golden("linear_dq_c48")
+    x = np.ascontiguousarray(d["x"], np.float32)
+    gy = np.ascontiguousarray(d["gy"], np.float32)
+    ws = [np.ascontiguousarray(d["w%d" % i], np.float32) for i in range(8)]
+    desc = LinearDesc(3, 1, x.shape[0], x.shape[1], gy.shape[1])          # SELDQ_ALG_DQ_LINEAR
+    for policy in ("default", "unfused"):
+        with _Env(POLICIES[policy]):
+            y = np.full(gy.shape, np.nan, np.float32)
+            info = (ctypes.c_int32 * 10)()
+            assert emul.emul_cl_linear(ctypes.byref(desc), 0, fptr(x), ptr_array(ws), fptr(y), 148, info) == 0, emul.emul_last_error()
+            assert A.rel_err(y, d["y"] - d["b"]) < 1e-5, (policy, list(info))
+            gx = np.full(x.shape, np.nan, np.float32)
+            assert emul.emul_cl_linear(ctypes.byref(desc), 1, fptr(gy), ptr_array(ws), fptr(gx), 148, info) == 0, emul.emul_last_error()
+            assert A.rel_err(gx, d["gx"]) < 1e-5, (policy, list(info))
