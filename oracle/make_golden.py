@@ -162,6 +162,18 @@ def model_case(name, cfg, time_dim, B, seed):
         for k, p in me.named_parameters():
             if p.grad is not None:
                 d[tag + "_grad/" + k] = p.grad.numpy().astype(np.float32)
+    # the reference's own DCASE21 SELD scores of its own outputs (train.py:84-130: gen_submission_list_task2 ->
+    # segment_labels -> SELDMetrics), clip by clip; num_frames = the fixture's output frames
+    ns_ = ref_import.load()
+    mt = ns_.dcase.SELDMetrics(nb_classes=14, doa_threshold=20)
+    for i in range(B):
+        _, pd_ = ns_.uf.gen_submission_list_task2(d["sed"][i], d["doa"][i], max_overlaps=3, max_loc_value=2.0)
+        _, td_ = ns_.uf.gen_submission_list_task2(d["target"][i][:, :n_sed], d["target"][i][:, n_sed:], max_overlaps=3,
+                                                  max_loc_value=2.0)
+        mt.update_seld_scores(ns_.dcase.segment_labels(pd_, n_out), ns_.dcase.segment_labels(td_, n_out))
+    d["seld_scores"] = np.array([float(v) for v in mt.compute_seld_scores()], np.float64)
+    # how close the SED outputs come to the 0.5 threshold (metric identity needs the error to stay below this)
+    d["sed_margin"] = np.float64(np.abs(d["sed"] - 0.5).min())
     meta = dict(kind="model", cfg=cfg, time_dim=time_dim, B=B, seed=seed, model_name=m.model_name,
                 n_params=int(sum(p.numel() for p in m.parameters())), n_grads=ngrad,
                 source="model.py:324-480 + train.py:186-204")

@@ -113,3 +113,45 @@ def test_oracle_matches_live_reference():
     o = A.spectrum_fast(x, nperseg=512, noverlap=112, output_phase=True)
     assert r.shape == o.shape == (16, 256, 80)
     assert np.abs(r[:8] - o[:8]).max() < 1e-14
+
+
+def _random_seld_case(rng, frames, p_on, jitter):
+    """Targets with up to three simultaneous events per class; predictions = targets with flips and jittered locations."""
+    n_sed = 42
+    t_sed = (rng.random((frames, n_sed)) < p_on).astype(np.float64)
+    t_doa = (2 * rng.random((frames, n_sed * 3)) - 1) * np.repeat(t_sed, 3, axis=-1)
+    sed = np.clip(t_sed * 0.9 + 0.05 + 0.6 * (rng.random((frames, n_sed)) < 0.03) * (1 - 2 * t_sed), 0, 1)
+    doa = np.clip(t_doa + jitter * rng.standard_normal(t_doa.shape), -1, 1)
+    return sed, doa, np.concatenate([t_sed, t_doa], axis=-1)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="/root/reference is only present in the build container")
+@pytest.mark.parametrize("seed,frames,p_on,jitter", [(0, 600, 0.05, 0.05), (1, 600, 0.3, 0.5), (2, 95, 0.1, 0.2), (3, 40, 0.6, 1.0),
+                                                     (4, 20, 0.0, 0.1)])
+def test_seld_metric_restatement_matches_live_reference(seed, frames, p_on, jitter):
+    """oracle/seld_metrics.py against the imported utility_functions.gen_submission_list_task2 +
+    Dcase21_metrics.segment_labels + SELDMetrics (the loop of train.py:84-130): the four scores bit-identical."""
+    from oracle import seld_metrics as M
+    ns = ref_import.load()
+    rng = np.random.default_rng(seed)
+    ref = ns.dcase.SELDMetrics(nb_classes=14, doa_threshold=20)
+    mine = M.SeldScores(20, 14)
+    for clip in range(3):
+        sed, doa, target = _random_seld_case(rng, frames, p_on, jitter)
+        _, pd = ns.uf.gen_submission_list_task2(sed, doa, max_overlaps=3, max_loc_value=2.0)
+        _, td = ns.uf.gen_submission_list_task2(target[:, :42], target[:, 42:], max_overlaps=3, max_loc_value=2.0)
+        assert pd == M.events_per_frame(sed, doa) and td == M.events_per_frame(target[:, :42], target[:, 42:])
+        pl, tl = ns.dcase.segment_labels(pd, frames), ns.dcase.segment_labels(td, frames)
+        assert pl == M.blocks(pd, frames) and tl == M.blocks(td, frames)
+        ref.update_seld_scores(pl, tl)
+        mine.update(M.blocks(M.events_per_frame(sed, doa), frames), M.blocks(td, frames))
+    assert tuple(float(v) for v in ref.compute_seld_scores()) == tuple(float(v) for v in mine.scores())
+
+
+@pytest.mark.parametrize("name", golden_names("model"))
+def test_seld_metric_restatement_matches_golden_scores(name):
+    """The scores the REFERENCE's code gave for the reference's own outputs of each model fixture (oracle/make_golden.py)."""
+    from oracle import seld_metrics as M
+    meta, d = load_golden(name)
+    got = M.seld_scores(d["sed"], d["doa"], d["target"], num_frames=d["sed"].shape[1])
+    assert got == tuple(float(v) for v in d["seld_scores"])
