@@ -14,19 +14,31 @@ __global__ void __launch_bounds__(NT, 1) stft_magphase_kernel(const __grid_const
   init_tables(s, threadIdx.x);
   __syncthreads();
   Thread th;
-  for (long long batch = blockIdx.x; batch < p.total; batch += gridDim.x) {
-    int signal, t0;
+  int buf = 0;
+  long long batch = blockIdx.x;
+  int signal = 0, t0 = 0;
+  if (batch < p.total) {
     batch_decode(p, batch, &signal, &t0);
-    phase_a(p, s, th, threadIdx.x, signal, t0);
+    phase_a_load(p, th, threadIdx.x, signal, t0);
+  }
+  for (; batch < p.total; batch += gridDim.x, buf ^= 1) {
+    phase_a_compute(s, th, threadIdx.x);
     __syncwarp();                                  // a frame lives in one half-warp
     phase_b(s, th, threadIdx.x);
     __syncwarp();
     phase_b2(s, th, threadIdx.x);
     __syncwarp();
-    phase_c(p, s, th, threadIdx.x);
+    phase_c(p, s, th, threadIdx.x, buf);
+    // The only block-wide barrier of a batch.  It also orders this batch's writes of tile[buf] after the reads
+    // phase_d made of it two batches ago: every thread passed the previous batch's barrier after those reads.
     __syncthreads();
-    phase_d(p, s, threadIdx.x, signal, t0);
-    __syncthreads();
+    const int cur_signal = signal, cur_t0 = t0;
+    const long long next = batch + gridDim.x;
+    if (next < p.total) {                          // the next batch's samples are in flight during the stores below
+      batch_decode(p, next, &signal, &t0);
+      phase_a_load(p, th, threadIdx.x, signal, t0);
+    }
+    phase_d(p, s, threadIdx.x, cur_signal, cur_t0, buf);
   }
 }
 

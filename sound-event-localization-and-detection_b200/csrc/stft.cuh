@@ -13,6 +13,9 @@
 //   phase_b2 / phase_c   Z goes back through the exchange buffer so that thread j can pair Z[k] with Z[256 - k]
 //             (owned by thread 16 - j), untangle, |.| and atan2, into a [bin][frame] staging tile
 //   phase_d   the tile leaves as rows of 32 consecutive frames (128-byte stores)
+// The staging tile is double-buffered over batches and the raw samples of the next batch are requested before the
+// stores of the current one (stft.cu), so a block pays ONE block-wide barrier per batch and the global-load latency of
+// batch i + 1 hides behind the stores of batch i.
 //
 // Phases are __host__ __device__ so tests/host_emul can execute them on the CPU.
 #pragma once
@@ -46,7 +49,7 @@ struct Params {
 
 struct Shared {
   float2 xch[FRB][16][17];           // exchange buffer, one 16 x 16 complex matrix (pitch 17) per frame
-  float tile[2][MAXBINS][FRB + 1];   // staging: [plane][bin][frame]
+  float tile[2][2][MAXBINS][FRB + 1];   // staging, double-buffered over batches: [buffer][plane][bin][frame]
   float2 tw256[16][16];              // [k1][j] = W256^(j k1)
   float2 tw512[17][16];              // [q][j]  = W512^(j + 16 q)
   float2 win[16][16];                // [r][j]  = window at samples 2 (j + 16 r), 2 (j + 16 r) + 1, / sum(w)
@@ -144,7 +147,8 @@ SELDQ_HD void batch_decode(const Params& p, long long batch, int* signal, int* t
   *t0 = (int)(batch - (long long)(*signal) * p.groups) * FRB;
 }
 
-SELDQ_HD void phase_a(const Params& p, Shared& s, Thread& th, int tid, int signal, int t0) {
+// raw samples of this thread's 16 complex points z[j + 16 r] = x[2 m] + i x[2 m + 1] (zero outside the signal)
+SELDQ_HD void phase_a_load(const Params& p, Thread& th, int tid, int signal, int t0) {
   const int f = tid >> 4, j = tid & 15;
   const long long g0 = (long long)(t0 + f) * p.hop - NFFT / 2;
   const float* src = p.x + (long long)signal * p.n_samples;
@@ -154,9 +158,8 @@ SELDQ_HD void phase_a(const Params& p, Shared& s, Thread& th, int tid, int signa
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const float2 v = __ldg(reinterpret_cast<const float2*>(src + g0) + (j + 16 * r));
-      const float2 w = s.win[r][j];
-      th.re[r] = v.x * w.x;
-      th.im[r] = v.y * w.y;
+      th.re[r] = v.x;
+      th.im[r] = v.y;
     }
   } else
 #endif
@@ -164,12 +167,20 @@ SELDQ_HD void phase_a(const Params& p, Shared& s, Thread& th, int tid, int signa
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const long long g = g0 + 2 * (j + 16 * r);
-      const float x0 = (interior || (g >= 0 && g < p.n_samples)) ? src[g] : 0.f;
-      const float x1 = (interior || (g + 1 >= 0 && g + 1 < p.n_samples)) ? src[g + 1] : 0.f;
-      const float2 w = s.win[r][j];
-      th.re[r] = x0 * w.x;
-      th.im[r] = x1 * w.y;
+      th.re[r] = (interior || (g >= 0 && g < p.n_samples)) ? src[g] : 0.f;
+      th.im[r] = (interior || (g + 1 >= 0 && g + 1 < p.n_samples)) ? src[g + 1] : 0.f;
     }
+  }
+}
+
+// window, DFT16 over r, twiddle, into the exchange buffer
+SELDQ_HD void phase_a_compute(Shared& s, Thread& th, int tid) {
+  const int f = tid >> 4, j = tid & 15;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const float2 w = s.win[r][j];
+    th.re[r] *= w.x;
+    th.im[r] *= w.y;
   }
   dft16(th.re, th.im);
 #pragma unroll
@@ -177,6 +188,11 @@ SELDQ_HD void phase_a(const Params& p, Shared& s, Thread& th, int tid, int signa
     const float2 w = s.tw256[k1][j];
     s.xch[f][k1][j] = make_float2(th.re[k1] * w.x - th.im[k1] * w.y, th.re[k1] * w.y + th.im[k1] * w.x);
   }
+}
+
+SELDQ_HD void phase_a(const Params& p, Shared& s, Thread& th, int tid, int signal, int t0) {
+  phase_a_load(p, th, tid, signal, t0);
+  phase_a_compute(s, th, tid);
 }
 
 SELDQ_HD void phase_b(const Shared& s, Thread& th, int tid) {
@@ -196,14 +212,14 @@ SELDQ_HD void phase_b2(Shared& s, const Thread& th, int tid) {
   for (int q = 0; q < 16; ++q) s.xch[f][q][j] = make_float2(th.re[q], th.im[q]);
 }
 
-SELDQ_HD void emit_bin(const Params& p, Shared& s, int f, int kb, float xr, float xi) {
+SELDQ_HD void emit_bin(const Params& p, Shared& s, int buf, int f, int kb, float xr, float xi) {
   if (kb < 0) return;
-  s.tile[0][kb][f] = sqrtf(xr * xr + xi * xi);
-  if (p.output_phase) s.tile[1][kb][f] = atan2f(xi, xr);
+  s.tile[buf][0][kb][f] = sqrtf(xr * xr + xi * xi);
+  if (p.output_phase) s.tile[buf][1][kb][f] = atan2f(xi, xr);
 }
 
 // real-input untangle: R[k] = E[k] + W512^k O[k], E = (Z[k] + conj Z[256-k]) / 2, O = (Z[k] - conj Z[256-k]) / 2i
-SELDQ_HD void phase_c(const Params& p, Shared& s, const Thread& th, int tid) {
+SELDQ_HD void phase_c(const Params& p, Shared& s, const Thread& th, int tid, int buf = 0) {
   const int f = tid >> 4, j = tid & 15;
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
@@ -212,13 +228,13 @@ SELDQ_HD void phase_c(const Params& p, Shared& s, const Thread& th, int tid) {
     const float er = 0.5f * (a + cc), ei = 0.5f * (bb - d);
     const float orr = 0.5f * (bb + d), oi = -0.5f * (a - cc);
     const float2 w = s.tw512[q][j];
-    emit_bin(p, s, f, j + 16 * q - p.bin0, er + w.x * orr - w.y * oi, ei + w.x * oi + w.y * orr);
+    emit_bin(p, s, buf, f, j + 16 * q - p.bin0, er + w.x * orr - w.y * oi, ei + w.x * oi + w.y * orr);
   }
-  if (j == 0) emit_bin(p, s, f, 256 - p.bin0, th.re[0] - th.im[0], 0.f);     // Nyquist bin
+  if (j == 0) emit_bin(p, s, buf, f, 256 - p.bin0, th.re[0] - th.im[0], 0.f);     // Nyquist bin
 }
 
 // rows of FRB consecutive frames; warp w takes rows w, w + 16, ...
-SELDQ_HD void phase_d(const Params& p, const Shared& s, int tid, int signal, int t0) {
+SELDQ_HD void phase_d(const Params& p, const Shared& s, int tid, int signal, int t0, int buf = 0) {
   const int b = signal / p.n_ch, c = signal - b * p.n_ch;
   const int planes = p.output_phase ? 2 : 1;
   const int warp = tid >> 5, lane = tid & 31;
@@ -227,7 +243,7 @@ SELDQ_HD void phase_d(const Params& p, const Shared& s, int tid, int signal, int
   for (int row = warp; row < planes * p.n_bins; row += NT / 32) {
     const int plane = row >= p.n_bins ? 1 : 0, kb = row - plane * p.n_bins;
     float* dst = p.out + ((long long)(b * planes * p.n_ch + plane * p.n_ch + c) * p.n_bins + kb) * p.n_frames;
-    dst[t] = s.tile[plane][kb][lane];
+    dst[t] = s.tile[buf][plane][kb][lane];
   }
 }
 
