@@ -338,24 +338,41 @@ __global__ void __launch_bounds__(256, 3) cnn_tail_fwd_vec_kernel(const __grid_c
         const int c = comp * p.cc + ci;
         const float4 cf = __ldg(reinterpret_cast<const float4*>(p.coef) + c);
         const __half* src = p.y + (((long long)n * p.C + c) * p.H + (long long)hp * p.pool) * p.W + w;
-        float best[8], ybest[8];
-        int arg[8];
+        // BN is affine, v = a y + b, so the pooled maximum of v is attained where t = sign(a) y is largest: the row
+        // scan runs on packed fp16 pairs (sign flip, compare, max and arg-select are one instruction per PAIR; the
+        // fp32 compare / select chain per element kept the ALU pipe 60 % busy, ncu) and BN is applied once per
+        // pooled element -- the same a*y + b FMA as before, bit for bit.  First maximum wins (strict >); NaN propagates.
+        const uint32_t sflip = cf.x < 0.f ? 0x80008000u : 0u;
+        uint32_t best2[4], arg2[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; ybest[j] = 0.f; }
+        for (int j = 0; j < 4; ++j) { best2[j] = 0xfc00fc00u; arg2[j] = 0u; }       // -inf, row 0
         uint4 rows[POOL];
 #pragma unroll
         for (int q = 0; q < POOL; ++q) rows[q] = __ldg(reinterpret_cast<const uint4*>(src + (long long)q * p.W));
 #pragma unroll
         for (int q = 0; q < POOL; ++q) {
-          const uint4 v = rows[q];
-          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+          const uint32_t rw[4] = {rows[q].x, rows[q].y, rows[q].z, rows[q].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h2[j]);
-            const float v0 = cf.x * f.x + cf.y, v1 = cf.x * f.y + cf.y;
-            if (v0 > best[2 * j] || v0 != v0) { best[2 * j] = v0; arg[2 * j] = q; ybest[2 * j] = f.x; }
-            if (v1 > best[2 * j + 1] || v1 != v1) { best[2 * j + 1] = v1; arg[2 * j + 1] = q; ybest[2 * j + 1] = f.y; }
+            const uint32_t tb = rw[j] ^ sflip;
+            const __half2 t = *reinterpret_cast<const __half2*>(&tb), bo = *reinterpret_cast<const __half2*>(&best2[j]);
+            const uint32_t gt = __hgt2_mask(t, bo);                                  // 0xffff per half where t > best
+            const __half2 bn = __hmax2_nan(bo, t);
+            best2[j] = *reinterpret_cast<const uint32_t*>(&bn);
+            arg2[j] = (arg2[j] & ~gt) | ((uint32_t)(q * 0x00010001) & gt);
           }
+        }
+        float best[8], ybest[8];
+        int arg[8];
+        const float aa = fabsf(cf.x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 tf = __half22float2(*reinterpret_cast<const __half2*>(&best2[j]));
+          const uint32_t yb = best2[j] ^ sflip;
+          const float2 yf = __half22float2(*reinterpret_cast<const __half2*>(&yb));
+          best[2 * j] = fmaf(aa, tf.x, cf.y); best[2 * j + 1] = fmaf(aa, tf.y, cf.y);
+          ybest[2 * j] = yf.x; ybest[2 * j + 1] = yf.y;
+          arg[2 * j] = (int)(arg2[j] & 0xffffu); arg[2 * j + 1] = (int)(arg2[j] >> 16);
         }
         const long long e = (((long long)n * p.C + c) * HP + hp) * p.W + w;
         if (p.ymax) {
