@@ -215,8 +215,9 @@ SELDQ_HD void phase_b2(Shared& s, const Thread& th, int tid) {
 SELDQ_HD void emit_bin(const Params& p, Shared& s, int buf, int f, int kb, float xr, float xi) {
   if (kb < 0) return;
 #if defined(__CUDA_ARCH__)
-  const float v = xr * xr + xi * xi;                       // |Z| = v * rsqrt(v): one MUFU + one multiply (2 ulp) instead of
-  s.tile[buf][0][kb][f] = v > 0.f ? v * rsqrtf(v) : 0.f;   // the IEEE square-root sequence; the tolerance is 1e-4
+  float mag;                                               // sqrt.approx: one MUFU (+ a multiply), relative error 2^-22 against a
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(xr * xr + xi * xi));     // tolerance of 1e-4; 0, inf and NaN behave as in sqrtf
+  s.tile[buf][0][kb][f] = mag;
 #else
   s.tile[buf][0][kb][f] = sqrtf(xr * xr + xi * xi);
 #endif
