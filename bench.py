@@ -67,7 +67,37 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
 
+    def _nvml(self):
+        """NVML handle for fast polling (a timed region of a few steps lasts tens of milliseconds; spawning
+        nvidia-smi takes longer than that), or None."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            return None
+
     def run(self):
+        nv = self._nvml()
+        if nv is not None:
+            pynvml, h = nv
+            bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))     # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+            while not self._halt.is_set():
+                try:
+                    row = [str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                           str(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                           str(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3), "", "", "", ""]
+                    try:
+                        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    except Exception:
+                        mask = 0
+                    for bit, col in bits:
+                        row[col] = "Active" if mask & bit else "Not Active"
+                    self.rows.append(row)
+                except Exception:
+                    pass
+                self._halt.wait(0.01)
+            return
         while not self._halt.is_set():
             try:
                 out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
