@@ -144,6 +144,7 @@ struct WgradParams {
   int chunks_w;
   long long ksteps;
   int splits, nstages, tmem_cols;
+  int x_one_box;                // x operand: one rank-5 TMA box per tap (all channel chunks) instead of one per chunk
   uint32_t stage_bytes, b_tap_bytes;
   int8_t pair_n[8];             // which (a,b) blocks feed compact tensor e
   int8_t pair_a[8][8], pair_b[8][8], pair_neg[8][8];

@@ -80,12 +80,18 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
           ptx::mbar_wait(&empty_bar[slot], parity ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[slot], a_bytes + (uint32_t)ntap * p.b_tap_bytes);
           uint8_t* st = smem + (size_t)slot * p.stage_bytes;
-          for (int a = 0; a < p.ncomp; ++a)
-            ptx::tma_load_4d(st + (size_t)a * p.OS * 128, tm_g, &full_bar[slot], w0, h, a * p.g.Oc + o0, n);
-          for (int t = 0; t < ntap; ++t)
-            for (int c = 0; c < p.nchunks; ++c)
-              ptx::tma_load_4d(st + a_bytes + (size_t)t * p.b_tap_bytes + (size_t)c * 8192, &tm_x, &full_bar[slot],
-                               c * 64, w0 + p.off_w[tap0 + t], h + p.off_h[tap0 + t], n);
+          // one box per operand and tap: the component / channel-chunk axes are box dimensions of rank-5 maps (a stage
+          // was 8 + 6 boxes of 128-byte rows before; the K loop is bound by the latency of its TMA traffic)
+          ptx::tma_load_5d(st, tm_g, &full_bar[slot], w0, h, o0, 0, n);
+          for (int t = 0; t < ntap; ++t) {
+            if (p.x_one_box)
+              ptx::tma_load_5d(st + a_bytes + (size_t)t * p.b_tap_bytes, &tm_x, &full_bar[slot], 0,
+                               w0 + p.off_w[tap0 + t], 0, h + p.off_h[tap0 + t], n);
+            else
+              for (int c = 0; c < p.nchunks; ++c)
+                ptx::tma_load_4d(st + a_bytes + (size_t)t * p.b_tap_bytes + (size_t)c * 8192, &tm_x, &full_bar[slot],
+                                 c * 64, w0 + p.off_w[tap0 + t], h + p.off_h[tap0 + t], n);
+          }
           if (++slot == (uint32_t)nstages) { slot = 0; parity ^= 1; }
         }
       }
@@ -240,18 +246,28 @@ int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, 
   alignas(64) CUtensorMap tm_g, tm_g2, tm_x;
   for (int k = 0; k < 2; ++k) {
     const uint64_t pitch = (uint64_t)nchw16_pitch(g.OW);
-    const uint64_t dims[4] = {pitch, (uint64_t)g.OH, (uint64_t)g.P, (uint64_t)g.N};
-    const uint64_t strides[3] = {pitch * 2, pitch * g.OH * 2, pitch * g.OH * g.P * 2};
-    const uint32_t box[4] = {64, 1, (uint32_t)p.OS, 1};
-    const int rc = encode_tensor_map(k ? &tm_g2 : &tm_g, (k && p.nprob == 2) ? gy2_nchw16 : gy_nchw16, 2, 4, dims, strides,
+    // (t, h, channel inside a component, component, n): box {64 t, 1, OS channels, all components, 1}
+    const uint64_t dims[5] = {pitch, (uint64_t)g.OH, (uint64_t)g.Oc, (uint64_t)nc, (uint64_t)g.N};
+    const uint64_t strides[4] = {pitch * 2, pitch * g.OH * 2, pitch * g.OH * g.Oc * 2, pitch * g.OH * g.P * 2};
+    const uint32_t box[5] = {64, 1, (uint32_t)p.OS, (uint32_t)nc, 1};
+    const int rc = encode_tensor_map(k ? &tm_g2 : &tm_g, (k && p.nprob == 2) ? gy2_nchw16 : gy_nchw16, 2, 5, dims, strides,
                                      box, 3);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[4] = {(uint64_t)lx.Cp, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
-    const uint64_t strides[3] = {(uint64_t)lx.Cp * 2, (uint64_t)lx.Cp * 2 * g.IW, (uint64_t)lx.Cp * 2 * g.IW * g.IH};
-    const uint32_t box[4] = {64, 64, 1, 1};
-    const int rc = encode_tensor_map(&tm_x, x_cl, 2, 4, dims, strides, box, 3);
+    // (channel inside a 64-channel chunk, w, chunk, h, n): box {64 ch, 64 t, all chunks, 1, 1} lands as nchunks
+    // [64 t x 128 B] tiles, the layout the six separate boxes produced
+    const uint64_t dims[5] = {64, (uint64_t)g.IW, (uint64_t)p.nchunks, (uint64_t)g.IH, (uint64_t)g.N};
+    const uint64_t strides[4] = {(uint64_t)lx.Cp * 2, 128, (uint64_t)lx.Cp * 2 * g.IW, (uint64_t)lx.Cp * 2 * g.IW * g.IH};
+    const uint32_t box[5] = {64, 64, (uint32_t)p.nchunks, 1, 1};
+    p.x_one_box = getenv("SELDQ_WGRAD_X_BOXES") == nullptr && encode_tensor_map(&tm_x, x_cl, 2, 5, dims, strides, box, 3) == SELDQ_OK;
+    int rc = SELDQ_OK;
+    if (!p.x_one_box) {       // the driver refused the map whose chunk stride is smaller than its w stride: one box per chunk
+      const uint64_t dims4[4] = {(uint64_t)lx.Cp, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+      const uint64_t strides4[3] = {(uint64_t)lx.Cp * 2, (uint64_t)lx.Cp * 2 * g.IW, (uint64_t)lx.Cp * 2 * g.IW * g.IH};
+      const uint32_t box4[4] = {64, 64, 1, 1};
+      rc = encode_tensor_map(&tm_x, x_cl, 2, 4, dims4, strides4, box4, 3);
+    }
     if (rc) return rc;
   }
   cudaError_t e = cudaFuncSetAttribute(qconv_cl_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
