@@ -295,6 +295,13 @@ int seldq_probe_umma(const void* a_image, uint32_t a_bytes, const void* b_image,
                      uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int32_t n_mma,
                      uint32_t a_desc_step, uint32_t b_desc_step, int32_t n_cols,
                      float* out_128xN, void* stream);
+/* tcgen05.mma issue-rate probes (tools/umma_rate.py, tools/umma_ts.py): cycles per MMA versus N for the product
+ * kernels' operand layouts, and the A-from-tensor-memory variant (tcgen05.cp + TS-form MMA).  out: 2 x blocks int64
+ * (issue cycles, issue + drain cycles); mode 0 of the second probe returns mismatch / non-zero counts instead. */
+int seldq_probe_umma_rate(uint32_t n, int32_t n_mma, int32_t d_cycle, int32_t mode, int32_t blocks, void* out,
+                          void* stream);
+int seldq_probe_umma_ts(uint32_t n, int32_t n_slabs, int32_t g, int32_t mode, int32_t nbuf, int32_t blocks, void* out,
+                        void* stream);
 
 #ifdef __cplusplus
 }
