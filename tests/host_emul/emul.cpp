@@ -26,7 +26,6 @@ static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* co
   size_t smem = 0;
   int rc = cl::plan_fprop(g, &p, &smem, n_sms);
   if (rc) { delete pp; return rc; }
-  if (p.dense) { delete pp; return fail(SELDQ_ERR_UNSUPPORTED, "emulation covers the packed (non-dense) path"); }
   if (info) { info[0] = p.fuse; info[1] = p.pair_xor; info[2] = p.gc; info[3] = p.ngroups; info[4] = p.rs; info[5] = p.tps;
               info[6] = p.acc_cols; info[7] = p.acc_stages; info[8] = p.nstages; info[9] = (int)smem; }
   const cl::WeightPlan wp = cl::weight_plan(g);
@@ -35,6 +34,20 @@ static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* co
   cl::PackParams pk{};
   cl::fill_pack_params(g, wp, &pk);
   const int rows = cl::pack_rows(pk);
+  if (p.dense) {
+    // dense mode (K side narrower than 8 channels per component, or the real algebra): the signed EXPANDED tile is
+    // built in shared memory by the kernel's prologue, tile (tap, j) = B[n][k], n = out channel, k = in channel 16 j + k
+    pk.n_img = 0;
+    for (int tap = 0; tap < p.ntaps; ++tap)
+      for (int j = 0; j < p.J; ++j)
+        for (int kc = 0; kc < 2; ++kc)
+          for (int n = 0; n < p.NBp; ++n)
+            for (int jj = 0; jj < 8; ++jj) {
+              const int ch = j * 16 + kc * 8 + jj;
+              const size_t off = (size_t)(tap * p.J + j) * p.slab_bytes + (size_t)kc * (p.NBp * 16) + (n >> 3) * 128 + (n & 7) * 16;
+              packed[off / 2 + jj] = (n < g.P && ch < g.R) ? expanded_weight(g, w, n, ch, tap) : 0.f;
+            }
+  }
   for (int img = 0; img < pk.n_img; ++img)
     for (int tap = 0; tap < pk.ntaps; ++tap)
       for (int j = 0; j < pk.J; ++j)
@@ -53,7 +66,7 @@ static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* co
             }
           }
   // the channels-last operand: [n][h][w][Cp], every component padded to cpad channels
-  const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, false);
+  const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, p.dense != 0);
   std::vector<float> xcl((size_t)g.N * g.IH * g.IW * l.Cp, 0.f);
   for (int n = 0; n < g.N; ++n)
     for (int c = 0; c < g.R; ++c)

@@ -252,3 +252,36 @@ def test_tensor_core_plan_dq_linear_as_1x1_convolution(emul):
             gx = np.full(x.shape, np.nan, np.float32)
             assert emul.emul_cl_linear(ctypes.byref(desc), 1, fptr(gy), ptr_array(ws), fptr(gx), 148, info) == 0, emul.emul_last_error()
             assert A.rel_err(gx, d["gx"]) < 1e-5, (policy, list(info))
+
+
+@pytest.mark.parametrize("no_tps", [False, True])
+def test_tensor_core_plan_first_layer_dense_mode(emul, no_tps):
+    """The first CNN layer (one input channel per component): the activation is ONE 16-channel-padded component, the
+    signed expanded weight tile is built in shared memory, and all nine taps share one stage (tps = 9)."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((1, 8, 6, 140)).astype(np.float32)
+    ws = [(0.3 * rng.standard_normal((24, 1, 3, 3))).astype(np.float32) for _ in range(8)]
+    y_ref = A.qconv(x.astype(np.float64), [w.astype(np.float64) for w in ws], None, 1, 1, 1, "DQ")
+    desc = ConvDesc(ALG["DQ"], 1, 2, 1, 8, 192, 6, 140, 3, 3, 1, 1, 1, 1, 1, 1)
+    saved = os.environ.pop("SELDQ_NO_TPS", None)
+    try:
+        if no_tps:
+            os.environ["SELDQ_NO_TPS"] = "1"
+        y, info = _cl_conv(emul, desc, 0, x, ws, y_ref.shape)
+    finally:
+        os.environ.pop("SELDQ_NO_TPS", None)
+        if saved is not None:
+            os.environ["SELDQ_NO_TPS"] = saved
+    assert A.rel_err(y, y_ref) < 1e-5, (info, A.rel_err(y, y_ref))
+    assert info["fuse"] == 0 and info["tps"] == (1 if no_tps else 9) and info["rs"] == 0, info
+    # the golden first-layer fixture, forward and input gradient (both passes are dense here)
+    meta, d = load_golden("conv2d_dq_first")
+    gd = conv_desc(meta, d)
+    gd.precision = 1
+    gx_in = np.ascontiguousarray(d["x"], np.float32)
+    gws = [np.ascontiguousarray(d["w%d" % i], np.float32) for i in range(8)]
+    bias = d["b"].reshape(1, -1, 1, 1) if meta["bias"] else 0.0
+    y2, _ = _cl_conv(emul, gd, 0, gx_in, gws, d["y"].shape)
+    assert A.rel_err(y2, d["y"] - bias) < 1e-5
+    gx2, _ = _cl_conv(emul, gd, 1, np.ascontiguousarray(d["gy"], np.float32), gws, gx_in.shape)
+    assert A.rel_err(gx2, d["gx"]) < 1e-5
