@@ -346,5 +346,75 @@ inline int plan_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes, int
   return SELDQ_OK;
 }
 
+
+// weight-gradient kernel (wgrad_cl.cu): tile decode, tap groups, split-K ranges, the (a, b) -> compact-tensor fold table
+inline int plan_wgrad(const ConvGeom& g, int nprob, int n_sms, WgradParams* pp, size_t* smem_bytes) {
+  if (g.sh != 1 || g.sw != 1) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 tensor-core path implements stride 1 only");
+  const int ntaps = g.KH * g.KW;
+  if (ntaps > kMaxTaps) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 path supports at most %d taps", kMaxTaps);
+  const int nc = g.tab.nc;
+  const OperandLayout lx = operand_layout(g.tab.nc, g.tab.nc * g.Ic, g.tab.nc == 1 || g.Ic < 8);      // = x_operand_layout
+  if (lx.nc != nc || lx.Cp % 64) return fail(SELDQ_ERR_INVALID, "channels-last wgrad needs a component-padded x operand");
+  if (lx.Cp > 512) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 wgrad supports at most 512 padded input channels, got %d", lx.Cp);
+  WgradParams& p = *pp;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.nprob = nprob;
+  p.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) {
+    p.off_h[t] = (t / g.KW) * g.dh - g.ph;
+    p.off_w[t] = (t % g.KW) * g.dw - g.pw;
+  }
+  p.OH = g.OH; p.OW = g.OW; p.N = g.N;
+  p.ncomp = nc;
+  p.OS = 128 / nc;
+  p.o_tiles = (g.Oc + p.OS - 1) / p.OS;
+  p.cpad_in = lx.cpad; p.Cp = lx.Cp; p.nchunks = lx.Cp / 64;
+  for (int a = 0; a < nc; ++a)
+    for (int b = 0; b < nc; ++b) {
+      const int e = g.tab.widx[a][b];
+      if (e < 0) continue;
+      const int k = p.pair_n[e]++;
+      p.pair_a[e][k] = (int8_t)a; p.pair_b[e][k] = (int8_t)b; p.pair_neg[e][k] = (int8_t)(g.tab.sign[a][b] < 0);
+    }
+  p.taps_per_group = 256 / lx.Cp;
+  if (p.taps_per_group < 1) p.taps_per_group = 1;
+  if (p.taps_per_group > ntaps) p.taps_per_group = ntaps;
+  p.tap_groups = (ntaps + p.taps_per_group - 1) / p.taps_per_group;
+  int cols = 32;
+  while (cols < p.taps_per_group * lx.Cp) cols <<= 1;
+  p.tmem_cols = cols;
+  p.chunks_w = (g.OW + 63) / 64;
+  p.ksteps = (long long)g.N * g.OH * p.chunks_w;
+  const int tiles = p.nprob * p.tap_groups * p.o_tiles;
+  // split-K over positions: one wave of CTAs (every split pays a TMEM round trip and one atomicAdd per compact
+  // element in its epilogue), at least 4 K steps each, and no empty splits
+  long long splits = n_sms / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > (p.ksteps + 3) / 4) splits = (p.ksteps + 3) / 4;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  if (const char* e = getenv("SELDQ_WGRAD_SPLITS")) {      // tuning knob (tools/kprof.py)
+    const long long v = atoll(e);
+    if (v >= 1 && v <= p.ksteps) splits = v;
+  }
+  const long long per = (p.ksteps + splits - 1) / splits;
+  splits = (p.ksteps + per - 1) / per;
+  p.splits = (int)splits;
+  p.b_tap_bytes = (uint32_t)lx.Cp * 128u;
+  p.stage_bytes = 128u * 128u + (uint32_t)p.taps_per_group * p.b_tap_bytes;
+  size_t ns = (208 * 1024) / p.stage_bytes;
+  if (ns > (size_t)kWgradStages) ns = kWgradStages;
+  if (ns < 2) return fail(SELDQ_ERR_UNSUPPORTED, "bf16 wgrad: operand stage of %u B does not fit twice", p.stage_bytes);
+  p.nstages = (int)ns;
+  size_t smem = ns * p.stage_bytes;
+  const size_t stg = (size_t)128 * (nc * 16 + 1) * 4;
+  if (smem < stg) smem = stg;
+  smem += 4096;   // slack: the tensor core may fetch past the logical end of the last operand tile
+
+  *smem_bytes = smem;
+  return SELDQ_OK;
+}
+
 }  // namespace cl
 }  // namespace seldq

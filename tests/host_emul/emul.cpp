@@ -140,6 +140,81 @@ static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* co
   return 0;
 }
 
+// ---- weight-gradient kernel (csrc/wgrad_cl.cu), data flow on the CPU ---------------------------------------------------
+// Real host plan (cl::plan_wgrad: o tiles, tap groups, split-K ranges, the (a, b) -> compact tensor fold table) through
+// a plain-loop model of the kernel: per CTA the dense [128 rows = (component, out channel)] x [taps x Cp in channels]
+// accumulator over its slice of the position axis (operand boxes with zero fill), then the sign-weighted fold onto
+// the compact gradients, accumulated like the kernel's atomicAdd.
+static int run_cl_wgrad(const ConvGeom& g, const float* x_nchw, const float* gy_nchw, float* const* gw, int n_sms,
+                        int* info) {
+  cl::WgradParams* pp = new cl::WgradParams;
+  size_t smem = 0;
+  int rc = cl::plan_wgrad(g, 1, n_sms, pp, &smem);
+  if (rc) { delete pp; return rc; }
+  const cl::WgradParams& p = *pp;
+  if (info) { info[0] = p.o_tiles; info[1] = p.tap_groups; info[2] = p.taps_per_group; info[3] = p.splits;
+              info[4] = p.nstages; info[5] = (int)smem; info[6] = p.tmem_cols; info[7] = p.Cp; }
+  const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.tab.nc * g.Ic, false);
+  std::vector<float> xcl((size_t)g.N * g.IH * g.IW * l.Cp, 0.f);
+  for (int n = 0; n < g.N; ++n)
+    for (int c = 0; c < g.R; ++c)
+      for (int h = 0; h < g.IH; ++h)
+        for (int x = 0; x < g.IW; ++x)
+          xcl[(((size_t)n * g.IH + h) * g.IW + x) * l.Cp + (c / l.cc) * l.cpad + c % l.cc] =
+              x_nchw[n * g.in_sN + c * g.in_sC + h * g.in_sH + x * g.in_sW];
+  const int tiles = p.nprob * p.tap_groups * p.o_tiles;
+  std::vector<double> acc((size_t)128 * 512);
+  for (int bx = 0; bx < tiles; ++bx)
+    for (int by = 0; by < p.splits; ++by) {
+      const int o_tile = bx % p.o_tiles, tg = (bx / p.o_tiles) % p.tap_groups;
+      const int tap0 = tg * p.taps_per_group;
+      const int ntap = p.taps_per_group < p.ntaps - tap0 ? p.taps_per_group : p.ntaps - tap0;
+      const int o0 = o_tile * p.OS;
+      const long long per = (p.ksteps + p.splits - 1) / p.splits;
+      const long long k_begin = (long long)by * per, k_end = k_begin + per < p.ksteps ? k_begin + per : p.ksteps;
+      if (k_end <= k_begin) continue;
+      if (ntap * p.Cp > p.tmem_cols) { delete pp; return fail(SELDQ_ERR_INVALID, "accumulator beyond the TMEM allocation"); }
+      std::fill(acc.begin(), acc.end(), 0.0);
+      for (long long ks = k_begin; ks < k_end; ++ks) {
+        long long u = ks;
+        const int wc = (int)(u % p.chunks_w); u /= p.chunks_w;
+        const int h = (int)(u % p.OH), n = (int)(u / p.OH), w0 = wc * 64;
+        for (int a = 0; a < p.ncomp; ++a)
+          for (int ol = 0; ol < p.OS; ++ol) {
+            const int o = o0 + ol;
+            if (o >= g.Oc) continue;                                    // rows beyond the component read zero
+            for (int t = 0; t < 64; ++t) {
+              if (w0 + t >= g.OW) continue;
+              const double gyv = gy_nchw[n * g.out_sN + (a * g.Oc + o) * g.out_sC + h * g.out_sH + (w0 + t) * g.out_sW];
+              if (gyv == 0.0) continue;
+              for (int tl = 0; tl < ntap; ++tl) {
+                const int hh = h + p.off_h[tap0 + tl], xx = w0 + t + p.off_w[tap0 + tl];
+                if (hh < 0 || hh >= g.IH || xx < 0 || xx >= g.IW) continue;
+                const float* xr = &xcl[(((size_t)n * g.IH + hh) * g.IW + xx) * l.Cp];
+                double* ar = &acc[(size_t)(a * p.OS + ol) * 512 + tl * p.Cp];
+                for (int ch = 0; ch < p.Cp; ++ch) ar[ch] += gyv * xr[ch];
+              }
+            }
+          }
+      }
+      // epilogue: fold the (a, b) blocks onto the compact tensors
+      for (int tl = 0; tl < ntap; ++tl)
+        for (int e = 0; e < g.tab.nw; ++e)
+          for (int ol = 0; ol < p.OS; ++ol)
+            for (int i = 0; i < g.Ic; ++i) {
+              if (o0 + ol >= g.Oc) continue;
+              double v = 0.0;
+              for (int k = 0; k < p.pair_n[e]; ++k) {
+                const double val = acc[(size_t)(p.pair_a[e][k] * p.OS + ol) * 512 + tl * p.Cp + p.pair_b[e][k] * p.cpad_in + i];
+                v += p.pair_neg[e][k] ? -val : val;
+              }
+              gw[e][(long long)(o0 + ol) * g.wsO + (long long)i * g.wsI + (long long)(tap0 + tl) * g.wsT] += (float)v;
+            }
+    }
+  delete pp;
+  return 0;
+}
+
 static void run_conv(const simt::ConvParams& p) {
   const ConvGeom& g = p.g;
   const int gx = (g.OW + simt::BN - 1) / simt::BN, gy = (g.P + simt::BM - 1) / simt::BM, gz = g.N * g.OH;
@@ -191,6 +266,15 @@ int emul_cl_conv(const seldq_conv_desc_t* d, int pass, const float* in, const fl
   int rc = make_conv_geom(d, pass, &g);
   if (rc) return rc;
   return run_cl_fprop(g, in, w, out, n_sms, info);
+}
+// compact weight gradients (accumulated into gw, which the caller zeroes) through the emulated weight-gradient kernel;
+// info (8 ints, may be NULL): o_tiles, tap_groups, taps_per_group, splits, nstages, smem bytes, tmem_cols, Cp
+int emul_cl_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const float* gy, float* const* gw, int n_sms,
+                       int* info) {
+  ConvGeom g;
+  int rc = make_conv_geom(d, SELDQ_PASS_WGRAD, &g);
+  if (rc) return rc;
+  return run_cl_wgrad(g, x, gy, gw, n_sms, info);
 }
 int emul_cl_linear(const seldq_linear_desc_t* d, int pass, const float* in, const float* const* w, float* out,
                    int n_sms, int* info) {

@@ -285,3 +285,24 @@ def test_tensor_core_plan_first_layer_dense_mode(emul, no_tps):
     assert A.rel_err(y2, d["y"] - bias) < 1e-5
     gx2, _ = _cl_conv(emul, gd, 1, np.ascontiguousarray(d["gy"], np.float32), gws, gx_in.shape)
     assert A.rel_err(gx2, d["gx"]) < 1e-5
+
+
+@pytest.mark.parametrize("n_sms", [148, 5])
+@pytest.mark.parametrize("name", CL_GOLDEN)
+def test_tensor_core_wgrad_plan_reproduces_golden(emul, name, n_sms):
+    """csrc/wgrad_cl.cu's host plan (o tiles, tap groups, split-K ranges, the (a, b) -> compact tensor fold table)
+    through a CPU model of the kernel: dense accumulator per CTA and split, sign-weighted fold, accumulation across
+    splits.  n_sms = 5 forces few or no splits."""
+    meta, d = load_golden(name)
+    nw = NW[meta["algebra"]]
+    desc = conv_desc(meta, d)
+    desc.precision = 1
+    x = np.ascontiguousarray(d["x"], np.float32)
+    gy = np.ascontiguousarray(d["gy"], np.float32)
+    gws = [np.zeros(d["w%d" % i].shape, np.float32) for i in range(nw)]
+    info = (ctypes.c_int32 * 8)()
+    rc = emul.emul_cl_conv_wgrad(ctypes.byref(desc), fptr(x), fptr(gy), ptr_array(gws), n_sms, info)
+    assert rc == 0, emul.emul_last_error()
+    for i in range(nw):
+        assert A.rel_err(gws[i], d["gw%d" % i]) < 1e-5, (i, list(info), A.rel_err(gws[i], d["gw%d" % i]))
+    assert info[5] <= 227 * 1024 and info[2] * info[7] <= info[6] <= 512, list(info)
