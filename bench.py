@@ -45,6 +45,16 @@ CONFIGS = {
                                           cnn_filters=[64, 64, 64], G=128, U=128, V=[128, 128], fc_layers=[128],
                                           parallel_ConvTC_block="1", parallel_magphase=False,
                                           extra_name="_parallel_8ch", batch_size=4, conv_train_gflop=99.7),
+    # config/SERVER_DQSELD-TCN-S1-PHI_micAMagPhaseParallelmicBMagPhase.txt: two DQ ConvTC branches (mic A / mic B,
+    # magnitude + phase each, model.py:463-471), real-valued heads
+    "DQSELD-TCN-S1-PHI_micAMagPhaseParallelmicBMagPhase": dict(
+        input_channels=16, domain="DQ", domain_classifier="R", cnn_filters=[192, 192, 192], G=384, U=384,
+        V=[384, 384], fc_layers=[128], parallel_ConvTC_block="2Parallel", parallel_magphase=True,
+        extra_name="_micAMagPhaseParallelmicBMagPhase", batch_size=4, conv_train_gflop=1141.8),
+    # config/SERVER_SELD-TCN-S1-PHI_8ch.txt: the real-valued baseline (nn.Conv* layers: none of the Q / DQ kernels)
+    "SELD-TCN-S1-PHI_8ch": dict(input_channels=8, domain="R", domain_classifier="R", cnn_filters=[64, 64, 64],
+                                G=128, U=128, V=[128, 128], fc_layers=[128], parallel_ConvTC_block="False",
+                                parallel_magphase=False, extra_name="_8ch", batch_size=4, conv_train_gflop=99.7),
 }
 TIME_DIM, N_FRAMES_OUT, N_SED = 4800, 600, 42
 
@@ -134,23 +144,79 @@ def synth_batch(pkg, cfg, batch, seed, device):
     return feat.contiguous(), torch.cat([sed, doa], -1).to(device)
 
 
+def frontend_roofline(pkg, device, peaks, batches=(1, 4, 16), iters=10):
+    """STFT front end (utility_functions.py:129-155 -> csrc/stft.cuh), kernel-level: clips/s and achieved HBM GB/s
+    against the measured copy bandwidth, for magnitude-only and magnitude + phase output, over a batch sweep.
+    Algorithmic bytes per clip: 61.44 MB read + 39.32 MB (mag) [+ 39.32 MB (phase)] written.  Every
+    iteration reads a different resident clip set (inputs of >= 61 MB per clip rotate through > 126 MB of L2)."""
+    out = {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["source"], "sweep": []}
+    g = torch.Generator().manual_seed(7)
+    nb = max(batches)
+    wav = (0.1 * torch.randn(nb + 2, 8, 1_920_000, generator=g)).to(device)
+    for phase in (False, True):
+        bytes_clip = 8 * 1_920_000 * 4 + (2 if phase else 1) * 8 * 256 * 4800 * 4
+        for b in batches:
+            for _ in range(2):
+                pkg.stft_magphase(wav[:b], 512, 112, True, phase, True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(iters):
+                o = i % 3 if b + 2 <= wav.shape[0] else 0
+                pkg.stft_magphase(wav[o:o + b], 512, 112, True, phase, True)
+            e1.record()
+            torch.cuda.synchronize()
+            us = 1e3 * e0.elapsed_time(e1) / iters
+            gbs = b * bytes_clip / (us * 1e-6) / 1e9
+            out["sweep"].append(dict(batch=b, phase=phase, us_per_launch=us, clips_per_s=b / (us * 1e-6),
+                                     achieved=gbs, frac=gbs / peaks["hbm_gbs"]))
+    head = next(r for r in out["sweep"] if r["batch"] == 1 and not r["phase"])
+    out.update(kernel="stft_magphase_kernel", achieved=head["achieved"], frac=head["frac"],
+               workload="8 ch x 60 s @ 32 kHz clip, nperseg 512, hop 400, magnitude only, batch 1")
+    del wav
+    return out
+
+
 def model_kwargs(cfg):
     kw = dict(COMMON)
     kw.update({k: v for k, v in cfg.items() if k not in ("batch_size", "conv_train_gflop")})
     return kw
 
 
+def _cpu_train_step(model, opt, x, target):
+    """The step body of train.py:546-561 with seld_loss of train.py:186-204 (BCE + 5 * MSE)."""
+    import torch.nn.functional as tF
+    opt.zero_grad()
+    sed, doa = model(x)
+    loss = (tF.binary_cross_entropy(torch.flatten(sed, 1), torch.flatten(target[:, :, :N_SED], 1))
+            + 5.0 * tF.mse_loss(torch.flatten(doa, 1), torch.flatten(target[:, :, N_SED:], 1)))
+    loss.backward()
+    opt.step()
+    return loss
+
+
 def run_reference(args, cfg, rank, world):
-    """The reference's CPU arithmetic (oracle/cpu_model.py: torch.cat expansion + F.conv / mm, stock
-    BatchNorm etc.) for the same config, on the host cores of this box.  Rank 0 only."""
+    """The reference's own CPU implementation for the same config on the host cores of this box: the UNMODIFIED
+    model.SELD_Model from the shipped copy of the reference (oracle/_ref, made by oracle/fetch_ref.sh; kind
+    "reference"), or -- where that copy is absent -- the port of its arithmetic (oracle/cpu_model.py: torch.cat
+    expansion + F.conv / mm, stock BatchNorm etc.; kind "port").  Rank 0 only."""
     if rank != 0:
         return
-    from oracle import cpu_model
+    from oracle import ref_import
     torch.set_num_threads(os.cpu_count())
     np.random.seed(1)
     torch.manual_seed(1)
     batch = args.batch or cfg["batch_size"]
-    model = cpu_model.build_model(time_dim=TIME_DIM, **model_kwargs(cfg)).train()
+    if ref_import.available() and not os.environ.get("SELDQ_REF_PORT"):
+        kind = "reference"
+        model = ref_import.load().model.SELD_Model(time_dim=TIME_DIM, **model_kwargs(cfg)).train()
+        note = ("the reference's unmodified model.SELD_Model (%s), one replica on the host cores"
+                % os.path.relpath(ref_import.REFERENCE_ROOT, ROOT))
+    else:
+        from oracle import cpu_model
+        kind = "port"
+        model = cpu_model.build_model(time_dim=TIME_DIM, **model_kwargs(cfg)).train()
+        note = "CPU port of the reference arithmetic, one replica on the host cores"
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     g = torch.Generator().manual_seed(1234)
     # features of the same distribution as the GPU arm's (standardised STFT magnitudes): N(0,1) surrogate
@@ -160,18 +226,18 @@ def run_reference(args, cfg, rank, world):
     target = torch.cat([sed, doa], -1)
     steps, warm = max(1, min(args.steps, args.ref_max_steps)), max(1, min(args.warmup, 1))
     for _ in range(warm):
-        cpu_model.train_step(model, opt, x, target)
+        _cpu_train_step(model, opt, x, target)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_model.train_step(model, opt, x, target)
+        _cpu_train_step(model, opt, x, target)
     dt = time.perf_counter() - t0
     value = steps * batch / dt
     line = dict(metric="train_samples_per_sec", value=value, unit="samples/s", n_gpus=args.gpus, steps=steps,
                 warmup=warm, ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
                 config=dict(workload=args.config, per_gpu_batch=batch, global_batch=batch,
-                            note="CPU port of the reference arithmetic, one replica on the host cores"),
-                cpu_baseline=dict(value=value, unit="samples/s", cores=os.cpu_count(), kind="port",
+                            note=note),
+                cpu_baseline=dict(value=value, unit="samples/s", cores=os.cpu_count(), kind=kind,
                                   sample="%d warm-up + %d timed full training steps, batch %d" % (warm, steps, batch)),
                 e2e=dict(value=value, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -190,6 +256,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="drive every step from Python instead of one CUDA graph")
     ap.add_argument("--ref-max-steps", type=int, default=3)
+    ap.add_argument("--model", default="mirror", choices=["mirror", "reference"],
+                    help="mirror: this repository's seld_model.SELD_Model.  reference: the reference's UNMODIFIED "
+                         "model.py (shipped copy oracle/_ref) imported on the drop-in layer modules, fused glue wired "
+                         "in by install_dropin(fuse_model=True)")
+    ap.add_argument("--no-fuse-model", action="store_true",
+                    help="with --model reference: layers only, model.py's own forward code drives them one by one")
+    ap.add_argument("--no-frontend", action="store_true", help="skip the STFT front-end measurement")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -214,7 +287,13 @@ def main():
 
     np.random.seed(1)
     torch.manual_seed(1)                                   # train.py:214-221
-    model = pkg.SELD_Model(time_dim=TIME_DIM, **model_kwargs(cfg)).to(device).train()
+    if args.model == "reference":
+        # the caller is the reference's own model.py (host code only: every kernel it launches is this repository's)
+        from oracle import ref_import
+        model_cls = ref_import.load_model_on_dropin(pkg, fuse_model=not args.no_fuse_model).SELD_Model
+    else:
+        model_cls = pkg.SELD_Model
+    model = model_cls(time_dim=TIME_DIM, **model_kwargs(cfg)).to(device).train()
     trainer = trainer_mod.Trainer(model, lr=1e-4, n_sed=N_SED)
     trainer.broadcast_parameters()
     torch.manual_seed(100 + rank)                          # dropout masks differ per replica
@@ -292,6 +371,12 @@ def main():
     F.profile_reset(enable=False)
     prof["launches"] *= args.steps                         # the same kernels run in each timed step
 
+    frontend = None
+    if rank == 0 and not args.no_frontend:
+        try:
+            frontend = frontend_roofline(pkg, device, load_peaks())
+        except Exception as e:       # reported next to the headline, never required for it
+            frontend = dict(error=repr(e))
     if rank == 0:
         peaks = load_peaks()
         k = prof["kernels"].get("qconv_cl_fprop_kernel" if args.precision == "bf16" else "conv_simt_kernel", None)
@@ -316,12 +401,15 @@ def main():
                     vs_baseline=None, dtype=args.precision, data="synthetic",
                     config=dict(workload=args.config, per_gpu_batch=batch, global_batch=batch * world,
                                 time_frames=TIME_DIM, parallelism="dp%d" % world, cuda_graph=use_graph,
+                                caller={"mirror": "seld_model.py (this repository's assembly)",
+                                        "reference": "reference model.py, unmodified, on install_dropin()"}[args.model]
+                                + (" layers only" if args.model == "reference" and args.no_fuse_model else ""),
                                 l2="activations per step (>1 GB) exceed the 126 MB L2; %d distinct input batches "
                                    "are rotated" % args.pool),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                              ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=prof["launches"], roofline=roof,
+                    gpu_launches=prof["launches"], roofline=roof, roofline_frontend=frontend,
                     conv_tflops_per_gpu=cfg["conv_train_gflop"] * value / world / 1e3,
                     conv_frac_of_peak=cfg["conv_train_gflop"] * value / world / 1e3 / peaks["tflops"])
         if world == 1 and not args.no_cpu_baseline:

@@ -284,25 +284,6 @@ int seldq_stft_magphase(const float* x, int32_t n_batch, int32_t n_ch, int64_t n
                         int32_t nperseg, int32_t noverlap, int32_t cut_dc, int32_t output_phase,
                         int32_t cut_last, float* out, void* stream);
 
-/* ---- debug / bring-up probes (tools/umma_probe.py); not part of the reference surface ---- */
-int seldq_probe_tensor_map(void* host_map_128B, const void* gaddr, int32_t elem_bytes, int32_t rank,
-                           const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                           int32_t swizzle);
-int seldq_probe_tma_load(const void* host_map_128B, const void* dev_map_128B, int32_t rank,
-                         const int32_t* coords, uint32_t box_bytes, uint32_t smem_offset,
-                         void* out_smem_dump, uint32_t dump_bytes, void* stream);
-int seldq_probe_umma(const void* a_image, uint32_t a_bytes, const void* b_image, uint32_t b_bytes,
-                     uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int32_t n_mma,
-                     uint32_t a_desc_step, uint32_t b_desc_step, int32_t n_cols,
-                     float* out_128xN, void* stream);
-/* tcgen05.mma issue-rate probes (tools/umma_rate.py, tools/umma_ts.py): cycles per MMA versus N for the product
- * kernels' operand layouts, and the A-from-tensor-memory variant (tcgen05.cp + TS-form MMA).  out: 2 x blocks int64
- * (issue cycles, issue + drain cycles); mode 0 of the second probe returns mismatch / non-zero counts instead. */
-int seldq_probe_umma_rate(uint32_t n, int32_t n_mma, int32_t d_cycle, int32_t mode, int32_t blocks, void* out,
-                          void* stream);
-int seldq_probe_umma_ts(uint32_t n, int32_t n_slabs, int32_t g, int32_t mode, int32_t nbuf, int32_t blocks, void* out,
-                        void* stream);
-
 #ifdef __cplusplus
 }
 #endif

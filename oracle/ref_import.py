@@ -4,9 +4,11 @@ Imports the *unmodified* reference (AuroraEchos/Sound-Event-Localization-and-Det
 from /root/reference so that the oracle restatement in ``oracle/algebra.py`` can be pinned
 against it and golden vectors can be minted (``oracle/make_golden.py``).
 
-/root/reference exists only in the build container, not on the GPU box: everything here is
-guarded by ``available()`` and nothing under ``tests -m gpu``, ``smoke()`` or ``bench.py``
-may call it.
+/root/reference exists only in the build container, not on the GPU box.  What travels to the box is
+``oracle/_ref`` -- a verbatim, git-ignored copy of the reference's Python files made by the committed
+recipe ``oracle/fetch_ref.sh`` (the reference is pure Python, so copying is its whole build).  The root
+is resolved in this order: $SELDQ_REFERENCE_ROOT, /root/reference, oracle/_ref; everything here is
+guarded by ``available()``.  Only tests/, smoke() and bench.py's reference arm may import this module.
 
 Stub recipe: SURVEY.md Appendix A (model.py:3 needs torchinfo, utility_functions.py:9 needs
 librosa; metrics.py:6-10 needs jiwer/pystoi/transformers).
@@ -17,7 +19,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SELDQ_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SHIPPED_ROOT = os.path.join(_HERE, "_ref")
+
+
+def _resolve_root():
+    env = os.environ.get("SELDQ_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", SHIPPED_ROOT):
+        if os.path.isfile(os.path.join(cand, "model.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def available() -> bool:
@@ -124,3 +140,32 @@ def build_reference_model(cfg="DQ_8ch", time_dim=4800, spatial_dropout_rate=0.5,
     m = ns.model.SELD_Model(time_dim=time_dim, spatial_dropout_rate=spatial_dropout_rate,
                             dropout_perc=dropout_perc, **kw)
     return m
+
+
+def load_model_on_dropin(pkg, fuse_model=True):
+    """The reference's model.py, UNMODIFIED, imported on top of the product's drop-in layer modules
+    (pkg.install_dropin(): model.py:7-8 then star-imports the sm_100a layers).  Returns the module object; the
+    interpreter's sys.modules / sys.path are restored afterwards, so the real reference (load()) and the drop-in
+    build can live in one test process."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    _stub("torchinfo", summary=lambda *a, **k: None)
+    _stub("librosa")
+    saved_mods = {n: sys.modules.pop(n) for n in _REF_MODULE_NAMES if n in sys.modules}
+    saved_path = list(sys.path)
+    try:
+        sys.path[:] = [p for p in sys.path if not os.path.abspath(p).startswith(REFERENCE_ROOT)]
+        pkg.install_dropin(fuse_model=fuse_model)
+        sys.path.append(REFERENCE_ROOT)                    # model.py and utility_functions.py only
+        mod = importlib.import_module("model")
+        assert _is_reference_module(mod), mod.__file__
+        assert mod.DualQuaternionConv is pkg.DualQuaternionConv, "model.py did not pick up the drop-in layers"
+        if fuse_model:
+            pkg._maybe_patch_reference_model()
+        return mod
+    finally:
+        # keep the drop-in build reachable only through the returned module object
+        for n in _REF_MODULE_NAMES:
+            sys.modules.pop(n, None)
+        sys.modules.update(saved_mods)
+        sys.path[:] = saved_path

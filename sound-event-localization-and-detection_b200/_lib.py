@@ -118,14 +118,6 @@ _PROTOS = {
                                         ctypes.POINTER(ctypes.c_int32)]),
     "seldq_stft_magphase": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32,
                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P]),
-    "seldq_probe_tensor_map": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32,
-                                              ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
-                                              ctypes.POINTER(ctypes.c_uint32), ctypes.c_int32]),
-    "seldq_probe_tma_load": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_uint32,
-                                            ctypes.c_uint32, _P, ctypes.c_uint32, _P]),
-    "seldq_probe_umma": (ctypes.c_int, [_P, ctypes.c_uint32, _P, ctypes.c_uint32, ctypes.c_uint64,
-                                        ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32, ctypes.c_uint32,
-                                        ctypes.c_uint32, ctypes.c_int32, _P, _P]),
 }
 
 _lib = None

@@ -167,8 +167,27 @@ def stage_operand(t, desc, which, want_cl=True, want_t16=False):
 # packed bf16 weight tiles, one set per (layer, pass); re-packed when a weight's version counter moves
 # (optimizer.step updates in place) and always while a CUDA graph is being captured, so that a replayed
 # step packs the weights it is about to use
+# Entries hold their weights through weak references (a model that is dropped frees its tiles, and repack_all()
+# never re-packs dead models).  Validity = (version counters, epoch): writes through `.data` (dist.broadcast of
+# p.data, EMA swaps, clipping via p.data.copy_) do NOT move a version counter -- such callers must call
+# invalidate_packed_weights(), as trainer.broadcast_parameters / FlatGradBucket do.
 _PACKED = {}
 _PACK_EPOCH = 0
+
+
+def _live_weights(info):
+    """The weight tensors of a cache entry, or None when any of them has been freed."""
+    ws = tuple(r() for r in info[0])
+    return None if any(w is None for w in ws) else ws
+
+
+def _evict_dead():
+    global _PACK_TABLE
+    dead = [k for k, ent in _PACKED.items() if _live_weights(ent[2]) is None]
+    for k in dead:
+        del _PACKED[k]
+    if dead:
+        _PACK_TABLE = None
 
 
 def invalidate_packed_weights():
@@ -195,6 +214,9 @@ def packed_weights(weights, desc, pass_, cache=True):
     key = (tuple(w.data_ptr() for w in weights), pass_, desc.algebra, desc.cin, desc.cout, desc.k_h, desc.k_w)
     versions = tuple(w._version for w in weights)
     ent = _PACKED.get(key)
+    if ent is not None:
+        if _live_weights(ent[2]) is None:
+            ent = None                  # the entry's tensors were freed: the address now belongs to something else
     capturing = torch.cuda.is_current_stream_capturing()
     if ent is not None and ent[1].numel() == nbytes and ent[0] == versions and ent[3] == _PACK_EPOCH:
         # valid as long as the version counters stand still; while a graph is being captured only sets that
@@ -209,7 +231,9 @@ def packed_weights(weights, desc, pass_, cache=True):
     if ent is None or ent[1] is not buf:
         global _PACK_TABLE
         _PACK_TABLE = None                              # a new buffer: the multi-pack table must be rebuilt
-    _PACKED[key] = (versions, buf, (tuple(weights), _lib.ConvDesc.from_buffer_copy(desc), pass_), _PACK_EPOCH)
+    import weakref
+    _PACKED[key] = (versions, buf, (tuple(weakref.ref(w) for w in weights), _lib.ConvDesc.from_buffer_copy(desc), pass_),
+                    _PACK_EPOCH)
     return buf
 
 
@@ -222,6 +246,7 @@ def repack_all():
     ready (and a captured step holds one pack launch instead of one per layer and pass)."""
     import ctypes
     global _PACK_TABLE, _PACK_EPOCH
+    _evict_dead()
     if not _PACKED:
         return
     L = _lib.lib()
@@ -231,7 +256,8 @@ def repack_all():
         host = torch.zeros(len(keys) * esz, dtype=torch.uint8)
         max_items = 0
         for i, k in enumerate(keys):
-            _, buf, (ws, desc, pass_), _ = _PACKED[k]
+            _, buf, info, _ = _PACKED[k]
+            ws, desc, pass_ = _live_weights(info), info[1], info[2]
             wp = _lib.ptr_array([w.data_ptr() for w in ws])
             items = ctypes.c_int32()
             _lib.check(L.seldq_conv_pack_table_fill(ctypes.byref(desc), pass_, wp, buf.data_ptr(),
@@ -244,7 +270,7 @@ def repack_all():
         L.seldq_conv_pack_table_run(table.data_ptr(), count, max_items, _stream())))
     _PACK_EPOCH += 1
     for k, (ver, buf, info, _) in list(_PACKED.items()):
-        _PACKED[k] = (tuple(w._version for w in info[0]), buf, info, _PACK_EPOCH)
+        _PACKED[k] = (tuple(w._version for w in _live_weights(info)), buf, info, _PACK_EPOCH)
 
 
 def _conv_desc(algebra, prec, x_shape, cout, ksize, stride, padding, dilation):

@@ -39,6 +39,25 @@ def _side_stream(dev):
     return _SIDE[key]
 
 
+def next_drop_seed(module, device):
+    """Seed of this step's dropout masks on the fused paths of `module` (a ConvTC_Block or TC_Block, the mirror's or
+    the reference's own): an int64 device scalar kept as the non-persistent buffer `_drop_seed`.  Its base value is
+    drawn from the torch RNG the first time the module takes a fused path -- so torch.manual_seed governs it, every
+    replica (per-rank seed) and every module (branch_A / branch_B, CNN / TCN) gets its own, and a resumed run that
+    restores the RNG state continues with fresh masks -- and it advances by one per step (a device-side add, so a
+    captured CUDA graph keeps stepping it).  The kernels hash (seed, per-layer salt, element index)."""
+    seed = module._buffers.get("_drop_seed")
+    if seed is None or seed.device != device or not getattr(module, "_drop_seed_ready", False):
+        base = torch.randint(1, 2 ** 62, (1,), dtype=torch.int64)          # default CPU generator
+        if seed is None or seed.device != device:
+            module.register_buffer("_drop_seed", base.to(device), persistent=False)
+        else:
+            seed.copy_(base)
+        module._drop_seed_ready = True
+    module._drop_seed.add_(1)
+    return module._drop_seed
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 

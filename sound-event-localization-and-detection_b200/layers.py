@@ -17,6 +17,17 @@ from . import functional as F
 from . import init as I
 from ._lib import ALG_DQ, ALG_Q
 
+
+
+def _dropin_hook():
+    """install_dropin(fuse_model=True): the first layer the reference's model.py constructs wires the fused glue
+    kernels into model.TC_Block / ConvTC_Block (package __init__._maybe_patch_reference_model)."""
+    import sys
+    hook = getattr(sys.modules.get(__package__), "_maybe_patch_reference_model", None)
+    if hook is not None:
+        hook()
+
+
 _Q_NAMES = ("r_weight", "i_weight", "j_weight", "k_weight")
 _DQ_NAMES = _Q_NAMES + tuple(n + "_2" for n in _Q_NAMES)
 
@@ -66,6 +77,7 @@ class _BlockConvBase(Module):
         else:
             self.register_parameter("bias", None)
         self.reset_parameters()
+        _dropin_hook()
 
     def _weights(self):
         return tuple(getattr(self, n) for n in self._names)

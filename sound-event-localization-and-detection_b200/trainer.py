@@ -45,6 +45,10 @@ class FlatGradBucket(object):
                 p.grad = self.flat[off:off + n].view_as(p)
                 off += n
         self.flat_param.grad = self.flat
+        if dev.type == "cuda":
+            # p.data was re-pointed: packed bf16 tiles keyed on the old addresses are stale
+            from . import functional
+            functional.invalidate_packed_weights()
 
     def zero(self):
         self.flat.zero_()
@@ -76,8 +80,14 @@ class Trainer(object):
 
     def broadcast_parameters(self, src=0):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            for t in list(self.model.parameters()) + list(self.model.buffers()):
+            # the dropout seeds of the fused paths (seld_model._drop_seed) stay per replica: every rank draws its own
+            # from its torch RNG, so the Dropout / Dropout1d masks differ across the global batch
+            bufs = [b for n, b in self.model.named_buffers() if not n.endswith("_drop_seed")]
+            for t in list(self.model.parameters()) + bufs:
                 dist.broadcast(t.data, src=src, group=self.group)
+            if self._functional is not None:
+                # writes through .data do not move the version counters the packed-weight cache watches
+                self._functional.invalidate_packed_weights()
 
     def capture(self, x, target, warmup=3):
         """Captures zero_grad -> forward -> loss -> backward -> all-reduce -> Adam into ONE CUDA graph

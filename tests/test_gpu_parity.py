@@ -155,10 +155,12 @@ def test_stft_edge_cases(seldq):
         _check_stft(out, ref, 3, True)
 
 
-def _run_model(seldq, name, prec):
+def _run_model(seldq, name, prec, model_cls=None):
+    """model_cls: the model class to build (default: the product's mirror; tests/test_gpu_reference_model.py passes
+    the reference's own model.SELD_Model imported on the drop-in layers)."""
     meta, d = load_golden(name)
     cfg = dict(meta["cfg"])
-    m = seldq.SELD_Model(time_dim=meta["time_dim"], spatial_dropout_rate=0, dropout_perc=0, **cfg)
+    m = (model_cls or seldq.SELD_Model)(time_dim=meta["time_dim"], spatial_dropout_rate=0, dropout_perc=0, **cfg)
     m.load_state_dict({k[6:]: torch.from_numpy(np.asarray(v)) for k, v in d.items() if k.startswith("param/")})
     m = m.cuda().train()
     x, target = cuda(d["x"]), cuda(d["target"])
@@ -287,8 +289,7 @@ def test_fused_tcn_blocks_match_layerwise(seldq, domain, chans):
                 res = xi
                 if fused:
                     assert seldq.fused.tcn_stack_supported(mod.ResBlocks, res, True)
-                    mod._drop_seed.add_(1)
-                    y = seldq.fused.tcn_stack(res, mod.ResBlocks, mod._drop_seed)
+                    y = seldq.fused.tcn_stack(res, mod.ResBlocks, seldq.fused.next_drop_seed(mod, res.device))
                 else:
                     y = None
                     for b in mod.ResBlocks:
@@ -369,6 +370,7 @@ def test_fused_first_layer_backward_matches_two_kernel_path(seldq):
         try:
             blk.zero_grad(set_to_none=True)
             blk._drop_seed.fill_(3)
+            blk._drop_seed_ready = True              # keep the value set above: both runs draw the same masks
             with seldq.precision("bf16"):
                 z = blk._cnn_forward(x)
                 if gz is None:

@@ -1,0 +1,86 @@
+"""The reference's OWN model.py, unmodified, running on the sm_100a path ("model.py and train.py use the new path
+as a drop-in", BASELINE.json north_star): model.py is imported from the shipped copy of the reference (oracle/_ref,
+made by oracle/fetch_ref.sh; /root/reference in the build container) on top of install_dropin(), so its
+`from dual_quaternion.dual_quaternion_layers import *` (model.py:7-8) resolves to this repository's layer modules.
+
+fuse=False: only the layers are replaced -- model.py's own forward code drives them one by one.
+fuse=True:  install_dropin(fuse_model=True) also rebinds model.TC_Block / ConvTC_Block / MultiHeadAttention.forward
+            to the fused CNN / TCN glue kernels (seld_model.patch_reference_model); model.py itself is untouched.
+Both are held to the fixtures minted from the reference on CPU in float64, with the gates of test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import algebra as A
+from oracle import ref_import
+from test_gpu_parity import _run_model
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_import.available(), reason="no reference tree (oracle/_ref) on this box")]
+
+_MODS = {}
+
+
+def _reference_model_module(seldq, fuse):
+    if fuse not in _MODS:
+        _MODS[fuse] = ref_import.load_model_on_dropin(seldq, fuse_model=fuse)
+    return _MODS[fuse]
+
+
+@pytest.mark.parametrize("name", ["model_dq_tiny", "model_dq_mid"])
+def test_unmodified_model_py_fp32_matches_fixture(seldq, name):
+    mod = _reference_model_module(seldq, False)
+    assert mod.DualQuaternionConv is seldq.DualQuaternionConv
+    meta, d, sed, doa, loss, grads = _run_model(seldq, name, "fp32", model_cls=mod.SELD_Model)
+    assert A.rel_err(sed, d["sed"]) < 1e-4
+    assert A.rel_err(doa, d["doa"]) < 1e-4
+    assert abs(loss - float(d["loss"])) < 1e-4 * max(1.0, abs(float(d["loss"])))
+    bad = {}
+    for k, g in grads.items():
+        e, tol = A.rel_err(g, d["grad/" + k]), max(5e-4, 4.0 * float(d["ref32err/" + k]))
+        if not e < tol:
+            bad[k] = (e, tol)
+    assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+@pytest.mark.parametrize("name", ["model_dq_tiny", "model_dq_mid"])
+def test_unmodified_model_py_bf16_matches_fixture(seldq, name, fuse):
+    mod = _reference_model_module(seldq, fuse)
+    sm = __import__("importlib").import_module(seldq.__name__ + ".seld_model")
+    if fuse:
+        assert mod.TC_Block.forward is sm.tc_block_forward and mod.ConvTC_Block.forward is sm.convtc_block_forward
+    else:
+        assert mod.TC_Block.forward is not sm.tc_block_forward
+    meta, d, sed, doa, loss, grads = _run_model(seldq, name, "bf16", model_cls=mod.SELD_Model)
+    emu = "bf16emu16" if (fuse and name == "model_dq_mid") else "bf16emu"
+    assert A.rel_err(sed, d["sed"]) < 2e-2
+    assert A.rel_err(doa, d["doa"]) < 2e-2
+    assert A.rel_err(sed, d[emu + "/sed"]) < 1e-2
+    assert A.rel_err(doa, d[emu + "/doa"]) < 1e-2
+    bad = {}
+    for k, g in grads.items():
+        noise = A.rel_err(d[emu + "_grad/" + k], d["grad/" + k])
+        e, tol = A.rel_err(g, d["grad/" + k]), max(2e-2, 2.0 * noise)
+        if not e < tol:
+            bad[k] = (e, tol)
+    assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
+
+
+def test_unmodified_model_py_fused_step_matches_mirror(seldq):
+    """Same weights, same input: the reference's model.py with the fused glue wired in by install_dropin must launch
+    the same kernels as the repository's mirror (seld_model.SELD_Model) -- outputs agree to the tensor path's
+    run-to-run noise."""
+    mod = _reference_model_module(seldq, True)
+    meta, d = load_golden("model_dq_mid")
+    outs = []
+    for cls in (mod.SELD_Model, seldq.SELD_Model):
+        m = cls(time_dim=meta["time_dim"], spatial_dropout_rate=0, dropout_perc=0, **dict(meta["cfg"]))
+        m.load_state_dict({k[6:]: torch.from_numpy(np.asarray(v)) for k, v in d.items() if k.startswith("param/")})
+        m = m.cuda().train()
+        with seldq.precision("bf16"):
+            sed, doa = m(torch.from_numpy(np.ascontiguousarray(d["x"], np.float32)).cuda())
+        torch.cuda.synchronize()
+        outs.append((sed.detach().cpu().numpy(), doa.detach().cpu().numpy()))
+    assert A.rel_err(outs[0][0], outs[1][0]) < 2e-3 and A.rel_err(outs[0][1], outs[1][1]) < 2e-3

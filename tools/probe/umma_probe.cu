@@ -3,16 +3,18 @@
 //   * seldq_probe_umma     : host-provided shared-memory images + raw descriptors -> tcgen05.mma ->
 //                            TMEM -> dump (checks descriptor semantics: major-ness, LBO/SBO, swizzle,
 //                            negate bits) without recompiling
-// They expose hardware behaviour only; nothing in the product path calls them.
+// They expose hardware behaviour only; nothing in the product path calls them, and they are built into their own
+// tools library (tools/probe/libseldq_probe.so), not into libseldq.so.
 #include <cstdlib>
 
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
-#include "launch.h"
-#include "tensor_map.h"
-#include "umma_ptx.cuh"
+#include "seldq_probe.h"
+#include "../../sound-event-localization-and-detection_b200/csrc/launch.h"
+#include "../../sound-event-localization-and-detection_b200/csrc/tensor_map.h"
+#include "../../sound-event-localization-and-detection_b200/csrc/umma_ptx.cuh"
 
 namespace seldq {
 namespace probe {
@@ -402,3 +404,5 @@ extern "C" int seldq_probe_umma_ts(uint32_t n, int32_t n_slabs, int32_t g, int32
   probe::umma_ts_kernel<<<blocks, 128, smem, (cudaStream_t)stream>>>(n, n_slabs, g, mode, nbuf, (long long*)out);
   return check_launch("probe::umma_ts_kernel");
 }
+
+extern "C" const char* seldq_probe_last_error(void) { return seldq::error_buffer(); }

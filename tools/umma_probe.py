@@ -18,9 +18,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("sound-event-localization-and-detection_b200")
 L = pkg._lib
-lib = L.lib()
+sys.path.insert(0, os.path.join(ROOT, "tools", "probe"))
+import probe_lib  # noqa: E402
+lib = probe_lib.lib()
 
+_P = ctypes.c_void_p
+lib.seldq_probe_tensor_map.argtypes = [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64),
+                                       ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint32), ctypes.c_int32]
+lib.seldq_probe_tma_load.argtypes = [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_uint32,
+                                     ctypes.c_uint32, _P, ctypes.c_uint32, _P]
+lib.seldq_probe_umma.argtypes = [_P, ctypes.c_uint32, _P, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
+                                 ctypes.c_uint32, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int32, _P, _P]
+lib.seldq_probe_last_error.restype = ctypes.c_char_p
 SW_NONE, SW_128 = 0, 2
+
+
+def check(rc):
+    assert rc == 0, (rc, lib.seldq_probe_last_error())
+
 
 
 def bf16_bits(a):
@@ -48,7 +63,7 @@ def run_umma(a_img, b_img, a_desc, b_desc, idsc, n_mma, a_step, b_step, n_cols):
     out = torch.full((128, n_cols), float("nan"), device="cuda")
     rc = lib.seldq_probe_umma(a.data_ptr(), a.numel(), b.data_ptr(), b.numel(), a_desc, b_desc, idsc, n_mma,
                               a_step, b_step, n_cols, out.data_ptr(), None)
-    L.check(rc)
+    check(rc)
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
@@ -204,7 +219,7 @@ def probe_t1(res):
         dims = (ctypes.c_uint64 * 2)(W, C)
         strides = (ctypes.c_uint64 * 1)(W * 2)
         box = (ctypes.c_uint32 * 2)(64, 16)
-    L.check(lib.seldq_probe_tensor_map(tmap, src16.data_ptr(), 2, rank, dims, strides, box, swz))
+    check(lib.seldq_probe_tensor_map(tmap, src16.data_ptr(), 2, rank, dims, strides, box, swz))
     print("tensor map words:", [hex(w) for w in np.frombuffer(bytes(tmap), np.uint32)[:16]])
     dmap = torch.from_numpy(np.frombuffer(bytes(tmap), np.uint8).copy()).cuda() if via_global else None
     cases = {"interior": (8, 8), "right_oob": (176, 24), "chan_oob": (0, 32), "neg_aligned": (-8, 0),
@@ -217,7 +232,7 @@ def probe_t1(res):
         coords = (ctypes.c_int32 * 4)(w0, 0, c0, 0) if rank == 4 else (ctypes.c_int32 * 4)(w0, c0, 0, 0)
         t0 = time.time()
         try:
-            L.check(lib.seldq_probe_tma_load(tmap, dmap.data_ptr() if via_global else None, rank, coords, 16 * 128, 0,
+            check(lib.seldq_probe_tma_load(tmap, dmap.data_ptr() if via_global else None, rank, coords, 16 * 128, 0,
                                              dump.data_ptr(), 16 * 128, None))
             torch.cuda.synchronize()
         finally:

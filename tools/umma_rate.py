@@ -1,4 +1,4 @@
-"""tcgen05.mma issue-rate probe (csrc/umma_probe.cu): cycles per MMA versus N for the product kernels'
+"""tcgen05.mma issue-rate probe (tools/probe/umma_probe.cu): cycles per MMA versus N for the product kernels'
 operand layouts.  Run on a B200:  python tools/umma_rate.py"""
 import ctypes
 import importlib
@@ -9,7 +9,9 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("sound-event-localization-and-detection_b200")
-L = pkg._lib.lib()
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "probe"))
+import probe_lib  # noqa: E402
+L = probe_lib.lib()
 L.seldq_probe_umma_rate.argtypes = [ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                     ctypes.c_void_p, ctypes.c_void_p]
 L.seldq_probe_umma_rate.restype = ctypes.c_int

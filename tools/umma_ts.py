@@ -1,4 +1,4 @@
-"""A-from-tensor-memory probe (csrc/umma_probe.cu, probe::umma_ts_kernel): does a K = 16 slab copied once to
+"""A-from-tensor-memory probe (tools/probe/umma_probe.cu, probe::umma_ts_kernel): does a K = 16 slab copied once to
 tensor memory (tcgen05.cp.128x256b) and read from there by G small MMAs beat G shared-memory-operand MMAs that
 each re-read the slab?  Run on a B200:  python tools/umma_ts.py"""
 import ctypes
@@ -10,7 +10,9 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("sound-event-localization-and-detection_b200")
-L = pkg._lib.lib()
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "probe"))
+import probe_lib  # noqa: E402
+L = probe_lib.lib()
 L.seldq_probe_umma_ts.argtypes = [ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                   ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
 L.seldq_probe_umma_ts.restype = ctypes.c_int
