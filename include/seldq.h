@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SELDQ_ABI_VERSION 2
+#define SELDQ_ABI_VERSION 3
 
 typedef enum {
   SELDQ_OK = 0,
@@ -158,6 +158,35 @@ int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_c
  * pre-staged (x as CL operand, the gy's as T16 operands). */
 int seldq_conv_wgrad_pair(const seldq_conv_desc_t* d, const void* x_cl, const void* gy_t16_a, const void* gy_t16_b,
                           float* const* host_gw_a, float* const* host_gw_b, int32_t accumulate, void* stream);
+
+/* Fused glue of a convolution's fp32 output (bf16 path, stride 1), replacing the element-wise passes model.py
+ * runs behind conv2_skip / conv2_residual and in front of the BatchNorms (model.py:114-132, :210-216):
+ *   mode 0   y  = conv(x)
+ *   mode 1   y += conv(x)              the running sum of the blocks' skip outputs (model.py:210-216)
+ *   mode 2   y  = addend + conv(x)     x + conv2_residual(y) (model.py:132); addend has y's layout, may not alias y
+ *   stats    when not NULL: per-channel (sum, sum of squares) of the values STORED in y are ADDED to
+ *            stats[2 c], stats[2 c + 1] (doubles, zeroed by the caller) -- the batch statistics of the BatchNorm
+ *            that follows (batch_filter2 / batch_gate2 / the next block's batch_filter1), so no pass re-reads y */
+typedef struct {
+  int32_t mode;
+  const float* addend;
+  double* stats;
+} seldq_conv_epilogue_t;
+
+/* one convolution pass (SELDQ_PASS_FWD | SELDQ_PASS_DGRAD) from pre-staged operands with a fused epilogue */
+int seldq_conv_epi(const seldq_conv_desc_t* d, int32_t pass, const void* in_cl, const void* packed_w, float* out,
+                   const seldq_conv_epilogue_t* epi, void* stream);
+
+/* TWO sibling convolutions of equal geometry in ONE launch: conv1_filter / conv1_gate (same x) or conv2_skip /
+ * conv2_residual (same y) of a residual block (model.py:118-119, :130-131), forward or dgrad (then the inputs are
+ * the two output gradients).  At the reference's batch size of 1 a TCN launch holds ~2 us of tensor-core work in
+ * ~10 us of fixed cost; sharing the launch halves that cost.  Operands pre-staged (CL operands, packed weights of
+ * the same pass), fp32 outputs, epilogues as above (epi_a / epi_b may be NULL).  Needs >= 8 channels per component
+ * on the K side (seldq_conv_pair_supported returns 1). */
+int seldq_conv_pair_supported(const seldq_conv_desc_t* d, int32_t pass);
+int seldq_conv_pair(const seldq_conv_desc_t* d, int32_t pass, const void* in_cl_a, const void* in_cl_b,
+                    const void* packed_a, const void* packed_b, float* out_a, float* out_b,
+                    const seldq_conv_epilogue_t* epi_a, const seldq_conv_epilogue_t* epi_b, void* stream);
 
 /* ---- glue between the convolutions (E1 in SURVEY.md 8a) -------------------------------------------------
  * CNN block, model.py:276-283: conv -> BatchNorm2d(train) -> ReLU -> MaxPool2d([pool,1]) -> Dropout(drop_p).

@@ -181,13 +181,126 @@ def model_case(name, cfg, time_dim, B, seed):
     print(name, m.model_name, meta["n_params"], "params;", "loss", loss.item())
 
 
+def sample_indices(numel, i, n=4096):
+    """The fixed subset of a flattened tensor that full-size fixtures keep (tensor number i in named_parameters order)."""
+    if numel <= n:
+        return np.arange(numel)
+    return np.sort(np.random.default_rng(1000 + i).choice(numel, n, replace=False))
+
+
+def full_size_input(cfg, time_dim, B, seed):
+    """Seeded input / target of a full-size fixture: regenerated by the tests, only check sums are stored."""
+    rng = np.random.default_rng(seed + 100)
+    x = rng.standard_normal((B, cfg["input_channels"], cfg["freq_dim"], time_dim)).astype(np.float32)
+    n_out, n_sed = time_dim // 8, 14 * 3
+    sed_t = (rng.random((B, n_out, n_sed)) < 0.05).astype(np.float64)
+    doa_t = (2 * rng.random((B, n_out, n_sed * 3)) - 1) * np.repeat(sed_t, 3, axis=-1)
+    return x, np.concatenate([sed_t, doa_t], axis=-1).astype(np.float32)
+
+
+def full_size_case(name, cfg_name, time_dim, B, seed):
+    """BASELINE-size forward + backward of the reference's model.SELD_Model in float64 (model.py:324-480 +
+    train.py:186-204), dropout off.  The fixture keeps the outputs, the loss and, per parameter, the gradient's L2
+    norm and a fixed 4096-element sample (sample_indices); input, target and initial weights regenerate from the
+    seeds (full_size_input; np.random.seed / torch.manual_seed as train.py:214-221) and are pinned by check sums.
+    Yard-sticks as in model_case: the reference's own float32 run, and the ideal bf16-operand emulation with fp16
+    storage of the 2-d conv outputs (what the fused path does)."""
+    from oracle import algebra as A
+    cfg = dict(ref_import.COMMON)
+    cfg.update(ref_import.CONFIGS[cfg_name])
+    m = ref_import.build_reference_model(cfg, time_dim=time_dim, spatial_dropout_rate=0, dropout_perc=0, seed=seed)
+    m.train()
+    sd32 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x, target = full_size_input(cfg, time_dim, B, seed)
+    n_sed = 14 * 3
+    d = dict(x_sum=np.float64(x.astype(np.float64).sum()), x_abs=np.float64(np.abs(x.astype(np.float64)).sum()),
+             target_sum=np.float64(target.astype(np.float64).sum()))
+    names = [k for k, _ in m.named_parameters()]
+    for k, v in sd32.items():
+        if v.dtype.is_floating_point:
+            d["psum/" + k] = np.float64(v.double().abs().sum().item())
+    m = m.double()
+    sed, doa = m(torch.tensor(x, dtype=torch.float64))
+    loss = seld_loss(sed, doa, torch.tensor(target, dtype=torch.float64), n_sed)
+    loss.backward()
+    d.update(sed=sed.detach().numpy().astype(np.float32), doa=doa.detach().numpy().astype(np.float32),
+             loss=np.float64(loss.item()))
+    grads64, ngrad = {}, 0
+    for i, (k, p) in enumerate(m.named_parameters()):
+        if p.grad is None:
+            continue
+        g = p.grad.numpy().ravel()
+        grads64[k] = g
+        d["gnorm/" + k] = np.float64(np.linalg.norm(g))
+        d["gmax/" + k] = np.float64(np.abs(g).max())
+        d["gsample/" + k] = g[sample_indices(g.size, i)].astype(np.float32)
+        ngrad += 1
+    del m
+    print(name, "float64 run done, loss", loss.item(), flush=True)
+    m32 = ref_import.build_reference_model(cfg, time_dim=time_dim, spatial_dropout_rate=0, dropout_perc=0, seed=seed)
+    m32.load_state_dict(sd32)
+    m32.train()
+    s32, d32 = m32(torch.tensor(x))
+    seld_loss(s32, d32, torch.tensor(target), n_sed).backward()
+    for k, p in m32.named_parameters():
+        if p.grad is not None:
+            d["ref32err/" + k] = np.float64(np.abs(p.grad.numpy().ravel().astype(np.float64) - grads64[k]).max()
+                                            / max(d["gmax/" + k], 1e-300))
+    d["ref32/sed_err"] = np.float64(A.rel_err(s32.detach().numpy(), d["sed"]))
+    d["ref32/doa_err"] = np.float64(A.rel_err(d32.detach().numpy(), d["doa"]))
+    del m32
+    print(name, "float32 run done", flush=True)
+    from oracle import bf16_emulation, cpu_model
+    me = cpu_model.build_model(time_dim=time_dim, spatial_dropout_rate=0, dropout_perc=0, **cfg)
+    me.load_state_dict(sd32)
+    me = me.double().train()
+    with bf16_emulation.bf16_operand_convs(store_conv2d_f16=True):
+        se, de = me(torch.tensor(x, dtype=torch.float64))
+        cpu_model.seld_loss(se, de, torch.tensor(target, dtype=torch.float64)).backward()
+    d["bf16emu16/sed"], d["bf16emu16/doa"] = se.detach().numpy().astype(np.float32), de.detach().numpy().astype(np.float32)
+    for k, p in me.named_parameters():
+        if p.grad is not None:
+            d["bf16emu16_err/" + k] = np.float64(np.abs(p.grad.numpy().ravel() - grads64[k]).max()
+                                                 / max(d["gmax/" + k], 1e-300))
+    meta = dict(kind="model_full", cfg=cfg, cfg_name=cfg_name, time_dim=time_dim, B=B, seed=seed, n_grads=ngrad,
+                param_names=names, source="model.py:324-480 + train.py:186-204",
+                input="oracle.make_golden.full_size_input(cfg, time_dim, B, seed)")
+    _save(name, meta, d)
+    print(name, "saved;", ngrad, "gradient tensors")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
+    if "--full-size" in sys.argv:
+        full_size_case("model_dq_8ch_full", "DQ_8ch", 4800, 1, 1)
+        return
+    if "--round2" in sys.argv:
+        round2_cases(ns)
+        return
     only_models = "--models-only" in sys.argv
     if not only_models:
         per_op_cases(ns)
     model_cases()
+
+
+def round2_cases(ns):
+    """Pins added in round 2: the 16-channel first layer (C4: compact 8 x (24, 2, 3, 3)), a reduced 16chMagPhase
+    model whose first block has the real 16 -> 192 widths, and a reduced real-valued model (config
+    SERVER_SELD-TCN-S1-PHI_8ch.txt: nn.Conv* layers)."""
+    conv_case(ns, "conv2d_dq_first16", "DQ", 2, 1, 2, 24, (16, 136), 3, 1, 1, 1, False, 22)
+    tiny = dict(ref_import.COMMON)
+    tiny.update(input_channels=8, freq_dim=128, domain="DQ", domain_classifier="DQ",
+                cnn_filters=[16, 16, 16], G=16, U=16, V=[16, 16], fc_layers=[16],
+                parallel_ConvTC_block="False", parallel_magphase=False, extra_name="_tiny")
+    c4 = dict(tiny)
+    c4.update(input_channels=16, freq_dim=256, cnn_filters=[192, 64, 64], G=128, U=128, V=[128, 128], fc_layers=[128],
+              extra_name="_16chMagPhase_mid")
+    model_case("model_dq_16ch_mid", c4, 160, 2, 5)
+    r8 = dict(tiny)
+    r8.update(domain="R", domain_classifier="R", freq_dim=256, cnn_filters=[32, 32, 32], G=64, U=64, V=[64, 64],
+              fc_layers=[64], extra_name="_r_mid")
+    model_case("model_r_mid", r8, 160, 2, 6)
 
 
 def per_op_cases(ns):

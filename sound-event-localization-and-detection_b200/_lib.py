@@ -48,6 +48,14 @@ TCN_PREACT_FWD, TCN_ROW_STATS, TCN_GATE_FWD, TCN_RESIDUAL_FWD = 0, 1, 2, 3
 TCN_GATE_BWD_REDUCE, TCN_GATE_BWD_APPLY, TCN_PREACT_BWD_REDUCE, TCN_PREACT_BWD_APPLY = 4, 5, 6, 7
 
 
+class ConvEpilogue(ctypes.Structure):
+    """seldq_conv_epilogue_t (include/seldq.h)."""
+    _fields_ = [("mode", ctypes.c_int32), ("addend", ctypes.c_void_p), ("stats", ctypes.c_void_p)]
+
+
+EPI_STORE, EPI_ACCUMULATE, EPI_ADD = 0, 1, 2
+
+
 class LinearDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("algebra", "precision", "rows", "in_features", "out_features")]
 
@@ -103,6 +111,11 @@ _PROTOS = {
                                         ctypes.c_size_t, _P]),
     "seldq_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.POINTER(_P), _P,
                                         ctypes.c_int32, _P, ctypes.c_size_t, _P]),
+    "seldq_conv_epi": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32, _P, _P, _P, ctypes.POINTER(ConvEpilogue),
+                                      _P]),
+    "seldq_conv_pair_supported": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32]),
+    "seldq_conv_pair": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32, _P, _P, _P, _P, _P, _P,
+                                       ctypes.POINTER(ConvEpilogue), ctypes.POINTER(ConvEpilogue), _P]),
     "seldq_conv_wgrad_pair": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, ctypes.POINTER(_P),
                                              ctypes.POINTER(_P), ctypes.c_int32, _P]),
     "seldq_linear_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(LinearDesc), ctypes.c_int32]),

@@ -55,20 +55,57 @@ __device__ __forceinline__ uint32_t to_f16x2_sat(float lo, float hi) {
   return r;
 }
 
-// Unit schedule of a CTA: units are ordered heaviest group first; round r hands unit r*G + b to CTA b in even rounds
-// and r*G + (G-1-b) in odd rounds (snake order), so the few units of a last, partial round go to the CTAs that
-// hold the lightest units of the round before instead of the heaviest.  Returns -1 when the CTA sits a round out.
-__device__ __forceinline__ int unit_of_round(int round, int total_units) {
-  const int G = (int)gridDim.x, b = (int)blockIdx.x;
-  const int u = round * G + ((round & 1) ? G - 1 - b : b);
-  return u < total_units ? u : -1;
+// Per-channel sums over the 32 rows a warp holds: every lane owns v[0..16) = 16 channels of ONE row.  Butterfly
+// "halve the channels, double the rows": after the exchanges with lanes ^16, ^8, ^4, ^2 a lane holds the partial sum
+// of ONE channel, ch = bit4 * 8 + bit3 * 4 + bit2 * 2 + bit1 of its lane number; the last exchange (^1) completes it
+// in both lanes of a pair.  15 shuffles instead of 16 x 5.
+__device__ __forceinline__ float warp_channel_sums(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mine = hi ? v[8 + j] : v[j], other = hi ? v[j] : v[8 + j];
+      a[j] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+    }
+  }
+  {
+    const bool hi = (lane & 8) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mine = hi ? a[4 + j] : a[j], other = hi ? a[j] : a[4 + j];
+      b[j] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+    }
+  }
+  {
+    const bool hi = (lane & 4) != 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float mine = hi ? b[2 + j] : b[j], other = hi ? b[j] : b[2 + j];
+      c[j] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+    }
+  }
+  const bool hi = (lane & 2) != 0;
+  const float mine = hi ? c[1] : c[0], other = hi ? c[0] : c[1];
+  float d = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
 }
+__device__ __forceinline__ int warp_channel_of_lane(int lane) { return (lane >> 1) & 15; }
 
-template <int GC>
+// GLUE = the fused-glue epilogue of the fp32 output path (FpropParams::epi_mode / stats) is compiled in; the plain
+// instantiations carry none of its registers or branches
+template <int GC, bool GLUE>
 __global__ void __launch_bounds__(kFpropThreads, 1)
-qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ FpropParams p) {
+qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
+                      const __grid_constant__ FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
+  // sibling launch: even CTAs serve problem 0, odd CTAs problem 1; G CTAs share a problem's units
+  const int prob = p.nprob == 2 ? (int)(blockIdx.x & 1u) : 0;
+  const int G = p.nprob == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int cta = p.nprob == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const CUtensorMap& tm_in = prob ? tm_in1 : tm_in0;
   __shared__ uint2 op_tbl_s[kOpTableEntries];
   __shared__ __align__(16) uint8_t out_stage[4 * kEpiSets][8 * 64];    // per epilogue warp: [8 ch][32 w] fp16
   // warp index through a shuffle: provably warp-uniform, so role branches and the MMA loop compile to the
@@ -134,13 +171,13 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         ptx::mbar_arrive_expect_tx(w_bar, p.w_bytes);
         for (uint32_t off = 0; off < p.w_bytes; off += 32768u) {
           const uint32_t n = p.w_bytes - off < 32768u ? p.w_bytes - off : 32768u;
-          ptx::bulk_load(b_img + off, p.packed + off, n, w_bar);
+          ptx::bulk_load(b_img + off, (prob ? p.packed1 : p.packed) + off, n, w_bar);
         }
       }
       pdl_wait();            // activations of the previous kernel from here on (the weights above never race)
       uint32_t slot = 0, parity = 0;
-      for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
-        const int u = unit_of_round(round, p.total_units);
+      for (int round = 0; round * G < p.total_units; ++round) {
+        const int u = unit_of_round(round, p.total_units, G, cta);
         if (u < 0) continue;
         const int group = p.group_order[u / p.total_tiles];
         int r = u % p.total_tiles;
@@ -194,8 +231,8 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
                                            : ((uint32_t)my_tl * p.box_bytes) >> 4;
       if (!p.dense) ptx::mbar_wait(w_bar, 0);
       uint32_t slot = 0, parity = 0, it = 0;
-      for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
-        const int u = unit_of_round(round, p.total_units);
+      for (int round = 0; round * G < p.total_units; ++round) {
+        const int u = unit_of_round(round, p.total_units, G, cta);
         if (u < 0) continue;
         const int gi = u / p.total_tiles;
         const uint32_t mask = p.chunk_mask[p.group_order[gi]];
@@ -263,8 +300,8 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     const bool vec16 = p.out16 != nullptr && (p.OW & 7) == 0 && (p.out_sC & 7) == 0 && (p.out_sH & 7) == 0 &&
                        (p.out_sN & 7) == 0 && (reinterpret_cast<unsigned long long>(p.out16) & 15ull) == 0;
     uint32_t it = 0;
-    for (int round = 0; round * (int)gridDim.x < p.total_units; ++round) {
-      const int u = unit_of_round(round, p.total_units);
+    for (int round = 0; round * G < p.total_units; ++round) {
+      const int u = unit_of_round(round, p.total_units, G, cta);
       if (u < 0) continue;
       const int group = p.group_order[u / p.total_tiles];
       const uint32_t as = p.acc_stages == 2 ? (it & 1) : 0;
@@ -275,12 +312,30 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
       const int n = r / p.OH;
       const int w = wt * kTileM + row;
       const bool w_ok = w < p.OW;
+      const long long row_off = (long long)n * p.out_sN + (long long)h * p.out_sH + w;
+      float* out_row = (prob ? p.out1 : p.out) + row_off;
+      __half* out16_row = p.out16 + row_off;
+      const int epi_mode = GLUE ? p.epi_mode[prob] : 0;
+      const float* add_row = GLUE && p.addend[prob] ? p.addend[prob] + row_off : nullptr;
+      double* stats = GLUE ? p.stats[prob] : nullptr;
+      // fused glue: the tensor this warp adds to (skip sum or x) is requested into L1 one 16-channel piece ahead --
+      // the first piece while the unit's MMAs are still running -- so the epilogue's loads do not pay an L2 round
+      // trip per piece
+      auto prefetch_piece = [&](int pn) {
+        if (!GLUE || !w_ok || !(epi_mode == 1 || epi_mode == 2)) return;
+        const int ppc = (p.Pc + 15) >> 4;
+        if (pn >= GC * ppc) return;
+        const int pal = pn / ppc, pc0 = (pn - pal * ppc) * 16;
+        const float* src = (epi_mode == 1 ? out_row : add_row) + (long long)(p.comp_of[group][pal] * p.Pc + pc0) * p.out_sC;
+        const int plim = p.Pc - pc0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < plim) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + (long long)j * p.out_sC));
+      };
+      prefetch_piece(eset);
       ptx::mbar_wait(&tfull_bar[as], use & 1);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
-      const long long row_off = (long long)n * p.out_sN + (long long)h * p.out_sH + w;
-      float* out_row = p.out + row_off;
-      __half* out16_row = p.out16 + row_off;
       int piece_no = 0;
       for (int al = 0; al < GC; ++al) {
         const int ch_base = p.comp_of[group][al] * p.Pc;
@@ -357,6 +412,64 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
               if (j < lim)
                 *dst = to_f16_sat(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch_base + c0 + j) : 0.f));
               dst += p.out_sC;
+            }
+          } else if (GLUE && (epi_mode != 0 || stats != nullptr)) {
+            // fused glue (conv_cl.h): running skip sum / x + residual, and the next BatchNorm's batch statistics.
+            // The epilogue warps run a dependent chain at a fraction of an instruction per cycle, so the common case
+            // (a full 16-channel piece, no bias) is straight-line code without per-channel predicates; loads first,
+            // all in flight together, then the stores (the lines were requested into L1 one piece ahead).
+            const int lim = p.Pc - c0;
+            const long long off0 = (long long)(ch_base + c0) * p.out_sC;
+            const bool loads = epi_mode == 1 || epi_mode == 2;
+            prefetch_piece(piece_no + kEpiSets);
+            float f[16];
+            if (lim >= 16 && p.bias == nullptr) {
+              if (w_ok) {
+                float* dst = out_row + off0;
+                if (loads) {
+                  const float* src = (epi_mode == 1 ? out_row : add_row) + off0;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) f[j] = src[(long long)j * p.out_sC];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(v[j]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dst[(long long)j * p.out_sC] = f[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = 0.f;
+              if (w_ok && loads) {
+                const float* src = (epi_mode == 1 ? out_row : add_row) + off0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (j < lim) f[j] = src[(long long)j * p.out_sC];
+              }
+              if (w_ok) {
+                float* dst = out_row + off0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if (j < lim) {
+                    f[j] += __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ch_base + c0 + j) : 0.f);
+                    *dst = f[j];
+                  }
+                  dst += p.out_sC;
+                }
+              }
+            }
+            if (stats != nullptr) {                 // warp-uniform: every lane takes part in the shuffles
+              float q[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) q[j] = f[j] * f[j];
+              const float s1 = warp_channel_sums(f, lane), s2 = warp_channel_sums(q, lane);
+              const int j = warp_channel_of_lane(lane);
+              if (j < lim) atomicAdd(stats + 2 * (ch_base + c0 + j) + (lane & 1), (double)((lane & 1) ? s2 : s1));
             }
           } else if (w_ok) {
             float* dst = out_row + (long long)(ch_base + c0) * p.out_sC;
@@ -506,8 +619,34 @@ static int encode_cl_map(CUtensorMap* tm, const void* data, const cl::OperandLay
   return encode_tensor_map(tm, data, 2, 4, dims, strides, box, l.BK == 64 ? 3 : (l.BK == 32 ? 2 : 1));
 }
 
+typedef void (*FpropKernel)(const CUtensorMap, const CUtensorMap, const FpropParams);
+static int fprop_kernel_for(int gc, bool glue, FpropKernel* kern) {
+  switch (gc) {
+    case 1: *kern = glue ? cl::qconv_cl_fprop_kernel<1, true> : cl::qconv_cl_fprop_kernel<1, false>; break;
+    case 2: *kern = glue ? cl::qconv_cl_fprop_kernel<2, true> : cl::qconv_cl_fprop_kernel<2, false>; break;
+    case 4: *kern = glue ? cl::qconv_cl_fprop_kernel<4, true> : cl::qconv_cl_fprop_kernel<4, false>; break;
+    case 8: *kern = glue ? cl::qconv_cl_fprop_kernel<8, true> : cl::qconv_cl_fprop_kernel<8, false>; break;
+    default: return fail(SELDQ_ERR_UNSUPPORTED, "unexpected out-component group size %d", gc);
+  }
+  return SELDQ_OK;
+}
+static bool wants_glue(const FpropParams& p) {
+  return p.epi_mode[0] != 0 || p.epi_mode[1] != 0 || p.stats[0] != nullptr || p.stats[1] != nullptr;
+}
+
+static int set_fprop_epilogue(FpropParams& p, int prob, const cl::FpropEpilogue* e, const float* out) {
+  if (!e) return SELDQ_OK;
+  if (e->mode < 0 || e->mode > 3) return fail(SELDQ_ERR_INVALID, "convolution epilogue mode %d", e->mode);
+  if (e->mode == 2 && !e->addend) return fail(SELDQ_ERR_INVALID, "convolution epilogue mode 2 needs the addend tensor");
+  if (e->mode == 2 && e->addend == out) return fail(SELDQ_ERR_INVALID, "the addend of a convolution epilogue may not alias its output");
+  p.epi_mode[prob] = e->mode;
+  p.addend[prob] = e->mode == 2 ? e->addend : nullptr;
+  p.stats[prob] = e->stats;
+  return SELDQ_OK;
+}
+
 int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
-                    const float* bias, float* out, void* out_f16, cudaStream_t st) {
+                    const float* bias, float* out, void* out_f16, cudaStream_t st, const cl::FpropEpilogue* epi) {
   FpropParams p;
   size_t smem = 0;
   int rc = plan_cl_fprop(g, &p, &smem);
@@ -523,23 +662,58 @@ int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* ho
   p.out = out;
   p.out16 = reinterpret_cast<__half*>(out_f16);
   p.out_sN = g.out_sN; p.out_sC = g.out_sC; p.out_sH = g.out_sH;
+  if (epi && (epi->mode != 0 || epi->stats) && out_f16)
+    return fail(SELDQ_ERR_UNSUPPORTED, "fused convolution epilogues exist for the fp32 output only");
+  if ((rc = set_fprop_epilogue(p, 0, epi, out))) return rc;
   const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, p.dense != 0);
   alignas(64) CUtensorMap tm;
   rc = encode_cl_map(&tm, in_cl, l, g.IW, g.IH, g.N, p.box_rows);
   if (rc) return rc;
   const int grid = p.total_units < cl::num_sms() ? p.total_units : cl::num_sms();
-  void (*kern)(const CUtensorMap, const FpropParams) = nullptr;
-  switch (p.gc) {
-    case 1: kern = cl::qconv_cl_fprop_kernel<1>; break;
-    case 2: kern = cl::qconv_cl_fprop_kernel<2>; break;
-    case 4: kern = cl::qconv_cl_fprop_kernel<4>; break;
-    case 8: kern = cl::qconv_cl_fprop_kernel<8>; break;
-    default: return fail(SELDQ_ERR_UNSUPPORTED, "unexpected out-component group size %d", p.gc);
-  }
+  FpropKernel kern = nullptr;
+  if ((rc = fprop_kernel_for(p.gc, wants_glue(p), &kern))) return rc;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "fprop smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
-  const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(cl::kFpropThreads), smem, st, tm, p);
+  const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(cl::kFpropThreads), smem, st, tm, tm, p);
   if (le != cudaSuccess) return fail(SELDQ_ERR_CUDA, "qconv_cl_fprop_kernel: %s", cudaGetErrorString(le));
+  return check_launch("qconv_cl_fprop_kernel");
+}
+
+int plan_cl_fprop_pair(const ConvGeom& g, FpropParams* p, size_t* smem_bytes) {
+  return cl::plan_fprop(g, p, smem_bytes, cl::num_sms(), 2);
+}
+
+int launch_cl_fprop_pair(const ConvGeom& g, const void* const in_cl[2], const void* const packed[2], float* const out[2],
+                         const cl::FpropEpilogue epi[2], cudaStream_t st) {
+  FpropParams p;
+  size_t smem = 0;
+  int rc = plan_cl_fprop_pair(g, &p, &smem);
+  if (rc) return rc;
+  if (p.dense) return fail(SELDQ_ERR_UNSUPPORTED, "sibling launches serve layers with >= 8 channels per component");
+  for (int k = 0; k < 2; ++k) {
+    if (!in_cl[k] || !packed[k] || !out[k]) return fail(SELDQ_ERR_INVALID, "sibling convolution launch: null pointer");
+    if (reinterpret_cast<uintptr_t>(packed[k]) & 15) return fail(SELDQ_ERR_INVALID, "packed weights must be 16-byte aligned");
+  }
+  if (out[0] == out[1]) return fail(SELDQ_ERR_INVALID, "sibling convolutions need distinct outputs");
+  p.packed = reinterpret_cast<const uint8_t*>(packed[0]);
+  p.packed1 = reinterpret_cast<const uint8_t*>(packed[1]);
+  p.out = out[0];
+  p.out1 = out[1];
+  p.out_sN = g.out_sN; p.out_sC = g.out_sC; p.out_sH = g.out_sH;
+  for (int k = 0; k < 2; ++k)
+    if ((rc = set_fprop_epilogue(p, k, epi ? &epi[k] : nullptr, out[k]))) return rc;
+  const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, false);
+  alignas(64) CUtensorMap tm[2];
+  for (int k = 0; k < 2; ++k)
+    if ((rc = encode_cl_map(&tm[k], in_cl[k], l, g.IW, g.IH, g.N, p.box_rows))) return rc;
+  const int per = cl::num_sms() / 2;
+  const int grid = 2 * (p.total_units < per ? p.total_units : per);
+  FpropKernel kern = nullptr;
+  if ((rc = fprop_kernel_for(p.gc, wants_glue(p), &kern))) return rc;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "fprop smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+  const cudaError_t le = launch_pdl(kern, dim3(grid), dim3(cl::kFpropThreads), smem, st, tm[0], tm[1], p);
+  if (le != cudaSuccess) return fail(SELDQ_ERR_CUDA, "qconv_cl_fprop_kernel (pair): %s", cudaGetErrorString(le));
   return check_launch("qconv_cl_fprop_kernel");
 }
 

@@ -123,7 +123,28 @@ struct FpropParams {
   //   y = the complete instruction descriptor (carries the block's sign in its negate-B bit)
   // `first` marks the first MMA of a unit into that out component's accumulator columns (tap 0 only)
   uint32_t tap_stride16;        // J * slab_bytes >> 4
+  // Sibling launch (nprob = 2): two convolutions of EQUAL geometry -- conv1_filter / conv1_gate or conv2_skip /
+  // conv2_residual of a residual block (model.py:118-119, :130-131), forward or dgrad -- share one launch: even
+  // CTAs run problem 0, odd CTAs problem 1, each with its own weight tiles, input map and output.  (At batch 1 a
+  // launch is bound by its fixed costs, not by its ~2 us of MMAs: one launch for two layers halves them.)
+  int nprob;
+  const uint8_t* packed1;       // problem 1's weight tiles
+  float* out1;                  // problem 1's fp32 output
+  // Fused glue of the fp32 output path, per problem (model.py:114-132):
+  //   epi_mode 0: out = v    1: out += v (running sum of the skip outputs)    2: out = addend + v (x + residual)
+  //   stats != null: per-channel (sum, sum of squares) of the STORED values are added there (double[2 C], zeroed by
+  //   the caller): the BatchNorm batch statistics of the layer that follows, so no separate pass reads the output
+  int epi_mode[2];
+  const float* addend[2];
+  double* stats[2];
   uint2 op_tbl[kOpTableEntries];
+};
+
+// the fused-glue options of one problem as the host passes them (seldq_conv_epilogue_t of include/seldq.h)
+struct FpropEpilogue {
+  int mode = 0;
+  const float* addend = nullptr;
+  double* stats = nullptr;
 };
 
 // wgrad: D[(a,o), (b,i)] per tap = sum_t GY[(a,o), t] * X[t + off(tap), (b,i)]
@@ -164,7 +185,12 @@ size_t pack_table_entry_bytes();
 int fill_pack_table_entry(const ConvGeom& pass_geom, const float* const* host_w, void* packed, void* entry, int* items);
 int launch_pack_weights_multi(const void* dev_table, int count, int max_items, cudaStream_t st);
 int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* host_w, const void* packed,
-                    const float* bias, float* out, void* out_f16, cudaStream_t st);
+                    const float* bias, float* out, void* out_f16, cudaStream_t st,
+                    const cl::FpropEpilogue* epi = nullptr);
+// two sibling convolutions of equal geometry in one launch (FpropParams::nprob)
+int plan_cl_fprop_pair(const ConvGeom& g, cl::FpropParams* p, size_t* smem_bytes);
+int launch_cl_fprop_pair(const ConvGeom& g, const void* const in_cl[2], const void* const packed[2], float* const out[2],
+                         const cl::FpropEpilogue epi[2], cudaStream_t st);
 int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, float* const* host_gw,
                     cudaStream_t st, const void* gy2_nchw16 = nullptr, float* const* host_gw2 = nullptr);
 // fp32 NCHW -> CL operand (and, optionally, the pitched NCHW bf16 copy wgrad reads gy from)

@@ -11,6 +11,15 @@
 namespace seldq {
 namespace cl {
 
+// Unit schedule of a CTA (shared by the kernel and its CPU model): units are ordered heaviest group first; round r
+// hands unit r*G + b to CTA b in even rounds and r*G + (G-1-b) in odd rounds (snake order), so the few units of a
+// last, partial round go to the CTAs that hold the lightest units of the round before instead of the heaviest.
+// G = CTAs that share the problem, b = this CTA's index among them.  Returns -1 when the CTA sits a round out.
+SELDQ_HD int unit_of_round(int round, int total_units, int G, int b) {
+  const int u = round * G + ((round & 1) ? G - 1 - b : b);
+  return u < total_units ? u : -1;
+}
+
 // compact fp32 weights -> bf16 UMMA B tiles [img][tap][j][NBp x 16] (K-major, no swizzle; see the dense
 // prologue above for the byte layout).  Row n / column k of tile (img, tap, j):
 //   forward : W_img[o = n][i = 16 j + k][tap]        dgrad : W_img[o = 16 j + k][i = n][tap]
@@ -138,8 +147,11 @@ inline void fill_pack_params(const ConvGeom& g, const WeightPlan& w, PackParams*
   p->pair_xor = w.fuse ? w.pair_xor : 0; p->NB8 = w.NB8;
 }
 
-inline int plan_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes, int n_sms) {
+// nprob = 2 plans a sibling launch (conv_cl.h): each problem has n_sms / 2 CTAs to itself
+inline int plan_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes, int n_sms, int nprob = 1) {
   memset(p, 0, sizeof(*p));
+  p->nprob = nprob;
+  if (nprob == 2) n_sms /= 2;
   if (g.sh != 1 || g.sw != 1)
     return fail(SELDQ_ERR_UNSUPPORTED, "bf16 tensor-core path implements stride 1 only (got %dx%d)", g.sh, g.sw);
   const int ntaps = g.KH * g.KW;
@@ -204,7 +216,10 @@ inline int plan_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes, int
   while (ngroups < max_groups && tiles * ngroups * 2 <= n_sms + n_sms / 16) ngroups *= 2;
   // SELDQ_ACC_DOUBLE=1: split once more if that lets the accumulators double-buffer (the epilogue of a unit then
   // overlaps the MMAs of the next; costs re-loading the shared channel chunks per group)
-  if (getenv("SELDQ_ACC_DOUBLE") && atoi(getenv("SELDQ_ACC_DOUBLE")) != 0 && ngroups < max_groups &&
+  // sibling launches take that split by default: their CTAs run two or more units each, so an exposed epilogue
+  // would be paid per unit
+  if (((getenv("SELDQ_ACC_DOUBLE") && atoi(getenv("SELDQ_ACC_DOUBLE")) != 0) ||
+       (nprob == 2 && !(getenv("SELDQ_ACC_DOUBLE") && atoi(getenv("SELDQ_ACC_DOUBLE")) == 0))) && ngroups < max_groups &&
       p->ncomp_out / ngroups * cols_per_comp * 2 > 512 && p->ncomp_out / (ngroups * 2) * cols_per_comp * 2 <= 512 &&
       tiles * ngroups >= n_sms)
     ngroups *= 2;

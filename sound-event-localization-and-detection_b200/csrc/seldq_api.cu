@@ -277,6 +277,53 @@ extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, con
   return launch_cl_fprop(g, gy_cl, host_w, packed_w, nullptr, gx, nullptr, st);
 }
 
+static cl::FpropEpilogue to_epilogue(const seldq_conv_epilogue_t* e) {
+  cl::FpropEpilogue o;
+  if (e) { o.mode = e->mode; o.addend = e->addend; o.stats = e->stats; }
+  return o;
+}
+
+static int pair_geom(const seldq_conv_desc_t* d, int32_t pass, ConvGeom* g) {
+  if (!d) return fail(SELDQ_ERR_INVALID, "null descriptor");
+  if (pass != SELDQ_PASS_FWD && pass != SELDQ_PASS_DGRAD) return fail(SELDQ_ERR_INVALID, "pass must be FWD or DGRAD");
+  if (d->precision != SELDQ_PREC_BF16) return fail(SELDQ_ERR_UNSUPPORTED, "pre-staged convolution entry points exist on the SELDQ_PREC_BF16 path only");
+  return make_conv_geom(d, pass, g);
+}
+
+extern "C" int seldq_conv_epi(const seldq_conv_desc_t* d, int32_t pass, const void* in_cl, const void* packed_w,
+                              float* out, const seldq_conv_epilogue_t* epi, void* stream) {
+  ConvGeom g;
+  int rc = pair_geom(d, pass, &g);
+  if (rc) return rc;
+  if (!in_cl || !packed_w || !out) return fail(SELDQ_ERR_INVALID, "seldq_conv_epi: null pointer");
+  if (cl::is_dense(g)) return fail(SELDQ_ERR_UNSUPPORTED, "seldq_conv_epi serves layers with >= 8 channels per component");
+  if ((rc = cuda_ready())) return rc;
+  const cl::FpropEpilogue e = to_epilogue(epi);
+  return launch_cl_fprop(g, in_cl, nullptr, packed_w, nullptr, out, nullptr, (cudaStream_t)stream, &e);
+}
+
+extern "C" int seldq_conv_pair_supported(const seldq_conv_desc_t* d, int32_t pass) {
+  ConvGeom g;
+  if (pair_geom(d, pass, &g) || cl::is_dense(g)) return 0;
+  cl::FpropParams p;
+  size_t smem = 0;
+  return plan_cl_fprop_pair(g, &p, &smem) == SELDQ_OK ? 1 : 0;
+}
+
+extern "C" int seldq_conv_pair(const seldq_conv_desc_t* d, int32_t pass, const void* in_cl_a, const void* in_cl_b,
+                               const void* packed_a, const void* packed_b, float* out_a, float* out_b,
+                               const seldq_conv_epilogue_t* epi_a, const seldq_conv_epilogue_t* epi_b, void* stream) {
+  ConvGeom g;
+  int rc = pair_geom(d, pass, &g);
+  if (rc) return rc;
+  if ((rc = cuda_ready())) return rc;
+  const void* in[2] = {in_cl_a, in_cl_b};
+  const void* pk[2] = {packed_a, packed_b};
+  float* out[2] = {out_a, out_b};
+  const cl::FpropEpilogue e[2] = {to_epilogue(epi_a), to_epilogue(epi_b)};
+  return launch_cl_fprop_pair(g, in, pk, out, e, (cudaStream_t)stream);
+}
+
 extern "C" int seldq_conv_wgrad(const seldq_conv_desc_t* d, const float* x, const void* x_cl, const float* gy,
                                 const void* gy_t16, float* const* host_gw, float* gbias, int32_t accumulate,
                                 void* workspace, size_t workspace_bytes, void* stream) {

@@ -29,6 +29,12 @@ ENABLED = os.environ.get("SELDQ_FUSED", "1") != "0"      # SELDQ_FUSED=0: always
 FIRST_FUSED = os.environ.get("SELDQ_FIRST_FUSED", "1") != "0"
 # SELDQ_SIDE_WGRAD=0: the TCN weight gradients stay on the main stream
 SIDE_WGRAD = os.environ.get("SELDQ_SIDE_WGRAD", "1") != "0"
+# SELDQ_TCN_PAIR=0: one launch per convolution of a residual block and stand-alone statistics / residual kernels
+# (the round-1 schedule); default: sibling convolutions share a launch and the glue rides in their epilogues
+TCN_PAIR = os.environ.get("SELDQ_TCN_PAIR", "1") != "0"
+# SELDQ_TCN_EPI=1: the statistics / residual / skip-sum glue rides in the sibling launches' epilogues instead of
+# stand-alone kernels (seldq_conv_epilogue_t)
+TCN_EPI = os.environ.get("SELDQ_TCN_EPI", "0") != "0"
 _SIDE = {}
 
 
@@ -290,6 +296,29 @@ def _glue(op, layout_of, which, N, C, T, c2=0, eps=1e-5, momentum=0.1, drop_p=0.
         op, ctypes.byref(a), None if layout_of is None else ctypes.byref(layout_of), which, _stream())))
 
 
+def _epi(mode=0, addend=None, stats=None):
+    e = _lib.ConvEpilogue()
+    e.mode, e.addend, e.stats = mode, _ptr(addend), _ptr(stats)
+    return e
+
+
+def _conv_epi(d, pass_, in_cl, pk, out, epi, T):
+    """One convolution pass from pre-staged operands with a fused epilogue (seldq_conv_epi)."""
+    F._timed("qconv_cl_fprop_kernel", F._conv_flop(d, 1, T), 1, lambda: _lib.check(_lib.lib().seldq_conv_epi(
+        ctypes.byref(d), pass_, in_cl.data_ptr(), pk.data_ptr(), out.data_ptr(), ctypes.byref(epi), _stream())))
+
+
+def _conv_pair(d, pass_, in_a, in_b, pk_a, pk_b, out_a, out_b, epi_a, epi_b, T):
+    """Two sibling convolutions of a residual block in one launch (seldq_conv_pair)."""
+    F._timed("qconv_cl_fprop_kernel", 2 * F._conv_flop(d, 1, T), 1, lambda: _lib.check(_lib.lib().seldq_conv_pair(
+        ctypes.byref(d), pass_, in_a.data_ptr(), in_b.data_ptr(), pk_a.data_ptr(), pk_b.data_ptr(), out_a.data_ptr(),
+        out_b.data_ptr(), ctypes.byref(epi_a), ctypes.byref(epi_b), _stream())))
+
+
+def _same_geometry(a, b):
+    return bytes(a) == bytes(b)
+
+
 class _TcnStack(torch.autograd.Function):
     """All residual blocks of TC_Block in one autograd node.
        spec: per block dict(algebra, nw, k, dil, pad, drop_p, salt, has_res, bn1, bnf, bng) with bn* = (eps, momentum,
@@ -338,45 +367,67 @@ class _TcnStack(torch.autograd.Function):
                 xa_cl = torch.empty(F._operand_info(d1, 0)[2], dtype=torch.uint8, device=dev)
                 _glue(_lib.TCN_PREACT_FWD, d1, 0, N, Lc, T, eps=e1, momentum=m1, bn=((sums1, g1, b1, rm1, rv1),),
                       inp=(r,), out32=xa, out_cl=(xa_cl,))
-                # y_f, y_g
-                ys = []
-                for w in (wf, wg):
-                    y = torch.empty((N, G, T), **f32)
-                    wp = _lib.ptr_array([t.data_ptr() for t in w])
-                    pk = F.packed_weights(w, d1, PASS_FWD)
-                    F._timed("qconv_cl_fprop_kernel", F._conv_flop(d1, 1, T), 1, lambda: _lib.check(
-                        L_.seldq_conv_fwd(ctypes.byref(d1), None, xa_cl.data_ptr(), wp, _ptr(pk), None, y.data_ptr(),
-                                          None, 0, _stream())))
-                    ys.append(y)
-                yf, yg = ys
+                # y_f, y_g: one sibling launch; the batch statistics of batch_filter2 / batch_gate2 come from the
+                # convolutions' epilogues (TCN_EPI) or from one row-statistics kernel
                 sums2 = stats[offs[k] + 2 * Lc:offs[k] + 2 * Lc + 4 * G].view(2, G, 2)
-                _glue(_lib.TCN_ROW_STATS, None, 0, N, G, T, inp=(yf, yg), stats_out=(sums2[0], sums2[1]), flag=2)
+                pair1 = TCN_PAIR and bool(L_.seldq_conv_pair_supported(ctypes.byref(d1), PASS_FWD))
+                yf, yg = torch.empty((N, G, T), **f32), torch.empty((N, G, T), **f32)
+                if pair1:
+                    _conv_pair(d1, PASS_FWD, xa_cl, xa_cl, F.packed_weights(wf, d1, PASS_FWD),
+                               F.packed_weights(wg, d1, PASS_FWD), yf, yg, _epi(stats=sums2[0] if TCN_EPI else None),
+                               _epi(stats=sums2[1] if TCN_EPI else None), T)
+                else:
+                    for w, y in ((wf, yf), (wg, yg)):
+                        wp = _lib.ptr_array([t.data_ptr() for t in w])
+                        pk = F.packed_weights(w, d1, PASS_FWD)
+                        F._timed("qconv_cl_fprop_kernel", F._conv_flop(d1, 1, T), 1, lambda: _lib.check(
+                            L_.seldq_conv_fwd(ctypes.byref(d1), None, xa_cl.data_ptr(), wp, _ptr(pk), None, y.data_ptr(),
+                                              None, 0, _stream())))
+                if not (pair1 and TCN_EPI):
+                    _glue(_lib.TCN_ROW_STATS, None, 0, N, G, T, inp=(yf, yg), stats_out=(sums2[0], sums2[1]), flag=2)
                 # y = dropout1d(tanh(BN_f y_f) * sigmoid(BN_g y_g)), only as conv2's operand
                 y_cl = torch.empty(F._operand_info(dsk, 0)[2], dtype=torch.uint8, device=dev)
                 _glue(_lib.TCN_GATE_FWD, dsk, 0, N, G, T, eps=ef, momentum=mf, drop_p=s["drop_p"], salt=s["salt"],
                       bn=((sums2[0], gf, bf, rmf, rvf), (sums2[1], gg, bg, rmg, rvg)), inp=(yf, yg), out_cl=(y_cl,),
                       seed=seed)
-                outs = []
-                for w, d, on in ((wsk, dsk, True), (wr, dre, s["has_res"])):
-                    if not on:
-                        outs.append(None)
-                        continue
-                    o = torch.empty((N, d.cout, T), **f32)
-                    wp = _lib.ptr_array([t.data_ptr() for t in w])
-                    pk = F.packed_weights(w, d, PASS_FWD)
-                    F._timed("qconv_cl_fprop_kernel", F._conv_flop(d, 1, T), 1, lambda: _lib.check(
-                        L_.seldq_conv_fwd(ctypes.byref(d), None, y_cl.data_ptr(), wp, _ptr(pk), None, o.data_ptr(),
-                                          None, 0, _stream())))
-                    outs.append(o)
-                skip, res = outs
                 if skip_sum is None:
                     skip_sum = torch.empty((N, U, T), **f32)
                 r_next = sums1_next = None
                 if s["has_res"]:
                     r_next = torch.empty((N, Lc, T), **f32)
                     sums1_next = stats[offs[k + 1]:offs[k + 1] + 2 * Lc].view(Lc, 2)
-                _glue(_lib.TCN_RESIDUAL_FWD, None, 0, N, Lc, T, c2=U, inp=(xa, res, skip), out32=r_next,
-                      dsums=sums1_next, accum=skip_sum, flag=1 if k == 0 else 0)
+                pair2 = TCN_PAIR and bool(L_.seldq_conv_pair_supported(ctypes.byref(dsk), PASS_FWD))
+                if pair2 and TCN_EPI:
+                    # skips (+)= conv2_skip(y) and r' = x + conv2_residual(y) with the statistics of r' for the next
+                    # block's batch_filter1, all in the convolutions' epilogues: no stand-alone residual kernel
+                    e_skip = _epi(_lib.EPI_STORE if k == 0 else _lib.EPI_ACCUMULATE)
+                    if s["has_res"]:
+                        e_res = _epi(_lib.EPI_ADD, addend=xa, stats=sums1_next)
+                        if _same_geometry(dsk, dre):
+                            _conv_pair(dsk, PASS_FWD, y_cl, y_cl, F.packed_weights(wsk, dsk, PASS_FWD),
+                                       F.packed_weights(wr, dre, PASS_FWD), skip_sum, r_next, e_skip, e_res, T)
+                        else:
+                            _conv_epi(dsk, PASS_FWD, y_cl, F.packed_weights(wsk, dsk, PASS_FWD), skip_sum, e_skip, T)
+                            _conv_epi(dre, PASS_FWD, y_cl, F.packed_weights(wr, dre, PASS_FWD), r_next, e_res, T)
+                    else:
+                        _conv_epi(dsk, PASS_FWD, y_cl, F.packed_weights(wsk, dsk, PASS_FWD), skip_sum, e_skip, T)
+                else:
+                    skip = torch.empty((N, U, T), **f32)
+                    res = torch.empty((N, Lc, T), **f32) if s["has_res"] else None
+                    if pair2 and s["has_res"] and _same_geometry(dsk, dre):
+                        _conv_pair(dsk, PASS_FWD, y_cl, y_cl, F.packed_weights(wsk, dsk, PASS_FWD),
+                                   F.packed_weights(wr, dre, PASS_FWD), skip, res, _epi(), _epi(), T)
+                    else:
+                        for w, d, o in ((wsk, dsk, skip), (wr, dre, res)):
+                            if o is None:
+                                continue
+                            wp = _lib.ptr_array([t.data_ptr() for t in w])
+                            pk = F.packed_weights(w, d, PASS_FWD)
+                            F._timed("qconv_cl_fprop_kernel", F._conv_flop(d, 1, T), 1, lambda: _lib.check(
+                                L_.seldq_conv_fwd(ctypes.byref(d), None, y_cl.data_ptr(), wp, _ptr(pk), None, o.data_ptr(),
+                                                  None, 0, _stream())))
+                    _glue(_lib.TCN_RESIDUAL_FWD, None, 0, N, Lc, T, c2=U, inp=(xa, res, skip), out32=r_next,
+                          dsums=sums1_next, accum=skip_sum, flag=1 if k == 0 else 0)
                 saved += [r, xa, xa_cl, yf, yg, y_cl, sums1, sums2]
                 metas.append((s, d1, dsk, dre, G, U))
                 r, sums1 = r_next, sums1_next
@@ -459,10 +510,17 @@ class _TcnStack(torch.autograd.Function):
                 if gs_cl is None:
                     gs_cl, gs_t16 = F.stage_operand(gs, dsk, 1, want_cl=True, want_t16=True)
                 # conv2: gradient w.r.t. y and the weights
-                gy1 = dgrad(dsk, wsk, gs_cl)
                 gy2, gw_r = None, [None] * len(wr)
+                if (TCN_PAIR and s["has_res"] and _same_geometry(dsk, dre)
+                        and L_.seldq_conv_pair_supported(ctypes.byref(dsk), PASS_DGRAD)):
+                    gy1, gy2 = torch.empty((N, dsk.cin, T), **f32), torch.empty((N, dsk.cin, T), **f32)
+                    _conv_pair(dsk, PASS_DGRAD, gs_cl, g_rn_cl, F.packed_weights(wsk, dsk, PASS_DGRAD),
+                               F.packed_weights(wr, dre, PASS_DGRAD), gy1, gy2, _epi(), _epi(), T)
+                else:
+                    gy1 = dgrad(dsk, wsk, gs_cl)
+                    if s["has_res"]:
+                        gy2 = dgrad(dre, wr, g_rn_cl)
                 if s["has_res"]:
-                    gy2 = dgrad(dre, wr, g_rn_cl)
                     if dsk.cout == dre.cout:               # same geometry: both weight gradients in one launch
                         gw_sk, gw_r = wgrad_pair(dsk, wsk, wr, y_cl, gs_t16, g_rn_t16)
                     else:
@@ -481,8 +539,13 @@ class _TcnStack(torch.autograd.Function):
                 _glue(_lib.TCN_GATE_BWD_APPLY, d1, 1, N, G, T, eps=ef, drop_p=s["drop_p"], salt=s["salt"], bn=bn2,
                       inp=(yf, yg, gy1, gy2), dsums=dsg, out_cl=(df_cl, dg_cl), out_t16=(df_t16, dg_t16), seed=ctx.seed)
                 # conv1
-                gx1 = dgrad(d1, wf, df_cl)
-                gx2 = dgrad(d1, wg, dg_cl)
+                if TCN_PAIR and L_.seldq_conv_pair_supported(ctypes.byref(d1), PASS_DGRAD):
+                    gx1, gx2 = torch.empty((N, d1.cin, T), **f32), torch.empty((N, d1.cin, T), **f32)
+                    _conv_pair(d1, PASS_DGRAD, df_cl, dg_cl, F.packed_weights(wf, d1, PASS_DGRAD),
+                               F.packed_weights(wg, d1, PASS_DGRAD), gx1, gx2, _epi(), _epi(), T)
+                else:
+                    gx1 = dgrad(d1, wf, df_cl)
+                    gx2 = dgrad(d1, wg, dg_cl)
                 gw_f, gw_g = wgrad_pair(d1, wf, wg, xa_cl, df_t16, dg_t16)
                 # pre-activation
                 bn1 = ((sums1, g1, b1, None, None),)

@@ -20,12 +20,27 @@ using namespace seldq;
 // bit, accumulate flag honoured), accumulator column sets, epilogue combination.  No rounding to bf16: the result
 // must match the expanded-weight convolution to float accuracy, so any table or offset error shows as O(1).
 static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* const* w, float* out, int n_sms,
-                        int* info) {
+                        int* info, int nprob = 1) {
   cl::FpropParams* pp = new cl::FpropParams;
   cl::FpropParams& p = *pp;
   size_t smem = 0;
-  int rc = cl::plan_fprop(g, &p, &smem, n_sms);
+  int rc = cl::plan_fprop(g, &p, &smem, n_sms, nprob);
   if (rc) { delete pp; return rc; }
+  {
+    // the kernel's schedule: grid = nprob * min(units, n_sms / nprob) CTAs, CTA x serves problem x % nprob as
+    // number x / nprob of its G CTAs; every unit of every problem must be visited exactly once
+    const int per = n_sms / nprob, G = p.total_units < per ? p.total_units : per;
+    std::vector<int> seen((size_t)nprob * p.total_units, 0);
+    for (int x = 0; x < nprob * G; ++x) {
+      const int prob = nprob == 2 ? (x & 1) : 0, cta = nprob == 2 ? (x >> 1) : x;
+      for (int round = 0; round * G < p.total_units; ++round) {
+        const int u = cl::unit_of_round(round, p.total_units, G, cta);
+        if (u >= 0) ++seen[(size_t)prob * p.total_units + u];
+      }
+    }
+    for (size_t i = 0; i < seen.size(); ++i)
+      if (seen[i] != 1) { delete pp; return fail(SELDQ_ERR_INVALID, "schedule: unit %zu visited %d times", i, seen[i]); }
+  }
   if (info) { info[0] = p.fuse; info[1] = p.pair_xor; info[2] = p.gc; info[3] = p.ngroups; info[4] = p.rs; info[5] = p.tps;
               info[6] = p.acc_cols; info[7] = p.acc_stages; info[8] = p.nstages; info[9] = (int)smem; }
   const cl::WeightPlan wp = cl::weight_plan(g);
@@ -266,6 +281,15 @@ int emul_cl_conv(const seldq_conv_desc_t* d, int pass, const float* in, const fl
   int rc = make_conv_geom(d, pass, &g);
   if (rc) return rc;
   return run_cl_fprop(g, in, w, out, n_sms, info);
+}
+// the plan of a SIBLING launch (two problems, n_sms / 2 CTAs each; conv_cl.h) run for one of its problems: the data
+// flow per problem is the single launch's, the plan (groups, accumulator buffering) and the CTA schedule differ
+int emul_cl_conv_pair(const seldq_conv_desc_t* d, int pass, const float* in, const float* const* w, float* out,
+                      int n_sms, int* info) {
+  ConvGeom g;
+  int rc = make_conv_geom(d, pass, &g);
+  if (rc) return rc;
+  return run_cl_fprop(g, in, w, out, n_sms, info, 2);
 }
 // compact weight gradients (accumulated into gw, which the caller zeroes) through the emulated weight-gradient kernel;
 // info (8 ints, may be NULL): o_tiles, tap_groups, taps_per_group, splits, nstages, smem bytes, tmem_cols, Cp

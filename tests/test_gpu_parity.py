@@ -15,7 +15,7 @@ NW = {"Q": 4, "DQ": 8}
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
 # fixtures whose channel counts suit the tensor-core path (multiple of 8 per component, or a small dense layer)
 BF16_CONV = ["conv1d_q_k3_d5", "conv1d_dq_k3_d5", "conv1d_dq_c48_d3", "conv1d_q_c32_d2", "conv2d_dq_c24",
-             "conv2d_q_c16", "conv2d_dq_first", "conv2d_q_3x3", "conv2d_dq_3x3"]
+             "conv2d_q_c16", "conv2d_dq_first", "conv2d_dq_first16", "conv2d_q_3x3", "conv2d_dq_3x3"]
 
 
 def cuda(a):
@@ -181,7 +181,10 @@ def _run_model(seldq, name, prec, model_cls=None):
     return meta, d, sed.detach().cpu().numpy(), doa.detach().cpu().numpy(), loss.item(), grads
 
 
-@pytest.mark.parametrize("name", ["model_dq_tiny", "model_q_tiny", "model_dq_2branch_tiny", "model_dq_mid"])
+MODEL_FIXTURES = ["model_dq_tiny", "model_q_tiny", "model_dq_2branch_tiny", "model_dq_mid", "model_dq_16ch_mid", "model_r_mid"]
+
+
+@pytest.mark.parametrize("name", MODEL_FIXTURES)
 def test_model_fp32_matches_reference_fixture(seldq, name):
     """Whole model through the fp32 kernels.  Forward: rel 1e-4 against the float64 reference.
     Gradients: this network's gradients are ill-conditioned -- the reference's OWN float32 run
@@ -191,23 +194,33 @@ def test_model_fp32_matches_reference_fixture(seldq, name):
     assert A.rel_err(sed, d["sed"]) < 1e-4
     assert A.rel_err(doa, d["doa"]) < 1e-4
     assert abs(loss - float(d["loss"])) < 1e-4 * max(1.0, abs(float(d["loss"])))
+    # the real-valued model (config SERVER_SELD-TCN-S1-PHI_8ch.txt) runs nn.Conv* layers, i.e. the library's fp32
+    # convolution kernels, none of this repository's: their own accumulation-order error sets the floor there
+    floor = 2e-3 if meta["cfg"]["domain"] == "R" else 5e-4
     bad = {}
     for k, g in grads.items():
-        e, tol = A.rel_err(g, d["grad/" + k]), max(5e-4, 4.0 * float(d["ref32err/" + k]))
+        e, tol = A.rel_err(g, d["grad/" + k]), max(floor, 4.0 * float(d["ref32err/" + k]))
         if not e < tol:
             bad[k] = (e, tol)
     assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
 
 
+# fixtures whose CNN is wide enough for the fused CNN-block kernels (>= 8 channels per component behind block 0):
+# their fused run stores the 2-d conv outputs in fp16, which the bf16emu16* emulation keys model
+_FUSED_CNN = ("model_dq_mid", "model_dq_16ch_mid")
+
+
 @pytest.mark.parametrize("fused", [False, True])
-@pytest.mark.parametrize("name", ["model_dq_tiny", "model_dq_mid"])
+@pytest.mark.parametrize("name", MODEL_FIXTURES)
 def test_model_bf16_matches_reference_fixture(seldq, name, fused):
     """Whole model through the tcgen05 bf16 kernels.  Forward: rel 2e-2 against the float64
     reference (north_star tolerance).  Gradients: bf16 operand rounding (2.7e-3 per convolution)
     is amplified to tens of percent on some tensors by this network's conditioning, for ANY bf16
     implementation; the fixture therefore carries the result of an ideal bf16-operand
     implementation (oracle/bf16_emulation.py): its own distance to the float64 reference is the
-    inherent bf16 noise of each tensor, and the GPU may be at most twice as far (floor 2e-2).  The
+    inherent bf16 noise of each tensor, and the GPU may be at most twice as far (floor 2e-2) in the relative L2
+    norm of the tensor's error, three times in its largest entry (the maximum over a tensor of one noise sample
+    against the maximum of another: the emulation and the GPU round different intermediate values).  The
     outputs must match the emulation itself to 1e-2 (the emulation runs everything between the
     convolutions in float64, the GPU in float32 with a timing-dependent accumulation order in the
     tensor path, so a few activations round to the other bf16 neighbour; observed 3e-3 .. 5.2e-3
@@ -222,17 +235,19 @@ def test_model_bf16_matches_reference_fixture(seldq, name, fused):
         meta, d, sed, doa, loss, grads = _run_model(seldq, name, "bf16")
     finally:
         seldq.fused.ENABLED = prev
-    emu = "bf16emu16" if (fused and name == "model_dq_mid") else "bf16emu"
+    emu = "bf16emu16" if (fused and name in _FUSED_CNN) else "bf16emu"
     assert A.rel_err(sed, d["sed"]) < 2e-2
     assert A.rel_err(doa, d["doa"]) < 2e-2
     assert A.rel_err(sed, d[emu + "/sed"]) < 1e-2
     assert A.rel_err(doa, d[emu + "/doa"]) < 1e-2
     bad = {}
     for k, g in grads.items():
-        noise = A.rel_err(d[emu + "_grad/" + k], d["grad/" + k])
-        e, tol = A.rel_err(g, d["grad/" + k]), max(2e-2, 2.0 * noise)
-        if not e < tol:
-            bad[k] = (e, tol)
+        ref, em = d["grad/" + k].astype(np.float64), d[emu + "_grad/" + k].astype(np.float64)
+        nrm = max(float(np.linalg.norm(ref)), 1e-300)
+        e2, n2 = float(np.linalg.norm(g - ref)) / nrm, float(np.linalg.norm(em - ref)) / nrm
+        e, noise = A.rel_err(g, ref), A.rel_err(em, ref)
+        if not (e2 < max(2e-2, 2.0 * n2) and e < max(2e-2, 3.0 * noise)):
+            bad[k] = (e2, n2, e, noise)
     assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
 
 
@@ -494,7 +509,7 @@ def test_full_size_training_step_fused_vs_layerwise(seldq):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("name", ["model_dq_tiny", "model_q_tiny", "model_dq_2branch_tiny", "model_dq_mid"])
+@pytest.mark.parametrize("name", MODEL_FIXTURES)
 def test_model_seld_metrics_match_reference(seldq, name, prec):
     """"Dcase21 SELD metrics identical on fixed seeds" (BASELINE.json north_star).  The fixture holds the scores the
     REFERENCE's own code (gen_submission_list_task2 -> segment_labels -> SELDMetrics, train.py:84-130) gave for the
@@ -509,6 +524,8 @@ def test_model_seld_metrics_match_reference(seldq, name, prec):
     identical and LE within 2e-2."""
     from oracle import seld_metrics as M
     meta, d, sed, doa, loss, grads = _run_model(seldq, name, prec)
+    # the outputs the metrics are computed from are themselves inside the north_star tolerance
+    assert A.rel_err(sed, d["sed"]) < TOL[prec] and A.rel_err(doa, d["doa"]) < TOL[prec]
     ref_scores = tuple(float(v) for v in d["seld_scores"])
     frames = sed.shape[1]
     got = M.seld_scores(sed, doa, d["target"], num_frames=frames)
@@ -522,3 +539,54 @@ def test_model_seld_metrics_match_reference(seldq, name, prec):
     if not flips.any():
         assert got[0] == ref_scores[0] and got[1] == ref_scores[1] and got[3] == ref_scores[3], (got, ref_scores)
         assert abs(got[2] - ref_scores[2]) <= (1e-4 if prec == "fp32" else 2e-2) * max(1.0, abs(ref_scores[2])), (got, ref_scores)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_full_size_model_matches_reference_fixture(seldq, prec):
+    """BASELINE.json configs[1] at its real size -- DQSELD-TCN-S1-PHI_8ch, one 60 s clip, T = 4800, batch 1, dropout
+    off -- against the REFERENCE: tests/golden/model_dq_8ch_full.npz holds what the unmodified model.SELD_Model gave
+    in float64 on CPU (oracle/make_golden.py --full-size): sed, doa, loss and, per parameter, the gradient's L2 norm
+    and a fixed 4096-element sample.  Input, target and initial weights regenerate from the seeds and are pinned by
+    the fixture's check sums.  fp32 mode: outputs 1e-4; gradient samples within max(5e-4, 4 x the reference's own
+    float32 error on that tensor).  bf16 mode (the fused path of the bench): outputs 2e-2; gradient samples within
+    max(2e-2, 2 x the error of the ideal bf16-operand emulation on that tensor); gradient norms within the same."""
+    from oracle import make_golden as MG
+    meta, d = load_golden("model_dq_8ch_full")
+    cfg = dict(meta["cfg"])
+    np.random.seed(meta["seed"])
+    torch.manual_seed(meta["seed"])
+    m = seldq.SELD_Model(time_dim=meta["time_dim"], spatial_dropout_rate=0, dropout_perc=0, **cfg)
+    for k, v in m.state_dict().items():
+        if v.dtype.is_floating_point:
+            assert abs(float(v.double().abs().sum()) - float(d["psum/" + k])) <= 1e-9 * max(1.0, float(d["psum/" + k])), k
+    x, target = MG.full_size_input(cfg, meta["time_dim"], meta["B"], meta["seed"])
+    assert abs(float(x.astype(np.float64).sum()) - float(d["x_sum"])) < 1e-6 * float(d["x_abs"])
+    m = m.cuda().train()
+    xt, tt = torch.from_numpy(x).cuda(), torch.from_numpy(target).cuda()
+    with seldq.precision(prec):
+        sed, doa = m(xt)
+        loss = (torch.nn.BCELoss()(torch.flatten(sed, 1), torch.flatten(tt[:, :, :42], 1))
+                + 5.0 * torch.nn.MSELoss()(torch.flatten(doa, 1), torch.flatten(tt[:, :, 42:], 1)))
+        loss.backward()
+    torch.cuda.synchronize()
+    tol = TOL[prec]
+    e_sed, e_doa = A.rel_err(sed.detach().cpu().numpy(), d["sed"]), A.rel_err(doa.detach().cpu().numpy(), d["doa"])
+    print("full size %s: sed %.2e doa %.2e loss %.6f vs %.6f" % (prec, e_sed, e_doa, loss.item(), float(d["loss"])))
+    assert e_sed < tol and e_doa < tol
+    assert abs(loss.item() - float(d["loss"])) < tol * max(1.0, abs(float(d["loss"])))
+    bad, n = {}, 0
+    for i, (k, p) in enumerate(m.named_parameters()):
+        if ("gsample/" + k) not in d:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        n += 1
+        g = p.grad.detach().double().cpu().numpy().ravel()
+        yard = float(d["ref32err/" + k]) * 4.0 if prec == "fp32" else float(d["bf16emu16_err/" + k]) * 2.0
+        gate = max(5e-4 if prec == "fp32" else 2e-2, yard)
+        gmax = float(d["gmax/" + k])
+        e_s = float(np.abs(g[MG.sample_indices(g.size, i)] - d["gsample/" + k].astype(np.float64)).max()) / max(gmax, 1e-300)
+        e_n = abs(float(np.linalg.norm(g)) - float(d["gnorm/" + k])) / max(float(d["gnorm/" + k]), 1e-300)
+        if not (e_s < gate and e_n < max(gate, 2e-2 if prec == "bf16" else 1e-3)):
+            bad[k] = (e_s, e_n, gate)
+    assert n == meta["n_grads"]
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]

@@ -236,6 +236,37 @@ def test_tensor_core_plan_matches_oracle_on_random_layers(emul, alg, cc_in, cc_o
                     assert info["rs"] == 1 and info["tps"] == 3, info
 
 
+@pytest.mark.parametrize("cc,ks,dil,shape", [(48, (3,), 5, (1, 4800)), (48, (1,), 1, (1, 4800)), (48, (3,), 55, (4, 520)),
+                                             (16, (3,), 2, (2, 200))])
+def test_tensor_core_plan_of_a_sibling_launch(emul, cc, ks, dil, shape):
+    """seldq_conv_pair (conv_cl.h `nprob`): filter / gate or skip / residual convolutions of a residual block in one
+    launch.  The plan for n_sms / 2 CTAs per problem must reproduce the convolution, visit every unit of both
+    problems exactly once (checked inside the emulation), and double-buffer its accumulators."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((shape[0], 8 * cc, shape[1])).astype(np.float32)
+    ws = [(0.3 * rng.standard_normal((cc, cc) + ks)).astype(np.float32) for _ in range(8)]
+    pad = dil * (ks[-1] - 1) // 2
+    desc = ConvDesc(ALG["DQ"], 1, 1, x.shape[0], x.shape[1], 8 * cc, 1, x.shape[-1], 1, ks[-1], 1, 1, 0, pad, 1, dil)
+    if shape[1] > 1000:       # full TCN length: the oracle is slow there, compare with the single-launch emulation
+        y_ref, _ = _cl_conv(emul, desc, 0, x, ws, x.shape)
+        gx_ref = None
+    else:
+        y_ref = A.qconv(x.astype(np.float64), [w.astype(np.float64) for w in ws], None, 1, pad, dil, "DQ")
+        gx_ref, _, _ = A.qconv_backward(x.astype(np.float64), [w.astype(np.float64) for w in ws], x.astype(np.float64), 1,
+                                        pad, dil, "DQ")
+    for pass_, ref in ((0, y_ref), (1, gx_ref)):
+        if ref is None:
+            continue
+        out = np.full(x.shape, np.nan, np.float32)
+        info = (ctypes.c_int32 * 10)()
+        rc = emul.emul_cl_conv_pair(ctypes.byref(desc), pass_, fptr(x), ptr_array(ws), fptr(out), 148, info)
+        assert rc == 0, emul.emul_last_error()
+        assert A.rel_err(out, ref) < 1e-5
+        if cc == 48 and shape == (1, 4800):
+            # batch-1 TCN layer: 38 tiles x 4 pair groups = 152 units for 74 CTAs, accumulators double-buffered
+            assert info[2] == 2 and info[3] == 4 and info[7] == 2, list(info)
+
+
 def test_tensor_core_plan_dq_linear_as_1x1_convolution(emul):
     """dual_quaternion_linear's block table (the transpose of the convolution's) through the same planner."""
     meta, d = load_golden("linear_dq_c48")
