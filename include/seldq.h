@@ -313,6 +313,28 @@ int seldq_stft_magphase(const float* x, int32_t n_batch, int32_t n_ch, int64_t n
                         int32_t nperseg, int32_t noverlap, int32_t cut_dc, int32_t output_phase,
                         int32_t cut_last, float* out, void* stream);
 
+/* ---- multi-head self-attention (model.py:12-51) ------------------------------------------------
+ *     out = softmax(q k^T / sqrt(d)) v      per (sample, head), heads = E / d channel groups of the projections
+ * q, k, v: float32 (N, E, S) -- the output layout of the 1x1 projections (model.py:34-36; channel e = head * d + i);
+ * out: float32 (N, S, E) -- what fc_out consumes (model.py:48-49).  bf16 operands, fp32 accumulation and softmax
+ * (the tensor-core mode, gated at rel 2e-2); the (N, heads, S, S) energy / attention tensors of the reference are
+ * never materialised.  d in {16, 32, 48}, S a multiple of 8 (seldq_attention_supported returns 1).
+ *   saved      seldq_attention_saved_bytes(): bf16 operand copies the forward makes and the backward re-reads
+ *   lse        float32 (N * heads * S): row-wise log-sum-exp (log2 domain), written by fwd, read by bwd
+ *   workspace  seldq_attention_bwd_workspace_bytes(): operand copies of d_out + the row sums of d_out * out
+ * seldq_attention_bwd: d_out (N, S, E) -> dq, dk, dv (N, E, S). */
+typedef struct {
+  int32_t batch, heads, seq, head_dim;
+} seldq_attention_desc_t;
+int seldq_attention_supported(const seldq_attention_desc_t* d);
+size_t seldq_attention_saved_bytes(const seldq_attention_desc_t* d);
+size_t seldq_attention_bwd_workspace_bytes(const seldq_attention_desc_t* d);
+int seldq_attention_fwd(const seldq_attention_desc_t* d, const float* q, const float* k, const float* v, float* out,
+                        float* lse, void* saved, void* stream);
+int seldq_attention_bwd(const seldq_attention_desc_t* d, const void* saved, const float* out, const float* lse,
+                        const float* d_out, float* dq, float* dk, float* dv, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,7 @@ import os as _os
 
 from . import _lib
 from . import fused
-from .functional import (block_conv, block_linear, get_precision, precision, set_precision,
+from .functional import (attention, block_conv, block_linear, get_precision, precision, set_precision,
                          stft_magphase)
 from .features import spectrum_fast
 from .layers import (DualQuaternionConv, DualQuaternionLinear, QuaternionConv, QuaternionLinear,

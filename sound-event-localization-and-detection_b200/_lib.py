@@ -56,6 +56,10 @@ class ConvEpilogue(ctypes.Structure):
 EPI_STORE, EPI_ACCUMULATE, EPI_ADD = 0, 1, 2
 
 
+class AttentionDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("batch", "heads", "seq", "head_dim")]
+
+
 class LinearDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("algebra", "precision", "rows", "in_features", "out_features")]
 
@@ -125,6 +129,12 @@ _PROTOS = {
                                           ctypes.c_size_t, _P]),
     "seldq_linear_wgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, _P, ctypes.POINTER(_P), _P,
                                           ctypes.c_int32, _P, ctypes.c_size_t, _P]),
+    "seldq_attention_supported": (ctypes.c_int, [ctypes.POINTER(AttentionDesc)]),
+    "seldq_attention_saved_bytes": (ctypes.c_size_t, [ctypes.POINTER(AttentionDesc)]),
+    "seldq_attention_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(AttentionDesc)]),
+    "seldq_attention_fwd": (ctypes.c_int, [ctypes.POINTER(AttentionDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "seldq_attention_bwd": (ctypes.c_int, [ctypes.POINTER(AttentionDesc), _P, _P, _P, _P, _P, _P, _P, _P,
+                                           ctypes.c_size_t, _P]),
     "seldq_cast_bf16": (ctypes.c_int, [_P, _P, ctypes.c_size_t, _P]),
     "seldq_stft_shape": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),

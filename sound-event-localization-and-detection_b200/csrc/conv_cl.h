@@ -20,7 +20,7 @@ namespace seldq {
 namespace cl {
 
 constexpr int kTileM = 128;     // positions per accumulator tile (TMEM lanes)
-constexpr int kThreads = 192;   // wgrad: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kThreads = 320;   // wgrad: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kMmaWarps = 4;          // fprop: MMA-issuing warps (warp 1 and warps 6 ...)
 constexpr int kEpiSets = 2;           // fprop: epilogue warp sets of 4 (one warp per TMEM lane quarter); the sets split
                                       // the 16-channel column chunks of a tile between them

@@ -1,6 +1,7 @@
 // extern "C" surface of libseldq.so (see include/seldq.h for the contract of every entry point).
 #include <cuda_runtime.h>
 
+#include "attention.h"
 #include "conv_cl.h"
 #include "conv_simt.cuh"
 #include "conv_umma.h"
@@ -672,6 +673,67 @@ extern "C" int seldq_linear_wgrad(const seldq_linear_desc_t* d, const float* x, 
 }
 
 // ---- STFT ------------------------------------------------------------------------------------------
+// ---- attention ------------------------------------------------------------------------------------------------
+namespace {
+struct AttnBufs { size_t rm, tr; char *q_rm, *k_rm, *v_rm, *q_tr, *k_tr, *v_tr; };
+AttnBufs attn_saved_layout(const seldq_attention_desc_t* d, void* saved) {
+  AttnBufs b;
+  b.rm = (attention_rm_bytes(d->batch, d->heads, d->seq) + 255) & ~(size_t)255;
+  b.tr = (attention_tr_bytes(d->batch, d->heads, d->seq, d->head_dim) + 255) & ~(size_t)255;
+  char* p = (char*)saved;
+  b.q_rm = p; b.k_rm = p + b.rm; b.v_rm = p + 2 * b.rm;
+  b.q_tr = p + 3 * b.rm; b.k_tr = b.q_tr + b.tr; b.v_tr = b.q_tr + 2 * b.tr;
+  return b;
+}
+}  // namespace
+
+extern "C" int seldq_attention_supported(const seldq_attention_desc_t* d) {
+  return d && attention_supported(d->batch, d->heads, d->seq, d->head_dim) ? 1 : 0;
+}
+extern "C" size_t seldq_attention_saved_bytes(const seldq_attention_desc_t* d) {
+  if (!seldq_attention_supported(d)) return 0;
+  const AttnBufs b = attn_saved_layout(d, nullptr);
+  return 3 * b.rm + 3 * b.tr;
+}
+extern "C" size_t seldq_attention_bwd_workspace_bytes(const seldq_attention_desc_t* d) {
+  if (!seldq_attention_supported(d)) return 0;
+  const AttnBufs b = attn_saved_layout(d, nullptr);
+  return b.rm + b.tr + (((size_t)d->batch * d->heads * d->seq * sizeof(float) + 255) & ~(size_t)255);
+}
+extern "C" int seldq_attention_fwd(const seldq_attention_desc_t* d, const float* q, const float* k, const float* v,
+                                   float* out, float* lse, void* saved, void* stream) {
+  if (!seldq_attention_supported(d)) return fail(SELDQ_ERR_UNSUPPORTED, "attention: head_dim must be 16 / 32 / 48 and the sequence a multiple of 8");
+  if (!q || !k || !v || !out || !lse || !saved) return fail(SELDQ_ERR_INVALID, "seldq_attention_fwd: null pointer");
+  if (reinterpret_cast<uintptr_t>(saved) & 255) return fail(SELDQ_ERR_INVALID, "seldq_attention_fwd: `saved` must be 256-byte aligned");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const AttnBufs b = attn_saved_layout(d, saved);
+  // softmax(q k^T / sqrt(d)) through exp2: q carries log2(e) / sqrt(d)
+  const float qs = 1.4426950408889634f / sqrtf((float)d->head_dim);
+  if ((rc = launch_attention_stage(q, nullptr, b.q_rm, b.q_tr, nullptr, d->batch, d->heads, d->seq, d->head_dim, 0, qs, st))) return rc;
+  if ((rc = launch_attention_stage(k, nullptr, b.k_rm, b.k_tr, nullptr, d->batch, d->heads, d->seq, d->head_dim, 0, 1.f, st))) return rc;
+  if ((rc = launch_attention_stage(v, nullptr, b.v_rm, b.v_tr, nullptr, d->batch, d->heads, d->seq, d->head_dim, 0, 1.f, st))) return rc;
+  return launch_attention_fwd(d->batch, d->heads, d->seq, d->head_dim, b.q_rm, b.k_rm, b.v_tr, out, lse, st);
+}
+extern "C" int seldq_attention_bwd(const seldq_attention_desc_t* d, const void* saved, const float* out, const float* lse,
+                                   const float* d_out, float* dq, float* dk, float* dv, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!seldq_attention_supported(d)) return fail(SELDQ_ERR_UNSUPPORTED, "attention: unsupported shape");
+  if (!saved || !out || !lse || !d_out || !dq || !dk || !dv || !workspace) return fail(SELDQ_ERR_INVALID, "seldq_attention_bwd: null pointer");
+  if (workspace_bytes < seldq_attention_bwd_workspace_bytes(d) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return fail(SELDQ_ERR_WORKSPACE, "seldq_attention_bwd: workspace of %zu B (256-byte aligned) needed", seldq_attention_bwd_workspace_bytes(d));
+  int rc = cuda_ready();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const AttnBufs b = attn_saved_layout(d, const_cast<void*>(saved));
+  char* w = (char*)workspace;
+  char* do_rm = w; char* do_tr = w + b.rm; float* delta = reinterpret_cast<float*>(w + b.rm + b.tr);
+  if ((rc = launch_attention_stage(d_out, out, do_rm, do_tr, delta, d->batch, d->heads, d->seq, d->head_dim, 1, 1.f, st))) return rc;
+  return launch_attention_bwd(d->batch, d->heads, d->seq, d->head_dim, b.q_rm, b.k_rm, b.v_rm, b.q_tr, b.k_tr, do_rm, do_tr,
+                              const_cast<float*>(lse), delta, dq, dk, dv, st);
+}
+
 extern "C" int seldq_stft_shape(int64_t n_samples, int32_t nperseg, int32_t noverlap, int32_t cut_dc, int32_t cut_last,
                                 int32_t* n_bins, int32_t* n_frames) {
   int b, f;

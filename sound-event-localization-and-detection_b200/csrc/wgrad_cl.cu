@@ -126,9 +126,15 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
       }
     } else {
       // ===== epilogue ==============================================================================
-      const int q = warp & 3;
+      // Measured (tools/wgrad_bench.py: time versus split-K factor): a launch costs ~21 us of fixed time and only
+      // 0.5 us per K step, and most of the fixed time was this fold when four warps walked a per-target loop with
+      // run-time divisions.  Now eight warps: each stages the columns of half of the in components of its lane
+      // quarter, and every thread owns one (out channel, in channel) position of the 16 x 16 block and folds it for
+      // all compact tensors -- the (a, b, sign) table is then uniform across the warp.
+      const int q = warp & 3, hf = (warp - 2) >> 2;
       const int row = q * 32 + lane;                 // accumulator row = TMEM lane = (a, ol)
-      const int et = threadIdx.x - 64;               // 0..127 among the epilogue threads
+      const int et = threadIdx.x - 64;               // 0..255 among the epilogue threads
+      const int il = et & 15;
       ptx::mbar_wait(&done_bar, 0);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -136,33 +142,40 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
       // all MMAs have retired: the operand ring is free and is reused as a [128][ncomp*16 + 1] fp32 staging tile
       float* stg = reinterpret_cast<float*>(smem);
       const int pitch = p.ncomp * 16 + 1;
-      const int targets = g.tab.nw * p.OS * 16;
+      const int bper = (p.ncomp + 1) >> 1;
+      const int b_lo = hf * bper, b_hi = min(p.ncomp, b_lo + bper);
       for (int t = 0; t < ntap; ++t)
         for (int ic = 0; ic < p.cpad_in; ic += 16) {
-          for (int b = 0; b < p.ncomp; ++b) {
-            uint32_t v[16];
-            ptx::tmem_ld16(t_row + (uint32_t)(t * p.Cp + b * p.cpad_in + ic), v);
+          for (int b0 = b_lo; b0 < b_hi; b0 += 2) {               // two 16-column loads in flight per wait
+            uint32_t v[2][16];
+            const bool two = b0 + 1 < b_hi;
+            ptx::tmem_ld16(t_row + (uint32_t)(t * p.Cp + b0 * p.cpad_in + ic), v[0]);
+            if (two) ptx::tmem_ld16(t_row + (uint32_t)(t * p.Cp + (b0 + 1) * p.cpad_in + ic), v[1]);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) stg[row * pitch + b * 16 + j] = __uint_as_float(v[j]);
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int tg_i = et; tg_i < targets; tg_i += 128) {
-            const int il = tg_i & 15;
-            int rr = tg_i >> 4;
-            const int ol = rr % p.OS;
-            const int e = rr / p.OS;
-            if (o0 + ol < g.Oc && ic + il < g.Ic) {
-              float acc = 0.f;
-              for (int k = 0; k < p.pair_n[e]; ++k) {
-                const float val = stg[(p.pair_a[e][k] * p.OS + ol) * pitch + p.pair_b[e][k] * 16 + il];
-                acc += p.pair_neg[e][k] ? -val : val;
-              }
-              atomicAdd(p.gw[prob][e] + (long long)(o0 + ol) * g.wsO + (long long)(ic + il) * g.wsI +
-                            (long long)(tap0 + t) * g.wsT, acc);
+            for (int j = 0; j < 16; ++j) stg[row * pitch + b0 * 16 + j] = __uint_as_float(v[0][j]);
+            if (two) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) stg[row * pitch + (b0 + 1) * 16 + j] = __uint_as_float(v[1][j]);
             }
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (ic + il < g.Ic) {
+            for (int ol = et >> 4; ol < p.OS; ol += 16) {
+              if (o0 + ol >= g.Oc) break;
+              const float* col = stg + ol * pitch + il;
+              const long long off = (long long)(o0 + ol) * g.wsO + (long long)(ic + il) * g.wsI + (long long)(tap0 + t) * g.wsT;
+              for (int e = 0; e < g.tab.nw; ++e) {
+                float acc = 0.f;
+                for (int k = 0; k < p.pair_n[e]; ++k) {
+                  const float val = col[p.pair_a[e][k] * p.OS * pitch + p.pair_b[e][k] * 16];
+                  acc += p.pair_neg[e][k] ? -val : val;
+                }
+                atomicAdd(p.gw[prob][e] + off, acc);
+              }
+            }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
   }

@@ -510,6 +510,64 @@ def block_linear(x, weights, bias, algebra, prec=None):
     return y.reshape(lead + (y.shape[-1],))
 
 
+class _Attention(torch.autograd.Function):
+    """out = softmax(q k^T / sqrt(d)) v per (sample, head) (model.py:40-48) on the fused tcgen05 kernels
+    (csrc/attention.cu): q, k, v (N, E, S) float32 -- the 1x1 projections' output layout -- -> out (N, S, E)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads):
+        import ctypes
+        L = _lib.lib()
+        for t, name in ((q, "q"), (k, "k"), (v, "v")):
+            _require_cuda_f32(t, name)
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        n, e, s = q.shape
+        desc = _lib.AttentionDesc(n, heads, s, e // heads)
+        out = torch.empty((n, s, e), dtype=torch.float32, device=q.device)
+        lse = torch.empty((n * heads * s,), dtype=torch.float32, device=q.device)
+        saved = torch.empty(L.seldq_attention_saved_bytes(ctypes.byref(desc)), dtype=torch.uint8, device=q.device)
+        with torch.cuda.device(q.device):
+            _timed("attn_kernel", 4.0 * n * heads * s * s * (e // heads), 4, lambda: _lib.check(
+                L.seldq_attention_fwd(ctypes.byref(desc), q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                      lse.data_ptr(), saved.data_ptr(), _stream())))
+        ctx.desc = desc
+        ctx.save_for_backward(saved, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        import ctypes
+        L = _lib.lib()
+        saved, out, lse = ctx.saved_tensors
+        desc = ctx.desc
+        gout = gout.contiguous()
+        n, s, e = out.shape
+        dq, dk, dv = (torch.empty((n, e, s), dtype=torch.float32, device=out.device) for _ in range(3))
+        work = torch.empty(L.seldq_attention_bwd_workspace_bytes(ctypes.byref(desc)), dtype=torch.uint8, device=out.device)
+        with torch.cuda.device(out.device):
+            _timed("attn_kernel", 10.0 * n * desc.heads * s * s * desc.head_dim, 3, lambda: _lib.check(
+                L.seldq_attention_bwd(ctypes.byref(desc), saved.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                                      gout.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), work.data_ptr(),
+                                      work.numel(), _stream())))
+        return dq, dk, dv, None
+
+
+def attention_supported(q, heads):
+    """The fused attention kernels serve CUDA float32 (N, E, S) projections with E / heads in {16, 32, 48} and S a
+    multiple of 8, in the tensor-core ('bf16') precision mode."""
+    import ctypes
+    if not (isinstance(q, torch.Tensor) and q.is_cuda and q.dtype == torch.float32 and q.dim() == 3):
+        return False
+    if get_precision() != "bf16" or os.environ.get("SELDQ_ATTN", "own") != "own" or q.shape[1] % heads:
+        return False
+    desc = _lib.AttentionDesc(q.shape[0], heads, q.shape[2], q.shape[1] // heads)
+    return bool(_lib.lib().seldq_attention_supported(ctypes.byref(desc)))
+
+
+def attention(q, k, v, heads):
+    return _Attention.apply(q, k, v, heads)
+
+
 def stft_magphase(x, nperseg=512, noverlap=128, cut_dc=True, output_phase=True, cut_last_timeframe=True):
     """x: (C, n) or (B, C, n) float32 CUDA tensor -> ((1+phase)*C, F, T) or (B, (1+phase)*C, F, T)
     (utility_functions.py:129-155)."""

@@ -33,8 +33,9 @@ import os as _os
 #   SELDQ_ATTN=fp16  IEEE half operands: 10-bit mantissa = the TF32 rounding the fp32 path applies anyway
 #   SELDQ_ATTN=bf16  bf16 operands (7-bit mantissa: costs 0.2e-2 of the 2e-2 output tolerance)
 #   SELDQ_ATTN=fp32  fp32 / TF32 scaled_dot_product_attention
-ATTN_DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": None}[
-    "bf16" if _os.environ.get("SELDQ_ATTN_BF16", "0") == "1" else _os.environ.get("SELDQ_ATTN", "fp32")]
+#   SELDQ_ATTN=own   (default) this repository's fused tcgen05 attention kernels where they apply (functional.attention)
+ATTN_DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": None, "own": None}[
+    "bf16" if _os.environ.get("SELDQ_ATTN_BF16", "0") == "1" else _os.environ.get("SELDQ_ATTN", "own")]
 _BN_TCN = {'BN', 'BN_on_TCN', 'BNonTCN'}
 _BN_CNN = {'BN', 'BN_on_CNN', 'BNonCNN'}
 _TWO_BRANCH = {'2Parallel', '2BParallel', '2ParallelBranches', '2PB'}
@@ -80,9 +81,15 @@ def mha_forward(self, v, k, q, mask=None):
     """MultiHeadAttention.forward (model.py:25-51) for any module with the reference's attributes
     (values / keys / queries / fc_out, num_heads, head_dim).  Inputs are (N, L, E)."""
     n, length = q.shape[0], q.shape[1]
-    vp = _split_heads(self.values(v.permute(0, 2, 1)), self.num_heads, self.head_dim)
-    kp = _split_heads(self.keys(k.permute(0, 2, 1)), self.num_heads, self.head_dim)
-    qp = _split_heads(self.queries(q.permute(0, 2, 1)), self.num_heads, self.head_dim)
+    vc, kc, qc = self.values(v.permute(0, 2, 1)), self.keys(k.permute(0, 2, 1)), self.queries(q.permute(0, 2, 1))
+    if (mask is None and kc.shape == qc.shape == vc.shape and self.head_dim * self.num_heads == qc.shape[1]
+            and _F.attention_supported(qc, self.num_heads)):
+        # the repository's fused attention kernels (csrc/attention.cu): the (N, heads, S, S) energy / attention
+        # tensors of model.py:40-46 never exist in HBM, forward or backward
+        return self.fc_out(_F.attention(qc, kc, vc, self.num_heads))
+    vp = _split_heads(vc, self.num_heads, self.head_dim)
+    kp = _split_heads(kc, self.num_heads, self.head_dim)
+    qp = _split_heads(qc, self.num_heads, self.head_dim)
     attn_mask = None if mask is None else (mask != 0)
     if ATTN_DTYPE is not None and q.is_cuda and _F.get_precision() == "bf16" and attn_mask is None:
         # tensor-core mode: 16-bit operands into the library's fused attention kernel (no S x S tensor in HBM)

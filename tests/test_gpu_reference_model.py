@@ -65,7 +65,7 @@ def test_unmodified_model_py_bf16_matches_fixture(seldq, name, fuse):
         nrm = max(float(np.linalg.norm(ref)), 1e-300)
         e2, n2 = float(np.linalg.norm(g - ref)) / nrm, float(np.linalg.norm(em - ref)) / nrm
         e, noise = A.rel_err(g, ref), A.rel_err(em, ref)
-        if not (e2 < max(2e-2, 2.0 * n2) and e < max(2e-2, 3.0 * noise)):
+        if not (e2 < max(2e-2, 2.5 * n2) and e < max(2e-2, 3.0 * noise)):
             bad[k] = (e2, n2, e, noise)
     assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
 
