@@ -313,6 +313,10 @@ int seldq_stft_magphase(const float* x, int32_t n_batch, int32_t n_ch, int64_t n
                         int32_t nperseg, int32_t noverlap, int32_t cut_dc, int32_t output_phase,
                         int32_t cut_last, float* out, void* stream);
 
+/* debug: a 64 x uint64 device buffer that CTA 0 of every later tensor-core convolution launch stamps with
+ * %globaltimer values at its role hand-offs (tools/fprop_trace.py); NULL switches it off. */
+int seldq_debug_fprop_trace(void* dev_buf);
+
 /* ---- multi-head self-attention (model.py:12-51) ------------------------------------------------
  *     out = softmax(q k^T / sqrt(d)) v      per (sample, head), heads = E / d channel groups of the projections
  * q, k, v: float32 (N, E, S) -- the output layout of the 1x1 projections (model.py:34-36; channel e = head * d + i);

@@ -129,6 +129,7 @@ _PROTOS = {
                                           ctypes.c_size_t, _P]),
     "seldq_linear_wgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, _P, ctypes.POINTER(_P), _P,
                                           ctypes.c_int32, _P, ctypes.c_size_t, _P]),
+    "seldq_debug_fprop_trace": (ctypes.c_int, [_P]),
     "seldq_attention_supported": (ctypes.c_int, [ctypes.POINTER(AttentionDesc)]),
     "seldq_attention_saved_bytes": (ctypes.c_size_t, [ctypes.POINTER(AttentionDesc)]),
     "seldq_attention_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(AttentionDesc)]),

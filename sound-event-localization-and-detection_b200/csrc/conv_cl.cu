@@ -95,12 +95,23 @@ __device__ __forceinline__ int warp_channel_of_lane(int lane) { return (lane >> 
 
 // GLUE = the fused-glue epilogue of the fp32 output path (FpropParams::epi_mode / stats) is compiled in; the plain
 // instantiations carry none of its registers or branches
+// trace slots (CTA 0 only): 0 kernel entry, 1 set-up done, 2 weights resident (MMA warp), 3 first activation stage landed,
+// 8 + 4 u + {0: MMA unit start, 1: MMA unit issued, 2: epilogue sees the accumulator, 3: epilogue unit done}, 7 exit
+__device__ __forceinline__ void trace_stamp(const FpropParams& p, int slot) {
+  if (p.trace != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[slot] = t;
+  }
+}
+
 template <int GC, bool GLUE>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
                       const __grid_constant__ FpropParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
+  if (threadIdx.x == 0) trace_stamp(p, 0);
   // sibling launch: even CTAs serve problem 0, odd CTAs problem 1; G CTAs share a problem's units
   const int prob = p.nprob == 2 ? (int)(blockIdx.x & 1u) : 0;
   const int G = p.nprob == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -150,7 +161,8 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
   }
   if (threadIdx.x == 0) {
     // two MMA-issuing warps: each arrives once per stage / accumulator
-    for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], kMmaWarps); }
+    // a stage is consumed by ONE MMA warp (the stage's owner)
+    for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], kMmaWarps); ptx::mbar_init(&tempty_bar[i], 4 * kEpiSets); }
     ptx::mbar_init(w_bar, 1);
     ptx::fence_barrier_init();
@@ -162,6 +174,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc_cols = (uint32_t)p.acc_cols;
+  if (threadIdx.x == 0) trace_stamp(p, 1);
 
   if (warp == 0) {
     // ===== TMA producer ============================================================================
@@ -205,16 +218,18 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
     }
   } else if (warp == 1 || (warp >= 6 && warp < kFirstExtraEpiWarp)) {
     // ===== MMA issuers =============================================================================
-    // Lane-parallel issue: the MMAs of one stage (<= 32: slabs x out components of the group, structural zero
-    // blocks left out) form a dense list in (slab, component) order.  All lanes build their descriptors at once;
-    // the tcgen05.mma under the lane predicate then costs one short elect-and-issue round per active lane (~40
-    // cycles per MMA instead of ~100 for descriptor arithmetic on the uniform datapath; tools/umma_rate.py).
-    // kMmaWarps warps share the list (entry i goes to warp i mod kMmaWarps) and issue concurrently: accumulating MMAs commute, so only
-    // the accumulator-initialising ones (tap 0, one per out component, distinct columns) need an order -- they go
-    // first, from all warps, and a named barrier separates them from the rest of that stage.
-    // The accumulate flag of an issue site must be warp-uniform (ptxas derives the instruction's predicate with a
-    // vote over the issuing lanes), hence the separate sites.  tcgen05.commit tracks the MMAs of the executing
-    // thread; the tensor pipe retires in order, so each warp's commit comes from the lane that issued last.
+    // Lane-parallel issue: the MMAs of one stage (<= 32: taps x slabs x out components of the group, structural zero
+    // blocks left out) form a dense list; all lanes of a warp build their descriptors at once and the tcgen05.mma
+    // under the lane predicate then costs one short elect-and-issue round per active lane (~40 cycles per MMA
+    // instead of ~100 for descriptor arithmetic on the uniform datapath; tools/umma_rate.py).
+    // Every accumulator starts from ZERO -- the epilogue warps clear it with tcgen05.st after reading it -- so all
+    // MMAs accumulate and commute, nothing orders them, and the kMmaWarps warps take whole STAGES in turn (stage n
+    // of the CTA belongs to warp n mod kMmaWarps).  Measured with the CTA timeline (tools/fprop_trace.py): when the
+    // four warps shared every stage (entry i to warp i mod 4, a named barrier behind the initialising MMAs), a
+    // stage cost ~0.35 us of wait / barrier / commit bookkeeping on top of its MMAs and a TCN unit took 2.7-4.4 us
+    // for 1.0-2.1 us of tensor-core work; with a stage per warp that bookkeeping overlaps four ways.
+    // tcgen05.commit tracks the MMAs of the executing thread; the tensor pipe retires in order, so a warp's commit
+    // comes from the lane that issued last.
     {
       const int me = warp == 1 ? 0 : warp - 5;
       const uint64_t a_hi = ptx::make_smem_desc_hi(16, p.a_sbo, p.a_swz);                 // K-major, swizzled
@@ -222,15 +237,16 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
       const uint32_t a_base = ptx::smem_u32(a_ring), b_lo16 = ptx::smem_u32(b_img) >> 4;
       const int lanes_per_chunk = p.slabs_per_chunk * p.mma_per_slab;   // op-table entries of one (group, chunk)
       const int lanes_per_stage = lanes_per_chunk * p.tps;         // a stage holds p.tps taps (1, or all of them)
-      const int my_entry = kMmaWarps * lane + me;
-      const int my_tl = my_entry / lanes_per_chunk;                // tap of the stage this lane's MMA belongs to
-      const int my_rest = my_entry - my_tl * lanes_per_chunk;      // ... and its entry in the chunk's op list
+      const bool lane_on = lane < lanes_per_stage;
+      const int my_tl = lane_on ? lane / lanes_per_chunk : 0;      // tap of the stage this lane's MMA belongs to
+      const int my_rest = lane - my_tl * lanes_per_chunk;          // ... and its entry in the chunk's op list
       // where that tap's A operand starts inside a stage: its own box, or a row offset into the shared box
-      const uint32_t my_tap_off16 = my_tl >= p.tps ? 0u
+      const uint32_t my_tap_off16 = !lane_on ? 0u
                                     : p.rs ? (uint32_t)p.rs_row[my_tl] * ((uint32_t)p.BK * 2u >> 4)
                                            : ((uint32_t)my_tl * p.box_bytes) >> 4;
       if (!p.dense) ptx::mbar_wait(w_bar, 0);
-      uint32_t slot = 0, parity = 0, it = 0;
+      if (warp == 1 && lane == 0) trace_stamp(p, 2);
+      uint32_t slot = 0, parity = 0, it = 0, sc = 0;               // sc: stages of this CTA so far
       for (int round = 0; round * G < p.total_units; ++round) {
         const int u = unit_of_round(round, p.total_units, G, cta);
         if (u < 0) continue;
@@ -238,45 +254,43 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
         const uint32_t mask = p.chunk_mask[p.group_order[gi]];
         const uint32_t as = p.acc_stages == 2 ? (it & 1) : 0;
         const uint32_t use = p.acc_stages == 2 ? (it >> 1) : it;
-        ptx::mbar_wait(&tempty_bar[as], (use & 1) ^ 1);
+        ptx::mbar_wait(&tempty_bar[as], use & 1);                  // read AND cleared by the epilogue warps
         ptx::tc_fence_after();
+        if (warp == 1 && lane == 0 && it < 6) trace_stamp(p, 8 + 4 * (int)it);
         const uint32_t d_unit = tmem_base + as * acc_cols;
         const uint2* tbl_g = op_tbl_s + (size_t)p.group_order[gi] * p.chunks * lanes_per_chunk;
         int last_closer = -1;                                  // lane that issued this warp's last MMA of the unit
         for (int c = 0; c < p.chunks; ++c) {
           if (!((mask >> c) & 1u)) continue;
-          // per chunk: this lane's MMA (the same for every tap up to the tap's weight-tile offset)
-          uint2 e = make_uint2(0u, 0u);
-          if (my_entry < lanes_per_stage) e = tbl_g[c * lanes_per_chunk + my_rest];
-          const bool valid = (int)e.x < 0;
-          const bool first = valid && (e.x & (1u << 30)) != 0u && my_tl == 0;
-          const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-          const bool any = vmask != 0u;
-          const int closer = any ? 31 - __clz((int)vmask) : -1;
-          if (any) last_closer = closer;
-          const uint32_t a_off16 = ((e.x >> 16) & 3u) * 2u + my_tap_off16;
-          const uint32_t d_lane = d_unit + ((e.x >> 20) & 0x1ffu);
-          uint32_t b16 = b_lo16 + (e.x & 0x3fffu) + (uint32_t)my_tl * p.tap_stride16;
-          for (int tap = 0; tap < p.ntaps; tap += p.tps, b16 += p.tap_stride16 * (uint32_t)p.tps) {
-            const uint64_t a_desc = a_hi | (uint64_t)((((a_base + slot * p.stage_bytes) >> 4) + a_off16) & 0x3fffu);
-            const uint64_t b_desc = b_hi | (uint64_t)(b16 & 0x3fffu);
+          for (int tap = 0; tap < p.ntaps; tap += p.tps, ++sc) {
+            // EVERY warp observes every phase of every stage barrier (a parity wait tells the current phase from the
+            // previous one only: a warp that skipped a lap of the ring would take an unfilled slot for a filled one);
+            // for a stage that has landed this is one try_wait
             ptx::mbar_wait(&full_bar[slot], parity);
-            ptx::tc_fence_after();
-            if (tap == 0) {
-              if (first) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 0u);
-              __syncwarp();
-              asm volatile("bar.sync 2, %0;" ::"n"(32 * kMmaWarps) : "memory");      // every warp's initialising MMAs are issued
-              if (valid && !first) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 1u);
-            } else {
+            if ((int)(sc % (uint32_t)kMmaWarps) == me) {
+              // this lane's MMA of the stage
+              uint2 e = make_uint2(0u, 0u);
+              if (lane_on) e = tbl_g[c * lanes_per_chunk + my_rest];
+              const bool valid = (int)e.x < 0;
+              const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+              const uint32_t a_off16 = ((e.x >> 16) & 3u) * 2u + my_tap_off16;
+              const uint32_t d_lane = d_unit + ((e.x >> 20) & 0x1ffu);
+              const uint32_t b16 = b_lo16 + (e.x & 0x3fffu) + (uint32_t)(tap + my_tl) * p.tap_stride16;
+              const uint64_t a_desc = a_hi | (uint64_t)((((a_base + slot * p.stage_bytes) >> 4) + a_off16) & 0x3fffu);
+              const uint64_t b_desc = b_hi | (uint64_t)(b16 & 0x3fffu);
+              ptx::tc_fence_after();
+              if (warp == 1 && lane == 0 && it == 0 && sc == 0) trace_stamp(p, 3);
               if (valid) ptx::umma_f16(d_lane, a_desc, b_desc, e.y, 1u);
+              __syncwarp();
+              if (vmask != 0u) {
+                const int closer = 31 - __clz((int)vmask);
+                last_closer = closer;
+                if (lane == closer) ptx::umma_commit(&empty_bar[slot]);
+              } else if (lane == 0) {
+                ptx::mbar_arrive(&empty_bar[slot]);             // nothing reads the slot
+              }
+              __syncwarp();
             }
-            __syncwarp();
-            if (any) {
-              if (lane == closer) ptx::umma_commit(&empty_bar[slot]);
-            } else if (lane == 0) {
-              ptx::mbar_arrive(&empty_bar[slot]);               // nothing of this warp reads the slot
-            }
-            __syncwarp();
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }
         }
@@ -287,15 +301,30 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
           ptx::mbar_arrive(&tfull_bar[as]);
         }
         __syncwarp();
+        if (warp == 1 && lane == 0 && it < 6) trace_stamp(p, 9 + 4 * (int)it);
         ++it;
       }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global ===================================================
-    pdl_wait();
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     const int eset = warp >= kFirstExtraEpiWarp ? 1 + (warp - kFirstExtraEpiWarp) / 4 : 0;
     const int row = q * 32 + lane;
+    // The accumulators start from zero (every MMA accumulates: see the issuers): the warps of a lane quarter clear
+    // alternate 16-column groups of all buffers here; behind a unit every warp clears the columns it has read.
+    auto clear_acc = [&](uint32_t first_col, uint32_t ncols) {
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + first_col;
+      for (uint32_t col = 16u * (uint32_t)eset; col < ncols; col += 16u * kEpiSets) ptx::tmem_st16_zero(t0 + col);
+      ptx::tmem_st_wait();
+    };
+    clear_acc(0u, acc_cols * (uint32_t)p.acc_stages);
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::mbar_arrive(&tempty_bar[0]);
+      ptx::mbar_arrive(&tempty_bar[1]);
+    }
+    pdl_wait();
     // 16-byte bf16 stores need 8-element alignment of every row start
     const bool vec16 = p.out16 != nullptr && (p.OW & 7) == 0 && (p.out_sC & 7) == 0 && (p.out_sH & 7) == 0 &&
                        (p.out_sN & 7) == 0 && (reinterpret_cast<unsigned long long>(p.out16) & 15ull) == 0;
@@ -335,16 +364,20 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
       prefetch_piece(eset);
       ptx::mbar_wait(&tfull_bar[as], use & 1);
       ptx::tc_fence_after();
+      if (warp == 2 && lane == 0 && it < 6) trace_stamp(p, 10 + 4 * (int)it);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * acc_cols;
       int piece_no = 0;
       for (int al = 0; al < GC; ++al) {
         const int ch_base = p.comp_of[group][al] * p.Pc;
         for (int c0 = 0; c0 < p.Pc; c0 += 16, ++piece_no) {
           if (piece_no % kEpiSets != eset) continue;
+          const bool tr = warp == 2 && lane == 0 && it == 0 && piece_no < 3 * kEpiSets;
+          if (tr) trace_stamp(p, 40 + 4 * (piece_no / kEpiSets));
           uint32_t v[16];
           if (!p.fuse) {
             ptx::tmem_ld16(t_row + (uint32_t)(al * p.NBp + c0), v);
             ptx::tmem_ld_wait();
+            ptx::tmem_st16_zero(t_row + (uint32_t)(al * p.NBp + c0));      // read once, by this warp only: clear it
           } else {
             // fusion: channels [c0, c0 + 8) and [c0 + 8, c0 + 16) of this component are 8-column groups of the
             // (up to four) column sets of its pair / quad; sum them with the component's signs (conv_cl.h)
@@ -365,6 +398,15 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
                 }
               }
             ptx::tmem_ld_wait();
+            if (tr) trace_stamp(p, 41 + 4 * (piece_no / kEpiSets));
+            // every 8-column group belongs to one (component, channel group), i.e. to this piece alone: clear it
+            // for the next unit right away (no pass over the whole accumulator, no barrier between the warps)
+#pragma unroll
+            for (int st = 0; st < 4; ++st)
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf)
+                if (p.epi_sgn[group][al][st] != 0 && c0 + hf * 8 < p.Pc)
+                  ptx::tmem_st8_zero(t_row + (uint32_t)p.epi_col[group][al][st] + (uint32_t)((c0 >> 3) + hf) * og_stride);
             const float s0 = (float)p.epi_sgn[group][al][0], s1 = (float)p.epi_sgn[group][al][1];
             const float s2 = (float)p.epi_sgn[group][al][2], s3 = (float)p.epi_sgn[group][al][3];
 #pragma unroll
@@ -373,6 +415,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
               for (int j = 0; j < 8; ++j)
                 v[hf * 8 + j] = __float_as_uint(fmaf(s3, __uint_as_float(u[3][hf][j]), fmaf(s2, __uint_as_float(u[2][hf][j]),
                                                 fmaf(s1, __uint_as_float(u[1][hf][j]), s0 * __uint_as_float(u[0][hf][j])))));
+            if (tr) trace_stamp(p, 42 + 4 * (piece_no / kEpiSets));
           }
           if (p.out16 && vec16) {
             // fp16 output in the tensor's own NCHW order (fused CNN-block path, epilogue.cu): the warp's
@@ -477,6 +520,7 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
             if (lim >= 16 && p.bias == nullptr) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) { *dst = __uint_as_float(v[j]); dst += p.out_sC; }
+              if (tr) trace_stamp(p, 43 + 4 * (piece_no / kEpiSets));
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -487,14 +531,17 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
           }
         }
       }
+      ptx::tmem_st_wait();                         // this warp's clears of the columns it read have landed
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      if (warp == 2 && lane == 0 && it < 6) trace_stamp(p, 11 + 4 * (int)it);
       ++it;
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_stamp(p, 7);
   if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -531,6 +578,10 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackParam
   const int items = p.n_img * p.ntaps * p.J * 2 * pack_rows(p);
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) pack_item(p, it);
 }
+
+static unsigned long long* g_fprop_trace = nullptr;
+void set_fprop_trace(void* dev_buf) { g_fprop_trace = reinterpret_cast<unsigned long long*>(dev_buf); }
+unsigned long long* fprop_trace() { return g_fprop_trace; }
 
 static int g_num_sms = 0;
 int num_sms() {
@@ -665,6 +716,7 @@ int launch_cl_fprop(const ConvGeom& g, const void* in_cl, const float* const* ho
   if (epi && (epi->mode != 0 || epi->stats) && out_f16)
     return fail(SELDQ_ERR_UNSUPPORTED, "fused convolution epilogues exist for the fp32 output only");
   if ((rc = set_fprop_epilogue(p, 0, epi, out))) return rc;
+  p.trace = cl::fprop_trace();
   const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, p.dense != 0);
   alignas(64) CUtensorMap tm;
   rc = encode_cl_map(&tm, in_cl, l, g.IW, g.IH, g.N, p.box_rows);
@@ -702,6 +754,7 @@ int launch_cl_fprop_pair(const ConvGeom& g, const void* const in_cl[2], const vo
   p.out_sN = g.out_sN; p.out_sC = g.out_sC; p.out_sH = g.out_sH;
   for (int k = 0; k < 2; ++k)
     if ((rc = set_fprop_epilogue(p, k, epi ? &epi[k] : nullptr, out[k]))) return rc;
+  p.trace = cl::fprop_trace();
   const cl::OperandLayout l = cl::operand_layout(g.tab.nc, g.R, false);
   alignas(64) CUtensorMap tm[2];
   for (int k = 0; k < 2; ++k)

@@ -22,7 +22,7 @@ namespace cl {
 constexpr int kTileM = 128;     // positions per accumulator tile (TMEM lanes)
 constexpr int kThreads = 320;   // wgrad: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kMmaWarps = 4;          // fprop: MMA-issuing warps (warp 1 and warps 6 ...)
-constexpr int kEpiSets = 2;           // fprop: epilogue warp sets of 4 (one warp per TMEM lane quarter); the sets split
+constexpr int kEpiSets = 3;           // fprop: epilogue warp sets of 4 (one warp per TMEM lane quarter); the sets split
                                       // the 16-channel column chunks of a tile between them
 constexpr int kFirstExtraEpiWarp = 6 + (kMmaWarps - 1);
 constexpr int kFpropThreads = 192 + 32 * (kMmaWarps - 1) + 128 * (kEpiSets - 1);
@@ -137,6 +137,8 @@ struct FpropParams {
   int epi_mode[2];
   const float* addend[2];
   double* stats[2];
+  // optional timeline of CTA 0 (tools/fprop_trace.py): when not null, the roles write globaltimer stamps here
+  unsigned long long* trace;
   uint2 op_tbl[kOpTableEntries];
 };
 
@@ -172,6 +174,8 @@ struct WgradParams {
 };
 
 int num_sms();
+void set_fprop_trace(void* dev_buf);      // debug: timeline of CTA 0 of every later fprop launch (null: off)
+unsigned long long* fprop_trace();
 
 }  // namespace cl
 

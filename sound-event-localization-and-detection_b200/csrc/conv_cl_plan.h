@@ -281,7 +281,8 @@ inline int plan_fprop(const ConvGeom& g, FpropParams* p, size_t* smem_bytes, int
   // Row-shared taps (conv_cl.h): the KW taps of a kernel row from one box, if their shifts span at most 128 rows (a TMA
   // box has at most 256): every dilation of the TCN qualifies -- a launch's time grows by ~1.4 ns per 128-byte row it
   // loads (ncu, per-launch list), so 128 + 2 d rows instead of 3 x 128 is worth 1-2 us of a 12-14 us launch
-  if (p->tps == 1 && l.BK == 64 && g.KW > 1 && (g.KW - 1) * g.dw <= 128 && g.KW * lps <= 32 * kMmaWarps &&
+  // (a stage's MMAs are issued by the lanes of ONE warp: at most 32 per stage)
+  if (p->tps == 1 && l.BK == 64 && g.KW > 1 && (g.KW - 1) * g.dw <= 128 && g.KW * lps <= 32 &&
       !getenv("SELDQ_NO_RS")) {
     int mn = p->off_w[0];
     for (int t = 0; t < g.KW; ++t) mn = p->off_w[t] < mn ? p->off_w[t] : mn;

@@ -278,6 +278,13 @@ extern "C" int seldq_conv_dgrad(const seldq_conv_desc_t* d, const float* gy, con
   return launch_cl_fprop(g, gy_cl, host_w, packed_w, nullptr, gx, nullptr, st);
 }
 
+// debug (tools/fprop_trace.py): 64 x uint64 device buffer that CTA 0 of every later convolution launch stamps with
+// globaltimer values (conv_cl.cu trace_stamp); NULL switches the trace off.  Not part of the reference surface.
+extern "C" int seldq_debug_fprop_trace(void* dev_buf) {
+  cl::set_fprop_trace(dev_buf);
+  return SELDQ_OK;
+}
+
 static cl::FpropEpilogue to_epilogue(const seldq_conv_epilogue_t* e) {
   cl::FpropEpilogue o;
   if (e) { o.mode = e->mode; o.addend = e->addend; o.stats = e->stats; }

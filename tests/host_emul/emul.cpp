@@ -17,7 +17,7 @@ using namespace seldq;
 // Runs the REAL host plan (cl::plan_fprop: fusion sets, op table, epilogue column / sign table, stage geometry, chunk
 // masks, group schedule) and the REAL pack mapping (cl::pack_dst_offset) through a plain-loop model of what the kernel
 // does with them: TMA boxes with zero fill, one "MMA" per op-table entry (A rows x B rows, K = 16, sign = negate-B
-// bit, accumulate flag honoured), accumulator column sets, epilogue combination.  No rounding to bf16: the result
+// bit, every accumulator starting from zero as the epilogue warps leave it), accumulator column sets, epilogue combination.  No rounding to bf16: the result
 // must match the expanded-weight convolution to float accuracy, so any table or offset error shows as O(1).
 static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* const* w, float* out, int n_sms,
                         int* info, int nprob = 1) {
@@ -95,14 +95,12 @@ static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* co
   };
   const int lpc = p.slabs_per_chunk * p.mma_per_slab;
   std::vector<double> acc((size_t)cl::kTileM * 512);
-  std::vector<char> init((size_t)512);
   for (int u = 0; u < p.total_units; ++u) {
     const int group = p.group_order[u / p.total_tiles];
     int r = u % p.total_tiles;
     const int wt = r % p.tiles_w; r /= p.tiles_w;
     const int h = r % p.OH, n = r / p.OH, w0 = wt * cl::kTileM;
-    std::fill(acc.begin(), acc.end(), 1e30);                          // an accumulator never initialised shows up
-    std::fill(init.begin(), init.end(), 0);
+    std::fill(acc.begin(), acc.end(), 0.0);       // the epilogue warps clear every accumulator (tcgen05.st): all MMAs accumulate
     for (int c = 0; c < p.chunks; ++c) {
       if (!((p.chunk_mask[group] >> c) & 1u)) continue;
       for (int tap0 = 0; tap0 < p.ntaps; tap0 += p.tps)
@@ -111,7 +109,6 @@ static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* co
             const uint2 e = p.op_tbl[((size_t)group * p.chunks + c) * lpc + e_i];
             if (!((int)e.x < 0)) continue;
             const int tap = tap0 + tl;
-            const bool first = (e.x & (1u << 30)) != 0u && tap == 0;
             const int col = (e.x >> 20) & 0x1ff, slab = (e.x >> 16) & 3;
             const size_t tile = ((size_t)(e.x & 0x3fffu) + (size_t)tap * p.tap_stride16) * 16;   // bytes
             const int nmma = (e.y >> 17) & 0x3f, neg = (e.y >> 14) & 1;
@@ -129,10 +126,8 @@ static int run_cl_fprop(const ConvGeom& g, const float* in_nchw, const float* co
                   const double b = packed[(tile + (size_t)(k >> 3) * (p.NBmma * 16) + (nn >> 3) * 128 + (nn & 7) * 16) / 2 + (k & 7)];
                   sacc += a * b;
                 }
-                double& d = acc[(size_t)m * 512 + col + nn];
-                d = (first ? 0.0 : d) + (neg ? -sacc : sacc);
+                acc[(size_t)m * 512 + col + nn] += neg ? -sacc : sacc;
               }
-            if (first) for (int nn = 0; nn < p.NBmma; ++nn) init[col + nn] = 1;
           }
     }
     // epilogue
