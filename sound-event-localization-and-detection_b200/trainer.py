@@ -30,19 +30,29 @@ class FlatGradBucket(object):
     second one holding the parameters themselves (every p.data / p.grad is a view), so that the all-reduce and the
     optimiser each touch ONE tensor instead of a few hundred."""
 
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+    def __init__(self, params, late=None):
+        """late(p) -> True for parameters whose gradient completes LAST in the backward pass (the CNN front): they are
+        laid out first, so that flat[n_late:] -- everything whose gradient is complete once the TCN backward has
+        finished -- is one contiguous slice that can be all-reduced while the CNN backward still runs."""
+        params = [p for p in params if p.requires_grad]
+        self.model_order = list(params)                       # model.parameters() order (checkpoint layout)
+        if late is not None:
+            params = [p for p in params if late(p)] + [p for p in params if not late(p)]
+        self.params = params
+        self.n_late = sum(p.numel() for p in params if late is not None and late(p))
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=self.params[0].dtype, device=dev)
         self.flat_param = torch.nn.Parameter(torch.empty(total, dtype=self.params[0].dtype, device=dev))
         off = 0
+        self.offsets = {}
         with torch.no_grad():
             for p in self.params:
                 n = p.numel()
                 self.flat_param.data[off:off + n].copy_(p.data.reshape(-1))
                 p.data = self.flat_param.data[off:off + n].view_as(p)
                 p.grad = self.flat[off:off + n].view_as(p)
+                self.offsets[id(p)] = (off, n)
                 off += n
         self.flat_param.grad = self.flat
         if dev.type == "cuda":
@@ -55,28 +65,142 @@ class FlatGradBucket(object):
 
     def all_reduce_mean(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(dist.get_world_size(group))
+            if self.flat.is_cuda:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)      # ncclAvg: no separate division pass
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
+
+    # ---- the exchange in two parts: flat[n_late:] as soon as the TCN backward is done, flat[:n_late] at the end ----
+    def all_reduce_early(self, group, stream):
+        """Sum flat[n_late:] across ranks on `stream` (forked behind the current stream; None on a CPU run, where
+        the call is simply made at this point of the backward pass)."""
+        if stream is None:
+            dist.all_reduce(self.flat[self.n_late:], op=dist.ReduceOp.SUM, group=group)
+            return
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            dist.all_reduce(self.flat[self.n_late:], op=dist.ReduceOp.AVG, group=group)    # NCCL averages in the collective
+
+    def all_reduce_rest_mean(self, group, stream):
+        """Sum flat[:n_late], join `stream`, divide everything by the world size."""
+        if stream is not None:
+            if self.n_late:
+                dist.all_reduce(self.flat[:self.n_late], op=dist.ReduceOp.AVG, group=group)
+            torch.cuda.current_stream().wait_stream(stream)
+            return
+        if self.n_late:
+            dist.all_reduce(self.flat[:self.n_late], op=dist.ReduceOp.SUM, group=group)
+        self.flat.div_(dist.get_world_size(group))
 
 
 class Trainer(object):
-    def __init__(self, model, lr=1e-4, n_sed=42, group=None):
+    def __init__(self, model, lr=1e-4, n_sed=42, group=None, overlap_all_reduce=True):
         self.model = model
         self.n_sed = n_sed
         self.group = group
-        self.bucket = FlatGradBucket(model.parameters())
+        # gradients of the CNN front complete last (backward runs heads -> TCN -> CNN): they go first in the bucket
+        late_ids = {id(p) for n, p in model.named_parameters() if ".cnn." in n or n.startswith("cnn.")}
+        self.bucket = FlatGradBucket(model.parameters(), late=lambda p: id(p) in late_ids)
         on_cuda = self.bucket.flat.is_cuda
         self._functional = None
+        self._prev_accumulate = None
         if on_cuda:
             # the weight-gradient kernels add straight into the bucket (functional.set_grad_accumulation)
             from . import functional
-            functional.set_grad_accumulation(True)
+            self._prev_accumulate = functional.set_grad_accumulation(True)
             self._functional = functional
+        # SURVEY.md 8e: the exchange of everything but the CNN front's gradients (flat[n_late:], ~80 % of the bucket)
+        # is launched on a side stream the moment the TCN backward has finished and overlaps the CNN backward: a
+        # gradient hook on the input of every TC_Block (the mirror's or the reference's own) marks that moment
+        # SELDQ_AR_OVERLAP=0: one all-reduce of the whole bucket behind the backward pass (the round-1 schedule)
+        self._overlap = bool(overlap_all_reduce) and __import__("os").environ.get("SELDQ_AR_OVERLAP", "1") != "0"
+        self._on_cuda = on_cuda
+        self._ar_stream = None
+        self._tc_blocks = [m for m in model.modules() if hasattr(m, "ResBlocks") and hasattr(m, "attention")]
+        self._pending = 0
+        self._early_launched = False
+        if self._overlap:
+            for m in self._tc_blocks:
+                m.register_forward_pre_hook(self._tcn_pre_hook)
         # Adam with the reference's hyper-parameters (train.py:502-504); fused = one kernel per step,
         # capturable so that the whole step can live in a CUDA graph
         # (element-wise update: one flat parameter is the same arithmetic as one tensor per parameter)
         self.optimizer = torch.optim.Adam([self.bucket.flat_param], lr=lr, fused=on_cuda, capturable=on_cuda)
         self._graph = None
+
+    def close(self):
+        """Restores the process-wide gradient-accumulation switch this trainer flipped."""
+        if self._functional is not None and self._prev_accumulate is not None:
+            self._functional.set_grad_accumulation(self._prev_accumulate)
+            self._prev_accumulate = None
+
+    def _distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _tcn_pre_hook(self, module, inputs):
+        x = inputs[0]
+        if self._overlap and self._distributed() and torch.is_grad_enabled() and x.requires_grad:
+            self._pending += 1
+            x.register_hook(self._tcn_backward_done)
+
+    def _tcn_backward_done(self, grad):
+        self._pending -= 1
+        if self._pending == 0 and not self._early_launched:
+            if self._ar_stream is None and self._on_cuda:
+                self._ar_stream = torch.cuda.Stream()
+            self.bucket.all_reduce_early(self.group, self._ar_stream)
+            self._early_launched = True
+        return None
+
+    def reduce_gradients(self):
+        """The step's one exchange: mean of the flat bucket over the ranks (second half of it when the first was
+        launched from the backward pass)."""
+        if not self._distributed():
+            return
+        if self._early_launched:
+            self.bucket.all_reduce_rest_mean(self.group, self._ar_stream)
+        else:
+            self.bucket.all_reduce_mean(self.group)
+
+    # ---- optimiser state in the reference's checkpoint layout (utility_functions.save_model / load_model) ----------
+    def optimizer_state_dict(self):
+        """Adam's state as `torch.optim.Adam(model.parameters())` would hold it: one {step, exp_avg, exp_avg_sq} entry
+        per parameter in model.parameters() order (the flat optimiser here keeps ONE entry for the whole bucket)."""
+        st = self.optimizer.state.get(self.bucket.flat_param, {})
+        group = {k: v for k, v in self.optimizer.param_groups[0].items() if k != "params"}
+        out = {"state": {}, "param_groups": [dict(group, params=list(range(len(self.bucket.model_order))))]}
+        if st:
+            for i, p in enumerate(self.bucket.model_order):
+                off, n = self.bucket.offsets[id(p)]
+                out["state"][i] = {"step": st["step"].detach().clone().cpu() if torch.is_tensor(st["step"]) else st["step"],
+                                   "exp_avg": st["exp_avg"][off:off + n].view_as(p).clone(),
+                                   "exp_avg_sq": st["exp_avg_sq"][off:off + n].view_as(p).clone()}
+        return out
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of optimizer_state_dict: accepts the reference's per-parameter 'optimizer_state_dict'."""
+        fp = self.bucket.flat_param
+        if not sd.get("state"):
+            return
+        st = self.optimizer.state[fp]
+        step = None
+        if "exp_avg" not in st:
+            st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(fp.data), torch.zeros_like(fp.data)
+        for i, p in enumerate(self.bucket.model_order):
+            e = sd["state"].get(i, sd["state"].get(str(i)))
+            if e is None:
+                continue
+            off, n = self.bucket.offsets[id(p)]
+            st["exp_avg"][off:off + n].copy_(e["exp_avg"].reshape(-1))
+            st["exp_avg_sq"][off:off + n].copy_(e["exp_avg_sq"].reshape(-1))
+            step = e["step"]
+        if step is not None:
+            step = torch.as_tensor(step, dtype=torch.float32)
+            st["step"] = step.to(fp.device) if self.optimizer.param_groups[0].get("capturable") else step.cpu()
+        for k, v in sd["param_groups"][0].items():
+            if k != "params":
+                self.optimizer.param_groups[0][k] = v
 
     def broadcast_parameters(self, src=0):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
@@ -142,10 +266,11 @@ class Trainer(object):
     def step(self, x, target):
         """One optimisation step on this rank's shard; returns the (local) loss tensor."""
         self.bucket.zero()
+        self._pending, self._early_launched = 0, False
         sed, doa = self.model(x)
         loss = seld_loss(sed, doa, target, self.n_sed)
         loss.backward()
-        self.bucket.all_reduce_mean(self.group)
+        self.reduce_gradients()
         self.optimizer.step()
         if self._functional is not None:
             # the flat update bypasses the parameters' version counters: refresh every packed bf16 weight set now,

@@ -56,6 +56,8 @@ def _rank_main(rank, world, port, out_dir):
     tr.broadcast_parameters(src=0)
     xs, ts = _shards(d, world)
     tr.step(xs[rank], ts[rank])
+    # the exchange ran in two parts: everything but the CNN front from the TC_Block's gradient hook, the rest at the end
+    assert tr._early_launched and 0 < tr.bucket.n_late < tr.bucket.flat.numel()
     torch.save({"flat": tr.bucket.flat.clone(), "params": [p.detach().clone() for p in m.parameters()]},
                os.path.join(out_dir, "rank%d.pt" % rank))
     dist.destroy_process_group()
@@ -85,3 +87,38 @@ def test_two_rank_gloo_step_matches_sequential_mean(tmp_path):
     ref = _build(meta, d)
     moved = sum(float((p0 - q.detach()).abs().max()) > 0 for p0, q in zip(outs[0]["params"], ref.parameters()))
     assert moved > 0
+
+
+def test_optimizer_state_in_the_reference_checkpoint_layout():
+    """Trainer.optimizer_state_dict(): one Adam entry per parameter in model.parameters() order, the layout the
+    reference's save_model / load_model write (train.py:26-81); loading it into a fresh trainer continues identically."""
+    trainer_mod = importlib.import_module(PKG + ".trainer")
+    meta, d = load_golden("model_dq_tiny")
+    xs, ts = _shards(d, 1)
+    m = _build(meta, d)
+    tr = trainer_mod.Trainer(m, lr=1e-3, n_sed=42)
+    tr.step(xs[0], ts[0])
+    sd = tr.optimizer_state_dict()
+    params = list(m.parameters())
+    assert sd["param_groups"][0]["params"] == list(range(len(params))) and len(sd["state"]) == len(params)
+    for i, p in enumerate(params):
+        assert sd["state"][i]["exp_avg"].shape == p.shape
+    # the same numbers a per-parameter Adam produces
+    m2 = _build(meta, d)
+    opt = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    from oracle import cpu_model
+    cpu_model.train_step(m2, opt, xs[0], ts[0])
+    for i, p in enumerate(m2.parameters()):
+        if p.grad is None:
+            continue
+        assert torch.allclose(sd["state"][i]["exp_avg"], opt.state[p]["exp_avg"], rtol=1e-9, atol=1e-14)
+        assert torch.allclose(sd["state"][i]["exp_avg_sq"], opt.state[p]["exp_avg_sq"], rtol=1e-9, atol=1e-18)
+    # round trip: a fresh trainer that loads model + optimiser state takes the same second step
+    m3 = _build(meta, d)
+    m3.load_state_dict(m.state_dict())
+    tr3 = trainer_mod.Trainer(m3, lr=1e-3, n_sed=42)
+    tr3.load_optimizer_state_dict(sd)
+    tr.step(xs[0], ts[0])
+    tr3.step(xs[0], ts[0])
+    for a, b in zip(m.parameters(), m3.parameters()):
+        assert torch.allclose(a, b, rtol=1e-10, atol=1e-14)
