@@ -313,6 +313,16 @@ int seldq_stft_magphase(const float* x, int32_t n_batch, int32_t n_ch, int64_t n
                         int32_t nperseg, int32_t noverlap, int32_t cut_dc, int32_t output_phase,
                         int32_t cut_last, float* out, void* stream);
 
+/* TC_Block tail, model.py:210-231: activation followed by nn.MaxPool1d(pool) (stride = pool, floor mode) in one kernel
+ * per direction.  act: SELDQ_ACT_RELU (relu1 / relu2 + maxpool1 / maxpool2) or SELDQ_ACT_TANH (tanh + maxpool3).
+ * x: float32 (rows = N * C, t); y, gy: (rows, t / pool); gx: (rows, t).  The backward pass re-derives the arg-max
+ * from x (first maximum wins, as nn.MaxPool1d) and needs y for the activation's derivative. */
+#define SELDQ_ACT_RELU 0
+#define SELDQ_ACT_TANH 1
+int seldq_act_pool1d_fwd(const float* x, int64_t rows, int32_t t, int32_t pool, int32_t act, float* y, void* stream);
+int seldq_act_pool1d_bwd(const float* x, const float* y, const float* gy, int64_t rows, int32_t t, int32_t pool,
+                         int32_t act, float* gx, void* stream);
+
 /* debug: a 64 x uint64 device buffer that CTA 0 of every later tensor-core convolution launch stamps with
  * %globaltimer values at its role hand-offs (tools/fprop_trace.py); NULL switches it off. */
 int seldq_debug_fprop_trace(void* dev_buf);

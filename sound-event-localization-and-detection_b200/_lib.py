@@ -54,6 +54,7 @@ class ConvEpilogue(ctypes.Structure):
 
 
 EPI_STORE, EPI_ACCUMULATE, EPI_ADD = 0, 1, 2
+ACT_RELU, ACT_TANH = 0, 1
 
 
 class AttentionDesc(ctypes.Structure):
@@ -129,6 +130,9 @@ _PROTOS = {
                                           ctypes.c_size_t, _P]),
     "seldq_linear_wgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, _P, ctypes.POINTER(_P), _P,
                                           ctypes.c_int32, _P, ctypes.c_size_t, _P]),
+    "seldq_act_pool1d_fwd": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P]),
+    "seldq_act_pool1d_bwd": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                            _P, _P]),
     "seldq_debug_fprop_trace": (ctypes.c_int, [_P]),
     "seldq_attention_supported": (ctypes.c_int, [ctypes.POINTER(AttentionDesc)]),
     "seldq_attention_saved_bytes": (ctypes.c_size_t, [ctypes.POINTER(AttentionDesc)]),

@@ -9,6 +9,7 @@
 #include "geom.h"
 #include "launch.h"
 #include "stft.cuh"
+#include "tail.h"
 #include "tcn_glue.h"
 #include "wgrad_first.h"
 
@@ -680,6 +681,24 @@ extern "C" int seldq_linear_wgrad(const seldq_linear_desc_t* d, const float* x, 
 }
 
 // ---- STFT ------------------------------------------------------------------------------------------
+// ---- TC_Block tail ---------------------------------------------------------------------------------------------
+extern "C" int seldq_act_pool1d_fwd(const float* x, int64_t rows, int32_t t, int32_t pool, int32_t act, float* y,
+                                    void* stream) {
+  if (!x || !y || rows < 1 || t < 1 || (act != SELDQ_ACT_RELU && act != SELDQ_ACT_TANH))
+    return fail(SELDQ_ERR_INVALID, "seldq_act_pool1d_fwd: bad argument");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  return launch_act_pool_fwd(x, y, rows, t, pool, act, (cudaStream_t)stream);
+}
+extern "C" int seldq_act_pool1d_bwd(const float* x, const float* y, const float* gy, int64_t rows, int32_t t,
+                                    int32_t pool, int32_t act, float* gx, void* stream) {
+  if (!x || !y || !gy || !gx || rows < 1 || t < 1 || (act != SELDQ_ACT_RELU && act != SELDQ_ACT_TANH))
+    return fail(SELDQ_ERR_INVALID, "seldq_act_pool1d_bwd: bad argument");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  return launch_act_pool_bwd(x, y, gy, gx, rows, t, pool, act, (cudaStream_t)stream);
+}
+
 // ---- attention ------------------------------------------------------------------------------------------------
 namespace {
 struct AttnBufs { size_t rm, tr; char *q_rm, *k_rm, *v_rm, *q_tr, *k_tr, *v_tr; };

@@ -1,0 +1,97 @@
+// Glue of the TC_Block tail (model.py:210-231):
+//     sum of skips -> ReLU -> MaxPool1d(p) -> conv1 -> attention -> ReLU -> MaxPool1d(p) -> conv2 -> tanh -> MaxPool1d(p)
+// Each activation + pooling pair is ONE bandwidth-bound kernel per direction instead of two PyTorch kernels each
+// (activation, pooling; pooling backward, activation backward).  Both activations are monotone, so
+// max_k act(x[p t + k]) = act(max_k x[p t + k]) -- one activation per pooled element instead of p -- and the first
+// maximum wins, as in nn.MaxPool1d.  x: fp32 (rows = N * C, T); y: fp32 (rows, T / p) (floor mode: a tail of T % p
+// samples is dropped and gets a zero gradient).
+#include <cuda_runtime.h>
+
+#include "launch.h"
+#include "pdl.cuh"
+#include "tail.h"
+
+namespace seldq {
+namespace tail {
+
+// act: 0 = ReLU, 1 = tanh
+template <int P>
+__global__ void __launch_bounds__(256) act_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows,
+                                                          int T, int To, int pool, int act) {
+  const long long total = rows * To;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / To;
+    const int t = (int)(i - r * To);
+    const float* src = x + r * T + (long long)t * pool;
+    float m;
+    if (P == 2) {                                          // the shipped configurations: one 8-byte load
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+      m = fmaxf(v.x, v.y);
+    } else {
+      m = __ldg(src);
+      for (int k = 1; k < pool; ++k) m = fmaxf(m, __ldg(src + k));
+    }
+    y[i] = act == 0 ? fmaxf(m, 0.f) : tanhf(m);
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) act_pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                          const float* __restrict__ gy, float* __restrict__ gx,
+                                                          long long rows, int T, int To, int pool, int act) {
+  // one thread per POOLED element writes the p input gradients of its window (+ the dropped tail of the row)
+  const long long total = rows * To;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / To;
+    const int t = (int)(i - r * To);
+    const float* src = x + r * T + (long long)t * pool;
+    float* dst = gx + r * T + (long long)t * pool;
+    const float yo = __ldg(y + i), g = __ldg(gy + i);
+    // d act / d (its argument) at the maximum: ReLU: 1 where the maximum is positive; tanh: 1 - y^2
+    const float d = act == 0 ? (yo > 0.f ? g : 0.f) : g * (1.f - yo * yo);
+    if (P == 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+      const bool first = v.x >= v.y;                       // ties: the first index, as nn.MaxPool1d
+      *reinterpret_cast<float2*>(dst) = make_float2(first ? d : 0.f, first ? 0.f : d);
+    } else {
+      int arg = 0;
+      float m = __ldg(src);
+      for (int k = 1; k < pool; ++k) {
+        const float v = __ldg(src + k);
+        if (v > m) { m = v; arg = k; }
+      }
+      for (int k = 0; k < pool; ++k) dst[k] = k == arg ? d : 0.f;
+    }
+    if (t == To - 1)
+      for (int k = To * pool; k < T; ++k) gx[r * T + k] = 0.f;
+  }
+}
+
+}  // namespace tail
+
+static int grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = 148LL * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int launch_act_pool_fwd(const float* x, float* y, long long rows, int T, int pool, int act, cudaStream_t st) {
+  if (pool < 1 || T / pool < 1) return fail(SELDQ_ERR_INVALID, "act_pool: pool %d does not fit a row of %d", pool, T);
+  const int To = T / pool;
+  const bool p2 = pool == 2 && (T % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+  if (p2) tail::act_pool_fwd_kernel<2><<<grid_for(rows * To), 256, 0, st>>>(x, y, rows, T, To, pool, act);
+  else tail::act_pool_fwd_kernel<0><<<grid_for(rows * To), 256, 0, st>>>(x, y, rows, T, To, pool, act);
+  return check_launch("act_pool_fwd_kernel");
+}
+
+int launch_act_pool_bwd(const float* x, const float* y, const float* gy, float* gx, long long rows, int T, int pool, int act,
+                        cudaStream_t st) {
+  if (pool < 1 || T / pool < 1) return fail(SELDQ_ERR_INVALID, "act_pool: pool %d does not fit a row of %d", pool, T);
+  const int To = T / pool;
+  const bool p2 = pool == 2 && (T % 2) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gx)) & 7) == 0;
+  if (p2) tail::act_pool_bwd_kernel<2><<<grid_for(rows * To), 256, 0, st>>>(x, y, gy, gx, rows, T, To, pool, act);
+  else tail::act_pool_bwd_kernel<0><<<grid_for(rows * To), 256, 0, st>>>(x, y, gy, gx, rows, T, To, pool, act);
+  return check_launch("act_pool_bwd_kernel");
+}
+
+}  // namespace seldq

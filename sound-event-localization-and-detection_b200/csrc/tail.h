@@ -1,0 +1,11 @@
+// TC_Block tail glue (tail.cu): activation + MaxPool1d in one kernel per direction.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace seldq {
+int launch_act_pool_fwd(const float* x, float* y, long long rows, int T, int pool, int act, cudaStream_t st);
+int launch_act_pool_bwd(const float* x, const float* y, const float* gy, float* gx, long long rows, int T, int pool, int act,
+                        cudaStream_t st);
+}  // namespace seldq

@@ -510,6 +510,55 @@ def block_linear(x, weights, bias, algebra, prec=None):
     return y.reshape(lead + (y.shape[-1],))
 
 
+class _ActPool1d(torch.autograd.Function):
+    """y = MaxPool1d(pool)(act(x)), act = ReLU | tanh: the activation + pooling pairs of the TC_Block tail
+    (model.py:214-231) as one kernel per direction (csrc/tail.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, act, pool):
+        _require_cuda_f32(x, "input")
+        x = x.contiguous()
+        n, c, t = x.shape
+        y = torch.empty((n, c, t // pool), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _timed("act_pool_kernel", 0.0, 1, lambda: _lib.check(_lib.lib().seldq_act_pool1d_fwd(
+                x.data_ptr(), n * c, t, pool, act, y.data_ptr(), _stream())))
+        ctx.act, ctx.pool = act, pool
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y = ctx.saved_tensors
+        gy = gy.contiguous()
+        n, c, t = x.shape
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _timed("act_pool_kernel", 0.0, 1, lambda: _lib.check(_lib.lib().seldq_act_pool1d_bwd(
+                x.data_ptr(), y.data_ptr(), gy.data_ptr(), n * c, t, ctx.pool, ctx.act, gx.data_ptr(), _stream())))
+        return gx, None, None
+
+
+def act_pool1d(x, act_module, pool_module):
+    """act_module (nn.ReLU | nn.Tanh) followed by pool_module (nn.MaxPool1d | None) on the fused kernel where it
+    applies -- CUDA float32 (N, C, T), pooling with stride = kernel, no padding / dilation, floor mode -- and through
+    the modules themselves otherwise.  Same arithmetic in both precision modes."""
+    import torch.nn as nn
+    act = _lib.ACT_RELU if isinstance(act_module, nn.ReLU) else _lib.ACT_TANH if isinstance(act_module, nn.Tanh) else None
+    ok = (act is not None and isinstance(pool_module, nn.MaxPool1d) and isinstance(x, torch.Tensor) and x.is_cuda
+          and x.dtype == torch.float32 and x.dim() == 3 and os.environ.get("SELDQ_TAIL", "1") != "0")
+    if ok:
+        k, s = pool_module.kernel_size, pool_module.stride
+        k = k[0] if isinstance(k, (tuple, list)) else k
+        s = s[0] if isinstance(s, (tuple, list)) else s
+        ok = (isinstance(k, int) and s == k and pool_module.padding in (0, (0,)) and pool_module.dilation in (1, (1,))
+              and not pool_module.ceil_mode and not pool_module.return_indices and 1 <= k <= x.shape[2])
+    if ok:
+        return _ActPool1d.apply(x, act, k)
+    y = act_module(x)
+    return y if pool_module is None else pool_module(y)
+
+
 class _Attention(torch.autograd.Function):
     """out = softmax(q k^T / sqrt(d)) v per (sample, head) (model.py:40-48) on the fused tcgen05 kernels
     (csrc/attention.cu): q, k, v (N, E, S) float32 -- the 1x1 projections' output layout -- -> out (N, S, E)."""

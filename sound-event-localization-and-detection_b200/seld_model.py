@@ -217,20 +217,16 @@ def tc_block_forward(self, residual):
         for block in self.ResBlocks:
             residual, skip = block(residual)
             sum_skip = skip if sum_skip is None else sum_skip + skip
-    out = self.relu1(sum_skip)
-    if self.pool_time == 'TCN':
-        out = self.maxpool1(out)
+    # activation + MaxPool1d pairs of the tail (model.py:214-231): one kernel per direction each (csrc/tail.cu)
+    pooled = self.pool_time == 'TCN'
+    out = _F.act_pool1d(sum_skip, self.relu1, self.maxpool1) if pooled else self.relu1(sum_skip)
     out = self.conv1(out)
     out = out.permute(0, 2, 1)
     out = self.attention(out, out, out, mask=None)
     out = out.permute(0, 2, 1)
-    out = self.relu2(out)
-    if self.pool_time == 'TCN':
-        out = self.maxpool2(out)
+    out = _F.act_pool1d(out, self.relu2, self.maxpool2) if pooled else self.relu2(out)
     out = self.conv2(out)
-    out = self.tanh(out)
-    if self.pool_time == 'TCN':
-        out = self.maxpool3(out)
+    out = _F.act_pool1d(out, self.tanh, self.maxpool3) if pooled else self.tanh(out)
     return out
 
 

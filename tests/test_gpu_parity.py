@@ -595,3 +595,25 @@ def test_full_size_model_matches_reference_fixture(seldq, prec):
             bad[k] = (e_s, e_n, gate)
     assert n == meta["n_grads"]
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]
+
+
+@pytest.mark.parametrize("act,pool,T", [("relu", 2, 4800), ("tanh", 2, 1200), ("relu", 3, 100), ("tanh", 4, 37), ("relu", 1, 16)])
+def test_tail_activation_pool_kernels_match_pytorch(seldq, act, pool, T):
+    """csrc/tail.cu (activation + nn.MaxPool1d in one kernel per direction, model.py:214-231) against the two PyTorch
+    modules, forward and backward, including ties (first maximum wins) and a dropped tail (T % pool != 0)."""
+    torch.manual_seed(T)
+    x = torch.randn(2, 24, T, device="cuda")
+    x[:, :, 0:4] = 0.25                          # ties inside the first windows
+    x[0, 0, :8] = -1.0                           # ReLU: an all-negative window
+    mods = (torch.nn.ReLU() if act == "relu" else torch.nn.Tanh(), torch.nn.MaxPool1d(pool))
+    gy = torch.randn(2, 24, T // pool, device="cuda")
+    xa = x.clone().requires_grad_(True)
+    ya = seldq.functional.act_pool1d(xa, *mods)
+    assert type(ya.grad_fn).__name__.startswith("_ActPool1d")
+    ya.backward(gy)
+    xb = x.clone().requires_grad_(True)
+    yb = mods[1](mods[0](xb))
+    yb.backward(gy)
+    torch.cuda.synchronize()
+    assert torch.allclose(ya, yb, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(xa.grad, xb.grad, rtol=1e-5, atol=1e-7)
