@@ -313,6 +313,22 @@ int seldq_stft_magphase(const float* x, int32_t n_batch, int32_t n_ch, int64_t n
                         int32_t nperseg, int32_t noverlap, int32_t cut_dc, int32_t output_phase,
                         int32_t cut_last, float* out, void* stream);
 
+/* The same front end with the steps train.py runs around it fused in:
+ *   input_int16   x is int16 PCM (value / 32768) instead of float32: half the bytes read
+ *   mean, inv_std the data-set normalisation of train.py:374-408, per plane (0 magnitude, 1 phase):
+ *                 out = (feature - mean) * inv_std   ({0, 0} and {1, 1}: none)
+ *   stats         when not NULL: sum and sum of squares of the UN-normalised features per plane are added to
+ *                 stats[2 plane], stats[2 plane + 1] (doubles, zeroed by the caller) -- what np.mean / np.std of
+ *                 train.py reduce over the stored array; with out == NULL the pass only gathers them (no store) */
+typedef struct {
+  int32_t input_int16;
+  float mean[2], inv_std[2];
+  double* stats;
+} seldq_stft_options_t;
+int seldq_stft_features(const void* x, int32_t n_batch, int32_t n_ch, int64_t n_samples, int32_t nperseg,
+                        int32_t noverlap, int32_t cut_dc, int32_t output_phase, int32_t cut_last,
+                        const seldq_stft_options_t* opt, float* out, void* stream);
+
 /* TC_Block tail, model.py:210-231: activation followed by nn.MaxPool1d(pool) (stride = pool, floor mode) in one kernel
  * per direction.  act: SELDQ_ACT_RELU (relu1 / relu2 + maxpool1 / maxpool2) or SELDQ_ACT_TANH (tanh + maxpool3).
  * x: float32 (rows = N * C, t); y, gy: (rows, t / pool); gx: (rows, t).  The backward pass re-derives the arg-max

@@ -61,6 +61,12 @@ class AttentionDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("batch", "heads", "seq", "head_dim")]
 
 
+class StftOptions(ctypes.Structure):
+    """seldq_stft_options_t (include/seldq.h)."""
+    _fields_ = [("input_int16", ctypes.c_int32), ("mean", ctypes.c_float * 2), ("inv_std", ctypes.c_float * 2),
+                ("stats", ctypes.c_void_p)]
+
+
 class LinearDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("algebra", "precision", "rows", "in_features", "out_features")]
 
@@ -130,6 +136,9 @@ _PROTOS = {
                                           ctypes.c_size_t, _P]),
     "seldq_linear_wgrad": (ctypes.c_int, [ctypes.POINTER(LinearDesc), _P, _P, ctypes.POINTER(_P), _P,
                                           ctypes.c_int32, _P, ctypes.c_size_t, _P]),
+    "seldq_stft_features": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.POINTER(StftOptions), _P, _P]),
     "seldq_act_pool1d_fwd": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "seldq_act_pool1d_bwd": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                             _P, _P]),

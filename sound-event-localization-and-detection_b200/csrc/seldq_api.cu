@@ -780,5 +780,24 @@ extern "C" int seldq_stft_magphase(const float* x, int32_t n_batch, int32_t n_ch
   if ((rc = cuda_ready())) return rc;
   p.x = x; p.out = out; p.n_samples = n_samples; p.n_ch = n_ch; p.hop = nperseg - noverlap;
   p.bin0 = cut_dc ? 1 : 0; p.output_phase = output_phase ? 1 : 0;
+  p.norm_mul[0] = p.norm_mul[1] = 1.f;
+  return launch_stft(p, n_batch * n_ch, (cudaStream_t)stream);
+}
+
+extern "C" int seldq_stft_features(const void* x, int32_t n_batch, int32_t n_ch, int64_t n_samples, int32_t nperseg,
+                                   int32_t noverlap, int32_t cut_dc, int32_t output_phase, int32_t cut_last,
+                                   const seldq_stft_options_t* opt, float* out, void* stream) {
+  if (!x || !opt || (!out && !opt->stats) || n_batch <= 0 || n_ch <= 0)
+    return fail(SELDQ_ERR_INVALID, "seldq_stft_features: bad arguments");
+  stft::Params p{};
+  int rc = stft_shape(n_samples, nperseg, noverlap, cut_dc, cut_last, &p.n_bins, &p.n_frames);
+  if (rc) return rc;
+  if ((rc = cuda_ready())) return rc;
+  if (opt->input_int16) p.x16 = reinterpret_cast<const short*>(x);
+  else p.x = reinterpret_cast<const float*>(x);
+  p.out = out; p.n_samples = n_samples; p.n_ch = n_ch; p.hop = nperseg - noverlap;
+  p.bin0 = cut_dc ? 1 : 0; p.output_phase = output_phase ? 1 : 0;
+  for (int k = 0; k < 2; ++k) { p.norm_sub[k] = opt->mean[k]; p.norm_mul[k] = opt->inv_std[k]; }
+  p.stats = opt->stats;
   return launch_stft(p, n_batch * n_ch, (cudaStream_t)stream);
 }

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(NT, 1) stft_magphase_kernel(const __grid_const
   init_tables(s, threadIdx.x);
   __syncthreads();
   Thread th;
+  Stats acc = {0.f, 0.f, 0.f, 0.f};
   int buf = 0;
   long long batch = blockIdx.x;
   int signal = 0, t0 = 0;
@@ -38,7 +39,23 @@ __global__ void __launch_bounds__(NT, 1) stft_magphase_kernel(const __grid_const
       batch_decode(p, next, &signal, &t0);
       phase_a_load(p, th, threadIdx.x, signal, t0);
     }
-    phase_d(p, s, threadIdx.x, cur_signal, cur_t0, buf);
+    phase_d(p, s, acc, threadIdx.x, cur_signal, cur_t0, buf);
+  }
+  if (p.stats != nullptr) {
+    // feature statistics (sum, sum of squares per plane): warp shuffle, then one double atomicAdd per warp and quantity
+    const int planes = p.output_phase ? 2 : 1;
+    for (int pl = 0; pl < planes; ++pl) {
+      float a = pl == 0 ? acc.mag1 : acc.ph1, b = pl == 0 ? acc.mag2 : acc.ph2;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(p.stats + 2 * pl, (double)a);
+        atomicAdd(p.stats + 2 * pl + 1, (double)b);
+      }
+    }
   }
 }
 

@@ -18,6 +18,12 @@
 // batch i + 1 hides behind the stores of batch i.
 //
 // Phases are __host__ __device__ so tests/host_emul can execute them on the CPU.
+//
+// Tried and measured in round 2 (tools/kernel_bench.py, profiles/r2r_stft_*.json): the same pipeline with complex
+// numbers as float2 and the packed fp32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: half the ALU instructions of the
+// butterflies) needs the twiddles as two pre-arranged pairs each, i.e. twice the shared-memory loads, and came out at
+// 73.7 us per clip against 63.5 us for this scalar form -- the kernel is bound by its total instruction issue
+// (ALU + LDS), not by the ALU alone.
 #pragma once
 #include <cmath>
 #include <vector_types.h>
@@ -34,8 +40,9 @@ constexpr int NT = FRB * TPF;    // 512 threads
 constexpr int MAXBINS = NFFT / 2 + 1;
 
 struct Params {
-  const float* x;       // (n_signals, n_samples)
-  float* out;           // (n_batch, planes*n_ch, n_bins, n_frames)
+  const float* x;       // (n_signals, n_samples) float32 ...
+  const short* x16;     // ... or, when not null, int16 PCM (scaled by 1 / 32768 on load: half the input bytes)
+  float* out;           // (n_batch, planes*n_ch, n_bins, n_frames); may be null with `stats` (statistics pass only)
   long long n_samples;
   int n_ch;             // signals per batch item
   int hop;
@@ -45,6 +52,12 @@ struct Params {
   int output_phase;
   int groups;           // ceil(n_frames / FRB)
   long long total;      // n_signals * groups
+  // dataset normalisation fused into the store (train.py:374-408): out = (v - norm_sub[plane]) * norm_mul[plane]
+  // (plane 0 = magnitude, 1 = phase; sub = mean, mul = 1 / std; 0 and 1 leave the features as they are)
+  float norm_sub[2], norm_mul[2];
+  // when not null: sum and sum of squares of the (un-normalised) features per plane are ADDED to
+  // stats[2 * plane], stats[2 * plane + 1] -- the reduction train.py runs with np.mean / np.std over the stored array
+  double* stats;
 };
 
 struct Shared {
@@ -57,6 +70,11 @@ struct Shared {
 
 struct Thread {
   float re[16], im[16];
+};
+// running feature statistics of a thread (Params::stats): separate scalars -- a dynamically indexed member would
+// send the whole register-resident Thread to local memory
+struct Stats {
+  float mag1, mag2, ph1, ph2;
 };
 
 SELDQ_HD void sincospi_f(float x, float* sn, float* cs) {
@@ -151,8 +169,27 @@ SELDQ_HD void batch_decode(const Params& p, long long batch, int* signal, int* t
 SELDQ_HD void phase_a_load(const Params& p, Thread& th, int tid, int signal, int t0) {
   const int f = tid >> 4, j = tid & 15;
   const long long g0 = (long long)(t0 + f) * p.hop - NFFT / 2;
-  const float* src = p.x + (long long)signal * p.n_samples;
   const bool interior = g0 >= 0 && g0 + NFFT <= p.n_samples;
+  if (p.x16 != nullptr) {            // int16 PCM ingest
+    const short* s16 = p.x16 + (long long)signal * p.n_samples;
+    const float sc = 1.0f / 32768.0f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const long long g = g0 + 2 * (j + 16 * r);
+#if defined(__CUDA_ARCH__)
+      if (interior && ((reinterpret_cast<unsigned long long>(s16 + g0) & 3ull) == 0)) {
+        const short2 v = __ldg(reinterpret_cast<const short2*>(s16 + g0) + (j + 16 * r));
+        th.re[r] = (float)v.x * sc;
+        th.im[r] = (float)v.y * sc;
+        continue;
+      }
+#endif
+      th.re[r] = (interior || (g >= 0 && g < p.n_samples)) ? (float)s16[g] * sc : 0.f;
+      th.im[r] = (interior || (g + 1 >= 0 && g + 1 < p.n_samples)) ? (float)s16[g + 1] * sc : 0.f;
+    }
+    return;
+  }
+  const float* src = p.x + (long long)signal * p.n_samples;
 #if defined(__CUDA_ARCH__)
   if (interior && ((reinterpret_cast<unsigned long long>(src + g0) & 7ull) == 0)) {
 #pragma unroll
@@ -239,17 +276,33 @@ SELDQ_HD void phase_c(const Params& p, Shared& s, const Thread& th, int tid, int
   if (j == 0) emit_bin(p, s, buf, f, 256 - p.bin0, th.re[0] - th.im[0], 0.f);     // Nyquist bin
 }
 
-// rows of FRB consecutive frames; warp w takes rows w, w + 16, ...
-SELDQ_HD void phase_d(const Params& p, const Shared& s, int tid, int signal, int t0, int buf = 0) {
+// rows of FRB consecutive frames; warp w takes rows w, w + 16, ...; the dataset normalisation is applied on the way
+// out and the running statistics of the un-normalised features are kept per thread
+SELDQ_HD void phase_d(const Params& p, const Shared& s, Stats& st, int tid, int signal, int t0, int buf = 0) {
   const int b = signal / p.n_ch, c = signal - b * p.n_ch;
   const int planes = p.output_phase ? 2 : 1;
   const int warp = tid >> 5, lane = tid & 31;
   const int t = t0 + lane;
   if (t >= p.n_frames) return;
+  if (p.stats == nullptr && p.norm_sub[0] == 0.f && p.norm_mul[0] == 1.f && p.norm_sub[1] == 0.f && p.norm_mul[1] == 1.f) {
+    for (int row = warp; row < planes * p.n_bins; row += NT / 32) {      // plain features (spectrum_fast)
+      const int plane = row >= p.n_bins ? 1 : 0, kb = row - plane * p.n_bins;
+      float* dst = p.out + ((long long)(b * planes * p.n_ch + plane * p.n_ch + c) * p.n_bins + kb) * p.n_frames;
+      dst[t] = s.tile[buf][plane][kb][lane];
+    }
+    return;
+  }
   for (int row = warp; row < planes * p.n_bins; row += NT / 32) {
     const int plane = row >= p.n_bins ? 1 : 0, kb = row - plane * p.n_bins;
-    float* dst = p.out + ((long long)(b * planes * p.n_ch + plane * p.n_ch + c) * p.n_bins + kb) * p.n_frames;
-    dst[t] = s.tile[buf][plane][kb][lane];
+    const float v = s.tile[buf][plane][kb][lane];
+    if (p.stats != nullptr) {
+      if (plane == 0) { st.mag1 += v; st.mag2 = fmaf(v, v, st.mag2); }
+      else { st.ph1 += v; st.ph2 = fmaf(v, v, st.ph2); }
+    }
+    if (p.out != nullptr) {
+      float* dst = p.out + ((long long)(b * planes * p.n_ch + plane * p.n_ch + c) * p.n_bins + kb) * p.n_frames;
+      dst[t] = (v - p.norm_sub[plane]) * p.norm_mul[plane];
+    }
   }
 }
 

@@ -638,3 +638,49 @@ def stft_magphase(x, nperseg=512, noverlap=128, cut_dc=True, output_phase=True, 
             L.seldq_stft_magphase(xb.data_ptr(), B, C, n, nperseg, noverlap, int(cut_dc), int(output_phase),
                                   int(cut_last_timeframe), out.data_ptr(), _stream())))
     return out if batched else out[0]
+
+
+def stft_features(x, nperseg=512, noverlap=128, cut_dc=True, output_phase=True, cut_last_timeframe=True, mean_std=None,
+                  stats_only=False):
+    """The front end with train.py's surrounding steps fused in (include/seldq.h, seldq_stft_features).
+    x: (B, C, n) CUDA tensor, float32 or int16 PCM.  mean_std: ((mean_mag, std_mag), (mean_phase, std_phase)) or
+    ((mean_mag, std_mag),): the data-set normalisation of train.py:374-408 applied on the way out.
+    stats_only=True: nothing is stored; returns a (2, 2) float64 tensor [plane][sum, sum of squares] of the features
+    (feature_mean_std turns it into the mean / population std train.py computes with np.mean / np.std)."""
+    import ctypes
+    L = _lib.lib()
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 3 and x.dtype in (torch.float32, torch.int16)):
+        raise TypeError("stft_features expects a (batch, channels, samples) CUDA tensor of float32 or int16")
+    x = x.contiguous()
+    B, C, n = x.shape
+    nb, nf = ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(L.seldq_stft_shape(n, nperseg, noverlap, int(cut_dc), int(cut_last_timeframe), ctypes.byref(nb),
+                                  ctypes.byref(nf)))
+    planes = 2 if output_phase else 1
+    opt = _lib.StftOptions()
+    opt.input_int16 = 1 if x.dtype == torch.int16 else 0
+    for k in range(2):
+        opt.mean[k], opt.inv_std[k] = 0.0, 1.0
+    if mean_std is not None:
+        for k, (mu, sd) in enumerate(mean_std):
+            opt.mean[k], opt.inv_std[k] = float(mu), 1.0 / float(sd)
+    stats = out = None
+    if stats_only:
+        stats = torch.zeros((2, 2), dtype=torch.float64, device=x.device)
+        opt.stats = stats.data_ptr()
+    else:
+        out = torch.empty((B, planes * C, nb.value, nf.value), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _timed("stft_magphase_kernel", 0.0, 1, lambda: _lib.check(
+            L.seldq_stft_features(x.data_ptr(), B, C, n, nperseg, noverlap, int(cut_dc), int(output_phase),
+                                  int(cut_last_timeframe), ctypes.byref(opt), _ptr(out), _stream())))
+    return stats if stats_only else out
+
+
+def feature_mean_std(stats, count_per_plane):
+    """(sum, sum of squares) per plane -> ((mean, std), ...) with the population std (np.std default, train.py:379-380)."""
+    out = []
+    for s1, s2 in stats.cpu().tolist():
+        mu = s1 / count_per_plane
+        out.append((mu, max(s2 / count_per_plane - mu * mu, 0.0) ** 0.5))
+    return tuple(out)

@@ -357,8 +357,10 @@ int emul_stft(const float* x, int n_batch, int n_ch, long long n_samples, int np
   p.n_frames = n_frames; p.bin0 = cut_dc ? 1 : 0; p.n_bins = n_bins; p.output_phase = output_phase;
   p.groups = (n_frames + stft::FRB - 1) / stft::FRB;
   p.total = (long long)n_batch * n_ch * p.groups;
+  p.norm_mul[0] = p.norm_mul[1] = 1.f;
   stft::Shared* sh = new stft::Shared;
   std::vector<stft::Thread> th(stft::NT);
+  stft::Stats acc = {0.f, 0.f, 0.f, 0.f};
   for (int t = 0; t < stft::NT; ++t) stft::init_tables(*sh, t);
   for (long long batch = 0; batch < p.total; ++batch) {
     int signal, t0;
@@ -367,7 +369,7 @@ int emul_stft(const float* x, int n_batch, int n_ch, long long n_samples, int np
     for (int t = 0; t < stft::NT; ++t) stft::phase_b(*sh, th[t], t);
     for (int t = 0; t < stft::NT; ++t) stft::phase_b2(*sh, th[t], t);
     for (int t = 0; t < stft::NT; ++t) stft::phase_c(p, *sh, th[t], t);
-    for (int t = 0; t < stft::NT; ++t) stft::phase_d(p, *sh, t, signal, t0);
+    for (int t = 0; t < stft::NT; ++t) stft::phase_d(p, *sh, acc, t, signal, t0);
   }
   delete sh;
   return 0;
