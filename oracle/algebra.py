@@ -181,6 +181,22 @@ def qconv_backward(x, weights, gy, stride=1, padding=0, dilation=1, algebra="Q")
     return gx, compact_grads(gW, algebra, O, I), gb
 
 
+def qconv_transpose(x, weights, bias=None, padding=0, dilation=1):
+    """quaternion_transpose_conv, stride 1 (quaternion_ops.py:149-172): F.conv_transpose of the expanded
+    (in, out, k...) weight, whose blocks follow the convolution's table -- i.e. the input gradient of the convolution
+    with the same compact tensors read as (out', in') = (in, out), evaluated at gy = x."""
+    x = np.asarray(x, np.float64)
+    nd = x.ndim - 2
+    pad, dil = _pair(padding) if nd == 2 else (padding,), _pair(dilation) if nd == 2 else (dilation,)
+    ks = weights[0].shape[2:]
+    out_sp = tuple(x.shape[2 + i] + (ks[i] - 1) * dil[i] - 2 * pad[i] for i in range(nd))
+    dummy = np.zeros((x.shape[0], 4 * weights[0].shape[1]) + out_sp)
+    gx, _, _ = qconv_backward(dummy, weights, x, 1, padding, dilation, "Q")
+    if bias is not None:
+        gx = gx + np.asarray(bias, np.float64).reshape((1, -1) + (1,) * nd)
+    return gx
+
+
 def qlinear(x, weights, bias=None, algebra="Q"):
     """quaternion_linear (quaternion_ops.py:299-327) for algebra='Q';
     dual_quaternion_linear (dual_quaternion_ops.py:156-203) for algebra='DQ_LINEAR'."""

@@ -63,6 +63,32 @@ def conv_case(ns, name, algebra, ndim, N, I, O, spatial, k, stride, padding, dil
     print(name, tuple(x.shape), "->", tuple(y.shape))
 
 
+def convT_case(ns, name, ndim, N, I, O, spatial, k, padding, dilation, bias, seed):
+    """quaternion_transpose_conv (quaternion_ops.py:149-172), stride 1: weights are (in / 4, out / 4, k...)."""
+    rng = np.random.default_rng(seed)
+    kshape = (k,) * ndim
+    ws = [f32(rng.standard_normal((I, O) + kshape) * 0.2) for _ in range(4)]
+    x = f32(rng.standard_normal((N, 4 * I) + tuple(spatial)))
+    b = f32(rng.standard_normal(4 * O)) if bias else None
+    tx = torch.tensor(x, requires_grad=True)
+    tw = [torch.tensor(w, requires_grad=True) for w in ws]
+    tb = torch.tensor(b, requires_grad=True) if bias else None
+    y = ns.q_ops.quaternion_transpose_conv(tx, *tw, tb, 1, padding, 0, 1, dilation)
+    gy = f32(rng.standard_normal(tuple(y.shape)))
+    y.backward(torch.tensor(gy))
+    d = dict(x=x, gy=gy, y=y.detach().numpy(), gx=tx.grad.numpy())
+    for i, (w, t) in enumerate(zip(ws, tw)):
+        d["w%d" % i] = w
+        d["gw%d" % i] = t.grad.numpy()
+    if bias:
+        d["b"] = b
+        d["gb"] = tb.grad.numpy()
+    meta = dict(kind="convT", algebra="Q", ndim=ndim, stride=1, padding=padding, dilation=dilation, bias=bool(bias),
+                seed=seed, source="quaternion_ops.py:149-172")
+    _save(name, meta, d)
+    print(name, tuple(x.shape), "->", tuple(y.shape))
+
+
 def linear_case(ns, name, algebra, rows, I, O, bias, seed, use_function=False):
     rng = np.random.default_rng(seed)
     nc = {"Q": 4, "DQ": 8}[algebra]
@@ -289,6 +315,12 @@ def round2_cases(ns):
     model whose first block has the real 16 -> 192 widths, and a reduced real-valued model (config
     SERVER_SELD-TCN-S1-PHI_8ch.txt: nn.Conv* layers)."""
     conv_case(ns, "conv2d_dq_first16", "DQ", 2, 1, 2, 24, (16, 136), 3, 1, 1, 1, False, 22)
+    if "--convT" in sys.argv or True:
+        convT_case(ns, "convT1d_q_k3_d2", 1, 2, 16, 8, (72,), 3, 1, 2, True, 23)
+        convT_case(ns, "convT2d_q_3x3", 2, 1, 8, 16, (6, 40), 3, 1, 1, False, 24)
+        convT_case(ns, "convT1d_q_small", 1, 2, 3, 5, (31,), 3, 0, 1, True, 25)
+    if "--convT" in sys.argv:
+        return
     tiny = dict(ref_import.COMMON)
     tiny.update(input_channels=8, freq_dim=128, domain="DQ", domain_classifier="DQ",
                 cnn_filters=[16, 16, 16], G=16, U=16, V=[16, 16], fc_layers=[16],

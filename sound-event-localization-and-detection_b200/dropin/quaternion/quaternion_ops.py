@@ -95,7 +95,13 @@ def _out_of_scope(name):
     return fn
 
 
-quaternion_transpose_conv = _out_of_scope("quaternion_transpose_conv")
+def quaternion_transpose_conv(input, r_weight, i_weight, j_weight, k_weight, bias, stride, padding, output_padding, groups,
+                              dilatation):
+    """quaternion_ops.py:149-172 on the convolution kernels (stride 1, groups 1; functional.block_conv_transpose)."""
+    return _F.block_conv_transpose(input, (r_weight, i_weight, j_weight, k_weight), bias, stride, padding, output_padding,
+                                   groups, dilatation, _ALG_Q)
+
+
 quaternion_conv_rotation = _out_of_scope("quaternion_conv_rotation")
 quaternion_transpose_conv_rotation = _out_of_scope("quaternion_transpose_conv_rotation")
 quaternion_linear_rotation = _out_of_scope("quaternion_linear_rotation")

@@ -398,6 +398,98 @@ class _BlockConv(torch.autograd.Function):
         return (gx, gb, None, None, None, None, None) + tuple(gws)
 
 
+class _BlockConvTranspose(torch.autograd.Function):
+    """y = conv_transpose(x, expand(weights)) + bias for stride 1 (quaternion_ops.py:149-172).
+    The expanded (in, out, k...) weight of the transposed convolution has the block table of the convolution's, so
+    the operator IS the input-gradient pass of the convolution whose compact weights are these same tensors read as
+    (out', in') = (in, out): forward = seldq_conv_dgrad, gradient w.r.t. x = seldq_conv_fwd, weight gradient =
+    seldq_conv_wgrad with the roles of the two activations swapped.  No new kernel."""
+
+    @staticmethod
+    def forward(ctx, x, bias, padding, dilation, algebra, prec, *weights):
+        import ctypes
+        L = _lib.lib()
+        nc = _NCOMP[algebra]
+        _require_cuda_f32(x, "input")
+        for w in weights:
+            _require_cuda_f32(w, "weight")
+        x = x.contiguous()
+        weights = tuple(w.contiguous() for w in weights)
+        w0 = weights[0]
+        nd = x.dim() - 2
+        if w0.shape[0] * nc != x.shape[1]:
+            raise RuntimeError("Given transposed=1, weight of size %s (x%d components), expected input%s to have %d channels, "
+                               "but got %d channels instead" % (list(w0.shape), nc, list(x.shape), w0.shape[0] * nc, x.shape[1]))
+        pad = (0, _pair(padding)[1]) if nd == 1 else _pair(padding)
+        dil = (1, _pair(dilation)[1]) if nd == 1 else _pair(dilation)
+        ks = (1, w0.shape[2]) if nd == 1 else tuple(w0.shape[2:])
+        cout = w0.shape[1] * nc
+        in_sp = (1, x.shape[2]) if nd == 1 else tuple(x.shape[2:])
+        out_sp = tuple(in_sp[i] + (ks[i] - 1) * dil[i] - 2 * pad[i] for i in range(2))
+        if min(out_sp) < 1:
+            raise RuntimeError("transposed convolution: output size is too small")
+        # the convolution this operator is the input gradient of: (N, cout, out_sp) -> (N, cin, in_sp)
+        desc = _lib.ConvDesc(algebra, prec, nd, x.shape[0], cout, x.shape[1], out_sp[0], out_sp[1], ks[0], ks[1], 1, 1,
+                             pad[0], pad[1], dil[0], dil[1])
+        y = torch.empty((x.shape[0], cout) + (out_sp[1:] if nd == 1 else out_sp), dtype=torch.float32, device=x.device)
+        wp = _lib.ptr_array([w.data_ptr() for w in weights])
+        with torch.cuda.device(x.device):
+            work = torch.empty(max(1, L.seldq_conv_workspace_bytes(ctypes.byref(desc), PASS_DGRAD)), dtype=torch.uint8,
+                               device=x.device)
+            _timed("qconv_cl_fprop_kernel" if prec == PREC_BF16 else "conv_simt_kernel", 0.0, 1, lambda: _lib.check(
+                L.seldq_conv_dgrad(ctypes.byref(desc), x.data_ptr(), None, wp, None, y.data_ptr(), work.data_ptr(),
+                                   work.numel(), _stream())))
+            if bias is not None:
+                y += bias.view((1, -1) + (1,) * nd)
+        ctx.desc, ctx.nd, ctx.has_bias = desc, nd, bias is not None
+        ctx.save_for_backward(x, *weights)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        import ctypes
+        L = _lib.lib()
+        desc = ctx.desc
+        x, *weights = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gb = None
+        gws = [None] * len(weights)
+        wp = _lib.ptr_array([w.data_ptr() for w in weights])
+        with torch.cuda.device(gy.device):
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                work = torch.empty(max(1, L.seldq_conv_workspace_bytes(ctypes.byref(desc), PASS_FWD)), dtype=torch.uint8,
+                                   device=gy.device)
+                _lib.check(L.seldq_conv_fwd(ctypes.byref(desc), gy.data_ptr(), None, wp, None, None, gx.data_ptr(),
+                                            work.data_ptr(), work.numel(), _stream()))
+            if any(ctx.needs_input_grad[6:]):
+                gws = [torch.empty_like(w) for w in weights]
+                gp = _lib.ptr_array([g.data_ptr() for g in gws])
+                work = torch.empty(max(1, L.seldq_conv_workspace_bytes(ctypes.byref(desc), PASS_WGRAD)), dtype=torch.uint8,
+                                   device=gy.device)
+                # <conv_transpose(x; W), gy> = <x, conv(gy; W)>: the convolution's "input" is gy, its "output gradient" x
+                _lib.check(L.seldq_conv_wgrad(ctypes.byref(desc), gy.data_ptr(), None, x.data_ptr(), None, gp, None, 0,
+                                              work.data_ptr(), work.numel(), _stream()))
+            if ctx.has_bias and ctx.needs_input_grad[1]:
+                gb = gy.sum(dim=[0] + list(range(2, gy.dim())))
+        return (gx, gb, None, None, None, None) + tuple(gws)
+
+
+def block_conv_transpose(x, weights, bias, stride, padding, output_padding, groups, dilation, algebra, prec=None):
+    """quaternion_transpose_conv (quaternion_ops.py:149-172) on the convolution kernels: stride 1, groups 1."""
+    if x.dim() not in (3, 4):
+        if x.dim() == 5:
+            raise NotImplementedError("seldq: 3-d transposed convolution (5-d input) is not implemented")
+        raise Exception("The convolutional input is either 3, 4 or 5 dimensions. input.dim = " + str(x.dim()))
+    if _pair(stride) != (1, 1) or _pair(output_padding) != (0, 0) or groups != 1:
+        raise NotImplementedError("seldq: transposed convolution is implemented for stride 1, output_padding 0, groups 1")
+    prec = _PRECISION if prec is None else prec
+    nc = _NCOMP[algebra]
+    if prec == PREC_BF16 and min(weights[0].shape[0], weights[0].shape[1]) < 8:
+        prec = PREC_FP32          # narrow layers: the tensor-core path's dense mode serves forward convolutions only
+    return _BlockConvTranspose.apply(x, bias, padding, dilation, algebra, prec, *weights)
+
+
 class _BlockLinear(torch.autograd.Function):
     """y = x @ expand(weights) + bias  (quaternion_ops.py:299-327 / :392-464,
     dual_quaternion_ops.py:156-203).  x is (rows, in)."""

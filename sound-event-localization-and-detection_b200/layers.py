@@ -256,8 +256,42 @@ class DualQuaternionLinear(_BlockLinearBase):
 
 
 class QuaternionTransposeConv(Module):
-    """quaternion_layers.py:19-98 -- never instantiated by model.py."""
+    """quaternion_layers.py:19-98 (never instantiated by model.py): same constructor, parameters
+    (in / 4, out / 4, k...) and initialisation; forward = quaternion_transpose_conv on the convolution kernels
+    (functional.block_conv_transpose: stride 1; the rotation variant is not implemented)."""
 
-    def __init__(self, *args, **kwargs):
+    def __init__(self, in_channels, out_channels, kernel_size, stride, dilatation=1, padding=0, output_padding=0, groups=1,
+                 bias=True, init_criterion='glorot', weight_init='quaternion', seed=None, operation='convolution2d',
+                 rotation=False, quaternion_format=False):
         super(QuaternionTransposeConv, self).__init__()
-        raise NotImplementedError("QuaternionTransposeConv is outside the SELD hot path (SURVEY.md 8f, N4)")
+        self.in_channels = in_channels // 4
+        self.out_channels = out_channels // 4
+        self.stride, self.padding, self.output_padding = stride, padding, output_padding
+        self.groups, self.dilatation = groups, dilatation
+        self.init_criterion, self.weight_init = init_criterion, weight_init
+        self.seed = seed if seed is not None else np.random.randint(0, 1234)
+        self.rng = RandomState(self.seed)
+        self.operation, self.rotation, self.quaternion_format = operation, rotation, quaternion_format
+        self.winit = _Q_INITS[self.weight_init]
+        # (out, in) swapped as in quaternion_layers.py:49-50: the weights are (in / 4, out / 4, k...)
+        self.kernel_size, self.w_shape = I.get_kernel_and_weight_shape(self.operation, self.out_channels, self.in_channels,
+                                                                       kernel_size)
+        for name in _Q_NAMES:
+            setattr(self, name, Parameter(torch.Tensor(*self.w_shape)))
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        I.affect_init_conv(tuple(getattr(self, n) for n in _Q_NAMES), self.kernel_size, self.winit, self.rng,
+                           self.init_criterion)
+        if self.bias is not None:
+            self.bias.data.zero_()
+
+    def forward(self, input):
+        if self.rotation:
+            raise NotImplementedError("quaternion_transpose_conv_rotation is not implemented (SURVEY.md 8f N4)")
+        return F.block_conv_transpose(input, tuple(getattr(self, n) for n in _Q_NAMES), self.bias, self.stride,
+                                      self.padding, self.output_padding, self.groups, self.dilatation, ALG_Q)

@@ -617,3 +617,25 @@ def test_tail_activation_pool_kernels_match_pytorch(seldq, act, pool, T):
     torch.cuda.synchronize()
     assert torch.allclose(ya, yb, rtol=1e-6, atol=1e-7)
     assert torch.allclose(xa.grad, xb.grad, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["convT1d_q_k3_d2", "convT2d_q_3x3", "convT1d_q_small"])
+def test_transposed_conv_matches_reference_fixture(seldq, name, prec):
+    """quaternion_transpose_conv / QuaternionTransposeConv (quaternion_ops.py:149-172, quaternion_layers.py:19-98;
+    SURVEY.md 8f N4) on the convolution kernels: forward = the dgrad pass, backward = forward + wgrad passes."""
+    meta, d = load_golden(name)
+    x = cuda(d["x"]).requires_grad_(True)
+    ws = [cuda(d["w%d" % i]).requires_grad_(True) for i in range(4)]
+    b = cuda(d["b"]).requires_grad_(True) if meta["bias"] else None
+    with seldq.precision(prec):
+        y = seldq.functional.block_conv_transpose(x, ws, b, 1, meta["padding"], 0, 1, meta["dilation"], seldq._lib.ALG_Q)
+        y.backward(cuda(d["gy"]))
+    torch.cuda.synchronize()
+    tol = TOL[prec]
+    errs = {"y": A.rel_err(y.detach().cpu().numpy(), d["y"]), "gx": A.rel_err(x.grad.cpu().numpy(), d["gx"])}
+    for i in range(4):
+        errs["gw%d" % i] = A.rel_err(ws[i].grad.cpu().numpy(), d["gw%d" % i])
+    if meta["bias"]:
+        errs["gb"] = A.rel_err(b.grad.cpu().numpy(), d["gb"])
+    assert all(v < tol for v in errs.values()), (name, prec, errs)

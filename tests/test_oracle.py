@@ -155,3 +155,12 @@ def test_seld_metric_restatement_matches_golden_scores(name):
     meta, d = load_golden(name)
     got = M.seld_scores(d["sed"], d["doa"], d["target"], num_frames=d["sed"].shape[1])
     assert got == tuple(float(v) for v in d["seld_scores"])
+
+
+@pytest.mark.parametrize("name", ["convT1d_q_k3_d2", "convT2d_q_3x3", "convT1d_q_small"])
+def test_oracle_transposed_conv_matches_reference_fixture(name):
+    """quaternion_transpose_conv (quaternion_ops.py:149-172) = the convolution's input-gradient pass."""
+    meta, d = load_golden(name)
+    ws = [d["w%d" % i].astype(np.float64) for i in range(4)]
+    y = A.qconv_transpose(d["x"], ws, d["b"] if meta["bias"] else None, meta["padding"], meta["dilation"])
+    assert A.rel_err(y, d["y"]) < 1e-12
