@@ -339,6 +339,14 @@ int seldq_act_pool1d_fwd(const float* x, int64_t rows, int32_t t, int32_t pool, 
 int seldq_act_pool1d_bwd(const float* x, const float* y, const float* gy, int64_t rows, int32_t t, int32_t pool,
                          int32_t act, float* gx, void* stream);
 
+/* Evaluation path: gen_submission_list_task2 (utility_functions.py:184-210) for a batch of clips.
+ * sed: float32 (clips, frames, classes * overlaps), doa: float32 (clips, frames, classes * overlaps * 3).  A cell whose
+ * SED output rounds to non-zero (round half to even, as np.round) yields the row
+ * [frame, class, x * max_loc, y * max_loc, z * max_loc, overlap] (6 floats); rows: (clips, frames * classes * overlaps, 6)
+ * capacity, filled per clip in the reference's order (frame, then cell); counts[clip] = rows written. */
+int seldq_seld_events(const float* sed, const float* doa, int32_t clips, int32_t frames, int32_t classes,
+                      int32_t overlaps, float max_loc, float* rows, int32_t* counts, void* stream);
+
 /* debug: a 64 x uint64 device buffer that CTA 0 of every later tensor-core convolution launch stamps with
  * %globaltimer values at its role hand-offs (tools/fprop_trace.py); NULL switches it off. */
 int seldq_debug_fprop_trace(void* dev_buf);

@@ -13,7 +13,7 @@ from . import _lib
 from . import fused
 from .functional import (attention, block_conv, block_linear, get_precision, precision, set_precision,
                          stft_magphase)
-from .features import spectrum_fast
+from .features import gen_submission_list_task2, spectrum_fast
 from .layers import (DualQuaternionConv, DualQuaternionLinear, QuaternionConv, QuaternionLinear,
                      QuaternionLinearAutograd, QuaternionTransposeConv)
 from .seld_model import ConvTC_Block, MultiHeadAttention, ResBlock, SELD_Model, TC_Block
@@ -48,6 +48,7 @@ def install_dropin(patch_utility_functions=True, fuse_model=True):
         sys.path.insert(0, p)
     if patch_utility_functions and "utility_functions" in sys.modules:
         sys.modules["utility_functions"].spectrum_fast = spectrum_fast
+        sys.modules["utility_functions"].gen_submission_list_task2 = gen_submission_list_task2
     _DROPIN["fuse_model"] = bool(fuse_model)
     if fuse_model:
         _maybe_patch_reference_model()

@@ -6,6 +6,7 @@
 #include "conv_simt.cuh"
 #include "conv_umma.h"
 #include "epilogue.h"
+#include "eval.h"
 #include "geom.h"
 #include "launch.h"
 #include "stft.cuh"
@@ -697,6 +698,15 @@ extern "C" int seldq_act_pool1d_bwd(const float* x, const float* y, const float*
   int rc = cuda_ready();
   if (rc) return rc;
   return launch_act_pool_bwd(x, y, gy, gx, rows, t, pool, act, (cudaStream_t)stream);
+}
+
+// ---- evaluation path -------------------------------------------------------------------------------------------
+extern "C" int seldq_seld_events(const float* sed, const float* doa, int32_t clips, int32_t frames, int32_t classes,
+                                 int32_t overlaps, float max_loc, float* rows, int32_t* counts, void* stream) {
+  if (!sed || !doa || !rows || !counts) return fail(SELDQ_ERR_INVALID, "seldq_seld_events: null pointer");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  return launch_seld_events(sed, doa, clips, frames, classes, overlaps, max_loc, rows, counts, (cudaStream_t)stream);
 }
 
 // ---- attention ------------------------------------------------------------------------------------------------

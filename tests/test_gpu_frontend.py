@@ -49,3 +49,32 @@ def test_statistics_pass_and_fused_normalisation_match_numpy(seldq, phase):
     ref = np.concatenate([(g - g.mean()) / g.std() for g in groups], axis=1)
     assert A.rel_err(out[:, :8], ref[:, :8]) < 1e-4
     assert abs(out[:, :8].mean()) < 1e-4 and abs(out[:, :8].std() - 1.0) < 1e-3
+
+
+def test_device_submission_list_matches_the_reference_scan(seldq):
+    """gen_submission_list_task2 (utility_functions.py:184-210) on the device against the restatement
+    of the reference's triple loop (oracle/seld_metrics.events_per_frame, pinned to the imported reference in
+    tests/test_oracle.py), including cells exactly at the 0.5 threshold (np.round: half to even -> inactive), frames
+    without events, and the DCASE21 scores computed from both lists."""
+    from oracle import seld_metrics as M
+    rng = np.random.default_rng(3)
+    clips, frames = 3, 600
+    sed = rng.random((clips, frames, 42)).astype(np.float32) ** 6          # mostly inactive
+    sed[:, ::7, 5] = 0.5                                                    # exactly at the threshold
+    sed[:, 1::50, :] = 0.0                                                  # frames without events
+    sed[0, 10, 3], sed[0, 10, 4] = 0.9, 0.51
+    doa = (2 * rng.random((clips, frames, 126)) - 1).astype(np.float32)
+    got = seldq.gen_submission_list_task2(torch.from_numpy(sed).cuda(), torch.from_numpy(doa).cuda())
+    assert len(got) == clips
+    for c in range(clips):
+        want = M.events_per_frame(sed[c], doa[c])
+        arr, d = got[c]
+        assert sorted(d) == sorted(want)
+        for fr in want:
+            assert [e[0] for e in d[fr]] == [e[0] for e in want[fr]] and [e[4] for e in d[fr]] == [e[4] for e in want[fr]]
+            assert np.allclose(np.array([e[1:4] for e in d[fr]]), np.array([e[1:4] for e in want[fr]]), rtol=1e-6, atol=1e-7)
+        assert arr.shape == (sum(len(v) for v in want.values()), 5)
+        assert np.all(np.diff(arr[:, 0]) >= 0)
+    # single clip, numpy in: the reference's call signature
+    arr1, d1 = seldq.gen_submission_list_task2(sed[1], doa[1], max_overlaps=3, max_loc_value=2.0)
+    assert sorted(d1) == sorted(M.events_per_frame(sed[1], doa[1]))
