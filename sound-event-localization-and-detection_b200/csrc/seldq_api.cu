@@ -700,6 +700,14 @@ extern "C" int seldq_act_pool1d_bwd(const float* x, const float* y, const float*
   return launch_act_pool_bwd(x, y, gy, gx, rows, t, pool, act, (cudaStream_t)stream);
 }
 
+extern "C" int seldq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                               float b1, float b2, float eps, float* step, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step) return fail(SELDQ_ERR_INVALID, "seldq_adam_step: null pointer");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, b1, b2, eps, step, (cudaStream_t)stream);
+}
+
 // ---- evaluation path -------------------------------------------------------------------------------------------
 extern "C" int seldq_seld_events(const float* sed, const float* doa, int32_t clips, int32_t frames, int32_t classes,
                                  int32_t overlaps, float max_loc, float* rows, int32_t* counts, void* stream) {

@@ -95,3 +95,58 @@ int launch_act_pool_bwd(const float* x, const float* y, const float* gy, float* 
 }
 
 }  // namespace seldq
+
+// ---- optimiser step ------------------------------------------------------------------------------------------------
+// Adam as torch.optim.Adam(lr, betas, eps; no weight decay, no amsgrad) applies it (train.py:502-504), over the
+// trainer's ONE flat parameter / gradient bucket: a single bandwidth-bound pass (7 x 4 bytes per parameter) instead
+// of the multi-tensor kernel's chunked walk.  The step counter lives on the device (float, as PyTorch's capturable
+// Adam keeps it), so the launch can be captured in a CUDA graph; the kernel increments it.
+namespace seldq {
+namespace tail {
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                  float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                  float* __restrict__ step) {
+  const float t = *step + 1.f;
+  // bias corrections as torch/optim/adam.py: step_size = lr / (1 - b1^t), denom = sqrt(v) / sqrt(1 - b2^t) + eps
+  const float bc1 = 1.f - powf(b1, t), bc2s = sqrtf(1.f - powf(b2, t));
+  const float step_size = lr / bc1;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ma[k] = ma[k] + (1.f - b1) * (ga[k] - ma[k]);                 // exp_avg.lerp_(grad, 1 - beta1)
+      va[k] = b2 * va[k] + (1.f - b2) * ga[k] * ga[k];              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      pa[k] -= step_size * (ma[k] / (sqrtf(va[k]) / bc2s + eps));
+    }
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 << 2; i < n; ++i) {
+      m[i] = m[i] + (1.f - b1) * (g[i] - m[i]);
+      v[i] = b2 * v[i] + (1.f - b2) * g[i] * g[i];
+      p[i] -= step_size * (m[i] / (sqrtf(v[i]) / bc2s + eps));
+    }
+}
+// the counter moves in its own one-thread launch BEHIND the update (every block of adam_kernel reads the old value)
+__global__ void adam_count_kernel(float* step) { *step += 1.f; }
+
+}  // namespace tail
+
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float* step,
+                cudaStream_t st) {
+  if (n < 1) return SELDQ_OK;
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return fail(SELDQ_ERR_INVALID, "seldq_adam_step: buffers must be 16-byte aligned");
+  tail::adam_kernel<<<grid_for(n >> 2), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, step);
+  int rc = check_launch("adam_kernel");
+  if (rc) return rc;
+  tail::adam_count_kernel<<<1, 1, 0, st>>>(step);
+  return check_launch("adam_count_kernel");
+}
+
+}  // namespace seldq

@@ -64,6 +64,29 @@ def next_drop_seed(module, device):
     return module._drop_seed
 
 
+_COUNTERS = {}
+
+
+def _bump_counters(bns):
+    """nn.BatchNorm's step counters (num_batches_tracked += 1) of a fused stack in ONE element-wise launch: the
+    counters become 0-dim views of one flat int64 tensor (as the trainer does with parameters and gradients); a
+    multi-tensor launch over 30 one-element tensors cost 13 us.  Rebuilt whenever a counter no longer aliases the flat
+    tensor (model.to(...), load of a different module, ...)."""
+    key = tuple(id(b) for b in bns)
+    flat = _COUNTERS.get(key)
+    ok = flat is not None and flat.numel() == len(bns) and all(
+        b.num_batches_tracked is not None and b.num_batches_tracked.device == flat.device
+        and b.num_batches_tracked.data_ptr() == flat[i].data_ptr() for i, b in enumerate(bns))
+    if not ok:
+        flat = torch.stack([b.num_batches_tracked.detach().reshape(()).to(torch.int64) for b in bns]).contiguous()
+        for i, b in enumerate(bns):
+            b._buffers["num_batches_tracked"] = flat[i]
+        if len(_COUNTERS) > 64:
+            _COUNTERS.clear()
+        _COUNTERS[key] = flat
+    flat.add_(1)
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -264,8 +287,7 @@ def cnn_stack(x, convs, bns, pools, drops, seed):
                          momentum=float(bn.momentum), nw=len(ws), running_mean=bn.running_mean,
                          running_var=bn.running_var, salt=k + 1))
         tensors += list(ws) + [bn.weight, bn.bias]
-    # nn.BatchNorm's step counters: one multi-tensor launch instead of one tiny kernel per layer
-    torch._foreach_add_([bn.num_batches_tracked for bn in bns], 1)
+    _bump_counters(bns)
     return _CnnStack.apply(x, spec, seed, *tensors)
 
 
@@ -648,6 +670,6 @@ def tcn_stack(x, blocks, seed):
             tensors += list(w)
         for bn in bns:
             tensors += [bn.weight, bn.bias]
-            counters.append(bn.num_batches_tracked)
-    torch._foreach_add_(counters, 1)      # one multi-tensor launch for the 30 BatchNorm step counters
+            counters.append(bn)
+    _bump_counters(counters)
     return _TcnStack.apply(x, spec, seed, *tensors)

@@ -94,6 +94,39 @@ class FlatGradBucket(object):
         self.flat.div_(dist.get_world_size(group))
 
 
+class FlatAdam(object):
+    """torch.optim.Adam(lr, betas, eps) -- the reference's optimiser, train.py:502-504 -- over the trainer's one flat
+    CUDA parameter: the update is ONE kernel of this library (seldq_adam_step, csrc/tail.cu) with the step counter on
+    the device, so it can be captured in the step's CUDA graph.  `state` / `param_groups` keep torch.optim's layout
+    (Trainer.optimizer_state_dict splits it per parameter for the reference's checkpoints)."""
+
+    def __init__(self, flat_param, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.flat_param = flat_param
+        self.param_groups = [dict(params=[flat_param], lr=lr, betas=tuple(betas), eps=eps, weight_decay=0, amsgrad=False,
+                                  capturable=True)]
+        self.state = {}
+
+    def _ensure_state(self):
+        st = self.state.setdefault(self.flat_param, {})
+        if "exp_avg" not in st:
+            st["exp_avg"] = torch.zeros_like(self.flat_param.data)
+            st["exp_avg_sq"] = torch.zeros_like(self.flat_param.data)
+        if not torch.is_tensor(st.get("step")) or st["step"].device != self.flat_param.device:
+            st["step"] = torch.as_tensor(float(st.get("step", 0.0)), dtype=torch.float32).to(self.flat_param.device).reshape(())
+        return st
+
+    def step(self):
+        from . import _lib
+        st = self._ensure_state()
+        g = self.param_groups[0]
+        fp = self.flat_param
+        with torch.cuda.device(fp.device):
+            _lib.check(_lib.lib().seldq_adam_step(fp.data.data_ptr(), fp.grad.data_ptr(), st["exp_avg"].data_ptr(),
+                                                  st["exp_avg_sq"].data_ptr(), fp.numel(), float(g["lr"]), float(g["betas"][0]),
+                                                  float(g["betas"][1]), float(g["eps"]), st["step"].data_ptr(),
+                                                  torch.cuda.current_stream().cuda_stream))
+
+
 class Trainer(object):
     def __init__(self, model, lr=1e-4, n_sed=42, group=None, overlap_all_reduce=True):
         self.model = model
@@ -126,7 +159,11 @@ class Trainer(object):
         # Adam with the reference's hyper-parameters (train.py:502-504); fused = one kernel per step,
         # capturable so that the whole step can live in a CUDA graph
         # (element-wise update: one flat parameter is the same arithmetic as one tensor per parameter)
-        self.optimizer = torch.optim.Adam([self.bucket.flat_param], lr=lr, fused=on_cuda, capturable=on_cuda)
+        if on_cuda:
+            self.optimizer = FlatAdam(self.bucket.flat_param, lr=lr)
+            self.optimizer._ensure_state()                 # allocated outside any graph capture
+        else:
+            self.optimizer = torch.optim.Adam([self.bucket.flat_param], lr=lr)
         self._graph = None
 
     def close(self):
@@ -183,7 +220,7 @@ class Trainer(object):
         fp = self.bucket.flat_param
         if not sd.get("state"):
             return
-        st = self.optimizer.state[fp]
+        st = self.optimizer.state.setdefault(fp, {}) if isinstance(self.optimizer, FlatAdam) else self.optimizer.state[fp]
         step = None
         if "exp_avg" not in st:
             st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(fp.data), torch.zeros_like(fp.data)

@@ -639,3 +639,27 @@ def test_transposed_conv_matches_reference_fixture(seldq, name, prec):
     if meta["bias"]:
         errs["gb"] = A.rel_err(b.grad.cpu().numpy(), d["gb"])
     assert all(v < tol for v in errs.values()), (name, prec, errs)
+
+
+def test_own_adam_step_matches_torch_adam(seldq):
+    """seldq_adam_step (csrc/tail.cu) through trainer.FlatAdam against torch.optim.Adam, five steps, same gradients."""
+    import importlib
+    trainer_mod = importlib.import_module(seldq.__name__ + ".trainer")
+    torch.manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n, device="cuda")
+    pa = torch.nn.Parameter(p0.clone())
+    pb = torch.nn.Parameter(p0.clone())
+    pa.grad = torch.zeros_like(pa)
+    opt_a = trainer_mod.FlatAdam(pa, lr=1e-2)
+    opt_b = torch.optim.Adam([pb], lr=1e-2)
+    for k in range(5):
+        g = torch.randn(n, device="cuda") * (0.1 + k)
+        pa.grad.copy_(g)
+        pb.grad = g.clone()
+        opt_a.step()
+        opt_b.step()
+    torch.cuda.synchronize()
+    assert float(opt_a.state[pa]["step"]) == 5.0
+    assert torch.allclose(pa.data, pb.data, rtol=2e-6, atol=2e-7)
+    assert torch.allclose(opt_a.state[pa]["exp_avg_sq"], opt_b.state[pb]["exp_avg_sq"], rtol=1e-5, atol=1e-12)
