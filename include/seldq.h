@@ -350,9 +350,10 @@ int seldq_seld_events(const float* sed, const float* doa, int32_t clips, int32_t
 /* The optimiser step of train.py:502-504, :560 -- torch.optim.Adam(lr, betas = (b1, b2), eps), no weight decay, no
  * amsgrad -- over flat float32 buffers of n elements (parameters, gradients, exp_avg, exp_avg_sq; 16-byte aligned).
  * step: device float holding the number of steps taken so far; incremented by the call (so the launch can be
- * captured in a CUDA graph). */
-int seldq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float b1,
-                    float b2, float eps, float* step, void* stream);
+ * captured in a CUDA graph).  The hyper-parameters arrive as the doubles PyTorch holds them in: 1 - b1, 1 - b2 and the
+ * bias corrections are formed in double, as torch/optim/adam.py forms them, before anything is rounded to float. */
+int seldq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double b1,
+                    double b2, double eps, float* step, void* stream);
 
 /* debug: a 64 x uint64 device buffer that CTA 0 of every later tensor-core convolution launch stamps with
  * %globaltimer values at its role hand-offs (tools/fprop_trace.py); NULL switches it off. */

@@ -142,8 +142,8 @@ _PROTOS = {
     "seldq_act_pool1d_fwd": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "seldq_act_pool1d_bwd": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                             _P, _P]),
-    "seldq_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
-                                       ctypes.c_float, _P, _P]),
+    "seldq_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                       ctypes.c_double, _P, _P]),
     "seldq_seld_events": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                          ctypes.c_float, _P, _P, _P]),
     "seldq_debug_fprop_trace": (ctypes.c_int, [_P]),

@@ -160,9 +160,11 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
     ptx::fence_proxy_async();
   }
   if (threadIdx.x == 0) {
-    // two MMA-issuing warps: each arrives once per stage / accumulator
-    // a stage is consumed by ONE MMA warp (the stage's owner)
-    for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    // a stage is consumed by ONE MMA warp (its owner, whose tcgen05.commit releases the slot), but EVERY MMA warp
+    // arrives on the slot's empty barrier once it has observed the stage's full phase: a slot is refilled only after
+    // all of them have seen it, so a warp that lags (a profiler's instrumentation is enough) can never find the
+    // barrier two phases on and mistake the refilled slot's phase for the one it still has to observe
+    for (int i = 0; i < p.nstages; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], kMmaWarps); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], kMmaWarps); ptx::mbar_init(&tempty_bar[i], 4 * kEpiSets); }
     ptx::mbar_init(w_bar, 1);
     ptx::fence_barrier_init();
@@ -290,6 +292,9 @@ qconv_cl_fprop_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_c
                 ptx::mbar_arrive(&empty_bar[slot]);             // nothing reads the slot
               }
               __syncwarp();
+            } else {
+              __syncwarp();                                     // every lane is past its wait on this phase
+              if (lane == 0) ptx::mbar_arrive(&empty_bar[slot]);
             }
             if (++slot == (uint32_t)p.nstages) { slot = 0; parity ^= 1; }
           }

@@ -171,6 +171,7 @@ struct WgradParams {
   uint32_t stage_bytes, b_tap_bytes;
   int8_t pair_n[8];             // which (a,b) blocks feed compact tensor e
   int8_t pair_a[8][8], pair_b[8][8], pair_neg[8][8];
+  unsigned long long* trace;    // debug timeline of CTA (0, 0) (seldq_debug_fprop_trace, tools/wgrad_trace.py)
 };
 
 int num_sms();

@@ -700,8 +700,8 @@ extern "C" int seldq_act_pool1d_bwd(const float* x, const float* y, const float*
   return launch_act_pool_bwd(x, y, gy, gx, rows, t, pool, act, (cudaStream_t)stream);
 }
 
-extern "C" int seldq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                               float b1, float b2, float eps, float* step, void* stream) {
+extern "C" int seldq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                               double b1, double b2, double eps, float* step, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step) return fail(SELDQ_ERR_INVALID, "seldq_adam_step: null pointer");
   int rc = cuda_ready();
   if (rc) return rc;

@@ -105,12 +105,13 @@ namespace seldq {
 namespace tail {
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                  float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                                                  float* __restrict__ step) {
-  const float t = *step + 1.f;
-  // bias corrections as torch/optim/adam.py: step_size = lr / (1 - b1^t), denom = sqrt(v) / sqrt(1 - b2^t) + eps
-  const float bc1 = 1.f - powf(b1, t), bc2s = sqrtf(1.f - powf(b2, t));
-  const float step_size = lr / bc1;
+                                                  float* __restrict__ v, long long n, double lr, double b1d, double b2d,
+                                                  float eps, float* __restrict__ step) {
+  // scalars as torch/optim/adam.py forms them: Python doubles (1 - beta, beta^t, lr / (1 - beta1^t), sqrt(1 - beta2^t)),
+  // rounded to float only where they meet the tensors
+  const double t = (double)*step + 1.0;
+  const float b2 = (float)b2d, omb1 = (float)(1.0 - b1d), omb2 = (float)(1.0 - b2d);
+  const float step_size = (float)(lr / (1.0 - pow(b1d, t))), bc2s = (float)sqrt(1.0 - pow(b2d, t));
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
@@ -118,16 +119,16 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      ma[k] = ma[k] + (1.f - b1) * (ga[k] - ma[k]);                 // exp_avg.lerp_(grad, 1 - beta1)
-      va[k] = b2 * va[k] + (1.f - b2) * ga[k] * ga[k];              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      ma[k] = ma[k] + omb1 * (ga[k] - ma[k]);                       // exp_avg.lerp_(grad, 1 - beta1)
+      va[k] = __fmaf_rn(omb2 * ga[k], ga[k], b2 * va[k]);           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
       pa[k] -= step_size * (ma[k] / (sqrtf(va[k]) / bc2s + eps));
     }
     reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0)
     for (long long i = n4 << 2; i < n; ++i) {
-      m[i] = m[i] + (1.f - b1) * (g[i] - m[i]);
-      v[i] = b2 * v[i] + (1.f - b2) * g[i] * g[i];
+      m[i] = m[i] + omb1 * (g[i] - m[i]);
+      v[i] = __fmaf_rn(omb2 * g[i], g[i], b2 * v[i]);
       p[i] -= step_size * (m[i] / (sqrtf(v[i]) / bc2s + eps));
     }
 }
@@ -136,13 +137,13 @@ __global__ void adam_count_kernel(float* step) { *step += 1.f; }
 
 }  // namespace tail
 
-int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float* step,
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps, float* step,
                 cudaStream_t st) {
   if (n < 1) return SELDQ_OK;
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15)
     return fail(SELDQ_ERR_INVALID, "seldq_adam_step: buffers must be 16-byte aligned");
-  tail::adam_kernel<<<grid_for(n >> 2), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, step);
+  tail::adam_kernel<<<grid_for(n >> 2), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, (float)eps, step);
   int rc = check_launch("adam_kernel");
   if (rc) return rc;
   tail::adam_count_kernel<<<1, 1, 0, st>>>(step);

@@ -29,11 +29,22 @@
 namespace seldq {
 namespace cl {
 
+// trace slots (CTA (0, 0) only): 0 entry, 1 set-up done, 2 first stage requested, 3 first stage landed, 4 last MMA issued,
+// 5 epilogue sees the accumulator, 6 fold done, 7 exit; 8 + ks: MMA warp saw stage ks (first 24 K steps)
+__device__ __forceinline__ void wtrace(const WgradParams& p, int slot) {
+  if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[slot] = t;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_constant__ CUtensorMap tm_g1,
                       const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   pdl_trigger();
+  if (threadIdx.x == 0) wtrace(p, 0);
   __shared__ __align__(8) uint64_t full_bar[kWgradStages], empty_bar[kWgradStages], done_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -67,6 +78,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   pdl_wait();                   // operands and the gradient buffers belong to earlier kernels up to here
+  if (threadIdx.x == 0) wtrace(p, 1);
 
   if (nk > 0) {
     if (warp == 0) {
@@ -93,6 +105,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
                 ptx::tma_load_4d(st + a_bytes + (size_t)t * p.b_tap_bytes + (size_t)c * 8192, &tm_x, &full_bar[slot],
                                  c * 64, w0 + p.off_w[tap0 + t], h + p.off_h[tap0 + t], n);
           }
+          if (ks == 0) wtrace(p, 2);
           if (++slot == (uint32_t)nstages) { slot = 0; parity ^= 1; }
         }
       }
@@ -108,6 +121,8 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
         for (int ks = 0; ks < nk; ++ks) {
           ptx::mbar_wait(&full_bar[slot], parity);
           ptx::tc_fence_after();
+          if (ks == 0) wtrace(p, 3);
+          if (ks < 24) wtrace(p, 8 + ks);
           const uint32_t st = base + slot * p.stage_bytes;
           for (int t = 0; t < ntap; ++t)
             for (int n0 = 0; n0 < p.Cp; n0 += 256) {
@@ -123,6 +138,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
           if (++slot == (uint32_t)nstages) { slot = 0; parity ^= 1; }
         }
         ptx::umma_commit(&done_bar);
+        wtrace(p, 4);
       }
     } else {
       // ===== epilogue ==============================================================================
@@ -137,6 +153,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
       const int il = et & 15;
       ptx::mbar_wait(&done_bar, 0);
       ptx::tc_fence_after();
+      if (et == 0) wtrace(p, 5);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
       const ConvGeom& g = p.g;
       // all MMAs have retired: the operand ring is free and is reused as a [128][ncomp*16 + 1] fp32 staging tile
@@ -177,10 +194,12 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
+      if (et == 0) wtrace(p, 6);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) wtrace(p, 7);
   if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -197,6 +216,7 @@ int launch_cl_wgrad(const ConvGeom& g, const void* x_cl, const void* gy_nchw16, 
   }
   const int nc = g.tab.nc;
   const OperandLayout lx = x_operand_layout(g);
+  p.trace = cl::fprop_trace();
   for (int i = 0; i < g.tab.nw; ++i) {
     p.gw[0][i] = host_gw[i];
     p.gw[1][i] = p.nprob == 2 ? host_gw2[i] : nullptr;
