@@ -258,7 +258,18 @@ int seldq_cnn_first_bwd(const seldq_cnn_tail_desc_t* t, const seldq_conv_desc_t*
 enum {
   SELDQ_TCN_PREACT_FWD = 0, SELDQ_TCN_ROW_STATS = 1, SELDQ_TCN_GATE_FWD = 2, SELDQ_TCN_RESIDUAL_FWD = 3,
   SELDQ_TCN_GATE_BWD_REDUCE = 4, SELDQ_TCN_GATE_BWD_APPLY = 5, SELDQ_TCN_PREACT_BWD_REDUCE = 6,
-  SELDQ_TCN_PREACT_BWD_APPLY = 7
+  SELDQ_TCN_PREACT_BWD_APPLY = 7,
+  /* single-launch forms (one block per 64-channel x 64-t tile, reduce and apply on either side of a grid barrier;
+   * `sync` = a zeroed uint32 the call may use once; seldq_tcn_glue_fused_supported tells whether the tensor's tiles
+   * can all be resident at once -- the call fails with SELDQ_ERR_UNSUPPORTED otherwise):
+   *   GATE_BWD            = GATE_BWD_REDUCE + GATE_BWD_APPLY      (same arguments)
+   *   PREACT_BWD          = PREACT_BWD_REDUCE + PREACT_BWD_APPLY  (same arguments)
+   *   GATE_FWD_STATS      = ROW_STATS(y_f, y_g) + GATE_FWD: stats_out[i] += statistics of in[i] (caller zeroes;
+   *                         bn[i].sums is ignored, the step reads stats_out[i]), then GATE_FWD
+   *   RESIDUAL_PREACT_FWD = RESIDUAL_FWD (c2 == c, in[1] and in[2] not NULL, dsums not NULL) + the NEXT block's
+   *                         PREACT_FWD: bn[0] = the next block's batch_filter1 (its sums are dsums),
+   *                         out32b = tanh(BN(r')), out_cl[0] = its operand */
+  SELDQ_TCN_GATE_BWD = 8, SELDQ_TCN_PREACT_BWD = 9, SELDQ_TCN_GATE_FWD_STATS = 10, SELDQ_TCN_RESIDUAL_PREACT_FWD = 11
 };
 typedef struct {
   const double* sums;                 /* [C][2] batch sum, sum of squares */
@@ -283,9 +294,12 @@ typedef struct {
   float* accum;
   const int64_t* seed;                /* device counter, advanced by the caller every step (iff drop_p > 0) */
   int32_t flag;
+  uint32_t* sync;                     /* single-launch forms: zeroed grid-barrier counter */
+  float* out32b;                      /* RESIDUAL_PREACT_FWD: tanh(BN(r')) */
 } seldq_tcn_glue_t;
 int seldq_tcn_glue(int32_t op, const seldq_tcn_glue_t* args, const seldq_conv_desc_t* layout_of, int32_t which,
                    void* stream);
+int seldq_tcn_glue_fused_supported(int32_t n, int32_t c, int32_t t);
 
 /* ---- linear (A3, A4) ------------------------------------------------------------------- */
 size_t seldq_linear_workspace_bytes(const seldq_linear_desc_t* d, int32_t pass);

@@ -41,11 +41,13 @@ class TcnGlue(ctypes.Structure):
                 ("salt", ctypes.c_uint32), ("count", ctypes.c_double), ("bn", BnRef * 2),
                 ("inp", ctypes.c_void_p * 5), ("out32", ctypes.c_void_p), ("out_cl", ctypes.c_void_p * 2),
                 ("out_t16", ctypes.c_void_p * 2), ("dsums", ctypes.c_void_p), ("stats_out", ctypes.c_void_p * 2),
-                ("accum", ctypes.c_void_p), ("seed", ctypes.c_void_p), ("flag", ctypes.c_int32)]
+                ("accum", ctypes.c_void_p), ("seed", ctypes.c_void_p), ("flag", ctypes.c_int32),
+                ("sync", ctypes.c_void_p), ("out32b", ctypes.c_void_p)]
 
 
 TCN_PREACT_FWD, TCN_ROW_STATS, TCN_GATE_FWD, TCN_RESIDUAL_FWD = 0, 1, 2, 3
 TCN_GATE_BWD_REDUCE, TCN_GATE_BWD_APPLY, TCN_PREACT_BWD_REDUCE, TCN_PREACT_BWD_APPLY = 4, 5, 6, 7
+TCN_GATE_BWD, TCN_PREACT_BWD, TCN_GATE_FWD_STATS, TCN_RESIDUAL_PREACT_FWD = 8, 9, 10, 11
 
 
 class ConvEpilogue(ctypes.Structure):
@@ -118,6 +120,7 @@ _PROTOS = {
                                            _P, ctypes.POINTER(_P), ctypes.c_int32, _P, ctypes.c_size_t, _P]),
     "seldq_tcn_glue": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(TcnGlue), ctypes.POINTER(ConvDesc), ctypes.c_int32,
                                       _P]),
+    "seldq_tcn_glue_fused_supported": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "seldq_conv_dgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, ctypes.POINTER(_P), _P, _P, _P,
                                         ctypes.c_size_t, _P]),
     "seldq_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, ctypes.POINTER(_P), _P,

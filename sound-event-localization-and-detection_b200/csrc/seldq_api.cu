@@ -585,6 +585,7 @@ extern "C" int seldq_tcn_glue(int32_t op, const seldq_tcn_glue_t* a, const seldq
   }
   for (int i = 0; i < 5; ++i) p.in[i] = a->in[i];
   p.out32 = a->out32; p.dsums = a->dsums; p.accum = a->accum;
+  p.out32b = a->out32b; p.sync = a->sync;
   p.cc = a->c; p.cpad = (a->c + 63) / 64 * 64; p.Cp = p.cpad;
   p.pitch = nchw16_pitch(a->t);
   int rc;
@@ -626,11 +627,30 @@ extern "C" int seldq_tcn_glue(int32_t op, const seldq_tcn_glue_t* a, const seldq
     case SELDQ_TCN_PREACT_BWD_APPLY:
       rc = need(a->in[1] && a->in[2] && a->in[3] && a->in[4] && a->dsums && a->bn[0].sums && a->out32);
       break;
+    case SELDQ_TCN_GATE_BWD:
+      rc = need(a->in[0] && a->in[1] && a->in[2] && a->dsums && a->bn[0].sums && a->bn[1].sums && a->out_cl[0] &&
+                a->out_cl[1] && a->out_t16[0] && a->out_t16[1] && a->sync);
+      break;
+    case SELDQ_TCN_PREACT_BWD:
+      rc = need(a->in[1] && a->in[2] && a->in[3] && a->in[4] && a->dsums && a->bn[0].sums && a->out32 && a->sync);
+      break;
+    case SELDQ_TCN_GATE_FWD_STATS:
+      rc = need(a->in[0] && a->in[1] && a->out_cl[0] && a->stats_out[0] && a->stats_out[1] && a->sync);
+      break;
+    case SELDQ_TCN_RESIDUAL_PREACT_FWD:
+      rc = need(a->in[0] && a->in[1] && a->in[2] && a->out32 && a->out32b && a->out_cl[0] && a->accum && a->dsums &&
+                a->c2 == a->c && a->sync);
+      break;
     default: return fail(SELDQ_ERR_INVALID, "seldq_tcn_glue: unknown op %d", op);
   }
   if (rc) return rc;
   if ((rc = cuda_ready())) return rc;
   return launch_tcn_glue(op, p, a->flag, (cudaStream_t)stream);
+}
+
+extern "C" int seldq_tcn_glue_fused_supported(int32_t n, int32_t c, int32_t t) {
+  if (cuda_ready()) return 0;
+  return tcn_glue_fused_supported(n, c, t);
 }
 
 // ---- linear: 0.18 GFLOP per call in the reference configs -> always the fp32 FFMA kernels -----------

@@ -16,7 +16,11 @@ enum Op {
   OP_GATE_BWD_REDUCE = SELDQ_TCN_GATE_BWD_REDUCE,
   OP_GATE_BWD_APPLY = SELDQ_TCN_GATE_BWD_APPLY,
   OP_PREACT_BWD_REDUCE = SELDQ_TCN_PREACT_BWD_REDUCE,
-  OP_PREACT_BWD_APPLY = SELDQ_TCN_PREACT_BWD_APPLY
+  OP_PREACT_BWD_APPLY = SELDQ_TCN_PREACT_BWD_APPLY,
+  OP_GATE_BWD = SELDQ_TCN_GATE_BWD,
+  OP_PREACT_BWD = SELDQ_TCN_PREACT_BWD,
+  OP_GATE_FWD_STATS = SELDQ_TCN_GATE_FWD_STATS,
+  OP_RESIDUAL_PREACT_FWD = SELDQ_TCN_RESIDUAL_PREACT_FWD
 };
 
 // one train-mode BatchNorm1d: batch statistics as per-channel (sum, sum of squares) in double
@@ -39,6 +43,7 @@ struct GlueParams {
   BnRef bn[2];
   const float* in[5];
   float* out32;
+  float* out32b;         // residual_preact_fwd: the next block's x = tanh(BN1(r'))
   __nv_bfloat16* out_cl[2];
   __nv_bfloat16* out_t16[2];
   double* dsums;         // reduce kernels: output (zeroed by the caller); apply kernels: input
@@ -47,6 +52,7 @@ struct GlueParams {
   float drop_p;
   const long long* seed_ptr;
   uint32_t salt;
+  unsigned int* sync;    // fused (reduce + apply in one launch) kernels: grid-barrier counter, zeroed by the caller
   int tiles_t, tiles_c;  // filled by the launcher
   long long total_blocks;
 };
@@ -54,5 +60,7 @@ struct GlueParams {
 }  // namespace tcn
 
 int launch_tcn_glue(int op, tcn::GlueParams& p, int flag, cudaStream_t st);
+// 1 when the single-launch (grid-barrier) steps can hold every tile of an (N, C, T) tensor resident at once
+int tcn_glue_fused_supported(int n, int c, int t);
 
 }  // namespace seldq

@@ -39,7 +39,39 @@ __device__ __forceinline__ void wtrace(const WgradParams& p, int slot) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// one (out channel, in channel) position of the staged 128 x (ncomp * 16) block folded onto the compact tensors:
+// gw_e[off] += sum_k sign(e, k) * block(a(e, k), b(e, k)); table entries beyond a tensor's pair count have sign 0.
+// Two tensors per round: their 2 * KMAX table entries, then their 2 * KMAX values, are in flight together (compile-time
+// trip counts, no predicate between the loads) while the register footprint stays small -- the kernel's CTAs share
+// their SMs with the glue kernels of the main stream, which need the registers (all eight tensors in one round
+// took 121 registers per thread and cost the training step 0.06 ms).
+template <int NW, int KMAX>
+__device__ __forceinline__ void fold_block(const float* col, const int2* tbl, float* const* gw, long long off) {
+  constexpr int EB = NW >= 2 ? 2 : 1;
+#pragma unroll 1
+  for (int e0 = 0; e0 < NW; e0 += EB) {
+    int2 f[EB][KMAX];
+#pragma unroll
+    for (int e = 0; e < EB; ++e)
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) f[e][k] = tbl[(e0 + e) * 8 + k];
+    float v[EB][KMAX];
+#pragma unroll
+    for (int e = 0; e < EB; ++e)
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) v[e][k] = col[f[e][k].x];
+#pragma unroll
+    for (int e = 0; e < EB; ++e) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) acc = fmaf(__int_as_float(f[e][k].y), v[e][k], acc);
+      atomicAdd(gw[e0 + e] + off, acc);
+    }
+  }
+}
+
+// (register cap of 64: one CTA per SM by shared memory, but the glue kernels of the main stream co-reside in what is left)
+__global__ void __launch_bounds__(kThreads, 3)
 qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_constant__ CUtensorMap tm_g1,
                       const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -47,6 +79,7 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
   if (threadIdx.x == 0) wtrace(p, 0);
   __shared__ __align__(8) uint64_t full_bar[kWgradStages], empty_bar[kWgradStages], done_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ int2 fold_tbl[64];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   // tile decode: blockIdx.x = (problem * tap_groups + tap_group) * o_tiles + o_tile, blockIdx.y = split
@@ -151,6 +184,20 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
       const int row = q * 32 + lane;                 // accumulator row = TMEM lane = (a, ol)
       const int et = threadIdx.x - 64;               // 0..255 among the epilogue threads
       const int il = et & 15;
+      // fold table: entry (e, k) = {offset of block (a, b) inside the staging tile, +-1.f | 0.f for an unused entry}.
+      // Measured (tools/wgrad_trace.py): with the (a, b, sign) bytes read from the parameter block inside a rolled loop
+      // the fold was a serial chain of constant-bank and shared-memory latencies, 8 us of a 17 us launch; with the
+      // table in shared memory and the loops unrolled all loads of a fold are in flight together.
+      const int pitch = p.ncomp * 16 + 1;
+      if (et < 64) {
+        const int e = et >> 3, k = et & 7;
+        const bool on = e < p.g.tab.nw && k < p.pair_n[e];
+        fold_tbl[et] = make_int2(on ? p.pair_a[e][k] * p.OS * pitch + p.pair_b[e][k] * 16 : 0,
+                                 on ? __float_as_int(p.pair_neg[e][k] ? -1.f : 1.f) : 0);
+      }
+      int kmax = 0;
+      for (int e = 0; e < p.g.tab.nw; ++e) kmax = max(kmax, (int)p.pair_n[e]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       ptx::mbar_wait(&done_bar, 0);
       ptx::tc_fence_after();
       if (et == 0) wtrace(p, 5);
@@ -158,7 +205,6 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
       const ConvGeom& g = p.g;
       // all MMAs have retired: the operand ring is free and is reused as a [128][ncomp*16 + 1] fp32 staging tile
       float* stg = reinterpret_cast<float*>(smem);
-      const int pitch = p.ncomp * 16 + 1;
       const int bper = (p.ncomp + 1) >> 1;
       const int b_lo = hf * bper, b_hi = min(p.ncomp, b_lo + bper);
       for (int t = 0; t < ntap; ++t)
@@ -182,13 +228,18 @@ qconv_cl_wgrad_kernel(const __grid_constant__ CUtensorMap tm_g0, const __grid_co
               if (o0 + ol >= g.Oc) break;
               const float* col = stg + ol * pitch + il;
               const long long off = (long long)(o0 + ol) * g.wsO + (long long)(ic + il) * g.wsI + (long long)(tap0 + t) * g.wsT;
-              for (int e = 0; e < g.tab.nw; ++e) {
-                float acc = 0.f;
-                for (int k = 0; k < p.pair_n[e]; ++k) {
-                  const float val = col[p.pair_a[e][k] * p.OS * pitch + p.pair_b[e][k] * 16];
-                  acc += p.pair_neg[e][k] ? -val : val;
+              if (g.tab.nw == 8 && kmax <= 6) fold_block<8, 6>(col, fold_tbl, p.gw[prob], off);          // dual quaternion
+              else if (g.tab.nw == 4 && kmax <= 4) fold_block<4, 4>(col, fold_tbl, p.gw[prob], off);     // quaternion
+              else if (g.tab.nw == 1 && kmax <= 1) fold_block<1, 1>(col, fold_tbl, p.gw[prob], off);     // real
+              else {
+                for (int e = 0; e < g.tab.nw; ++e) {
+                  float acc = 0.f;
+                  for (int k = 0; k < kmax; ++k) {
+                    const int2 f = fold_tbl[e * 8 + k];
+                    acc = fmaf(__int_as_float(f.y), col[f.x], acc);
+                  }
+                  atomicAdd(p.gw[prob][e] + off, acc);
                 }
-                atomicAdd(p.gw[prob][e] + off, acc);
               }
             }
           }

@@ -35,6 +35,9 @@ TCN_PAIR = os.environ.get("SELDQ_TCN_PAIR", "1") != "0"
 # SELDQ_TCN_EPI=1: the statistics / residual / skip-sum glue rides in the sibling launches' epilogues instead of
 # stand-alone kernels (seldq_conv_epilogue_t)
 TCN_EPI = os.environ.get("SELDQ_TCN_EPI", "0") != "0"
+# SELDQ_TCN_FUSED_GLUE=0: every reduce / apply pair of the residual-block glue stays two launches (default: one launch
+# with a grid barrier where all tiles of the tensor can be resident at once -- seldq_tcn_glue_fused_supported)
+TCN_FUSED_GLUE = os.environ.get("SELDQ_TCN_FUSED_GLUE", "0") != "0"
 _SIDE = {}
 
 
@@ -293,7 +296,7 @@ def cnn_stack(x, convs, bns, pools, drops, seed):
 
 # ---- TCN residual blocks (model.py:109-132) -------------------------------------------------------------------
 def _glue(op, layout_of, which, N, C, T, c2=0, eps=1e-5, momentum=0.1, drop_p=0.0, salt=0, bn=(), inp=(), out32=None,
-          out_cl=(), out_t16=(), dsums=None, stats_out=(), accum=None, seed=None, flag=0):
+          out_cl=(), out_t16=(), dsums=None, stats_out=(), accum=None, seed=None, flag=0, sync=None, out32b=None):
     """One seldq_tcn_glue call (include/seldq.h).  bn: up to two (sums, gamma, beta, running_mean, running_var)."""
     a = _lib.TcnGlue()
     a.n, a.c, a.t, a.c2 = N, C, T, c2
@@ -314,6 +317,7 @@ def _glue(op, layout_of, which, N, C, T, c2=0, eps=1e-5, momentum=0.1, drop_p=0.
     a.accum = _ptr(accum)
     a.seed = _ptr(seed) if drop_p > 0 else None
     a.flag = flag
+    a.sync, a.out32b = _ptr(sync), _ptr(out32b)
     F._timed("tcn_glue_kernels", 0.0, 1, lambda: _lib.check(_lib.lib().seldq_tcn_glue(
         op, ctypes.byref(a), None if layout_of is None else ctypes.byref(layout_of), which, _stream())))
 
@@ -374,6 +378,10 @@ class _TcnStack(torch.autograd.Function):
                 o += 2 * Lc + 4 * g
             sums1 = stats[:2 * Lc].view(Lc, 2)
             _glue(_lib.TCN_ROW_STATS, None, 0, N, Lc, T, inp=(r,), stats_out=(sums1,), flag=1)
+            # single-launch glue steps (grid barrier): one zeroed counter per step
+            fuse_l = TCN_FUSED_GLUE and not TCN_EPI and bool(L_.seldq_tcn_glue_fused_supported(N, Lc, T))
+            syncs = torch.zeros(2 * len(blocks), dtype=torch.int32, device=dev)
+            xa = xa_cl = None
             for k, (s, wf, wg, wsk, wr, bnp) in enumerate(blocks):
                 nc = F._NCOMP[s["algebra"]]
                 G, U = wf[0].shape[0] * nc, wsk[0].shape[0] * nc
@@ -384,11 +392,12 @@ class _TcnStack(torch.autograd.Function):
                 e1, m1, rm1, rv1 = s["bn1"]
                 ef, mf, rmf, rvf = s["bnf"]
                 eg, mg, rmg, rvg = s["bng"]
-                # x = tanh(BN1(r))
-                xa = torch.empty((N, Lc, T), **f32)
-                xa_cl = torch.empty(F._operand_info(d1, 0)[2], dtype=torch.uint8, device=dev)
-                _glue(_lib.TCN_PREACT_FWD, d1, 0, N, Lc, T, eps=e1, momentum=m1, bn=((sums1, g1, b1, rm1, rv1),),
-                      inp=(r,), out32=xa, out_cl=(xa_cl,))
+                # x = tanh(BN1(r)) (already there when the block before produced it together with r)
+                if xa is None:
+                    xa = torch.empty((N, Lc, T), **f32)
+                    xa_cl = torch.empty(F._operand_info(d1, 0)[2], dtype=torch.uint8, device=dev)
+                    _glue(_lib.TCN_PREACT_FWD, d1, 0, N, Lc, T, eps=e1, momentum=m1, bn=((sums1, g1, b1, rm1, rv1),),
+                          inp=(r,), out32=xa, out_cl=(xa_cl,))
                 # y_f, y_g: one sibling launch; the batch statistics of batch_filter2 / batch_gate2 come from the
                 # convolutions' epilogues (TCN_EPI) or from one row-statistics kernel
                 sums2 = stats[offs[k] + 2 * Lc:offs[k] + 2 * Lc + 4 * G].view(2, G, 2)
@@ -405,13 +414,19 @@ class _TcnStack(torch.autograd.Function):
                         F._timed("qconv_cl_fprop_kernel", F._conv_flop(d1, 1, T), 1, lambda: _lib.check(
                             L_.seldq_conv_fwd(ctypes.byref(d1), None, xa_cl.data_ptr(), wp, _ptr(pk), None, y.data_ptr(),
                                               None, 0, _stream())))
-                if not (pair1 and TCN_EPI):
-                    _glue(_lib.TCN_ROW_STATS, None, 0, N, G, T, inp=(yf, yg), stats_out=(sums2[0], sums2[1]), flag=2)
+                fuse_g = fuse_l and bool(L_.seldq_tcn_glue_fused_supported(N, G, T))
                 # y = dropout1d(tanh(BN_f y_f) * sigmoid(BN_g y_g)), only as conv2's operand
                 y_cl = torch.empty(F._operand_info(dsk, 0)[2], dtype=torch.uint8, device=dev)
-                _glue(_lib.TCN_GATE_FWD, dsk, 0, N, G, T, eps=ef, momentum=mf, drop_p=s["drop_p"], salt=s["salt"],
-                      bn=((sums2[0], gf, bf, rmf, rvf), (sums2[1], gg, bg, rmg, rvg)), inp=(yf, yg), out_cl=(y_cl,),
-                      seed=seed)
+                if fuse_g:
+                    _glue(_lib.TCN_GATE_FWD_STATS, dsk, 0, N, G, T, eps=ef, momentum=mf, drop_p=s["drop_p"], salt=s["salt"],
+                          bn=((sums2[0], gf, bf, rmf, rvf), (sums2[1], gg, bg, rmg, rvg)), inp=(yf, yg),
+                          stats_out=(sums2[0], sums2[1]), out_cl=(y_cl,), seed=seed, sync=syncs[2 * k:])
+                else:
+                    if not (pair1 and TCN_EPI):
+                        _glue(_lib.TCN_ROW_STATS, None, 0, N, G, T, inp=(yf, yg), stats_out=(sums2[0], sums2[1]), flag=2)
+                    _glue(_lib.TCN_GATE_FWD, dsk, 0, N, G, T, eps=ef, momentum=mf, drop_p=s["drop_p"], salt=s["salt"],
+                          bn=((sums2[0], gf, bf, rmf, rvf), (sums2[1], gg, bg, rmg, rvg)), inp=(yf, yg), out_cl=(y_cl,),
+                          seed=seed)
                 if skip_sum is None:
                     skip_sum = torch.empty((N, U, T), **f32)
                 r_next = sums1_next = None
@@ -448,11 +463,30 @@ class _TcnStack(torch.autograd.Function):
                             F._timed("qconv_cl_fprop_kernel", F._conv_flop(d, 1, T), 1, lambda: _lib.check(
                                 L_.seldq_conv_fwd(ctypes.byref(d), None, y_cl.data_ptr(), wp, _ptr(pk), None, o.data_ptr(),
                                                   None, 0, _stream())))
-                    _glue(_lib.TCN_RESIDUAL_FWD, None, 0, N, Lc, T, c2=U, inp=(xa, res, skip), out32=r_next,
-                          dsums=sums1_next, accum=skip_sum, flag=1 if k == 0 else 0)
+                    xa_next = xa_cl_next = None
+                    if fuse_l and s["has_res"] and U == Lc:
+                        # r' and the skip sum, then -- behind the grid barrier -- the next block's x = tanh(BN1(r'))
+                        sn = blocks[k + 1][0]
+                        d1n = _lib.ConvDesc(sn["algebra"], PREC_BF16, 1, N, Lc, blocks[k + 1][2][0].shape[0] *
+                                            F._NCOMP[sn["algebra"]], 1, T, 1, sn["k"], 1, 1, 0, sn["pad"], 1, sn["dil"])
+                        g1n, b1n = blocks[k + 1][5][0], blocks[k + 1][5][1]
+                        e1n, m1n, rm1n, rv1n = sn["bn1"]
+                        xa_next = torch.empty((N, Lc, T), **f32)
+                        xa_cl_next = torch.empty(F._operand_info(d1n, 0)[2], dtype=torch.uint8, device=dev)
+                        _glue(_lib.TCN_RESIDUAL_PREACT_FWD, d1n, 0, N, Lc, T, c2=U, eps=e1n, momentum=m1n,
+                              bn=((sums1_next, g1n, b1n, rm1n, rv1n),), inp=(xa, res, skip), out32=r_next,
+                              out32b=xa_next, out_cl=(xa_cl_next,), dsums=sums1_next, accum=skip_sum,
+                              flag=1 if k == 0 else 0, sync=syncs[2 * k + 1:])
+                    else:
+                        _glue(_lib.TCN_RESIDUAL_FWD, None, 0, N, Lc, T, c2=U, inp=(xa, res, skip), out32=r_next,
+                              dsums=sums1_next, accum=skip_sum, flag=1 if k == 0 else 0)
                 saved += [r, xa, xa_cl, yf, yg, y_cl, sums1, sums2]
                 metas.append((s, d1, dsk, dre, G, U))
                 r, sums1 = r_next, sums1_next
+                if TCN_EPI and pair2:
+                    xa = xa_cl = None
+                else:
+                    xa, xa_cl = xa_next, xa_cl_next
         ctx.metas = metas
         ctx.shape = (N, Lc, T)
         ctx.block_params = [(wf, wg, wsk, wr, bnp) for _, wf, wg, wsk, wr, bnp in blocks]
@@ -522,6 +556,8 @@ class _TcnStack(torch.autograd.Function):
             # [block](pre-activation (2, L), gate (4, G)), converted to fp32 once at the end
             sizes = [2 * Lc + 4 * m[4] for m in ctx.metas]
             red = torch.zeros(sum(sizes), dtype=torch.float64, device=dev)
+            fuse_l = TCN_FUSED_GLUE and bool(L_.seldq_tcn_glue_fused_supported(N, Lc, T))
+            syncs = torch.zeros(2 * nblocks, dtype=torch.int32, device=dev)
             roff = [sum(sizes[:i]) for i in range(nblocks)]
             for k in reversed(range(nblocks)):
                 s, d1, dsk, dre, G, U = ctx.metas[k]
@@ -553,13 +589,19 @@ class _TcnStack(torch.autograd.Function):
                 # gate
                 bn2 = ((sums2[0], gf, bf, None, None), (sums2[1], gg, bg, None, None))
                 dsg = red[roff[k] + 2 * Lc:roff[k] + 2 * Lc + 4 * G]
-                _glue(_lib.TCN_GATE_BWD_REDUCE, None, 0, N, G, T, eps=ef, drop_p=s["drop_p"], salt=s["salt"], bn=bn2,
-                      inp=(yf, yg, gy1, gy2), dsums=dsg, seed=ctx.seed)
                 _, _, clb, t16b = F._operand_info(d1, 1)
                 df_cl, dg_cl = torch.empty(clb, **u8), torch.empty(clb, **u8)
                 df_t16, dg_t16 = torch.empty(t16b, **u8), torch.empty(t16b, **u8)
-                _glue(_lib.TCN_GATE_BWD_APPLY, d1, 1, N, G, T, eps=ef, drop_p=s["drop_p"], salt=s["salt"], bn=bn2,
-                      inp=(yf, yg, gy1, gy2), dsums=dsg, out_cl=(df_cl, dg_cl), out_t16=(df_t16, dg_t16), seed=ctx.seed)
+                if fuse_l and L_.seldq_tcn_glue_fused_supported(N, G, T):
+                    _glue(_lib.TCN_GATE_BWD, d1, 1, N, G, T, eps=ef, drop_p=s["drop_p"], salt=s["salt"], bn=bn2,
+                          inp=(yf, yg, gy1, gy2), dsums=dsg, out_cl=(df_cl, dg_cl), out_t16=(df_t16, dg_t16),
+                          seed=ctx.seed, sync=syncs[2 * k:])
+                else:
+                    _glue(_lib.TCN_GATE_BWD_REDUCE, None, 0, N, G, T, eps=ef, drop_p=s["drop_p"], salt=s["salt"], bn=bn2,
+                          inp=(yf, yg, gy1, gy2), dsums=dsg, seed=ctx.seed)
+                    _glue(_lib.TCN_GATE_BWD_APPLY, d1, 1, N, G, T, eps=ef, drop_p=s["drop_p"], salt=s["salt"], bn=bn2,
+                          inp=(yf, yg, gy1, gy2), dsums=dsg, out_cl=(df_cl, dg_cl), out_t16=(df_t16, dg_t16),
+                          seed=ctx.seed)
                 # conv1
                 if TCN_PAIR and L_.seldq_conv_pair_supported(ctypes.byref(d1), PASS_DGRAD):
                     gx1, gx2 = torch.empty((N, d1.cin, T), **f32), torch.empty((N, d1.cin, T), **f32)
@@ -572,17 +614,21 @@ class _TcnStack(torch.autograd.Function):
                 # pre-activation
                 bn1 = ((sums1, g1, b1, None, None),)
                 ds1 = red[roff[k]:roff[k] + 2 * Lc]
-                _glue(_lib.TCN_PREACT_BWD_REDUCE, None, 0, N, Lc, T, eps=e1, bn=bn1, inp=(g_rn, gx1, gx2, xa, r), dsums=ds1)
+                apply_op = _lib.TCN_PREACT_BWD if fuse_l else _lib.TCN_PREACT_BWD_APPLY
+                sync = syncs[2 * k + 1:] if fuse_l else None
+                if not fuse_l:
+                    _glue(_lib.TCN_PREACT_BWD_REDUCE, None, 0, N, Lc, T, eps=e1, bn=bn1, inp=(g_rn, gx1, gx2, xa, r),
+                          dsums=ds1)
                 g_r = torch.empty((N, Lc, T), **f32)
                 if k > 0:
                     dprev = ctx.metas[k - 1][3]
                     _, _, clb, t16b = F._operand_info(dprev, 1)
                     g_rn_cl, g_rn_t16 = torch.empty(clb, **u8), torch.empty(t16b, **u8)
-                    _glue(_lib.TCN_PREACT_BWD_APPLY, dprev, 1, N, Lc, T, eps=e1, bn=bn1, inp=(g_rn, gx1, gx2, xa, r),
-                          dsums=ds1, out32=g_r, out_cl=(g_rn_cl,), out_t16=(g_rn_t16,))
+                    _glue(apply_op, dprev, 1, N, Lc, T, eps=e1, bn=bn1, inp=(g_rn, gx1, gx2, xa, r),
+                          dsums=ds1, out32=g_r, out_cl=(g_rn_cl,), out_t16=(g_rn_t16,), sync=sync)
                 else:
-                    _glue(_lib.TCN_PREACT_BWD_APPLY, None, 0, N, Lc, T, eps=e1, bn=bn1, inp=(g_rn, gx1, gx2, xa, r),
-                          dsums=ds1, out32=g_r)
+                    _glue(apply_op, None, 0, N, Lc, T, eps=e1, bn=bn1, inp=(g_rn, gx1, gx2, xa, r),
+                          dsums=ds1, out32=g_r, sync=sync)
                 g_rn = g_r
                 grads[k] = list(gw_f) + list(gw_g) + list(gw_sk) + list(gw_r)
             if side is not None:

@@ -337,6 +337,50 @@ def test_fused_tcn_blocks_match_layerwise(seldq, domain, chans):
             assert np.allclose(bf[k], bl[k], rtol=1e-4, atol=1e-5), k
 
 
+@pytest.mark.parametrize("shape", [(1, 384, 4800), (2, 128, 264)])
+def test_tcn_glue_single_launch_steps_match_two_launch_steps(seldq, shape):
+    """The single-launch glue steps (tcn_glue.cu: reduce and apply on either side of a grid barrier, 450 resident
+    blocks at the model's shape) against the reduce / apply pairs they replace: same stack, same weights, same dropout
+    seed.  The two differ only in the order of the partial sums of the BatchNorm statistics (double atomics) -- and in
+    the tensor path's own run-to-run noise, which the gates below are set to (see the dropout test)."""
+    import copy
+    model_mod = __import__("importlib").import_module(seldq.__name__ + ".seld_model")
+    n, chans, T = shape
+    assert seldq._lib.lib().seldq_tcn_glue_fused_supported(n, chans, T) == 1
+    torch.manual_seed(11)
+    np.random.seed(11)
+    blk = model_mod.TC_Block(in_channels=chans, domain="DQ", G=chans, U=chans, V=[chans, chans], D=[3],
+                             spatial_dropout_rate=0.5, use_bias_conv=False, batch_norm='BN').cuda().train()
+    ref = copy.deepcopy(blk)
+    x = torch.randn(n, chans, T, device="cuda")
+    gy = torch.randn(n, chans, T, device="cuda")
+    outs = {}
+    for name, mod, one_launch in (("one", blk, True), ("two", ref, False)):
+        prev = seldq.fused.TCN_FUSED_GLUE
+        seldq.fused.TCN_FUSED_GLUE = one_launch
+        try:
+            mod._drop_seed.fill_(21)
+            xi = x.clone().requires_grad_(True)
+            with seldq.precision("bf16"):
+                y = seldq.fused.tcn_stack(xi, mod.ResBlocks, mod._drop_seed)
+                y.backward(gy)
+            torch.cuda.synchronize()
+            outs[name] = (y.detach().cpu().numpy(), xi.grad.cpu().numpy(),
+                          {k: p.grad.cpu().numpy() for k, p in mod.named_parameters() if p.grad is not None},
+                          {k: v.detach().cpu().numpy() for k, v in mod.named_buffers() if "running" in k})
+        finally:
+            seldq.fused.TCN_FUSED_GLUE = prev
+    y1, gx1, g1, b1 = outs["one"]
+    y2, gx2, g2, b2 = outs["two"]
+    assert np.isfinite(y1).all() and np.isfinite(gx1).all()
+    assert A.rel_err(y1, y2) < 2e-3 and A.rel_err(gx1, gx2) < 1e-2
+    assert set(g1) == set(g2)
+    for k in g2:
+        assert A.rel_err(g1[k], g2[k]) < 1e-2, (k, A.rel_err(g1[k], g2[k]))
+    for k in b2:
+        assert np.allclose(b1[k], b2[k], rtol=1e-5, atol=1e-6), k
+
+
 def test_fused_tcn_channel_dropout_is_consistent(seldq):
     """Channel dropout of the fused path: a (sample, channel) row of y is either dropped or scaled by 1/(1-p) --
     observed through the skip convolution's weight gradient being finite and the step being repeatable for the same

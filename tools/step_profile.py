@@ -52,5 +52,12 @@ for name, (us, n, each) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:args.
         print("             each: " + " ".join("%.0f" % e for e in each))
 if args.ops:
     print()
+    print("aten ops by self device time (the part of the step that is not this repository's kernels):")
+    ka = [e for e in prof.key_averages(group_by_input_shape=True) if e.key.startswith("aten::") and e.self_device_time_total > 0]
+    tot = sum(e.self_device_time_total for e in ka)
+    print("  total %.1f us over %d calls" % (tot, sum(e.count for e in ka)))
+    for e in sorted(ka, key=lambda e: -e.self_device_time_total)[:45]:
+        print("  %8.1f us %4d x  %-34s %s" % (e.self_device_time_total, e.count, e.key, str(e.input_shapes)[:110]))
+    print()
     print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=60,
                                                              max_name_column_width=48, max_shapes_column_width=70))
