@@ -9,6 +9,7 @@
 #include "../../sound-event-localization-and-detection_b200/csrc/conv_simt.cuh"
 #include "../../sound-event-localization-and-detection_b200/csrc/geom.h"
 #include "../../sound-event-localization-and-detection_b200/csrc/stft.cuh"
+#include "../../sound-event-localization-and-detection_b200/csrc/stft_pair.cuh"
 
 using namespace seldq;
 
@@ -266,6 +267,30 @@ static void run_wgrad(const simt::WgradParams& p) {
       }
 }
 
+// frame-pair kernel (csrc/stft_pair.cuh), PAIRS = 28 (the shape the launcher picks for 8 signals x 4800 frames) and 16
+template <int PAIRS>
+static int run_stft_pairs(stft::Params& p, int n_signals) {
+  p.groups = (p.n_frames + 2 * PAIRS - 1) / (2 * PAIRS);
+  p.total = (long long)n_signals * p.groups;
+  constexpr int NT = 16 * PAIRS;
+  stft2::Shared<PAIRS>* sh = new stft2::Shared<PAIRS>;
+  std::vector<stft2::Thread> th(NT);
+  std::vector<stft2::Raw> raw(NT);
+  for (int t = 0; t < NT; ++t) stft2::init_tables(*sh, t);
+  for (long long batch = 0; batch < p.total; ++batch) {
+    int signal, t0;
+    stft2::batch_decode<PAIRS>(p, batch, &signal, &t0);
+    for (int t = 0; t < NT; ++t) stft2::load_raw(p, raw[t], t, signal, t0);
+    for (int t = 0; t < NT; ++t) stft2::phase_a(*sh, raw[t], th[t], t);
+    for (int t = 0; t < NT; ++t) stft2::phase_b(*sh, th[t], t);
+    for (int t = 0; t < NT; ++t) stft2::phase_b2(*sh, th[t], t);
+    for (int t = 0; t < NT; ++t) stft2::phase_c(p, *sh, th[t], t);
+    for (int t = 0; t < NT; ++t) stft2::phase_d(p, *sh, t, signal, t0);
+  }
+  delete sh;
+  return 0;
+}
+
 extern "C" {
 
 // forward (pass 0) or dgrad (pass 1) of a Q / DQ convolution through the emulated tensor-core data flow; info (10
@@ -373,6 +398,18 @@ int emul_stft(const float* x, int n_batch, int n_ch, long long n_samples, int np
   }
   delete sh;
   return 0;
+}
+
+int emul_stft_pairs(const float* x, int n_batch, int n_ch, long long n_samples, int nperseg, int noverlap, int cut_dc,
+                    int cut_last, int pairs, float* out) {
+  int n_bins, n_frames;
+  int rc = stft_shape(n_samples, nperseg, noverlap, cut_dc, cut_last, &n_bins, &n_frames);
+  if (rc) return rc;
+  stft::Params p{};
+  p.x = x; p.out = out; p.n_samples = n_samples; p.n_ch = n_ch; p.hop = nperseg - noverlap;
+  p.n_frames = n_frames; p.bin0 = cut_dc ? 1 : 0; p.n_bins = n_bins; p.output_phase = 0;
+  p.norm_mul[0] = p.norm_mul[1] = 1.f;
+  return pairs == 16 ? run_stft_pairs<16>(p, n_batch * n_ch) : run_stft_pairs<28>(p, n_batch * n_ch);
 }
 
 }  // extern "C"
