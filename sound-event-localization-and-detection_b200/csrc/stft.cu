@@ -67,10 +67,10 @@ __global__ void __launch_bounds__(NT, 1) stft_magphase_kernel(const __grid_const
 namespace stft2 {
 
 // frame-pair kernel (stft_pair.cuh): one persistent block per SM, 16 threads per pair of consecutive frames
-template <int PAIRS, int BPS>
+template <int PAIRS, int BPS, int PLANES>
 __global__ void __launch_bounds__(16 * PAIRS, BPS) stft_pair_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Shared<PAIRS>& s = *reinterpret_cast<Shared<PAIRS>*>(smem_raw);
+  Shared<PAIRS, PLANES>& s = *reinterpret_cast<Shared<PAIRS, PLANES>*>(smem_raw);
   init_tables(s, threadIdx.x);
   __syncthreads();
   Raw raw;
@@ -102,17 +102,17 @@ __global__ void __launch_bounds__(16 * PAIRS, BPS) stft_pair_kernel(const __grid
 
 // BPS blocks per SM (each with its own tables, exchange buffer and tile): two or three smaller blocks decouple the
 // block-wide barriers and overlap one block's row stores with another's butterflies
-template <int PAIRS, int BPS>
+template <int PAIRS, int BPS, int PLANES = 1>
 static int launch_pairs(Params& p, int n_signals, cudaStream_t st) {
-  const size_t smem = sizeof(Shared<PAIRS>);
-  const cudaError_t e = cudaFuncSetAttribute(stft_pair_kernel<PAIRS, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = sizeof(Shared<PAIRS, PLANES>);
+  const cudaError_t e = cudaFuncSetAttribute(stft_pair_kernel<PAIRS, BPS, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SELDQ_ERR_CUDA, "stft (frame pairs) smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
   p.groups = (p.n_frames + 2 * PAIRS - 1) / (2 * PAIRS);
   p.total = (long long)n_signals * p.groups;
   if (p.total >= (1LL << 31)) return fail(SELDQ_ERR_UNSUPPORTED, "stft: too many frame batches (%lld)", p.total);
   const long long slots = (long long)cl::num_sms() * BPS;
   const unsigned grid = (unsigned)(p.total < slots ? p.total : slots);
-  stft_pair_kernel<PAIRS, BPS><<<grid, 16 * PAIRS, smem, st>>>(p);
+  stft_pair_kernel<PAIRS, BPS, PLANES><<<grid, 16 * PAIRS, smem, st>>>(p);
   return check_launch("stft_pair_kernel");
 }
 
@@ -136,6 +136,8 @@ static int pick_pairs(const Params& p, int n_signals) {
 int launch_stft(stft::Params& p, int n_signals, cudaStream_t st) {
   // magnitude-only feature extraction takes the frame-pair kernel (SELDQ_STFT_PAIR=0: always the per-frame kernel)
   static const bool pair_ok = [] { const char* e = getenv("SELDQ_STFT_PAIR"); return !(e && e[0] == '0'); }();
+  if (pair_ok && p.output_phase && p.stats == nullptr && p.out != nullptr)      // two staging planes: 2 blocks of 12 pairs per SM
+    return stft2::launch_pairs<12, 2, 2>(p, n_signals, st);
   if (pair_ok && !p.output_phase && p.stats == nullptr && p.out != nullptr) {
     switch (stft2::pick_pairs(p, n_signals)) {
       case 8: return stft2::launch_pairs<8, 3>(p, n_signals, st);

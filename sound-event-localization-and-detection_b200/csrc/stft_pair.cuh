@@ -11,8 +11,8 @@
 // DFT16 over n2, exchange, real-input untangle, |.|, [bin][frame] staging tile, row stores.  The factor 1/2 of the
 // untangle step is folded into the window table.
 //
-// Magnitude only, float32 or int16 input, optional normalisation; the phase plane, the statistics pass and odd hops
-// stay with stft.cuh (launch_stft picks).  PAIRS frame pairs per batch (block = 16 * PAIRS threads).
+// Magnitude (PLANES = 1) or magnitude + phase (PLANES = 2), float32 or int16 input, optional normalisation; the
+// statistics pass stays with stft.cuh (launch_stft picks).  PAIRS frame pairs per batch (block = 16 * PAIRS threads).
 #pragma once
 #include "stft.cuh"
 
@@ -60,10 +60,10 @@ SELDQ_HD P2 fma(P2 x, P2 y, P2 c) { return mk(fmaf(x.a, y.a, c.a), fmaf(x.b, y.b
 #define SELDQ_SCHED_FENCE()
 #endif
 
-template <int PAIRS>
+template <int PAIRS, int PLANES = 1>
 struct Shared {
   float4 xch[PAIRS][16][17];                 // exchange: one 16 x 16 complex matrix (pitch 17) per frame pair
-  float tile[MAXBINS][2 * PAIRS + 2];        // staging [bin][frame]; even pitch: a frame pair is one 8-byte store
+  float tile[PLANES][MAXBINS][2 * PAIRS + 2];   // staging [plane][bin][frame]; even pitch: a frame pair is one 8-byte store
   float2 tw256[16][16];                      // [k1][j] = W256^(j k1)
   float2 tw512[17][16];                      // [q][j]  = W512^(j + 16 q)
   float2 win[16][16];                        // [r][j]  = HALF the window at samples 2 (j + 16 r), + 1, / sum(w)
@@ -76,8 +76,8 @@ struct Raw {                                 // the thread's 16 complex points o
   float ax[16], ay[16], bx[16], by[16];
 };
 
-template <int PAIRS>
-SELDQ_HD void init_tables(Shared<PAIRS>& s, int tid) {
+template <int PAIRS, int PLANES>
+SELDQ_HD void init_tables(Shared<PAIRS, PLANES>& s, int tid) {
   for (int idx = tid; idx < 17 * 16; idx += 16 * PAIRS) {
     const int q = idx >> 4, j = idx & 15;
     float sn, cs;
@@ -200,8 +200,8 @@ SELDQ_HD void load_raw(const Params& p, Raw& raw, int tid, int signal, int t0) {
 }
 
 // window, DFT16 over r, twiddle, into the exchange buffer
-template <int PAIRS>
-SELDQ_HD void phase_a(Shared<PAIRS>& s, const Raw& raw, Thread& th, int tid) {
+template <int PAIRS, int PLANES>
+SELDQ_HD void phase_a(Shared<PAIRS, PLANES>& s, const Raw& raw, Thread& th, int tid) {
   const int fp = tid >> 4, j = tid & 15;
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
@@ -220,8 +220,8 @@ SELDQ_HD void phase_a(Shared<PAIRS>& s, const Raw& raw, Thread& th, int tid) {
   }
 }
 
-template <int PAIRS>
-SELDQ_HD void phase_b(const Shared<PAIRS>& s, Thread& th, int tid) {
+template <int PAIRS, int PLANES>
+SELDQ_HD void phase_b(const Shared<PAIRS, PLANES>& s, Thread& th, int tid) {
   const int fp = tid >> 4, j = tid & 15;
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) {
@@ -232,8 +232,8 @@ SELDQ_HD void phase_b(const Shared<PAIRS>& s, Thread& th, int tid) {
   dft16(th.re, th.im);          // th[q] = Z[j + 16 q] (half scale)
 }
 
-template <int PAIRS>
-SELDQ_HD void phase_b2(Shared<PAIRS>& s, const Thread& th, int tid) {
+template <int PAIRS, int PLANES>
+SELDQ_HD void phase_b2(Shared<PAIRS, PLANES>& s, const Thread& th, int tid) {
   const int fp = tid >> 4, j = tid & 15;
 #pragma unroll
   for (int q = 0; q < 16; ++q) s.xch[fp][q][j] = make_float4(th.re[q].a, th.re[q].b, th.im[q].a, th.im[q].b);
@@ -249,16 +249,50 @@ SELDQ_HD float mag_of(float m2) {
 #endif
 }
 
-template <int PAIRS>
-SELDQ_HD void emit_bin(const Params& p, Shared<PAIRS>& s, int fp, int kb, P2 xr, P2 xi) {
+// atan2 of both frames: Abramowitz & Stegun 4.4.49 (atan(t) / t as a degree-8 polynomial in t^2 on [0, 1], |error| <=
+// 2e-8) on packed registers, then the octant / quadrant reflections per half.  atan2f costs ~35 scalar instructions per
+// value; this is ~30 for the pair.  Zero magnitude gives 0 (as np.angle(0)), xi = +0 with xr < 0 gives pi.
+SELDQ_HD float refl_(float r, float ay, float ax, float y, float x) {
+  if (ay > ax) r = 1.57079632679489662f - r;
+  if (x < 0.f) r = 3.14159265358979324f - r;
+  return y < 0.f ? -r : r;
+}
+SELDQ_HD P2 atan2_p2(P2 y, P2 x) {
+  const float axa = fabsf(x.a), aya = fabsf(y.a), axb = fabsf(x.b), ayb = fabsf(y.b);
+  const float mxa = fmaxf(axa, aya), mna = fminf(axa, aya), mxb = fmaxf(axb, ayb), mnb = fminf(axb, ayb);
+#if defined(__CUDA_ARCH__)
+  const P2 t = mk(mxa > 0.f ? __fdividef(mna, mxa) : 0.f, mxb > 0.f ? __fdividef(mnb, mxb) : 0.f);
+#else
+  const P2 t = mk(mxa > 0.f ? mna / mxa : 0.f, mxb > 0.f ? mnb / mxb : 0.f);
+#endif
+  const P2 u = mul(t, t);
+  P2 q = mk(0.0028662257f, 0.0028662257f);
+  q = fma(q, u, mk(-0.0161657367f, -0.0161657367f));
+  q = fma(q, u, mk(0.0429096138f, 0.0429096138f));
+  q = fma(q, u, mk(-0.0752896400f, -0.0752896400f));
+  q = fma(q, u, mk(0.1065626393f, 0.1065626393f));
+  q = fma(q, u, mk(-0.1420889944f, -0.1420889944f));
+  q = fma(q, u, mk(0.1999355085f, 0.1999355085f));
+  q = fma(q, u, mk(-0.3333314528f, -0.3333314528f));
+  q = fma(q, u, mk(1.f, 1.f));
+  const P2 r = mul(q, t);
+  return mk(refl_(r.a, aya, axa, y.a, x.a), refl_(r.b, ayb, axb, y.b, x.b));
+}
+
+template <int PAIRS, int PLANES>
+SELDQ_HD void emit_bin(const Params& p, Shared<PAIRS, PLANES>& s, int fp, int kb, P2 xr, P2 xi) {
   if (kb < 0) return;
   const P2 m2 = fma(xi, xi, mul(xr, xr));
-  *reinterpret_cast<float2*>(&s.tile[kb][2 * fp]) = make_float2(mag_of(m2.a), mag_of(m2.b));
+  *reinterpret_cast<float2*>(&s.tile[0][kb][2 * fp]) = make_float2(mag_of(m2.a), mag_of(m2.b));
+  if (PLANES == 2) {
+    const P2 ph = atan2_p2(xi, xr);
+    *reinterpret_cast<float2*>(&s.tile[PLANES - 1][kb][2 * fp]) = make_float2(ph.a, ph.b);
+  }
 }
 
 // real-input untangle (window at half scale): R[k] = E + W512^k O, E = Z[k] + conj Z[256-k], O = (Z[k] - conj Z[256-k]) / i
-template <int PAIRS>
-SELDQ_HD void phase_c(const Params& p, Shared<PAIRS>& s, const Thread& th, int tid) {
+template <int PAIRS, int PLANES>
+SELDQ_HD void phase_c(const Params& p, Shared<PAIRS, PLANES>& s, const Thread& th, int tid) {
   const int fp = tid >> 4, j = tid & 15;
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
@@ -278,8 +312,8 @@ SELDQ_HD void phase_c(const Params& p, Shared<PAIRS>& s, const Thread& th, int t
 // rows of 2 * PAIRS consecutive frames leave the tile, a frame pair (8 bytes) per lane; warp w takes rows w, w + NW, ...
 // (the row loop is the whole cost of this phase -- one shared-memory load and one store per row and warp -- so the
 // common case carries nothing else: pointers advance by constants, alignment and range are decided once per batch)
-template <int PAIRS>
-SELDQ_HD void phase_d(const Params& p, const Shared<PAIRS>& s, int tid, int signal, int t0) {
+template <int PAIRS, int PLANES>
+SELDQ_HD void phase_d(const Params& p, const Shared<PAIRS, PLANES>& s, int tid, int signal, int t0) {
   constexpr int NW = PAIRS / 2;                       // warps per block
   constexpr int PITCH = 2 * PAIRS + 2;
   constexpr int LW = PAIRS <= 8 ? 8 : (PAIRS <= 16 ? 16 : 32);      // lanes per row: a warp stores 32 / LW rows at once
@@ -290,29 +324,33 @@ SELDQ_HD void phase_d(const Params& p, const Shared<PAIRS>& s, int tid, int sign
   const int t = t0 + 2 * fp;
   if (t >= p.n_frames) return;
   const bool both = t + 1 < p.n_frames;
-  const bool plain = p.norm_sub[0] == 0.f && p.norm_mul[0] == 1.f;
+  const int b = signal / p.n_ch, c = signal - b * p.n_ch;
   const int row0 = warp * RG + rg;
   const long long step = (long long)(NW * RG) * p.n_frames;
-  float* dst = p.out + ((long long)signal * p.n_bins + row0) * p.n_frames + t;      // magnitude plane: (b n_ch + c) = signal
-  const float* src = &s.tile[row0][2 * fp];
-  const bool vec = both && ((reinterpret_cast<unsigned long long>(dst) | (unsigned long long)(step * 4) |
-                             (unsigned long long)((long long)p.n_frames * 4)) & 7ull) == 0;
-  if (vec && plain) {
+#pragma unroll
+  for (int pl = 0; pl < PLANES; ++pl) {
+    const bool plain = p.norm_sub[pl] == 0.f && p.norm_mul[pl] == 1.f;
+    float* dst = p.out + ((long long)((b * PLANES + pl) * p.n_ch + c) * p.n_bins + row0) * p.n_frames + t;
+    const float* src = &s.tile[pl][row0][2 * fp];
+    const bool vec = both && ((reinterpret_cast<unsigned long long>(dst) | (unsigned long long)(step * 4) |
+                               (unsigned long long)((long long)p.n_frames * 4)) & 7ull) == 0;
+    if (vec && plain) {
 #pragma unroll 4
-    for (int kb = row0; kb < p.n_bins; kb += NW * RG, dst += step, src += NW * RG * PITCH)
-      *reinterpret_cast<float2*>(dst) = *reinterpret_cast<const float2*>(src);
-    return;
-  }
-  const float sub_ = p.norm_sub[0], mul_ = p.norm_mul[0];
-  for (int kb = row0; kb < p.n_bins; kb += NW * RG, dst += step, src += NW * RG * PITCH) {
-    float2 v = *reinterpret_cast<const float2*>(src);
-    v.x = (v.x - sub_) * mul_;
-    v.y = (v.y - sub_) * mul_;
-    if (vec) {
-      *reinterpret_cast<float2*>(dst) = v;
-    } else {
-      dst[0] = v.x;
-      if (both) dst[1] = v.y;
+      for (int kb = row0; kb < p.n_bins; kb += NW * RG, dst += step, src += NW * RG * PITCH)
+        *reinterpret_cast<float2*>(dst) = *reinterpret_cast<const float2*>(src);
+      continue;
+    }
+    const float sub_ = p.norm_sub[pl], mul_ = p.norm_mul[pl];
+    for (int kb = row0; kb < p.n_bins; kb += NW * RG, dst += step, src += NW * RG * PITCH) {
+      float2 v = *reinterpret_cast<const float2*>(src);
+      v.x = (v.x - sub_) * mul_;
+      v.y = (v.y - sub_) * mul_;
+      if (vec) {
+        *reinterpret_cast<float2*>(dst) = v;
+      } else {
+        dst[0] = v.x;
+        if (both) dst[1] = v.y;
+      }
     }
   }
 }

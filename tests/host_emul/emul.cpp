@@ -267,13 +267,13 @@ static void run_wgrad(const simt::WgradParams& p) {
       }
 }
 
-// frame-pair kernel (csrc/stft_pair.cuh), PAIRS = 28 (the shape the launcher picks for 8 signals x 4800 frames) and 16
-template <int PAIRS>
+// frame-pair kernel (csrc/stft_pair.cuh): PAIRS = 28 / 16 magnitude only, PAIRS = 12 with the phase plane
+template <int PAIRS, int PLANES>
 static int run_stft_pairs(stft::Params& p, int n_signals) {
   p.groups = (p.n_frames + 2 * PAIRS - 1) / (2 * PAIRS);
   p.total = (long long)n_signals * p.groups;
   constexpr int NT = 16 * PAIRS;
-  stft2::Shared<PAIRS>* sh = new stft2::Shared<PAIRS>;
+  stft2::Shared<PAIRS, PLANES>* sh = new stft2::Shared<PAIRS, PLANES>;
   std::vector<stft2::Thread> th(NT);
   std::vector<stft2::Raw> raw(NT);
   for (int t = 0; t < NT; ++t) stft2::init_tables(*sh, t);
@@ -401,15 +401,16 @@ int emul_stft(const float* x, int n_batch, int n_ch, long long n_samples, int np
 }
 
 int emul_stft_pairs(const float* x, int n_batch, int n_ch, long long n_samples, int nperseg, int noverlap, int cut_dc,
-                    int cut_last, int pairs, float* out) {
+                    int output_phase, int cut_last, int pairs, float* out) {
   int n_bins, n_frames;
   int rc = stft_shape(n_samples, nperseg, noverlap, cut_dc, cut_last, &n_bins, &n_frames);
   if (rc) return rc;
   stft::Params p{};
   p.x = x; p.out = out; p.n_samples = n_samples; p.n_ch = n_ch; p.hop = nperseg - noverlap;
-  p.n_frames = n_frames; p.bin0 = cut_dc ? 1 : 0; p.n_bins = n_bins; p.output_phase = 0;
+  p.n_frames = n_frames; p.bin0 = cut_dc ? 1 : 0; p.n_bins = n_bins; p.output_phase = output_phase;
   p.norm_mul[0] = p.norm_mul[1] = 1.f;
-  return pairs == 16 ? run_stft_pairs<16>(p, n_batch * n_ch) : run_stft_pairs<28>(p, n_batch * n_ch);
+  if (output_phase) return run_stft_pairs<12, 2>(p, n_batch * n_ch);
+  return pairs == 16 ? run_stft_pairs<16, 1>(p, n_batch * n_ch) : run_stft_pairs<28, 1>(p, n_batch * n_ch);
 }
 
 }  // extern "C"

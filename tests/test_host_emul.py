@@ -119,15 +119,25 @@ def test_emulated_stft_kernel_matches_golden(emul, name):
 @pytest.mark.parametrize("name", golden_names("stft"))
 def test_emulated_frame_pair_stft_kernel_matches_golden(emul, name, pairs):
     """csrc/stft_pair.cuh (two consecutive frames per packed register, 16 threads per frame pair): the magnitude plane
-    of every STFT fixture, with a batch size that divides the frame count (16 pairs) and one that does not (28)."""
+    of every STFT fixture, with a batch size that divides the frame count (16 pairs) and one that does not (28), and
+    the phase plane (packed polynomial atan2, 12 pairs per batch) where the fixture has one."""
     meta, d = load_golden(name)
     x = np.ascontiguousarray(d["x"], np.float32)
     C = x.shape[0]
     out = np.full((C,) + d["out"].shape[1:], np.nan, np.float32)
-    rc = emul.emul_stft_pairs(fptr(x), 1, C, ctypes.c_longlong(x.shape[1]), meta["nperseg"], meta["noverlap"], 1, 1,
+    rc = emul.emul_stft_pairs(fptr(x), 1, C, ctypes.c_longlong(x.shape[1]), meta["nperseg"], meta["noverlap"], 1, 0, 1,
                               pairs, fptr(out))
     assert rc == 0, emul.emul_last_error()
     assert A.rel_err(out, d["out"][:C]) < 1e-5
+    if meta["output_phase"] and pairs == 16:
+        out = np.full(d["out"].shape, np.nan, np.float32)
+        rc = emul.emul_stft_pairs(fptr(x), 1, C, ctypes.c_longlong(x.shape[1]), meta["nperseg"], meta["noverlap"], 1, 1,
+                                  1, 12, fptr(out))
+        assert rc == 0, emul.emul_last_error()
+        assert A.rel_err(out[:C], d["out"][:C]) < 1e-5
+        mag = d["out"][:C]
+        dphi = np.abs(np.angle(np.exp(1j * (out[C:].astype(np.float64) - d["out"][C:]))))
+        assert (dphi * mag / mag.max()).max() < 1e-5
 
 
 def test_dq_linear_runs_as_a_1x1_convolution_with_its_own_block_table(emul):
