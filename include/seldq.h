@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SELDQ_ABI_VERSION 3
+#define SELDQ_ABI_VERSION 4
 
 typedef enum {
   SELDQ_OK = 0,
