@@ -81,7 +81,19 @@ def mha_forward(self, v, k, q, mask=None):
     """MultiHeadAttention.forward (model.py:25-51) for any module with the reference's attributes
     (values / keys / queries / fc_out, num_heads, head_dim).  Inputs are (N, L, E)."""
     n, length = q.shape[0], q.shape[1]
-    vc, kc, qc = self.values(v.permute(0, 2, 1)), self.keys(k.permute(0, 2, 1)), self.queries(q.permute(0, 2, 1))
+    convs = (self.values, self.keys, self.queries)
+    if (v is k and k is q and n == 1 and q.is_cuda
+            and all(isinstance(c, nn.Conv1d) and c.bias is None and c.kernel_size == (1,) and c.stride == (1,)
+                    and c.padding == (0,) and c.dilation == (1,) and c.groups == 1 for c in convs)
+            and self.values.weight.shape == self.keys.weight.shape == self.queries.weight.shape):
+        # self-attention (model.py:218 passes the same tensor three times): the three 1x1 projections of model.py:33-35
+        # as ONE convolution over the stacked weights -- one GEMM forward, one dgrad and one wgrad GEMM backward instead
+        # of three each (the per-sample slices of the (1, 3E, L) result are contiguous)
+        e = self.values.weight.shape[0]
+        vkq = tF.conv1d(q.permute(0, 2, 1), torch.cat([c.weight for c in convs], 0))
+        vc, kc, qc = vkq.split(e, dim=1)              # one node: its backward is a single concatenation
+    else:
+        vc, kc, qc = self.values(v.permute(0, 2, 1)), self.keys(k.permute(0, 2, 1)), self.queries(q.permute(0, 2, 1))
     if (mask is None and kc.shape == qc.shape == vc.shape and self.head_dim * self.num_heads == qc.shape[1]
             and _F.attention_supported(qc, self.num_heads)):
         # the repository's fused attention kernels (csrc/attention.cu): the (N, heads, S, S) energy / attention
