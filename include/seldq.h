@@ -54,9 +54,14 @@ typedef enum {
   SELDQ_ALG_REAL = 0,      /* nc = 1, plain convolution / linear                              */
   SELDQ_ALG_Q = 1,         /* nc = 4, Wq[a*O+o, b*I+i] = sign[a][b] * W_{a^b}[o,i]            */
   SELDQ_ALG_DQ = 2,        /* nc = 8, [[Q(w),0],[Q(w2),Q(w)]]; linear uses the transposed form */
-  SELDQ_ALG_DQ_LINEAR = 3  /* nc = 8, the block table of dual_quaternion_linear (dual_quaternion_ops.py:170-188)
+  SELDQ_ALG_DQ_LINEAR = 3, /* nc = 8, the block table of dual_quaternion_linear (dual_quaternion_ops.py:170-188)
                               used as a convolution table: lets a DQ linear layer run as a 1x1 convolution over
                               the transposed matrices on the tensor-core path (functional.block_linear)          */
+  /* the linear layers as 1x1 convolutions that read (and, in seldq_conv_wgrad, write) the layer's OWN compact
+   * tensors, stored (in/nc, out/nc) as quaternion_layers.py:235-238 / dual_quaternion_layers.py keep them: no
+   * transposed copies, the weight gradient lands in the parameters' gradient buffers.  Kernel 1 x 1 only. */
+  SELDQ_ALG_Q_LINEAR_IO = 4,    /* table of SELDQ_ALG_Q         */
+  SELDQ_ALG_DQ_LINEAR_IO = 5    /* table of SELDQ_ALG_DQ_LINEAR */
 } seldq_algebra_t;
 
 /* arithmetic the contraction runs in */

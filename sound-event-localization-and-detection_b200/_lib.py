@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libseldq.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
 ALG_REAL, ALG_Q, ALG_DQ, ALG_DQ_LINEAR = 0, 1, 2, 3
+ALG_Q_LINEAR_IO, ALG_DQ_LINEAR_IO = 4, 5          # linear layers as 1x1 convolutions on their own (in, out) tensors
 PREC_FP32, PREC_BF16 = 0, 1
 PASS_FWD, PASS_DGRAD, PASS_WGRAD = 0, 1, 2
 ERR_INVALID, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = -1, -2, -3, -4

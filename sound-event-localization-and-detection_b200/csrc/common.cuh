@@ -48,6 +48,7 @@ inline bool make_block_table(int algebra, bool dq_linear, BlockTable* t) {
   memset(t, 0, sizeof(*t));
   for (int a = 0; a < 8; ++a)
     for (int b = 0; b < 8; ++b) t->widx[a][b] = -1;
+  if (algebra == SELDQ_ALG_Q_LINEAR_IO) algebra = SELDQ_ALG_Q;      // quaternion_linear's table is the convolution's
   if (algebra == SELDQ_ALG_REAL) {
     t->nc = 1; t->nw = 1; t->widx[0][0] = 0; t->sign[0][0] = 1;
     return true;
@@ -58,7 +59,7 @@ inline bool make_block_table(int algebra, bool dq_linear, BlockTable* t) {
       for (int b = 0; b < 4; ++b) { t->widx[a][b] = (int8_t)(a ^ b); t->sign[a][b] = S[a][b]; }
     return true;
   }
-  if (algebra == SELDQ_ALG_DQ_LINEAR) { algebra = SELDQ_ALG_DQ; dq_linear = true; }
+  if (algebra == SELDQ_ALG_DQ_LINEAR || algebra == SELDQ_ALG_DQ_LINEAR_IO) { algebra = SELDQ_ALG_DQ; dq_linear = true; }
   if (algebra == SELDQ_ALG_DQ) {
     t->nc = 8; t->nw = 8;
     for (int a = 0; a < 8; ++a)

@@ -43,6 +43,11 @@ inline int make_conv_geom(const seldq_conv_desc_t* d, int pass, ConvGeom* g) {
   g->ph = d->pad_h; g->pw = d->pad_w;
   g->dh = d->dil_h; g->dw = d->dil_w;
   g->wsT = 1; g->wsI = d->k_h * d->k_w; g->wsO = g->Ic * g->wsI;
+  if (d->algebra == SELDQ_ALG_Q_LINEAR_IO || d->algebra == SELDQ_ALG_DQ_LINEAR_IO) {
+    // the linear layer's own compact tensors, (in/nc, out/nc) row-major
+    if (d->k_h != 1 || d->k_w != 1) return fail(SELDQ_ERR_INVALID, "the linear-layer algebras serve 1 x 1 kernels only");
+    g->wsO = 1; g->wsI = g->Oc; g->wsT = 0;
+  }
   const long long xs[4] = {(long long)d->cin * d->in_h * d->in_w, (long long)d->in_h * d->in_w, d->in_w, 1};
   const long long ys[4] = {(long long)d->cout * oh * ow, (long long)oh * ow, ow, 1};
   if (pass == SELDQ_PASS_DGRAD) {

@@ -13,10 +13,11 @@ import os
 import torch
 
 from . import _lib
-from ._lib import ALG_DQ, ALG_DQ_LINEAR, ALG_Q, ALG_REAL, PASS_DGRAD, PASS_FWD, PASS_WGRAD, PREC_BF16, PREC_FP32
+from ._lib import ALG_DQ, ALG_DQ_LINEAR, ALG_DQ_LINEAR_IO, ALG_Q, ALG_Q_LINEAR_IO, ALG_REAL, PASS_DGRAD, PASS_FWD, PASS_WGRAD, PREC_BF16, PREC_FP32
 
 _PRECISION = {"fp32": PREC_FP32, "bf16": PREC_BF16}[os.environ.get("SELDQ_PRECISION", "bf16").lower()]
-_NCOMP = {ALG_REAL: 1, ALG_Q: 4, ALG_DQ: 8, ALG_DQ_LINEAR: 8}
+_NCOMP = {ALG_REAL: 1, ALG_Q: 4, ALG_DQ: 8, ALG_DQ_LINEAR: 8, ALG_Q_LINEAR_IO: 4, ALG_DQ_LINEAR_IO: 8}
+_IO_LAYOUT = (ALG_Q_LINEAR_IO, ALG_DQ_LINEAR_IO)      # compact tensors stored (in/nc, out/nc): the linear layers' own
 
 
 def _apply_tf32_policy():
@@ -112,7 +113,7 @@ def profile_collect():
 def _conv_flop(desc, oh, ow):
     """Algorithmic FLOPs of one pass: only the non-zero blocks of the expanded weight count
     (DQ: 0.75 of dense)."""
-    nz = 0.75 if desc.algebra in (ALG_DQ, ALG_DQ_LINEAR) else 1.0
+    nz = 0.75 if desc.algebra in (ALG_DQ, ALG_DQ_LINEAR, ALG_DQ_LINEAR_IO) else 1.0
     return 2.0 * nz * desc.cout * desc.cin * desc.k_h * desc.k_w * desc.batch * oh * ow
 
 
@@ -306,9 +307,10 @@ class _BlockConv(torch.autograd.Function):
             stride, padding, dilation = (1, _pair(stride)[1]), (0, _pair(padding)[1]), (1, _pair(dilation)[1])
         else:
             stride, padding, dilation = _pair(stride), _pair(padding), _pair(dilation)
-        ksize = tuple(w0.shape[2:])
-        cout = w0.shape[0] * nc
-        if w0.shape[1] * nc != x.shape[1]:
+        io = algebra in _IO_LAYOUT
+        ksize = (1,) * (x.dim() - 2) if io else tuple(w0.shape[2:])
+        cout = (w0.shape[1] if io else w0.shape[0]) * nc
+        if (w0.shape[0] if io else w0.shape[1]) * nc != x.shape[1]:
             raise RuntimeError("Given groups=1, weight of size %s (x%d components), expected input%s to have %d "
                                "channels, but got %d channels instead"
                                % (list(w0.shape), nc, list(x.shape), w0.shape[1] * nc, x.shape[1]))
@@ -573,19 +575,13 @@ def block_conv(x, weights, bias, stride, padding, dilation, algebra, prec=None):
 
 
 def _linear_as_conv(x, weights, bias, algebra):
-    """(rows, in) @ expand(weights) on the tensor-core path: the matrices are transposed into (1, features, rows)
-    NCW tensors and the layer runs as a 1x1 convolution whose block table is the linear layer's
-    (SELDQ_ALG_DQ_LINEAR for dual_quaternion_linear; quaternion_linear shares the convolution's table)."""
-    conv_alg = ALG_DQ_LINEAR if algebra == ALG_DQ else algebra
-    global _PACK_CACHE
-    # (in/nc, out/nc) -> (out/nc, in/nc, 1): one stacked transpose for all compact tensors (2 launches, not 2 per
-    # tensor; the slices of the stacked result are contiguous)
-    ws = tuple(w.unsqueeze(-1) for w in torch.stack(tuple(weights), 0).transpose(1, 2).contiguous().unbind(0))
-    prev, _PACK_CACHE = _PACK_CACHE, False
-    try:
-        y = _BlockConv.apply(x.t().contiguous().unsqueeze(0), bias, 1, 0, 1, conv_alg, PREC_BF16, *ws)
-    finally:
-        _PACK_CACHE = prev
+    """(rows, in) @ expand(weights) on the tensor-core path: x is transposed into a (1, in, rows) NCW tensor and the
+    layer runs as a 1x1 convolution that reads the layer's OWN compact tensors in their (in/nc, out/nc) layout
+    (SELDQ_ALG_Q_LINEAR_IO / SELDQ_ALG_DQ_LINEAR_IO: the block table of quaternion_linear / dual_quaternion_linear):
+    no transposed weight copies, the packed tiles live in the cache the trainer re-packs in one launch, and the
+    weight gradient is accumulated straight into the parameters' gradient buffers."""
+    conv_alg = ALG_DQ_LINEAR_IO if algebra == ALG_DQ else ALG_Q_LINEAR_IO
+    y = _BlockConv.apply(x.t().contiguous().unsqueeze(0), bias, 1, 0, 1, conv_alg, PREC_BF16, *weights)
     return y[0].t()
 
 

@@ -166,6 +166,34 @@ def test_dq_linear_runs_as_a_1x1_convolution_with_its_own_block_table(emul):
         assert A.rel_err(gws[i][:, :, 0].T, d["gw%d" % i]) < 1e-5, i
 
 
+@pytest.mark.parametrize("name,alg", [("linear_dq_c48", 5), ("linear_dq", 5), ("linear_q", 4)])
+def test_linear_layers_run_as_1x1_convolutions_on_their_own_tensors(emul, name, alg):
+    """SELDQ_ALG_Q_LINEAR_IO (4) / SELDQ_ALG_DQ_LINEAR_IO (5): the same 1x1 convolution reading -- and, in the weight
+    gradient, writing -- the linear layer's compact tensors in their own (in/nc, out/nc) layout: no transposed copies
+    (functional._linear_as_conv), against the reference fixtures of quaternion_linear / dual_quaternion_linear."""
+    meta, d = load_golden(name)
+    nw = 8 if alg == 5 else 4
+    x = np.ascontiguousarray(d["x"], np.float32)                      # (rows, in)
+    gy = np.ascontiguousarray(d["gy"], np.float32)                    # (rows, out)
+    rows, fin = x.shape
+    fout = gy.shape[1]
+    ws = [np.ascontiguousarray(d["w%d" % i], np.float32) for i in range(nw)]                   # (in/nc, out/nc) as stored
+    desc = ConvDesc(alg, 0, 1, 1, fin, fout, 1, rows, 1, 1, 1, 1, 0, 0, 1, 1)
+    xc = np.ascontiguousarray(x.T[None], np.float32)                  # (1, in, rows)
+    y = np.full((1, fout, rows), np.nan, np.float32)
+    b = np.ascontiguousarray(d["b"], np.float32) if "b" in d else None
+    assert emul.emul_conv(ctypes.byref(desc), 0, fptr(xc), ptr_array(ws), None if b is None else fptr(b), fptr(y)) == 0
+    assert A.rel_err(y[0].T, d["y"]) < 1e-5
+    gyc = np.ascontiguousarray(gy.T[None], np.float32)
+    gx = np.full(xc.shape, np.nan, np.float32)
+    assert emul.emul_conv(ctypes.byref(desc), 1, fptr(gyc), ptr_array(ws), None, fptr(gx)) == 0
+    assert A.rel_err(gx[0].T, d["gx"]) < 1e-5
+    gws = [np.zeros_like(w) for w in ws]
+    assert emul.emul_conv_wgrad(ctypes.byref(desc), fptr(xc), fptr(gyc), ptr_array(gws), 2) == 0
+    for i in range(nw):
+        assert A.rel_err(gws[i], d["gw%d" % i]) < 1e-5, i
+
+
 # ---- channels-last tensor-core path: the host plan (csrc/conv_cl_plan.h) through a CPU model of the kernel's data flow ---
 # tests/host_emul/emul.cpp run_cl_fprop: real plan_fprop (fusion sets, MMA op table, epilogue column / sign table, row-shared
 # taps, chunk masks, unit schedule) + real pack mapping, plain-loop "MMAs" in double.  A wrong table entry, tile offset, slot
