@@ -20,7 +20,7 @@ timeout 600 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__by
   -k regex:qconv_cl_fprop_kernel --csv --log-file $O/${TAG}_ncu_traffic.csv python tools/ncu_step.py > $O/${TAG}_ncu_traffic.log 2>&1; echo "ncu traffic rc=$?"
 # full captures of the top kernels, a few launches each (ncu replays every kernel ~40 times)
 i=0
-for spec in "qconv_cl_fprop_kernel:14" "qconv_cl_wgrad_kernel:6" "first_layer_bwd_kernel:1" "cnn_tail_fwd_vec_kernel:2" "cnn_tail_bwd_apply_vec_kernel:1" "stft_magphase_kernel:2" "gate_fwd_kernel:1" "gate_bwd_apply_kernel:1"; do
+for spec in "qconv_cl_fprop_kernel:14" "qconv_cl_wgrad_kernel:6" "first_layer_bwd_kernel:1" "cnn_tail_fwd_vec_kernel:2" "cnn_tail_bwd_apply_vec_kernel:1" "stft_:2" "gate_fwd_kernel:1" "gate_bwd_apply_kernel:1"; do
   k="${spec%%:*}"; c="${spec##*:}"; i=$((i+1))
   SELDQ_PDL=0 SELDQ_SIDE_WGRAD=0 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
     -k regex:"$k" -c $c -o $O/${TAG}_ncu_full_$i -f python tools/ncu_step.py --stft > $O/${TAG}_ncu_full_$i.log 2>&1; echo "ncu full $k rc=$?"
