@@ -140,6 +140,28 @@ def test_emulated_frame_pair_stft_kernel_matches_golden(emul, name, pairs):
         assert (dphi * mag / mag.max()).max() < 1e-5
 
 
+@pytest.mark.parametrize("n_samples", [700, 5000, 12345, 400 * 7 + 13])
+def test_emulated_frame_pair_stft_ragged_lengths_against_oracle(emul, n_samples):
+    """Frame-pair kernel on lengths that leave odd frame counts, partial frame pairs and partial batches, signals that
+    start / end inside a frame (zero boundary extension), one and three channels: magnitude (16 and 28 pairs per batch)
+    and magnitude + phase (12 pairs) against oracle.spectrum_fast."""
+    rng = np.random.default_rng(n_samples)
+    for C in (1, 3):
+        x = (0.3 * rng.standard_normal((C, n_samples))).astype(np.float32)
+        for phase in (0, 1):
+            ref = A.spectrum_fast(x.astype(np.float64), nperseg=512, noverlap=112, output_phase=bool(phase))
+            for pairs in ((12,) if phase else (16, 28)):
+                out = np.full(ref.shape, np.nan, np.float32)
+                rc = emul.emul_stft_pairs(fptr(x), 1, C, ctypes.c_longlong(n_samples), 512, 112, 1, phase, 1, pairs, fptr(out))
+                assert rc == 0, emul.emul_last_error()
+                assert np.isfinite(out).all()
+                assert A.rel_err(out[:C], ref[:C]) < 1e-5
+                if phase:
+                    mag = ref[:C]
+                    dphi = np.abs(np.angle(np.exp(1j * (out[C:].astype(np.float64) - ref[C:]))))
+                    assert (dphi * mag / mag.max()).max() < 1e-5
+
+
 def test_dq_linear_runs_as_a_1x1_convolution_with_its_own_block_table(emul):
     """functional._linear_as_conv: dual_quaternion_linear (dual_quaternion_ops.py:156-203) on (rows, in) equals a
     1x1 convolution over the transposed matrices with the block table SELDQ_ALG_DQ_LINEAR (= 3) and transposed
