@@ -11,13 +11,26 @@
 namespace seldq {
 namespace cl {
 
-// Unit schedule of a CTA (shared by the kernel and its CPU model): units are ordered heaviest group first; round r
-// hands unit r*G + b to CTA b in even rounds and r*G + (G-1-b) in odd rounds (snake order), so the few units of a
-// last, partial round go to the CTAs that hold the lightest units of the round before instead of the heaviest.
+// Unit schedule of a CTA (shared by the kernel and its CPU model): units are ordered heaviest group first.
 // G = CTAs that share the problem, b = this CTA's index among them.  Returns -1 when the CTA sits a round out.
+//   * many rounds (the CNN layers): round r hands unit r*G + b to CTA b in even rounds and r*G + (G-1-b) in odd rounds
+//     (snake order), so every CTA gets a mix of heavy and light units;
+//   * two or three rounds (the TCN launches: 152 units on 74 CTAs): a CTA's time is set by the NUMBER of its units -- each
+//     ends in a ~2.3 us epilogue, heavy or light, and the epilogues of a CTA do not overlap each other (tools/
+//     fprop_trace.py) -- so the `rem` CTAs that must take one unit more than the others take the LIGHTEST units (the tail
+//     of the list) in every round, and the others share the rest in snake order: 64 x (heavy, light), 6 x (heavy, heavy),
+//     4 x (light, light, light) instead of 4 x (heavy, light, light) finishing 2 us after everybody else.
 SELDQ_HD int unit_of_round(int round, int total_units, int G, int b) {
-  const int u = round * G + ((round & 1) ? G - 1 - b : b);
-  return u < total_units ? u : -1;
+  const int R = (total_units + G - 1) / G;            // rounds of the longest CTAs
+  const int rem = total_units - (R - 1) * G;          // CTAs with R units
+  if (R <= 1 || R > 3 || rem == G) {
+    const int u = round * G + ((round & 1) ? G - 1 - b : b);
+    return u < total_units ? u : -1;
+  }
+  if (b < rem) return round < R ? total_units - rem * R + round * rem + b : -1;
+  if (round >= R - 1) return -1;
+  const int Gs = G - rem, bb = b - rem;               // the head of the list holds exactly (R - 1) * Gs units
+  return round * Gs + ((round & 1) ? Gs - 1 - bb : bb);
 }
 
 // compact fp32 weights -> bf16 UMMA B tiles [img][tap][j][NBp x 16] (K-major, no swizzle; see the dense
