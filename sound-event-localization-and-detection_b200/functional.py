@@ -285,6 +285,15 @@ def _conv_desc(algebra, prec, x_shape, cout, ksize, stride, padding, dilation):
 
 
 _PACK_CACHE = True      # False while _linear_as_conv builds its node: its weights are per-call temporaries
+_CONV_BWD_FORK = os.environ.get("SELDQ_CONV_BWD_FORK", "1") != "0"
+_BWD_SIDE = {}
+
+
+def _bwd_side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _BWD_SIDE:
+        _BWD_SIDE[key] = torch.cuda.Stream(device=dev)
+    return _BWD_SIDE[key]
 
 
 class _BlockConv(torch.autograd.Function):
@@ -364,6 +373,9 @@ class _BlockConv(torch.autograd.Function):
             gy_cl = gy_t16 = None
             if bf16 and (need_x or need_w_any):
                 gy_cl, gy_t16 = stage_operand(gy, desc, 1, want_cl=need_x, want_t16=need_w_any)
+            fork_ev = None
+            if bf16 and need_x and need_w_any and _CONV_BWD_FORK and _PROF is None:
+                fork_ev = torch.cuda.current_stream().record_event()       # operands staged: the weight gradient may start here
             if need_x:
                 if desc.ndim == 1:
                     gx = torch.empty((desc.batch, desc.cin, desc.in_w), dtype=torch.float32, device=dev)
@@ -391,10 +403,26 @@ class _BlockConv(torch.autograd.Function):
                     work = torch.empty(L.seldq_conv_workspace_bytes(ctypes.byref(desc), PASS_WGRAD), dtype=torch.uint8,
                                        device=dev)
                 kern = "qconv_cl_wgrad_kernel" if bf16 else "wgrad_simt_kernel"
-                _timed(kern, _conv_flop(desc, *ctx.out_hw), 1 + (1 if need_b else 0), lambda: _lib.check(
-                    L.seldq_conv_wgrad(ctypes.byref(desc), _ptr(x32), _ptr(x_cl), gy.data_ptr(), _ptr(gy_t16), gp,
-                                       _ptr(gb), 1 if direct else 0, _ptr(work),
-                                       0 if work is None else work.numel(), _stream())))
+
+                def run_wgrad():
+                    _timed(kern, _conv_flop(desc, *ctx.out_hw), 1 + (1 if need_b else 0), lambda: _lib.check(
+                        L.seldq_conv_wgrad(ctypes.byref(desc), _ptr(x32), _ptr(x_cl), gy.data_ptr(), _ptr(gy_t16), gp,
+                                           _ptr(gb), 1 if direct else 0, _ptr(work),
+                                           0 if work is None else work.numel(), _stream())))
+
+                # The input-gradient and weight-gradient passes are independent; on the small layers of the TC tail
+                # neither fills the SMs (76 and 40 work units on 148 SMs), so with both wanted the weight gradient
+                # runs on a forked stream next to the dgrad launch above and is joined before this node returns
+                # (every tensor it touches outlives the join).  SELDQ_CONV_BWD_FORK=0: one after the other.
+                if bf16 and need_x and _CONV_BWD_FORK and _PROF is None:
+                    cur = torch.cuda.current_stream()
+                    side = _bwd_side_stream(dev)
+                    side.wait_event(fork_ev)
+                    with torch.cuda.stream(side):
+                        run_wgrad()
+                    cur.wait_stream(side)
+                else:
+                    run_wgrad()
                 if direct:                            # already added into param.grad
                     gws, gb = [None] * len(weights), None
         return (gx, gb, None, None, None, None, None) + tuple(gws)
