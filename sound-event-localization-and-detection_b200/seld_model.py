@@ -317,24 +317,82 @@ def convtc_block_forward(self, x):
     return x.permute(0, 2, 1)                         # (B, T/8, V)
 
 
+_HEAD_FORK = _os.environ.get("SELDQ_HEAD_FORK", "1") != "0"
+_FORK_SIDE = {}
+
+
+def _forked(fn_main, fn_side, ref):
+    """(fn_main(), fn_side()) with fn_side on a forked CUDA stream, joined before the results are used.  Autograd runs
+    each node's backward on the stream of its forward, so the backward passes overlap the same way.  Tensors that
+    cross the join are registered with the stream that consumes them.  Capturable into a CUDA graph."""
+    if not (_HEAD_FORK and isinstance(ref, torch.Tensor) and ref.is_cuda):
+        return fn_main(), fn_side()
+    key = (ref.device.type, ref.device.index)
+    side = _FORK_SIDE.get(key)
+    if side is None:
+        side = _FORK_SIDE[key] = torch.cuda.Stream(device=ref.device)
+    cur = torch.cuda.current_stream(ref.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        out_side = fn_side()
+    out_main = fn_main()
+    cur.wait_stream(side)
+    out_side.record_stream(cur)
+    return out_main, out_side
+
+
+def seld_heads(self, x):
+    """(self.sed(x), self.doa(x)) of model.py:473-474.  The two heads are independent chains of small kernels (Q / DQ
+    linear, dropout, nn.Linear, activation): the DOA head runs on a forked stream next to the SED head
+    (SELDQ_HEAD_FORK=0: one after the other)."""
+    sed, doa = _forked(lambda: self.sed(x), lambda: self.doa(x), x)
+    if x.is_cuda and _HEAD_FORK:
+        x.record_stream(_FORK_SIDE[(x.device.type, x.device.index)])
+    return sed, doa
+
+
+def seld_model_forward(self, x):
+    """SELD_Model.forward (model.py:461-480) for any module with the reference's attributes: same tensors, same order
+    of the concatenation; the two ConvTC branches of the parallel configurations and the two heads each run as a
+    forked pair."""
+    if self.parallel_ConvTC_block in _TWO_BRANCH:
+        if self.parallel_magphase:
+            x_a = torch.cat((x[:, :4], x[:, 8:12]), 1)      # mic A magnitude + phase
+            x_b = torch.cat((x[:, 4:8], x[:, 12:]), 1)      # mic B magnitude + phase
+        else:
+            half = self.input_channels // 2
+            x_a, x_b = x[:, :half].contiguous(), x[:, half:].contiguous()
+        a, b = _forked(lambda: self.branch_A(x_a), lambda: self.branch_B(x_b), x)
+        if x.is_cuda and _HEAD_FORK:
+            x_b.record_stream(_FORK_SIDE[(x.device.type, x.device.index)])
+        x = torch.cat((a, b), 2)
+    else:
+        x = self.seld_block(x)
+    sed, doa = seld_heads(self, x)
+    if getattr(self, "verbose", False):
+        print('sed prediction:  ', sed.shape)
+        print('doa prediction: ', doa.shape)
+    return sed, doa
+
+
 _PATCHED = set()
 
 
 def patch_reference_model(mod):
     """`mod` = the reference's own model.py, imported UNMODIFIED on top of the drop-in layer modules (model.py:7-8).
-    Rebinds the forward methods of its TC_Block / ConvTC_Block / MultiHeadAttention classes to the functions above:
+    Rebinds the forward methods of its TC_Block / ConvTC_Block / MultiHeadAttention / SELD_Model classes to the functions above:
     the same module attributes, parameters and semantics (every branch falls back to the layer-by-layer modules where
     the fused kernels do not apply), but the glue between the convolutions now runs in this repository's kernels.
     The originals stay reachable as `<class>._reference_forward`.  Idempotent."""
     if id(mod) in _PATCHED:
         return False
-    for cls_name, fn in (("TC_Block", tc_block_forward), ("ConvTC_Block", convtc_block_forward),
-                         ("MultiHeadAttention", mha_forward)):
+    targets = (("TC_Block", tc_block_forward), ("ConvTC_Block", convtc_block_forward),
+               ("MultiHeadAttention", mha_forward), ("SELD_Model", seld_model_forward))
+    for cls_name, fn in targets:
         cls = getattr(mod, cls_name, None)
         if cls is None or not isinstance(cls, type) or cls.__module__ == __name__:
             return False
-    for cls_name, fn in (("TC_Block", tc_block_forward), ("ConvTC_Block", convtc_block_forward),
-                         ("MultiHeadAttention", mha_forward)):
+    for cls_name, fn in targets:
         cls = getattr(mod, cls_name)
         cls._reference_forward = cls.forward
         cls.forward = fn
@@ -437,17 +495,7 @@ class SELD_Model(nn.Module):
         return name + extra_name
 
     def forward(self, x):
-        if self.parallel_ConvTC_block in _TWO_BRANCH:
-            if self.parallel_magphase:
-                x_a = torch.cat((x[:, :4], x[:, 8:12]), 1)      # mic A magnitude + phase
-                x_b = torch.cat((x[:, 4:8], x[:, 12:]), 1)      # mic B magnitude + phase
-            else:
-                half = self.input_channels // 2
-                x_a, x_b = x[:, :half], x[:, half:]
-            x = torch.cat((self.branch_A(x_a), self.branch_B(x_b)), 2)
-        else:
-            x = self.seld_block(x)
-        return self.sed(x), self.doa(x)
+        return seld_model_forward(self, x)
 
     def calculate_receptive_field(self, verbose=0):
         dils = _dilations(self.D, self.dilation_mode)
