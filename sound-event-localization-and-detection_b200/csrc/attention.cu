@@ -518,33 +518,19 @@ int launch_attention_bwd(int batch, int heads, int S, int d, const void* q_rm, c
   // stream forked off `st` and joined back: the 304 CTAs of both fill the SMs in three waves instead of four
   // (SELDQ_ATTN_BWD_FORK=0: one after the other).  The fork / join events are capturable into a CUDA graph.
   static const bool fork = [] { const char* e = getenv("SELDQ_ATTN_BWD_FORK"); return !(e && e[0] == '0'); }();
-  static thread_local cudaStream_t side = nullptr;
-  static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  static thread_local int side_dev = -1;
-  cudaStream_t st2 = st;
-  if (fork) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (side == nullptr || side_dev != dev) {
-      if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
-          cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)
-        return fail(SELDQ_ERR_CUDA, "attention backward: side stream: %s", cudaGetErrorString(cudaGetLastError()));
-      side_dev = dev;
-    }
-    if (cudaEventRecord(ev_fork, st) != cudaSuccess || cudaStreamWaitEvent(side, ev_fork, 0) != cudaSuccess)
-      return fail(SELDQ_ERR_CUDA, "attention backward: fork: %s", cudaGetErrorString(cudaGetLastError()));
-    st2 = side;
+  if (!fork) {
+    int rc = launch_attn<attn::MODE_DKV>(p, k_rm, v_rm, q_rm, do_rm, do_tr, q_tr, st);
+    if (rc) return rc;
+    p.o1 = dq; p.o2 = nullptr; p.scale1 = 1.f / sqrtf((float)d);
+    return launch_attn<attn::MODE_DQ>(p, q_rm, do_rm, k_rm, v_rm, k_tr, nullptr, st);
   }
+  ForkJoin fj(st, 0);
   int rc = launch_attn<attn::MODE_DKV>(p, k_rm, v_rm, q_rm, do_rm, do_tr, q_tr, st);
   if (rc == SELDQ_OK) {
     p.o1 = dq; p.o2 = nullptr; p.scale1 = 1.f / sqrtf((float)d);
-    rc = launch_attn<attn::MODE_DQ>(p, q_rm, do_rm, k_rm, v_rm, k_tr, nullptr, st2);
+    rc = launch_attn<attn::MODE_DQ>(p, q_rm, do_rm, k_rm, v_rm, k_tr, nullptr, fj.side());
   }
-  if (fork) {                                    // always join, also after a failed launch (a capture must not be left forked)
-    if (cudaEventRecord(ev_join, side) != cudaSuccess || cudaStreamWaitEvent(st, ev_join, 0) != cudaSuccess)
-      return fail(SELDQ_ERR_CUDA, "attention backward: join: %s", cudaGetErrorString(cudaGetLastError()));
-  }
+  if (!fj.join() && rc == SELDQ_OK) rc = fail(SELDQ_ERR_CUDA, "attention backward: join: %s", cudaGetErrorString(cudaGetLastError()));
   return rc;
 }
 

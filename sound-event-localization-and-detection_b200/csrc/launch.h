@@ -21,6 +21,34 @@ inline int check_launch(const char* what) {
   return SELDQ_OK;
 }
 
+// Fork / join of a library-internal side stream off a caller's stream (capturable into a CUDA graph): work launched on
+// side() between fork() and join() runs concurrently with what the caller's stream does in between.  One side stream
+// and event pair per host thread and call site (`slot`).
+struct ForkJoin {
+  cudaStream_t st, side_ = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool ok = false;
+  ForkJoin(cudaStream_t caller, int slot) : st(caller) {
+    struct Res { cudaStream_t s = nullptr; cudaEvent_t f = nullptr, j = nullptr; int dev = -1; };
+    static thread_local Res res[4];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Res& r = res[slot & 3];
+    if (r.s == nullptr || r.dev != dev) {
+      if (cudaStreamCreateWithFlags(&r.s, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&r.f, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&r.j, cudaEventDisableTiming) != cudaSuccess)
+        return;
+      r.dev = dev;
+    }
+    side_ = r.s; ev_fork = r.f; ev_join = r.j;
+    ok = cudaEventRecord(ev_fork, st) == cudaSuccess && cudaStreamWaitEvent(side_, ev_fork, 0) == cudaSuccess;
+  }
+  cudaStream_t side() const { return ok ? side_ : st; }
+  // always call, also after a failed launch: a capture must not be left forked
+  bool join() { return !ok || (cudaEventRecord(ev_join, side_) == cudaSuccess && cudaStreamWaitEvent(st, ev_join, 0) == cudaSuccess); }
+};
+
 int launch_conv_simt(const simt::ConvParams& p, cudaStream_t st);
 int launch_wgrad_simt(simt::WgradParams& p, cudaStream_t st);
 int launch_bias_grad(const float* gy, float* gb, int C, int N, int H, int W, long long sN, long long sC, long long sH,
