@@ -18,10 +18,18 @@ import torch.nn.functional as tF
 
 def seld_loss(sed, doa, target, n_sed, sed_weight=1.0, doa_weight=5.0):
     """train.py:186-204; target is (B, frames, n_sed + 3*n_sed) with SED first (train.py:191-192)."""
-    t_sed = torch.flatten(target[:, :, :n_sed], start_dim=1)
-    t_doa = torch.flatten(target[:, :, n_sed:], start_dim=1)
-    loss_sed = tF.binary_cross_entropy(torch.flatten(sed, start_dim=1), t_sed) * sed_weight
-    loss_doa = tF.mse_loss(torch.flatten(doa, start_dim=1), t_doa) * doa_weight
+    def sed_term():
+        return tF.binary_cross_entropy(torch.flatten(sed, start_dim=1), torch.flatten(target[:, :, :n_sed], start_dim=1)) * sed_weight
+
+    def doa_term():
+        return tF.mse_loss(torch.flatten(doa, start_dim=1), torch.flatten(target[:, :, n_sed:], start_dim=1)) * doa_weight
+
+    if sed.is_cuda:
+        # the two terms are independent chains of small kernels (forward and backward): a forked stream pair
+        from .seld_model import _forked
+        loss_sed, loss_doa = _forked(sed_term, doa_term, sed)
+    else:
+        loss_sed, loss_doa = sed_term(), doa_term()
     return loss_sed + loss_doa
 
 
