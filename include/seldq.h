@@ -373,6 +373,11 @@ int seldq_seld_events(const float* sed, const float* doa, int32_t clips, int32_t
  * bias corrections are formed in double, as torch/optim/adam.py forms them, before anything is rounded to float. */
 int seldq_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double b1,
                     double b2, double eps, float* step, void* stream);
+/* The same update over a PART of the buffers (pointers already offset, 16-byte aligned): every part of one optimiser
+ * step reads the same `step`; only the call with advance != 0 -- the last one -- increments it.  Lets a trainer update
+ * the parameters whose gradients are complete while the rest of the backward pass still runs. */
+int seldq_adam_step_part(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double b1,
+                         double b2, double eps, float* step, int32_t advance, void* stream);
 
 /* debug: a 64 x uint64 device buffer that CTA 0 of every later tensor-core convolution launch stamps with
  * %globaltimer values at its role hand-offs (tools/fprop_trace.py); NULL switches it off. */

@@ -148,6 +148,8 @@ _PROTOS = {
                                             _P, _P]),
     "seldq_adam_step": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                        ctypes.c_double, _P, _P]),
+    "seldq_adam_step_part": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                            ctypes.c_double, _P, ctypes.c_int32, _P]),
     "seldq_seld_events": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                          ctypes.c_float, _P, _P, _P]),
     "seldq_debug_fprop_trace": (ctypes.c_int, [_P]),

@@ -728,7 +728,15 @@ extern "C" int seldq_adam_step(float* param, const float* grad, float* exp_avg, 
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step) return fail(SELDQ_ERR_INVALID, "seldq_adam_step: null pointer");
   int rc = cuda_ready();
   if (rc) return rc;
-  return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, b1, b2, eps, step, (cudaStream_t)stream);
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, b1, b2, eps, step, 1, (cudaStream_t)stream);
+}
+
+extern "C" int seldq_adam_step_part(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                                    double b1, double b2, double eps, float* step, int32_t advance, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step) return fail(SELDQ_ERR_INVALID, "seldq_adam_step_part: null pointer");
+  int rc = cuda_ready();
+  if (rc) return rc;
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, b1, b2, eps, step, advance ? 1 : 0, (cudaStream_t)stream);
 }
 
 // ---- evaluation path -------------------------------------------------------------------------------------------

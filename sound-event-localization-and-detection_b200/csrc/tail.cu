@@ -138,7 +138,7 @@ __global__ void adam_count_kernel(float* step) { *step += 1.f; }
 }  // namespace tail
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps, float* step,
-                cudaStream_t st) {
+                int advance, cudaStream_t st) {
   if (n < 1) return SELDQ_OK;
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v)) & 15)
@@ -146,6 +146,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, doubl
   tail::adam_kernel<<<grid_for(n >> 2), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, (float)eps, step);
   int rc = check_launch("adam_kernel");
   if (rc) return rc;
+  if (!advance) return SELDQ_OK;
   tail::adam_count_kernel<<<1, 1, 0, st>>>(step);
   return check_launch("adam_count_kernel");
 }

@@ -9,5 +9,5 @@ int launch_act_pool_fwd(const float* x, float* y, long long rows, int T, int poo
 int launch_act_pool_bwd(const float* x, const float* y, const float* gy, float* gx, long long rows, int T, int pool, int act,
                         cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, double lr, double b1, double b2, double eps, float* step,
-                cudaStream_t st);
+                int advance, cudaStream_t st);
 }  // namespace seldq

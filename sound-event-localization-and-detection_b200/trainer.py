@@ -48,7 +48,9 @@ class FlatGradBucket(object):
             params = [p for p in params if late(p)] + [p for p in params if not late(p)]
         self.params = params
         self.n_late = sum(p.numel() for p in params if late is not None and late(p))
-        total = sum(p.numel() for p in self.params)
+        # 16-byte alignment of the boundary between the late and the early slice (the optimiser updates them separately)
+        self.pad = (-self.n_late) % 4 if self.n_late else 0
+        total = sum(p.numel() for p in self.params) + self.pad
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=self.params[0].dtype, device=dev)
         self.flat_param = torch.nn.Parameter(torch.empty(total, dtype=self.params[0].dtype, device=dev))
@@ -62,6 +64,8 @@ class FlatGradBucket(object):
                 p.grad = self.flat[off:off + n].view_as(p)
                 self.offsets[id(p)] = (off, n)
                 off += n
+                if off == self.n_late and self.pad:
+                    off += self.pad                         # padding elements: zero gradient, never read back
         self.flat_param.grad = self.flat
         if dev.type == "cuda":
             # p.data was re-pointed: packed bf16 tiles keyed on the old addresses are stale
@@ -124,15 +128,26 @@ class FlatAdam(object):
         return st
 
     def step(self):
+        self.step_part(0, self.flat_param.numel(), True)
+
+    def step_part(self, lo, hi, advance):
+        """The update of elements [lo, hi) on the current stream.  All parts of one step see the same step count; the
+        last one (advance=True) increments it.  lo must be a multiple of 4 (16-byte alignment)."""
         from . import _lib
         st = self._ensure_state()
         g = self.param_groups[0]
         fp = self.flat_param
+        if hi <= lo:
+            if not advance:
+                return
+            hi = lo                                           # nothing to update, but the counter must move
+        assert lo % 4 == 0
         with torch.cuda.device(fp.device):
-            _lib.check(_lib.lib().seldq_adam_step(fp.data.data_ptr(), fp.grad.data_ptr(), st["exp_avg"].data_ptr(),
-                                                  st["exp_avg_sq"].data_ptr(), fp.numel(), float(g["lr"]), float(g["betas"][0]),
-                                                  float(g["betas"][1]), float(g["eps"]), st["step"].data_ptr(),
-                                                  torch.cuda.current_stream().cuda_stream))
+            _lib.check(_lib.lib().seldq_adam_step_part(
+                fp.data.data_ptr() + 4 * lo, fp.grad.data_ptr() + 4 * lo, st["exp_avg"].data_ptr() + 4 * lo,
+                st["exp_avg_sq"].data_ptr() + 4 * lo, max(hi - lo, 0), float(g["lr"]), float(g["betas"][0]),
+                float(g["betas"][1]), float(g["eps"]), st["step"].data_ptr(), 1 if advance else 0,
+                torch.cuda.current_stream().cuda_stream))
 
 
 class Trainer(object):
@@ -161,6 +176,8 @@ class Trainer(object):
         self._tc_blocks = [m for m in model.modules() if hasattr(m, "ResBlocks") and hasattr(m, "attention")]
         self._pending = 0
         self._early_launched = False
+        self._early_adam_done = False
+        self._early_adam_ok = False                   # set below, once the optimiser is known
         if self._overlap:
             for m in self._tc_blocks:
                 m.register_forward_pre_hook(self._tcn_pre_hook)
@@ -170,6 +187,9 @@ class Trainer(object):
         if on_cuda:
             self.optimizer = FlatAdam(self.bucket.flat_param, lr=lr)
             self.optimizer._ensure_state()                 # allocated outside any graph capture
+            # SELDQ_EARLY_ADAM=0: one update of the whole bucket behind the backward pass
+            self._early_adam_ok = (self._overlap and bool(self._tc_blocks) and self.bucket.n_late > 0
+                                   and __import__("os").environ.get("SELDQ_EARLY_ADAM", "1") != "0")
         else:
             self.optimizer = torch.optim.Adam([self.bucket.flat_param], lr=lr)
         self._graph = None
@@ -185,7 +205,7 @@ class Trainer(object):
 
     def _tcn_pre_hook(self, module, inputs):
         x = inputs[0]
-        if self._overlap and self._distributed() and torch.is_grad_enabled() and x.requires_grad:
+        if self._overlap and (self._distributed() or self._early_adam_ok) and torch.is_grad_enabled() and x.requires_grad:
             self._pending += 1
             x.register_hook(self._tcn_backward_done)
 
@@ -194,8 +214,17 @@ class Trainer(object):
         if self._pending == 0 and not self._early_launched:
             if self._ar_stream is None and self._on_cuda:
                 self._ar_stream = torch.cuda.Stream()
-            self.bucket.all_reduce_early(self.group, self._ar_stream)
-            self._early_launched = True
+            if self._distributed():
+                self.bucket.all_reduce_early(self.group, self._ar_stream)
+                self._early_launched = True
+            elif self._ar_stream is not None:
+                self._ar_stream.wait_stream(torch.cuda.current_stream())
+            if self._early_adam_ok and self._ar_stream is not None:
+                # everything but the CNN front has its final gradient: its Adam update runs on the side stream, behind
+                # the early all-reduce, while the CNN backward still runs (the step counter moves with the last part)
+                with torch.cuda.stream(self._ar_stream):
+                    self.optimizer.step_part(self.bucket.n_late + self.bucket.pad, self.bucket.flat.numel(), False)
+                self._early_adam_done = True
         return None
 
     def reduce_gradients(self):
@@ -311,12 +340,16 @@ class Trainer(object):
     def step(self, x, target):
         """One optimisation step on this rank's shard; returns the (local) loss tensor."""
         self.bucket.zero()
-        self._pending, self._early_launched = 0, False
+        self._pending, self._early_launched, self._early_adam_done = 0, False, False
         sed, doa = self.model(x)
         loss = seld_loss(sed, doa, target, self.n_sed)
         loss.backward()
         self.reduce_gradients()
-        self.optimizer.step()
+        if self._early_adam_done:
+            torch.cuda.current_stream().wait_stream(self._ar_stream)       # (a no-op after the distributed join)
+            self.optimizer.step_part(0, self.bucket.n_late, True)
+        else:
+            self.optimizer.step()
         if self._functional is not None:
             # the flat update bypasses the parameters' version counters: refresh every packed bf16 weight set now,
             # in one launch, for the next step

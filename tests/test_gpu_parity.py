@@ -707,3 +707,24 @@ def test_own_adam_step_matches_torch_adam(seldq):
     assert float(opt_a.state[pa]["step"]) == 5.0
     assert torch.allclose(pa.data, pb.data, rtol=2e-6, atol=2e-7)
     assert torch.allclose(opt_a.state[pa]["exp_avg_sq"], opt_b.state[pb]["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+    # the same steps taken in two parts (trainer: everything but the CNN front first, on a side stream, the rest with the
+    # counter increment at the end) are bit-identical to the one-shot update, and the counter moves once per step
+    pc = torch.nn.Parameter(p0.clone())
+    pc.grad = torch.zeros_like(pc)
+    opt_c = trainer_mod.FlatAdam(pc, lr=1e-2)
+    pd = torch.nn.Parameter(p0.clone())
+    pd.grad = torch.zeros_like(pd)
+    opt_d = trainer_mod.FlatAdam(pd, lr=1e-2)
+    split = 40004
+    for k in range(4):
+        g = torch.randn(n, device="cuda") * (0.1 + k)
+        pc.grad.copy_(g)
+        pd.grad.copy_(g)
+        opt_c.step()
+        opt_d.step_part(split, n, False)
+        opt_d.step_part(0, split, True)
+    torch.cuda.synchronize()
+    assert float(opt_d.state[pd]["step"]) == 4.0
+    assert torch.equal(pc.data, pd.data)
+    assert torch.equal(opt_c.state[pc]["exp_avg"], opt_d.state[pd]["exp_avg"])
+    assert torch.equal(opt_c.state[pc]["exp_avg_sq"], opt_d.state[pd]["exp_avg_sq"])
