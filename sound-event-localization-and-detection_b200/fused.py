@@ -38,6 +38,8 @@ TCN_EPI = os.environ.get("SELDQ_TCN_EPI", "0") != "0"
 # SELDQ_TCN_FUSED_GLUE=0: every reduce / apply pair of the residual-block glue stays two launches (default: one launch
 # with a grid barrier where all tiles of the tensor can be resident at once -- seldq_tcn_glue_fused_supported)
 TCN_FUSED_GLUE = os.environ.get("SELDQ_TCN_FUSED_GLUE", "0") != "0"
+# SELDQ_TCN_SKIP_FORK=0: the running sum of the skip outputs stays in the residual kernel of the main stream
+TCN_SKIP_FORK = os.environ.get("SELDQ_TCN_SKIP_FORK", "1") != "0"
 _SIDE = {}
 
 
@@ -382,6 +384,7 @@ class _TcnStack(torch.autograd.Function):
             fuse_l = TCN_FUSED_GLUE and not TCN_EPI and bool(L_.seldq_tcn_glue_fused_supported(N, Lc, T))
             syncs = torch.zeros(2 * len(blocks), dtype=torch.int32, device=dev)
             xa = xa_cl = None
+            skip_stream = None
             for k, (s, wf, wg, wsk, wr, bnp) in enumerate(blocks):
                 nc = F._NCOMP[s["algebra"]]
                 G, U = wf[0].shape[0] * nc, wsk[0].shape[0] * nc
@@ -477,6 +480,20 @@ class _TcnStack(torch.autograd.Function):
                               bn=((sums1_next, g1n, b1n, rm1n, rv1n),), inp=(xa, res, skip), out32=r_next,
                               out32b=xa_next, out_cl=(xa_cl_next,), dsums=sums1_next, accum=skip_sum,
                               flag=1 if k == 0 else 0, sync=syncs[2 * k + 1:])
+                    elif TCN_SKIP_FORK:
+                        # the running sum of the skip outputs is a chain of its own (nothing in the residual stream
+                        # reads it): it accumulates on a forked stream, joined behind the last block, and the residual
+                        # kernel of the main stream moves three tensors instead of six
+                        if skip_stream is None:
+                            skip_stream = _side_stream(dev)
+                        skip_stream.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(skip_stream):
+                            _glue(_lib.TCN_RESIDUAL_FWD, None, 0, N, Lc, T, c2=U, inp=(None, None, skip), accum=skip_sum,
+                                  flag=1 if k == 0 else 0)
+                        skip.record_stream(skip_stream)
+                        if s["has_res"]:
+                            _glue(_lib.TCN_RESIDUAL_FWD, None, 0, N, Lc, T, c2=U, inp=(xa, res, None), out32=r_next,
+                                  dsums=sums1_next)
                     else:
                         _glue(_lib.TCN_RESIDUAL_FWD, None, 0, N, Lc, T, c2=U, inp=(xa, res, skip), out32=r_next,
                               dsums=sums1_next, accum=skip_sum, flag=1 if k == 0 else 0)
@@ -487,6 +504,8 @@ class _TcnStack(torch.autograd.Function):
                     xa = xa_cl = None
                 else:
                     xa, xa_cl = xa_next, xa_cl_next
+            if skip_stream is not None:
+                torch.cuda.current_stream().wait_stream(skip_stream)
         ctx.metas = metas
         ctx.shape = (N, Lc, T)
         ctx.block_params = [(wf, wg, wsk, wr, bnp) for _, wf, wg, wsk, wr, bnp in blocks]
