@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define SELDQ_ABI_VERSION 4
+#define SELDQ_ABI_VERSION 5
 
 typedef enum {
   SELDQ_OK = 0,
@@ -365,6 +365,36 @@ int seldq_act_pool1d_bwd(const float* x, const float* y, const float* gy, int64_
  * capacity, filled per clip in the reference's order (frame, then cell); counts[clip] = rows written. */
 int seldq_seld_events(const float* sed, const float* doa, int32_t clips, int32_t frames, int32_t classes,
                       int32_t overlaps, float max_loc, float* rows, int32_t* counts, void* stream);
+
+/* Rotation variants of the quaternion layers: quaternion_conv_rotation (quaternion_ops.py:174-232),
+ * quaternion_transpose_conv_rotation (:235-295) and quaternion_linear_rotation (:330-388) build ONE real weight of
+ * nc x nc blocks from the compact tensors -- nc = 3, or 4 with quaternion_format (block row 0 and block column 0 zero) --
+ * and run a plain convolution / matrix product on it.  host_w: host array of the 4 device pointers r, i, j, k, each
+ * float32 (d0, d1, taps) contiguous (convolution: (out / nc', in / nc', k...); transposed convolution and linear:
+ * (in / nc', out / nc', ...)).  out: float32 (nc d0, nc d1, taps), or its (nc d1, nc d0, taps) transpose with
+ * transpose_out (the linear variant runs as a 1 x 1 convolution, whose weight is (out, in)); IEEE float32 in the
+ * reference's order of operations (bit-identical to oracle/algebra.py rotation_weight in float32).  The contraction is seldq_conv_* with SELDQ_ALG_REAL on that weight.
+ * _bwd: g_out = gradient of `out` (same layout) -> host_gw: the gradients of r, i, j, k (overwritten). */
+int seldq_rotation_weight(const float* const* host_w, int64_t d0, int64_t d1, int64_t taps, int32_t quaternion_format,
+                          int32_t transpose_out, float* out, void* stream);
+int seldq_rotation_weight_bwd(const float* const* host_w, const float* g_out, int64_t d0, int64_t d1, int64_t taps,
+                              int32_t quaternion_format, int32_t transpose_out, float* const* host_gw, void* stream);
+
+/* Point-wise operators on quaternion-valued tensors read as float32 (outer, 4, m) -- component c of quaternion (o, x)
+ * at o * 4 m + c * m + x, the get_r / get_i / get_j / get_k slices of dimension 1 of the reference:
+ * hamilton_product (quaternion_ops.py:467-507 = dual_quaternion_ops.py:374-414), q_normalize and quaternion_exp
+ * (dual_quaternion_ops.py:206-246), and what their gradients need.  b is ignored by the one-operand operators. */
+typedef enum {
+  SELDQ_QOP_HAMILTON = 0,         /* out = a (x) b                                                          */
+  SELDQ_QOP_HAMILTON_CONJ_B = 1,  /* out = a (x) conj(b): gradient of the first factor, a = grad, b = second */
+  SELDQ_QOP_HAMILTON_CONJ_A = 2,  /* out = conj(a) (x) b: gradient of the second factor, a = first, b = grad */
+  SELDQ_QOP_NORMALIZE = 3,        /* out = a / sqrt(|a|^2 + 1e-4)                                            */
+  SELDQ_QOP_NORMALIZE_BWD = 4,    /* a = input, b = grad of the output -> grad of the input                  */
+  SELDQ_QOP_EXP = 5,              /* out = e^r (cos |v|', v / |v|' sin |v|'), |v|' = |v| + 1e-4              */
+  SELDQ_QOP_EXP_BWD = 6           /* a = input, b = grad of the output -> grad of the input                  */
+} seldq_qpointwise_op_t;
+int seldq_quaternion_pointwise(int32_t op, const float* a, const float* b, float* out, int64_t outer, int64_t m,
+                               void* stream);
 
 /* The optimiser step of train.py:502-504, :560 -- torch.optim.Adam(lr, betas = (b1, b2), eps), no weight decay, no
  * amsgrad -- over flat float32 buffers of n elements (parameters, gradients, exp_avg, exp_avg_sq; 16-byte aligned).

@@ -16,6 +16,8 @@ What is restated, and where it lives in the reference:
   * quaternion_linear ........................... quaternion_ops.py:299-327 (and :392-464)
   * dual_quaternion_linear (transposed table) ... dual_quaternion_ops.py:156-203
   * spectrum_fast (scipy.signal.stft defaults) .. utility_functions.py:129-155
+  * rotation variants (conv / transposed / linear) quaternion_ops.py:174-295, :330-388
+  * hamilton_product, q_normalize, quaternion_exp  quaternion_ops.py:467-507, dual_quaternion_ops.py:206-246, :374-414
 The third-party arithmetic underneath (torch F.conv*, torch.mm, scipy.signal.stft 1.18) is
 restated from its published definition: cross-correlation with zero padding, and
 Z = rfft(frame * w) / sum(w) with boundary='zeros', padded=True, periodic Hamming.
@@ -211,6 +213,114 @@ def qlinear_backward(x, weights, gy, algebra="Q"):
     gW = x2.T @ g2
     I, O = np.asarray(weights[0]).shape
     return gx, compact_grads(gW, algebra, O, I, linear=True), g2.sum(0)
+
+
+# ---- rotation variants and point-wise quaternion operators ------------------------------------------
+def rotation_weight(weights, quaternion_format=False, dtype=np.float64):
+    """The real weight of quaternion_conv_rotation / quaternion_transpose_conv_rotation / quaternion_linear_rotation
+    (quaternion_ops.py:188-220, :249-281, :344-376): compact (d0, d1, k...) -> (nc d0, nc d1, k...), nc = 4 with
+    quaternion_format (zero block row / column first), else 3.  Restated as written: norm_factor = 2 |q| (a product,
+    not the 2 / |q|^2 of the textbook formula), products as (f * a) * b, sums left to right -- in float32 every
+    operation rounds as torch's does, so dtype=np.float32 reproduces the reference's weight bit for bit."""
+    r, i, j, k = (np.asarray(w, dtype) for w in weights)
+    one, two = dtype(1.0), dtype(2.0)
+    norm = np.sqrt(r * r + i * i + j * j + k * k)
+    f = two * norm
+    si, sj, sk = f * (i * i), f * (j * j), f * (k * k)
+    ri, rj, rk = f * r * i, f * r * j, f * r * k
+    ij, ik, jk = f * i * j, f * i * k, f * j * k
+    cols = [[one - (sj + sk), ij - rk, ik + rj],
+            [ij + rk, one - (si + sk), jk - ri],
+            [ik - rj, jk + ri, one - (si + sj)]]
+    if quaternion_format:
+        z = np.zeros_like(r)
+        cols = [[z, z, z, z]] + [[z] + c for c in cols]
+    return np.concatenate([np.concatenate(c, axis=0) for c in cols], axis=1)
+
+
+def rotation_weight_backward(weights, gW, quaternion_format=False):
+    """Gradients of (r, i, j, k) given the gradient of rotation_weight's output: entry = delta_ab + f P_ab(q), f = 2 |q|,
+    so d entry / d q_c = (2 q_c / |q|) P_ab + f dP_ab / dq_c."""
+    q = [np.asarray(w, np.float64) for w in weights]
+    r, i, j, k = q
+    d0, d1 = r.shape[:2]
+    z = 1 if quaternion_format else 0
+    G = [[np.asarray(gW, np.float64)[(a + z) * d0:(a + z + 1) * d0, (b + z) * d1:(b + z + 1) * d1] for b in range(3)]
+         for a in range(3)]
+    n = np.sqrt(r * r + i * i + j * j + k * k)
+    f = 2.0 * n
+    P = [[-(j * j + k * k), i * j + r * k, i * k - r * j],
+         [i * j - r * k, -(i * i + k * k), j * k + r * i],
+         [i * k + r * j, j * k - r * i, -(i * i + j * j)]]
+    S = sum(G[a][b] * P[a][b] for a in range(3) for b in range(3))
+    zero = np.zeros_like(r)
+    # dP[c][a][b] = d P_ab / d q_c
+    dP = [[[zero, k, -j], [-k, zero, i], [j, -i, zero]],
+          [[zero, j, k], [j, -2 * i, r], [k, -r, -2 * i]],
+          [[-2 * j, i, -r], [i, zero, k], [r, k, -2 * j]],
+          [[-2 * k, r, i], [-r, -2 * k, j], [i, j, zero]]]
+    return [2.0 * q[c] / n * S + f * sum(G[a][b] * dP[c][a][b] for a in range(3) for b in range(3)) for c in range(4)]
+
+
+def qconv_rotation(x, weights, bias=None, stride=1, padding=0, dilation=1, quaternion_format=False):
+    """quaternion_conv_rotation (quaternion_ops.py:174-232)."""
+    return conv_nd(x, rotation_weight(weights, quaternion_format), bias, stride, padding, dilation)
+
+
+def qconv_rotation_backward(x, weights, gy, stride=1, padding=0, dilation=1, quaternion_format=False):
+    gx, gW, gb = conv_nd_backward(x, rotation_weight(weights, quaternion_format), gy, stride, padding, dilation)
+    return gx, rotation_weight_backward(weights, gW, quaternion_format), gb
+
+
+def qconv_transpose_rotation(x, weights, bias=None, padding=0, dilation=1, quaternion_format=False):
+    """quaternion_transpose_conv_rotation, stride 1 (quaternion_ops.py:235-295): F.conv_transpose of the (in, out, k...)
+    rotation weight = the input gradient of the convolution with that weight read as (out', in'), evaluated at x."""
+    x = np.asarray(x, np.float64)
+    W = rotation_weight(weights, quaternion_format)
+    nd = x.ndim - 2
+    pad, dil = _pair(padding) if nd == 2 else (padding,), _pair(dilation) if nd == 2 else (dilation,)
+    out_sp = tuple(x.shape[2 + a] + (W.shape[2 + a] - 1) * dil[a] - 2 * pad[a] for a in range(nd))
+    gx, _, _ = conv_nd_backward(np.zeros((x.shape[0], W.shape[1]) + out_sp), W, x, 1, padding, dilation)
+    return gx if bias is None else gx + np.asarray(bias, np.float64).reshape((1, -1) + (1,) * nd)
+
+
+def qlinear_rotation(x, weights, bias=None, quaternion_format=False):
+    """quaternion_linear_rotation (quaternion_ops.py:330-388)."""
+    y = np.asarray(x, np.float64) @ rotation_weight(weights, quaternion_format)
+    return y if bias is None else y + np.asarray(bias, np.float64)
+
+
+def _components(x):
+    """get_r / get_i / get_j / get_k of dual_quaternion_ops.py:34-85 for 2-d and >= 4-d inputs: quarters of dim 1."""
+    x = np.asarray(x)
+    n = x.shape[1] // 4
+    return [x[:, c * n:(c + 1) * n] for c in range(4)]
+
+
+def hamilton_product(q0, q1, dtype=np.float64):
+    """quaternion_ops.py:467-507 / dual_quaternion_ops.py:374-414."""
+    a, b = _components(np.asarray(q0, dtype)), _components(np.asarray(q1, dtype))
+    r = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3]
+    i = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2]
+    j = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1]
+    k = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]
+    return np.concatenate([r, i, j, k], axis=1)
+
+
+def q_normalize(x, dtype=np.float64):
+    """dual_quaternion_ops.py:206-223 (channel = 1)."""
+    r, i, j, k = _components(np.asarray(x, dtype))
+    norm = np.sqrt(r * r + i * i + j * j + k * k + dtype(0.0001))
+    return np.concatenate([r / norm, i / norm, j / norm, k / norm], axis=1)
+
+
+def quaternion_exp(x, dtype=np.float64):
+    """dual_quaternion_ops.py:227-246."""
+    r, i, j, k = _components(np.asarray(x, dtype))
+    nv = np.sqrt(i * i + j * j + k * k) + dtype(0.0001)
+    e = np.exp(r)
+    return np.concatenate([e * np.cos(nv), e * ((i / nv) * np.sin(nv)), e * ((j / nv) * np.sin(nv)),
+                           e * ((k / nv) * np.sin(nv))], axis=1)
 
 
 def hamming_periodic(n):

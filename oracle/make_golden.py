@@ -119,6 +119,99 @@ def linear_case(ns, name, algebra, rows, I, O, bias, seed, use_function=False):
     print(name, tuple(x.shape), "->", tuple(y.shape))
 
 
+def _rotation_weight32(ns, ws, qf):
+    """The float32 weight the reference's rotation variants build, read back exactly: quaternion_linear_rotation of an
+    identity input returns its global_rot_kernel (every product is 1 * w or 0 * w), applied to the compact tensors
+    flattened to (d0, d1 * taps) -- the construction is element-wise."""
+    w32 = [torch.tensor(np.asarray(w, np.float32)) for w in ws]
+    d0, d1 = w32[0].shape[:2]
+    taps = int(np.prod(w32[0].shape[2:])) if w32[0].dim() > 2 else 1
+    nc = 4 if qf else 3
+    flat = [w.reshape(d0, d1 * taps) for w in w32]
+    G = ns.q_ops.quaternion_linear_rotation(torch.eye(nc * d0, dtype=torch.float32), *flat, None, qf)
+    return G.reshape(nc * d0, nc, d1, taps).reshape(nc * d0, nc * d1, taps).numpy()
+
+
+def rotation_case(ns, name, kind, ndim, N, I, O, spatial, k, padding, dilation, bias, qf, seed, stride=1):
+    """quaternion_conv_rotation (quaternion_ops.py:174-232), quaternion_transpose_conv_rotation (:235-295) and
+    quaternion_linear_rotation (:330-388).  kind: 'conv' | 'convT' | 'linear'; I, O = compact sizes; for 'linear'
+    `spatial` holds the leading dimensions of the input."""
+    rng = np.random.default_rng(seed)
+    nc = 4 if qf else 3
+    if kind == "linear":
+        wshape, xshape = (I, O), tuple(spatial) + (nc * I,)
+    else:
+        kshape = (k,) * ndim
+        wshape = ((O, I) if kind == "conv" else (I, O)) + kshape
+        xshape = (N, nc * I) + tuple(spatial)
+    ws = [f32(rng.standard_normal(wshape) * 0.4) for _ in range(4)]
+    x = f32(rng.standard_normal(xshape))
+    b = f32(rng.standard_normal(nc * O)) if bias else None
+    tx = torch.tensor(x, requires_grad=True)
+    tw = [torch.tensor(w, requires_grad=True) for w in ws]
+    tb = torch.tensor(b, requires_grad=True) if bias else None
+    if kind == "conv":
+        y = ns.q_ops.quaternion_conv_rotation(tx, *tw, tb, stride, padding, 1, dilation, qf)
+        src = "quaternion_ops.py:174-232"
+    elif kind == "convT":
+        y = ns.q_ops.quaternion_transpose_conv_rotation(tx, *tw, tb, 1, padding, 0, 1, dilation, qf)
+        src = "quaternion_ops.py:235-295"
+    else:
+        y = ns.q_ops.quaternion_linear_rotation(tx, *tw, tb, qf)
+        src = "quaternion_ops.py:330-388"
+    gy = f32(rng.standard_normal(tuple(y.shape)))
+    y.backward(torch.tensor(gy))
+    d = dict(x=x, gy=gy, y=y.detach().numpy(), gx=tx.grad.numpy(), W32=_rotation_weight32(ns, ws, qf))
+    for i, (w, t) in enumerate(zip(ws, tw)):
+        d["w%d" % i] = w
+        d["gw%d" % i] = t.grad.numpy()
+    if bias:
+        d["b"] = b
+        d["gb"] = tb.grad.numpy()
+    meta = dict(kind="rot_" + kind, ndim=ndim, stride=stride, padding=padding, dilation=dilation, bias=bool(bias),
+                quaternion_format=bool(qf), seed=seed, source=src)
+    _save(name, meta, d)
+    print(name, tuple(x.shape), "->", tuple(y.shape))
+
+
+def qpointwise_case(ns, name, shape, seed):
+    """hamilton_product (dual_quaternion_ops.py:374-414; quaternion_ops.py:467-507 is the same arithmetic on 2-d
+    inputs), q_normalize and quaternion_exp (dual_quaternion_ops.py:206-246), each with its autograd gradients."""
+    rng = np.random.default_rng(seed)
+    a, b = f32(rng.standard_normal(shape)), f32(rng.standard_normal(shape))
+    g = f32(rng.standard_normal(shape))
+    d = dict(a=a, b=b, g=g)
+    ta, tb_ = torch.tensor(a, requires_grad=True), torch.tensor(b, requires_grad=True)
+    y = ns.dq_ops.hamilton_product(ta, tb_)
+    y.backward(torch.tensor(g))
+    d.update(ham=y.detach().numpy(), ham_ga=ta.grad.numpy(), ham_gb=tb_.grad.numpy())
+    if len(shape) == 2:
+        tq0, tq1 = torch.tensor(a), torch.tensor(b)
+        assert np.array_equal(ns.q_ops.hamilton_product(tq0, tq1).numpy(), d["ham"])
+    for key, fn in (("norm", ns.dq_ops.q_normalize), ("exp", ns.dq_ops.quaternion_exp)):
+        ta = torch.tensor(a, requires_grad=True)
+        y = fn(ta)
+        y.backward(torch.tensor(g))
+        d[key] = y.detach().numpy()
+        d[key + "_g"] = ta.grad.numpy()
+    _save(name, dict(kind="qpointwise", seed=seed, source="dual_quaternion_ops.py:206-246, :374-414"), d)
+    print(name, shape)
+
+
+def n4_cases(ns):
+    """Round 2, SURVEY.md 8f N4: the operators of quaternion_ops.py / dual_quaternion_ops.py the SELD models never
+    call."""
+    rotation_case(ns, "rot_conv1d_qf", "conv", 1, 2, 8, 8, (70,), 3, 2, 2, True, True, 51)
+    rotation_case(ns, "rot_conv2d_3c", "conv", 2, 1, 4, 8, (6, 40), 3, 1, 1, False, False, 52)
+    rotation_case(ns, "rot_conv1d_s2", "conv", 1, 2, 3, 5, (41,), 3, 1, 1, True, True, 53, stride=2)
+    rotation_case(ns, "rot_convT1d_qf", "convT", 1, 2, 8, 4, (50,), 3, 1, 2, True, True, 54)
+    rotation_case(ns, "rot_convT2d_3c", "convT", 2, 1, 3, 5, (5, 33), 3, 1, 1, False, False, 55)
+    rotation_case(ns, "rot_linear_qf", "linear", 0, 0, 6, 5, (9,), 0, 0, 0, True, True, 56)
+    rotation_case(ns, "rot_linear_3c", "linear", 0, 0, 8, 8, (4, 7), 0, 0, 0, False, False, 57)
+    qpointwise_case(ns, "qpointwise_2d", (7, 20), 58)
+    qpointwise_case(ns, "qpointwise_4d", (2, 12, 5, 9), 59)
+
+
 def stft_case(ns, name, C, n, nperseg, noverlap, phase, seed):
     rng = np.random.default_rng(seed)
     x = f32(0.1 * rng.standard_normal((C, n)))
@@ -303,6 +396,9 @@ def main():
         return
     if "--round2" in sys.argv:
         round2_cases(ns)
+        return
+    if "--n4" in sys.argv:
+        n4_cases(ns)
         return
     only_models = "--models-only" in sys.argv
     if not only_models:

@@ -58,6 +58,7 @@ class ConvEpilogue(ctypes.Structure):
 
 EPI_STORE, EPI_ACCUMULATE, EPI_ADD = 0, 1, 2
 ACT_RELU, ACT_TANH = 0, 1
+QOP_HAMILTON, QOP_HAMILTON_CONJ_B, QOP_HAMILTON_CONJ_A, QOP_NORMALIZE, QOP_NORMALIZE_BWD, QOP_EXP, QOP_EXP_BWD = range(7)
 
 
 class AttentionDesc(ctypes.Structure):
@@ -153,6 +154,11 @@ _PROTOS = {
     "seldq_seld_events": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                          ctypes.c_float, _P, _P, _P]),
     "seldq_debug_fprop_trace": (ctypes.c_int, [_P]),
+    "seldq_rotation_weight": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                             ctypes.c_int32, ctypes.c_int32, _P, _P]),
+    "seldq_rotation_weight_bwd": (ctypes.c_int, [ctypes.POINTER(_P), _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                 ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_P), _P]),
+    "seldq_quaternion_pointwise": (ctypes.c_int, [ctypes.c_int32, _P, _P, _P, ctypes.c_int64, ctypes.c_int64, _P]),
     "seldq_attention_supported": (ctypes.c_int, [ctypes.POINTER(AttentionDesc)]),
     "seldq_attention_saved_bytes": (ctypes.c_size_t, [ctypes.POINTER(AttentionDesc)]),
     "seldq_attention_bwd_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(AttentionDesc)]),

@@ -7,7 +7,7 @@ OUT="${1:-$HERE/../libseldq.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr
        --extended-lambda -Xcompiler -fPIC)
-SRCS=(seldq_api simt_kernels stft conv_cl wgrad_cl epilogue tcn_glue conv_umma wgrad_umma wgrad_first attention tail eval)
+SRCS=(seldq_api simt_kernels stft conv_cl wgrad_cl epilogue tcn_glue conv_umma wgrad_umma wgrad_first attention tail eval rotation)
 OBJDIR="$HERE/build"
 mkdir -p "$OBJDIR"
 pids=()

@@ -7,6 +7,7 @@
 #include "conv_umma.h"
 #include "epilogue.h"
 #include "eval.h"
+#include "rotation.h"
 #include "geom.h"
 #include "launch.h"
 #include "stft.cuh"
@@ -737,6 +738,30 @@ extern "C" int seldq_adam_step_part(float* param, const float* grad, float* exp_
   int rc = cuda_ready();
   if (rc) return rc;
   return launch_adam(param, grad, exp_avg, exp_avg_sq, n, lr, b1, b2, eps, step, advance ? 1 : 0, (cudaStream_t)stream);
+}
+
+// ---- rotation variants and quaternion point-wise operators ------------------------------------------
+extern "C" int seldq_rotation_weight(const float* const* host_w, int64_t d0, int64_t d1, int64_t taps,
+                                     int32_t quaternion_format, int32_t transpose_out, float* out, void* stream) {
+  if (!host_w || !host_w[0] || !host_w[1] || !host_w[2] || !host_w[3] || !out)
+    return fail(SELDQ_ERR_INVALID, "seldq_rotation_weight: null pointer");
+  return launch_rotation_weight(host_w, d0, d1, taps, quaternion_format, transpose_out, out, (cudaStream_t)stream);
+}
+
+extern "C" int seldq_rotation_weight_bwd(const float* const* host_w, const float* g_out, int64_t d0, int64_t d1, int64_t taps,
+                                         int32_t quaternion_format, int32_t transpose_out, float* const* host_gw,
+                                         void* stream) {
+  if (!host_w || !host_w[0] || !host_w[1] || !host_w[2] || !host_w[3] || !g_out || !host_gw || !host_gw[0] || !host_gw[1] ||
+      !host_gw[2] || !host_gw[3])
+    return fail(SELDQ_ERR_INVALID, "seldq_rotation_weight_bwd: null pointer");
+  return launch_rotation_weight_bwd(host_w, g_out, d0, d1, taps, quaternion_format, transpose_out, host_gw,
+                                    (cudaStream_t)stream);
+}
+
+extern "C" int seldq_quaternion_pointwise(int32_t op, const float* a, const float* b, float* out, int64_t outer, int64_t m,
+                                          void* stream) {
+  if (!a || !out) return fail(SELDQ_ERR_INVALID, "seldq_quaternion_pointwise: null pointer");
+  return launch_quaternion_pointwise(op, a, b, out, outer, m, (cudaStream_t)stream);
 }
 
 // ---- evaluation path -------------------------------------------------------------------------------------------

@@ -65,17 +65,35 @@ def dual_quaternion_linear(input, r_weight, i_weight, j_weight, k_weight,
     return _F.block_linear(input, ws, bias, _ALG_DQ)
 
 
-def _out_of_scope(name):
-    def fn(*args, **kwargs):
-        raise NotImplementedError("seldq: %s is unused by the SELD models and is not implemented "
-                                  "(SURVEY.md section 2, row 3)" % name)
-    fn.__name__ = name
-    return fn
+def _dim1_quaternions(input, what):
+    # get_r / get_i / get_j / get_k slice dimension 1 of 2-d and >= 4-d inputs (dual_quaternion_ops.py:34-85); for 3-d
+    # inputs they slice the LAST dimension while the results are concatenated along dimension 1
+    check_input(input)
+    if input.dim() == 3:
+        raise NotImplementedError("seldq: %s takes 2-d or >= 4-d inputs (components along dimension 1)" % what)
 
 
-q_normalize = _out_of_scope("q_normalize")
-quaternion_exp = _out_of_scope("quaternion_exp")
-hamilton_product = _out_of_scope("hamilton_product")
+def q_normalize(input, channel=1):
+    """dual_quaternion_ops.py:206-223."""
+    _dim1_quaternions(input, "q_normalize")
+    if channel != 1:
+        raise NotImplementedError("seldq: q_normalize concatenates along dimension 1")
+    return _F.q_normalize(input)
+
+
+def quaternion_exp(input):
+    """dual_quaternion_ops.py:227-246."""
+    _dim1_quaternions(input, "quaternion_exp")
+    return _F.quaternion_exp(input)
+
+
+def hamilton_product(q0, q1):
+    """dual_quaternion_ops.py:374-414."""
+    _dim1_quaternions(q0, "hamilton_product")
+    _dim1_quaternions(q1, "hamilton_product")
+    return _F.hamilton_product(q0, q1)
+
+
 quaternion_init = _I.dual_quaternion_init
 get_kernel_and_weight_shape = _I.get_kernel_and_weight_shape
 

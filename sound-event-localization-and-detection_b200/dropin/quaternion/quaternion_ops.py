@@ -1,7 +1,6 @@
 """Drop-in for the reference's quaternion/quaternion_ops.py: same public names and positional
-signatures, computed by libseldq.so (sm_100a).  Functions that model.py never reaches
-(transpose / rotation variants, hamilton_product) keep their names and raise NotImplementedError
-(SURVEY.md section 2, row 1)."""
+signatures, computed by libseldq.so (sm_100a) -- including the functions model.py never reaches
+(transpose / rotation variants, hamilton_product)."""
 import os as _os
 import sys as _sys
 
@@ -87,14 +86,6 @@ class QuaternionLinearFunction(object):
         return _F.block_linear(input, (r_weight, i_weight, j_weight, k_weight), bias, _ALG_Q)
 
 
-def _out_of_scope(name):
-    def fn(*args, **kwargs):
-        raise NotImplementedError("seldq: %s is never called by the SELD models and is not implemented "
-                                  "(SURVEY.md section 2 / 8f N4)" % name)
-    fn.__name__ = name
-    return fn
-
-
 def quaternion_transpose_conv(input, r_weight, i_weight, j_weight, k_weight, bias, stride, padding, output_padding, groups,
                               dilatation):
     """quaternion_ops.py:149-172 on the convolution kernels (stride 1, groups 1; functional.block_conv_transpose)."""
@@ -102,10 +93,34 @@ def quaternion_transpose_conv(input, r_weight, i_weight, j_weight, k_weight, bia
                                    groups, dilatation, _ALG_Q)
 
 
-quaternion_conv_rotation = _out_of_scope("quaternion_conv_rotation")
-quaternion_transpose_conv_rotation = _out_of_scope("quaternion_transpose_conv_rotation")
-quaternion_linear_rotation = _out_of_scope("quaternion_linear_rotation")
-hamilton_product = _out_of_scope("hamilton_product")
+def quaternion_conv_rotation(input, r_weight, i_weight, j_weight, k_weight, bias, stride,
+                             padding, groups, dilatation, quaternion_format):
+    """quaternion_ops.py:174-232: the rotation weight (csrc/rotation.cu) feeds the real-algebra convolution kernels."""
+    return _F.quaternion_conv_rotation(input, (r_weight, i_weight, j_weight, k_weight), bias, stride, padding, groups,
+                                       dilatation, quaternion_format)
+
+
+def quaternion_transpose_conv_rotation(input, r_weight, i_weight, j_weight, k_weight, bias, stride,
+                                       padding, output_padding, groups, dilatation, quaternion_format):
+    """quaternion_ops.py:235-295 (stride 1, groups 1)."""
+    return _F.quaternion_transpose_conv_rotation(input, (r_weight, i_weight, j_weight, k_weight), bias, stride, padding,
+                                                 output_padding, groups, dilatation, quaternion_format)
+
+
+def quaternion_linear_rotation(input, r_weight, i_weight, j_weight, k_weight, bias=None, quaternion_format=False):
+    """quaternion_ops.py:330-388."""
+    return _F.quaternion_linear_rotation(input, (r_weight, i_weight, j_weight, k_weight), bias, quaternion_format)
+
+
+def hamilton_product(q0, q1):
+    """quaternion_ops.py:467-507: (batch_size, 4 n) operands, as its docstring states (the 3-d inputs check_input would
+    let through slice the last dimension but concatenate along dimension 1 there)."""
+    check_input(q0)
+    check_input(q1)
+    if q0.dim() != 2:
+        raise NotImplementedError("seldq: hamilton_product takes (batch_size, quaternion_number) operands")
+    return _F.hamilton_product(q0, q1)
+
 
 unitary_init = _I.unitary_init
 random_init = _I.random_init

@@ -69,7 +69,7 @@ def set_grad_accumulation(flag):
 def _grad_targets(params, needs):
     """(buffers, direct): param.grad buffers to accumulate into when every parameter that needs a gradient has
     a contiguous fp32 one; otherwise fresh buffers that autograd accumulates as usual."""
-    if _ACCUMULATE and all((not n) or (p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32
+    if _ACCUMULATE and all((not n) or (p.is_leaf and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32
                                        and p.grad.device == p.device) for p, n in zip(params, needs)) and all(needs):
         return [p.grad for p in params], True
     return [torch.empty_like(p) for p in params], False
@@ -624,6 +624,162 @@ def block_linear(x, weights, bias, algebra, prec=None):
     lead = x.shape[:-1]
     y = _BlockLinear.apply(x.reshape(-1, x.shape[-1]), bias, algebra, prec, *weights)
     return y.reshape(lead + (y.shape[-1],))
+
+
+# ---- rotation variants and quaternion point-wise operators -------------------------------------------
+# The real-algebra contraction of the rotation variants follows the global precision where the tensor-core path serves
+# it (stride 1, 8 ... 256 channels on both sides: the kernels' dense mode, which builds the expanded bf16 tile from the
+# fp32 weight in its prologue) and runs the fp32 kernels otherwise; SELDQ_ROTATION_BF16=0: always the fp32 kernels.
+_ROTATION_BF16 = os.environ.get("SELDQ_ROTATION_BF16", "1") != "0"
+
+
+class _RotationWeight(torch.autograd.Function):
+    """(r, i, j, k) of shape (d0, d1, k...) -> the real weight (nc d0, nc d1, k...) the reference's rotation variants
+    build (quaternion_ops.py:188-220, :249-281, :344-376), or its (nc d1, nc d0, k...) transpose (csrc/rotation.cu);
+    nc = 4 with quaternion_format, else 3."""
+
+    @staticmethod
+    def forward(ctx, quaternion_format, transpose_out, *weights):
+        if len(weights) != 4:
+            raise ValueError("rotation weight: expected the four tensors r, i, j, k")
+        for w in weights:
+            _require_cuda_f32(w, "weight")
+            if w.shape != weights[0].shape or w.dim() < 2:
+                raise RuntimeError("rotation weight: r, i, j, k must share one shape of at least 2 dimensions")
+        weights = tuple(w.contiguous() for w in weights)
+        w0 = weights[0]
+        d0, d1 = w0.shape[0], w0.shape[1]
+        taps = 1
+        for k in w0.shape[2:]:
+            taps *= k
+        nc = 4 if quaternion_format else 3
+        lead = (nc * d1, nc * d0) if transpose_out else (nc * d0, nc * d1)
+        out = torch.empty(lead + tuple(w0.shape[2:]), dtype=torch.float32, device=w0.device)
+        if out.numel():
+            with torch.cuda.device(w0.device):
+                _lib.check(_lib.lib().seldq_rotation_weight(_lib.ptr_array([w.data_ptr() for w in weights]), d0, d1, taps,
+                                                            int(bool(quaternion_format)), int(bool(transpose_out)),
+                                                            out.data_ptr(), _stream()))
+        ctx.geom = (d0, d1, taps, int(bool(quaternion_format)), int(bool(transpose_out)))
+        ctx.save_for_backward(*weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        weights = ctx.saved_tensors
+        d0, d1, taps, qf, tr = ctx.geom
+        gout = gout.contiguous()
+        if gout.dtype != torch.float32:
+            raise TypeError("seldq: grad_output must be float32")
+        gws = [torch.empty_like(w) for w in weights]
+        if gws[0].numel():
+            with torch.cuda.device(gout.device):
+                _lib.check(_lib.lib().seldq_rotation_weight_bwd(_lib.ptr_array([w.data_ptr() for w in weights]),
+                                                                gout.data_ptr(), d0, d1, taps, qf, tr,
+                                                                _lib.ptr_array([g.data_ptr() for g in gws]), _stream()))
+        return (None, None) + tuple(gws)
+
+
+def rotation_weight(weights, quaternion_format=False, transpose_out=False):
+    return _RotationWeight.apply(bool(quaternion_format), bool(transpose_out), *weights)
+
+
+def _real_prec(prec, stride, channels):
+    prec = _PRECISION if prec is None else prec
+    if prec == PREC_BF16 and not (_ROTATION_BF16 and _pair(stride) == (1, 1) and max(channels) <= 256 and min(channels) >= 8):
+        prec = PREC_FP32
+    return prec
+
+
+def quaternion_conv_rotation(x, weights, bias, stride, padding, groups, dilation, quaternion_format, prec=None):
+    """quaternion_ops.py:174-232: a real convolution with the rotation weight of (r, i, j, k)."""
+    if groups != 1:
+        raise NotImplementedError("seldq: groups != 1 is not implemented")
+    w = rotation_weight(weights, quaternion_format)
+    return block_conv(x, (w,), bias, stride, padding, dilation, ALG_REAL, _real_prec(prec, stride, w.shape[:2]))
+
+
+def quaternion_transpose_conv_rotation(x, weights, bias, stride, padding, output_padding, groups, dilation,
+                                       quaternion_format, prec=None):
+    """quaternion_ops.py:235-295 (stride 1, as functional.block_conv_transpose): the weights are (in, out, k...)."""
+    w = rotation_weight(weights, quaternion_format)
+    return block_conv_transpose(x, (w,), bias, stride, padding, output_padding, groups, dilation, ALG_REAL,
+                                _real_prec(prec, stride, w.shape[:2]))
+
+
+def quaternion_linear_rotation(x, weights, bias=None, quaternion_format=False, prec=None):
+    """quaternion_ops.py:330-388: x @ R(r, i, j, k) (+ bias), R of shape (nc in, nc out).  Runs as a 1 x 1 real
+    convolution over the flattened rows, whose (out, in, 1) weight the rotation kernel writes directly."""
+    w = rotation_weight(tuple(t.unsqueeze(-1) for t in weights), quaternion_format, transpose_out=True)
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    y = block_conv(x2.t().contiguous().unsqueeze(0), (w,), bias, 1, 0, 1, ALG_REAL, _real_prec(prec, 1, w.shape[:2]))
+    return y[0].t().reshape(lead + (w.shape[0],))
+
+
+class _QPointwise(torch.autograd.Function):
+    """hamilton_product / q_normalize / quaternion_exp on (outer, 4, m) views (csrc/rotation.cu)."""
+
+    @staticmethod
+    def forward(ctx, op, a, b):
+        _require_cuda_f32(a, "input")
+        a = a.contiguous()
+        if b is not None:
+            _require_cuda_f32(b, "input")
+            if b.shape != a.shape:
+                raise RuntimeError("hamilton_product: operands must have the same shape, got %s and %s"
+                                   % (list(a.shape), list(b.shape)))
+            b = b.contiguous()
+        if a.dim() < 2 or a.shape[1] % 4:
+            raise RuntimeError("Quaternion Tensors must be divisible by 4. input.size()[1] = "
+                               + str(a.shape[1] if a.dim() > 1 else a.numel()))
+        outer = a.shape[0]
+        m = a.numel() // (4 * outer) if outer else 0
+        out = torch.empty_like(a)
+        if a.numel():
+            with torch.cuda.device(a.device):
+                _lib.check(_lib.lib().seldq_quaternion_pointwise(op, a.data_ptr(), _ptr(b), out.data_ptr(), outer, m,
+                                                                 _stream()))
+        ctx.op, ctx.outer, ctx.m = op, outer, m
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        L = _lib.lib()
+
+        def run(op, p, q):
+            out = torch.empty_like(a)
+            if a.numel():
+                with torch.cuda.device(a.device):
+                    _lib.check(L.seldq_quaternion_pointwise(op, p.data_ptr(), q.data_ptr(), out.data_ptr(), ctx.outer, ctx.m,
+                                                            _stream()))
+            return out
+
+        if ctx.op == _lib.QOP_HAMILTON:
+            ga = run(_lib.QOP_HAMILTON_CONJ_B, g, b) if ctx.needs_input_grad[1] else None
+            gb = run(_lib.QOP_HAMILTON_CONJ_A, a, g) if ctx.needs_input_grad[2] else None
+            return None, ga, gb
+        bwd = _lib.QOP_NORMALIZE_BWD if ctx.op == _lib.QOP_NORMALIZE else _lib.QOP_EXP_BWD
+        return None, run(bwd, a, g), None
+
+
+def hamilton_product(q0, q1):
+    """quaternion_ops.py:467-507 / dual_quaternion_ops.py:374-414: component slices and concatenation along dim 1
+    (2-d and >= 4-d inputs; the drop-in modules reject the 3-d inputs whose slices run along the last dimension)."""
+    return _QPointwise.apply(_lib.QOP_HAMILTON, q0, q1)
+
+
+def q_normalize(x):
+    """dual_quaternion_ops.py:206-223 with channel = 1."""
+    return _QPointwise.apply(_lib.QOP_NORMALIZE, x, None)
+
+
+def quaternion_exp(x):
+    """dual_quaternion_ops.py:227-246."""
+    return _QPointwise.apply(_lib.QOP_EXP, x, None)
 
 
 class _ActPool1d(torch.autograd.Function):

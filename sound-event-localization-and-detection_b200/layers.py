@@ -83,8 +83,9 @@ class _BlockConvBase(Module):
         return tuple(getattr(self, n) for n in self._names)
 
     def forward(self, input):
-        if self.rotation:
-            raise NotImplementedError("rotation convolutions are not used by the SELD models (SURVEY.md 2, row 1)")
+        if self.rotation:        # quaternion_layers.py:151-155
+            return F.quaternion_conv_rotation(input, self._weights(), self.bias, self.stride, self.padding, self.groups,
+                                              self.dilatation, self.quaternion_format)
         if self.groups != 1:
             raise NotImplementedError("seldq: groups != 1 is not implemented")
         return F.block_conv(input, self._weights(), self.bias, self.stride, self.padding, self.dilatation,
@@ -226,7 +227,7 @@ class QuaternionLinear(_BlockLinearBase):
 
 class QuaternionLinearAutograd(_BlockLinearBase):
     """quaternion_layers.py:174-225.  Same math as QuaternionLinear (quaternion_linear instead of the
-    custom Function); the rotation variant is not used by the SELD models."""
+    custom Function); rotation=True runs quaternion_linear_rotation (functional.py)."""
 
     def __init__(self, in_features, out_features, bias=True,
                  init_criterion='glorot', weight_init='quaternion',
@@ -237,8 +238,8 @@ class QuaternionLinearAutograd(_BlockLinearBase):
         self._setup(in_features, out_features, bias, init_criterion, weight_init, seed)
 
     def forward(self, input):
-        if self.rotation:
-            raise NotImplementedError("rotation linears are not used by the SELD models (SURVEY.md 2, row 1)")
+        if self.rotation:        # quaternion_layers.py:212-214
+            return F.quaternion_linear_rotation(input, self._weights(), self.bias, self.quaternion_format)
         return F.block_linear(input, self._weights(), self.bias, self._algebra)
 
 
@@ -258,7 +259,7 @@ class DualQuaternionLinear(_BlockLinearBase):
 class QuaternionTransposeConv(Module):
     """quaternion_layers.py:19-98 (never instantiated by model.py): same constructor, parameters
     (in / 4, out / 4, k...) and initialisation; forward = quaternion_transpose_conv on the convolution kernels
-    (functional.block_conv_transpose: stride 1; the rotation variant is not implemented)."""
+    (functional.block_conv_transpose: stride 1), or quaternion_transpose_conv_rotation with rotation=True."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride, dilatation=1, padding=0, output_padding=0, groups=1,
                  bias=True, init_criterion='glorot', weight_init='quaternion', seed=None, operation='convolution2d',
@@ -291,7 +292,9 @@ class QuaternionTransposeConv(Module):
             self.bias.data.zero_()
 
     def forward(self, input):
-        if self.rotation:
-            raise NotImplementedError("quaternion_transpose_conv_rotation is not implemented (SURVEY.md 8f N4)")
+        if self.rotation:        # quaternion_layers.py:75-80
+            return F.quaternion_transpose_conv_rotation(input, tuple(getattr(self, n) for n in _Q_NAMES), self.bias,
+                                                        self.stride, self.padding, self.output_padding, self.groups,
+                                                        self.dilatation, self.quaternion_format)
         return F.block_conv_transpose(input, tuple(getattr(self, n) for n in _Q_NAMES), self.bias, self.stride,
                                       self.padding, self.output_padding, self.groups, self.dilatation, ALG_Q)

@@ -8,6 +8,7 @@
 #include "../../sound-event-localization-and-detection_b200/csrc/conv_cl_plan.h"
 #include "../../sound-event-localization-and-detection_b200/csrc/conv_simt.cuh"
 #include "../../sound-event-localization-and-detection_b200/csrc/geom.h"
+#include "../../sound-event-localization-and-detection_b200/csrc/rotation.cuh"
 #include "../../sound-event-localization-and-detection_b200/csrc/stft.cuh"
 #include "../../sound-event-localization-and-detection_b200/csrc/stft_pair.cuh"
 
@@ -326,6 +327,25 @@ int emul_cl_linear(const seldq_linear_desc_t* d, int pass, const float* in, cons
   int rc = make_linear_geom(d, pass, &g);
   if (rc) return rc;
   return run_cl_fprop(g, in, w, out, n_sms, info);
+}
+
+// rotation weights and quaternion point-wise operators (csrc/rotation.cuh): the kernels' element functions, one call
+// per thread index
+int emul_rotation_weight(const float* const* w, long long d0, long long d1, long long taps, int qf, int tr, float* out) {
+  rot::RotGeom g{d0, d1, taps, qf ? 4 : 3, tr ? 1 : 0};
+  for (long long idx = 0; idx < d0 * d1 * taps; ++idx) rot::rot_fwd_element(g, idx, w[0], w[1], w[2], w[3], out);
+  return 0;
+}
+int emul_rotation_weight_bwd(const float* const* w, const float* gout, long long d0, long long d1, long long taps, int qf,
+                             int tr, float* const* gw) {
+  rot::RotGeom g{d0, d1, taps, qf ? 4 : 3, tr ? 1 : 0};
+  for (long long idx = 0; idx < d0 * d1 * taps; ++idx)
+    rot::rot_bwd_element(g, idx, w[0], w[1], w[2], w[3], gout, gw[0], gw[1], gw[2], gw[3]);
+  return 0;
+}
+int emul_qpointwise(int op, const float* a, const float* b, float* out, long long outer, long long m) {
+  for (long long idx = 0; idx < outer * m; ++idx) rot::qpointwise_element(op, a, b, out, idx, m);
+  return 0;
 }
 
 const char* emul_last_error() { return error_buffer(); }

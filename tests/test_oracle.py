@@ -164,3 +164,73 @@ def test_oracle_transposed_conv_matches_reference_fixture(name):
     ws = [d["w%d" % i].astype(np.float64) for i in range(4)]
     y = A.qconv_transpose(d["x"], ws, d["b"] if meta["bias"] else None, meta["padding"], meta["dilation"])
     assert A.rel_err(y, d["y"]) < 1e-12
+
+
+# ---- rotation variants, hamilton_product, q_normalize, quaternion_exp --------------------------------
+@pytest.mark.parametrize("name", golden_names("rot_conv") + golden_names("rot_convT") + golden_names("rot_linear"))
+def test_oracle_rotation_variants_match_reference_fixture(name):
+    """quaternion_conv_rotation / quaternion_transpose_conv_rotation / quaternion_linear_rotation
+    (quaternion_ops.py:174-232, :235-295, :330-388): outputs, input gradients and -- through the hand-derived gradient of
+    the rotation weight -- the compact weight gradients of the reference's autograd; the float32 weight to the last bit
+    or the one before it (torch's vectorised CPU square root is not correctly rounded, numpy's is)."""
+    meta, d = load_golden(name)
+    ws = [d["w%d" % i].astype(np.float64) for i in range(4)]
+    qf, kind = meta["quaternion_format"], meta["kind"]
+    b = d["b"] if meta["bias"] else None
+    W32 = A.rotation_weight(ws, qf, np.float32)
+    assert W32.dtype == np.float32
+    assert np.abs(W32.reshape(d["W32"].shape).astype(np.float64) - d["W32"]).max() <= 1.5e-7 * np.abs(d["W32"]).max()
+    if kind == "rot_conv":
+        y = A.qconv_rotation(d["x"], ws, b, meta["stride"], meta["padding"], meta["dilation"], qf)
+        gx, gws, gb = A.qconv_rotation_backward(d["x"], ws, d["gy"], meta["stride"], meta["padding"], meta["dilation"], qf)
+        assert A.rel_err(gx, d["gx"]) < 1e-12
+        for i in range(4):
+            assert A.rel_err(gws[i], d["gw%d" % i]) < 1e-12, i
+        if b is not None:
+            assert A.rel_err(gb, d["gb"]) < 1e-12
+    elif kind == "rot_convT":
+        y = A.qconv_transpose_rotation(d["x"], ws, b, meta["padding"], meta["dilation"], qf)
+    else:
+        y = A.qlinear_rotation(d["x"], ws, b, qf)
+        W = A.rotation_weight(ws, qf)
+        x2, g2 = d["x"].reshape(-1, W.shape[0]), d["gy"].reshape(-1, W.shape[1])
+        assert A.rel_err((g2 @ W.T).reshape(d["x"].shape), d["gx"]) < 1e-12
+        gws = A.rotation_weight_backward(ws, x2.T @ g2, qf)
+        for i in range(4):
+            assert A.rel_err(gws[i], d["gw%d" % i]) < 1e-12, i
+    assert A.rel_err(y, d["y"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", golden_names("qpointwise"))
+def test_oracle_quaternion_pointwise_operators_match_reference_fixture(name):
+    meta, d = load_golden(name)
+    assert A.rel_err(A.hamilton_product(d["a"], d["b"]), d["ham"]) < 1e-13
+    assert A.rel_err(A.q_normalize(d["a"]), d["norm"]) < 1e-13
+    assert A.rel_err(A.quaternion_exp(d["a"]), d["exp"]) < 1e-13
+    # the gradients of a Hamilton product are Hamilton products with a conjugate
+    conj = lambda q: np.concatenate([c if k == 0 else -c for k, c in enumerate(A._components(q))], axis=1)
+    assert A.rel_err(A.hamilton_product(d["g"], conj(d["b"])), d["ham_ga"]) < 1e-13
+    assert A.rel_err(A.hamilton_product(conj(d["a"]), d["g"]), d["ham_gb"]) < 1e-13
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree only exists in the build container")
+def test_oracle_rotation_variants_match_live_reference():
+    import torch
+    ns = ref_import.load()
+    rng = np.random.default_rng(8)
+    for qf in (False, True):
+        nc = 4 if qf else 3
+        ws = [0.5 * rng.standard_normal((3, 2, 3)) for _ in range(4)]
+        x = rng.standard_normal((2, nc * 2, 17))
+        b = rng.standard_normal(nc * 3)
+        tw = [torch.tensor(w) for w in ws]
+        yr = ns.q_ops.quaternion_conv_rotation(torch.tensor(x), *tw, torch.tensor(b), 1, 2, 1, 2, qf).numpy()
+        assert A.rel_err(A.qconv_rotation(x, ws, b, 1, 2, 2, qf), yr) < 1e-13
+        xt = rng.standard_normal((2, nc * 3, 17))
+        yr = ns.q_ops.quaternion_transpose_conv_rotation(torch.tensor(xt), *tw, None, 1, 1, 0, 1, 1, qf).numpy()
+        assert A.rel_err(A.qconv_transpose_rotation(xt, ws, None, 1, 1, qf), yr) < 1e-13
+        wl = [0.5 * rng.standard_normal((4, 3)) for _ in range(4)]
+        xl = rng.standard_normal((5, nc * 4))
+        yr = ns.q_ops.quaternion_linear_rotation(torch.tensor(xl), *[torch.tensor(w) for w in wl], None, qf).numpy()
+        assert A.rel_err(A.qlinear_rotation(xl, wl, None, qf), yr) < 1e-13
