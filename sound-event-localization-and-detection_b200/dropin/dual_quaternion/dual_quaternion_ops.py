@@ -65,6 +65,18 @@ def dual_quaternion_linear(input, r_weight, i_weight, j_weight, k_weight,
     return _F.block_linear(input, ws, bias, _ALG_DQ)
 
 
+class DualQuaternionLinearFunction(object):
+    """dual_quaternion_ops.py:248-372.  Its forward builds the weight matrix of dual_quaternion_linear; its backward takes
+    two output gradients for a single output and cannot run in the reference (nothing calls it).  Here: the same forward
+    on the same kernels, with dual_quaternion_linear's gradients."""
+
+    @staticmethod
+    def apply(input, r_weight, i_weight, j_weight, k_weight, r_weight_2, i_weight_2, j_weight_2, k_weight_2, bias=None):
+        check_input(input)
+        ws = (r_weight, i_weight, j_weight, k_weight, r_weight_2, i_weight_2, j_weight_2, k_weight_2)
+        return _F.block_linear(input, ws, bias, _ALG_DQ)
+
+
 def _dim1_quaternions(input, what):
     # get_r / get_i / get_j / get_k slice dimension 1 of 2-d and >= 4-d inputs (dual_quaternion_ops.py:34-85); for 3-d
     # inputs they slice the LAST dimension while the results are concatenated along dimension 1
