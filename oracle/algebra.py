@@ -183,20 +183,30 @@ def qconv_backward(x, weights, gy, stride=1, padding=0, dilation=1, algebra="Q")
     return gx, compact_grads(gW, algebra, O, I), gb
 
 
-def qconv_transpose(x, weights, bias=None, padding=0, dilation=1):
-    """quaternion_transpose_conv, stride 1 (quaternion_ops.py:149-172): F.conv_transpose of the expanded
-    (in, out, k...) weight, whose blocks follow the convolution's table -- i.e. the input gradient of the convolution
-    with the same compact tensors read as (out', in') = (in, out), evaluated at gy = x."""
+def _transpose_out_shape(in_sp, ks, stride, padding, dilation, output_padding):
+    nd = len(in_sp)
+    s, p, d, op = (v if nd == 2 else (v,) for v in (_pair(stride) if nd == 2 else stride, _pair(padding) if nd == 2 else padding,
+                                                    _pair(dilation) if nd == 2 else dilation,
+                                                    _pair(output_padding) if nd == 2 else output_padding))
+    return tuple((in_sp[a] - 1) * s[a] - 2 * p[a] + d[a] * (ks[a] - 1) + op[a] + 1 for a in range(nd))
+
+
+def conv_transpose_nd(x, W, bias=None, stride=1, padding=0, dilation=1, output_padding=0):
+    """F.conv_transpose1d / 2d of a dense (in, out, k...) weight: the input gradient of the convolution with that weight
+    read as (out', in') -- stride, padding and dilation the same -- evaluated at x; output_padding only picks the output
+    size among those the strided convolution maps onto x's."""
     x = np.asarray(x, np.float64)
     nd = x.ndim - 2
-    pad, dil = _pair(padding) if nd == 2 else (padding,), _pair(dilation) if nd == 2 else (dilation,)
-    ks = weights[0].shape[2:]
-    out_sp = tuple(x.shape[2 + i] + (ks[i] - 1) * dil[i] - 2 * pad[i] for i in range(nd))
-    dummy = np.zeros((x.shape[0], 4 * weights[0].shape[1]) + out_sp)
-    gx, _, _ = qconv_backward(dummy, weights, x, 1, padding, dilation, "Q")
-    if bias is not None:
-        gx = gx + np.asarray(bias, np.float64).reshape((1, -1) + (1,) * nd)
-    return gx
+    out_sp = _transpose_out_shape(x.shape[2:], W.shape[2:], stride, padding, dilation, output_padding)
+    gx, _, _ = conv_nd_backward(np.zeros((x.shape[0], W.shape[1]) + out_sp), np.asarray(W, np.float64), x, stride, padding,
+                                dilation)
+    return gx if bias is None else gx + np.asarray(bias, np.float64).reshape((1, -1) + (1,) * nd)
+
+
+def qconv_transpose(x, weights, bias=None, padding=0, dilation=1, stride=1, output_padding=0):
+    """quaternion_transpose_conv (quaternion_ops.py:149-172): F.conv_transpose of the expanded (in, out, k...) weight,
+    whose blocks follow the convolution's table."""
+    return conv_transpose_nd(x, expand_weight(weights, "Q"), bias, stride, padding, dilation, output_padding)
 
 
 def qlinear(x, weights, bias=None, algebra="Q"):
@@ -272,16 +282,11 @@ def qconv_rotation_backward(x, weights, gy, stride=1, padding=0, dilation=1, qua
     return gx, rotation_weight_backward(weights, gW, quaternion_format), gb
 
 
-def qconv_transpose_rotation(x, weights, bias=None, padding=0, dilation=1, quaternion_format=False):
-    """quaternion_transpose_conv_rotation, stride 1 (quaternion_ops.py:235-295): F.conv_transpose of the (in, out, k...)
-    rotation weight = the input gradient of the convolution with that weight read as (out', in'), evaluated at x."""
-    x = np.asarray(x, np.float64)
-    W = rotation_weight(weights, quaternion_format)
-    nd = x.ndim - 2
-    pad, dil = _pair(padding) if nd == 2 else (padding,), _pair(dilation) if nd == 2 else (dilation,)
-    out_sp = tuple(x.shape[2 + a] + (W.shape[2 + a] - 1) * dil[a] - 2 * pad[a] for a in range(nd))
-    gx, _, _ = conv_nd_backward(np.zeros((x.shape[0], W.shape[1]) + out_sp), W, x, 1, padding, dilation)
-    return gx if bias is None else gx + np.asarray(bias, np.float64).reshape((1, -1) + (1,) * nd)
+def qconv_transpose_rotation(x, weights, bias=None, padding=0, dilation=1, quaternion_format=False, stride=1,
+                             output_padding=0):
+    """quaternion_transpose_conv_rotation (quaternion_ops.py:235-295): F.conv_transpose of the (in, out, k...) rotation
+    weight."""
+    return conv_transpose_nd(x, rotation_weight(weights, quaternion_format), bias, stride, padding, dilation, output_padding)
 
 
 def qlinear_rotation(x, weights, bias=None, quaternion_format=False):

@@ -63,8 +63,8 @@ def conv_case(ns, name, algebra, ndim, N, I, O, spatial, k, stride, padding, dil
     print(name, tuple(x.shape), "->", tuple(y.shape))
 
 
-def convT_case(ns, name, ndim, N, I, O, spatial, k, padding, dilation, bias, seed):
-    """quaternion_transpose_conv (quaternion_ops.py:149-172), stride 1: weights are (in / 4, out / 4, k...)."""
+def convT_case(ns, name, ndim, N, I, O, spatial, k, padding, dilation, bias, seed, stride=1, output_padding=0):
+    """quaternion_transpose_conv (quaternion_ops.py:149-172): weights are (in / 4, out / 4, k...)."""
     rng = np.random.default_rng(seed)
     kshape = (k,) * ndim
     ws = [f32(rng.standard_normal((I, O) + kshape) * 0.2) for _ in range(4)]
@@ -73,7 +73,7 @@ def convT_case(ns, name, ndim, N, I, O, spatial, k, padding, dilation, bias, see
     tx = torch.tensor(x, requires_grad=True)
     tw = [torch.tensor(w, requires_grad=True) for w in ws]
     tb = torch.tensor(b, requires_grad=True) if bias else None
-    y = ns.q_ops.quaternion_transpose_conv(tx, *tw, tb, 1, padding, 0, 1, dilation)
+    y = ns.q_ops.quaternion_transpose_conv(tx, *tw, tb, stride, padding, output_padding, 1, dilation)
     gy = f32(rng.standard_normal(tuple(y.shape)))
     y.backward(torch.tensor(gy))
     d = dict(x=x, gy=gy, y=y.detach().numpy(), gx=tx.grad.numpy())
@@ -83,8 +83,8 @@ def convT_case(ns, name, ndim, N, I, O, spatial, k, padding, dilation, bias, see
     if bias:
         d["b"] = b
         d["gb"] = tb.grad.numpy()
-    meta = dict(kind="convT", algebra="Q", ndim=ndim, stride=1, padding=padding, dilation=dilation, bias=bool(bias),
-                seed=seed, source="quaternion_ops.py:149-172")
+    meta = dict(kind="convT", algebra="Q", ndim=ndim, stride=stride, padding=padding, dilation=dilation, bias=bool(bias),
+                output_padding=output_padding, seed=seed, source="quaternion_ops.py:149-172")
     _save(name, meta, d)
     print(name, tuple(x.shape), "->", tuple(y.shape))
 
@@ -132,7 +132,7 @@ def _rotation_weight32(ns, ws, qf):
     return G.reshape(nc * d0, nc, d1, taps).reshape(nc * d0, nc * d1, taps).numpy()
 
 
-def rotation_case(ns, name, kind, ndim, N, I, O, spatial, k, padding, dilation, bias, qf, seed, stride=1):
+def rotation_case(ns, name, kind, ndim, N, I, O, spatial, k, padding, dilation, bias, qf, seed, stride=1, output_padding=0):
     """quaternion_conv_rotation (quaternion_ops.py:174-232), quaternion_transpose_conv_rotation (:235-295) and
     quaternion_linear_rotation (:330-388).  kind: 'conv' | 'convT' | 'linear'; I, O = compact sizes; for 'linear'
     `spatial` holds the leading dimensions of the input."""
@@ -154,7 +154,7 @@ def rotation_case(ns, name, kind, ndim, N, I, O, spatial, k, padding, dilation, 
         y = ns.q_ops.quaternion_conv_rotation(tx, *tw, tb, stride, padding, 1, dilation, qf)
         src = "quaternion_ops.py:174-232"
     elif kind == "convT":
-        y = ns.q_ops.quaternion_transpose_conv_rotation(tx, *tw, tb, 1, padding, 0, 1, dilation, qf)
+        y = ns.q_ops.quaternion_transpose_conv_rotation(tx, *tw, tb, stride, padding, output_padding, 1, dilation, qf)
         src = "quaternion_ops.py:235-295"
     else:
         y = ns.q_ops.quaternion_linear_rotation(tx, *tw, tb, qf)
@@ -169,7 +169,7 @@ def rotation_case(ns, name, kind, ndim, N, I, O, spatial, k, padding, dilation, 
         d["b"] = b
         d["gb"] = tb.grad.numpy()
     meta = dict(kind="rot_" + kind, ndim=ndim, stride=stride, padding=padding, dilation=dilation, bias=bool(bias),
-                quaternion_format=bool(qf), seed=seed, source=src)
+                output_padding=output_padding, quaternion_format=bool(qf), seed=seed, source=src)
     _save(name, meta, d)
     print(name, tuple(x.shape), "->", tuple(y.shape))
 
@@ -198,6 +198,13 @@ def qpointwise_case(ns, name, shape, seed):
     print(name, shape)
 
 
+def strided_transpose_cases(ns):
+    """Transposed convolutions with stride > 1 and output_padding (fp32 kernels)."""
+    convT_case(ns, "convT1d_q_s2", 1, 2, 8, 4, (31,), 3, 1, 1, True, 60, stride=2, output_padding=1)
+    convT_case(ns, "convT2d_q_s2", 2, 1, 4, 8, (5, 19), 3, 1, 1, False, 61, stride=2, output_padding=0)
+    rotation_case(ns, "rot_convT1d_s3", "convT", 1, 2, 4, 3, (17,), 3, 0, 2, True, True, 62, stride=3, output_padding=2)
+
+
 def n4_cases(ns):
     """Round 2, SURVEY.md 8f N4: the operators of quaternion_ops.py / dual_quaternion_ops.py the SELD models never
     call."""
@@ -208,8 +215,12 @@ def n4_cases(ns):
     rotation_case(ns, "rot_convT2d_3c", "convT", 2, 1, 3, 5, (5, 33), 3, 1, 1, False, False, 55)
     rotation_case(ns, "rot_linear_qf", "linear", 0, 0, 6, 5, (9,), 0, 0, 0, True, True, 56)
     rotation_case(ns, "rot_linear_3c", "linear", 0, 0, 8, 8, (4, 7), 0, 0, 0, False, False, 57)
+    if "--strided-only" in sys.argv:
+        strided_transpose_cases(ns)
+        return
     qpointwise_case(ns, "qpointwise_2d", (7, 20), 58)
     qpointwise_case(ns, "qpointwise_4d", (2, 12, 5, 9), 59)
+    strided_transpose_cases(ns)
 
 
 def stft_case(ns, name, C, n, nperseg, noverlap, phase, seed):

@@ -88,7 +88,7 @@ class QuaternionLinearFunction(object):
 
 def quaternion_transpose_conv(input, r_weight, i_weight, j_weight, k_weight, bias, stride, padding, output_padding, groups,
                               dilatation):
-    """quaternion_ops.py:149-172 on the convolution kernels (stride 1, groups 1; functional.block_conv_transpose)."""
+    """quaternion_ops.py:149-172 on the convolution kernels (groups 1; functional.block_conv_transpose)."""
     return _F.block_conv_transpose(input, (r_weight, i_weight, j_weight, k_weight), bias, stride, padding, output_padding,
                                    groups, dilatation, _ALG_Q)
 
@@ -102,7 +102,7 @@ def quaternion_conv_rotation(input, r_weight, i_weight, j_weight, k_weight, bias
 
 def quaternion_transpose_conv_rotation(input, r_weight, i_weight, j_weight, k_weight, bias, stride,
                                        padding, output_padding, groups, dilatation, quaternion_format):
-    """quaternion_ops.py:235-295 (stride 1, groups 1)."""
+    """quaternion_ops.py:235-295 (groups 1)."""
     return _F.quaternion_transpose_conv_rotation(input, (r_weight, i_weight, j_weight, k_weight), bias, stride, padding,
                                                  output_padding, groups, dilatation, quaternion_format)
 

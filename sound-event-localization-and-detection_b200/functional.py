@@ -429,14 +429,15 @@ class _BlockConv(torch.autograd.Function):
 
 
 class _BlockConvTranspose(torch.autograd.Function):
-    """y = conv_transpose(x, expand(weights)) + bias for stride 1 (quaternion_ops.py:149-172).
+    """y = conv_transpose(x, expand(weights)) + bias (quaternion_ops.py:149-172).
     The expanded (in, out, k...) weight of the transposed convolution has the block table of the convolution's, so
-    the operator IS the input-gradient pass of the convolution whose compact weights are these same tensors read as
-    (out', in') = (in, out): forward = seldq_conv_dgrad, gradient w.r.t. x = seldq_conv_fwd, weight gradient =
-    seldq_conv_wgrad with the roles of the two activations swapped.  No new kernel."""
+    the operator IS the input-gradient pass of the convolution -- same stride, padding, dilation -- whose compact weights
+    are these same tensors read as (out', in') = (in, out): forward = seldq_conv_dgrad, gradient w.r.t. x =
+    seldq_conv_fwd, weight gradient = seldq_conv_wgrad with the roles of the two activations swapped.  No new kernel.
+    output_padding only picks the output size among those the strided convolution maps onto x's."""
 
     @staticmethod
-    def forward(ctx, x, bias, padding, dilation, algebra, prec, *weights):
+    def forward(ctx, x, bias, stride, padding, output_padding, dilation, algebra, prec, *weights):
         import ctypes
         L = _lib.lib()
         nc = _NCOMP[algebra]
@@ -452,15 +453,25 @@ class _BlockConvTranspose(torch.autograd.Function):
                                "but got %d channels instead" % (list(w0.shape), nc, list(x.shape), w0.shape[0] * nc, x.shape[1]))
         pad = (0, _pair(padding)[1]) if nd == 1 else _pair(padding)
         dil = (1, _pair(dilation)[1]) if nd == 1 else _pair(dilation)
+        std = (1, _pair(stride)[1]) if nd == 1 else _pair(stride)
+        opad = (0, _pair(output_padding)[1]) if nd == 1 else _pair(output_padding)
         ks = (1, w0.shape[2]) if nd == 1 else tuple(w0.shape[2:])
         cout = w0.shape[1] * nc
         in_sp = (1, x.shape[2]) if nd == 1 else tuple(x.shape[2:])
-        out_sp = tuple(in_sp[i] + (ks[i] - 1) * dil[i] - 2 * pad[i] for i in range(2))
+        if any(opad[i] >= max(std[i], dil[i]) for i in range(2) if opad[i]):
+            raise RuntimeError("output padding must be smaller than either stride or dilation, but got output_padding=%s, "
+                               "stride=%s, dilation=%s" % (list(opad[2 - nd:]), list(std[2 - nd:]), list(dil[2 - nd:])))
+        out_sp = tuple((in_sp[i] - 1) * std[i] + (ks[i] - 1) * dil[i] - 2 * pad[i] + opad[i] + 1 for i in range(2))
         if min(out_sp) < 1:
             raise RuntimeError("transposed convolution: output size is too small")
         # the convolution this operator is the input gradient of: (N, cout, out_sp) -> (N, cin, in_sp)
-        desc = _lib.ConvDesc(algebra, prec, nd, x.shape[0], cout, x.shape[1], out_sp[0], out_sp[1], ks[0], ks[1], 1, 1,
+        desc = _lib.ConvDesc(algebra, prec, nd, x.shape[0], cout, x.shape[1], out_sp[0], out_sp[1], ks[0], ks[1], std[0], std[1],
                              pad[0], pad[1], dil[0], dil[1])
+        oh, ow = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(L.seldq_conv_out_shape(ctypes.byref(desc), ctypes.byref(oh), ctypes.byref(ow)))
+        if (oh.value, ow.value) != tuple(in_sp):
+            raise RuntimeError("transposed convolution: inconsistent output_padding %s for stride %s"
+                               % (list(opad[2 - nd:]), list(std[2 - nd:])))
         y = torch.empty((x.shape[0], cout) + (out_sp[1:] if nd == 1 else out_sp), dtype=torch.float32, device=x.device)
         wp = _lib.ptr_array([w.data_ptr() for w in weights])
         with torch.cuda.device(x.device):
@@ -492,7 +503,7 @@ class _BlockConvTranspose(torch.autograd.Function):
                                    device=gy.device)
                 _lib.check(L.seldq_conv_fwd(ctypes.byref(desc), gy.data_ptr(), None, wp, None, None, gx.data_ptr(),
                                             work.data_ptr(), work.numel(), _stream()))
-            if any(ctx.needs_input_grad[6:]):
+            if any(ctx.needs_input_grad[8:]):
                 gws = [torch.empty_like(w) for w in weights]
                 gp = _lib.ptr_array([g.data_ptr() for g in gws])
                 work = torch.empty(max(1, L.seldq_conv_workspace_bytes(ctypes.byref(desc), PASS_WGRAD)), dtype=torch.uint8,
@@ -502,22 +513,22 @@ class _BlockConvTranspose(torch.autograd.Function):
                                               work.data_ptr(), work.numel(), _stream()))
             if ctx.has_bias and ctx.needs_input_grad[1]:
                 gb = gy.sum(dim=[0] + list(range(2, gy.dim())))
-        return (gx, gb, None, None, None, None) + tuple(gws)
+        return (gx, gb, None, None, None, None, None, None) + tuple(gws)
 
 
 def block_conv_transpose(x, weights, bias, stride, padding, output_padding, groups, dilation, algebra, prec=None):
-    """quaternion_transpose_conv (quaternion_ops.py:149-172) on the convolution kernels: stride 1, groups 1."""
+    """quaternion_transpose_conv (quaternion_ops.py:149-172) on the convolution kernels: groups 1; stride 1 on either
+    path, stride > 1 on the fp32 kernels (the tensor-core path implements stride 1)."""
     if x.dim() not in (3, 4):
         if x.dim() == 5:
             raise NotImplementedError("seldq: 3-d transposed convolution (5-d input) is not implemented")
         raise Exception("The convolutional input is either 3, 4 or 5 dimensions. input.dim = " + str(x.dim()))
-    if _pair(stride) != (1, 1) or _pair(output_padding) != (0, 0) or groups != 1:
-        raise NotImplementedError("seldq: transposed convolution is implemented for stride 1, output_padding 0, groups 1")
+    if groups != 1:
+        raise NotImplementedError("seldq: groups != 1 is not implemented")
     prec = _PRECISION if prec is None else prec
-    nc = _NCOMP[algebra]
-    if prec == PREC_BF16 and min(weights[0].shape[0], weights[0].shape[1]) < 8:
+    if prec == PREC_BF16 and (min(weights[0].shape[0], weights[0].shape[1]) < 8 or _pair(stride) != (1, 1)):
         prec = PREC_FP32          # narrow layers: the tensor-core path's dense mode serves forward convolutions only
-    return _BlockConvTranspose.apply(x, bias, padding, dilation, algebra, prec, *weights)
+    return _BlockConvTranspose.apply(x, bias, stride, padding, output_padding, dilation, algebra, prec, *weights)
 
 
 class _BlockLinear(torch.autograd.Function):
@@ -701,7 +712,8 @@ def quaternion_conv_rotation(x, weights, bias, stride, padding, groups, dilation
 
 def quaternion_transpose_conv_rotation(x, weights, bias, stride, padding, output_padding, groups, dilation,
                                        quaternion_format, prec=None):
-    """quaternion_ops.py:235-295 (stride 1, as functional.block_conv_transpose): the weights are (in, out, k...)."""
+    """quaternion_ops.py:235-295: a real transposed convolution (functional.block_conv_transpose) with the rotation weight
+    of the (in, out, k...) tensors."""
     w = rotation_weight(weights, quaternion_format)
     return block_conv_transpose(x, (w,), bias, stride, padding, output_padding, groups, dilation, ALG_REAL,
                                 _real_prec(prec, stride, w.shape[:2]))

@@ -259,7 +259,7 @@ class DualQuaternionLinear(_BlockLinearBase):
 class QuaternionTransposeConv(Module):
     """quaternion_layers.py:19-98 (never instantiated by model.py): same constructor, parameters
     (in / 4, out / 4, k...) and initialisation; forward = quaternion_transpose_conv on the convolution kernels
-    (functional.block_conv_transpose: stride 1), or quaternion_transpose_conv_rotation with rotation=True."""
+    (functional.block_conv_transpose), or quaternion_transpose_conv_rotation with rotation=True."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride, dilatation=1, padding=0, output_padding=0, groups=1,
                  bias=True, init_criterion='glorot', weight_init='quaternion', seed=None, operation='convolution2d',

@@ -45,7 +45,8 @@ def _run_rotation(seldq, meta, d, prec):
     if kind == "rot_conv":
         y = F.quaternion_conv_rotation(x, ws, b, meta["stride"], meta["padding"], 1, meta["dilation"], qf, prec=prec)
     elif kind == "rot_convT":
-        y = F.quaternion_transpose_conv_rotation(x, ws, b, 1, meta["padding"], 0, 1, meta["dilation"], qf, prec=prec)
+        y = F.quaternion_transpose_conv_rotation(x, ws, b, meta["stride"], meta["padding"], meta.get("output_padding", 0), 1,
+                                                 meta["dilation"], qf, prec=prec)
     else:
         y = F.quaternion_linear_rotation(x, ws, b, qf, prec=prec)
     y.backward(cuda(d["gy"]))

@@ -485,7 +485,7 @@ def test_emulated_rotation_variants_match_golden(emul, name):
             xin, gout = gy, x
             yshape = d["y"].shape
             desc = ConvDesc(ALG["R"], 0, meta["ndim"], yshape[0], yshape[1], W.shape[0], 1 if one_d else yshape[2],
-                            yshape[-1], 1 if one_d else W.shape[2], W.shape[-1], 1, 1, 0 if one_d else p, p,
+                            yshape[-1], 1 if one_d else W.shape[2], W.shape[-1], 1 if one_d else s, s, 0 if one_d else p, p,
                             1 if one_d else dl, dl)
     fwd_in, fwd_ref = (xin, d["y"]) if kind != "rot_convT" else (gout, d["y"])
     bwd_in, bwd_ref = (gout, d["gx"]) if kind != "rot_convT" else (xin, d["gx"])
@@ -549,3 +549,32 @@ def test_emulated_quaternion_pointwise_operators_match_golden(emul, name):
     assert A.rel_err(run(4, a, g), d["norm_g"]) < 1e-5
     assert A.rel_err(run(5, a, None), d["exp"]) < 1e-6
     assert A.rel_err(run(6, a, g), d["exp_g"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", golden_names("convT"))
+def test_emulated_transposed_conv_is_the_input_gradient_pass(emul, name):
+    """quaternion_transpose_conv (quaternion_ops.py:149-172) as functional.block_conv_transpose runs it: the input-gradient
+    pass of the convolution (N, cout, out) -> (N, cin, in) with the same stride / padding / dilation on the compact
+    tensors read as (out', in'); its own gradients are that convolution's forward and weight-gradient passes with the
+    two activations swapped.  Includes stride > 1 with output_padding (fp32 kernels)."""
+    meta, d = load_golden(name)
+    ws = [np.ascontiguousarray(d["w%d" % i], np.float32) for i in range(4)]
+    x = np.ascontiguousarray(d["x"], np.float32)
+    gy = np.ascontiguousarray(d["gy"], np.float32)
+    one_d = meta["ndim"] == 1
+    s, p, dl = meta["stride"], meta["padding"], meta["dilation"]
+    ys = d["y"].shape
+    desc = ConvDesc(ALG["Q"], 0, meta["ndim"], ys[0], ys[1], x.shape[1], 1 if one_d else ys[2], ys[-1],
+                    1 if one_d else ws[0].shape[2], ws[0].shape[-1], 1 if one_d else s, s, 0 if one_d else p, p,
+                    1 if one_d else dl, dl)
+    bias = d["b"].reshape((1, -1) + (1,) * (x.ndim - 2)) if meta["bias"] else 0.0
+    y = np.full(ys, np.nan, np.float32)
+    assert emul.emul_conv(ctypes.byref(desc), 1, fptr(x), ptr_array(ws), None, fptr(y)) == 0, emul.emul_last_error()
+    assert A.rel_err(y + bias, d["y"]) < 1e-5
+    gx = np.full(x.shape, np.nan, np.float32)
+    assert emul.emul_conv(ctypes.byref(desc), 0, fptr(gy), ptr_array(ws), None, fptr(gx)) == 0, emul.emul_last_error()
+    assert A.rel_err(gx, d["gx"]) < 1e-5
+    gws = [np.zeros_like(w) for w in ws]
+    assert emul.emul_conv_wgrad(ctypes.byref(desc), fptr(gy), fptr(x), ptr_array(gws), 3) == 0, emul.emul_last_error()
+    for i in range(4):
+        assert A.rel_err(gws[i], d["gw%d" % i]) < 1e-5, i

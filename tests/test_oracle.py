@@ -157,12 +157,13 @@ def test_seld_metric_restatement_matches_golden_scores(name):
     assert got == tuple(float(v) for v in d["seld_scores"])
 
 
-@pytest.mark.parametrize("name", ["convT1d_q_k3_d2", "convT2d_q_3x3", "convT1d_q_small"])
+@pytest.mark.parametrize("name", golden_names("convT"))
 def test_oracle_transposed_conv_matches_reference_fixture(name):
     """quaternion_transpose_conv (quaternion_ops.py:149-172) = the convolution's input-gradient pass."""
     meta, d = load_golden(name)
     ws = [d["w%d" % i].astype(np.float64) for i in range(4)]
-    y = A.qconv_transpose(d["x"], ws, d["b"] if meta["bias"] else None, meta["padding"], meta["dilation"])
+    y = A.qconv_transpose(d["x"], ws, d["b"] if meta["bias"] else None, meta["padding"], meta["dilation"], meta["stride"],
+                          meta.get("output_padding", 0))
     assert A.rel_err(y, d["y"]) < 1e-12
 
 
@@ -189,7 +190,8 @@ def test_oracle_rotation_variants_match_reference_fixture(name):
         if b is not None:
             assert A.rel_err(gb, d["gb"]) < 1e-12
     elif kind == "rot_convT":
-        y = A.qconv_transpose_rotation(d["x"], ws, b, meta["padding"], meta["dilation"], qf)
+        y = A.qconv_transpose_rotation(d["x"], ws, b, meta["padding"], meta["dilation"], qf, meta["stride"],
+                                       meta.get("output_padding", 0))
     else:
         y = A.qlinear_rotation(d["x"], ws, b, qf)
         W = A.rotation_weight(ws, qf)
