@@ -189,7 +189,8 @@ def test_model_fp32_matches_reference_fixture(seldq, name):
     """Whole model through the fp32 kernels.  Forward: rel 1e-4 against the float64 reference.
     Gradients: this network's gradients are ill-conditioned -- the reference's OWN float32 run
     differs from its float64 run by up to 1.4e-2 on some tensors (fixture key ref32err/*, SURVEY.md
-    8c) -- so each tensor is gated at max(5e-4, 4 x the reference's float32 error on that tensor)."""
+    8c) -- so each tensor is gated at max(5e-4, 2 x the reference's float32 error on that tensor), the yardstick SURVEY.md 8c
+    sets (worst error / gate over the fixtures: 0.77, profiles/r2end_parity_margin_fp32.txt)."""
     meta, d, sed, doa, loss, grads = _run_model(seldq, name, "fp32")
     assert A.rel_err(sed, d["sed"]) < 1e-4
     assert A.rel_err(doa, d["doa"]) < 1e-4
@@ -199,7 +200,7 @@ def test_model_fp32_matches_reference_fixture(seldq, name):
     floor = 2e-3 if meta["cfg"]["domain"] == "R" else 5e-4
     bad = {}
     for k, g in grads.items():
-        e, tol = A.rel_err(g, d["grad/" + k]), max(floor, 4.0 * float(d["ref32err/" + k]))
+        e, tol = A.rel_err(g, d["grad/" + k]), max(floor, 2.0 * float(d["ref32err/" + k]))
         if not e < tol:
             bad[k] = (e, tol)
     assert not bad, (name, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8])
@@ -623,7 +624,7 @@ def test_full_size_model_matches_reference_fixture(seldq, prec):
     print("full size %s: sed %.2e doa %.2e loss %.6f vs %.6f" % (prec, e_sed, e_doa, loss.item(), float(d["loss"])))
     assert e_sed < tol and e_doa < tol
     assert abs(loss.item() - float(d["loss"])) < tol * max(1.0, abs(float(d["loss"])))
-    bad, n = {}, 0
+    bad, n, worst2 = {}, 0, (0.0, "")
     for i, (k, p) in enumerate(m.named_parameters()):
         if ("gsample/" + k) not in d:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
@@ -637,6 +638,10 @@ def test_full_size_model_matches_reference_fixture(seldq, prec):
         e_n = abs(float(np.linalg.norm(g)) - float(d["gnorm/" + k])) / max(float(d["gnorm/" + k]), 1e-300)
         if not (e_s < gate and e_n < max(gate, 2e-2 if prec == "bf16" else 1e-3)):
             bad[k] = (e_s, e_n, gate)
+        if prec == "fp32":
+            worst2 = max(worst2, (e_s / max(5e-4, 2.0 * float(d["ref32err/" + k])), k))
+    if prec == "fp32":
+        print("full size fp32: worst gradient-sample error / max(5e-4, 2 x ref32err) = %.2f (%s)" % worst2)
     assert n == meta["n_grads"]
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1][0])[:8]
 

@@ -35,3 +35,19 @@ for name in T.MODEL_FIXTURES:
         if worst:
             print("%-24s fused=%-5s worst error/gate per run: %s  (%s)" % (
                 name, fused, " ".join("%.2f" % r for r, _ in worst), max(worst)[1]), flush=True)
+
+# fp32 mode (test_model_fp32_matches_reference_fixture): worst error / gate with the gate at max(floor, F x the
+# reference's own float32 error) for F = 2 and F = 4
+for name in T.MODEL_FIXTURES:
+    rows = []
+    for _ in range(min(runs, 3)):
+        meta, d, sed, doa, loss, grads = T._run_model(seldq, name, "fp32")
+        floor = 2e-3 if meta["cfg"]["domain"] == "R" else 5e-4
+        w2 = w4 = (0.0, "")
+        for k, g in grads.items():
+            e, r32 = A.rel_err(g, d["grad/" + k]), float(d["ref32err/" + k])
+            w2 = max(w2, (e / max(floor, 2.0 * r32), k))
+            w4 = max(w4, (e / max(floor, 4.0 * r32), k))
+        rows.append((w2, w4))
+    print("%-24s fp32 worst error/gate per run, gate 2x: %s  gate 4x: %s  (%s)" % (
+        name, " ".join("%.2f" % a[0] for a, _ in rows), " ".join("%.2f" % b[0] for _, b in rows), max(rows)[0][1]), flush=True)
