@@ -598,7 +598,8 @@ def test_full_size_model_matches_reference_fixture(seldq, prec):
     in float64 on CPU (oracle/make_golden.py --full-size): sed, doa, loss and, per parameter, the gradient's L2 norm
     and a fixed 4096-element sample.  Input, target and initial weights regenerate from the seeds and are pinned by
     the fixture's check sums.  fp32 mode: outputs 1e-4; gradient samples within max(5e-4, 4 x the reference's own
-    float32 error on that tensor).  bf16 mode (the fused path of the bench): outputs 2e-2; gradient samples within
+    float32 error on that tensor) -- measured worst: 0.79 of that gate (1.58 x the 2 x yardstick the reduced-size fixtures
+    meet; this 110-layer-deep gradient at T = 4800 is where float32 accumulation order shows most).  bf16 mode (the fused path of the bench): outputs 2e-2; gradient samples within
     max(2e-2, 2 x the error of the ideal bf16-operand emulation on that tensor); gradient norms within the same."""
     from oracle import make_golden as MG
     meta, d = load_golden("model_dq_8ch_full")
