@@ -6,6 +6,8 @@ import sys as _sys
 _sys.path.append(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 from _seldq_pkg import pkg as _pkg  # noqa: E402
 
+import torch  # noqa: E402
+
 _F = _pkg.functional
 _I = _pkg.init
 _ALG_DQ = _pkg._lib.ALG_DQ
@@ -43,6 +45,21 @@ def get_j(input):
 
 def get_k(input):
     return _component(input, 3)
+
+
+def get_modulus(input, vector_form=False):
+    # dual_quaternion_ops.py:88-97
+    r, i, j, k = get_r(input), get_i(input), get_j(input), get_k(input)
+    sq = r * r + i * i + j * j + k * k
+    return torch.sqrt(sq) if vector_form else torch.sqrt(sq.sum(dim=0))
+
+
+def get_normalized(input, eps=0.0001):
+    # dual_quaternion_ops.py:100-107 (2-d and 3-d inputs, as there)
+    check_input(input)
+    m = get_modulus(input)
+    rep = m.repeat(1, 4) if input.dim() == 2 else m.repeat(1, 1, 4)
+    return input / (rep.expand_as(input) + eps)
 
 
 def dual_quaternion_conv(input, r_weight, i_weight, j_weight, k_weight,
@@ -108,6 +125,8 @@ def hamilton_product(q0, q1):
 
 quaternion_init = _I.dual_quaternion_init
 get_kernel_and_weight_shape = _I.get_kernel_and_weight_shape
+get_kernel_and_weight_shape_dual = _I.get_kernel_and_weight_shape      # dual_quaternion_ops.py:671-703: the same shapes
+create_dropout_mask = _I.create_dropout_mask
 
 
 def unitary_init(in_features, out_features, rng, kernel_size=None, criterion='he'):

@@ -126,6 +126,7 @@ unitary_init = _I.unitary_init
 random_init = _I.random_init
 quaternion_init = _I.quaternion_init
 get_kernel_and_weight_shape = _I.get_kernel_and_weight_shape
+create_dropout_mask = _I.create_dropout_mask
 
 
 def affect_init(r_weight, i_weight, j_weight, k_weight, init_func, rng, init_criterion):

@@ -159,3 +159,12 @@ def get_kernel_and_weight_shape(operation, in_channels, out_channels, kernel_siz
                              % (dims, dims, str(kernel_size)))
         ks = kernel_size
     return ks, (out_channels, in_channels) + tuple(ks)
+
+
+def create_dropout_mask(dropout_p, size, rng, as_type, operation='linear'):
+    """quaternion_ops.py:648-653 / dual_quaternion_ops.py:555-561: a Bernoulli(1 - p) keep mask drawn from the numpy
+    RandomState `rng`, as a tensor of type `as_type`."""
+    if operation != 'linear':
+        raise Exception("create_dropout_mask accepts only 'linear'. Found operation = " + str(operation))
+    import torch
+    return torch.from_numpy(rng.binomial(n=1, p=1 - dropout_p, size=size)).type(as_type)

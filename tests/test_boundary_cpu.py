@@ -184,3 +184,82 @@ def test_trainer_keeps_parameters_and_gradients_in_flat_buffers(seldq):
     m(torch.ones(5, 4)).sum().backward()
     tr.optimizer.step()
     assert all(not torch.equal(p.detach(), b) for p, b in zip(m.parameters(), before))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/quaternion"), reason="reference tree only exists in the build container")
+def test_dropin_modules_define_every_public_name_of_the_reference_modules():
+    """A user of the reference who switches sys.path to the drop-in finds every function and class the four hot-path
+    modules define (quaternion_ops / quaternion_layers / dual_quaternion_ops / dual_quaternion_layers)."""
+    import ast
+
+    def defs(path):
+        return {n.name for n in ast.parse(open(path).read()).body if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
+
+    def names(path):
+        out = set()
+        for n in ast.parse(open(path).read()).body:
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+                out.add(n.name)
+            elif isinstance(n, ast.Assign):
+                out |= {t.id for t in n.targets if isinstance(t, ast.Name)}
+        return out
+
+    dropin = os.path.join(ROOT, PKG, "dropin")
+    for rel in ("quaternion/quaternion_ops.py", "quaternion/quaternion_layers.py", "dual_quaternion/dual_quaternion_ops.py",
+                "dual_quaternion/dual_quaternion_layers.py"):
+        have = names(os.path.join(dropin, rel))
+        if rel.endswith("_layers.py"):          # the layer modules star-import their ops module, as the reference's do
+            have |= names(os.path.join(dropin, rel.replace("_layers.py", "_ops.py")))
+        missing = defs(os.path.join("/root/reference", rel)) - have
+        assert not missing, (rel, sorted(missing))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/quaternion"), reason="reference tree only exists in the build container")
+def test_dropin_host_helpers_match_the_live_reference():
+    """The host-side helpers that are plain tensor code in the reference too (component getters, get_modulus,
+    get_normalized, create_dropout_mask, the depthwise-separable blocks), drop-in against reference, in a subprocess per
+    side (both trees use the same module names)."""
+    code = r'''
+import sys, json, numpy as np, torch
+from numpy.random import RandomState
+sys.path.insert(0, %r)
+if %r:
+    sys.path.insert(0, %r); import importlib; importlib.import_module(%r).install_dropin()
+from quaternion import quaternion_ops as q
+from dual_quaternion import dual_quaternion_ops as dq
+from dual_quaternion import dual_quaternion_layers as dql
+torch.manual_seed(0)
+x2, x3, x4 = torch.randn(5, 12), torch.randn(3, 5, 8), torch.randn(2, 8, 3, 4)
+out = {}
+out["q_mod"] = q.get_modulus(x2).tolist(); out["q_modv"] = q.get_modulus(x3, True).tolist()
+out["q_norm"] = q.get_normalized(x2).tolist(); out["q_norm3"] = q.get_normalized(x3).tolist()
+out["dq_mod"] = dq.get_modulus(x2).tolist(); out["dq_mod4"] = dq.get_modulus(x4, True).tolist()
+out["dq_norm"] = dq.get_normalized(x3).tolist()
+out["dq_k4"] = dq.get_k(x4).tolist(); out["q_j"] = q.get_j(x3).tolist()
+out["mask"] = q.create_dropout_mask(0.3, (4, 6), RandomState(3), torch.FloatTensor).tolist()
+out["dmask"] = np.asarray(dq.create_dropout_mask(0.5, (3, 3), RandomState(4), torch.FloatTensor)).tolist()
+out["shape"] = [list(map(str, dq.get_kernel_and_weight_shape_dual("convolution2d", 3, 5, 3))),
+                list(map(str, dq.get_kernel_and_weight_shape_dual("convolution1d", 3, 5, 2)))]
+torch.manual_seed(1)
+m = dql.DepthwiseSeparableConv1D(6, 10, 3, 1, 1)
+out["ds_keys"] = sorted(m.state_dict()); out["ds"] = m(torch.randn(2, 6, 9)).tolist()
+torch.manual_seed(2)
+m2 = dql.DepthwiseSeparableConv2D(4, 6, 3, 2, 1)
+out["ds2"] = m2(torch.randn(1, 4, 7, 8)).tolist()
+print("RESULT" + json.dumps(out))
+'''
+    import json
+
+    def run(dropin):
+        root = os.path.join(ROOT, PKG, "dropin") if dropin else "/root/reference"
+        src = code % (root, bool(dropin), ROOT, PKG)
+        out = subprocess.check_output([sys.executable, "-c", src], stderr=subprocess.STDOUT).decode()
+        return json.loads(out[out.index("RESULT") + 6:])
+
+    ours, ref = run(True), run(False)
+    assert sorted(ours) == sorted(ref)
+    for k in ref:
+        if isinstance(ref[k], list) and ref[k] and not isinstance(ref[k][0], str) and k not in ("shape", "ds_keys"):
+            assert np.allclose(np.asarray(ours[k], np.float64), np.asarray(ref[k], np.float64), rtol=1e-6, atol=1e-7), k
+        else:
+            assert ours[k] == ref[k], k
