@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libseldq.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
+ABI_VERSION = 5                                   # SELDQ_ABI_VERSION of include/seldq.h this binding was written against
 ALG_REAL, ALG_Q, ALG_DQ, ALG_DQ_LINEAR = 0, 1, 2, 3
 ALG_Q_LINEAR_IO, ALG_DQ_LINEAR_IO = 4, 5          # linear layers as 1x1 convolutions on their own (in, out) tensors
 PREC_FP32, PREC_BF16 = 0, 1
@@ -188,6 +189,9 @@ def lib():
             fn = getattr(h, name)
             fn.restype = res
             fn.argtypes = args
+        if h.seldq_abi_version() != ABI_VERSION:
+            raise RuntimeError("libseldq.so reports ABI version %d, this package binds version %d: rebuild it "
+                               "(csrc/build.sh)" % (h.seldq_abi_version(), ABI_VERSION))
         _lib = h
     return _lib
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(seldq):
     assert declared, "no declarations parsed"
     assert declared <= exported, sorted(declared - exported)
     lib = seldq._lib.lib()
-    assert lib.seldq_abi_version() == 5
+    assert lib.seldq_abi_version() == seldq._lib.ABI_VERSION == int(re.search(r"#define SELDQ_ABI_VERSION (\d+)", header).group(1))
     assert set(seldq._lib.exported_symbols()) <= exported
 
 
