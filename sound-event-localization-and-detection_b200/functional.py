@@ -639,8 +639,9 @@ def block_linear(x, weights, bias, algebra, prec=None):
 
 # ---- rotation variants and quaternion point-wise operators -------------------------------------------
 # The real-algebra contraction of the rotation variants follows the global precision where the tensor-core path serves
-# it (stride 1, 8 ... 256 channels on both sides: the kernels' dense mode, which builds the expanded bf16 tile from the
-# fp32 weight in its prologue) and runs the fp32 kernels otherwise; SELDQ_ROTATION_BF16=0: always the fp32 kernels.
+# it (_real_prec below: stride 1, 8 ... 256 channels on both sides -- the kernels' dense mode, which builds the expanded
+# bf16 tile from the fp32 weight in its prologue) and runs the fp32 kernels otherwise; SELDQ_ROTATION_BF16=0: always the
+# fp32 kernels.
 _ROTATION_BF16 = os.environ.get("SELDQ_ROTATION_BF16", "1") != "0"
 
 
@@ -696,9 +697,16 @@ def rotation_weight(weights, quaternion_format=False, transpose_out=False):
 
 
 def _real_prec(prec, stride, channels):
+    """Precision of a real-algebra contraction: bf16 only where all three tensor-core passes serve the layer -- stride 1,
+    8 ... 256 channels on both sides (forward / input gradient: dense mode, csrc/conv_cl_plan.h) and channel counts that
+    are both multiples of 8 or both at most 64 (weight gradient: csrc/wgrad_umma.cu) -- else the fp32 kernels."""
     prec = _PRECISION if prec is None else prec
-    if prec == PREC_BF16 and not (_ROTATION_BF16 and _pair(stride) == (1, 1) and max(channels) <= 256 and min(channels) >= 8):
-        prec = PREC_FP32
+    if prec == PREC_BF16:
+        lo, hi = min(channels), max(channels)
+        ok = (_ROTATION_BF16 and _pair(stride) == (1, 1) and 8 <= lo and hi <= 256
+              and (all(c % 8 == 0 for c in channels) or hi <= 64))
+        if not ok:
+            prec = PREC_FP32
     return prec
 
 

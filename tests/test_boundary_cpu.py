@@ -263,3 +263,17 @@ print("RESULT" + json.dumps(out))
             assert np.allclose(np.asarray(ours[k], np.float64), np.asarray(ref[k], np.float64), rtol=1e-6, atol=1e-7), k
         else:
             assert ours[k] == ref[k], k
+
+
+def test_real_algebra_precision_choice_stays_inside_what_the_tensor_core_kernels_serve(seldq):
+    """functional._real_prec (rotation variants): bf16 only for stride 1, 8 ... 256 channels on both sides, and channel
+    counts that are both multiples of 8 or both <= 64 (csrc/wgrad_umma.cu); everything else runs the fp32 kernels."""
+    F, L = seldq.functional, seldq._lib
+    bf16 = [(32, 32), (24, 12), (16, 32), (24, 24), (72, 72), (60, 20), (256, 8)]
+    fp32 = [(100, 40), (300, 8), (4, 4), (12, 4), (264, 264), (72, 12)]
+    for ch in bf16:
+        assert F._real_prec(L.PREC_BF16, 1, ch) == L.PREC_BF16, ch
+        assert F._real_prec(L.PREC_BF16, 2, ch) == L.PREC_FP32, ch
+        assert F._real_prec(L.PREC_FP32, 1, ch) == L.PREC_FP32, ch
+    for ch in fp32:
+        assert F._real_prec(L.PREC_BF16, 1, ch) == L.PREC_FP32, ch
