@@ -11,9 +11,24 @@ batches would in the reference.  Parameters that never receive a gradient (the u
 batch_gate1 of every ResBlock and the last block's conv2_residual) simply keep
 zeros in their slice.
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn.functional as tF
+
+# SELDQ_AR_SUM=1: exchange with ncclSum and scale by 1 / world afterwards instead of ncclAvg.  NCCL implements the average
+# as a pre-multiplied sum, which its in-switch reduction (NVLS) does not take for float32 (ncclNvlsSupported: ncclDevSum
+# only); the plain sum is eligible.  Not yet measured at 8 GPUs (DESIGN.md 9) -- the default stays the measured schedule.
+_AR_SUM = os.environ.get("SELDQ_AR_SUM", "0") != "0"
+
+
+def _nccl_mean_(t, group):
+    if _AR_SUM:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.mul_(1.0 / dist.get_world_size(group))
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)      # ncclAvg: no separate division pass
 
 
 def seld_loss(sed, doa, target, n_sed, sed_weight=1.0, doa_weight=5.0):
@@ -78,7 +93,7 @@ class FlatGradBucket(object):
     def all_reduce_mean(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             if self.flat.is_cuda:
-                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)      # ncclAvg: no separate division pass
+                _nccl_mean_(self.flat, group)
             else:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
                 self.flat.div_(dist.get_world_size(group))
@@ -92,13 +107,13 @@ class FlatGradBucket(object):
             return
         stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(stream):
-            dist.all_reduce(self.flat[self.n_late:], op=dist.ReduceOp.AVG, group=group)    # NCCL averages in the collective
+            _nccl_mean_(self.flat[self.n_late:], group)
 
     def all_reduce_rest_mean(self, group, stream):
         """Sum flat[:n_late], join `stream`, divide everything by the world size."""
         if stream is not None:
             if self.n_late:
-                dist.all_reduce(self.flat[:self.n_late], op=dist.ReduceOp.AVG, group=group)
+                _nccl_mean_(self.flat[:self.n_late], group)
             torch.cuda.current_stream().wait_stream(stream)
             return
         if self.n_late:
