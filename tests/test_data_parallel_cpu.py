@@ -122,3 +122,26 @@ def test_optimizer_state_in_the_reference_checkpoint_layout():
     tr3.step(xs[0], ts[0])
     for a, b in zip(m.parameters(), m3.parameters()):
         assert torch.allclose(a, b, rtol=1e-10, atol=1e-14)
+
+
+def _sum_exchange_main(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    trainer_mod = importlib.import_module(PKG + ".trainer")
+    trainer_mod._AR_SUM = True                   # SELDQ_AR_SUM=1: sum + scaling pass (gloo has no average either)
+    t = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    trainer_mod._nccl_mean_(t[2:], None)         # a slice of the bucket, as the two-part exchange passes it
+    torch.save(t, os.path.join(out_dir, "sum%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_sum_exchange_switch_averages_a_bucket_slice(tmp_path):
+    """trainer._nccl_mean_ with SELDQ_AR_SUM=1 (ncclSum + scaling instead of ncclAvg): in place on a view of the bucket,
+    mean over the ranks, the rest of the bucket untouched."""
+    world = 2
+    mp.spawn(_sum_exchange_main, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    base = torch.arange(10, dtype=torch.float32)
+    for r in range(world):
+        t = torch.load(os.path.join(str(tmp_path), "sum%d.pt" % r))
+        assert torch.equal(t[:2], base[:2] * (r + 1))
+        assert torch.allclose(t[2:], base[2:] * 1.5)
